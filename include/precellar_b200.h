@@ -1,0 +1,228 @@
+/*
+ * precellar_b200.h -- C ABI of the B200-native barcode hot path.
+ *
+ * This is the drop-in boundary for precellar's read-preprocessing hot path:
+ *     seqspec-driven segment extraction  ->  whitelist frequency count  ->
+ *     Phred-weighted 1-Hamming barcode correction
+ * implemented as hand-written sm_100a CUDA kernels.  Plain pointers and sizes only; no C++,
+ * CUDA or torch types cross this boundary.  There is NO CPU fallback behind these entry points:
+ * every compute call fails with PCL_ERR_CUDA when no usable device is present.
+ *
+ * What each entry point replaces in the reference (paths relative to the precellar repo):
+ *   pcl_layout_set          Assay::get_segments_by_modality -> Read::get_segments -> truncate_max
+ *                           (seqspec/src/lib.rs:416-440, seqspec/src/read.rs:182-212,
+ *                           seqspec/src/read/segment.rs:144-164): the per-read SegmentInfo tables,
+ *                           already derived by the host (precellar_b200/layout.py).
+ *   pcl_whitelist_load      Assay::get_whitelists + WhitelistBuilder::new
+ *                           (seqspec/src/lib.rs:443-472, precellar/src/barcode.rs:393-407)
+ *   pcl_chunk_* (inputs)    BatchedFqReader::next batches (precellar/src/align/fastq.rs:400-448)
+ *   pcl_count               BarcodeAnalyzer::new, hot loop A: split + WhitelistBuilder::add
+ *                           (precellar/src/barcode.rs:59-137,410-426; segment.rs:180-368)
+ *   pcl_counts_allreduce    (new) merges per-GPU counts; the reference is single-process
+ *   pcl_correct             FastqAnnotator::annotate + BarcodeAnalyzer::correct_barcode +
+ *                           OligoFrequncy::likelihood1, hot loop B
+ *                           (precellar/src/align/fastq.rs:474-525, precellar/src/barcode.rs:160-184,311-358)
+ *   pcl_chunk_fetch         the AnnotatedFastq fields a consumer reads
+ *                           (precellar/src/align/fastq.rs:528-556)
+ *   pcl_counts_fetch        Whitelist{barcode_counts, mismatch_count, total_count}
+ *                           (precellar/src/barcode.rs:362-366,431-437)
+ *   pcl_qc_fetch            QcFastq::num_reads / num_defect (precellar/src/qc.rs:21-27)
+ *
+ * Threading: one host thread drives one ctx (one GPU).  Calls on a ctx are not re-entrant.
+ * Different ctxs are independent.  Work on a chunk is stream-ordered on the chunk's stream;
+ * pcl_chunk_fetch / pcl_sync block.
+ *
+ * Errors: every function returns 0 or a negative pcl_status; pcl_last_error() gives the message.
+ * Nothing throws or aborts across this boundary.  Per-read structural failures are data
+ * (status bits in the results), not errors.
+ */
+#ifndef PRECELLAR_B200_H
+#define PRECELLAR_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PCL_ABI_VERSION 1
+
+#define PCL_MAX_READS 8          /* read files per read-group                     */
+#define PCL_MAX_ELEMS 16         /* SegmentInfo elements per read                 */
+#define PCL_MAX_ANCHOR 64        /* bytes of a Fixed (anchor) sequence            */
+#define PCL_MAX_REGIONS 8        /* barcode regions (whitelists) per modality     */
+#define PCL_MAX_BC_PER_READ 4    /* barcode elements per read                     */
+#define PCL_MAX_UMI_PER_READ 4   /* UMI elements per read                         */
+#define PCL_MAX_KEY_LEN 31       /* bases in one packed barcode / UMI key         */
+#define PCL_MAX_STRIDE 4096      /* bytes per record slot                         */
+
+typedef enum {
+    PCL_OK = 0,
+    PCL_ERR_ARG = -1,            /* bad argument / call order                              */
+    PCL_ERR_CUDA = -2,           /* CUDA runtime failure, or no device                     */
+    PCL_ERR_NCCL = -3,           /* NCCL failure / libnccl not loadable                    */
+    PCL_ERR_UNSUPPORTED = -4,    /* layout / whitelist outside what the kernels implement  */
+    PCL_ERR_INPUT = -5,          /* inconsistent input (the reference would panic/assert)  */
+    PCL_ERR_NOMEM = -6
+} pcl_status;
+
+/* Region classes the path distinguishes (seqspec/src/region.rs:342-376). */
+typedef enum { PCL_KIND_OTHER = 0, PCL_KIND_BARCODE = 1, PCL_KIND_UMI = 2, PCL_KIND_TARGET = 3 } pcl_kind;
+
+/* One SegmentInfoElem (seqspec/src/read/segment.rs:371-378). */
+typedef struct {
+    uint8_t kind;                /* pcl_kind                                                   */
+    uint8_t is_fixed_seq;        /* sequence_type == Fixed: acts as an anchor after a variable run */
+    uint16_t min_len;
+    uint16_t max_len;
+    int16_t region_slot;         /* barcode elements: index of the region's whitelist; else -1 */
+    uint8_t seq_len;             /* strlen(sequence) when is_fixed_seq                         */
+    uint8_t reserved[3];
+    char sequence[PCL_MAX_ANCHOR];
+} pcl_elem_desc;
+
+/* One sequenced read of the modality (seqspec/src/read.rs:56-66) with its derived SegmentInfo. */
+typedef struct {
+    uint16_t n_elems;
+    uint8_t is_reverse;          /* strand: neg                                                */
+    uint8_t reserved;
+    uint32_t max_len;            /* Read.max_len: records are truncated to it when > 0 (read.rs:98-103) */
+    pcl_elem_desc elems[PCL_MAX_ELEMS];
+} pcl_read_desc;
+
+/* ---- results ------------------------------------------------------------------------------
+ * fstatus (uint16, one per read file and record):
+ *   bits 1:0   split status: 0 ok, 1 AnchorNotFound, 2 PatternMismatch (record is a "defect",
+ *              precellar/src/align/fastq.rs:369-374), 3 more than one target segment (reference panics)
+ *   bit  2     target segment present (tcoord valid)
+ *   bit  3     reserved
+ *   bits 15:4  four 3-bit codes, one per barcode element of this read in element order:        */
+#define PCL_SPLIT_OK 0
+#define PCL_SPLIT_ANCHOR_NOT_FOUND 1
+#define PCL_SPLIT_PATTERN_MISMATCH 2
+#define PCL_SPLIT_MULTI_TARGET 3
+#define PCL_FSTATUS_TARGET 0x4
+#define PCL_BC_EXACT 0u          /* raw barcode is in the whitelist: corrected == raw (posterior 1.0)  */
+#define PCL_BC_ABSENT 3u         /* segment not produced by split (short read / defect)                */
+#define PCL_BC_NO_MATCH 4u       /* Err(NoMatch)          -- also the state between pcl_count and pcl_correct */
+#define PCL_BC_CORRECTED 5u      /* Ok(key) by one substitution, posterior >= threshold                */
+#define PCL_BC_LOW_CONF 6u       /* Err(LowConfidence)                                                 */
+#define PCL_BC_EXCEED_EE 7u      /* Err(ExceedExpectedError)                                           */
+#define PCL_BC_CODE(fstatus, j) (((fstatus) >> (4 + 3 * (j))) & 7u)
+/*
+ * Packed keys (barcodes and UMIs): 2 bits per base, A=0 C=1 G=2 T=3, first base most significant,
+ * and a marker bit above the first base: key = (1 << 2L) | bases, in the orientation the reference
+ * reports (reverse-complemented for neg-strand reads).  Keys are stored 4 bytes wide when the element
+ * is at most 15 bases long, or exactly 16 (min_len == max_len == 16), and 8 bytes wide otherwise
+ * (pcl_read_info.*_key_bytes); a 4-byte key of a 16-base element has its marker bit (bit 32) dropped.
+ *   bc_key   valid only for PCL_BC_EXACT (the raw key) and PCL_BC_CORRECTED (the whitelist key).
+ *   umi_key  0 = present but not packable (a byte outside ACGT, or longer than PCL_MAX_KEY_LEN;
+ *            16-base UMIs are stored 8 bytes wide so that 0 stays free); all-ones = segment absent.
+ *
+ * Coordinates: (start << 16) | len inside the (max_len-truncated) record; 0xFFFFFFFF = absent.
+ * For reads whose layout is all fixed-length (pcl_read_info.fixed_layout) barcode/UMI coordinates are
+ * static (pcl_read_info.static_start, element lengths) and bcoord/ucoord are not produced.
+ */
+#define PCL_KEY_ABSENT32 0xFFFFFFFFu
+#define PCL_KEY_ABSENT64 0xFFFFFFFFFFFFFFFFull
+#define PCL_COORD_ABSENT 0xFFFFFFFFu
+
+typedef struct {
+    uint8_t n_bc;                          /* barcode elements, in element order                      */
+    uint8_t n_umi;                         /* UMI elements                                            */
+    uint8_t has_target;
+    uint8_t fixed_layout;                  /* all elements fixed-length except an optional last one   */
+    uint8_t needs_payload;                 /* seq/qual bytes are read (else lengths only)             */
+    uint8_t reserved[3];
+    uint8_t bc_elem[PCL_MAX_BC_PER_READ];  /* element index of each barcode element                   */
+    uint8_t bc_key_bytes[PCL_MAX_BC_PER_READ];   /* 4 or 8                                            */
+    uint8_t umi_elem[PCL_MAX_UMI_PER_READ];      /* element index of each UMI element                 */
+    uint8_t umi_key_bytes[PCL_MAX_UMI_PER_READ]; /* 4 or 8                                            */
+    uint16_t static_start[PCL_MAX_ELEMS];  /* fixed_layout: start of every element                    */
+} pcl_read_info;
+
+/* Host-side views handed to pcl_chunk_fetch; any pointer may be NULL to skip that array.
+ * bc_key[j] / umi_key[j] point at n keys of the width given by pcl_read_info. */
+typedef struct {
+    uint16_t *fstatus;                     /* [n]                                              */
+    uint32_t *tcoord;                      /* [n]          if has_target                       */
+    void *bc_key[PCL_MAX_BC_PER_READ];     /* [n] each                                         */
+    void *umi_key[PCL_MAX_UMI_PER_READ];   /* [n] each                                         */
+    uint32_t *bcoord[PCL_MAX_BC_PER_READ]; /* [n] each     only when !fixed_layout             */
+    uint32_t *ucoord[PCL_MAX_UMI_PER_READ];/* [n] each     only when !fixed_layout             */
+} pcl_read_results;
+
+typedef struct pcl_ctx pcl_ctx;
+typedef struct pcl_chunk pcl_chunk;
+
+/* ---- context ---------------------------------------------------------------------------- */
+int pcl_abi_version(void);
+/* Message of the last failure on this ctx (ctx == NULL: last failure of pcl_ctx_create on this thread). */
+const char *pcl_last_error(const pcl_ctx *ctx);
+int pcl_device_count(void);                                     /* >= 0, or PCL_ERR_CUDA            */
+int pcl_ctx_create(pcl_ctx **out, int device);
+int pcl_ctx_destroy(pcl_ctx *ctx);
+int pcl_sync(pcl_ctx *ctx);                                     /* wait for all streams of the ctx  */
+
+/* Multi-GPU (one ctx per rank; ranks may be threads or processes).  uid is ncclUniqueId (128 bytes). */
+int pcl_comm_unique_id(void *uid128);
+int pcl_comm_init(pcl_ctx *ctx, int nranks, int rank, const void *uid128);
+
+/* ---- configuration ----------------------------------------------------------------------- */
+int pcl_layout_set(pcl_ctx *ctx, const pcl_read_desc *reads, int n_reads);
+int pcl_read_info_get(const pcl_ctx *ctx, int read_slot, pcl_read_info *out);
+/* Whitelist of one barcode region: n byte strings, string i = bytes[offsets[i] .. offsets[i+1]).
+ * File order; duplicates are dropped keeping the first (IndexSet semantics).  Entries must be
+ * upper-case ACGT of length 1..PCL_MAX_KEY_LEN, else PCL_ERR_UNSUPPORTED. */
+int pcl_whitelist_load(pcl_ctx *ctx, int region_slot, const uint8_t *bytes, const uint64_t *offsets, uint64_t n);
+uint64_t pcl_whitelist_size(const pcl_ctx *ctx, int region_slot);   /* after dedup */
+
+/* ---- chunks: one batch of read-groups, all read files of a group in the same chunk -------- */
+int pcl_chunk_create(pcl_ctx *ctx, uint64_t capacity_records, pcl_chunk **out);
+int pcl_chunk_destroy(pcl_chunk *chunk);
+/* Set the number of records of the next fill (<= capacity) and invalidate previous contents. */
+int pcl_chunk_reset(pcl_chunk *chunk, uint64_t n_records);
+/* Record slot size (multiple of 16) the ctx uses for this read's seq/qual planes. */
+uint32_t pcl_read_stride(const pcl_ctx *ctx, int read_slot);
+/* Asynchronous H2D of one read file's SoA planes: record i occupies [i*stride, i*stride+len[i]).
+ * seq/qual may be NULL when !needs_payload.  Host buffers should be pinned (pcl_host_alloc) and must
+ * stay valid until the next blocking call on the chunk. */
+int pcl_chunk_upload(pcl_chunk *chunk, int read_slot, const uint8_t *seq, const uint8_t *qual, const uint16_t *len);
+/* Zero-copy producers (a GPU-side decoder or generator) may fill the device planes directly. */
+int pcl_chunk_device_ptrs(pcl_chunk *chunk, int read_slot, void **seq, void **qual, void **len);
+void *pcl_chunk_stream(pcl_chunk *chunk);                        /* cudaStream_t of the chunk        */
+
+/* ---- the three stages --------------------------------------------------------------------- */
+int pcl_counts_reset(pcl_ctx *ctx);
+int pcl_count(pcl_ctx *ctx, pcl_chunk *chunk);                   /* pass 1 on this chunk (async)     */
+int pcl_counts_allreduce(pcl_ctx *ctx);                          /* sums counts over ranks; blocks until all chunks counted */
+int pcl_correct(pcl_ctx *ctx, pcl_chunk *chunk, double threshold, double max_expected_errors); /* pass 2 (async) */
+
+/* ---- outputs ------------------------------------------------------------------------------ */
+int pcl_chunk_fetch(pcl_chunk *chunk, int read_slot, const pcl_read_results *out);   /* D2H + wait */
+/* counts[i] for whitelist entry i (deduplicated file order); any pointer may be NULL. */
+int pcl_counts_fetch(pcl_ctx *ctx, int region_slot, uint64_t *counts, uint64_t *mismatch, uint64_t *total);
+/* per read file: num_reads, num_defect (2 * n_reads values) accumulated by pcl_count since the last reset */
+int pcl_qc_fetch(pcl_ctx *ctx, uint64_t *per_read);
+/* Unpack a key into ASCII (host utility): returns the length or -1. */
+int pcl_key_decode(uint64_t key, char *out32);
+
+/* ---- pinned host memory ------------------------------------------------------------------- */
+void *pcl_host_alloc(uint64_t bytes);
+void pcl_host_free(void *p);
+
+/* ---- instrumentation (used by bench.py; CUDA events on the launching stream) --------------- */
+enum { PCL_K_COUNT = 0, PCL_K_CORRECT = 1, PCL_K_MAX = 4 };
+int pcl_profile_enable(pcl_ctx *ctx, int on);                    /* bracket every kernel with events */
+/* accumulated ms and launches of kernel k since the last pcl_profile_reset (syncs the ctx) */
+int pcl_profile_get(pcl_ctx *ctx, int k, double *ms, uint64_t *launches);
+int pcl_profile_reset(pcl_ctx *ctx);
+uint64_t pcl_launch_count(const pcl_ctx *ctx);                   /* kernels launched by this ctx     */
+/* cudaEvent-based stopwatch on a chunk's stream */
+int pcl_timer_start(pcl_chunk *chunk);
+int pcl_timer_stop_ms(pcl_chunk *chunk, double *ms);             /* blocks                           */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PRECELLAR_B200_H */

@@ -1,0 +1,59 @@
+"""In-tree build of libprecellar_b200.so (sm_100a only).
+
+    python -m precellar_b200.build [--force]
+
+nvcc cross-compiles without a GPU; the resulting .so is git-ignored but travels with the tree.
+"""
+from __future__ import annotations
+
+import os
+import shutil
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+OUT = os.path.join(HERE, "libprecellar_b200.so")
+SOURCES = [os.path.join(CSRC, "pcl.cu")]
+DEPS = [os.path.join(CSRC, f) for f in ("pcl.cu", "kernels.cuh", "hd_core.h", "host_build.h")] + \
+       [os.path.join(HERE, "..", "include", "precellar_b200.h")]
+
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a",   # B200 only: no PTX for other targets, no multi-arch fatbin
+    "-lineinfo", "-O3", "-std=c++17", "--shared", "-Xcompiler", "-fPIC",
+    "-Xptxas", "-v",
+]
+
+
+def nvcc_path() -> str:
+    for cand in (shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
+        if cand and os.path.exists(cand):
+            return cand
+    raise RuntimeError("nvcc not found")
+
+
+def is_stale() -> bool:
+    if not os.path.exists(OUT):
+        return True
+    t = os.path.getmtime(OUT)
+    return any(os.path.getmtime(d) > t for d in DEPS if os.path.exists(d))
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    if not force and not is_stale():
+        return OUT
+    cmd = [nvcc_path()] + NVCC_FLAGS + ["-o", OUT] + SOURCES + ["-ldl"]
+    proc = subprocess.run(cmd, capture_output=True, text=True)
+    log = proc.stdout + proc.stderr
+    with open(os.path.join(HERE, "build.log"), "w") as fh:
+        fh.write(" ".join(cmd) + "\n" + log)
+    if proc.returncode != 0:
+        sys.stderr.write(log)
+        raise RuntimeError("nvcc failed")
+    if verbose:
+        print(log)
+    return OUT
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose=True))

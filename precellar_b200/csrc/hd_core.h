@@ -1,0 +1,359 @@
+// hd_core.h -- per-record logic of the barcode hot path as __host__ __device__ functions.
+//
+// The CUDA kernels in kernels.cu are thin wrappers around these functions.  They are also
+// compiled for the host by tests/emul (a CPU-side unit-test harness that checks this logic
+// against the oracle without a GPU).  The product library only calls them from device code.
+//
+// Reference semantics implemented here (paths relative to the precellar repository):
+//   pcl_split            SegmentInfo::split_with_tolerance(read, 1.0, 0.2) + consume_buf +
+//                        find_best_pattern_match      seqspec/src/read/segment.rs:180-368,496-535
+//   pcl_pack_key         the byte string handed to WhitelistBuilder::add / correct_barcode, i.e.
+//                        the segment or precellar::utils::rev_compl(segment)
+//                        precellar/src/barcode.rs:104-115, precellar/src/utils.rs:138-149
+//   pcl_probe            OligoFrequncy: HashMap<Vec<u8>, usize> lookup   precellar/src/barcode.rs:189
+//   pcl_correct_one      correct_barcode + likelihood1 + update_best_option
+//                        precellar/src/barcode.rs:160-184,311-358
+#ifndef PCL_HD_CORE_H
+#define PCL_HD_CORE_H
+
+#include <stdint.h>
+
+#include "../../include/precellar_b200.h"
+
+#ifdef __CUDACC__
+#define PCL_HD __host__ __device__ __forceinline__
+#else
+#define PCL_HD inline
+#endif
+
+// ------------------------------------------------------------------------------------------
+// device-side layout tables
+// ------------------------------------------------------------------------------------------
+struct DElem {
+    uint16_t min_len, max_len;
+    uint8_t kind;        // pcl_kind
+    uint8_t is_anchor;   // sequence_type == Fixed
+    uint8_t seq_len;     // strlen(sequence)
+    uint8_t max_mis;     // largest k with (double)k <= 0.2 * (double)seq_len   (segment.rs:267)
+    int8_t bc_j;         // index among the read's barcode elements, else -1
+    int8_t umi_j;        // index among the read's UMI elements, else -1
+    uint8_t pad[2];
+    uint8_t seq[PCL_MAX_ANCHOR];
+};
+
+struct DRead {
+    uint16_t n_elems;
+    uint8_t is_reverse;
+    uint8_t fixed_layout;
+    uint32_t max_len;    // reader truncation, 0 = none
+    uint32_t stride;     // bytes per record slot
+    uint8_t n_bc, n_umi, has_target, needs_payload;
+    DElem elems[PCL_MAX_ELEMS];
+};
+
+// Whitelist hash table of one barcode region: buckets of 32 bytes (one DRAM/L2 sector) holding
+// 8 x 32-bit or 4 x 64-bit keys; the slot position is the identity of the entry (counts[slot]).
+enum { PCL_TAB_K32_MARKER = 0, PCL_TAB_K32_L16 = 1, PCL_TAB_K64 = 2 };
+struct DTable {
+    const void *keys;
+    uint32_t *counts;                   // [n_buckets * slots_per_bucket]
+    unsigned long long *total;          // total_count
+    unsigned long long *mismatch;       // mismatch_count
+    uint64_t empty;                     // key value marking an empty slot (never a whitelist key)
+    uint32_t n_buckets;
+    uint32_t mode;                      // PCL_TAB_*
+};
+
+// ------------------------------------------------------------------------------------------
+// base coding
+// ------------------------------------------------------------------------------------------
+// Forward reads: only upper-case ACGT are bases; any other byte is "invalid" (it can never equal a
+// whitelist byte, and likelihood1 tries all four substitutions there).  Reverse reads go through
+// precellar::utils::rev_compl which also maps lower-case acgt to their upper-case complement
+// (precellar/src/utils.rs:138-149), so there lower-case letters are bases too.
+// Returns 0..3 (A C G T) or 4 (invalid); `rev` also complements.
+PCL_HD uint32_t pcl_base_code(uint8_t b, bool rev) {
+    if (rev) b &= 0xDF;                                  // fold case: only 'a','c','g','t' reach ACGT
+    uint32_t c = ((b >> 1) ^ (b >> 2)) & 3u;             // A->0 C->1 G->2 T->3
+    uint32_t expect = (0x54474341u >> (8u * c)) & 0xFFu; // "ACGT"[c]
+    if (b != expect) return 4u;
+    return rev ? 3u - c : c;
+}
+
+// Pack the barcode/UMI that the reference would see for segment [start, start+len) of `rec`.
+// key = (1 << 2L) | bases (first base most significant); positions with an invalid byte contribute 0.
+// *n_invalid = number of invalid positions, *inv_pos = position (in reported orientation) of the last one.
+// len > PCL_MAX_KEY_LEN is not packable: returns 0 and n_invalid = len.
+PCL_HD uint64_t pcl_pack_key(const uint8_t *rec, uint32_t start, uint32_t len, bool rev, uint32_t *n_invalid,
+                             uint32_t *inv_pos) {
+    if (len > PCL_MAX_KEY_LEN) { *n_invalid = len; *inv_pos = 0; return 0; }
+    uint64_t key = 1;
+    uint32_t ninv = 0, ip = 0;
+    for (uint32_t p = 0; p < len; ++p) {
+        uint8_t b = rev ? rec[start + len - 1 - p] : rec[start + p];
+        uint32_t c = pcl_base_code(b, rev);
+        if (c > 3u) { ++ninv; ip = p; c = 0; }
+        key = (key << 2) | c;
+    }
+    *n_invalid = ninv;
+    *inv_pos = ip;
+    return key;
+}
+
+// ------------------------------------------------------------------------------------------
+// whitelist table probe
+// ------------------------------------------------------------------------------------------
+PCL_HD uint32_t pcl_hash_bucket(uint64_t key, uint32_t n_buckets) {
+    uint64_t h = key * 0x9E3779B97F4A7C15ull;
+    h ^= h >> 32;
+    h *= 0xD6E8FEB86659FD93ull;
+    h ^= h >> 32;
+    return (uint32_t)(((h & 0xFFFFFFFFull) * (uint64_t)n_buckets) >> 32);
+}
+
+#ifdef __CUDA_ARCH__
+#define PCL_LDG128(p) __ldg(reinterpret_cast<const uint4 *>(p))
+#else
+struct pcl_u4 { uint32_t x, y, z, w; };
+#define PCL_LDG128(p) (*reinterpret_cast<const pcl_u4 *>(p))
+#endif
+
+// Look `key` (marker form, `len` bases) up in the table.  Returns the slot or 0xFFFFFFFF.
+PCL_HD uint32_t pcl_probe(const DTable &t, uint64_t key, uint32_t len) {
+    const uint32_t MISS = 0xFFFFFFFFu;
+    if (t.n_buckets == 0) return MISS;
+    if (t.mode == PCL_TAB_K64) {
+        if (key == t.empty) return MISS;
+        uint32_t b = pcl_hash_bucket(key, t.n_buckets);
+        const uint64_t *keys = reinterpret_cast<const uint64_t *>(t.keys);
+        for (;;) {
+            auto v0 = PCL_LDG128(keys + (uint64_t)b * 4);
+            auto v1 = PCL_LDG128(keys + (uint64_t)b * 4 + 2);
+            uint64_t k0 = ((uint64_t)v0.y << 32) | v0.x, k1 = ((uint64_t)v0.w << 32) | v0.z;
+            uint64_t k2 = ((uint64_t)v1.y << 32) | v1.x, k3 = ((uint64_t)v1.w << 32) | v1.z;
+            if (k0 == key) return b * 4u;
+            if (k1 == key) return b * 4u + 1u;
+            if (k2 == key) return b * 4u + 2u;
+            if (k3 == key) return b * 4u + 3u;
+            if (k0 == t.empty || k1 == t.empty || k2 == t.empty || k3 == t.empty) return MISS;
+            b = (b + 1u == t.n_buckets) ? 0u : b + 1u;
+        }
+    } else {
+        if (t.mode == PCL_TAB_K32_L16) { if (len != 16u) return MISS; }
+        else if (len > 15u) return MISS;
+        uint32_t k = (uint32_t)key, e = (uint32_t)t.empty;
+        if (k == e) return MISS;
+        uint32_t b = pcl_hash_bucket((uint64_t)k, t.n_buckets);
+        const uint32_t *keys = reinterpret_cast<const uint32_t *>(t.keys);
+        for (;;) {
+            auto v0 = PCL_LDG128(keys + (uint64_t)b * 8);
+            auto v1 = PCL_LDG128(keys + (uint64_t)b * 8 + 4);
+            if (v0.x == k) return b * 8u;
+            if (v0.y == k) return b * 8u + 1u;
+            if (v0.z == k) return b * 8u + 2u;
+            if (v0.w == k) return b * 8u + 3u;
+            if (v1.x == k) return b * 8u + 4u;
+            if (v1.y == k) return b * 8u + 5u;
+            if (v1.z == k) return b * 8u + 6u;
+            if (v1.w == k) return b * 8u + 7u;
+            if (v0.x == e || v0.y == e || v0.z == e || v0.w == e || v1.x == e || v1.y == e || v1.z == e || v1.w == e)
+                return MISS;
+            b = (b + 1u == t.n_buckets) ? 0u : b + 1u;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// split
+// ------------------------------------------------------------------------------------------
+struct SplitOut {
+    uint32_t seg[PCL_MAX_ELEMS];   // (start << 16) | len per element, PCL_COORD_ABSENT if the element has no Single segment
+    uint32_t tcoord;               // the target segment (Single target or a Joined run containing one)
+    uint32_t status;               // PCL_SPLIT_*
+};
+
+// haystack byte k of the anchor search: the window itself, or seqspec::utils::rev_compl(window)
+// (upper-case only, seqspec/src/utils.rs:176-187) for neg-strand reads.
+PCL_HD uint8_t pcl_window_byte(const uint8_t *w, uint32_t n, uint32_t k, bool rev) {
+    if (!rev) return w[k];
+    uint8_t x = w[n - 1u - k];
+    switch (x) {
+        case 'A': return 'T';
+        case 'T': return 'A';
+        case 'C': return 'G';
+        case 'G': return 'C';
+        default: return x;
+    }
+}
+
+// find_best_pattern_match (segment.rs:496-535).  The KMP pre-pass returns the first exact occurrence,
+// which is also what the leftmost-strict-minimum scan returns when the minimum is 0, so one scan suffices.
+// Returns false for (None, _).
+PCL_HD bool pcl_best_match(const uint8_t *w, uint32_t n, const uint8_t *needle, uint32_t m, bool rev, uint32_t *pos,
+                           uint32_t *mis) {
+    if (m == 0u || n == 0u || m > n) return false;
+    uint32_t best = 0xFFFFFFFFu, bpos = 0;
+    for (uint32_t i = 0; i + m <= n; ++i) {
+        uint32_t d = 0;
+        for (uint32_t j = 0; j < m; ++j) {
+            d += pcl_window_byte(w, n, i + j, rev) != needle[j];
+            if (d >= best) break;                          // cannot become a strict improvement
+        }
+        if (d < best) { best = d; bpos = i; if (d == 0u) break; }
+    }
+    if (m == 1u && best != 0u) return false;               // (None, 1)  (segment.rs:508-512)
+    *pos = bpos;
+    *mis = best;
+    return true;
+}
+
+// consume_buf (segment.rs:186-232) over buffered elements [b0, b1] and record range [lo, hi).
+PCL_HD void pcl_consume(const DRead &rd, SplitOut &o, int b0, int b1, uint32_t lo, uint32_t hi, uint32_t *n_target) {
+    int e = b1;
+    while (e >= b0 && rd.elems[e].min_len == rd.elems[e].max_len) {
+        uint32_t l = hi - lo;
+        uint32_t ml = rd.elems[e].max_len;
+        uint32_t i = l - ml;                               // never underflows for derived layouts (range >= sum of min_len)
+        uint32_t c = ((lo + i) << 16) | ml;
+        o.seg[e] = c;
+        if (rd.elems[e].kind == PCL_KIND_TARGET) { o.tcoord = c; ++*n_target; }
+        hi = lo + i;
+        --e;
+    }
+    if (e >= b0) {
+        uint32_t c = (lo << 16) | (hi - lo);
+        if (e == b0) {
+            o.seg[b0] = c;
+            if (rd.elems[b0].kind == PCL_KIND_TARGET) { o.tcoord = c; ++*n_target; }
+        } else {
+            // Joined(region types): never a barcode / UMI; a target if any member is (segment.rs:71-90)
+            bool has_t = false;
+            for (int k = b0; k <= e; ++k) has_t |= rd.elems[k].kind == PCL_KIND_TARGET;
+            if (has_t) { o.tcoord = c; ++*n_target; }
+        }
+    }
+}
+
+PCL_HD void pcl_split(const DRead &rd, const uint8_t *rec, uint32_t len, SplitOut &o) {
+    for (int e = 0; e < PCL_MAX_ELEMS; ++e) o.seg[e] = PCL_COORD_ABSENT;
+    o.tcoord = PCL_COORD_ABSENT;
+    o.status = PCL_SPLIT_OK;
+    uint32_t min_off = 0, max_off = 0, buf_sum_min = 0, n_target = 0;
+    int buf_start = -1, buf_end = -1;
+    const int n_elems = rd.n_elems;
+    for (int e = 0; e < n_elems; ++e) {
+        const DElem &el = rd.elems[e];
+        const uint32_t mn = el.min_len, mx = el.max_len;
+        if (max_off >= len || min_off + mn > len) break;                         // segment.rs:245-248
+        if (mn == mx) {
+            if (buf_start >= 0) {
+                if (el.is_anchor) {                                              // segment.rs:254-311
+                    uint32_t wend = max_off + mx < len ? max_off + mx : len;
+                    uint32_t pos = 0, mis = 0;
+                    if (!pcl_best_match(rec + min_off, wend - min_off, el.seq, el.seq_len, rd.is_reverse != 0, &pos, &mis)) {
+                        o.status = PCL_SPLIT_ANCHOR_NOT_FOUND;
+                        return;
+                    }
+                    if (mis <= el.max_mis) {
+                        uint32_t off_left = min_off - buf_sum_min, off_right = min_off + pos;
+                        pcl_consume(rd, o, buf_start, buf_end, off_left, off_right, &n_target);
+                        buf_start = -1; buf_sum_min = 0;
+                        min_off = off_right; max_off = off_right;
+                        uint32_t c = (off_right << 16) | mx;
+                        o.seg[e] = c;
+                        if (el.kind == PCL_KIND_TARGET) { o.tcoord = c; ++n_target; }
+                    } else if (max_off + mx > len) {
+                        break;                                                   // segment.rs:303-305
+                    } else {
+                        o.status = PCL_SPLIT_PATTERN_MISMATCH;                   // segment.rs:306-308
+                        return;
+                    }
+                } else {
+                    buf_end = e; buf_sum_min += mn;                              // segment.rs:312-314
+                }
+            } else {
+                uint32_t c = (max_off << 16) | mx;                               // segment.rs:315-344
+                o.seg[e] = c;
+                if (el.kind == PCL_KIND_TARGET) { o.tcoord = c; ++n_target; }
+            }
+        } else {
+            if (buf_start < 0) buf_start = e;                                    // segment.rs:345-347
+            buf_end = e; buf_sum_min += mn;
+        }
+        min_off += mn;                                                           // segment.rs:349-350
+        max_off += mx;
+    }
+    if (buf_start >= 0) {                                                        // segment.rs:353-365
+        uint32_t hi = max_off < len ? max_off : len;
+        pcl_consume(rd, o, buf_start, buf_end, min_off - buf_sum_min, hi, &n_target);
+    }
+    if (n_target > 1u) o.status = PCL_SPLIT_MULTI_TARGET;                        // fastq.rs:505-506 panics
+}
+
+// ------------------------------------------------------------------------------------------
+// correction
+// ------------------------------------------------------------------------------------------
+#ifdef __CUDA_ARCH__
+#define PCL_DMUL(a, b) __dmul_rn((a), (b))
+#define PCL_DADD(a, b) __dadd_rn((a), (b))
+#define PCL_DDIV(a, b) __ddiv_rn((a), (b))
+#else
+// host build of the test harness uses -ffp-contract=off
+#define PCL_DMUL(a, b) ((a) * (b))
+#define PCL_DADD(a, b) ((a) + (b))
+#define PCL_DDIV(a, b) ((a) / (b))
+#endif
+
+// correct_barcode (barcode.rs:160-184) for one barcode that is NOT an exact whitelist member unless
+// `is_exact`.  `qual` points at the segment's quality bytes in record orientation; position p of the
+// reported barcode uses qual[start + (rev ? len-1-p : p)].  lut_cap[q] = error_probability(min(q, 66)),
+// lut_raw[q] = error_probability(q).  Returns a PCL_BC_* code; *out_key = chosen whitelist key.
+PCL_HD uint32_t pcl_correct_one(const DTable &t, uint64_t key, uint32_t len, uint32_t n_invalid, uint32_t inv_pos,
+                                const uint8_t *qual, uint32_t start, bool rev, bool is_exact, double threshold,
+                                double max_expected_errors, bool check_ee, const double *lut_cap,
+                                const double *lut_raw, uint64_t *out_key) {
+    if (check_ee) {                                                   // barcode.rs:167-170, uncapped q
+        double expected = 0.0;
+        for (uint32_t p = 0; p < len; ++p) {
+            uint8_t q = qual[start + (rev ? len - 1u - p : p)];
+            expected = PCL_DADD(expected, lut_raw[q]);
+        }
+        if (expected >= max_expected_errors) return PCL_BC_EXCEED_EE;
+    }
+    if (is_exact) { *out_key = key; return PCL_BC_EXACT; }            // (query, 1.0); 1.0 >= thr decided by the caller
+    if (len > PCL_MAX_KEY_LEN || n_invalid > 1u) return PCL_BC_NO_MATCH;   // no single substitution reaches the list
+    bool have = false;
+    double best_like = 0.0, total = 0.0;
+    uint64_t best_key = 0;
+    for (uint32_t pos = 0; pos < len; ++pos) {                        // barcode.rs:319-334
+        if (n_invalid == 1u && pos != inv_pos) continue;              // another position holds a non-ACGT byte
+        uint8_t q = qual[start + (rev ? len - 1u - pos : pos)];
+        uint32_t sh = 2u * (len - 1u - pos);
+        uint32_t existing = (n_invalid == 1u) ? 4u : (uint32_t)((key >> sh) & 3u);
+        uint64_t base = key & ~(3ull << sh);
+        for (uint32_t val = 0; val < 4u; ++val) {                     // BASE_OPTS order A C G T
+            if (val == existing) continue;
+            uint64_t cand = base | ((uint64_t)val << sh);
+            uint32_t slot = pcl_probe(t, cand, len);
+            if (slot != 0xFFFFFFFFu) {
+                uint32_t c = t.counts[slot];
+                double like = PCL_DMUL((double)(1ull + (uint64_t)c), lut_cap[q]);   // barcode.rs:326-327
+                if (!have || best_like < like) { have = true; best_like = like; best_key = cand; }   // :345-358
+                total = PCL_DADD(total, like);
+            }
+        }
+    }
+    if (!have) return PCL_BC_NO_MATCH;                                // (query, 0.0) -> prob <= 0
+    double prob = PCL_DDIV(best_like, total);
+    if (prob <= 0.0) return PCL_BC_NO_MATCH;
+    if (prob >= threshold) { *out_key = best_key; return PCL_BC_CORRECTED; }
+    return PCL_BC_LOW_CONF;
+}
+
+// Store a key in its device width (see precellar_b200.h).
+PCL_HD void pcl_store_key(void *arr, uint32_t key_bytes, uint64_t i, uint64_t key) {
+    if (key_bytes == 4u) reinterpret_cast<uint32_t *>(arr)[i] = (uint32_t)key;
+    else reinterpret_cast<uint64_t *>(arr)[i] = key;
+}
+
+#endif  // PCL_HD_CORE_H

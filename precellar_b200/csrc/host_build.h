@@ -1,0 +1,191 @@
+// host_build.h -- host-side construction of the device tables (pure C++, no CUDA calls):
+//   * pcl_build_read : pcl_read_desc -> DRead + pcl_read_info   (the "compiled region table")
+//   * pcl_build_table: whitelist byte strings -> bucketed open-addressing key table
+// Used by pcl.cu (which uploads the results) and by the CPU unit-test harness in tests/emul.
+#ifndef PCL_HOST_BUILD_H
+#define PCL_HOST_BUILD_H
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "hd_core.h"
+
+inline uint32_t pcl_key_bytes_for(const pcl_elem_desc &e) {
+    if (e.max_len <= 15) return 4;
+    if (e.min_len == 16 && e.max_len == 16) return 4;
+    return 8;
+}
+
+inline int pcl_build_fail(std::string *err, int code, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (err) *err = buf;
+    return code;
+}
+
+// Derive the device-side description of one read.  bc_region[j] = whitelist region of barcode j.
+inline int pcl_build_read(int r, const pcl_read_desc &rd, DRead *out, pcl_read_info *info_out, int *bc_region,
+                          std::string *err) {
+    if (rd.n_elems < 1 || rd.n_elems > PCL_MAX_ELEMS)
+        return pcl_build_fail(err, PCL_ERR_UNSUPPORTED, "read %d: %d elements outside 1..%d", r, rd.n_elems, PCL_MAX_ELEMS);
+    DRead d;
+    memset(&d, 0, sizeof d);
+    pcl_read_info info;
+    memset(&info, 0, sizeof info);
+    d.n_elems = rd.n_elems;
+    d.is_reverse = rd.is_reverse ? 1 : 0;
+    d.max_len = rd.max_len;
+    bool fixed = true, payload = false;
+    uint32_t reach = 0, start = 0;
+    for (int e = 0; e < rd.n_elems; ++e) {
+        const pcl_elem_desc &el = rd.elems[e];
+        DElem &de = d.elems[e];
+        if (el.min_len > el.max_len) return pcl_build_fail(err, PCL_ERR_ARG, "read %d elem %d: min_len > max_len", r, e);
+        de.min_len = el.min_len; de.max_len = el.max_len; de.kind = el.kind;
+        de.is_anchor = el.is_fixed_seq ? 1 : 0;
+        de.bc_j = -1; de.umi_j = -1;
+        const bool fixed_len = el.min_len == el.max_len;
+        if (el.is_fixed_seq) {
+            if (el.seq_len > PCL_MAX_ANCHOR)
+                return pcl_build_fail(err, PCL_ERR_UNSUPPORTED, "read %d elem %d: fixed sequence longer than %d", r, e, PCL_MAX_ANCHOR);
+            de.seq_len = el.seq_len;
+            memcpy(de.seq, el.sequence, el.seq_len);
+            uint32_t k = 0;                                   // `mis as f64 <= 0.2 * len as f64` (segment.rs:267)
+            while ((double)(k + 1) <= 0.2 * (double)el.seq_len) ++k;
+            de.max_mis = (uint8_t)k;
+        }
+        const bool may_anchor = !fixed && el.is_fixed_seq && fixed_len;   // a variable run precedes it
+        if (may_anchor) {
+            payload = true;
+            if (el.seq_len != el.max_len)
+                return pcl_build_fail(err, PCL_ERR_UNSUPPORTED, "read %d elem %d: anchor sequence length %d != max_len %d", r, e, el.seq_len, el.max_len);
+        }
+        if (!fixed_len && e != rd.n_elems - 1) fixed = false;
+        info.static_start[e] = (uint16_t)start;
+        start += el.max_len;
+        if (el.kind == PCL_KIND_BARCODE) {
+            if (info.n_bc >= PCL_MAX_BC_PER_READ)
+                return pcl_build_fail(err, PCL_ERR_UNSUPPORTED, "read %d: more than %d barcode elements", r, PCL_MAX_BC_PER_READ);
+            if (el.region_slot < 0 || el.region_slot >= PCL_MAX_REGIONS)
+                return pcl_build_fail(err, PCL_ERR_ARG, "read %d elem %d: bad region_slot", r, e);
+            if (el.max_len > 255) return pcl_build_fail(err, PCL_ERR_UNSUPPORTED, "read %d elem %d: barcode longer than 255", r, e);
+            de.bc_j = (int8_t)info.n_bc;
+            bc_region[info.n_bc] = el.region_slot;
+            info.bc_elem[info.n_bc] = (uint8_t)e;
+            info.bc_key_bytes[info.n_bc] = (uint8_t)pcl_key_bytes_for(el);
+            info.n_bc++;
+            payload = true;
+        } else if (el.kind == PCL_KIND_UMI) {
+            if (info.n_umi >= PCL_MAX_UMI_PER_READ)
+                return pcl_build_fail(err, PCL_ERR_UNSUPPORTED, "read %d: more than %d UMI elements", r, PCL_MAX_UMI_PER_READ);
+            de.umi_j = (int8_t)info.n_umi;
+            info.umi_elem[info.n_umi] = (uint8_t)e;
+            info.umi_key_bytes[info.n_umi] = (uint8_t)(el.max_len <= 15 ? 4 : 8);
+            info.n_umi++;
+            payload = true;
+        } else if (el.kind == PCL_KIND_TARGET) {
+            info.has_target = 1;
+        }
+        if (el.kind == PCL_KIND_BARCODE || el.kind == PCL_KIND_UMI || may_anchor)
+            if (start > reach) reach = start;                  // last byte split()/pack may touch
+    }
+    uint32_t need = payload ? reach : 0;
+    if (rd.max_len && need > rd.max_len) need = rd.max_len;
+    uint32_t stride = need ? ((need + 15u) / 16u) * 16u : 0;
+    if (stride > PCL_MAX_STRIDE)
+        return pcl_build_fail(err, PCL_ERR_UNSUPPORTED, "read %d: %u payload bytes per record exceed %d", r, stride, PCL_MAX_STRIDE);
+    if (start > 0xFFFF) return pcl_build_fail(err, PCL_ERR_UNSUPPORTED, "read %d: layout longer than 65535", r);
+    d.stride = stride;
+    d.fixed_layout = fixed ? 1 : 0;
+    d.n_bc = info.n_bc; d.n_umi = info.n_umi; d.has_target = info.has_target; d.needs_payload = payload ? 1 : 0;
+    info.fixed_layout = d.fixed_layout;
+    info.needs_payload = d.needs_payload;
+    *out = d;
+    *info_out = info;
+    return PCL_OK;
+}
+
+struct HostTable {
+    uint32_t mode = 0, slots_per_bucket = 8;
+    uint64_t n_buckets = 0, n_slots = 0, n_entries = 0, empty = 0;
+    std::vector<uint32_t> tab32;
+    std::vector<uint64_t> tab64;
+    std::vector<uint32_t> index_to_slot;     // whitelist index (dedup file order) -> slot
+    const void *data() const { return mode == PCL_TAB_K64 ? (const void *)tab64.data() : (const void *)tab32.data(); }
+    size_t key_bytes() const { return mode == PCL_TAB_K64 ? 8 : 4; }
+};
+
+// Build the whitelist table of one region (WhitelistBuilder::new semantics: a set of byte strings,
+// file order, duplicates dropped -- precellar/src/barcode.rs:393-407, seqspec/src/region.rs:459-469).
+// Deterministic: every rank builds the same table, so counts[] can be all-reduced slot-wise.
+inline int pcl_build_table(const uint8_t *bytes, const uint64_t *offsets, uint64_t n, HostTable *out, std::string *err) {
+    std::vector<uint64_t> keys;
+    keys.reserve(n);
+    std::unordered_map<uint64_t, uint32_t> seen;
+    seen.reserve(n * 2);
+    bool all16 = true, all_le15 = true;
+    for (uint64_t i = 0; i < n; ++i) {
+        uint64_t a = offsets[i], b = offsets[i + 1];
+        if (b < a) return pcl_build_fail(err, PCL_ERR_ARG, "whitelist offsets not monotone at %llu", (unsigned long long)i);
+        uint64_t L = b - a;
+        if (L < 1 || L > PCL_MAX_KEY_LEN)
+            return pcl_build_fail(err, PCL_ERR_UNSUPPORTED, "whitelist entry %llu has length %llu (supported: 1..%d)",
+                                  (unsigned long long)i, (unsigned long long)L, PCL_MAX_KEY_LEN);
+        uint32_t ninv, ipos;
+        uint64_t key = pcl_pack_key(bytes + a, 0, (uint32_t)L, false, &ninv, &ipos);
+        if (ninv)
+            return pcl_build_fail(err, PCL_ERR_UNSUPPORTED, "whitelist entry %llu contains a byte outside upper-case ACGT", (unsigned long long)i);
+        if (seen.emplace(key, (uint32_t)keys.size()).second) {
+            keys.push_back(key);
+            all16 &= (L == 16);
+            all_le15 &= (L <= 15);
+        }
+    }
+    HostTable t;
+    const uint64_t m = keys.size();
+    t.n_entries = m;
+    t.mode = all_le15 ? PCL_TAB_K32_MARKER : (all16 ? PCL_TAB_K32_L16 : PCL_TAB_K64);
+    t.slots_per_bucket = t.mode == PCL_TAB_K64 ? 4 : 8;
+    const uint32_t spb = t.slots_per_bucket;
+    t.n_buckets = (2 * m + spb - 1) / spb;                     // load factor <= 0.5
+    if (t.n_buckets < 2) t.n_buckets = 2;
+    t.n_slots = t.n_buckets * spb;
+    if (t.n_slots >= (1ull << 29))
+        return pcl_build_fail(err, PCL_ERR_UNSUPPORTED, "whitelist too large (%llu entries)", (unsigned long long)m);
+    // Empty marker: a value that is not a key.  Marker-form keys (<= 31 bases) never have all bits set;
+    // for marker-less 16-mers walk down from 0xFFFFFFFF until a free value is found (at most m steps).
+    t.empty = t.mode == PCL_TAB_K64 ? 0xFFFFFFFFFFFFFFFFull : 0xFFFFFFFFull;
+    if (t.mode == PCL_TAB_K32_L16)
+        while (seen.count((1ull << 32) | t.empty)) --t.empty;
+    t.index_to_slot.resize(m);
+    if (t.mode == PCL_TAB_K64) t.tab64.assign(t.n_slots, t.empty); else t.tab32.assign(t.n_slots, (uint32_t)t.empty);
+    for (uint64_t i = 0; i < m; ++i) {
+        const uint64_t k = t.mode == PCL_TAB_K64 ? keys[i] : (keys[i] & 0xFFFFFFFFull);
+        uint32_t b = pcl_hash_bucket(k, (uint32_t)t.n_buckets);
+        for (;;) {
+            bool placed = false;
+            for (uint32_t s = 0; s < spb && !placed; ++s) {
+                const uint64_t idx = (uint64_t)b * spb + s;
+                if (t.mode == PCL_TAB_K64) {
+                    if (t.tab64[idx] == t.empty) { t.tab64[idx] = k; placed = true; }
+                } else {
+                    if (t.tab32[idx] == (uint32_t)t.empty) { t.tab32[idx] = (uint32_t)k; placed = true; }
+                }
+                if (placed) t.index_to_slot[i] = (uint32_t)idx;
+            }
+            if (placed) break;
+            b = (b + 1 == t.n_buckets) ? 0 : b + 1;
+        }
+    }
+    *out = std::move(t);
+    return PCL_OK;
+}
+
+#endif  // PCL_HOST_BUILD_H

@@ -1,0 +1,277 @@
+// kernels.cuh -- sm_100a kernels of the barcode hot path (included once, by pcl.cu).
+//
+//   k_count     pass 1: split -> pack -> whitelist probe -> histogram (+ miss worklist, UMI keys, coords)
+//               replaces hot loop A, BarcodeAnalyzer::new  (precellar/src/barcode.rs:85-119)
+//               and the split/rev-comp part of FastqAnnotator::annotate (align/fastq.rs:484-516)
+//   k_enum_all  builds a worklist of every present barcode (only when max_expected_errors is finite)
+//   k_correct   pass 2: likelihood1 posterior for every worklist entry (barcode.rs:160-184,311-358)
+#ifndef PCL_KERNELS_CUH
+#define PCL_KERNELS_CUH
+
+#include <cuda_runtime.h>
+
+#include "hd_core.h"
+
+#define PCL_BLOCK 256
+#define PCL_HCACHE_BITS 12
+#define PCL_HCACHE (1u << PCL_HCACHE_BITS)
+#define PCL_HEMPTY 0xFFFFFFFFu
+
+struct CountParams {
+    DRead rd;
+    DTable tab[PCL_MAX_BC_PER_READ];
+    const uint8_t *seq;
+    const uint16_t *len;
+    uint64_t n;
+    uint16_t *fstatus;
+    uint32_t *tcoord;
+    void *bc_key[PCL_MAX_BC_PER_READ];
+    void *umi_key[PCL_MAX_UMI_PER_READ];
+    uint32_t *bcoord[PCL_MAX_BC_PER_READ];
+    uint32_t *ucoord[PCL_MAX_UMI_PER_READ];
+    uint8_t bc_key_bytes[PCL_MAX_BC_PER_READ];
+    uint8_t umi_key_bytes[PCL_MAX_UMI_PER_READ];
+    uint8_t bc_elem[PCL_MAX_BC_PER_READ];
+    uint8_t umi_elem[PCL_MAX_UMI_PER_READ];
+    unsigned long long *worklist;        // entries: rec | start<<32 | len<<48 | j<<56
+    unsigned long long *wl_count;
+    unsigned long long *num_defect;
+};
+
+struct CorrectParams {
+    DRead rd;
+    DTable tab[PCL_MAX_BC_PER_READ];
+    const uint8_t *seq;
+    const uint8_t *qual;
+    const uint16_t *len;
+    uint64_t n;
+    uint16_t *fstatus;
+    void *bc_key[PCL_MAX_BC_PER_READ];
+    uint32_t *bcoord[PCL_MAX_BC_PER_READ];
+    uint8_t bc_key_bytes[PCL_MAX_BC_PER_READ];
+    uint8_t bc_elem[PCL_MAX_BC_PER_READ];
+    uint16_t static_start[PCL_MAX_ELEMS];
+    unsigned long long *worklist;
+    unsigned long long *wl_count;
+    const double *lut_cap;
+    const double *lut_raw;
+    double threshold;
+    double max_expected_errors;
+    int check_ee;
+};
+
+__device__ __forceinline__ unsigned long long pcl_wl_entry(uint64_t rec, uint32_t start, uint32_t len, uint32_t j) {
+    return (unsigned long long)rec | ((unsigned long long)start << 32) | ((unsigned long long)len << 48) |
+           ((unsigned long long)j << 56);
+}
+
+// Per-CTA histogram cache: a direct-mapped table in shared memory keyed on (j, slot).  Zipf-distributed
+// barcodes send a large share of the reads to a few counters; the cache turns those into shared-memory
+// atomics and one global atomic per cached key at the end of the CTA's life.
+__device__ __forceinline__ void pcl_hist_add(uint32_t *ck, uint32_t *cc, uint32_t j, uint32_t slot, uint32_t *gcounts) {
+    const uint32_t id = (j << 29) | slot;
+    const uint32_t h = (id * 2654435761u) >> (32 - PCL_HCACHE_BITS);
+    uint32_t cur = ((volatile uint32_t *)ck)[h];
+    if (cur == PCL_HEMPTY) {
+        uint32_t old = atomicCAS(&ck[h], PCL_HEMPTY, id);
+        cur = (old == PCL_HEMPTY) ? id : old;
+    }
+    if (cur == id) atomicAdd(&cc[h], 1u);
+    else atomicAdd(&gcounts[slot], 1u);
+}
+
+__global__ void __launch_bounds__(PCL_BLOCK) k_count(const __grid_constant__ CountParams p) {
+    __shared__ uint32_t ck[PCL_HCACHE];
+    __shared__ uint32_t cc[PCL_HCACHE];
+    const DRead &rd = p.rd;
+    const bool use_hist = rd.n_bc > 0;
+    if (use_hist) {
+        for (uint32_t h = threadIdx.x; h < PCL_HCACHE; h += blockDim.x) { ck[h] = PCL_HEMPTY; cc[h] = 0; }
+        __syncthreads();
+    }
+
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint64_t step = (uint64_t)gridDim.x * blockDim.x;
+    unsigned long long n_total[PCL_MAX_BC_PER_READ] = {0, 0, 0, 0};
+    unsigned long long n_mis[PCL_MAX_BC_PER_READ] = {0, 0, 0, 0};
+    unsigned long long n_defect = 0;
+    const bool rev = rd.is_reverse != 0;
+
+    // every lane of a warp runs the same number of iterations (full-mask ballots below)
+    for (uint64_t base = (uint64_t)blockIdx.x * blockDim.x + (threadIdx.x & ~31u); base < p.n; base += step) {
+        const uint64_t i = base + lane;
+        const bool live = i < p.n;
+        uint32_t miss_mask_j = 0;                 // bit j: barcode j of this record goes to the worklist
+        uint32_t miss_coord[PCL_MAX_BC_PER_READ];
+        if (live) {
+            uint32_t L = p.len[i];
+            if (rd.max_len && L > rd.max_len) L = rd.max_len;          // FastqReader::read_record (read.rs:98-103)
+            const uint8_t *rec = p.seq + i * (uint64_t)rd.stride;
+            SplitOut so;
+            pcl_split(rd, rec, L, so);
+            uint32_t fs = so.status;
+            const bool ok = so.status == PCL_SPLIT_OK;
+            if (so.status == PCL_SPLIT_ANCHOR_NOT_FOUND || so.status == PCL_SPLIT_PATTERN_MISMATCH) ++n_defect;
+            if (ok && so.tcoord != PCL_COORD_ABSENT) fs |= PCL_FSTATUS_TARGET;
+            if (rd.has_target) p.tcoord[i] = ok ? so.tcoord : PCL_COORD_ABSENT;
+
+#pragma unroll
+            for (uint32_t j = 0; j < PCL_MAX_BC_PER_READ; ++j) {
+                if (j >= rd.n_bc) { fs |= PCL_BC_ABSENT << (4 + 3 * j); continue; }
+                const uint32_t c = ok ? so.seg[p.bc_elem[j]] : PCL_COORD_ABSENT;
+                if (!rd.fixed_layout) p.bcoord[j][i] = c;
+                uint32_t code = PCL_BC_ABSENT;
+                uint64_t key = 0;
+                if (c != PCL_COORD_ABSENT) {
+                    const uint32_t start = c >> 16, blen = c & 0xFFFFu;
+                    uint32_t ninv, ipos;
+                    key = pcl_pack_key(rec, start, blen, rev, &ninv, &ipos);
+                    uint32_t slot = 0xFFFFFFFFu;
+                    if (ninv == 0u) slot = pcl_probe(p.tab[j], key, blen);
+                    ++n_total[j];                                      // WhitelistBuilder::add (barcode.rs:410-426)
+                    if (slot != 0xFFFFFFFFu) {
+                        code = PCL_BC_EXACT;
+                        pcl_hist_add(ck, cc, j, slot, p.tab[j].counts);
+                    } else {
+                        code = PCL_BC_NO_MATCH;
+                        ++n_mis[j];
+                        miss_mask_j |= 1u << j;
+                        miss_coord[j] = c;
+                    }
+                }
+                pcl_store_key(p.bc_key[j], p.bc_key_bytes[j], i, key);
+                fs |= code << (4 + 3 * j);
+            }
+#pragma unroll
+            for (uint32_t j = 0; j < PCL_MAX_UMI_PER_READ; ++j) {
+                if (j >= rd.n_umi) continue;
+                const uint32_t c = ok ? so.seg[p.umi_elem[j]] : PCL_COORD_ABSENT;
+                if (!rd.fixed_layout) p.ucoord[j][i] = c;
+                uint64_t key = PCL_KEY_ABSENT64;
+                if (c != PCL_COORD_ABSENT) {
+                    uint32_t ninv, ipos;
+                    key = pcl_pack_key(rec, c >> 16, c & 0xFFFFu, rev, &ninv, &ipos);
+                    if (ninv) key = 0;
+                }
+                pcl_store_key(p.umi_key[j], p.umi_key_bytes[j], i, key);
+            }
+            p.fstatus[i] = (uint16_t)fs;
+        }
+        // warp-aggregated append of the misses to the worklist
+#pragma unroll
+        for (uint32_t j = 0; j < PCL_MAX_BC_PER_READ; ++j) {
+            if (j >= rd.n_bc) break;
+            const bool m = (miss_mask_j >> j) & 1u;
+            const uint32_t ballot = __ballot_sync(0xFFFFFFFFu, m);
+            if (ballot) {
+                unsigned long long pos = 0;
+                if (lane == 0) pos = atomicAdd(p.wl_count, (unsigned long long)__popc(ballot));
+                pos = __shfl_sync(0xFFFFFFFFu, pos, 0);
+                if (m) {
+                    const uint32_t rank = __popc(ballot & ((1u << lane) - 1u));
+                    p.worklist[pos + rank] = pcl_wl_entry(i, miss_coord[j] >> 16, miss_coord[j] & 0xFFFFu, j);
+                }
+            }
+        }
+    }
+
+    // totals: warp reduce, one atomic per warp
+#pragma unroll
+    for (uint32_t j = 0; j < PCL_MAX_BC_PER_READ; ++j) {
+        if (j >= rd.n_bc) break;
+        unsigned long long t = n_total[j], m = n_mis[j];
+        for (int o = 16; o > 0; o >>= 1) {
+            t += __shfl_xor_sync(0xFFFFFFFFu, t, o);
+            m += __shfl_xor_sync(0xFFFFFFFFu, m, o);
+        }
+        if (lane == 0) {
+            if (t) atomicAdd(p.tab[j].total, t);
+            if (m) atomicAdd(p.tab[j].mismatch, m);
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) n_defect += __shfl_xor_sync(0xFFFFFFFFu, n_defect, o);
+    if (lane == 0 && n_defect) atomicAdd(p.num_defect, n_defect);
+
+    if (use_hist) {
+        __syncthreads();
+        for (uint32_t h = threadIdx.x; h < PCL_HCACHE; h += blockDim.x) {
+            const uint32_t id = ck[h], c = cc[h];
+            if (id != PCL_HEMPTY && c) atomicAdd(&p.tab[id >> 29].counts[id & 0x1FFFFFFFu], c);
+        }
+    }
+}
+
+// Worklist of every present barcode (exact and not): the expected-error test of correct_barcode
+// precedes the whitelist lookup, so with a finite max_expected_errors every barcode needs its qualities.
+__global__ void __launch_bounds__(PCL_BLOCK) k_enum_all(const __grid_constant__ CorrectParams p) {
+    const DRead &rd = p.rd;
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint64_t step = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t base = (uint64_t)blockIdx.x * blockDim.x + (threadIdx.x & ~31u); base < p.n; base += step) {
+        const uint64_t i = base + lane;
+        const bool live = i < p.n;
+        const uint32_t fs = live ? p.fstatus[i] : 0xFFFFu;
+        for (uint32_t j = 0; j < rd.n_bc; ++j) {
+            const uint32_t code = PCL_BC_CODE(fs, j);
+            const bool m = live && (code == PCL_BC_EXACT || code == PCL_BC_NO_MATCH);
+            const uint32_t ballot = __ballot_sync(0xFFFFFFFFu, m);
+            if (!ballot) continue;
+            unsigned long long pos = 0;
+            if (lane == 0) pos = atomicAdd(p.wl_count, (unsigned long long)__popc(ballot));
+            pos = __shfl_sync(0xFFFFFFFFu, pos, 0);
+            if (m) {
+                uint32_t c;
+                if (rd.fixed_layout) {
+                    const uint32_t e = p.bc_elem[j];
+                    uint32_t L = p.len[i];
+                    if (rd.max_len && L > rd.max_len) L = rd.max_len;
+                    uint32_t s = p.static_start[e], l = rd.elems[e].max_len;
+                    if (rd.elems[e].min_len != rd.elems[e].max_len) l = (s + l < L ? s + l : L) - s;   // trailing variable barcode
+                    c = (s << 16) | l;
+                } else {
+                    c = p.bcoord[j][i];
+                }
+                const uint32_t rank = __popc(ballot & ((1u << lane) - 1u));
+                p.worklist[pos + rank] = pcl_wl_entry(i, c >> 16, c & 0xFFFFu, j);
+            }
+        }
+    }
+}
+
+__device__ __forceinline__ void pcl_fstatus_or(uint16_t *fstatus, uint64_t i, uint32_t bits) {
+    uintptr_t a = reinterpret_cast<uintptr_t>(fstatus + i);
+    uint32_t *w = reinterpret_cast<uint32_t *>(a & ~(uintptr_t)3);
+    atomicOr(w, (a & 2) ? bits << 16 : bits);
+}
+
+__global__ void __launch_bounds__(PCL_BLOCK) k_correct(const __grid_constant__ CorrectParams p) {
+    const DRead &rd = p.rd;
+    const unsigned long long n_work = *p.wl_count;
+    const uint64_t step = (uint64_t)gridDim.x * blockDim.x;
+    const bool rev = rd.is_reverse != 0;
+    for (uint64_t w = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; w < n_work; w += step) {
+        const unsigned long long ent = p.worklist[w];
+        const uint64_t rec_i = ent & 0xFFFFFFFFull;
+        const uint32_t start = (uint32_t)(ent >> 32) & 0xFFFFu, blen = (uint32_t)(ent >> 48) & 0xFFu,
+                       j = (uint32_t)(ent >> 56);
+        const uint8_t *rec = p.seq + rec_i * (uint64_t)rd.stride;
+        const uint8_t *ql = p.qual + rec_i * (uint64_t)rd.stride;
+        uint32_t ninv, ipos;
+        const uint64_t key = pcl_pack_key(rec, start, blen, rev, &ninv, &ipos);
+        const bool is_exact = PCL_BC_CODE((uint32_t)p.fstatus[rec_i], j) == PCL_BC_EXACT;
+        uint64_t out_key = 0;
+        const uint32_t code = pcl_correct_one(p.tab[j], key, blen, ninv, ipos, ql, start, rev, is_exact, p.threshold,
+                                              p.max_expected_errors, p.check_ee != 0, p.lut_cap, p.lut_raw, &out_key);
+        if (code == PCL_BC_CORRECTED) pcl_store_key(p.bc_key[j], p.bc_key_bytes[j], rec_i, out_key);
+        if (code != PCL_BC_EXACT && code != PCL_BC_NO_MATCH) pcl_fstatus_or(p.fstatus, rec_i, code << (4 + 3 * j));
+    }
+}
+
+// counts in whitelist order for pcl_counts_fetch
+__global__ void k_gather_counts(const uint32_t *__restrict__ counts, const uint32_t *__restrict__ index_to_slot,
+                                unsigned long long *__restrict__ out, uint64_t n) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x)
+        out[i] = counts[index_to_slot[i]];
+}
+
+#endif  // PCL_KERNELS_CUH

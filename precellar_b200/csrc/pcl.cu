@@ -1,0 +1,743 @@
+// pcl.cu -- implementation of the C ABI in include/precellar_b200.h (sm_100a only).
+//
+// Host side: context / layout / whitelist-table construction / chunk memory / stream ordering.
+// Device side: kernels.cuh.  No CPU fallback: compute entry points need a CUDA device.
+
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+
+#include <cfloat>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "host_build.h"
+#include "kernels.cuh"
+
+// ------------------------------------------------------------------------------------------
+// NCCL through dlopen: the library has no link-time dependency on libnccl, and inside a process
+// that already loaded NCCL (e.g. through torch) the same copy is reused.
+// ------------------------------------------------------------------------------------------
+namespace {
+
+struct NcclUid { char internal[128]; };
+typedef void *NcclComm;
+struct NcclApi {
+    void *h = nullptr;
+    int (*GetUniqueId)(NcclUid *) = nullptr;
+    int (*CommInitRank)(NcclComm *, int, NcclUid, int) = nullptr;
+    int (*AllReduce)(const void *, void *, size_t, int, int, NcclComm, cudaStream_t) = nullptr;
+    int (*GroupStart)() = nullptr;
+    int (*GroupEnd)() = nullptr;
+    int (*CommDestroy)(NcclComm) = nullptr;
+    const char *(*GetErrorString)(int) = nullptr;
+    bool ok = false;
+};
+const int kNcclUint32 = 3, kNcclUint64 = 5, kNcclSum = 0;
+
+NcclApi &nccl() {
+    static NcclApi api;
+    static bool tried = false;
+    if (tried) return api;
+    tried = true;
+    const char *names[] = {"libnccl.so.2", "libnccl.so"};
+    for (const char *n : names) {
+        api.h = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+        if (api.h) break;
+    }
+    if (!api.h) return api;
+    api.GetUniqueId = (int (*)(NcclUid *))dlsym(api.h, "ncclGetUniqueId");
+    api.CommInitRank = (int (*)(NcclComm *, int, NcclUid, int))dlsym(api.h, "ncclCommInitRank");
+    api.AllReduce = (int (*)(const void *, void *, size_t, int, int, NcclComm, cudaStream_t))dlsym(api.h, "ncclAllReduce");
+    api.GroupStart = (int (*)())dlsym(api.h, "ncclGroupStart");
+    api.GroupEnd = (int (*)())dlsym(api.h, "ncclGroupEnd");
+    api.CommDestroy = (int (*)(NcclComm))dlsym(api.h, "ncclCommDestroy");
+    api.GetErrorString = (const char *(*)(int))dlsym(api.h, "ncclGetErrorString");
+    api.ok = api.GetUniqueId && api.CommInitRank && api.AllReduce && api.GroupStart && api.GroupEnd && api.CommDestroy;
+    return api;
+}
+
+thread_local std::string g_create_err;
+
+struct Table {
+    bool loaded = false;
+    DTable d{};
+    uint64_t n_entries = 0;
+    uint64_t n_slots = 0;
+    void *d_keys = nullptr;
+    uint32_t *d_counts = nullptr;
+    uint32_t *d_index_to_slot = nullptr;
+    unsigned long long *d_scalars = nullptr;   // [0] total, [1] mismatch
+};
+
+struct EvPair { cudaEvent_t a, b; int k; };
+
+}  // namespace
+
+struct pcl_chunk;
+
+struct pcl_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev_reduced = nullptr;
+    std::string err;
+    int n_reads = 0;
+    pcl_read_desc descs[PCL_MAX_READS];
+    DRead dreads[PCL_MAX_READS];
+    pcl_read_info infos[PCL_MAX_READS];
+    int bc_region[PCL_MAX_READS][PCL_MAX_BC_PER_READ];
+    Table tables[PCL_MAX_REGIONS];
+    double *d_lut = nullptr;                  // [0..255] capped, [256..511] raw
+    unsigned long long *d_qc = nullptr;       // [PCL_MAX_READS] num_defect
+    uint64_t qc_reads[PCL_MAX_READS] = {0};
+    std::vector<pcl_chunk *> chunks;
+    // nccl
+    NcclComm comm = nullptr;
+    int nranks = 1, rank = 0;
+    // instrumentation
+    bool profile = false;
+    std::vector<EvPair> evs;
+    double prof_ms[PCL_K_MAX] = {0};
+    uint64_t prof_n[PCL_K_MAX] = {0};
+    uint64_t launches = 0;
+    int sm_count = 148;
+};
+
+struct ReadBuf {
+    uint8_t *seq = nullptr, *qual = nullptr;
+    uint16_t *len = nullptr;
+    uint16_t *fstatus = nullptr;
+    uint32_t *tcoord = nullptr;
+    void *bc_key[PCL_MAX_BC_PER_READ] = {nullptr};
+    void *umi_key[PCL_MAX_UMI_PER_READ] = {nullptr};
+    uint32_t *bcoord[PCL_MAX_BC_PER_READ] = {nullptr};
+    uint32_t *ucoord[PCL_MAX_UMI_PER_READ] = {nullptr};
+    unsigned long long *worklist = nullptr;
+    unsigned long long *wl_count = nullptr;
+    bool filled = false;
+};
+
+struct pcl_chunk {
+    pcl_ctx *ctx = nullptr;
+    uint64_t cap = 0, n = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev = nullptr, t0 = nullptr, t1 = nullptr;
+    ReadBuf rb[PCL_MAX_READS];
+    std::vector<void *> allocs;
+};
+
+namespace {
+
+int fail(pcl_ctx *ctx, int code, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (ctx) ctx->err = buf; else g_create_err = buf;
+    return code;
+}
+
+#define CU(ctx, call)                                                                               \
+    do {                                                                                            \
+        cudaError_t e_ = (call);                                                                    \
+        if (e_ != cudaSuccess) return fail(ctx, PCL_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(e_)); \
+    } while (0)
+
+int bind(pcl_ctx *ctx) {
+    cudaError_t e = cudaSetDevice(ctx->device);
+    if (e != cudaSuccess) return fail(ctx, PCL_ERR_CUDA, "cudaSetDevice(%d): %s", ctx->device, cudaGetErrorString(e));
+    return PCL_OK;
+}
+
+// error_probability (precellar/src/barcode.rs:464-468) with the host libm, as the reference does.
+double error_probability(int q) { return std::pow(10.0, -(((double)q - 33.0) / 10.0)); }
+
+void prof_begin(pcl_ctx *ctx, cudaStream_t s, int k) {
+    ctx->launches += 1;
+    if (!ctx->profile) return;
+    EvPair p;
+    cudaEventCreate(&p.a);
+    cudaEventCreate(&p.b);
+    p.k = k;
+    cudaEventRecord(p.a, s);
+    ctx->evs.push_back(p);
+}
+void prof_end(pcl_ctx *ctx, cudaStream_t s) {
+    if (!ctx->profile) return;
+    cudaEventRecord(ctx->evs.back().b, s);
+}
+
+int grid_for(const pcl_ctx *ctx, uint64_t n_threads_wanted, int blocks_per_sm) {
+    uint64_t blocks = (n_threads_wanted + PCL_BLOCK - 1) / PCL_BLOCK;
+    uint64_t cap = (uint64_t)ctx->sm_count * blocks_per_sm;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    return (int)blocks;
+}
+
+}  // namespace
+
+extern "C" {
+
+int pcl_abi_version(void) { return PCL_ABI_VERSION; }
+
+const char *pcl_last_error(const pcl_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_err.c_str(); }
+
+int pcl_device_count(void) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) return fail(nullptr, PCL_ERR_CUDA, "cudaGetDeviceCount: %s", cudaGetErrorString(e));
+    return n;
+}
+
+int pcl_ctx_create(pcl_ctx **out, int device) {
+    if (!out) return fail(nullptr, PCL_ERR_ARG, "out is NULL");
+    *out = nullptr;
+    int n = pcl_device_count();
+    if (n < 0) return n;
+    if (n == 0) return fail(nullptr, PCL_ERR_CUDA, "no CUDA device: this library has no CPU fallback");
+    if (device < 0 || device >= n) return fail(nullptr, PCL_ERR_ARG, "device %d out of range (0..%d)", device, n - 1);
+    cudaDeviceProp prop;
+    cudaError_t e = cudaGetDeviceProperties(&prop, device);
+    if (e != cudaSuccess) return fail(nullptr, PCL_ERR_CUDA, "cudaGetDeviceProperties: %s", cudaGetErrorString(e));
+    if (prop.major != 10)
+        return fail(nullptr, PCL_ERR_CUDA, "device %d is sm_%d%d; this build contains sm_100a code only", device, prop.major, prop.minor);
+    pcl_ctx *ctx = new pcl_ctx();
+    ctx->device = device;
+    ctx->sm_count = prop.multiProcessorCount;
+    memset(ctx->descs, 0, sizeof ctx->descs);
+    memset(ctx->dreads, 0, sizeof ctx->dreads);
+    memset(ctx->infos, 0, sizeof ctx->infos);
+    auto bail = [&](const char *what, cudaError_t ce) {
+        fail(nullptr, PCL_ERR_CUDA, "%s: %s", what, cudaGetErrorString(ce));
+        delete ctx;
+        return PCL_ERR_CUDA;
+    };
+    if ((e = cudaSetDevice(device)) != cudaSuccess) return bail("cudaSetDevice", e);
+    if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", e);
+    if ((e = cudaEventCreateWithFlags(&ctx->ev_reduced, cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", e);
+    if ((e = cudaMalloc(&ctx->d_lut, 512 * sizeof(double))) != cudaSuccess) return bail("cudaMalloc", e);
+    if ((e = cudaMalloc(&ctx->d_qc, PCL_MAX_READS * sizeof(unsigned long long))) != cudaSuccess) return bail("cudaMalloc", e);
+    double lut[512];
+    for (int q = 0; q < 256; ++q) {
+        lut[q] = error_probability(q < 66 ? q : 66);     // BC_MAX_QV cap (barcode.rs:18,320)
+        lut[256 + q] = error_probability(q);
+    }
+    if ((e = cudaMemcpy(ctx->d_lut, lut, sizeof lut, cudaMemcpyHostToDevice)) != cudaSuccess) return bail("cudaMemcpy", e);
+    if ((e = cudaMemset(ctx->d_qc, 0, PCL_MAX_READS * sizeof(unsigned long long))) != cudaSuccess) return bail("cudaMemset", e);
+    *out = ctx;
+    return PCL_OK;
+}
+
+static void table_free(Table &t) {
+    if (t.d_keys) cudaFree(t.d_keys);
+    if (t.d_counts) cudaFree(t.d_counts);
+    if (t.d_index_to_slot) cudaFree(t.d_index_to_slot);
+    if (t.d_scalars) cudaFree(t.d_scalars);
+    t = Table();
+}
+
+int pcl_ctx_destroy(pcl_ctx *ctx) {
+    if (!ctx) return PCL_OK;
+    cudaSetDevice(ctx->device);
+    cudaDeviceSynchronize();
+    while (!ctx->chunks.empty()) pcl_chunk_destroy(ctx->chunks.back());
+    for (Table &t : ctx->tables) table_free(t);
+    for (EvPair &p : ctx->evs) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
+    if (ctx->comm && nccl().ok) nccl().CommDestroy(ctx->comm);
+    if (ctx->d_lut) cudaFree(ctx->d_lut);
+    if (ctx->d_qc) cudaFree(ctx->d_qc);
+    if (ctx->ev_reduced) cudaEventDestroy(ctx->ev_reduced);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+    return PCL_OK;
+}
+
+int pcl_sync(pcl_ctx *ctx) {
+    if (!ctx) return PCL_ERR_ARG;
+    if (int r = bind(ctx)) return r;
+    for (pcl_chunk *c : ctx->chunks) CU(ctx, cudaStreamSynchronize(c->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    return PCL_OK;
+}
+
+int pcl_comm_unique_id(void *uid128) {
+    if (!uid128) return fail(nullptr, PCL_ERR_ARG, "uid is NULL");
+    if (!nccl().ok) return fail(nullptr, PCL_ERR_NCCL, "libnccl.so.2 could not be loaded");
+    NcclUid id;
+    int r = nccl().GetUniqueId(&id);
+    if (r != 0) return fail(nullptr, PCL_ERR_NCCL, "ncclGetUniqueId: %d", r);
+    memcpy(uid128, &id, sizeof id);
+    return PCL_OK;
+}
+
+int pcl_comm_init(pcl_ctx *ctx, int nranks, int rank, const void *uid128) {
+    if (!ctx) return PCL_ERR_ARG;
+    if (nranks < 1 || rank < 0 || rank >= nranks) return fail(ctx, PCL_ERR_ARG, "bad nranks/rank");
+    ctx->nranks = nranks;
+    ctx->rank = rank;
+    if (nranks == 1) return PCL_OK;
+    if (!uid128) return fail(ctx, PCL_ERR_ARG, "uid is NULL");
+    if (!nccl().ok) return fail(ctx, PCL_ERR_NCCL, "libnccl.so.2 could not be loaded");
+    if (int r = bind(ctx)) return r;
+    NcclUid id;
+    memcpy(&id, uid128, sizeof id);
+    int r = nccl().CommInitRank(&ctx->comm, nranks, id, rank);
+    if (r != 0) return fail(ctx, PCL_ERR_NCCL, "ncclCommInitRank: %s", nccl().GetErrorString ? nccl().GetErrorString(r) : "?");
+    return PCL_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// layout
+// ------------------------------------------------------------------------------------------
+int pcl_layout_set(pcl_ctx *ctx, const pcl_read_desc *reads, int n_reads) {
+    if (!ctx || !reads) return PCL_ERR_ARG;
+    if (n_reads < 1 || n_reads > PCL_MAX_READS) return fail(ctx, PCL_ERR_UNSUPPORTED, "n_reads %d outside 1..%d", n_reads, PCL_MAX_READS);
+    if (!ctx->chunks.empty()) return fail(ctx, PCL_ERR_ARG, "layout cannot change while chunks exist");
+    for (int r = 0; r < n_reads; ++r) {
+        DRead d;
+        pcl_read_info info;
+        int rc = pcl_build_read(r, reads[r], &d, &info, ctx->bc_region[r], &ctx->err);
+        if (rc != PCL_OK) return rc;
+        ctx->descs[r] = reads[r];
+        ctx->dreads[r] = d;
+        ctx->infos[r] = info;
+    }
+    ctx->n_reads = n_reads;
+    return PCL_OK;
+}
+
+int pcl_read_info_get(const pcl_ctx *ctx, int read_slot, pcl_read_info *out) {
+    if (!ctx || !out || read_slot < 0 || read_slot >= ctx->n_reads) return PCL_ERR_ARG;
+    *out = ctx->infos[read_slot];
+    return PCL_OK;
+}
+
+uint32_t pcl_read_stride(const pcl_ctx *ctx, int read_slot) {
+    if (!ctx || read_slot < 0 || read_slot >= ctx->n_reads) return 0;
+    return ctx->dreads[read_slot].stride;
+}
+
+// ------------------------------------------------------------------------------------------
+// whitelist table
+// ------------------------------------------------------------------------------------------
+int pcl_whitelist_load(pcl_ctx *ctx, int region_slot, const uint8_t *bytes, const uint64_t *offsets, uint64_t n) {
+    if (!ctx || region_slot < 0 || region_slot >= PCL_MAX_REGIONS) return PCL_ERR_ARG;
+    if (n && (!bytes || !offsets)) return fail(ctx, PCL_ERR_ARG, "NULL whitelist buffers");
+    if (int r = bind(ctx)) return r;
+    if (n == 0)
+        return fail(ctx, PCL_ERR_UNSUPPORTED, "region %d has no whitelist: observed-barcode mode (precellar/src/barcode.rs:418-423) is not implemented on the device", region_slot);
+    HostTable ht;
+    if (int rc = pcl_build_table(bytes, offsets, n, &ht, &ctx->err)) return rc;
+    Table &t = ctx->tables[region_slot];
+    table_free(t);
+    const uint64_t m = ht.n_entries, n_slots = ht.n_slots;
+    const size_t key_bytes = ht.key_bytes();
+    CU(ctx, cudaMalloc(&t.d_keys, n_slots * key_bytes));
+    CU(ctx, cudaMalloc(&t.d_counts, n_slots * sizeof(uint32_t)));
+    CU(ctx, cudaMalloc(&t.d_index_to_slot, m * sizeof(uint32_t)));
+    CU(ctx, cudaMalloc(&t.d_scalars, 2 * sizeof(unsigned long long)));
+    CU(ctx, cudaMemcpy(t.d_keys, ht.data(), n_slots * key_bytes, cudaMemcpyHostToDevice));
+    CU(ctx, cudaMemcpy(t.d_index_to_slot, ht.index_to_slot.data(), m * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    CU(ctx, cudaMemset(t.d_counts, 0, n_slots * sizeof(uint32_t)));
+    CU(ctx, cudaMemset(t.d_scalars, 0, 2 * sizeof(unsigned long long)));
+    t.d.keys = t.d_keys;
+    t.d.counts = t.d_counts;
+    t.d.total = t.d_scalars;
+    t.d.mismatch = t.d_scalars + 1;
+    t.d.empty = ht.empty;
+    t.d.n_buckets = (uint32_t)ht.n_buckets;
+    t.d.mode = ht.mode;
+    t.n_entries = m;
+    t.n_slots = n_slots;
+    t.loaded = true;
+    return PCL_OK;
+}
+
+uint64_t pcl_whitelist_size(const pcl_ctx *ctx, int region_slot) {
+    if (!ctx || region_slot < 0 || region_slot >= PCL_MAX_REGIONS) return 0;
+    return ctx->tables[region_slot].n_entries;
+}
+
+// ------------------------------------------------------------------------------------------
+// chunks
+// ------------------------------------------------------------------------------------------
+static int chunk_alloc(pcl_chunk *c, void **p, size_t bytes) {
+    if (bytes == 0) bytes = 16;
+    cudaError_t e = cudaMalloc(p, bytes);
+    if (e != cudaSuccess) return fail(c->ctx, e == cudaErrorMemoryAllocation ? PCL_ERR_NOMEM : PCL_ERR_CUDA, "cudaMalloc(%zu): %s", bytes, cudaGetErrorString(e));
+    c->allocs.push_back(*p);
+    return PCL_OK;
+}
+
+int pcl_chunk_create(pcl_ctx *ctx, uint64_t capacity_records, pcl_chunk **out) {
+    if (!ctx || !out) return PCL_ERR_ARG;
+    *out = nullptr;
+    if (ctx->n_reads == 0) return fail(ctx, PCL_ERR_ARG, "pcl_layout_set must be called first");
+    if (capacity_records == 0 || capacity_records >= (1ull << 32)) return fail(ctx, PCL_ERR_ARG, "capacity must be in 1..2^32-1");
+    if (int r = bind(ctx)) return r;
+    pcl_chunk *c = new pcl_chunk();
+    c->ctx = ctx;
+    c->cap = capacity_records;
+    const uint64_t cap = capacity_records;
+    int rc = PCL_OK;
+    auto A = [&](void **p, size_t bytes) { if (rc == PCL_OK) rc = chunk_alloc(c, p, bytes); };
+    if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&c->ev, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreate(&c->t0) != cudaSuccess || cudaEventCreate(&c->t1) != cudaSuccess)
+        rc = fail(ctx, PCL_ERR_CUDA, "stream/event creation failed: %s", cudaGetErrorString(cudaGetLastError()));
+    for (int r = 0; r < ctx->n_reads && rc == PCL_OK; ++r) {
+        const DRead &d = ctx->dreads[r];
+        const pcl_read_info &inf = ctx->infos[r];
+        ReadBuf &b = c->rb[r];
+        if (d.needs_payload) {
+            A((void **)&b.seq, cap * d.stride);
+            A((void **)&b.qual, cap * d.stride);
+        }
+        A((void **)&b.len, cap * 2 + 16);
+        A((void **)&b.fstatus, cap * 2 + 16);
+        if (inf.has_target) A((void **)&b.tcoord, cap * 4);
+        for (int j = 0; j < inf.n_bc; ++j) {
+            A(&b.bc_key[j], cap * inf.bc_key_bytes[j]);
+            if (!inf.fixed_layout) A((void **)&b.bcoord[j], cap * 4);
+        }
+        for (int j = 0; j < inf.n_umi; ++j) {
+            A(&b.umi_key[j], cap * inf.umi_key_bytes[j]);
+            if (!inf.fixed_layout) A((void **)&b.ucoord[j], cap * 4);
+        }
+        if (inf.n_bc) A((void **)&b.worklist, cap * inf.n_bc * 8);
+        A((void **)&b.wl_count, 16);
+    }
+    if (rc != PCL_OK) {
+        for (void *p : c->allocs) cudaFree(p);
+        if (c->stream) cudaStreamDestroy(c->stream);
+        delete c;
+        return rc;
+    }
+    ctx->chunks.push_back(c);
+    *out = c;
+    return PCL_OK;
+}
+
+int pcl_chunk_destroy(pcl_chunk *c) {
+    if (!c) return PCL_OK;
+    pcl_ctx *ctx = c->ctx;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(c->stream);
+    for (void *p : c->allocs) cudaFree(p);
+    cudaEventDestroy(c->ev); cudaEventDestroy(c->t0); cudaEventDestroy(c->t1);
+    cudaStreamDestroy(c->stream);
+    for (size_t i = 0; i < ctx->chunks.size(); ++i)
+        if (ctx->chunks[i] == c) { ctx->chunks.erase(ctx->chunks.begin() + i); break; }
+    delete c;
+    return PCL_OK;
+}
+
+int pcl_chunk_reset(pcl_chunk *c, uint64_t n_records) {
+    if (!c) return PCL_ERR_ARG;
+    if (n_records > c->cap) return fail(c->ctx, PCL_ERR_ARG, "n_records %llu exceeds chunk capacity %llu", (unsigned long long)n_records, (unsigned long long)c->cap);
+    c->n = n_records;
+    for (int r = 0; r < c->ctx->n_reads; ++r) c->rb[r].filled = false;
+    return PCL_OK;
+}
+
+int pcl_chunk_upload(pcl_chunk *c, int read_slot, const uint8_t *seq, const uint8_t *qual, const uint16_t *len) {
+    if (!c) return PCL_ERR_ARG;
+    pcl_ctx *ctx = c->ctx;
+    if (read_slot < 0 || read_slot >= ctx->n_reads) return fail(ctx, PCL_ERR_ARG, "bad read_slot");
+    if (!len) return fail(ctx, PCL_ERR_ARG, "len is NULL");
+    if (int r = bind(ctx)) return r;
+    const DRead &d = ctx->dreads[read_slot];
+    ReadBuf &b = c->rb[read_slot];
+    if (d.needs_payload) {
+        if (!seq || !qual) return fail(ctx, PCL_ERR_ARG, "read %d needs seq and qual planes", read_slot);
+        CU(ctx, cudaMemcpyAsync(b.seq, seq, c->n * d.stride, cudaMemcpyHostToDevice, c->stream));
+        CU(ctx, cudaMemcpyAsync(b.qual, qual, c->n * d.stride, cudaMemcpyHostToDevice, c->stream));
+    }
+    CU(ctx, cudaMemcpyAsync(b.len, len, c->n * 2, cudaMemcpyHostToDevice, c->stream));
+    b.filled = true;
+    return PCL_OK;
+}
+
+int pcl_chunk_device_ptrs(pcl_chunk *c, int read_slot, void **seq, void **qual, void **len) {
+    if (!c) return PCL_ERR_ARG;
+    if (read_slot < 0 || read_slot >= c->ctx->n_reads) return fail(c->ctx, PCL_ERR_ARG, "bad read_slot");
+    ReadBuf &b = c->rb[read_slot];
+    if (seq) *seq = b.seq;
+    if (qual) *qual = b.qual;
+    if (len) *len = b.len;
+    b.filled = true;
+    return PCL_OK;
+}
+
+void *pcl_chunk_stream(pcl_chunk *c) { return c ? (void *)c->stream : nullptr; }
+
+// ------------------------------------------------------------------------------------------
+// stages
+// ------------------------------------------------------------------------------------------
+int pcl_counts_reset(pcl_ctx *ctx) {
+    if (!ctx) return PCL_ERR_ARG;
+    if (int r = bind(ctx)) return r;
+    if (int r = pcl_sync(ctx)) return r;
+    for (Table &t : ctx->tables) {
+        if (!t.loaded) continue;
+        CU(ctx, cudaMemset(t.d_counts, 0, t.n_slots * sizeof(uint32_t)));
+        CU(ctx, cudaMemset(t.d_scalars, 0, 2 * sizeof(unsigned long long)));
+    }
+    CU(ctx, cudaMemset(ctx->d_qc, 0, PCL_MAX_READS * sizeof(unsigned long long)));
+    memset(ctx->qc_reads, 0, sizeof ctx->qc_reads);
+    return PCL_OK;
+}
+
+static int check_ready(pcl_ctx *ctx, pcl_chunk *c) {
+    if (!ctx || !c || c->ctx != ctx) return PCL_ERR_ARG;
+    for (int r = 0; r < ctx->n_reads; ++r) {
+        if (!c->rb[r].filled) return fail(ctx, PCL_ERR_INPUT, "read %d of the chunk has no data (Unequal number of reads in the chunk)", r);
+        for (int j = 0; j < ctx->infos[r].n_bc; ++j)
+            if (!ctx->tables[ctx->bc_region[r][j]].loaded)
+                return fail(ctx, PCL_ERR_ARG, "whitelist of region %d not loaded", ctx->bc_region[r][j]);
+    }
+    return PCL_OK;
+}
+
+int pcl_count(pcl_ctx *ctx, pcl_chunk *c) {
+    if (int r = check_ready(ctx, c)) return r;
+    if (int r = bind(ctx)) return r;
+    if (c->n == 0) return PCL_OK;
+    for (int r = 0; r < ctx->n_reads; ++r) {
+        const pcl_read_info &inf = ctx->infos[r];
+        ReadBuf &b = c->rb[r];
+        CountParams p;
+        memset(&p, 0, sizeof p);
+        p.rd = ctx->dreads[r];
+        for (int j = 0; j < inf.n_bc; ++j) {
+            p.tab[j] = ctx->tables[ctx->bc_region[r][j]].d;
+            p.bc_key[j] = b.bc_key[j]; p.bcoord[j] = b.bcoord[j];
+            p.bc_key_bytes[j] = inf.bc_key_bytes[j]; p.bc_elem[j] = inf.bc_elem[j];
+        }
+        for (int j = 0; j < inf.n_umi; ++j) {
+            p.umi_key[j] = b.umi_key[j]; p.ucoord[j] = b.ucoord[j];
+            p.umi_key_bytes[j] = inf.umi_key_bytes[j]; p.umi_elem[j] = inf.umi_elem[j];
+        }
+        p.seq = b.seq; p.len = b.len; p.n = c->n;
+        p.fstatus = b.fstatus; p.tcoord = b.tcoord;
+        p.worklist = b.worklist; p.wl_count = b.wl_count;
+        p.num_defect = ctx->d_qc + r;
+        CU(ctx, cudaMemsetAsync(b.wl_count, 0, sizeof(unsigned long long), c->stream));
+        const int grid = grid_for(ctx, c->n, 6);
+        prof_begin(ctx, c->stream, PCL_K_COUNT);
+        k_count<<<grid, PCL_BLOCK, 0, c->stream>>>(p);
+        prof_end(ctx, c->stream);
+        CU(ctx, cudaGetLastError());
+        ctx->qc_reads[r] += c->n;
+    }
+    return PCL_OK;
+}
+
+int pcl_counts_allreduce(pcl_ctx *ctx) {
+    if (!ctx) return PCL_ERR_ARG;
+    if (int r = bind(ctx)) return r;
+    // ctx stream waits for every chunk's count pass ...
+    for (pcl_chunk *c : ctx->chunks) {
+        CU(ctx, cudaEventRecord(c->ev, c->stream));
+        CU(ctx, cudaStreamWaitEvent(ctx->stream, c->ev, 0));
+    }
+    if (ctx->nranks > 1) {
+        if (!ctx->comm) return fail(ctx, PCL_ERR_NCCL, "communicator not initialised");
+        NcclApi &n = nccl();
+        n.GroupStart();
+        for (Table &t : ctx->tables) {
+            if (!t.loaded) continue;
+            int r1 = n.AllReduce(t.d_counts, t.d_counts, t.n_slots, kNcclUint32, kNcclSum, ctx->comm, ctx->stream);
+            int r2 = n.AllReduce(t.d_scalars, t.d_scalars, 2, kNcclUint64, kNcclSum, ctx->comm, ctx->stream);
+            if (r1 || r2) { n.GroupEnd(); return fail(ctx, PCL_ERR_NCCL, "ncclAllReduce failed (%d,%d)", r1, r2); }
+        }
+        int r = n.GroupEnd();
+        if (r) return fail(ctx, PCL_ERR_NCCL, "ncclGroupEnd: %d", r);
+    }
+    // ... and every chunk's later work waits for the reduced counts
+    CU(ctx, cudaEventRecord(ctx->ev_reduced, ctx->stream));
+    for (pcl_chunk *c : ctx->chunks) CU(ctx, cudaStreamWaitEvent(c->stream, ctx->ev_reduced, 0));
+    return PCL_OK;
+}
+
+int pcl_correct(pcl_ctx *ctx, pcl_chunk *c, double threshold, double max_expected_errors) {
+    if (int r = check_ready(ctx, c)) return r;
+    if (int r = bind(ctx)) return r;
+    if (c->n == 0) return PCL_OK;
+    const bool check_ee = max_expected_errors < DBL_MAX;
+    for (int r = 0; r < ctx->n_reads; ++r) {
+        const pcl_read_info &inf = ctx->infos[r];
+        if (inf.n_bc == 0) continue;
+        ReadBuf &b = c->rb[r];
+        CorrectParams p;
+        memset(&p, 0, sizeof p);
+        p.rd = ctx->dreads[r];
+        for (int j = 0; j < inf.n_bc; ++j) {
+            p.tab[j] = ctx->tables[ctx->bc_region[r][j]].d;
+            p.bc_key[j] = b.bc_key[j]; p.bcoord[j] = b.bcoord[j];
+            p.bc_key_bytes[j] = inf.bc_key_bytes[j]; p.bc_elem[j] = inf.bc_elem[j];
+        }
+        memcpy(p.static_start, inf.static_start, sizeof p.static_start);
+        p.seq = b.seq; p.qual = b.qual; p.len = b.len; p.n = c->n;
+        p.fstatus = b.fstatus;
+        p.worklist = b.worklist; p.wl_count = b.wl_count;
+        p.lut_cap = ctx->d_lut; p.lut_raw = ctx->d_lut + 256;
+        p.threshold = threshold; p.max_expected_errors = max_expected_errors; p.check_ee = check_ee;
+        if (check_ee) {
+            CU(ctx, cudaMemsetAsync(b.wl_count, 0, sizeof(unsigned long long), c->stream));
+            ctx->launches += 1;
+            k_enum_all<<<grid_for(ctx, c->n, 8), PCL_BLOCK, 0, c->stream>>>(p);
+            CU(ctx, cudaGetLastError());
+        }
+        // the worklist size lives on the device; size the grid for the worst case and let idle CTAs exit
+        const int grid = grid_for(ctx, check_ee ? c->n * inf.n_bc : (c->n * inf.n_bc + 3) / 4, 8);
+        prof_begin(ctx, c->stream, PCL_K_CORRECT);
+        k_correct<<<grid, PCL_BLOCK, 0, c->stream>>>(p);
+        prof_end(ctx, c->stream);
+        CU(ctx, cudaGetLastError());
+    }
+    return PCL_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// outputs
+// ------------------------------------------------------------------------------------------
+int pcl_chunk_fetch(pcl_chunk *c, int read_slot, const pcl_read_results *out) {
+    if (!c || !out) return PCL_ERR_ARG;
+    pcl_ctx *ctx = c->ctx;
+    if (read_slot < 0 || read_slot >= ctx->n_reads) return fail(ctx, PCL_ERR_ARG, "bad read_slot");
+    if (int r = bind(ctx)) return r;
+    const pcl_read_info &inf = ctx->infos[read_slot];
+    ReadBuf &b = c->rb[read_slot];
+    const uint64_t n = c->n;
+    auto D2H = [&](void *dst, const void *src, size_t bytes) -> cudaError_t {
+        if (!dst || !src || !bytes) return cudaSuccess;
+        return cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, c->stream);
+    };
+    CU(ctx, D2H(out->fstatus, b.fstatus, n * 2));
+    if (inf.has_target) CU(ctx, D2H(out->tcoord, b.tcoord, n * 4));
+    for (int j = 0; j < inf.n_bc; ++j) {
+        CU(ctx, D2H(out->bc_key[j], b.bc_key[j], n * inf.bc_key_bytes[j]));
+        if (!inf.fixed_layout) CU(ctx, D2H(out->bcoord[j], b.bcoord[j], n * 4));
+    }
+    for (int j = 0; j < inf.n_umi; ++j) {
+        CU(ctx, D2H(out->umi_key[j], b.umi_key[j], n * inf.umi_key_bytes[j]));
+        if (!inf.fixed_layout) CU(ctx, D2H(out->ucoord[j], b.ucoord[j], n * 4));
+    }
+    CU(ctx, cudaStreamSynchronize(c->stream));
+    return PCL_OK;
+}
+
+int pcl_counts_fetch(pcl_ctx *ctx, int region_slot, uint64_t *counts, uint64_t *mismatch, uint64_t *total) {
+    if (!ctx || region_slot < 0 || region_slot >= PCL_MAX_REGIONS) return PCL_ERR_ARG;
+    Table &t = ctx->tables[region_slot];
+    if (!t.loaded) return fail(ctx, PCL_ERR_ARG, "whitelist of region %d not loaded", region_slot);
+    if (int r = pcl_sync(ctx)) return r;
+    if (counts && t.n_entries) {
+        unsigned long long *d_out = nullptr;
+        CU(ctx, cudaMalloc(&d_out, t.n_entries * sizeof(unsigned long long)));
+        ctx->launches += 1;
+        k_gather_counts<<<grid_for(ctx, t.n_entries, 8), PCL_BLOCK, 0, ctx->stream>>>(t.d_counts, t.d_index_to_slot, d_out, t.n_entries);
+        cudaError_t e = cudaMemcpyAsync(counts, d_out, t.n_entries * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+        cudaFree(d_out);
+        if (e != cudaSuccess) return fail(ctx, PCL_ERR_CUDA, "counts fetch: %s", cudaGetErrorString(e));
+    }
+    unsigned long long sc[2];
+    CU(ctx, cudaMemcpy(sc, t.d_scalars, sizeof sc, cudaMemcpyDeviceToHost));
+    if (total) *total = sc[0];
+    if (mismatch) *mismatch = sc[1];
+    return PCL_OK;
+}
+
+int pcl_qc_fetch(pcl_ctx *ctx, uint64_t *per_read) {
+    if (!ctx || !per_read) return PCL_ERR_ARG;
+    if (int r = pcl_sync(ctx)) return r;
+    unsigned long long d[PCL_MAX_READS];
+    CU(ctx, cudaMemcpy(d, ctx->d_qc, sizeof d, cudaMemcpyDeviceToHost));
+    for (int r = 0; r < ctx->n_reads; ++r) { per_read[2 * r] = ctx->qc_reads[r]; per_read[2 * r + 1] = d[r]; }
+    return PCL_OK;
+}
+
+int pcl_key_decode(uint64_t key, char *out32) {
+    if (!out32 || key == 0 || key == PCL_KEY_ABSENT64) return -1;
+    int top = 63;
+    while (top >= 0 && !((key >> top) & 1ull)) --top;
+    if (top & 1) return -1;                      // marker must sit on an even bit
+    int L = top / 2;
+    static const char B[4] = {'A', 'C', 'G', 'T'};
+    for (int p = 0; p < L; ++p) out32[p] = B[(key >> (2 * (L - 1 - p))) & 3ull];
+    out32[L] = 0;
+    return L;
+}
+
+void *pcl_host_alloc(uint64_t bytes) {
+    void *p = nullptr;
+    if (cudaHostAlloc(&p, bytes ? bytes : 16, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return p;
+}
+void pcl_host_free(void *p) { if (p) cudaFreeHost(p); }
+
+// ------------------------------------------------------------------------------------------
+// instrumentation
+// ------------------------------------------------------------------------------------------
+int pcl_profile_enable(pcl_ctx *ctx, int on) {
+    if (!ctx) return PCL_ERR_ARG;
+    ctx->profile = on != 0;
+    return PCL_OK;
+}
+
+static int prof_drain(pcl_ctx *ctx) {
+    if (int r = pcl_sync(ctx)) return r;
+    for (EvPair &p : ctx->evs) {
+        float ms = 0;
+        if (cudaEventElapsedTime(&ms, p.a, p.b) == cudaSuccess) { ctx->prof_ms[p.k] += ms; ctx->prof_n[p.k] += 1; }
+        cudaEventDestroy(p.a);
+        cudaEventDestroy(p.b);
+    }
+    ctx->evs.clear();
+    return PCL_OK;
+}
+
+int pcl_profile_get(pcl_ctx *ctx, int k, double *ms, uint64_t *launches) {
+    if (!ctx || k < 0 || k >= PCL_K_MAX) return PCL_ERR_ARG;
+    if (int r = prof_drain(ctx)) return r;
+    if (ms) *ms = ctx->prof_ms[k];
+    if (launches) *launches = ctx->prof_n[k];
+    return PCL_OK;
+}
+
+int pcl_profile_reset(pcl_ctx *ctx) {
+    if (!ctx) return PCL_ERR_ARG;
+    if (int r = prof_drain(ctx)) return r;
+    for (int k = 0; k < PCL_K_MAX; ++k) { ctx->prof_ms[k] = 0; ctx->prof_n[k] = 0; }
+    return PCL_OK;
+}
+
+uint64_t pcl_launch_count(const pcl_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+int pcl_timer_start(pcl_chunk *c) {
+    if (!c) return PCL_ERR_ARG;
+    if (int r = bind(c->ctx)) return r;
+    CU(c->ctx, cudaEventRecord(c->t0, c->stream));
+    return PCL_OK;
+}
+
+int pcl_timer_stop_ms(pcl_chunk *c, double *ms) {
+    if (!c || !ms) return PCL_ERR_ARG;
+    if (int r = bind(c->ctx)) return r;
+    CU(c->ctx, cudaEventRecord(c->t1, c->stream));
+    CU(c->ctx, cudaEventSynchronize(c->t1));
+    float f = 0;
+    CU(c->ctx, cudaEventElapsedTime(&f, c->t0, c->t1));
+    *ms = f;
+    return PCL_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,174 @@
+// emul.cpp -- CPU-side unit-test harness for the __host__ __device__ logic in
+// precellar_b200/csrc/hd_core.h and host_build.h.
+//
+// TEST INFRASTRUCTURE ONLY.  It runs the per-record functions the CUDA kernels wrap (pcl_split,
+// pcl_pack_key, pcl_probe, pcl_correct_one) record by record on the host so that their logic can be
+// checked against the oracle in the CPU-only test tier.  It is not part of the product library and
+// nothing in precellar_b200/ links or loads it.
+#include <cfloat>
+#include <cmath>
+#include <string>
+#include <vector>
+
+#include "../../precellar_b200/csrc/host_build.h"
+
+extern "C" {
+
+int emu_read_info(const pcl_read_desc *rd, pcl_read_info *info, uint32_t *stride, char *err, int errcap) {
+    DRead d;
+    int bcr[PCL_MAX_BC_PER_READ];
+    std::string e;
+    int rc = pcl_build_read(0, *rd, &d, info, bcr, &e);
+    if (rc != PCL_OK) { snprintf(err, errcap, "%s", e.c_str()); return rc; }
+    *stride = d.stride;
+    return PCL_OK;
+}
+
+struct emu_read_io {
+    const uint8_t *seq, *qual;
+    const uint16_t *len;
+    uint16_t *fstatus;
+    uint32_t *tcoord;
+    void *bc_key[PCL_MAX_BC_PER_READ];
+    void *umi_key[PCL_MAX_UMI_PER_READ];
+    uint32_t *bcoord[PCL_MAX_BC_PER_READ];
+    uint32_t *ucoord[PCL_MAX_UMI_PER_READ];
+};
+
+// counts_out[region]: n_entries values in whitelist order; scalars_out: total, mismatch per region;
+// defects_out: per read.
+int emu_run(const pcl_read_desc *reads, int n_reads, int n_regions, const uint8_t **wl_bytes, const uint64_t **wl_offs,
+            const uint64_t *wl_n, emu_read_io *io, uint64_t n, int correct, double threshold, double max_ee,
+            uint64_t **counts_out, uint64_t *scalars_out, uint64_t *defects_out, char *err, int errcap) {
+    std::string e;
+    std::vector<HostTable> ht(n_regions);
+    std::vector<std::vector<uint32_t>> counts(n_regions);
+    std::vector<unsigned long long> scal(2 * n_regions, 0);
+    std::vector<DTable> dt(n_regions);
+    for (int g = 0; g < n_regions; ++g) {
+        int rc = pcl_build_table(wl_bytes[g], wl_offs[g], wl_n[g], &ht[g], &e);
+        if (rc != PCL_OK) { snprintf(err, errcap, "%s", e.c_str()); return rc; }
+        counts[g].assign(ht[g].n_slots, 0);
+        dt[g].keys = ht[g].data();
+        dt[g].counts = counts[g].data();
+        dt[g].total = &scal[2 * g];
+        dt[g].mismatch = &scal[2 * g + 1];
+        dt[g].empty = ht[g].empty;
+        dt[g].n_buckets = (uint32_t)ht[g].n_buckets;
+        dt[g].mode = ht[g].mode;
+    }
+    double lut[512];
+    for (int q = 0; q < 256; ++q) {
+        lut[q] = std::pow(10.0, -(((double)(q < 66 ? q : 66) - 33.0) / 10.0));
+        lut[256 + q] = std::pow(10.0, -(((double)q - 33.0) / 10.0));
+    }
+    std::vector<DRead> dr(n_reads);
+    std::vector<pcl_read_info> inf(n_reads);
+    std::vector<std::vector<int>> bcr(n_reads, std::vector<int>(PCL_MAX_BC_PER_READ, -1));
+    for (int r = 0; r < n_reads; ++r) {
+        int rc = pcl_build_read(r, reads[r], &dr[r], &inf[r], bcr[r].data(), &e);
+        if (rc != PCL_OK) { snprintf(err, errcap, "%s", e.c_str()); return rc; }
+    }
+    struct Work { uint64_t rec; uint32_t start, len, j; };
+    std::vector<std::vector<Work>> work(n_reads);
+    // ---- pass 1 (mirrors k_count) ----
+    for (int r = 0; r < n_reads; ++r) {
+        const DRead &rd = dr[r];
+        const pcl_read_info &in = inf[r];
+        const bool rev = rd.is_reverse != 0;
+        defects_out[r] = 0;
+        for (uint64_t i = 0; i < n; ++i) {
+            uint32_t L = io[r].len[i];
+            if (rd.max_len && L > rd.max_len) L = rd.max_len;
+            const uint8_t *rec = io[r].seq ? io[r].seq + i * (uint64_t)rd.stride : nullptr;
+            SplitOut so;
+            pcl_split(rd, rec, L, so);
+            uint32_t fs = so.status;
+            const bool ok = so.status == PCL_SPLIT_OK;
+            if (so.status == PCL_SPLIT_ANCHOR_NOT_FOUND || so.status == PCL_SPLIT_PATTERN_MISMATCH) defects_out[r]++;
+            if (ok && so.tcoord != PCL_COORD_ABSENT) fs |= PCL_FSTATUS_TARGET;
+            if (rd.has_target) io[r].tcoord[i] = ok ? so.tcoord : PCL_COORD_ABSENT;
+            for (uint32_t j = 0; j < PCL_MAX_BC_PER_READ; ++j) {
+                if (j >= rd.n_bc) { fs |= PCL_BC_ABSENT << (4 + 3 * j); continue; }
+                const uint32_t c = ok ? so.seg[in.bc_elem[j]] : PCL_COORD_ABSENT;
+                if (!rd.fixed_layout) io[r].bcoord[j][i] = c;
+                uint32_t code = PCL_BC_ABSENT;
+                uint64_t key = 0;
+                if (c != PCL_COORD_ABSENT) {
+                    uint32_t ninv, ipos;
+                    key = pcl_pack_key(rec, c >> 16, c & 0xFFFFu, rev, &ninv, &ipos);
+                    DTable &t = dt[bcr[r][j]];
+                    uint32_t slot = 0xFFFFFFFFu;
+                    if (ninv == 0) slot = pcl_probe(t, key, c & 0xFFFFu);
+                    ++*t.total;
+                    if (slot != 0xFFFFFFFFu) { code = PCL_BC_EXACT; t.counts[slot]++; }
+                    else { code = PCL_BC_NO_MATCH; ++*t.mismatch; work[r].push_back({i, c >> 16, c & 0xFFFFu, j}); }
+                }
+                pcl_store_key(io[r].bc_key[j], in.bc_key_bytes[j], i, key);
+                fs |= code << (4 + 3 * j);
+            }
+            for (uint32_t j = 0; j < rd.n_umi; ++j) {
+                const uint32_t c = ok ? so.seg[in.umi_elem[j]] : PCL_COORD_ABSENT;
+                if (!rd.fixed_layout) io[r].ucoord[j][i] = c;
+                uint64_t key = PCL_KEY_ABSENT64;
+                if (c != PCL_COORD_ABSENT) {
+                    uint32_t ninv, ipos;
+                    key = pcl_pack_key(rec, c >> 16, c & 0xFFFFu, rev, &ninv, &ipos);
+                    if (ninv) key = 0;
+                }
+                pcl_store_key(io[r].umi_key[j], in.umi_key_bytes[j], i, key);
+            }
+            io[r].fstatus[i] = (uint16_t)fs;
+        }
+    }
+    // ---- pass 2 (mirrors k_enum_all + k_correct) ----
+    if (correct) {
+        const bool check_ee = max_ee < DBL_MAX;
+        for (int r = 0; r < n_reads; ++r) {
+            const DRead &rd = dr[r];
+            const pcl_read_info &in = inf[r];
+            if (!rd.n_bc) continue;
+            const bool rev = rd.is_reverse != 0;
+            if (check_ee) {
+                work[r].clear();
+                for (uint64_t i = 0; i < n; ++i) {
+                    uint32_t fs = io[r].fstatus[i];
+                    for (uint32_t j = 0; j < rd.n_bc; ++j) {
+                        uint32_t code = PCL_BC_CODE(fs, j);
+                        if (code != PCL_BC_EXACT && code != PCL_BC_NO_MATCH) continue;
+                        uint32_t c;
+                        if (rd.fixed_layout) {
+                            uint32_t el = in.bc_elem[j];
+                            uint32_t L = io[r].len[i];
+                            if (rd.max_len && L > rd.max_len) L = rd.max_len;
+                            uint32_t s = in.static_start[el], l = rd.elems[el].max_len;
+                            if (rd.elems[el].min_len != rd.elems[el].max_len) l = (s + l < L ? s + l : L) - s;
+                            c = (s << 16) | l;
+                        } else c = io[r].bcoord[j][i];
+                        work[r].push_back({i, c >> 16, c & 0xFFFFu, j});
+                    }
+                }
+            }
+            for (const Work &w : work[r]) {
+                const uint8_t *rec = io[r].seq + w.rec * (uint64_t)rd.stride;
+                const uint8_t *ql = io[r].qual + w.rec * (uint64_t)rd.stride;
+                uint32_t ninv, ipos;
+                uint64_t key = pcl_pack_key(rec, w.start, w.len, rev, &ninv, &ipos);
+                bool is_exact = PCL_BC_CODE((uint32_t)io[r].fstatus[w.rec], w.j) == PCL_BC_EXACT;
+                uint64_t out_key = 0;
+                uint32_t code = pcl_correct_one(dt[bcr[r][w.j]], key, w.len, ninv, ipos, ql, w.start, rev, is_exact, threshold,
+                                                max_ee, check_ee, lut, lut + 256, &out_key);
+                if (code == PCL_BC_CORRECTED) pcl_store_key(io[r].bc_key[w.j], in.bc_key_bytes[w.j], w.rec, out_key);
+                if (code != PCL_BC_EXACT && code != PCL_BC_NO_MATCH) io[r].fstatus[w.rec] |= (uint16_t)(code << (4 + 3 * w.j));
+            }
+        }
+    }
+    for (int g = 0; g < n_regions; ++g) {
+        for (uint64_t i = 0; i < ht[g].n_entries; ++i) counts_out[g][i] = counts[g][ht[g].index_to_slot[i]];
+        scalars_out[2 * g] = scal[2 * g];
+        scalars_out[2 * g + 1] = scal[2 * g + 1];
+    }
+    return PCL_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,156 @@
+"""CPU tier: the __host__ __device__ logic the kernels wrap (hd_core.h / host_build.h, run on the host by
+tests/emul) against the oracle, bit-exact, on randomised layouts and reads."""
+import numpy as np
+import pytest
+
+from oracle import pyoracle as O
+from precellar_b200 import _ffi
+from tests import util as U
+from tests.util import bc, cdna, gdna, linker, make_layout, poly, umi, var
+
+
+def _layouts(rng):
+    wl16 = U.gen_whitelist(rng, 300, 16)
+    wl_hp = U.gen_whitelist(rng, 120, [9, 10])
+    wl_rt = U.gen_whitelist(rng, 96, 10)
+    wl8a, wl8b, wl8c = (U.gen_whitelist(rng, 48, 8) for _ in range(3))
+    wl24 = U.gen_whitelist(rng, 200, 24)
+    wl7 = U.gen_whitelist(rng, 64, 7)
+    out = {}
+    # 10x v3: R1 [B16 U12], R2 [cDNA 1-1000] neg
+    out["v3"] = make_layout([
+        dict(read_id="R1", elems=[bc("cb", 16), umi(12)], max_len=28),
+        dict(read_id="R2", elems=[cdna(1, 1000)], is_reverse=True, max_len=91)], {"cb": wl16})
+    # 10x ATAC: I2 [B16] neg, R1/R2 gdna
+    out["atac"] = make_layout([
+        dict(read_id="R1", elems=[gdna(1, 1000)], max_len=50),
+        dict(read_id="I2", elems=[bc("cb", 16)], is_reverse=True, max_len=16),
+        dict(read_id="R2", elems=[gdna(1, 1000)], is_reverse=True, max_len=50)], {"cb": wl16}, "atac")
+    # multiome ATAC: I2 [O8 fixed, B16] neg
+    out["multiome_atac"] = make_layout([
+        dict(read_id="R1", elems=[gdna(1, 1000)], max_len=50),
+        dict(read_id="I2", elems=[linker("CGCGTCTG"), bc("cb", 16)], is_reverse=True, max_len=24),
+        dict(read_id="R2", elems=[gdna(1, 1000)], is_reverse=True, max_len=50)], {"cb": wl16}, "atac")
+    # sci-RNA-seq3: R1 [B 9-10, O6 "CAGAGC", U8, B10], R2 [cdna]
+    out["sci3"] = make_layout([
+        dict(read_id="R1", elems=[bc("hp", 9, 10), linker("CAGAGC"), umi(8), bc("rt", 10)], max_len=34),
+        dict(read_id="R2", elems=[cdna(1, 1000)], is_reverse=True, max_len=100)], {"hp": wl_hp, "rt": wl_rt})
+    # SHARE-seq-like: three 8-mers separated by fixed linkers, one read; forward
+    out["share"] = make_layout([
+        dict(read_id="R1", elems=[gdna(1, 1000)], max_len=40),
+        dict(read_id="I1", elems=[bc("b1", 8), linker("ACGTACGTACGTACG"), bc("b2", 8), linker("TTGGCCAATTGGCCA"), bc("b3", 8)], max_len=54)],
+        {"b1": wl8a, "b2": wl8b, "b3": wl8c}, "atac")
+    # dscATAC-like: phase block 0-4 nt, 7-mers around anchors, then the insert in the same read
+    out["dsc"] = make_layout([
+        dict(read_id="R1", elems=[var(0, 4, "phase"), bc("b1", 7), linker("TATGCATGAC"), bc("b2", 7), linker("AGTCACTGAG"),
+                                  bc("b3", 7), linker("TCGTCGGCAGCGTC"), gdna(1, 1000)], max_len=100),
+        dict(read_id="R2", elems=[gdna(1, 1000)], is_reverse=True, max_len=60)],
+        {"b1": wl7, "b2": wl7[:40], "b3": wl7[10:]}, "atac")
+    # long barcode (64-bit keys), UMI of 16 (64-bit), reverse strand with a variable run and an anchor
+    out["k64_rev"] = make_layout([
+        dict(read_id="R1", elems=[bc("cb", 24), umi(16)], max_len=40),
+        dict(read_id="R2", elems=[var(1, 3), linker("GATTACA"), umi(5, "umi2"), cdna(1, 200)], is_reverse=True, max_len=80)],
+        {"cb": wl24})
+    # two UMI elements in one read (the later one wins inside a file), UMI in a second file too, targets both strands
+    out["multi_umi"] = make_layout([
+        dict(read_id="R1", elems=[umi(4, "u1"), bc("cb", 16), umi(6, "u2"), cdna(2, 30)], max_len=60),
+        dict(read_id="R2", elems=[umi(3, "u3"), gdna(1, 100)], is_reverse=True, max_len=40)], {"cb": wl16})
+    # the reference's own vector layouts (segment.rs:687-705) with a barcode whitelist
+    wl4, wl2 = U.gen_whitelist(rng, 40, 4), U.gen_whitelist(rng, 10, 2)
+    out["vec11"] = make_layout([
+        dict(read_id="R1", elems=[bc("b4", 4), var(1, 3), umi(2), linker("ACTGG"), var(2, 4, "v2"), bc("b2a", 2), linker("GGGG", "l2"),
+                                  var(2, 4, "v3"), bc("b2b", 2), linker("GGGG", "l3"), cdna(1, 100)], max_len=0)],
+        {"b4": wl4, "b2a": wl2, "b2b": wl2[:7]})
+    # joined remainder [TO], the same whitelist used by two elements, and a trailing variable barcode
+    out["joined"] = make_layout([
+        dict(read_id="R1", elems=[bc("b4", 4), umi(2), cdna(2, 10), poly(2, 10), bc("b4", 4), umi(2, "u2")], max_len=0),
+        dict(read_id="R2", elems=[umi(3, "u3"), bc("b4", 3, 5)], max_len=0)],
+        {"b4": wl4})
+    return out
+
+
+@pytest.fixture(scope="module")
+def layouts():
+    return _layouts(np.random.default_rng(20240607))
+
+
+NAMES = ["v3", "atac", "multiome_atac", "sci3", "share", "dsc", "k64_rev", "multi_umi", "vec11", "joined"]
+
+
+@pytest.mark.parametrize("name", NAMES)
+@pytest.mark.parametrize("mode", ["correct", "nocorrect", "ee", "lower"])
+def test_emul_matches_oracle(layouts, name, mode):
+    layout = layouts[name]
+    rng = np.random.default_rng(abs(hash((name, mode))) % (2 ** 31))
+    infos, strides = U.emul_infos(layout)
+    n = 700
+    # the reference asserts equal totals across whitelists (barcode.rs:126-129): with several barcode
+    # regions only reads too short for every barcode may be truncated
+    multi = len(layout.region_ids) > 1
+    full = U.gen_reads(rng, layout, n, strides, p_lower=0.02 if mode == "lower" else 0.0,
+                       p_short=0.0 if multi else 0.03, p_tiny=0.03 if multi else 0.0)
+    dev = U.narrow(full, strides)
+    kw = dict(correct=mode != "nocorrect", threshold=0.975 if mode != "lower" else 0.6,
+              max_expected_errors=1.5 if mode == "ee" else _ffi.F64_MAX)
+    infos, results, counts, defects = U.run_emul(layout, dev, **kw)
+    ores, ocounts = U.run_oracle(layout, full, **kw)
+    g = U.compare_with_oracle(layout, infos, full, results, counts, defects, ores, ocounts, correct=kw["correct"])
+    # the test data must exercise the interesting branches
+    codes = np.concatenate([b["code"] for b in g.bc])
+    assert (codes == _ffi.BC_EXACT).any() and (codes == _ffi.BC_ABSENT).any()
+    if mode == "correct":
+        assert (codes == _ffi.BC_CORRECTED).any() and (codes == _ffi.BC_NO_MATCH).any()
+    if mode == "ee":
+        assert (codes == _ffi.BC_EXCEED_EE).any()
+
+
+def test_reference_vectors_through_device_split():
+    """The 11 known-answer vectors of segment.rs:617-705 through pcl_split (element coordinates)."""
+    from tests.test_oracle_golden import GOLDEN
+    for read, oelems, expected in GOLDEN:
+        seq = "".join(read.split()).encode()
+        elems, wls = [], {}
+        for k, e in enumerate(oelems):
+            rid = f"{e.region_id}{k}"
+            if e.rtype == O.BARCODE:                 # one shared whitelist: totals stay equal when a barcode is swallowed
+                elems.append(bc("wl", e.min_len, e.max_len)); wls["wl"] = [b"AAAA", b"AATT", b"CA", b"AT"]
+            elif e.rtype == O.UMI:
+                elems.append(umi(e.min_len, rid))
+            elif e.rtype == O.TARGET:
+                elems.append(cdna(e.min_len, e.max_len, rid))
+            elif e.seq_fixed:
+                elems.append(linker(e.sequence, rid))
+            else:
+                elems.append(var(e.min_len, e.max_len, rid))
+        layout = make_layout([dict(read_id="R", elems=elems, max_len=0)], wls)
+        infos, strides = U.emul_infos(layout)
+        w = max(strides[0], len(seq))
+        sq = np.full((1, w), ord("N"), np.uint8); sq[0, :len(seq)] = np.frombuffer(seq, np.uint8)
+        ql = np.full((1, w), ord("@"), np.uint8)
+        full = [U.HostBatch(sq, ql, np.array([len(seq)], np.uint16))]
+        infos, results, counts, defects = U.run_emul(layout, U.narrow(full, strides))
+        ores, ocounts = U.run_oracle(layout, full)
+        U.compare_with_oracle(layout, infos, full, results, counts, defects, ores, ocounts)
+        # and the segments named in the expected string are where the device says they are
+        res = results[0]
+        want = dict()
+        for part in expected.split(","):
+            tag, s = part[1:part.index("]")], part[part.index("]") + 1:]
+            want.setdefault(tag, []).append(s)
+        got_b = []
+        for j in range(infos[0].n_bc):
+            c = int(res.bcoord[j][0]) if res.bcoord[j] is not None else None
+            if c is None:
+                code = (int(res.fstatus[0]) >> (4 + 3 * j)) & 7
+                if code != _ffi.BC_ABSENT:
+                    st = infos[0].static_start[infos[0].bc_elem[j]]
+                    got_b.append(seq[st:st + elems[infos[0].bc_elem[j]].max_len].decode())
+            elif c != _ffi.COORD_ABSENT:
+                got_b.append(seq[c >> 16:(c >> 16) + (c & 0xFFFF)].decode())
+        assert got_b == want.get("B", []), (read, got_b, want)
+        if res.tcoord is not None and int(res.fstatus[0]) & _ffi.FSTATUS_TARGET:
+            c = int(res.tcoord[0])
+            t = seq[c >> 16:(c >> 16) + (c & 0xFFFF)].decode()
+            assert [t] == (want.get("T") or want.get("TO")), (read, t, want)
+        else:
+            assert "T" not in want and "TO" not in want
