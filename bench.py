@@ -1,0 +1,411 @@
+#!/usr/bin/env python
+"""Benchmark of the barcode hot path (BASELINE.json metric: barcode-corrected read-pairs/s).
+
+    python bench.py --gpus N --steps K --warmup W            # our CUDA path (one rank per GPU under torchrun)
+    python bench.py --impl reference --gpus N --steps K ...  # the reference algorithm on the host cores
+
+Workload: 10x scRNA-seq v3 (16 nt CB + 12 nt UMI on R1, 91 nt cDNA on R2), 6.8 M-entry synthetic whitelist,
+125 M synthetic read pairs per GPU (= the 1 B-pair / 8 GPU configuration of BASELINE.json, weak scaling),
+barcodes Zipf-sampled over 10 000 cells with injected substitution errors (tools/synth).
+
+A step = one pass of the whole path over the rank's shard:
+    reset counts -> pass 1 (split + pack + whitelist probe + histogram) -> allreduce of the counts
+    -> pass 2 (1-Hamming correction with the fp64 posterior).
+`value` times it with the inputs resident in HBM; `e2e` times the same through the public API from pinned
+host buffers (H2D of every input plane and D2H of every result plane inside the timed region).
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+N_WHITELIST = 6_800_000
+R2_LEN = 91
+THRESHOLD = 0.975          # make_fastq default (precellar/src/align/fastq.rs:39)
+# algorithmic bytes per read pair (SURVEY.md 8d / DESIGN.md): B = 108 + 1536 * f_mis, split per kernel launch
+B_COUNT_R1 = 58 + 32 + 10  # R1 seq+qual+len, one 32 B probe sector, fstatus+bc_key+umi_key
+B_COUNT_R2 = 2 + 6         # R2 len, fstatus+tcoord
+B_CORRECT_PER_MISS = 1536  # 3 * 16 neighbour probes * 32 B
+
+
+def env_int(name, default):
+    try:
+        return int(os.environ.get(name, default))
+    except ValueError:
+        return default
+
+
+class ClockSampler:
+    """SM clock / throttle reasons of one GPU sampled during a timed region (NVML)."""
+
+    def __init__(self, index: int, period: float = 0.02):
+        self.index, self.period = index, period
+        self.samples, self.reasons = [], set()
+        self.max_mhz = None
+        self._stop = threading.Event()
+        self._thr = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def _run(self):
+        nv = self.nv
+        names = {0x1: "gpu_idle", 0x2: "applications_clocks_setting", 0x4: "sw_power_cap", 0x8: "hw_slowdown",
+                 0x10: "sync_boost", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown",
+                 0x80: "hw_power_brake_slowdown", 0x100: "display_clock_setting"}
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                for bit, nm in names.items():
+                    if r & bit and nm != "gpu_idle":
+                        self.reasons.add(nm)
+            except Exception:
+                pass
+            time.sleep(self.period)
+
+    def start(self):
+        if self.nv:
+            self._stop.clear()
+            self._thr = threading.Thread(target=self._run, daemon=True)
+            self._thr.start()
+
+    def stop(self):
+        if self._thr:
+            self._stop.set()
+            self._thr.join()
+            self._thr = None
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": 0}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+def pinned(nbytes: int, dtype, shape):
+    from precellar_b200 import _ffi
+    p = _ffi.lib().pcl_host_alloc(int(nbytes))
+    if not p:
+        raise MemoryError(f"pinned allocation of {nbytes} bytes failed")
+    buf = (C.c_uint8 * int(nbytes)).from_address(p)
+    arr = np.frombuffer(buf, dtype=dtype).reshape(shape)
+    return arr, p
+
+
+def run_reference_sample(wl, seq, qual, length, len2, n_threads, steps=1, warmup=0, want_outputs=False):
+    """The reference algorithm (oracle port: serial pass 1, parallel pass 2 over 128 sub-chunks per batch)
+    on host cores.  Returns (seconds per step list, OracleResult of the last step)."""
+    from oracle import pyoracle as O
+    from precellar_b200.configs import v3_layout
+    layout = v3_layout(wl, R2_LEN)
+    n_wl, k = wl.shape
+    orc = O.Oracle(O.reads_from_layout(layout), {0: (wl.reshape(-1), np.arange(n_wl + 1, dtype=np.uint64) * np.uint64(k), n_wl)})
+    orc.set_input(0, seq, qual, length, seq.shape[1])
+    orc.set_input(1, None, None, len2, 0)
+    times, res = [], None
+    for s in range(warmup + steps):
+        t0 = time.perf_counter()
+        orc.count()                                                     # BarcodeAnalyzer::new, serial
+        res = orc.annotate(correct=True, threshold=THRESHOLD, n_threads=n_threads, chunk_bases=1_000_000,
+                           outputs=want_outputs or s == warmup + steps - 1)
+        dt = time.perf_counter() - t0
+        if s >= warmup:
+            times.append(dt)
+    counts = orc.counts(0)
+    orc.close()
+    return times, res, counts
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--pairs-per-gpu", type=int, default=125_000_000)
+    ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--e2e-chunks", type=int, default=8)
+    ap.add_argument("--cpu-sample", type=int, default=2_500_000)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+
+    rank, local_rank, world = env_int("RANK", 0), env_int("LOCAL_RANK", 0), env_int("WORLD_SIZE", 1)
+    n = args.pairs_per_gpu
+    host_cores = os.cpu_count() or 1
+    workload = (f"10x scRNA-seq v3 (16nt CB + 12nt UMI, R2 {R2_LEN}nt), {N_WHITELIST} whitelist, "
+                f"{n} synthetic read pairs per GPU (1B-pair / 8-GPU config)")
+
+    from tools import synth as S
+    wl = S.make_whitelist(N_WHITELIST, 16)
+    spec = S.SynthSpec(N_WHITELIST, bc_len=16, umi_len=12, stride=32, n_cells=10000)
+
+    # ------------------------------------------------------------------ reference arm (host cores only)
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        syn = S.Synth(spec, wl)
+        # bounded sample: calibrate on 200k pairs, then size the per-step sample so the whole run takes ~2 minutes
+        nc = min(200_000, n)
+        seq, qual, length = syn.host_arrays(0, nc)
+        tcal, _, _ = run_reference_sample(wl, seq, qual, length, np.full(nc, R2_LEN, np.uint16), host_cores)
+        rate = nc / tcal[0]
+        w = min(args.warmup, 1)
+        ns = int(max(100_000, min(args.cpu_sample, n, 120.0 * rate / (args.steps + w))))
+        seq, qual, length = syn.host_arrays(0, ns)
+        len2 = np.full(ns, R2_LEN, np.uint16)
+        times, _, _ = run_reference_sample(wl, seq, qual, length, len2, host_cores, steps=args.steps, warmup=w)
+        ms = 1e3 * float(np.mean(times))
+        v = ns / (ms / 1e3)
+        cfg = {"workload": workload, "sample_pairs_per_step": ns, "l2": "inputs >> L2 (host arm)"}
+        print(json.dumps({
+            "impl": "reference", "metric": "barcode-corrected read-pairs/sec", "value": v, "unit": "read-pairs/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": min(args.warmup, 1), "ms_per_step": ms,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8/f64", "data": "synthetic",
+            "config": cfg,
+            "cpu_baseline": {"value": v, "unit": "read-pairs/s", "cores": host_cores, "kind": "port",
+                             "sample": f"{ns} read pairs per step: serial count pass + {host_cores}-thread correct pass "
+                                       "(C++ restatement of the reference algorithm, in-memory SoA input)"},
+            "e2e": {"value": v, "unit": "read-pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}))
+        return 0
+
+    # ------------------------------------------------------------------ our arm
+    import torch
+    import torch.distributed as dist
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+
+    def max_over_ranks(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    from precellar_b200 import _ffi
+    from precellar_b200.configs import v3_layout
+    from precellar_b200.pipeline import BarcodePipeline, HostBatch
+
+    uid = None
+    if world > 1:
+        t = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            t = torch.frombuffer(bytearray(BarcodePipeline.new_unique_id()), dtype=torch.uint8).cuda()
+        dist.broadcast(t, 0)
+        uid = bytes(t.cpu().numpy().tobytes())
+    layout = v3_layout(wl, R2_LEN)
+    pipe = BarcodePipeline(layout, device=local_rank, nranks=world, rank=rank, nccl_uid=uid)
+    syn = S.Synth(spec, wl)
+    first = rank * n
+
+    # device-resident shard, generated in place
+    big = pipe.new_chunk(n)
+    big.reset(n)
+    s1, q1, l1 = big.device_ptrs(0)
+    _, _, l2 = big.device_ptrs(1)
+    syn.fill_device(local_rank, first, n, s1, q1, l1, big.stream)
+    syn.fill_u16_device(local_rank, l2, R2_LEN, n, big.stream)
+    pipe.sync()
+
+    def step_resident():
+        pipe.reset_counts()
+        pipe.count(big)
+        pipe.allreduce()
+        pipe.correct(big, THRESHOLD)
+
+    clocks = ClockSampler(local_rank)
+    for _ in range(max(args.warmup, 3)):
+        step_resident()
+    pipe.sync()
+    pipe.profile_enable(True)
+    pipe.profile_reset()
+    launches0 = pipe.launch_count()
+    barrier()
+    clocks.start()
+    big.timer_start()
+    for _ in range(args.steps):
+        step_resident()
+    ms_total = big.timer_stop_ms()
+    barrier()
+    clocks.stop()
+    launches = pipe.launch_count() - launches0
+    ms_total = max_over_ranks(ms_total)
+    ms_step = ms_total / args.steps
+    value = n * world / (ms_step / 1e3)
+    prof = {k: pipe.profile_get(k) for k in (_ffi.K_COUNT, _ffi.K_CORRECT, _ffi.K_COUNT_LENONLY)}
+    pipe.profile_enable(False)
+    cnt, mismatch, total = pipe.counts(0)
+    assert total == n * world, (total, n, world)
+    f_mis_global = mismatch / total
+    # the rank's own miss count drives its correct kernel
+    f_mis = f_mis_global
+
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak = float(json.load(open(peaks_path))["hbm_gbs"])
+        peak_src = "MEASURED_PEAKS.json hbm_gbs (measured copy bandwidth)"
+    else:
+        peak, peak_src = 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
+    t_count = prof[_ffi.K_COUNT][0] / max(prof[_ffi.K_COUNT][1], 1)
+    t_corr = prof[_ffi.K_CORRECT][0] / max(prof[_ffi.K_CORRECT][1], 1)
+    t_len = prof[_ffi.K_COUNT_LENONLY][0] / max(prof[_ffi.K_COUNT_LENONLY][1], 1)
+    kern = {
+        "k_count(R1)": {"ms": t_count, "alg_bytes": n * B_COUNT_R1},
+        "k_correct(R1)": {"ms": t_corr, "alg_bytes": n * f_mis * B_CORRECT_PER_MISS},
+        "k_count(R2,len-only)": {"ms": t_len, "alg_bytes": n * B_COUNT_R2},
+    }
+    for kv in kern.values():
+        kv["gbs"] = kv["alg_bytes"] / (kv["ms"] / 1e3) / 1e9 if kv["ms"] > 0 else None
+    dom = max(kern, key=lambda k: kern[k]["ms"])
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if os.path.exists(tpath):
+        try:
+            traffic = json.load(open(tpath)).get(dom)
+        except Exception:
+            traffic = None
+    step_alg_bytes = n * (108 + B_CORRECT_PER_MISS * f_mis)
+    roofline = {
+        "bound": "hbm", "kernel": dom, "achieved": kern[dom]["gbs"], "peak": peak, "unit": "GB/s",
+        "frac": (kern[dom]["gbs"] / peak) if kern[dom]["gbs"] else None, "traffic": traffic, "peak_source": peak_src,
+        "algorithmic_bytes_per_launch": kern[dom]["alg_bytes"], "ms_per_launch": kern[dom]["ms"],
+        "kernels": {k: {"ms_per_launch": v["ms"], "achieved_gbs": v["gbs"], "alg_bytes_per_launch": v["alg_bytes"]} for k, v in kern.items()},
+        "whole_step": {"alg_bytes_per_pair": 108 + B_CORRECT_PER_MISS * f_mis,
+                       "achieved_gbs": step_alg_bytes / (ms_step / 1e3) / 1e9,
+                       "frac": step_alg_bytes / (ms_step / 1e3) / 1e9 / peak},
+    }
+
+    # ------------------------------------------------------------------ end to end from pinned host memory
+    e2e = None
+    parity = None
+    if not args.no_e2e:
+        nc = max(1, args.e2e_chunks)
+        bounds = np.linspace(0, n, nc + 1).astype(np.int64)
+        cap = int(np.max(np.diff(bounds)))
+        seq_h, _p1 = pinned(n * 32, np.uint8, (n, 32))
+        qual_h, _p2 = pinned(n * 32, np.uint8, (n, 32))
+        len_h, _p3 = pinned(n * 2, np.uint16, (n,))
+        len2_h, _p4 = pinned(n * 2, np.uint16, (n,))
+        fs1_h, _p5 = pinned(n * 2, np.uint16, (n,))
+        bck_h, _p6 = pinned(n * 4, np.uint32, (n,))
+        umi_h, _p7 = pinned(n * 4, np.uint32, (n,))
+        fs2_h, _p8 = pinned(n * 2, np.uint16, (n,))
+        tc2_h, _p9 = pinned(n * 4, np.uint32, (n,))
+        # same bytes as the resident shard: copy them out of the device planes (generator parity is tested separately)
+        syn.memcpy_d2h(local_rank, seq_h.ctypes.data, s1, n * 32)
+        syn.memcpy_d2h(local_rank, qual_h.ctypes.data, q1, n * 32)
+        syn.memcpy_d2h(local_rank, len_h.ctypes.data, l1, n * 2)
+        syn.memcpy_d2h(local_rank, len2_h.ctypes.data, l2, n * 2)
+        chunks = [pipe.new_chunk(cap) for _ in range(nc)]
+        from precellar_b200.pipeline import ReadResults
+        outs = []
+        for c in range(nc):
+            lo, hi = int(bounds[c]), int(bounds[c + 1])
+            r1 = ReadResults(pipe.infos[0], fs1_h[lo:hi], None, [bck_h[lo:hi]], [umi_h[lo:hi]], [None], [None])
+            r2 = ReadResults(pipe.infos[1], fs2_h[lo:hi], tc2_h[lo:hi], [], [], [], [])
+            outs.append((r1, r2))
+        h2d = n * (32 + 32 + 2 + 2)
+        d2h = n * (2 + 4 + 4 + 2 + 4)
+
+        def step_e2e():
+            pipe.reset_counts()
+            for c, ch in enumerate(chunks):
+                lo, hi = int(bounds[c]), int(bounds[c + 1])
+                ch.reset(hi - lo)
+                ch.upload(0, HostBatch(seq_h[lo:hi], qual_h[lo:hi], len_h[lo:hi]))
+                ch.upload(1, HostBatch(None, None, len2_h[lo:hi]))
+                pipe.count(ch)
+            pipe.allreduce()
+            for ch in chunks:
+                pipe.correct(ch, THRESHOLD)
+            for c, ch in enumerate(chunks):
+                ch.fetch(0, outs[c][0])
+                ch.fetch(1, outs[c][1])
+
+        for _ in range(2):
+            step_e2e()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.e2e_steps):
+            step_e2e()
+        pipe.sync()
+        barrier()
+        dt = max_over_ranks(time.perf_counter() - t0) / args.e2e_steps
+        e2e = {"value": n * world / dt, "unit": "read-pairs/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+               "ms_per_step": dt * 1e3, "chunks": nc,
+               "note": "pinned host SoA planes -> H2D -> count -> allreduce -> correct -> D2H of every result plane"}
+
+        # ------------------------------------------------------------- CPU baseline + parity on a bounded sample
+        if rank == 0 and world == 1 and not args.no_cpu:
+            ns = min(args.cpu_sample, n)
+            # GPU results for exactly this sample (counts are global, so rerun the path on the sample alone)
+            small = pipe.new_chunk(ns)
+            pipe.reset_counts()
+            small.reset(ns)
+            small.upload(0, HostBatch(seq_h[:ns], qual_h[:ns], len_h[:ns]))
+            small.upload(1, HostBatch(None, None, len2_h[:ns]))
+            pipe.count(small)
+            pipe.allreduce()
+            pipe.correct(small, THRESHOLD)
+            g1, g2 = small.fetch(0), small.fetch(1)
+            gcnt, gmm, gtot = pipe.counts(0)
+            times, ores, ocounts = run_reference_sample(wl, seq_h[:ns], qual_h[:ns], len_h[:ns], len2_h[:ns], host_cores,
+                                                        steps=1, warmup=0, want_outputs=True)
+            cpu_v = ns / float(np.mean(times))
+            from tools.v3check import compare_v3
+            fields = compare_v3(wl, g1, g2, (gcnt, gmm, gtot), ores, ocounts)
+            parity = {"checked_pairs": int(ns), "mismatches": int(sum(fields.values())), "fields": fields}
+            cpu_baseline = {"value": cpu_v, "unit": "read-pairs/s", "cores": host_cores, "kind": "port",
+                            "sample": f"first {ns} read pairs of the workload, one pass: serial count + {host_cores}-thread "
+                                      "correct (C++ restatement of the reference algorithm; in-memory SoA input, no gzip)"}
+        else:
+            cpu_baseline = None
+    else:
+        cpu_baseline = None
+
+    if rank == 0:
+        out = {
+            "metric": "barcode-corrected read-pairs/sec", "value": value, "unit": "read-pairs/s", "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "u8 (2-bit packed keys) + f64 posterior", "data": "synthetic",
+            "config": {"workload": workload, "pairs_per_gpu": n, "whitelist": N_WHITELIST, "n_cells": 10000,
+                       "f_mis": f_mis_global, "threshold": THRESHOLD, "parallelism": f"reads sharded over {world} GPU(s), "
+                       "whitelist replicated, one NCCL allreduce of the counts",
+                       "l2": "inputs (8.3 GB per GPU) are far larger than L2; no flush needed"},
+            "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": int(launches),
+            "clocks": clocks.summary(), "parity": parity, "host_cores": host_cores,
+        }
+        print(json.dumps(out))
+    pipe.close()
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

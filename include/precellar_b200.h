@@ -193,9 +193,9 @@ int pcl_chunk_device_ptrs(pcl_chunk *chunk, int read_slot, void **seq, void **qu
 void *pcl_chunk_stream(pcl_chunk *chunk);                        /* cudaStream_t of the chunk        */
 
 /* ---- the three stages --------------------------------------------------------------------- */
-int pcl_counts_reset(pcl_ctx *ctx);
+int pcl_counts_reset(pcl_ctx *ctx);                             /* stream-ordered against every chunk (async) */
 int pcl_count(pcl_ctx *ctx, pcl_chunk *chunk);                   /* pass 1 on this chunk (async)     */
-int pcl_counts_allreduce(pcl_ctx *ctx);                          /* sums counts over ranks; blocks until all chunks counted */
+int pcl_counts_allreduce(pcl_ctx *ctx);                          /* sums counts over ranks after every chunk's pass 1; later chunk work waits for it (async) */
 int pcl_correct(pcl_ctx *ctx, pcl_chunk *chunk, double threshold, double max_expected_errors); /* pass 2 (async) */
 
 /* ---- outputs ------------------------------------------------------------------------------ */
@@ -212,7 +212,7 @@ void *pcl_host_alloc(uint64_t bytes);
 void pcl_host_free(void *p);
 
 /* ---- instrumentation (used by bench.py; CUDA events on the launching stream) --------------- */
-enum { PCL_K_COUNT = 0, PCL_K_CORRECT = 1, PCL_K_MAX = 4 };
+enum { PCL_K_COUNT = 0, PCL_K_CORRECT = 1, PCL_K_COUNT_LENONLY = 2, PCL_K_ENUM = 3, PCL_K_MAX = 4 };
 int pcl_profile_enable(pcl_ctx *ctx, int on);                    /* bracket every kernel with events */
 /* accumulated ms and launches of kernel k since the last pcl_profile_reset (syncs the ctx) */
 int pcl_profile_get(pcl_ctx *ctx, int k, double *ms, uint64_t *launches);

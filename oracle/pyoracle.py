@@ -100,6 +100,23 @@ class ReadLayout:
     read_id: str = ""
 
 
+_PRIMER_TYPES = {"custom_primer", "truseq_read1", "truseq_read2", "nextera_read1", "nextera_read2", "illumina_p5",
+                 "illumina_p7"}
+
+
+def reads_from_layout(layout) -> List["ReadLayout"]:
+    """Oracle read tables from a compiled layout (duck-typed: .reads[].elems[] with seqspec field names)."""
+    out = []
+    for p in layout.reads:
+        elems = []
+        for e, slot in zip(p.elems, p.region_slots):
+            rt = (BARCODE if e.region_type == "barcode" else UMI if e.region_type == "umi"
+                  else TARGET if e.region_type in ("gdna", "cdna") else PRIMER if e.region_type in _PRIMER_TYPES else OTHER)
+            elems.append(Elem(rt, e.min_len, e.max_len, e.sequence_type == "fixed", e.sequence, slot, e.region_id))
+        out.append(ReadLayout(elems, p.is_reverse, p.max_len, p.read_id))
+    return out
+
+
 def _elem_array(elems: Sequence) -> "C.Array[_Elem]":
     arr = (_Elem * max(1, len(elems)))()
     for i, e in enumerate(elems):
@@ -197,12 +214,19 @@ class Oracle:
         self.n_bcsegs = sum(1 for r in self.reads for e in r.elems if e.rtype == BARCODE)
         self.wl_sizes = {}
         for region, items in whitelists.items():
-            items = list(items)
-            blob, offs = pack_strings(items)
-            rc = self.L.orc_set_whitelist(self.h, int(region), blob.ctypes.data, offs.ctypes.data, len(items))
+            if isinstance(items, tuple):            # (blob uint8[], offsets uint64[n+1], n_unique): large lists
+                blob, offs, n_unique = items
+                blob = np.ascontiguousarray(blob, np.uint8)
+                offs = np.ascontiguousarray(offs, np.uint64)
+                n_items = len(offs) - 1
+            else:
+                items = list(items)
+                blob, offs = pack_strings(items)
+                n_items, n_unique = len(items), len(dict.fromkeys(items))
+            rc = self.L.orc_set_whitelist(self.h, int(region), blob.ctypes.data, offs.ctypes.data, n_items)
             if rc < 0:
                 raise RuntimeError(self.error())
-            self.wl_sizes[int(region)] = len(dict.fromkeys(items))
+            self.wl_sizes[int(region)] = n_unique
         self.n = None
 
     def error(self) -> str:

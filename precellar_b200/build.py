@@ -55,5 +55,13 @@ def build(force: bool = False, verbose: bool = False) -> str:
     return OUT
 
 
+def build_tools(force: bool = False) -> None:
+    """Bench / test tooling that also contains sm_100a code (the synthetic read generator)."""
+    import importlib
+    sys.path.insert(0, os.path.dirname(HERE))
+    importlib.import_module("tools.synth").build(force)
+
+
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose=True))
+    build_tools(force="--force" in sys.argv)

@@ -483,13 +483,19 @@ void *pcl_chunk_stream(pcl_chunk *c) { return c ? (void *)c->stream : nullptr; }
 int pcl_counts_reset(pcl_ctx *ctx) {
     if (!ctx) return PCL_ERR_ARG;
     if (int r = bind(ctx)) return r;
-    if (int r = pcl_sync(ctx)) return r;
+    // stream-ordered: after everything already queued on the chunks, before anything queued later
+    for (pcl_chunk *c : ctx->chunks) {
+        CU(ctx, cudaEventRecord(c->ev, c->stream));
+        CU(ctx, cudaStreamWaitEvent(ctx->stream, c->ev, 0));
+    }
     for (Table &t : ctx->tables) {
         if (!t.loaded) continue;
-        CU(ctx, cudaMemset(t.d_counts, 0, t.n_slots * sizeof(uint32_t)));
-        CU(ctx, cudaMemset(t.d_scalars, 0, 2 * sizeof(unsigned long long)));
+        CU(ctx, cudaMemsetAsync(t.d_counts, 0, t.n_slots * sizeof(uint32_t), ctx->stream));
+        CU(ctx, cudaMemsetAsync(t.d_scalars, 0, 2 * sizeof(unsigned long long), ctx->stream));
     }
-    CU(ctx, cudaMemset(ctx->d_qc, 0, PCL_MAX_READS * sizeof(unsigned long long)));
+    CU(ctx, cudaMemsetAsync(ctx->d_qc, 0, PCL_MAX_READS * sizeof(unsigned long long), ctx->stream));
+    CU(ctx, cudaEventRecord(ctx->ev_reduced, ctx->stream));
+    for (pcl_chunk *c : ctx->chunks) CU(ctx, cudaStreamWaitEvent(c->stream, ctx->ev_reduced, 0));
     memset(ctx->qc_reads, 0, sizeof ctx->qc_reads);
     return PCL_OK;
 }
@@ -530,7 +536,7 @@ int pcl_count(pcl_ctx *ctx, pcl_chunk *c) {
         p.num_defect = ctx->d_qc + r;
         CU(ctx, cudaMemsetAsync(b.wl_count, 0, sizeof(unsigned long long), c->stream));
         const int grid = grid_for(ctx, c->n, 6);
-        prof_begin(ctx, c->stream, PCL_K_COUNT);
+        prof_begin(ctx, c->stream, ctx->dreads[r].needs_payload ? PCL_K_COUNT : PCL_K_COUNT_LENONLY);
         k_count<<<grid, PCL_BLOCK, 0, c->stream>>>(p);
         prof_end(ctx, c->stream);
         CU(ctx, cudaGetLastError());
@@ -591,8 +597,9 @@ int pcl_correct(pcl_ctx *ctx, pcl_chunk *c, double threshold, double max_expecte
         p.threshold = threshold; p.max_expected_errors = max_expected_errors; p.check_ee = check_ee;
         if (check_ee) {
             CU(ctx, cudaMemsetAsync(b.wl_count, 0, sizeof(unsigned long long), c->stream));
-            ctx->launches += 1;
+            prof_begin(ctx, c->stream, PCL_K_ENUM);
             k_enum_all<<<grid_for(ctx, c->n, 8), PCL_BLOCK, 0, c->stream>>>(p);
+            prof_end(ctx, c->stream);
             CU(ctx, cudaGetLastError());
         }
         // the worklist size lives on the device; size the grid for the worst case and let idle CTAs exit

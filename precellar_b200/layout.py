@@ -114,3 +114,20 @@ def is_paired_end(layout: CompiledLayout) -> bool:
     a = any(e.is_target() for p in layout.reads if p.is_reverse for e in p.elems)
     b = any(e.is_target() for p in layout.reads if not p.is_reverse for e in p.elems)
     return a and b
+
+
+def layout_from_elems(reads, whitelists, modality: str = "rna") -> CompiledLayout:
+    """Build a CompiledLayout from explicit element tables (no YAML): ``reads`` is a list of dicts with
+    read_id, elems (SegmentInfoElem list, already truncated), is_reverse, max_len; ``whitelists`` maps
+    barcode region ids to byte-string lists (or [n, k] uint8 arrays) in whitelist-slot order."""
+    region_ids = list(whitelists.keys())
+    slot_of = {r: i for i, r in enumerate(region_ids)}
+    plans = []
+    for r in reads:
+        elems = list(r["elems"])
+        slots = [slot_of[e.region_id] if e.is_barcode() else -1 for e in elems]
+        plans.append(ReadPlan(r["read_id"], bool(r.get("is_reverse", False)), int(r.get("max_len", 0)), elems, slots,
+                              list(r.get("files", []))))
+    wl = {k: (v if hasattr(v, "shape") else list(v)) for k, v in whitelists.items()}
+    return CompiledLayout(parse_modality(modality), plans, region_ids, wl, {k: True for k in region_ids},
+                          any(e.is_umi() for p in plans for e in p.elems))

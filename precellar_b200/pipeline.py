@@ -133,8 +133,12 @@ class BarcodePipeline:
             self.infos.append(info)
         self.wl_bytes: Dict[int, List[bytes]] = {}
         for slot, rid in enumerate(layout.region_ids):
-            items = list(dict.fromkeys(layout.whitelists[rid]))
-            self.load_whitelist(slot, items)
+            wl = layout.whitelists[rid]
+            if isinstance(wl, np.ndarray):             # [n, k] uint8: large equal-length list, no Python objects
+                n, k = wl.shape
+                self.load_whitelist_packed(slot, wl.reshape(-1), np.arange(n + 1, dtype=np.uint64) * np.uint64(k))
+            else:
+                self.load_whitelist(slot, list(dict.fromkeys(wl)))
         if nranks > 1:
             buf = C.create_string_buffer(nccl_uid, 128)
             check(ctx, L.pcl_comm_init(ctx, nranks, rank, buf))

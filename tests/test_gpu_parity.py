@@ -95,3 +95,67 @@ def test_unsupported_whitelists_are_rejected(layouts):
         with pytest.raises(_ffi.PclError) as ei:
             BarcodePipeline(layout)
         assert ei.value.code == _ffi.PCL_ERR_UNSUPPORTED
+
+
+def test_synth_host_and_device_generate_the_same_bytes():
+    from tools import synth as S
+    from precellar_b200.configs import v3_layout
+    from precellar_b200.pipeline import BarcodePipeline
+    wl = S.make_whitelist(50_000, 16)
+    syn = S.Synth(S.SynthSpec(50_000, n_cells=500), wl)
+    n = 200_000
+    pipe = BarcodePipeline(v3_layout(wl))
+    try:
+        ch = pipe.new_chunk(n)
+        ch.reset(n)
+        s1, q1, l1 = ch.device_ptrs(0)
+        syn.fill_device(0, 1234, n, s1, q1, l1, ch.stream)
+        pipe.sync()
+        seq_d, qual_d, len_d = np.empty((n, 32), np.uint8), np.empty((n, 32), np.uint8), np.empty(n, np.uint16)
+        syn.memcpy_d2h(0, seq_d.ctypes.data, s1, n * 32)
+        syn.memcpy_d2h(0, qual_d.ctypes.data, q1, n * 32)
+        syn.memcpy_d2h(0, len_d.ctypes.data, l1, n * 2)
+        seq_h, qual_h, len_h = syn.host_arrays(1234, n)
+        assert np.array_equal(seq_d, seq_h) and np.array_equal(qual_d, qual_h) and np.array_equal(len_d, len_h)
+    finally:
+        pipe.close()
+
+
+def test_v3_full_size_2p5M_pairs_6p8M_whitelist():
+    """BASELINE configs[0]: 2.5 M synthetic read pairs, 6.8 M-entry whitelist, every field against the oracle."""
+    from tools import synth as S
+    from tools.v3check import compare_v3
+    from oracle import pyoracle as O
+    from precellar_b200.configs import v3_layout
+    from precellar_b200.pipeline import BarcodePipeline, HostBatch
+    n_wl, n = 6_800_000, 2_500_000
+    wl = S.make_whitelist(n_wl, 16)
+    syn = S.Synth(S.SynthSpec(n_wl), wl)
+    seq, qual, length = syn.host_arrays(0, n)
+    len2 = np.full(n, 91, np.uint16)
+    len2[::1000] = 0                                   # a few empty / short inserts
+    len2[1::1000] = 300                                # longer than max_len: truncated to 91
+    layout = v3_layout(wl, 91)
+    pipe = BarcodePipeline(layout)
+    try:
+        g1, g2 = pipe.run([HostBatch(seq, qual, length), HostBatch(None, None, len2)], correct=True, threshold=0.975)
+        gcounts = pipe.counts(0)
+    finally:
+        pipe.close()
+    orc = O.Oracle(O.reads_from_layout(layout), {0: (wl.reshape(-1), np.arange(n_wl + 1, dtype=np.uint64) * np.uint64(16), n_wl)})
+    orc.set_input(0, seq, qual, length, 32)
+    orc.set_input(1, None, None, len2, 0)
+    orc.count()
+    ores = orc.annotate(correct=True, threshold=0.975, n_threads=16)
+    fields = compare_v3(wl, g1, g2, gcounts, ores, orc.counts(0))
+    assert sum(fields.values()) == 0, fields
+    # UMI keys against the input bytes
+    u = seq[:, 16:28]
+    code = ((u >> 1) ^ (u >> 2)) & 3
+    valid = np.isin(u, np.frombuffer(b"ACGT", np.uint8)).all(axis=1)
+    k = np.ones(n, np.uint64)
+    for p in range(12):
+        k = (k << np.uint64(2)) | code[:, p].astype(np.uint64)
+    assert np.array_equal(g1.umi_key[0], np.where(valid, k, 0).astype(np.uint32))
+    code_bc = (g1.fstatus.astype(np.uint32) >> 4) & 7
+    assert (code_bc == _ffi.BC_CORRECTED).sum() > 100_000 and (code_bc == _ffi.BC_EXACT).sum() > 1_500_000

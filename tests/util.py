@@ -49,15 +49,7 @@ def make_layout(reads: Sequence[dict], whitelists: Dict[str, List[bytes]], modal
 
 
 def oracle_reads(layout: CompiledLayout) -> List[O.ReadLayout]:
-    out = []
-    for p in layout.reads:
-        elems = []
-        for e, slot in zip(p.elems, p.region_slots):
-            rt = (O.BARCODE if e.is_barcode() else O.UMI if e.is_umi() else O.TARGET if e.is_target()
-                  else O.PRIMER if e.region_type in _PRIMERS else O.OTHER)
-            elems.append(O.Elem(rt, e.min_len, e.max_len, e.sequence_type == "fixed", e.sequence, slot, e.region_id))
-        out.append(O.ReadLayout(elems, p.is_reverse, p.max_len, p.read_id))
-    return out
+    return O.reads_from_layout(layout)
 
 
 # ------------------------------------------------------------------------------------------------
