@@ -41,6 +41,17 @@ struct DElem {
     uint8_t seq[PCL_MAX_ANCHOR];
 };
 
+// Register-resident path for the common short barcode reads (10x v2/v3 R1, ATAC / multiome I2 ...):
+// every element fixed-length (an optional trailing variable target), the whole record within 16 or 32 bytes,
+// exactly one barcode of <= 16 bases, at most one UMI of <= 15 bases.
+struct FastLayout {
+    uint8_t enabled;
+    uint8_t bc_start, bc_len, umi_start, umi_len;   // umi_len == 0: no UMI
+    uint8_t has_tail_target;                        // trailing variable target element
+    uint16_t t_start, t_min, t_max;
+    uint32_t bc_mask[8], umi_mask[8];               // byte masks of the two regions over the 8 record words
+};
+
 struct DRead {
     uint16_t n_elems;
     uint8_t is_reverse;
@@ -49,6 +60,7 @@ struct DRead {
     uint32_t stride;     // bytes per record slot
     uint8_t n_bc, n_umi, has_target, needs_payload;
     DElem elems[PCL_MAX_ELEMS];
+    FastLayout fast;
 };
 
 // Whitelist hash table of one barcode region: buckets of 32 bytes (one DRAM/L2 sector) holding
@@ -111,12 +123,58 @@ PCL_HD uint32_t pcl_hash_bucket(uint64_t key, uint32_t n_buckets) {
     return (uint32_t)(((h & 0xFFFFFFFFull) * (uint64_t)n_buckets) >> 32);
 }
 
+// 32-bit tables: lowbias32 mix + fastrange
+PCL_HD uint32_t pcl_hash32_bucket(uint32_t k, uint32_t n_buckets) {
+    k ^= k >> 16;
+    k *= 0x7feb352du;
+    k ^= k >> 15;
+    k *= 0x846ca68bu;
+    k ^= k >> 16;
+#ifdef __CUDA_ARCH__
+    return __umulhi(k, n_buckets);
+#else
+    return (uint32_t)(((uint64_t)k * (uint64_t)n_buckets) >> 32);
+#endif
+}
+
 #ifdef __CUDA_ARCH__
 #define PCL_LDG128(p) __ldg(reinterpret_cast<const uint4 *>(p))
 #else
 struct pcl_u4 { uint32_t x, y, z, w; };
 #define PCL_LDG128(p) (*reinterpret_cast<const pcl_u4 *>(p))
 #endif
+
+// One 32-byte bucket of a 32-bit table: slot of `k` or 0xFFFFFFFF; *full = no free slot in the bucket.
+// The host fills the slots of a bucket in order, so the bucket is full iff its last slot is occupied.
+PCL_HD uint32_t pcl_bucket32(const uint32_t *keys, uint32_t b, uint32_t k, uint32_t empty, bool *full) {
+    auto v0 = PCL_LDG128(keys + (uint64_t)b * 8);
+    auto v1 = PCL_LDG128(keys + (uint64_t)b * 8 + 4);
+    uint32_t j = 8;
+    j = (v1.w == k) ? 7u : j;
+    j = (v1.z == k) ? 6u : j;
+    j = (v1.y == k) ? 5u : j;
+    j = (v1.x == k) ? 4u : j;
+    j = (v0.w == k) ? 3u : j;
+    j = (v0.z == k) ? 2u : j;
+    j = (v0.y == k) ? 1u : j;
+    j = (v0.x == k) ? 0u : j;
+    *full = v1.w != empty;
+    return j < 8u ? b * 8u + j : 0xFFFFFFFFu;
+}
+
+// Probe of a 32-bit table (PCL_TAB_K32_MARKER / PCL_TAB_K32_L16); k != empty is the caller's business.
+PCL_HD uint32_t pcl_probe32(const DTable &t, uint32_t k) {
+    const uint32_t *keys = reinterpret_cast<const uint32_t *>(t.keys);
+    const uint32_t e = (uint32_t)t.empty;
+    if (k == e) return 0xFFFFFFFFu;
+    uint32_t b = pcl_hash32_bucket(k, t.n_buckets);
+    for (;;) {
+        bool full;
+        uint32_t slot = pcl_bucket32(keys, b, k, e, &full);
+        if (slot != 0xFFFFFFFFu || !full) return slot;
+        b = (b + 1u == t.n_buckets) ? 0u : b + 1u;
+    }
+}
 
 // Look `key` (marker form, `len` bases) up in the table.  Returns the slot or 0xFFFFFFFF.
 PCL_HD uint32_t pcl_probe(const DTable &t, uint64_t key, uint32_t len) {
@@ -135,31 +193,13 @@ PCL_HD uint32_t pcl_probe(const DTable &t, uint64_t key, uint32_t len) {
             if (k1 == key) return b * 4u + 1u;
             if (k2 == key) return b * 4u + 2u;
             if (k3 == key) return b * 4u + 3u;
-            if (k0 == t.empty || k1 == t.empty || k2 == t.empty || k3 == t.empty) return MISS;
+            if (k3 == t.empty) return MISS;                 // slots fill in order: a free last slot ends the chain
             b = (b + 1u == t.n_buckets) ? 0u : b + 1u;
         }
     } else {
         if (t.mode == PCL_TAB_K32_L16) { if (len != 16u) return MISS; }
         else if (len > 15u) return MISS;
-        uint32_t k = (uint32_t)key, e = (uint32_t)t.empty;
-        if (k == e) return MISS;
-        uint32_t b = pcl_hash_bucket((uint64_t)k, t.n_buckets);
-        const uint32_t *keys = reinterpret_cast<const uint32_t *>(t.keys);
-        for (;;) {
-            auto v0 = PCL_LDG128(keys + (uint64_t)b * 8);
-            auto v1 = PCL_LDG128(keys + (uint64_t)b * 8 + 4);
-            if (v0.x == k) return b * 8u;
-            if (v0.y == k) return b * 8u + 1u;
-            if (v0.z == k) return b * 8u + 2u;
-            if (v0.w == k) return b * 8u + 3u;
-            if (v1.x == k) return b * 8u + 4u;
-            if (v1.y == k) return b * 8u + 5u;
-            if (v1.z == k) return b * 8u + 6u;
-            if (v1.w == k) return b * 8u + 7u;
-            if (v0.x == e || v0.y == e || v0.z == e || v0.w == e || v1.x == e || v1.y == e || v1.z == e || v1.w == e)
-                return MISS;
-            b = (b + 1u == t.n_buckets) ? 0u : b + 1u;
-        }
+        return pcl_probe32(t, (uint32_t)key);
     }
 }
 
@@ -345,6 +385,130 @@ PCL_HD uint32_t pcl_correct_one(const DTable &t, uint64_t key, uint32_t len, uin
     }
     if (!have) return PCL_BC_NO_MATCH;                                // (query, 0.0) -> prob <= 0
     double prob = PCL_DDIV(best_like, total);
+    if (prob <= 0.0) return PCL_BC_NO_MATCH;
+    if (prob >= threshold) { *out_key = best_key; return PCL_BC_CORRECTED; }
+    return PCL_BC_LOW_CONF;
+}
+
+// ------------------------------------------------------------------------------------------
+// register-resident fixed-layout path
+// ------------------------------------------------------------------------------------------
+PCL_HD uint32_t pcl_brev32(uint32_t x) {
+#ifdef __CUDA_ARCH__
+    return __brev(x);
+#else
+    x = ((x >> 1) & 0x55555555u) | ((x & 0x55555555u) << 1);
+    x = ((x >> 2) & 0x33333333u) | ((x & 0x33333333u) << 2);
+    x = ((x >> 4) & 0x0F0F0F0Fu) | ((x & 0x0F0F0F0Fu) << 4);
+    x = ((x >> 8) & 0x00FF00FFu) | ((x & 0x00FF00FFu) << 8);
+    return (x >> 16) | (x << 16);
+#endif
+}
+
+// Four ASCII bytes -> four 2-bit codes packed into the low 8 bits (byte k -> bits 2k..2k+1), plus the
+// XOR of the word with the bytes those codes stand for (non-zero byte <=> not a base).
+PCL_HD uint32_t pcl_word_codes(uint32_t w, uint32_t *diff) {
+    const uint32_t c = ((w >> 1) ^ (w >> 2)) & 0x03030303u;              // A0 C1 G2 T3 per byte
+    const uint32_t m0 = c & 0x01010101u, m1 = (c >> 1) & 0x01010101u, a = m0 & m1;
+    // A 0x41  C 0x43  G 0x47  T 0x54 : bit6 | bit4 = c0&c1 | bit2 = c1 | bit1 = c0^c1 | bit0 = !(c0&c1)
+    const uint32_t expect = 0x40404040u | (a << 4) | (m1 << 2) | ((m0 ^ m1) << 1) | (a ^ 0x01010101u);
+    *diff = w ^ expect;
+    uint32_t t = c | (c >> 6);
+    return (t | (t >> 12)) & 0xFFu;
+}
+
+// 2-bit little-endian-by-position field (base i at bits 2i) -> reported key:
+//   forward: first base most significant; reverse: reverse complement, which is the complement of the
+//   little-endian field read as big-endian.
+PCL_HD uint32_t pcl_field_to_key(uint64_t codes, uint32_t start, uint32_t len, bool rev) {
+    const uint32_t mask = len >= 16u ? 0xFFFFFFFFu : ((1u << (2u * len)) - 1u);
+    const uint32_t f = (uint32_t)(codes >> (2u * start)) & mask;
+    if (rev) return (~f) & mask;
+    uint32_t r = pcl_brev32(f);
+    r = ((r >> 1) & 0x55555555u) | ((r & 0x55555555u) << 1);
+    return len >= 16u ? r : r >> (32u - 2u * len);
+}
+
+// w[8]: the 32 record bytes.  Keys come back WITHOUT marker for 16-base fields and with it otherwise
+// (i.e. in their 4-byte device form); *_bad = the field holds a byte that is not a base.
+PCL_HD void pcl_fast_extract(const FastLayout &f, const uint32_t *w, bool rev, uint32_t *bc_key, bool *bc_bad,
+                             uint32_t *umi_key, bool *umi_bad) {
+    uint64_t codes = 0;
+    uint32_t bbad = 0, ubad = 0;
+    const uint32_t fold = rev ? 0xDFDFDFDFu : 0xFFFFFFFFu;               // precellar::utils::rev_compl accepts lower case
+#ifdef __CUDA_ARCH__
+#pragma unroll
+#endif
+    for (int k = 0; k < 8; ++k) {
+        uint32_t d;
+        const uint32_t c8 = pcl_word_codes(w[k] & fold, &d);
+        codes |= (uint64_t)c8 << (8 * k);
+        bbad |= d & f.bc_mask[k];
+        ubad |= d & f.umi_mask[k];
+    }
+    uint32_t bk = pcl_field_to_key(codes, f.bc_start, f.bc_len, rev);
+    if (f.bc_len < 16u) bk |= 1u << (2u * f.bc_len);
+    *bc_key = bk;
+    *bc_bad = bbad != 0u;
+    uint32_t uk = 0;
+    if (f.umi_len) {
+        uk = pcl_field_to_key(codes, f.umi_start, f.umi_len, rev) | (1u << (2u * f.umi_len));
+        if (ubad) uk = 0;
+    }
+    *umi_key = uk;
+    *umi_bad = ubad != 0u;
+}
+
+// correct_barcode / likelihood1 for barcodes of a 32-bit table (see pcl_correct_one for the semantics).
+// `key32` is the 4-byte device key (marker kept for < 16 bases, dropped for 16).
+PCL_HD uint32_t pcl_correct_one32(const DTable &t, uint32_t key32, uint32_t len, uint32_t n_invalid, uint32_t inv_pos,
+                                  const uint8_t *qual, uint32_t start, bool rev, double threshold, const double *lut_cap,
+                                  uint32_t *out_key) {
+    if (n_invalid > 1u) return PCL_BC_NO_MATCH;
+    if (t.mode == PCL_TAB_K32_L16 ? len != 16u : len > 15u) return PCL_BC_NO_MATCH;   // no entry of that length
+    const uint32_t *keys = reinterpret_cast<const uint32_t *>(t.keys);
+    const uint32_t empty = (uint32_t)t.empty, nb = t.n_buckets;
+    bool have = false;
+    double best_like = 0.0, total = 0.0;
+    uint32_t best_key = 0;
+    const uint32_t p0 = n_invalid == 1u ? inv_pos : 0u, p1 = n_invalid == 1u ? inv_pos + 1u : len;
+    for (uint32_t pos = p0; pos < p1; ++pos) {
+        const uint32_t sh = 2u * (len - 1u - pos);
+        const uint32_t existing = n_invalid == 1u ? 4u : ((key32 >> sh) & 3u);
+        const uint32_t base = key32 & ~(3u << sh);
+        uint32_t slot[4];
+#ifdef __CUDA_ARCH__
+#pragma unroll
+#endif
+        for (uint32_t val = 0; val < 4u; ++val) {                      // the four bucket probes are independent
+            slot[val] = 0xFFFFFFFFu;
+            if (val == existing) continue;
+            const uint32_t cand = base | (val << sh);
+            if (cand == empty) continue;
+            uint32_t b = pcl_hash32_bucket(cand, nb);
+            bool full;
+            uint32_t s = pcl_bucket32(keys, b, cand, empty, &full);
+            while (s == 0xFFFFFFFFu && full) {                          // rare: overflow into the next bucket
+                b = (b + 1u == nb) ? 0u : b + 1u;
+                s = pcl_bucket32(keys, b, cand, empty, &full);
+            }
+            slot[val] = s;
+        }
+        if ((slot[0] & slot[1] & slot[2] & slot[3]) == 0xFFFFFFFFu) continue;
+        const double perr = lut_cap[qual[start + (rev ? len - 1u - pos : pos)]];
+#ifdef __CUDA_ARCH__
+#pragma unroll
+#endif
+        for (uint32_t val = 0; val < 4u; ++val) {                      // BASE_OPTS order A C G T (barcode.rs:322)
+            if (slot[val] == 0xFFFFFFFFu) continue;
+            const uint32_t c = t.counts[slot[val]];
+            const double like = PCL_DMUL((double)(1ull + (uint64_t)c), perr);
+            if (!have || best_like < like) { have = true; best_like = like; best_key = base | (val << sh); }
+            total = PCL_DADD(total, like);
+        }
+    }
+    if (!have) return PCL_BC_NO_MATCH;
+    const double prob = PCL_DDIV(best_like, total);
     if (prob <= 0.0) return PCL_BC_NO_MATCH;
     if (prob >= threshold) { *out_key = best_key; return PCL_BC_CORRECTED; }
     return PCL_BC_LOW_CONF;

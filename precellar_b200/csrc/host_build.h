@@ -107,6 +107,46 @@ inline int pcl_build_read(int r, const pcl_read_desc &rd, DRead *out, pcl_read_i
     d.n_bc = info.n_bc; d.n_umi = info.n_umi; d.has_target = info.has_target; d.needs_payload = payload ? 1 : 0;
     info.fixed_layout = d.fixed_layout;
     info.needs_payload = d.needs_payload;
+    // register-resident path: see FastLayout
+    {
+        FastLayout &f = d.fast;
+        const int ne = rd.n_elems;
+        const pcl_elem_desc &last = rd.elems[ne - 1];
+        const bool tail_var = last.min_len != last.max_len;
+        bool ok = fixed && payload && (stride == 16 || stride == 32) && info.n_bc == 1 && info.n_umi <= 1;
+        if (ok && tail_var && last.kind != PCL_KIND_TARGET) ok = false;         // a trailing variable barcode/UMI/other: generic path
+        if (ok) {
+            const pcl_elem_desc &b = rd.elems[info.bc_elem[0]];
+            ok = b.min_len == b.max_len && b.max_len >= 1 && b.max_len <= 16 && info.static_start[info.bc_elem[0]] + b.max_len <= 32;
+            if (ok && info.n_umi) {
+                const pcl_elem_desc &u = rd.elems[info.umi_elem[0]];
+                ok = u.min_len == u.max_len && u.max_len >= 1 && u.max_len <= 15 && info.static_start[info.umi_elem[0]] + u.max_len <= 32;
+            }
+            // targets other than a trailing variable one, or more than one target, stay on the generic path
+            int n_t = 0;
+            for (int e = 0; e < ne; ++e) n_t += rd.elems[e].kind == PCL_KIND_TARGET;
+            if (n_t > 1 || (n_t == 1 && !(tail_var && last.kind == PCL_KIND_TARGET))) ok = false;
+        }
+        if (ok) {
+            f.enabled = 1;
+            f.bc_start = (uint8_t)info.static_start[info.bc_elem[0]];
+            f.bc_len = (uint8_t)rd.elems[info.bc_elem[0]].max_len;
+            if (info.n_umi) {
+                f.umi_start = (uint8_t)info.static_start[info.umi_elem[0]];
+                f.umi_len = (uint8_t)rd.elems[info.umi_elem[0]].max_len;
+            }
+            for (uint32_t i = 0; i < 32; ++i) {
+                if (i >= f.bc_start && i < (uint32_t)f.bc_start + f.bc_len) f.bc_mask[i / 4] |= 0xFFu << (8 * (i % 4));
+                if (f.umi_len && i >= f.umi_start && i < (uint32_t)f.umi_start + f.umi_len) f.umi_mask[i / 4] |= 0xFFu << (8 * (i % 4));
+            }
+            if (tail_var) {
+                f.has_tail_target = 1;
+                f.t_start = info.static_start[ne - 1];
+                f.t_min = last.min_len;
+                f.t_max = last.max_len;
+            }
+        }
+    }
     *out = d;
     *info_out = info;
     return PCL_OK;
@@ -168,7 +208,7 @@ inline int pcl_build_table(const uint8_t *bytes, const uint64_t *offsets, uint64
     if (t.mode == PCL_TAB_K64) t.tab64.assign(t.n_slots, t.empty); else t.tab32.assign(t.n_slots, (uint32_t)t.empty);
     for (uint64_t i = 0; i < m; ++i) {
         const uint64_t k = t.mode == PCL_TAB_K64 ? keys[i] : (keys[i] & 0xFFFFFFFFull);
-        uint32_t b = pcl_hash_bucket(k, (uint32_t)t.n_buckets);
+        uint32_t b = t.mode == PCL_TAB_K64 ? pcl_hash_bucket(k, (uint32_t)t.n_buckets) : pcl_hash32_bucket((uint32_t)k, (uint32_t)t.n_buckets);
         for (;;) {
             bool placed = false;
             for (uint32_t s = 0; s < spb && !placed; ++s) {

@@ -201,6 +201,131 @@ __global__ void __launch_bounds__(PCL_BLOCK) k_count(const __grid_constant__ Cou
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// k_count_fast: pass 1 for reads with a FastLayout (10x v2/v3 R1, ATAC / multiome I2, ...).
+// One thread per record; the 32 record bytes arrive as two 128-bit streaming loads and stay in registers;
+// SWAR conversion to 2-bit codes; one bucket probe of the 32-bit key table.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint4 pcl_ld_stream(const uint4 *p) {
+    uint4 r;
+    asm volatile("ld.global.cs.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    return r;
+}
+
+__global__ void __launch_bounds__(PCL_BLOCK) k_count_fast(const __grid_constant__ CountParams p) {
+    __shared__ uint32_t ck[PCL_HCACHE];
+    __shared__ uint32_t cc[PCL_HCACHE];
+    for (uint32_t h = threadIdx.x; h < PCL_HCACHE; h += blockDim.x) { ck[h] = PCL_HEMPTY; cc[h] = 0; }
+    __syncthreads();
+
+    const DRead &rd = p.rd;
+    const FastLayout &f = rd.fast;
+    const DTable &tab = p.tab[0];
+    const bool rev = rd.is_reverse != 0;
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint64_t step = (uint64_t)gridDim.x * blockDim.x;
+    const uint32_t bc_end = (uint32_t)f.bc_start + f.bc_len, umi_end = (uint32_t)f.umi_start + f.umi_len;
+    const bool len_ok = tab.mode == PCL_TAB_K32_L16 ? f.bc_len == 16 : (tab.mode == PCL_TAB_K32_MARKER && f.bc_len <= 15);
+    const uint32_t absent_rest = (PCL_BC_ABSENT << 7) | (PCL_BC_ABSENT << 10) | (PCL_BC_ABSENT << 13);
+    uint32_t *bc_out = reinterpret_cast<uint32_t *>(p.bc_key[0]);
+    uint32_t *umi_out = reinterpret_cast<uint32_t *>(p.umi_key[0]);
+    unsigned long long n_total = 0, n_mis = 0;
+
+    for (uint64_t base = (uint64_t)blockIdx.x * blockDim.x + (threadIdx.x & ~31u); base < p.n; base += step) {
+        const uint64_t i = base + lane;
+        const bool live = i < p.n;
+        bool miss = false;
+        if (live) {
+            uint32_t L = p.len[i];
+            if (rd.max_len && L > rd.max_len) L = rd.max_len;
+            const uint4 *r = reinterpret_cast<const uint4 *>(p.seq + i * (uint64_t)rd.stride);
+            const uint4 a = pcl_ld_stream(r);
+            uint4 b = make_uint4(0u, 0u, 0u, 0u);                       // 16-byte records: the upper words are outside every mask
+            if (rd.stride == 32u) b = pcl_ld_stream(r + 1);
+            const uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+            uint32_t bk, uk;
+            bool bbad, ubad;
+            pcl_fast_extract(f, w, rev, &bk, &bbad, &uk, &ubad);
+            uint32_t fs = PCL_SPLIT_OK | absent_rest;
+            if (f.has_tail_target) {
+                uint32_t tc = PCL_COORD_ABSENT;
+                if (f.t_start < L && (uint32_t)f.t_start + f.t_min <= L) {
+                    const uint32_t hi = (uint32_t)f.t_start + f.t_max < L ? (uint32_t)f.t_start + f.t_max : L;
+                    tc = ((uint32_t)f.t_start << 16) | (hi - f.t_start);
+                    fs |= PCL_FSTATUS_TARGET;
+                }
+                p.tcoord[i] = tc;
+            }
+            uint32_t code = PCL_BC_ABSENT;
+            if (bc_end <= L) {
+                ++n_total;
+                uint32_t slot = 0xFFFFFFFFu;
+                if (!bbad && len_ok) slot = pcl_probe32(tab, bk);
+                if (slot != 0xFFFFFFFFu) {
+                    code = PCL_BC_EXACT;
+                    pcl_hist_add(ck, cc, 0u, slot, tab.counts);
+                } else {
+                    code = PCL_BC_NO_MATCH;
+                    ++n_mis;
+                    miss = true;
+                }
+            } else {
+                bk = 0;
+            }
+            fs |= code << 4;
+            bc_out[i] = bk;
+            if (f.umi_len) umi_out[i] = umi_end <= L ? uk : PCL_KEY_ABSENT32;
+            p.fstatus[i] = (uint16_t)fs;
+        }
+        const uint32_t ballot = __ballot_sync(0xFFFFFFFFu, miss);
+        if (ballot) {
+            unsigned long long pos = 0;
+            if (lane == 0) pos = atomicAdd(p.wl_count, (unsigned long long)__popc(ballot));
+            pos = __shfl_sync(0xFFFFFFFFu, pos, 0);
+            if (miss) p.worklist[pos + __popc(ballot & ((1u << lane) - 1u))] = pcl_wl_entry(i, f.bc_start, f.bc_len, 0u);
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        n_total += __shfl_xor_sync(0xFFFFFFFFu, n_total, o);
+        n_mis += __shfl_xor_sync(0xFFFFFFFFu, n_mis, o);
+    }
+    if (lane == 0) {
+        if (n_total) atomicAdd(tab.total, n_total);
+        if (n_mis) atomicAdd(tab.mismatch, n_mis);
+    }
+    __syncthreads();
+    for (uint32_t h = threadIdx.x; h < PCL_HCACHE; h += blockDim.x) {
+        const uint32_t id = ck[h], c = cc[h];
+        if (id != PCL_HEMPTY && c) atomicAdd(&tab.counts[id & 0x1FFFFFFFu], c);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_count_lenonly: pass 1 for fixed-layout reads without barcode / UMI / anchor (insert reads): only the
+// record length is read; emits fstatus and the insert coordinates.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(PCL_BLOCK) k_count_lenonly(const __grid_constant__ CountParams p) {
+    const DRead &rd = p.rd;
+    const uint32_t absent_all = (PCL_BC_ABSENT << 4) | (PCL_BC_ABSENT << 7) | (PCL_BC_ABSENT << 10) | (PCL_BC_ABSENT << 13);
+    const int ne = rd.n_elems;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < p.n; i += (uint64_t)gridDim.x * blockDim.x) {
+        uint32_t L = p.len[i];
+        if (rd.max_len && L > rd.max_len) L = rd.max_len;
+        uint32_t off = 0, tc = PCL_COORD_ABSENT, n_t = 0;
+        for (int e = 0; e < ne; ++e) {
+            const uint32_t mn = rd.elems[e].min_len, mx = rd.elems[e].max_len;
+            if (off >= L || off + mn > L) break;                       // segment.rs:245-248
+            const uint32_t hi = off + mx < L ? off + mx : L;           // a fixed element fits entirely; the trailing variable one is clipped
+            if (rd.elems[e].kind == PCL_KIND_TARGET) { tc = (off << 16) | (hi - off); ++n_t; }
+            off += mx;
+        }
+        uint32_t fs = absent_all | (n_t > 1u ? PCL_SPLIT_MULTI_TARGET : PCL_SPLIT_OK);
+        if (n_t == 1u) fs |= PCL_FSTATUS_TARGET;
+        if (rd.has_target) p.tcoord[i] = n_t == 1u ? tc : PCL_COORD_ABSENT;
+        p.fstatus[i] = (uint16_t)fs;
+    }
+}
+
 // Worklist of every present barcode (exact and not): the expected-error test of correct_barcode
 // precedes the whitelist lookup, so with a finite max_expected_errors every barcode needs its qualities.
 __global__ void __launch_bounds__(PCL_BLOCK) k_enum_all(const __grid_constant__ CorrectParams p) {
@@ -244,6 +369,8 @@ __device__ __forceinline__ void pcl_fstatus_or(uint16_t *fstatus, uint64_t i, ui
     atomicOr(w, (a & 2) ? bits << 16 : bits);
 }
 
+// kFast32: every table of this read is a 32-bit table and no expected-error test is requested.
+template <bool kFast32>
 __global__ void __launch_bounds__(PCL_BLOCK) k_correct(const __grid_constant__ CorrectParams p) {
     const DRead &rd = p.rd;
     const unsigned long long n_work = *p.wl_count;
@@ -258,11 +385,18 @@ __global__ void __launch_bounds__(PCL_BLOCK) k_correct(const __grid_constant__ C
         const uint8_t *ql = p.qual + rec_i * (uint64_t)rd.stride;
         uint32_t ninv, ipos;
         const uint64_t key = pcl_pack_key(rec, start, blen, rev, &ninv, &ipos);
-        const bool is_exact = PCL_BC_CODE((uint32_t)p.fstatus[rec_i], j) == PCL_BC_EXACT;
-        uint64_t out_key = 0;
-        const uint32_t code = pcl_correct_one(p.tab[j], key, blen, ninv, ipos, ql, start, rev, is_exact, p.threshold,
-                                              p.max_expected_errors, p.check_ee != 0, p.lut_cap, p.lut_raw, &out_key);
-        if (code == PCL_BC_CORRECTED) pcl_store_key(p.bc_key[j], p.bc_key_bytes[j], rec_i, out_key);
+        uint32_t code;
+        if (kFast32) {
+            uint32_t out32 = 0;
+            code = pcl_correct_one32(p.tab[j], (uint32_t)key, blen, ninv, ipos, ql, start, rev, p.threshold, p.lut_cap, &out32);
+            if (code == PCL_BC_CORRECTED) reinterpret_cast<uint32_t *>(p.bc_key[j])[rec_i] = out32;
+        } else {
+            const bool is_exact = PCL_BC_CODE((uint32_t)p.fstatus[rec_i], j) == PCL_BC_EXACT;
+            uint64_t out_key = 0;
+            code = pcl_correct_one(p.tab[j], key, blen, ninv, ipos, ql, start, rev, is_exact, p.threshold,
+                                   p.max_expected_errors, p.check_ee != 0, p.lut_cap, p.lut_raw, &out_key);
+            if (code == PCL_BC_CORRECTED) pcl_store_key(p.bc_key[j], p.bc_key_bytes[j], rec_i, out_key);
+        }
         if (code != PCL_BC_EXACT && code != PCL_BC_NO_MATCH) pcl_fstatus_or(p.fstatus, rec_i, code << (4 + 3 * j));
     }
 }

@@ -10,6 +10,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <unordered_map>
@@ -105,6 +106,7 @@ struct pcl_ctx {
     uint64_t prof_n[PCL_K_MAX] = {0};
     uint64_t launches = 0;
     int sm_count = 148;
+    bool force_generic = false;   // PCL_FORCE_GENERIC=1: only the generic kernels (tests compare both paths)
 };
 
 struct ReadBuf {
@@ -210,6 +212,7 @@ int pcl_ctx_create(pcl_ctx **out, int device) {
     pcl_ctx *ctx = new pcl_ctx();
     ctx->device = device;
     ctx->sm_count = prop.multiProcessorCount;
+    { const char *g = getenv("PCL_FORCE_GENERIC"); ctx->force_generic = g && g[0] == '1'; }
     memset(ctx->descs, 0, sizeof ctx->descs);
     memset(ctx->dreads, 0, sizeof ctx->dreads);
     memset(ctx->infos, 0, sizeof ctx->infos);
@@ -535,9 +538,13 @@ int pcl_count(pcl_ctx *ctx, pcl_chunk *c) {
         p.worklist = b.worklist; p.wl_count = b.wl_count;
         p.num_defect = ctx->d_qc + r;
         CU(ctx, cudaMemsetAsync(b.wl_count, 0, sizeof(unsigned long long), c->stream));
-        const int grid = grid_for(ctx, c->n, 6);
-        prof_begin(ctx, c->stream, ctx->dreads[r].needs_payload ? PCL_K_COUNT : PCL_K_COUNT_LENONLY);
-        k_count<<<grid, PCL_BLOCK, 0, c->stream>>>(p);
+        const DRead &d = ctx->dreads[r];
+        const bool fast = d.fast.enabled && ctx->tables[ctx->bc_region[r][0]].d.mode != PCL_TAB_K64 && !ctx->force_generic;
+        const bool lenonly = !d.needs_payload && d.fixed_layout && !ctx->force_generic;
+        prof_begin(ctx, c->stream, d.needs_payload ? PCL_K_COUNT : PCL_K_COUNT_LENONLY);
+        if (fast) k_count_fast<<<grid_for(ctx, c->n, 6), PCL_BLOCK, 0, c->stream>>>(p);
+        else if (lenonly) k_count_lenonly<<<grid_for(ctx, c->n, 8), PCL_BLOCK, 0, c->stream>>>(p);
+        else k_count<<<grid_for(ctx, c->n, 6), PCL_BLOCK, 0, c->stream>>>(p);
         prof_end(ctx, c->stream);
         CU(ctx, cudaGetLastError());
         ctx->qc_reads[r] += c->n;
@@ -605,7 +612,13 @@ int pcl_correct(pcl_ctx *ctx, pcl_chunk *c, double threshold, double max_expecte
         // the worklist size lives on the device; size the grid for the worst case and let idle CTAs exit
         const int grid = grid_for(ctx, check_ee ? c->n * inf.n_bc : (c->n * inf.n_bc + 3) / 4, 8);
         prof_begin(ctx, c->stream, PCL_K_CORRECT);
-        k_correct<<<grid, PCL_BLOCK, 0, c->stream>>>(p);
+        bool all32 = !check_ee && !ctx->force_generic;
+        for (int j = 0; j < inf.n_bc; ++j) {
+            all32 = all32 && ctx->tables[ctx->bc_region[r][j]].d.mode != PCL_TAB_K64;
+            all32 = all32 && inf.bc_key_bytes[j] == 4;
+        }
+        if (all32) k_correct<true><<<grid, PCL_BLOCK, 0, c->stream>>>(p);
+        else k_correct<false><<<grid, PCL_BLOCK, 0, c->stream>>>(p);
         prof_end(ctx, c->stream);
         CU(ctx, cudaGetLastError());
     }

@@ -24,6 +24,15 @@ int emu_read_info(const pcl_read_desc *rd, pcl_read_info *info, uint32_t *stride
     return PCL_OK;
 }
 
+int emu_fast_enabled(const pcl_read_desc *rd) {
+    DRead d;
+    pcl_read_info info;
+    int bcr[PCL_MAX_BC_PER_READ];
+    std::string e;
+    if (pcl_build_read(0, *rd, &d, &info, bcr, &e) != PCL_OK) return -1;
+    return d.fast.enabled ? 1 : ((!d.needs_payload && d.fixed_layout) ? 2 : 0);
+}
+
 struct emu_read_io {
     const uint8_t *seq, *qual;
     const uint16_t *len;
@@ -38,7 +47,7 @@ struct emu_read_io {
 // counts_out[region]: n_entries values in whitelist order; scalars_out: total, mismatch per region;
 // defects_out: per read.
 int emu_run(const pcl_read_desc *reads, int n_reads, int n_regions, const uint8_t **wl_bytes, const uint64_t **wl_offs,
-            const uint64_t *wl_n, emu_read_io *io, uint64_t n, int correct, double threshold, double max_ee,
+            const uint64_t *wl_n, emu_read_io *io, uint64_t n, int correct, double threshold, double max_ee, int use_fast,
             uint64_t **counts_out, uint64_t *scalars_out, uint64_t *defects_out, char *err, int errcap) {
     std::string e;
     std::vector<HostTable> ht(n_regions);
@@ -77,6 +86,66 @@ int emu_run(const pcl_read_desc *reads, int n_reads, int n_regions, const uint8_
         const pcl_read_info &in = inf[r];
         const bool rev = rd.is_reverse != 0;
         defects_out[r] = 0;
+        const bool fast = use_fast && rd.fast.enabled && dt[bcr[r][0]].mode != PCL_TAB_K64;
+        const bool lenonly = use_fast && !rd.needs_payload && rd.fixed_layout;
+        if (fast) {                                   // mirrors k_count_fast
+            const FastLayout &f = rd.fast;
+            DTable &tab = dt[bcr[r][0]];
+            const uint32_t bc_end = (uint32_t)f.bc_start + f.bc_len, umi_end = (uint32_t)f.umi_start + f.umi_len;
+            const bool len_ok = tab.mode == PCL_TAB_K32_L16 ? f.bc_len == 16 : (tab.mode == PCL_TAB_K32_MARKER && f.bc_len <= 15);
+            const uint32_t absent_rest = (PCL_BC_ABSENT << 7) | (PCL_BC_ABSENT << 10) | (PCL_BC_ABSENT << 13);
+            for (uint64_t i = 0; i < n; ++i) {
+                uint32_t L = io[r].len[i];
+                if (rd.max_len && L > rd.max_len) L = rd.max_len;
+                uint32_t w[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+                memcpy(w, io[r].seq + i * (uint64_t)rd.stride, rd.stride);
+                uint32_t bk, uk; bool bbad, ubad;
+                pcl_fast_extract(f, w, rev, &bk, &bbad, &uk, &ubad);
+                uint32_t fs = PCL_SPLIT_OK | absent_rest;
+                if (f.has_tail_target) {
+                    uint32_t tc = PCL_COORD_ABSENT;
+                    if (f.t_start < L && (uint32_t)f.t_start + f.t_min <= L) {
+                        const uint32_t hi = (uint32_t)f.t_start + f.t_max < L ? (uint32_t)f.t_start + f.t_max : L;
+                        tc = ((uint32_t)f.t_start << 16) | (hi - f.t_start);
+                        fs |= PCL_FSTATUS_TARGET;
+                    }
+                    io[r].tcoord[i] = tc;
+                }
+                uint32_t code = PCL_BC_ABSENT;
+                if (bc_end <= L) {
+                    ++*tab.total;
+                    uint32_t slot = 0xFFFFFFFFu;
+                    if (!bbad && len_ok) slot = pcl_probe32(tab, bk);
+                    if (slot != 0xFFFFFFFFu) { code = PCL_BC_EXACT; tab.counts[slot]++; }
+                    else { code = PCL_BC_NO_MATCH; ++*tab.mismatch; work[r].push_back({i, f.bc_start, f.bc_len, 0}); }
+                } else bk = 0;
+                fs |= code << 4;
+                ((uint32_t *)io[r].bc_key[0])[i] = bk;
+                if (f.umi_len) ((uint32_t *)io[r].umi_key[0])[i] = umi_end <= L ? uk : PCL_KEY_ABSENT32;
+                io[r].fstatus[i] = (uint16_t)fs;
+            }
+            continue;
+        }
+        if (lenonly) {                                // mirrors k_count_lenonly
+            const uint32_t absent_all = (PCL_BC_ABSENT << 4) | (PCL_BC_ABSENT << 7) | (PCL_BC_ABSENT << 10) | (PCL_BC_ABSENT << 13);
+            for (uint64_t i = 0; i < n; ++i) {
+                uint32_t L = io[r].len[i];
+                if (rd.max_len && L > rd.max_len) L = rd.max_len;
+                uint32_t off = 0, tc = PCL_COORD_ABSENT, n_t = 0;
+                for (int e = 0; e < rd.n_elems; ++e) {
+                    const uint32_t mn = rd.elems[e].min_len, mx = rd.elems[e].max_len;
+                    if (off >= L || off + mn > L) break;
+                    const uint32_t hi = off + mx < L ? off + mx : L;
+                    if (rd.elems[e].kind == PCL_KIND_TARGET) { tc = (off << 16) | (hi - off); ++n_t; }
+                    off += mx;
+                }
+                uint32_t fs = absent_all | (n_t > 1u ? PCL_SPLIT_MULTI_TARGET : PCL_SPLIT_OK);
+                if (n_t == 1u) fs |= PCL_FSTATUS_TARGET;
+                if (rd.has_target) io[r].tcoord[i] = n_t == 1u ? tc : PCL_COORD_ABSENT;
+                io[r].fstatus[i] = (uint16_t)fs;
+            }
+            continue;
+        }
         for (uint64_t i = 0; i < n; ++i) {
             uint32_t L = io[r].len[i];
             if (rd.max_len && L > rd.max_len) L = rd.max_len;
@@ -149,6 +218,8 @@ int emu_run(const pcl_read_desc *reads, int n_reads, int n_regions, const uint8_
                     }
                 }
             }
+            bool all32 = use_fast && !check_ee;
+            for (uint32_t j = 0; j < rd.n_bc; ++j) all32 = all32 && dt[bcr[r][j]].mode != PCL_TAB_K64 && in.bc_key_bytes[j] == 4;
             for (const Work &w : work[r]) {
                 const uint8_t *rec = io[r].seq + w.rec * (uint64_t)rd.stride;
                 const uint8_t *ql = io[r].qual + w.rec * (uint64_t)rd.stride;
@@ -156,8 +227,15 @@ int emu_run(const pcl_read_desc *reads, int n_reads, int n_regions, const uint8_
                 uint64_t key = pcl_pack_key(rec, w.start, w.len, rev, &ninv, &ipos);
                 bool is_exact = PCL_BC_CODE((uint32_t)io[r].fstatus[w.rec], w.j) == PCL_BC_EXACT;
                 uint64_t out_key = 0;
-                uint32_t code = pcl_correct_one(dt[bcr[r][w.j]], key, w.len, ninv, ipos, ql, w.start, rev, is_exact, threshold,
-                                                max_ee, check_ee, lut, lut + 256, &out_key);
+                uint32_t code;
+                if (all32) {                          // mirrors k_correct<true>
+                    uint32_t out32 = 0;
+                    code = pcl_correct_one32(dt[bcr[r][w.j]], (uint32_t)key, w.len, ninv, ipos, ql, w.start, rev, threshold, lut, &out32);
+                    out_key = out32;
+                } else {
+                    code = pcl_correct_one(dt[bcr[r][w.j]], key, w.len, ninv, ipos, ql, w.start, rev, is_exact, threshold,
+                                           max_ee, check_ee, lut, lut + 256, &out_key);
+                }
                 if (code == PCL_BC_CORRECTED) pcl_store_key(io[r].bc_key[w.j], in.bc_key_bytes[w.j], w.rec, out_key);
                 if (code != PCL_BC_EXACT && code != PCL_BC_NO_MATCH) io[r].fstatus[w.rec] |= (uint16_t)(code << (4 + 3 * w.j));
             }

@@ -21,6 +21,14 @@ def _layouts(rng):
     out["v3"] = make_layout([
         dict(read_id="R1", elems=[bc("cb", 16), umi(12)], max_len=28),
         dict(read_id="R2", elems=[cdna(1, 1000)], is_reverse=True, max_len=91)], {"cb": wl16})
+    # fast-path shapes: 12-base barcode (marker form) + UMI + trailing target in a 32-byte record; 10x v2 (UMI 10)
+    wl12 = U.gen_whitelist(rng, 300, 12)
+    out["fast12_tail"] = make_layout([
+        dict(read_id="R1", elems=[linker("ACG"), bc("cb", 12), umi(9), cdna(1, 500)], max_len=0),
+        dict(read_id="R2", elems=[bc("cb", 12), umi(15, "u15")], is_reverse=True, max_len=27)], {"cb": wl12})
+    out["v2"] = make_layout([
+        dict(read_id="R1", elems=[bc("cb", 16), umi(10)], max_len=26),
+        dict(read_id="R2", elems=[gdna(3, 7, "g0"), cdna(1, 1000)], is_reverse=True, max_len=98)], {"cb": wl16})
     # 10x ATAC: I2 [B16] neg, R1/R2 gdna
     out["atac"] = make_layout([
         dict(read_id="R1", elems=[gdna(1, 1000)], max_len=50),
@@ -74,12 +82,14 @@ def layouts():
     return _layouts(np.random.default_rng(20240607))
 
 
-NAMES = ["v3", "atac", "multiome_atac", "sci3", "share", "dsc", "k64_rev", "multi_umi", "vec11", "joined"]
+NAMES = ["v3", "fast12_tail", "v2", "atac", "multiome_atac", "sci3", "share", "dsc", "k64_rev", "multi_umi", "vec11", "joined"]
 
 
 @pytest.mark.parametrize("name", NAMES)
-@pytest.mark.parametrize("mode", ["correct", "nocorrect", "ee", "lower"])
+@pytest.mark.parametrize("mode", ["correct", "nocorrect", "ee", "lower", "correct-generic"])
 def test_emul_matches_oracle(layouts, name, mode):
+    use_fast = mode != "correct-generic"          # the specialised paths are on by default
+    mode = mode.split("-")[0]
     layout = layouts[name]
     rng = np.random.default_rng(abs(hash((name, mode))) % (2 ** 31))
     infos, strides = U.emul_infos(layout)
@@ -92,7 +102,7 @@ def test_emul_matches_oracle(layouts, name, mode):
     dev = U.narrow(full, strides)
     kw = dict(correct=mode != "nocorrect", threshold=0.975 if mode != "lower" else 0.6,
               max_expected_errors=1.5 if mode == "ee" else _ffi.F64_MAX)
-    infos, results, counts, defects = U.run_emul(layout, dev, **kw)
+    infos, results, counts, defects = U.run_emul(layout, dev, use_fast=use_fast, **kw)
     ores, ocounts = U.run_oracle(layout, full, **kw)
     g = U.compare_with_oracle(layout, infos, full, results, counts, defects, ores, ocounts, correct=kw["correct"])
     # the test data must exercise the interesting branches
@@ -154,3 +164,19 @@ def test_reference_vectors_through_device_split():
             assert [t] == (want.get("T") or want.get("TO")), (read, t, want)
         else:
             assert "T" not in want and "TO" not in want
+
+
+def test_fast_path_selection(layouts):
+    """Which reads take the register-resident / length-only kernels (1 / 2) and which the generic one (0)."""
+    L = U.emul_lib()
+    def sel(name):
+        d = layouts[name].descs()
+        return [L.emu_fast_enabled(C.byref(d[r])) for r in range(len(layouts[name].reads))]
+    import ctypes as C
+    assert sel("v3") == [1, 2]
+    assert sel("atac") == [2, 1, 2]
+    assert sel("multiome_atac") == [2, 1, 2]
+    assert sel("fast12_tail") == [1, 1]
+    assert sel("sci3") == [0, 2]
+    assert sel("k64_rev") == [0, 0]
+    assert sel("share") == [2, 0]

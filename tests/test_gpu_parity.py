@@ -56,8 +56,11 @@ def run_gpu(layout, dev_batches, correct=True, threshold=0.975, max_expected_err
 
 
 @pytest.mark.parametrize("name", NAMES)
-@pytest.mark.parametrize("mode", ["correct", "nocorrect", "ee", "lower"])
-def test_gpu_matches_oracle(layouts, name, mode):
+@pytest.mark.parametrize("mode", ["correct", "nocorrect", "ee", "lower", "correct-generic"])
+def test_gpu_matches_oracle(layouts, name, mode, monkeypatch):
+    # the specialised kernels are the default; "-generic" forces the interpreter kernels on the same data
+    monkeypatch.setenv("PCL_FORCE_GENERIC", "1" if mode.endswith("-generic") else "0")
+    mode = mode.split("-")[0]
     layout = layouts[name]
     rng = np.random.default_rng(abs(hash((name, mode, "gpu"))) % (2 ** 31))
     infos, strides = U.emul_infos(layout)

@@ -216,7 +216,7 @@ def alloc_results(info: _ffi.ReadInfo, n: int) -> ReadResults:
 
 
 def run_emul(layout: CompiledLayout, batches: Sequence[HostBatch], correct=True, threshold=0.975,
-             max_expected_errors=_ffi.F64_MAX):
+             max_expected_errors=_ffi.F64_MAX, use_fast=True):
     """Returns (infos, results, counts{slot: (counts, mismatch, total)}, defects)."""
     L = emul_lib()
     infos, strides = emul_infos(layout)
@@ -261,9 +261,9 @@ def run_emul(layout: CompiledLayout, batches: Sequence[HostBatch], correct=True,
     defects = np.zeros(n_reads, np.uint64)
     err = C.create_string_buffer(512)
     L.emu_run.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64,
-                          C.c_int, C.c_double, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p, C.c_char_p, C.c_int]
+                          C.c_int, C.c_double, C.c_double, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_char_p, C.c_int]
     rc = L.emu_run(descs, n_reads, n_regions, bp, op, wl_n, io, n, int(correct), threshold, max_expected_errors,
-                   cp, scal.ctypes.data, defects.ctypes.data, err, 512)
+                   int(use_fast), cp, scal.ctypes.data, defects.ctypes.data, err, 512)
     if rc != 0:
         raise _ffi.PclError(rc, err.value.decode())
     counts = {}
