@@ -65,6 +65,42 @@ __device__ __forceinline__ unsigned long long pcl_wl_entry(uint64_t rec, uint32_
            ((unsigned long long)j << 56);
 }
 
+// Worklist allocation.  A single global cursor bumped once per warp iteration serialises on one L2 address
+// (millions of same-address returning atomics per launch).  Each warp instead reserves PCL_WL_BATCH entries
+// at a time and hands them out locally; only the unused tail of a warp's LAST reservation is left over and is
+// filled with PCL_WL_HOLE, which k_correct skips.  *wl_count is the number of RESERVED entries
+// (misses + at most PCL_WL_BATCH holes per warp).
+#define PCL_WL_BATCH 256u
+#define PCL_WL_HOLE 0xFFFFFFFFFFFFFFFFull
+
+struct WlCursor { unsigned long long pos, end; };
+
+template <typename P>
+__device__ __forceinline__ void pcl_wl_push(const P &p, WlCursor &cur, bool m, unsigned long long entry, uint32_t lane) {
+    const uint32_t ballot = __ballot_sync(0xFFFFFFFFu, m);
+    if (!ballot) return;
+    const unsigned long long need = __popc(ballot), rank = __popc(ballot & ((1u << lane) - 1u));
+    const unsigned long long rem = cur.end - cur.pos;   // warp-uniform
+    if (need > rem) {
+        // finish the old reservation exactly (no holes in the middle of the list), continue in a new one
+        if (m && rank < rem) p.worklist[cur.pos + rank] = entry;
+        unsigned long long b = 0;
+        if (lane == 0) b = atomicAdd(p.wl_count, (unsigned long long)PCL_WL_BATCH);
+        b = __shfl_sync(0xFFFFFFFFu, b, 0);
+        if (m && rank >= rem) p.worklist[b + rank - rem] = entry;
+        cur.pos = b + need - rem;
+        cur.end = b + PCL_WL_BATCH;
+    } else {
+        if (m) p.worklist[cur.pos + rank] = entry;
+        cur.pos += need;
+    }
+}
+
+template <typename P>
+__device__ __forceinline__ void pcl_wl_finish(const P &p, const WlCursor &cur, uint32_t lane) {
+    for (unsigned long long q = cur.pos + lane; q < cur.end; q += 32) p.worklist[q] = PCL_WL_HOLE;
+}
+
 // Per-CTA histogram cache: a direct-mapped table in shared memory keyed on (j, slot).  Zipf-distributed
 // barcodes send a large share of the reads to a few counters; the cache turns those into shared-memory
 // atomics and one global atomic per cached key at the end of the CTA's life.
@@ -96,6 +132,7 @@ __global__ void __launch_bounds__(PCL_BLOCK) k_count(const __grid_constant__ Cou
     unsigned long long n_mis[PCL_MAX_BC_PER_READ] = {0, 0, 0, 0};
     unsigned long long n_defect = 0;
     const bool rev = rd.is_reverse != 0;
+    WlCursor wl = {0, 0};
 
     // every lane of a warp runs the same number of iterations (full-mask ballots below)
     for (uint64_t base = (uint64_t)blockIdx.x * blockDim.x + (threadIdx.x & ~31u); base < p.n; base += step) {
@@ -157,23 +194,15 @@ __global__ void __launch_bounds__(PCL_BLOCK) k_count(const __grid_constant__ Cou
             }
             p.fstatus[i] = (uint16_t)fs;
         }
-        // warp-aggregated append of the misses to the worklist
+        // warp-batched append of the misses to the worklist
 #pragma unroll
         for (uint32_t j = 0; j < PCL_MAX_BC_PER_READ; ++j) {
             if (j >= rd.n_bc) break;
             const bool m = (miss_mask_j >> j) & 1u;
-            const uint32_t ballot = __ballot_sync(0xFFFFFFFFu, m);
-            if (ballot) {
-                unsigned long long pos = 0;
-                if (lane == 0) pos = atomicAdd(p.wl_count, (unsigned long long)__popc(ballot));
-                pos = __shfl_sync(0xFFFFFFFFu, pos, 0);
-                if (m) {
-                    const uint32_t rank = __popc(ballot & ((1u << lane) - 1u));
-                    p.worklist[pos + rank] = pcl_wl_entry(i, miss_coord[j] >> 16, miss_coord[j] & 0xFFFFu, j);
-                }
-            }
+            pcl_wl_push(p, wl, m, m ? pcl_wl_entry(i, miss_coord[j] >> 16, miss_coord[j] & 0xFFFFu, j) : 0ull, lane);
         }
     }
+    pcl_wl_finish(p, wl, lane);
 
     // totals: warp reduce, one atomic per warp
 #pragma unroll
@@ -230,6 +259,7 @@ __global__ void __launch_bounds__(PCL_BLOCK) k_count_fast(const __grid_constant_
     uint32_t *bc_out = reinterpret_cast<uint32_t *>(p.bc_key[0]);
     uint32_t *umi_out = reinterpret_cast<uint32_t *>(p.umi_key[0]);
     unsigned long long n_total = 0, n_mis = 0;
+    WlCursor wl = {0, 0};
 
     for (uint64_t base = (uint64_t)blockIdx.x * blockDim.x + (threadIdx.x & ~31u); base < p.n; base += step) {
         const uint64_t i = base + lane;
@@ -277,14 +307,9 @@ __global__ void __launch_bounds__(PCL_BLOCK) k_count_fast(const __grid_constant_
             if (f.umi_len) umi_out[i] = umi_end <= L ? uk : PCL_KEY_ABSENT32;
             p.fstatus[i] = (uint16_t)fs;
         }
-        const uint32_t ballot = __ballot_sync(0xFFFFFFFFu, miss);
-        if (ballot) {
-            unsigned long long pos = 0;
-            if (lane == 0) pos = atomicAdd(p.wl_count, (unsigned long long)__popc(ballot));
-            pos = __shfl_sync(0xFFFFFFFFu, pos, 0);
-            if (miss) p.worklist[pos + __popc(ballot & ((1u << lane) - 1u))] = pcl_wl_entry(i, f.bc_start, f.bc_len, 0u);
-        }
+        pcl_wl_push(p, wl, miss, pcl_wl_entry(i, f.bc_start, f.bc_len, 0u), lane);
     }
+    pcl_wl_finish(p, wl, lane);
     for (int o = 16; o > 0; o >>= 1) {
         n_total += __shfl_xor_sync(0xFFFFFFFFu, n_total, o);
         n_mis += __shfl_xor_sync(0xFFFFFFFFu, n_mis, o);
@@ -332,6 +357,7 @@ __global__ void __launch_bounds__(PCL_BLOCK) k_enum_all(const __grid_constant__ 
     const DRead &rd = p.rd;
     const uint32_t lane = threadIdx.x & 31u;
     const uint64_t step = (uint64_t)gridDim.x * blockDim.x;
+    WlCursor wl = {0, 0};
     for (uint64_t base = (uint64_t)blockIdx.x * blockDim.x + (threadIdx.x & ~31u); base < p.n; base += step) {
         const uint64_t i = base + lane;
         const bool live = i < p.n;
@@ -339,11 +365,7 @@ __global__ void __launch_bounds__(PCL_BLOCK) k_enum_all(const __grid_constant__ 
         for (uint32_t j = 0; j < rd.n_bc; ++j) {
             const uint32_t code = PCL_BC_CODE(fs, j);
             const bool m = live && (code == PCL_BC_EXACT || code == PCL_BC_NO_MATCH);
-            const uint32_t ballot = __ballot_sync(0xFFFFFFFFu, m);
-            if (!ballot) continue;
-            unsigned long long pos = 0;
-            if (lane == 0) pos = atomicAdd(p.wl_count, (unsigned long long)__popc(ballot));
-            pos = __shfl_sync(0xFFFFFFFFu, pos, 0);
+            unsigned long long entry = 0;
             if (m) {
                 uint32_t c;
                 if (rd.fixed_layout) {
@@ -356,11 +378,12 @@ __global__ void __launch_bounds__(PCL_BLOCK) k_enum_all(const __grid_constant__ 
                 } else {
                     c = p.bcoord[j][i];
                 }
-                const uint32_t rank = __popc(ballot & ((1u << lane) - 1u));
-                p.worklist[pos + rank] = pcl_wl_entry(i, c >> 16, c & 0xFFFFu, j);
+                entry = pcl_wl_entry(i, c >> 16, c & 0xFFFFu, j);
             }
+            pcl_wl_push(p, wl, m, entry, lane);
         }
     }
+    pcl_wl_finish(p, wl, lane);
 }
 
 __device__ __forceinline__ void pcl_fstatus_or(uint16_t *fstatus, uint64_t i, uint32_t bits) {
@@ -378,6 +401,7 @@ __global__ void __launch_bounds__(PCL_BLOCK) k_correct(const __grid_constant__ C
     const bool rev = rd.is_reverse != 0;
     for (uint64_t w = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; w < n_work; w += step) {
         const unsigned long long ent = p.worklist[w];
+        if (ent == PCL_WL_HOLE) continue;
         const uint64_t rec_i = ent & 0xFFFFFFFFull;
         const uint32_t start = (uint32_t)(ent >> 32) & 0xFFFFu, blen = (uint32_t)(ent >> 48) & 0xFFu,
                        j = (uint32_t)(ent >> 56);

@@ -413,7 +413,8 @@ int pcl_chunk_create(pcl_ctx *ctx, uint64_t capacity_records, pcl_chunk **out) {
             A(&b.umi_key[j], cap * inf.umi_key_bytes[j]);
             if (!inf.fixed_layout) A((void **)&b.ucoord[j], cap * 4);
         }
-        if (inf.n_bc) A((void **)&b.worklist, cap * inf.n_bc * 8);
+        // misses + the unused tails of the per-warp reservations (largest grid: sm_count * 8 CTAs of 8 warps)
+        if (inf.n_bc) A((void **)&b.worklist, (cap * inf.n_bc + (uint64_t)ctx->sm_count * 8 * (PCL_BLOCK / 32) * PCL_WL_BATCH * inf.n_bc) * 8);
         A((void **)&b.wl_count, 16);
     }
     if (rc != PCL_OK) {
@@ -610,7 +611,7 @@ int pcl_correct(pcl_ctx *ctx, pcl_chunk *c, double threshold, double max_expecte
             CU(ctx, cudaGetLastError());
         }
         // the worklist size lives on the device; size the grid for the worst case and let idle CTAs exit
-        const int grid = grid_for(ctx, check_ee ? c->n * inf.n_bc : (c->n * inf.n_bc + 3) / 4, 8);
+        const int grid = grid_for(ctx, check_ee ? c->n * inf.n_bc : (c->n * inf.n_bc + 3) / 4 + 4096, 8);
         prof_begin(ctx, c->stream, PCL_K_CORRECT);
         bool all32 = !check_ee && !ctx->force_generic;
         for (int j = 0; j < inf.n_bc; ++j) {
