@@ -459,8 +459,31 @@ PCL_HD void pcl_fast_extract(const FastLayout &f, const uint32_t *w, bool rev, u
     *umi_bad = ubad != 0u;
 }
 
+// Any of the 8 keys of bucket b equal to k?  *full = the bucket has no free slot (a longer probe chain is possible).
+PCL_HD bool pcl_bucket32_any(const uint32_t *keys, uint32_t b, uint32_t k, uint32_t empty, bool *full) {
+    auto v0 = PCL_LDG128(keys + (uint64_t)b * 8);
+    auto v1 = PCL_LDG128(keys + (uint64_t)b * 8 + 4);
+    *full = v1.w != empty;
+    return (v0.x == k) | (v0.y == k) | (v0.z == k) | (v0.w == k) | (v1.x == k) | (v1.y == k) | (v1.z == k) | (v1.w == k);
+}
+
+PCL_HD uint32_t pcl_ctz64(uint64_t x) {
+#ifdef __CUDA_ARCH__
+    return (uint32_t)(__ffsll((long long)x) - 1);
+#else
+    return (uint32_t)__builtin_ctzll(x);
+#endif
+}
+
 // correct_barcode / likelihood1 for barcodes of a 32-bit table (see pcl_correct_one for the semantics).
 // `key32` is the 4-byte device key (marker kept for < 16 bases, dropped for 16).
+//
+// Two phases, so that the common case (a neighbour that is simply absent) is straight-line code:
+//   1. filter: one bucket per neighbour, branch-free; a neighbour survives when it is found or when its
+//      bucket is full (the probe chain may continue in the next bucket).  Survivors are bits of a 64-bit mask
+//      indexed (pos << 2 | base), i.e. already in the reference's (pos, ACGT) order.
+//   2. resolve: the few survivors are probed completely, in mask order, and enter the fp64 posterior in that
+//      order (barcode.rs:319-334: sum order and first-maximum tie-break).
 PCL_HD uint32_t pcl_correct_one32(const DTable &t, uint32_t key32, uint32_t len, uint32_t n_invalid, uint32_t inv_pos,
                                   const uint8_t *qual, uint32_t start, bool rev, double threshold, const double *lut_cap,
                                   uint32_t *out_key) {
@@ -468,44 +491,43 @@ PCL_HD uint32_t pcl_correct_one32(const DTable &t, uint32_t key32, uint32_t len,
     if (t.mode == PCL_TAB_K32_L16 ? len != 16u : len > 15u) return PCL_BC_NO_MATCH;   // no entry of that length
     const uint32_t *keys = reinterpret_cast<const uint32_t *>(t.keys);
     const uint32_t empty = (uint32_t)t.empty, nb = t.n_buckets;
-    bool have = false;
-    double best_like = 0.0, total = 0.0;
-    uint32_t best_key = 0;
     const uint32_t p0 = n_invalid == 1u ? inv_pos : 0u, p1 = n_invalid == 1u ? inv_pos + 1u : len;
+    uint64_t pend = 0;
     for (uint32_t pos = p0; pos < p1; ++pos) {
         const uint32_t sh = 2u * (len - 1u - pos);
         const uint32_t existing = n_invalid == 1u ? 4u : ((key32 >> sh) & 3u);
         const uint32_t base = key32 & ~(3u << sh);
-        uint32_t slot[4];
+        uint32_t m4 = 0;
 #ifdef __CUDA_ARCH__
 #pragma unroll
 #endif
-        for (uint32_t val = 0; val < 4u; ++val) {                      // the four bucket probes are independent
-            slot[val] = 0xFFFFFFFFu;
-            if (val == existing) continue;
+        for (uint32_t val = 0; val < 4u; ++val) {
             const uint32_t cand = base | (val << sh);
-            if (cand == empty) continue;
-            uint32_t b = pcl_hash32_bucket(cand, nb);
+            const bool act = (val != existing) & (cand != empty);
+            // inactive lanes read bucket 0 (one broadcast sector) instead of branching around the loads
+            const uint32_t b = act ? pcl_hash32_bucket(cand, nb) : 0u;
             bool full;
-            uint32_t s = pcl_bucket32(keys, b, cand, empty, &full);
-            while (s == 0xFFFFFFFFu && full) {                          // rare: overflow into the next bucket
-                b = (b + 1u == nb) ? 0u : b + 1u;
-                s = pcl_bucket32(keys, b, cand, empty, &full);
-            }
-            slot[val] = s;
+            const bool any = pcl_bucket32_any(keys, b, cand, empty, &full);
+            m4 |= (uint32_t)(act & (any | full)) << val;
         }
-        if ((slot[0] & slot[1] & slot[2] & slot[3]) == 0xFFFFFFFFu) continue;
+        pend |= (uint64_t)m4 << (4u * pos);
+    }
+    bool have = false;
+    double best_like = 0.0, total = 0.0;
+    uint32_t best_key = 0;
+    while (pend) {
+        const uint32_t bit = pcl_ctz64(pend);
+        pend &= pend - 1;
+        const uint32_t pos = bit >> 2, val = bit & 3u;
+        const uint32_t sh = 2u * (len - 1u - pos);
+        const uint32_t cand = (key32 & ~(3u << sh)) | (val << sh);
+        const uint32_t slot = pcl_probe32(t, cand);
+        if (slot == 0xFFFFFFFFu) continue;
+        const uint32_t c = t.counts[slot];
         const double perr = lut_cap[qual[start + (rev ? len - 1u - pos : pos)]];
-#ifdef __CUDA_ARCH__
-#pragma unroll
-#endif
-        for (uint32_t val = 0; val < 4u; ++val) {                      // BASE_OPTS order A C G T (barcode.rs:322)
-            if (slot[val] == 0xFFFFFFFFu) continue;
-            const uint32_t c = t.counts[slot[val]];
-            const double like = PCL_DMUL((double)(1ull + (uint64_t)c), perr);
-            if (!have || best_like < like) { have = true; best_like = like; best_key = base | (val << sh); }
-            total = PCL_DADD(total, like);
-        }
+        const double like = PCL_DMUL((double)(1ull + (uint64_t)c), perr);          // barcode.rs:326-327
+        if (!have || best_like < like) { have = true; best_like = like; best_key = cand; }   // :345-358
+        total = PCL_DADD(total, like);
     }
     if (!have) return PCL_BC_NO_MATCH;
     const double prob = PCL_DDIV(best_like, total);
