@@ -211,13 +211,8 @@ def main():
     from precellar_b200.configs import v3_layout
     from precellar_b200.pipeline import BarcodePipeline, HostBatch
 
-    uid = None
-    if world > 1:
-        t = torch.zeros(128, dtype=torch.uint8, device="cuda")
-        if rank == 0:
-            t = torch.frombuffer(bytearray(BarcodePipeline.new_unique_id()), dtype=torch.uint8).cuda()
-        dist.broadcast(t, 0)
-        uid = bytes(t.cpu().numpy().tobytes())
+    from precellar_b200.dist import exchange_unique_id
+    uid = exchange_unique_id(BarcodePipeline.new_unique_id, rank, world)
     layout = v3_layout(wl, R2_LEN)
     pipe = BarcodePipeline(layout, device=local_rank, nranks=world, rank=rank, nccl_uid=uid)
     syn = S.Synth(spec, wl)
@@ -260,7 +255,8 @@ def main():
     prof = {k: pipe.profile_get(k) for k in (_ffi.K_COUNT, _ffi.K_CORRECT, _ffi.K_COUNT_LENONLY)}
     pipe.profile_enable(False)
     cnt, mismatch, total = pipe.counts(0)
-    assert total == n * world, (total, n, world)
+    assert total == n * world, (total, n, world)                 # the allreduce summed every rank's shard
+    assert int(cnt.sum()) + mismatch == total
     f_mis_global = mismatch / total
     # the rank's own miss count drives its correct kernel
     f_mis = f_mis_global

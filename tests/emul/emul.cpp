@@ -48,7 +48,8 @@ struct emu_read_io {
 // defects_out: per read.
 int emu_run(const pcl_read_desc *reads, int n_reads, int n_regions, const uint8_t **wl_bytes, const uint64_t **wl_offs,
             const uint64_t *wl_n, emu_read_io *io, uint64_t n, int correct, double threshold, double max_ee, int use_fast,
-            uint64_t **counts_out, uint64_t *scalars_out, uint64_t *defects_out, char *err, int errcap) {
+            uint64_t **counts_out, uint64_t *scalars_out, uint64_t *defects_out, const uint64_t **counts_in,
+            char *err, int errcap) {
     std::string e;
     std::vector<HostTable> ht(n_regions);
     std::vector<std::vector<uint32_t>> counts(n_regions);
@@ -190,6 +191,16 @@ int emu_run(const pcl_read_desc *reads, int n_reads, int n_regions, const uint8_
             io[r].fstatus[i] = (uint16_t)fs;
         }
     }
+    for (int g = 0; g < n_regions; ++g) {
+        for (uint64_t i = 0; i < ht[g].n_entries; ++i) counts_out[g][i] = counts[g][ht[g].index_to_slot[i]];
+        scalars_out[2 * g] = scal[2 * g];
+        scalars_out[2 * g + 1] = scal[2 * g + 1];
+    }
+    // multi-rank runs: pass 2 sees the all-reduced counts (the prior of likelihood1 is the GLOBAL count)
+    if (counts_in)
+        for (int g = 0; g < n_regions; ++g)
+            if (counts_in[g])
+                for (uint64_t i = 0; i < ht[g].n_entries; ++i) counts[g][ht[g].index_to_slot[i]] = (uint32_t)counts_in[g][i];
     // ---- pass 2 (mirrors k_enum_all + k_correct) ----
     if (correct) {
         const bool check_ee = max_ee < DBL_MAX;
@@ -240,11 +251,6 @@ int emu_run(const pcl_read_desc *reads, int n_reads, int n_regions, const uint8_
                 if (code != PCL_BC_EXACT && code != PCL_BC_NO_MATCH) io[r].fstatus[w.rec] |= (uint16_t)(code << (4 + 3 * w.j));
             }
         }
-    }
-    for (int g = 0; g < n_regions; ++g) {
-        for (uint64_t i = 0; i < ht[g].n_entries; ++i) counts_out[g][i] = counts[g][ht[g].index_to_slot[i]];
-        scalars_out[2 * g] = scal[2 * g];
-        scalars_out[2 * g + 1] = scal[2 * g + 1];
     }
     return PCL_OK;
 }

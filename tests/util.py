@@ -216,7 +216,7 @@ def alloc_results(info: _ffi.ReadInfo, n: int) -> ReadResults:
 
 
 def run_emul(layout: CompiledLayout, batches: Sequence[HostBatch], correct=True, threshold=0.975,
-             max_expected_errors=_ffi.F64_MAX, use_fast=True):
+             max_expected_errors=_ffi.F64_MAX, use_fast=True, global_counts=None):
     """Returns (infos, results, counts{slot: (counts, mismatch, total)}, defects)."""
     L = emul_lib()
     infos, strides = emul_infos(layout)
@@ -259,11 +259,17 @@ def run_emul(layout: CompiledLayout, batches: Sequence[HostBatch], correct=True,
         cp[g] = c.ctypes.data
     scal = np.zeros(2 * max(n_regions, 1), np.uint64)
     defects = np.zeros(n_reads, np.uint64)
+    gin = None
+    if global_counts is not None:                    # {slot: uint64 counts in whitelist order} from an allreduce
+        gin = (C.c_void_p * max(n_regions, 1))()
+        gkeep = [np.ascontiguousarray(global_counts[g], np.uint64) for g in range(n_regions)]
+        for g in range(n_regions):
+            gin[g] = gkeep[g].ctypes.data
     err = C.create_string_buffer(512)
     L.emu_run.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64,
-                          C.c_int, C.c_double, C.c_double, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_char_p, C.c_int]
+                          C.c_int, C.c_double, C.c_double, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_char_p, C.c_int]
     rc = L.emu_run(descs, n_reads, n_regions, bp, op, wl_n, io, n, int(correct), threshold, max_expected_errors,
-                   int(use_fast), cp, scal.ctypes.data, defects.ctypes.data, err, 512)
+                   int(use_fast), cp, scal.ctypes.data, defects.ctypes.data, gin, err, 512)
     if rc != 0:
         raise _ffi.PclError(rc, err.value.decode())
     counts = {}
