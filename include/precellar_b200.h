@@ -27,6 +27,10 @@
  *   pcl_counts_fetch        Whitelist{barcode_counts, mismatch_count, total_count}
  *                           (precellar/src/barcode.rs:362-366,431-437)
  *   pcl_qc_fetch            QcFastq::num_reads / num_defect (precellar/src/qc.rs:21-27)
+ *   pcl_qc_accumulate /     QcFastq::update: bases and Q30 bases of barcode / umi / read1 / read2
+ *   pcl_qc_fetch_categories (precellar/src/qc.rs:30-69)
+ *   pcl_fastq_*             Read::open + FastqReader::read_record + the per-file half of BatchedFqReader::next
+ *                           (seqspec/src/read.rs:98-108,137-155; precellar/src/align/fastq.rs:400-448,612-621)
  *
  * Threading: one host thread drives one ctx (one GPU).  Calls on a ctx are not re-entrant.
  * Different ctxs are independent.  Work on a chunk is stream-ordered on the chunk's stream;
@@ -133,7 +137,8 @@ typedef struct {
     uint8_t has_target;
     uint8_t fixed_layout;                  /* all elements fixed-length except an optional last one   */
     uint8_t needs_payload;                 /* seq/qual bytes are read (else lengths only)             */
-    uint8_t reserved[3];
+    uint8_t qual_only;                     /* QC mode, insert read: only the quality plane is used    */
+    uint8_t reserved[2];
     uint8_t bc_elem[PCL_MAX_BC_PER_READ];  /* element index of each barcode element                   */
     uint8_t bc_key_bytes[PCL_MAX_BC_PER_READ];   /* 4 or 8                                            */
     uint8_t umi_elem[PCL_MAX_UMI_PER_READ];      /* element index of each UMI element                 */
@@ -170,6 +175,10 @@ int pcl_comm_init(pcl_ctx *ctx, int nranks, int rank, const void *uid128);
 
 /* ---- configuration ----------------------------------------------------------------------- */
 int pcl_layout_set(pcl_ctx *ctx, const pcl_read_desc *reads, int n_reads);
+/* FASTQ QC of inserts (QcFastq, precellar/src/qc.rs:30-69) needs every quality byte of the target segments.
+ * Call before pcl_layout_set: reads that hold a target then carry a quality plane of ceil16(Read.max_len)
+ * bytes per record (Read.max_len must be > 0), uploaded with pcl_chunk_upload like any other plane. */
+int pcl_qc_enable(pcl_ctx *ctx, int on);
 int pcl_read_info_get(const pcl_ctx *ctx, int read_slot, pcl_read_info *out);
 /* Whitelist of one barcode region: n byte strings, string i = bytes[offsets[i] .. offsets[i+1]).
  * File order; duplicates are dropped keeping the first (IndexSet semantics).  Entries must be
@@ -204,15 +213,33 @@ int pcl_chunk_fetch(pcl_chunk *chunk, int read_slot, const pcl_read_results *out
 int pcl_counts_fetch(pcl_ctx *ctx, int region_slot, uint64_t *counts, uint64_t *mismatch, uint64_t *total);
 /* per read file: num_reads, num_defect (2 * n_reads values) accumulated by pcl_count since the last reset */
 int pcl_qc_fetch(pcl_ctx *ctx, uint64_t *per_read);
+/* QcFastq::update over one chunk (after pcl_count; independent of pcl_correct): accumulates, for the categories
+ * umi, barcode, read1, read2 (in that order), {num_reads, num_total_bases, num_q30_bases}.  Needs pcl_qc_enable
+ * when a read holds a target.  pcl_counts_reset clears the accumulators. */
+int pcl_qc_accumulate(pcl_ctx *ctx, pcl_chunk *chunk);
+int pcl_qc_fetch_categories(pcl_ctx *ctx, uint64_t *cat12);
 /* Unpack a key into ASCII (host utility): returns the length or -1. */
 int pcl_key_decode(uint64_t key, char *out32);
+
+/* ---- host ingest: FASTQ (plain or gzip; the files of one read are concatenated) -> SoA planes ---------- */
+typedef struct pcl_fastq pcl_fastq;
+int pcl_fastq_open(const char *const *paths, int n_paths, pcl_fastq **out);
+void pcl_fastq_close(pcl_fastq *r);
+const char *pcl_fastq_error(const pcl_fastq *r);
+/* Reads up to max_records records into [max_records][stride] planes (seq/qual may be NULL), u16 lengths and
+ * the hash of the read name (definition up to the first blank, trailing /1 or /2 stripped: the value
+ * BatchedFqReader compares across files).  text/off (optional) keep definition, sequence and quality of every
+ * record: off[3i] .. off[3i+3] delimit them inside text; *text_used is advanced.  Returns the number of records
+ * (0 at end of input) or a negative pcl_status (pcl_fastq_error has the message). */
+int64_t pcl_fastq_read(pcl_fastq *r, uint64_t max_records, uint32_t stride, uint8_t *seq, uint8_t *qual, uint16_t *len,
+                       uint64_t *name_hash, uint8_t *text, uint64_t text_cap, uint64_t *off, uint64_t *text_used);
 
 /* ---- pinned host memory ------------------------------------------------------------------- */
 void *pcl_host_alloc(uint64_t bytes);
 void pcl_host_free(void *p);
 
 /* ---- instrumentation (used by bench.py; CUDA events on the launching stream) --------------- */
-enum { PCL_K_COUNT = 0, PCL_K_CORRECT = 1, PCL_K_COUNT_LENONLY = 2, PCL_K_ENUM = 3, PCL_K_MAX = 4 };
+enum { PCL_K_COUNT = 0, PCL_K_CORRECT = 1, PCL_K_COUNT_LENONLY = 2, PCL_K_ENUM = 3, PCL_K_QC = 4, PCL_K_MAX = 6 };
 int pcl_profile_enable(pcl_ctx *ctx, int on);                    /* bracket every kernel with events */
 /* accumulated ms and launches of kernel k since the last pcl_profile_reset (syncs the ctx) */
 int pcl_profile_get(pcl_ctx *ctx, int k, double *ms, uint64_t *launches);

@@ -25,7 +25,7 @@ SPLIT_OK, SPLIT_ANCHOR_NOT_FOUND, SPLIT_PATTERN_MISMATCH, SPLIT_MULTI_TARGET = 0
 FSTATUS_TARGET = 0x4
 BC_EXACT, BC_ABSENT, BC_NO_MATCH, BC_CORRECTED, BC_LOW_CONF, BC_EXCEED_EE = 0, 3, 4, 5, 6, 7
 KEY_ABSENT32, KEY_ABSENT64, COORD_ABSENT = 0xFFFFFFFF, 0xFFFFFFFFFFFFFFFF, 0xFFFFFFFF
-K_COUNT, K_CORRECT, K_COUNT_LENONLY, K_ENUM = 0, 1, 2, 3
+K_COUNT, K_CORRECT, K_COUNT_LENONLY, K_ENUM, K_QC = 0, 1, 2, 3, 4
 F64_MAX = 1.7976931348623157e308
 
 
@@ -42,7 +42,7 @@ class ReadDesc(C.Structure):
 
 class ReadInfo(C.Structure):
     _fields_ = [("n_bc", C.c_uint8), ("n_umi", C.c_uint8), ("has_target", C.c_uint8), ("fixed_layout", C.c_uint8),
-                ("needs_payload", C.c_uint8), ("reserved", C.c_uint8 * 3),
+                ("needs_payload", C.c_uint8), ("qual_only", C.c_uint8), ("reserved", C.c_uint8 * 2),
                 ("bc_elem", C.c_uint8 * PCL_MAX_BC_PER_READ), ("bc_key_bytes", C.c_uint8 * PCL_MAX_BC_PER_READ),
                 ("umi_elem", C.c_uint8 * PCL_MAX_UMI_PER_READ), ("umi_key_bytes", C.c_uint8 * PCL_MAX_UMI_PER_READ),
                 ("static_start", C.c_uint16 * PCL_MAX_ELEMS)]
@@ -69,6 +69,8 @@ SYMBOLS = [
     "pcl_counts_allreduce", "pcl_correct", "pcl_chunk_fetch", "pcl_counts_fetch", "pcl_qc_fetch", "pcl_key_decode",
     "pcl_host_alloc", "pcl_host_free", "pcl_profile_enable", "pcl_profile_get", "pcl_profile_reset",
     "pcl_launch_count", "pcl_timer_start", "pcl_timer_stop_ms",
+    "pcl_qc_enable", "pcl_qc_accumulate", "pcl_qc_fetch_categories",
+    "pcl_fastq_open", "pcl_fastq_close", "pcl_fastq_error", "pcl_fastq_read",
 ]
 
 _lib = None
@@ -120,6 +122,13 @@ def lib() -> C.CDLL:
         "pcl_launch_count": (u64, [vp]),
         "pcl_timer_start": (i32, [vp]),
         "pcl_timer_stop_ms": (i32, [vp, C.POINTER(f64)]),
+        "pcl_qc_enable": (i32, [vp, i32]),
+        "pcl_qc_accumulate": (i32, [vp, vp]),
+        "pcl_qc_fetch_categories": (i32, [vp, vp]),
+        "pcl_fastq_open": (i32, [C.POINTER(C.c_char_p), i32, C.POINTER(vp)]),
+        "pcl_fastq_close": (None, [vp]),
+        "pcl_fastq_error": (C.c_char_p, [vp]),
+        "pcl_fastq_read": (C.c_int64, [vp, u64, u32, vp, vp, vp, vp, vp, u64, vp, C.POINTER(u64)]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)

@@ -1,0 +1,118 @@
+"""Minimal zstd codec over the system libzstd.so.1 (ctypes; the image ships the library without headers).
+
+Used for ``.zst`` inputs (seqspec/src/utils.rs:44-56) and the ``R1.fq.zst`` / ``R2.fq.zst`` outputs of
+``make_fastq`` (python/src/lib.rs:136-146).  Only stable public entry points of libzstd are used.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import ctypes.util
+
+_lib = None
+
+
+class _Buf(C.Structure):
+    _fields_ = [("ptr", C.c_void_p), ("size", C.c_size_t), ("pos", C.c_size_t)]
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        name = ctypes.util.find_library("zstd") or "libzstd.so.1"
+        try:
+            L = C.CDLL(name)
+        except OSError as e:
+            raise RuntimeError("libzstd is not available on this system") from e
+        L.ZSTD_compressBound.restype = C.c_size_t
+        L.ZSTD_compressBound.argtypes = [C.c_size_t]
+        L.ZSTD_compress.restype = C.c_size_t
+        L.ZSTD_compress.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_int]
+        L.ZSTD_isError.restype = C.c_uint
+        L.ZSTD_isError.argtypes = [C.c_size_t]
+        L.ZSTD_getErrorName.restype = C.c_char_p
+        L.ZSTD_getErrorName.argtypes = [C.c_size_t]
+        L.ZSTD_createDStream.restype = C.c_void_p
+        L.ZSTD_freeDStream.argtypes = [C.c_void_p]
+        L.ZSTD_initDStream.restype = C.c_size_t
+        L.ZSTD_initDStream.argtypes = [C.c_void_p]
+        L.ZSTD_decompressStream.restype = C.c_size_t
+        L.ZSTD_decompressStream.argtypes = [C.c_void_p, C.POINTER(_Buf), C.POINTER(_Buf)]
+        _lib = L
+    return _lib
+
+
+def _check(code: int) -> int:
+    L = lib()
+    if L.ZSTD_isError(code):
+        raise RuntimeError("zstd: " + L.ZSTD_getErrorName(code).decode())
+    return code
+
+
+def compress(data: bytes, level: int = 9) -> bytes:
+    """One frame (the reference's default level for zstd outputs is 9, seqspec/src/utils.rs:33-35)."""
+    L = lib()
+    cap = L.ZSTD_compressBound(len(data))
+    out = C.create_string_buffer(cap)
+    n = _check(L.ZSTD_compress(out, cap, data, len(data), level))
+    return out.raw[:n]
+
+
+def decompress(data: bytes) -> bytes:
+    """All frames of a buffer (streaming API: content sizes need not be recorded)."""
+    L = lib()
+    ds = L.ZSTD_createDStream()
+    try:
+        _check(L.ZSTD_initDStream(ds))
+        src = C.create_string_buffer(data, len(data))
+        inb = _Buf(C.cast(src, C.c_void_p), len(data), 0)
+        chunk = 1 << 20
+        dst = C.create_string_buffer(chunk)
+        parts = []
+        while inb.pos < inb.size:
+            outb = _Buf(C.cast(dst, C.c_void_p), chunk, 0)
+            _check(L.ZSTD_decompressStream(ds, C.byref(outb), C.byref(inb)))
+            parts.append(dst.raw[:outb.pos])
+        # drain
+        while True:
+            outb = _Buf(C.cast(dst, C.c_void_p), chunk, 0)
+            r = _check(L.ZSTD_decompressStream(ds, C.byref(outb), C.byref(inb)))
+            if outb.pos:
+                parts.append(dst.raw[:outb.pos])
+            if outb.pos < chunk or r == 0:
+                break
+        return b"".join(parts)
+    finally:
+        L.ZSTD_freeDStream(ds)
+
+
+def decompress_file(path: str) -> bytes:
+    with open(path, "rb") as fh:
+        return decompress(fh.read())
+
+
+class Writer:
+    """Append-only .zst writer: independent frames of up to `block` bytes (a valid multi-frame zstd file)."""
+
+    def __init__(self, path: str, level: int = 9, block: int = 8 << 20):
+        self.fh = open(path, "wb")
+        self.level, self.block = level, block
+        self.buf = bytearray()
+
+    def write(self, data: bytes) -> None:
+        self.buf += data
+        while len(self.buf) >= self.block:
+            self.fh.write(compress(bytes(self.buf[:self.block]), self.level))
+            del self.buf[:self.block]
+
+    def close(self) -> None:
+        if self.fh:
+            if self.buf:
+                self.fh.write(compress(bytes(self.buf), self.level))
+            self.fh.close()
+            self.fh = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()

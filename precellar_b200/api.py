@@ -1,0 +1,293 @@
+"""Public API of the path, mirroring precellar's: ``FastqProcessor`` and ``make_fastq``.
+
+    reference                                                     here
+    FastqProcessor::{new, with_modality, with_barcode_correct_prob, gen_barcoded_fastq, get_fastq_qc}
+        precellar/src/align/fastq.rs:20-154                       class FastqProcessor
+    AnnotatedFastq / Barcode                                      dataclasses below
+        precellar/src/align/fastq.rs:528-604
+    precellar.make_fastq(assay, *, modality, out_dir, correct_barcode=False)
+        python/src/lib.rs:117-171                                 make_fastq
+
+The per-read work (split, whitelist count, correction, QC counters) runs in the CUDA library; this module
+only moves batches in and turns the result planes back into records.
+"""
+from __future__ import annotations
+
+import os
+from dataclasses import dataclass
+from typing import Iterator, List, Optional, Sequence, Union
+
+import numpy as np
+
+from . import _ffi
+from .ingest import FastqBatch, GroupReader
+from .layout import CompiledLayout, compile_layout, is_paired_end
+from .pipeline import BarcodePipeline, Chunk, assemble, decode_key_py, rev_compl
+from .seqspec import Assay, parse_modality
+
+
+@dataclass
+class FastqRecord:
+    """name + description (the FASTQ definition line without '@'), sequence, quality."""
+    definition: bytes
+    sequence: bytes
+    quality: bytes
+
+    @property
+    def name(self) -> bytes:
+        return self.definition.split(None, 1)[0] if self.definition else b""
+
+    def to_bytes(self) -> bytes:
+        return b"@" + self.definition + b"\n" + self.sequence + b"\n+\n" + self.quality + b"\n"
+
+
+@dataclass
+class Barcode:                                   # fastq.rs:528-532
+    raw: FastqRecord
+    corrected: Optional[bytes]
+
+
+@dataclass
+class AnnotatedFastq:                            # fastq.rs:549-556
+    barcode: Optional[Barcode]
+    umi: Optional[FastqRecord]
+    read1: Optional[FastqRecord]
+    read2: Optional[FastqRecord]
+
+
+def _as_assays(assay) -> List[Assay]:
+    """extract_assays (python/src/pyseqspec.rs:12-27): a path, an Assay, or a list of either."""
+    items = assay if isinstance(assay, (list, tuple)) else [assay]
+    return [a if isinstance(a, Assay) else Assay(os.fspath(a)) for a in items]
+
+
+class FastqProcessor:
+    """Barcode counting, correction and annotation of the FASTQ files named by one or more assays."""
+
+    def __init__(self, assay, device: int = 0):
+        self.assays = _as_assays(assay)
+        self.device = device
+        self.current_modality: Optional[str] = None
+        self.barcode_correct_prob = 0.975        # fastq.rs:39
+        self.mismatch_in_barcode = 1             # fastq.rs:40 (no setter in the reference either)
+        self._qc = None
+        self.compute_qc = True
+
+    def with_modality(self, modality: str) -> "FastqProcessor":
+        self.current_modality = parse_modality(modality)
+        return self
+
+    def with_barcode_correct_prob(self, prob: float) -> "FastqProcessor":
+        self.barcode_correct_prob = float(prob)
+        return self
+
+    def modality(self) -> str:
+        if self.current_modality is None:
+            raise RuntimeError("modality not set, please call set_modality first")
+        return self.current_modality
+
+    def get_fastq_qc(self) -> dict:
+        """QcFastq::to_json of everything processed so far (precellar/src/qc.rs:91-121)."""
+        if self._qc is None:
+            raise RuntimeError("fastq qc not found")
+        return self._qc
+
+    def is_paired_end(self) -> bool:
+        vals = {is_paired_end(compile_layout(a, self.modality(), require_files=True)) for a in self.assays}
+        if len(vals) != 1:
+            raise RuntimeError("Not all readers are with the same paired-end status")
+        return vals.pop()
+
+    # ------------------------------------------------------------------------------------------
+    def gen_barcoded_fastq(self, correct_barcode: bool, chunk_size: int = 1_000_000) -> Iterator[List[AnnotatedFastq]]:
+        """Batches of annotated records, assays one after the other (fastq.rs:109-153, 243-255)."""
+        modality = self.modality()
+        per_file = None
+        cats = np.zeros((4, 3), np.uint64)
+        read_ids: List[str] = []
+        for assay in self.assays:
+            layout = compile_layout(assay, modality, require_files=True)
+            for p in layout.reads:
+                if p.has_barcode and not p.files:
+                    raise RuntimeError(f"Failed to open FASTQ file: {p.read_id}")             # barcode.rs:88-90
+            # reads of the modality that carry barcodes but no files make BarcodeAnalyzer::new panic too
+            for read, info in assay.get_segments_by_modality(modality):
+                if any(e.is_barcode() for e in info) and not read.fastq_paths():
+                    raise RuntimeError(f"Failed to open FASTQ file: {read.read_id}")
+            pipe = BarcodePipeline(layout, device=self.device, qc=self.compute_qc)
+            try:
+                yield from self._run_assay(pipe, layout, correct_barcode, chunk_size)
+                q = pipe.qc()
+                cats += pipe.qc_categories() if self.compute_qc else 0
+                if per_file is None:
+                    per_file, read_ids = q.copy(), [p.read_id for p in layout.reads]
+                else:                                                                      # QcFastq::extend, keyed by read id
+                    for r, p in enumerate(layout.reads):
+                        if p.read_id in read_ids:
+                            per_file[read_ids.index(p.read_id)] += q[r]
+                        else:
+                            read_ids.append(p.read_id)
+                            per_file = np.vstack([per_file, q[r:r + 1]])
+            finally:
+                pipe.close()
+            out = {}
+            defect = {rid: float(per_file[k, 1]) / float(per_file[k, 0]) for k, rid in enumerate(read_ids) if per_file[k, 1] > 0}
+            if defect:
+                out["frac_reads_with_misformed_structure"] = defect
+            names = ("umi", "barcode", "read1", "read2")
+            out["frac_q30_bases"] = {names[k]: float(cats[k, 2]) / float(cats[k, 1]) for k in range(4) if cats[k, 1] > 0}
+            self._qc = out
+
+    def _run_assay(self, pipe: BarcodePipeline, layout: CompiledLayout, correct_barcode: bool, chunk_size: int):
+        n_reads = len(layout.reads)
+        strides = [pipe.stride(r) for r in range(n_reads)]
+        qonly = [bool(pipe.infos[r].qual_only) for r in range(n_reads)]
+        files = [p.files for p in layout.reads]
+        bases = sum((p.max_len or 100) for p in layout.reads)
+        per_chunk = max(1024, int(chunk_size) // max(bases, 1))
+
+        # pass 1 (BarcodeAnalyzer::new): every batch is uploaded, counted and kept resident on the device
+        chunks: List[Chunk] = []
+        sizes: List[int] = []
+        rdr = GroupReader(files, strides, qonly, keep_text=False)
+        try:
+            while True:
+                got = rdr.next(per_chunk)
+                if got is None:
+                    break
+                n = len(got[0].batch.length)
+                ch = pipe.new_chunk(n)
+                ch.reset(n)
+                for r in range(n_reads):
+                    ch.upload(r, got[r].batch)
+                pipe.count(ch)
+                if self.compute_qc:
+                    pipe.qc_accumulate(ch)
+                pipe.sync()                      # the host planes of this batch go out of scope
+                chunks.append(ch)
+                sizes.append(n)
+        finally:
+            rdr.close()
+        # "All whitelists should have the same total read count" (barcode.rs:125-129)
+        totals = {pipe.counts(g)[2] for g in range(len(layout.region_ids))}
+        if len(totals) > 1:
+            raise _ffi.PclError(_ffi.PCL_ERR_INPUT, "All whitelists should have the same total read count")
+        self.num_reads = totals.pop() if totals else 0
+        pipe.allreduce()
+
+        # pass 2 (AnnotatedFastqReader): correct, fetch, and rebuild the records from a second read of the files
+        rdr = GroupReader(files, [0] * n_reads, [False] * n_reads, keep_text=True,
+                          text_bytes=[2 * max(p.max_len, 1024) + 256 for p in layout.reads])
+        try:
+            for ch, n in zip(chunks, sizes):
+                if correct_barcode:
+                    pipe.correct(ch, self.barcode_correct_prob)
+                results = [ch.fetch(r) for r in range(n_reads)]
+                text = rdr.next(n)
+                assert text is not None and len(text[0].batch.length) == n
+                yield self._annotate(layout, pipe, text, results, correct_barcode)
+                ch.close()
+                pipe.chunks.remove(ch)
+        finally:
+            rdr.close()
+
+    @staticmethod
+    def _annotate(layout: CompiledLayout, pipe: BarcodePipeline, text: Sequence[FastqBatch], results,
+                  correct: bool) -> List[AnnotatedFastq]:
+        batches = [t.batch for t in text]
+        g = assemble(layout, pipe.infos, batches, results, correct=correct)
+        out: List[AnnotatedFastq] = []
+        n_reads = len(layout.reads)
+        for i in np.flatnonzero(g.has_barcode):                       # groups without a barcode are dropped (fastq.rs:381-385)
+            i = int(i)
+            recs = [t.record(i) for t in text]
+            bc_def = None
+            bseq = bqual = corr = b""
+            for b in g.bc:
+                if not b["present"][i]:
+                    continue
+                r = b["read"]
+                c = int(b["coord"][i])
+                s0, ln = c >> 16, c & 0xFFFF
+                s, q = recs[r][1][s0:s0 + ln], recs[r][2][s0:s0 + ln]
+                if layout.reads[r].is_reverse:
+                    s, q = rev_compl(s), q[::-1]
+                if bc_def is None:
+                    bc_def = recs[r][0]
+                bseq += s
+                bqual += q
+                if g.corrected_some[i]:
+                    corr += s if (not correct or int(b["code"][i]) == _ffi.BC_EXACT) else decode_key_py(int(b["key"][i]))
+            umi = None
+            for r in range(n_reads):
+                last = None
+                for u in g.umi:
+                    if u["read"] == r and u["present"][i]:
+                        last = u
+                if last is None:
+                    continue
+                c = int(last["coord"][i])
+                s0, ln = c >> 16, c & 0xFFFF
+                s, q = recs[r][1][s0:s0 + ln], recs[r][2][s0:s0 + ln]
+                if layout.reads[r].is_reverse:
+                    s, q = rev_compl(s), q[::-1]
+                if umi is None:
+                    umi = FastqRecord(recs[r][0], s, q)
+                else:                                                  # extend_fastq_record (fastq.rs:606-610)
+                    umi.sequence += s
+                    umi.quality += q
+            reads = []
+            for rd in (g.read1, g.read2):
+                o = int(rd["owner"][i])
+                if o < 0:
+                    reads.append(None)
+                else:
+                    c = int(rd["coord"][i])
+                    s0, ln = c >> 16, c & 0xFFFF
+                    reads.append(FastqRecord(recs[o][0], recs[o][1][s0:s0 + ln], recs[o][2][s0:s0 + ln]))
+            out.append(AnnotatedFastq(Barcode(FastqRecord(bc_def, bseq, bqual), corr if g.corrected_some[i] else None),
+                                      umi, reads[0], reads[1]))
+        return out
+
+
+def make_fastq(assay, *, modality: str, out_dir, correct_barcode: bool = False, device: int = 0) -> None:
+    """Generate consolidated fastq files from the sequencing specification.
+
+    The barcodes and UMIs are concatenated to the read 1 sequence; fixed sequences and linkers are removed
+    (python/src/lib.rs:114-171).  Writes ``R1.fq.zst`` and, for paired-end layouts, ``R2.fq.zst``; with
+    ``correct_barcode`` reads whose barcode cannot be corrected are dropped and the corrected sequence is written.
+    """
+    from . import _zstd
+    proc = FastqProcessor(assay, device=device).with_modality(modality)
+    out_dir = os.fspath(out_dir)
+    os.makedirs(out_dir, exist_ok=True)
+    paired = proc.is_paired_end()
+    w1 = _zstd.Writer(os.path.join(out_dir, "R1.fq.zst"))
+    w2 = _zstd.Writer(os.path.join(out_dir, "R2.fq.zst")) if paired else None
+    try:
+        for batch in proc.gen_barcoded_fastq(correct_barcode, 1_000_000):
+            b1, b2 = bytearray(), bytearray()
+            for rec in batch:
+                bc = rec.barcode
+                if correct_barcode and bc.corrected is None:
+                    continue
+                raw = FastqRecord(bc.raw.definition, bc.corrected if bc.corrected is not None else bc.raw.sequence, bc.raw.quality)
+                if rec.umi is not None:
+                    raw.sequence += rec.umi.sequence
+                    raw.quality += rec.umi.quality
+                if rec.read1 is None:
+                    raise RuntimeError("called `Option::unwrap()` on a `None` value: read1")     # lib.rs:160
+                raw.sequence += rec.read1.sequence
+                raw.quality += rec.read1.quality
+                b1 += raw.to_bytes()
+                if w2 is not None:
+                    if rec.read2 is None:
+                        raise RuntimeError("called `Option::unwrap()` on a `None` value: read2") # lib.rs:164
+                    b2 += rec.read2.to_bytes()
+            w1.write(bytes(b1))
+            if w2 is not None:
+                w2.write(bytes(b2))
+    finally:
+        w1.close()
+        if w2 is not None:
+            w2.close()

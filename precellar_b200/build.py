@@ -14,8 +14,8 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libprecellar_b200.so")
-SOURCES = [os.path.join(CSRC, "pcl.cu")]
-DEPS = [os.path.join(CSRC, f) for f in ("pcl.cu", "kernels.cuh", "hd_core.h", "host_build.h")] + \
+SOURCES = [os.path.join(CSRC, "pcl.cu"), os.path.join(CSRC, "ingest.cpp")]
+DEPS = [os.path.join(CSRC, f) for f in ("pcl.cu", "kernels.cuh", "hd_core.h", "host_build.h", "ingest.cpp")] + \
        [os.path.join(HERE, "..", "include", "precellar_b200.h")]
 
 NVCC_FLAGS = [
@@ -42,7 +42,7 @@ def is_stale() -> bool:
 def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not is_stale():
         return OUT
-    cmd = [nvcc_path()] + NVCC_FLAGS + ["-o", OUT] + SOURCES + ["-ldl"]
+    cmd = [nvcc_path()] + NVCC_FLAGS + ["-o", OUT] + SOURCES + ["-ldl", "-lz"]
     proc = subprocess.run(cmd, capture_output=True, text=True)
     log = proc.stdout + proc.stderr
     with open(os.path.join(HERE, "build.log"), "w") as fh:

@@ -59,6 +59,7 @@ struct DRead {
     uint32_t max_len;    // reader truncation, 0 = none
     uint32_t stride;     // bytes per record slot
     uint8_t n_bc, n_umi, has_target, needs_payload;
+    uint8_t qual_only, pad0[3];   // QC mode: insert read that carries only a quality plane
     DElem elems[PCL_MAX_ELEMS];
     FastLayout fast;
 };

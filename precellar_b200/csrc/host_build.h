@@ -32,7 +32,7 @@ inline int pcl_build_fail(std::string *err, int code, const char *fmt, ...) {
 
 // Derive the device-side description of one read.  bc_region[j] = whitelist region of barcode j.
 inline int pcl_build_read(int r, const pcl_read_desc &rd, DRead *out, pcl_read_info *info_out, int *bc_region,
-                          std::string *err) {
+                          std::string *err, bool qc = false) {
     if (rd.n_elems < 1 || rd.n_elems > PCL_MAX_ELEMS)
         return pcl_build_fail(err, PCL_ERR_UNSUPPORTED, "read %d: %d elements outside 1..%d", r, rd.n_elems, PCL_MAX_ELEMS);
     DRead d;
@@ -98,11 +98,20 @@ inline int pcl_build_read(int r, const pcl_read_desc &rd, DRead *out, pcl_read_i
     }
     uint32_t need = payload ? reach : 0;
     if (rd.max_len && need > rd.max_len) need = rd.max_len;
+    bool qual_only = false;
+    if (qc && info.has_target) {                       // QcFastq reads every quality byte of the target segment
+        if (rd.max_len == 0)
+            return pcl_build_fail(err, PCL_ERR_UNSUPPORTED, "read %d: FASTQ QC of a read with a target needs Read.max_len > 0", r);
+        if (rd.max_len > need) need = rd.max_len;
+        qual_only = !payload;
+    }
     uint32_t stride = need ? ((need + 15u) / 16u) * 16u : 0;
     if (stride > PCL_MAX_STRIDE)
         return pcl_build_fail(err, PCL_ERR_UNSUPPORTED, "read %d: %u payload bytes per record exceed %d", r, stride, PCL_MAX_STRIDE);
     if (start > 0xFFFF) return pcl_build_fail(err, PCL_ERR_UNSUPPORTED, "read %d: layout longer than 65535", r);
     d.stride = stride;
+    d.qual_only = qual_only ? 1 : 0;
+    info.qual_only = d.qual_only;
     d.fixed_layout = fixed ? 1 : 0;
     d.n_bc = info.n_bc; d.n_umi = info.n_umi; d.has_target = info.has_target; d.needs_payload = payload ? 1 : 0;
     info.fixed_layout = d.fixed_layout;

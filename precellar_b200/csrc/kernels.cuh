@@ -425,6 +425,102 @@ __global__ void __launch_bounds__(PCL_BLOCK) k_correct(const __grid_constant__ C
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// k_qc: QcFastq::update (precellar/src/qc.rs:30-69) for one read file of a chunk: bases and Q30 bases of the
+// barcode / UMI / target segments.  Categories: 0 umi, 1 barcode, 2 read1, 3 read2; per category
+// {num_reads, num_total_bases, num_q30_bases}.  `**s - 33 >= 30` is evaluated on u8 and wraps in release
+// builds of the reference, so bytes below 33 count as Q30 as well.
+// ------------------------------------------------------------------------------------------------
+struct QcParams {
+    DRead rd;
+    const uint8_t *qual;
+    const uint16_t *len;
+    const uint16_t *fstatus;
+    const uint32_t *tcoord;
+    const uint32_t *bcoord[PCL_MAX_BC_PER_READ];
+    const uint32_t *ucoord[PCL_MAX_UMI_PER_READ];
+    uint8_t bc_elem[PCL_MAX_BC_PER_READ];
+    uint8_t umi_elem[PCL_MAX_UMI_PER_READ];
+    uint16_t static_start[PCL_MAX_ELEMS];
+    uint64_t n;
+    unsigned long long *cat;      // [12]
+};
+
+__device__ __forceinline__ uint32_t pcl_q30_range(const uint8_t *row, uint32_t start, uint32_t len) {
+    // the row is 16-byte aligned; walk the 32-bit words that overlap [start, start+len)
+    const uint32_t *w = reinterpret_cast<const uint32_t *>(row);
+    const uint32_t hi = start + len;
+    uint32_t cnt = 0;
+    for (uint32_t k = start >> 2; (k << 2) < hi; ++k) {
+        const uint32_t b = k << 2;
+        const uint32_t c0 = start > b ? start - b : 0u, c1 = b + 4u > hi ? b + 4u - hi : 0u;
+        uint32_t mask = 0xFFFFFFFFu;
+        if (c0) mask &= 0xFFFFFFFFu << (8u * c0);
+        if (c1) mask &= 0xFFFFFFFFu >> (8u * c1);
+        const uint32_t v = __ldg(w + k);
+        const uint32_t q30 = __vcmpgeu4(v, 0x3F3F3F3Fu) | __vcmpltu4(v, 0x21212121u);   // q >= 63 or (wrapping) q < 33
+        cnt += __popc(q30 & mask) >> 3;
+    }
+    return cnt;
+}
+
+// coordinates of element e of a fixed layout for a record of (truncated) length L, or PCL_COORD_ABSENT
+__device__ __forceinline__ uint32_t pcl_static_coord(const DRead &rd, const uint16_t *static_start, uint32_t e, uint32_t L) {
+    const uint32_t s = static_start[e], mn = rd.elems[e].min_len, mx = rd.elems[e].max_len;
+    if (s >= L || s + mn > L) return PCL_COORD_ABSENT;
+    const uint32_t hi = s + mx < L ? s + mx : L;
+    return (s << 16) | (hi - s);
+}
+
+__global__ void __launch_bounds__(PCL_BLOCK) k_qc(const __grid_constant__ QcParams p) {
+    const DRead &rd = p.rd;
+    unsigned long long acc[6] = {0, 0, 0, 0, 0, 0};      // umi bases,q30 ; barcode bases,q30 ; target bases,q30
+    unsigned long long n_target = 0;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < p.n; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t fs = p.fstatus[i];
+        if ((fs & 3u) != PCL_SPLIT_OK) continue;          // defect records contribute no segment (fastq.rs:369-374)
+        uint32_t L = p.len[i];
+        if (rd.max_len && L > rd.max_len) L = rd.max_len;
+        const uint8_t *row = p.qual + i * (uint64_t)rd.stride;
+        for (uint32_t j = 0; j < rd.n_bc; ++j) {
+            if (PCL_BC_CODE(fs, j) == PCL_BC_ABSENT) continue;
+            const uint32_t c = rd.fixed_layout ? pcl_static_coord(rd, p.static_start, p.bc_elem[j], L) : p.bcoord[j][i];
+            acc[2] += c & 0xFFFFu;
+            acc[3] += pcl_q30_range(row, c >> 16, c & 0xFFFFu);
+        }
+        uint32_t uc = PCL_COORD_ABSENT;                   // the last UMI segment of a file wins (fastq.rs:502)
+        for (uint32_t j = 0; j < rd.n_umi; ++j) {
+            const uint32_t c = rd.fixed_layout ? pcl_static_coord(rd, p.static_start, p.umi_elem[j], L) : p.ucoord[j][i];
+            if (c != PCL_COORD_ABSENT) uc = c;
+        }
+        if (uc != PCL_COORD_ABSENT) {
+            acc[0] += uc & 0xFFFFu;
+            acc[1] += pcl_q30_range(row, uc >> 16, uc & 0xFFFFu);
+        }
+        if (fs & PCL_FSTATUS_TARGET) {
+            const uint32_t c = p.tcoord[i];
+            ++n_target;
+            acc[4] += c & 0xFFFFu;
+            acc[5] += pcl_q30_range(row, c >> 16, c & 0xFFFFu);
+        }
+    }
+    const uint32_t lane = threadIdx.x & 31u;
+#pragma unroll
+    for (int k = 0; k < 6; ++k)
+        for (int o = 16; o > 0; o >>= 1) acc[k] += __shfl_xor_sync(0xFFFFFFFFu, acc[k], o);
+    for (int o = 16; o > 0; o >>= 1) n_target += __shfl_xor_sync(0xFFFFFFFFu, n_target, o);
+    if (lane == 0) {
+        const int tcat = rd.is_reverse ? 3 : 2;           // read2 for neg-strand reads, read1 otherwise (fastq.rs:510-514)
+        if (acc[0]) atomicAdd(&p.cat[0 * 3 + 1], acc[0]);
+        if (acc[1]) atomicAdd(&p.cat[0 * 3 + 2], acc[1]);
+        if (acc[2]) atomicAdd(&p.cat[1 * 3 + 1], acc[2]);
+        if (acc[3]) atomicAdd(&p.cat[1 * 3 + 2], acc[3]);
+        if (n_target) atomicAdd(&p.cat[tcat * 3 + 0], n_target);
+        if (acc[4]) atomicAdd(&p.cat[tcat * 3 + 1], acc[4]);
+        if (acc[5]) atomicAdd(&p.cat[tcat * 3 + 2], acc[5]);
+    }
+}
+
 // counts in whitelist order for pcl_counts_fetch
 __global__ void k_gather_counts(const uint32_t *__restrict__ counts, const uint32_t *__restrict__ index_to_slot,
                                 unsigned long long *__restrict__ out, uint64_t n) {

@@ -93,7 +93,8 @@ struct pcl_ctx {
     int bc_region[PCL_MAX_READS][PCL_MAX_BC_PER_READ];
     Table tables[PCL_MAX_REGIONS];
     double *d_lut = nullptr;                  // [0..255] capped, [256..511] raw
-    unsigned long long *d_qc = nullptr;       // [PCL_MAX_READS] num_defect
+    unsigned long long *d_qc = nullptr;       // [PCL_MAX_READS] num_defect, then [12] QcFastq category counters
+    bool qc_enabled = false;
     uint64_t qc_reads[PCL_MAX_READS] = {0};
     std::vector<pcl_chunk *> chunks;
     // nccl
@@ -225,14 +226,14 @@ int pcl_ctx_create(pcl_ctx **out, int device) {
     if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", e);
     if ((e = cudaEventCreateWithFlags(&ctx->ev_reduced, cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", e);
     if ((e = cudaMalloc(&ctx->d_lut, 512 * sizeof(double))) != cudaSuccess) return bail("cudaMalloc", e);
-    if ((e = cudaMalloc(&ctx->d_qc, PCL_MAX_READS * sizeof(unsigned long long))) != cudaSuccess) return bail("cudaMalloc", e);
+    if ((e = cudaMalloc(&ctx->d_qc, (PCL_MAX_READS + 12) * sizeof(unsigned long long))) != cudaSuccess) return bail("cudaMalloc", e);
     double lut[512];
     for (int q = 0; q < 256; ++q) {
         lut[q] = error_probability(q < 66 ? q : 66);     // BC_MAX_QV cap (barcode.rs:18,320)
         lut[256 + q] = error_probability(q);
     }
     if ((e = cudaMemcpy(ctx->d_lut, lut, sizeof lut, cudaMemcpyHostToDevice)) != cudaSuccess) return bail("cudaMemcpy", e);
-    if ((e = cudaMemset(ctx->d_qc, 0, PCL_MAX_READS * sizeof(unsigned long long))) != cudaSuccess) return bail("cudaMemset", e);
+    if ((e = cudaMemset(ctx->d_qc, 0, (PCL_MAX_READS + 12) * sizeof(unsigned long long))) != cudaSuccess) return bail("cudaMemset", e);
     *out = ctx;
     return PCL_OK;
 }
@@ -305,13 +306,20 @@ int pcl_layout_set(pcl_ctx *ctx, const pcl_read_desc *reads, int n_reads) {
     for (int r = 0; r < n_reads; ++r) {
         DRead d;
         pcl_read_info info;
-        int rc = pcl_build_read(r, reads[r], &d, &info, ctx->bc_region[r], &ctx->err);
+        int rc = pcl_build_read(r, reads[r], &d, &info, ctx->bc_region[r], &ctx->err, ctx->qc_enabled);
         if (rc != PCL_OK) return rc;
         ctx->descs[r] = reads[r];
         ctx->dreads[r] = d;
         ctx->infos[r] = info;
     }
     ctx->n_reads = n_reads;
+    return PCL_OK;
+}
+
+int pcl_qc_enable(pcl_ctx *ctx, int on) {
+    if (!ctx) return PCL_ERR_ARG;
+    if (ctx->n_reads) return fail(ctx, PCL_ERR_ARG, "pcl_qc_enable must be called before pcl_layout_set");
+    ctx->qc_enabled = on != 0;
     return PCL_OK;
 }
 
@@ -398,10 +406,8 @@ int pcl_chunk_create(pcl_ctx *ctx, uint64_t capacity_records, pcl_chunk **out) {
         const DRead &d = ctx->dreads[r];
         const pcl_read_info &inf = ctx->infos[r];
         ReadBuf &b = c->rb[r];
-        if (d.needs_payload) {
-            A((void **)&b.seq, cap * d.stride);
-            A((void **)&b.qual, cap * d.stride);
-        }
+        if (d.needs_payload) A((void **)&b.seq, cap * d.stride);
+        if (d.needs_payload || d.qual_only) A((void **)&b.qual, cap * d.stride);
         A((void **)&b.len, cap * 2 + 16);
         A((void **)&b.fstatus, cap * 2 + 16);
         if (inf.has_target) A((void **)&b.tcoord, cap * 4);
@@ -463,6 +469,10 @@ int pcl_chunk_upload(pcl_chunk *c, int read_slot, const uint8_t *seq, const uint
         CU(ctx, cudaMemcpyAsync(b.seq, seq, c->n * d.stride, cudaMemcpyHostToDevice, c->stream));
         CU(ctx, cudaMemcpyAsync(b.qual, qual, c->n * d.stride, cudaMemcpyHostToDevice, c->stream));
     }
+    if (d.qual_only) {
+        if (!qual) return fail(ctx, PCL_ERR_ARG, "read %d needs its quality plane (FASTQ QC is enabled)", read_slot);
+        CU(ctx, cudaMemcpyAsync(b.qual, qual, c->n * d.stride, cudaMemcpyHostToDevice, c->stream));
+    }
     CU(ctx, cudaMemcpyAsync(b.len, len, c->n * 2, cudaMemcpyHostToDevice, c->stream));
     b.filled = true;
     return PCL_OK;
@@ -497,7 +507,7 @@ int pcl_counts_reset(pcl_ctx *ctx) {
         CU(ctx, cudaMemsetAsync(t.d_counts, 0, t.n_slots * sizeof(uint32_t), ctx->stream));
         CU(ctx, cudaMemsetAsync(t.d_scalars, 0, 2 * sizeof(unsigned long long), ctx->stream));
     }
-    CU(ctx, cudaMemsetAsync(ctx->d_qc, 0, PCL_MAX_READS * sizeof(unsigned long long), ctx->stream));
+    CU(ctx, cudaMemsetAsync(ctx->d_qc, 0, (PCL_MAX_READS + 12) * sizeof(unsigned long long), ctx->stream));
     CU(ctx, cudaEventRecord(ctx->ev_reduced, ctx->stream));
     for (pcl_chunk *c : ctx->chunks) CU(ctx, cudaStreamWaitEvent(c->stream, ctx->ev_reduced, 0));
     memset(ctx->qc_reads, 0, sizeof ctx->qc_reads);
@@ -683,6 +693,42 @@ int pcl_qc_fetch(pcl_ctx *ctx, uint64_t *per_read) {
     unsigned long long d[PCL_MAX_READS];
     CU(ctx, cudaMemcpy(d, ctx->d_qc, sizeof d, cudaMemcpyDeviceToHost));
     for (int r = 0; r < ctx->n_reads; ++r) { per_read[2 * r] = ctx->qc_reads[r]; per_read[2 * r + 1] = d[r]; }
+    return PCL_OK;
+}
+
+int pcl_qc_accumulate(pcl_ctx *ctx, pcl_chunk *c) {
+    if (int r = check_ready(ctx, c)) return r;
+    if (int r = bind(ctx)) return r;
+    if (c->n == 0) return PCL_OK;
+    for (int r = 0; r < ctx->n_reads; ++r) {
+        const pcl_read_info &inf = ctx->infos[r];
+        const DRead &d = ctx->dreads[r];
+        if (!inf.n_bc && !inf.n_umi && !inf.has_target) continue;
+        if (inf.has_target && !ctx->qc_enabled)
+            return fail(ctx, PCL_ERR_ARG, "read %d holds a target: call pcl_qc_enable before pcl_layout_set", r);
+        ReadBuf &b = c->rb[r];
+        QcParams p;
+        memset(&p, 0, sizeof p);
+        p.rd = d;
+        p.qual = b.qual; p.len = b.len; p.fstatus = b.fstatus; p.tcoord = b.tcoord; p.n = c->n;
+        for (int j = 0; j < inf.n_bc; ++j) { p.bcoord[j] = b.bcoord[j]; p.bc_elem[j] = inf.bc_elem[j]; }
+        for (int j = 0; j < inf.n_umi; ++j) { p.ucoord[j] = b.ucoord[j]; p.umi_elem[j] = inf.umi_elem[j]; }
+        memcpy(p.static_start, inf.static_start, sizeof p.static_start);
+        p.cat = ctx->d_qc + PCL_MAX_READS;
+        prof_begin(ctx, c->stream, PCL_K_QC);
+        k_qc<<<grid_for(ctx, c->n, 8), PCL_BLOCK, 0, c->stream>>>(p);
+        prof_end(ctx, c->stream);
+        CU(ctx, cudaGetLastError());
+    }
+    return PCL_OK;
+}
+
+int pcl_qc_fetch_categories(pcl_ctx *ctx, uint64_t *cat12) {
+    if (!ctx || !cat12) return PCL_ERR_ARG;
+    if (int r = pcl_sync(ctx)) return r;
+    unsigned long long d[12];
+    CU(ctx, cudaMemcpy(d, ctx->d_qc + PCL_MAX_READS, sizeof d, cudaMemcpyDeviceToHost));
+    for (int k = 0; k < 12; ++k) cat12[k] = d[k];
     return PCL_OK;
 }
 

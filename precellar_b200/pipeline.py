@@ -59,11 +59,15 @@ class Chunk:
         length = np.ascontiguousarray(batch.length, dtype=np.uint16)
         assert len(length) == self.n, "all read files of a chunk must hold the same number of records"
         sp = qp = None
-        if self.pipe.infos[read_slot].needs_payload:
+        info = self.pipe.infos[read_slot]
+        if info.needs_payload:
             assert batch.seq is not None and batch.qual is not None
             assert batch.seq.dtype == np.uint8 and batch.seq.shape == (self.n, stride) and batch.seq.flags.c_contiguous
+            sp = batch.seq.ctypes.data
+        if info.needs_payload or info.qual_only:
+            assert batch.qual is not None, "this read needs its quality plane"
             assert batch.qual.dtype == np.uint8 and batch.qual.shape == (self.n, stride) and batch.qual.flags.c_contiguous
-            sp, qp = batch.seq.ctypes.data, batch.qual.ctypes.data
+            qp = batch.qual.ctypes.data
         self._keep.append((batch, length))
         check(self.pipe.ctx, lib().pcl_chunk_upload(self.h, read_slot, sp, qp, length.ctypes.data))
 
@@ -115,7 +119,7 @@ class BarcodePipeline:
     """One GPU's instance of the hot path for one (assay, modality)."""
 
     def __init__(self, layout: CompiledLayout, device: int = 0, nranks: int = 1, rank: int = 0,
-                 nccl_uid: Optional[bytes] = None):
+                 nccl_uid: Optional[bytes] = None, qc: bool = False):
         L = lib()
         ctx = C.c_void_p()
         rc = L.pcl_ctx_create(C.byref(ctx), int(device))
@@ -124,6 +128,9 @@ class BarcodePipeline:
         self.ctx = ctx
         self.layout = layout
         self.device = device
+        self.qc_enabled = bool(qc)
+        if qc:                                          # QcFastq needs the quality plane of insert reads too
+            check(ctx, L.pcl_qc_enable(ctx, 1))
         self._descs = layout.descs()
         check(ctx, L.pcl_layout_set(ctx, self._descs, len(layout.reads)))
         self.infos: List[_ffi.ReadInfo] = []
@@ -216,8 +223,30 @@ class BarcodePipeline:
         return cnt[:n], mm.value, tot.value
 
     def qc(self) -> np.ndarray:
+        """[n_reads, 2]: num_reads, num_defect per read file (QcFastq, precellar/src/qc.rs:23-24)."""
         out = np.zeros((len(self.layout.reads), 2), np.uint64)
         check(self.ctx, lib().pcl_qc_fetch(self.ctx, out.ctypes.data))
+        return out
+
+    def qc_accumulate(self, chunk: Chunk) -> None:
+        """QcFastq::update over a counted chunk (bases / Q30 bases per category)."""
+        check(self.ctx, lib().pcl_qc_accumulate(self.ctx, chunk.h))
+
+    def qc_categories(self) -> np.ndarray:
+        """[4, 3]: rows umi, barcode, read1, read2; columns num_reads, num_total_bases, num_q30_bases."""
+        out = np.zeros((4, 3), np.uint64)
+        check(self.ctx, lib().pcl_qc_fetch_categories(self.ctx, out.ctypes.data))
+        return out
+
+    def qc_json(self) -> dict:
+        """QcFastq::to_json (precellar/src/qc.rs:91-121)."""
+        per, cat = self.qc(), self.qc_categories()
+        out = {}
+        defect = {p.read_id: float(per[r, 1]) / float(per[r, 0]) for r, p in enumerate(self.layout.reads) if per[r, 1] > 0}
+        if defect:
+            out["frac_reads_with_misformed_structure"] = defect
+        names = ("umi", "barcode", "read1", "read2")
+        out["frac_q30_bases"] = {names[k]: float(cat[k, 2]) / float(cat[k, 1]) for k in range(4) if cat[k, 1] > 0}
         return out
 
     # -- instrumentation -----------------------------------------------------------------------------

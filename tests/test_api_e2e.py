@@ -1,0 +1,174 @@
+"""GPU tier, end to end through the public API: seqspec YAML + FASTQ files on disk -> FastqProcessor /
+make_fastq, against the oracle fed with the same records."""
+import gzip
+import os
+
+import numpy as np
+import pytest
+import yaml
+
+from oracle import pyoracle as O
+from tests import util as U
+
+pytestmark = pytest.mark.gpu
+
+
+def region(rid, rtype, stype, seq, lo, hi, onlist=None):
+    d = dict(region_id=rid, region_type=rtype, name=rid, sequence_type=stype, sequence=seq, min_len=lo, max_len=hi,
+             onlist=None, regions=None)
+    if onlist:
+        d["onlist"] = dict(file_id=os.path.basename(onlist), filename=os.path.basename(onlist), filetype="txt",
+                           filesize=0, url=onlist, urltype="local", md5=0, location="local")
+    return d
+
+
+def write_spec(td, hp, rt):
+    open(os.path.join(td, "hp.txt"), "wb").write(b"\n".join(hp))                 # no trailing newline, like the fixtures
+    with gzip.open(os.path.join(td, "rt.txt.gz"), "wb") as fh:
+        fh.write(b"\r\n".join(rt) + b"\r\n")
+    regions = [
+        region("p5", "illumina_p5", "fixed", "AATGATACGGCGACCACCGAGATCTACAC", 29, 29),
+        region("i5_primer", "truseq_read1", "fixed", "ACACTCTTTCCCTACACGACGCTCTTCCGATCT", 33, 33),
+        region("hairpin_barcode", "barcode", "onlist", "N" * 10, 9, 10, "hp.txt"),
+        region("linker", "linker", "fixed", "CAGAGC", 6, 6),
+        region("umi", "umi", "random", "N" * 8, 8, 8),
+        region("rt_barcode", "barcode", "onlist", "N" * 10, 10, 10, "rt.txt.gz"),
+        region("poly_t", "poly_t", "random", "T" * 30, 30, 32),
+        region("cdna", "cdna", "random", "X", 1, 1000),
+        region("me", "nextera_read2", "fixed", "CTGTCTCTTATACACATCTCCGAGCCCACGAGAC", 34, 34),
+        region("p7", "illumina_p7", "fixed", "ATCTCGTATGCCGTCTTCTGCTTG", 24, 24),
+    ]
+    spec = dict(seqspec_version="0.3.0", assay_id="sci3-test", name="sci3-test", doi="", date="", description="",
+                modalities=["rna"], lib_struct="", library_protocol="x", library_kit="x", sequence_protocol="x",
+                sequence_kit="x",
+                sequence_spec=[
+                    dict(read_id="R1", name="R1", modality="rna", primer_id="i5_primer", min_len=34, max_len=34, strand="pos"),
+                    dict(read_id="R2", name="R2", modality="rna", primer_id="me", min_len=40, max_len=60, strand="neg")],
+                library_spec=[dict(region_id="rna", region_type="rna", name="rna", sequence_type="joined", sequence="",
+                                   min_len=0, max_len=0, onlist=None, regions=regions)])
+    path = os.path.join(td, "spec.yaml")
+    yaml.safe_dump(spec, open(path, "w"), sort_keys=False)
+    return path
+
+
+def write_fastq(path, names, batch, gz):
+    op = gzip.open if gz else open
+    with op(path, "wb") as fh:
+        for i, nm in enumerate(names):
+            L = int(batch.length[i])
+            fh.write(b"@" + nm + b"\n" + batch.seq[i, :L].tobytes() + b"\n+\n" + batch.qual[i, :L].tobytes() + b"\n")
+
+
+@pytest.fixture(scope="module")
+def dataset(tmp_path_factory):
+    td = str(tmp_path_factory.mktemp("e2e"))
+    rng = np.random.default_rng(11)
+    hp = U.gen_whitelist(rng, 96, [9, 10])
+    rt = U.gen_whitelist(rng, 96, 10)
+    spec = write_spec(td, hp, rt)
+    from precellar_b200 import Assay, compile_layout
+    assay = Assay(spec)
+    layout0 = compile_layout(assay, "rna")
+    n = 5000
+    full = U.gen_reads(rng, layout0, n, [64, 64], p_short=0.0, p_tiny=0.02, read_len=[34, 60])
+    # the insert read of the synthetic generator is 1..60 long; make every sequence non-empty for a valid FASTQ
+    for b in full:
+        b.length[:] = np.maximum(b.length, 1)
+    names1 = [f"read{i}/1 x:{i}".encode() for i in range(n)]
+    names2 = [f"read{i}/2".encode() for i in range(n)]
+    h = n // 2
+    from precellar_b200.pipeline import HostBatch
+    sl = lambda b, lo, hi: HostBatch(b.seq[lo:hi], b.qual[lo:hi], b.length[lo:hi])
+    write_fastq(os.path.join(td, "R1_a.fq.gz"), names1[:h], sl(full[0], 0, h), True)      # two files per read: concatenated
+    write_fastq(os.path.join(td, "R1_b.fq"), names1[h:], sl(full[0], h, n), False)
+    write_fastq(os.path.join(td, "R2.fq.gz"), names2, full[1], True)
+    assay.update_read("R1", fastq=[os.path.join(td, "R1_a.fq.gz"), os.path.join(td, "R1_b.fq")])
+    assay.update_read("R2", fastq=os.path.join(td, "R2.fq.gz"))
+    return dict(td=td, assay=assay, full=full, names1=names1, names2=names2, n=n)
+
+
+def oracle_lines(assay, full, correct, threshold=0.975):
+    from precellar_b200 import compile_layout
+    layout = compile_layout(assay, "rna", require_files=True)
+    ores, _ = U.run_oracle(layout, full, correct=correct, threshold=threshold)
+    return layout, ores
+
+
+def test_update_read_inferred_lengths(dataset):
+    a = dataset["assay"]
+    r1, r2 = a.sequence_spec["R1"], a.sequence_spec["R2"]
+    L1, L2 = dataset["full"][0].length, dataset["full"][1].length
+    assert (r1.min_len, r1.max_len) == (int(L1.min()), int(L1.max()))
+    assert (r2.min_len, r2.max_len) == (int(L2.min()), int(L2.max()))
+
+
+@pytest.mark.parametrize("correct", [False, True])
+def test_gen_barcoded_fastq_matches_oracle(dataset, correct):
+    from precellar_b200.api import FastqProcessor
+    proc = FastqProcessor(dataset["assay"]).with_modality("rna").with_barcode_correct_prob(0.9)
+    got = []
+    for batch in proc.gen_barcoded_fastq(correct, chunk_size=100_000):      # several chunks
+        got.extend(batch)
+    layout, ores = oracle_lines(dataset["assay"], dataset["full"], correct, 0.9)
+    want = [ln for ln in ores.lines if ln]
+    assert len(got) == len(want) > 3000
+    for rec, line in zip(got, want):
+        f = line.split("\t")
+        mine = [rec.barcode.raw.sequence, rec.barcode.raw.quality, rec.barcode.corrected if rec.barcode.corrected is not None else b"*",
+                rec.umi.sequence if rec.umi else b"", rec.umi.quality if rec.umi else b"",
+                rec.read1.sequence if rec.read1 else b"", rec.read1.quality if rec.read1 else b"",
+                rec.read2.sequence if rec.read2 else b"", rec.read2.quality if rec.read2 else b""]
+        assert [m.decode("latin-1") for m in mine] == f
+    # definitions: barcode/umi carry R1's definition line, read2 its own
+    k = next(i for i, ln in enumerate(ores.lines) if ln)
+    assert got[0].barcode.raw.definition == dataset["names1"][k] and got[0].read2.definition == dataset["names2"][k]
+    # QcFastq
+    qc = proc.get_fastq_qc()
+    cat = ores.qc_cat.astype(float)
+    for j, nm in enumerate(("umi", "barcode", "read1", "read2")):
+        if cat[j, 1] > 0:
+            assert qc["frac_q30_bases"][nm] == cat[j, 2] / cat[j, 1]
+        else:
+            assert nm not in qc["frac_q30_bases"]
+    per = ores.qc_per_file
+    want_defect = {rid: per[r, 1] / per[r, 0] for r, rid in enumerate(("R1", "R2")) if per[r, 1] > 0}
+    assert qc.get("frac_reads_with_misformed_structure", {}) == want_defect and want_defect
+
+
+def test_make_fastq(dataset, tmp_path):
+    from precellar_b200 import _zstd
+    from precellar_b200.api import make_fastq
+    out = str(tmp_path / "out")
+    make_fastq(dataset["assay"], modality="rna", out_dir=out, correct_barcode=True)
+    layout, ores = oracle_lines(dataset["assay"], dataset["full"], True, 0.975)
+    assert not os.path.exists(os.path.join(out, "R2.fq.zst"))      # is_paired_end quirk: no pos-strand target here
+    r1 = _zstd.decompress_file(os.path.join(out, "R1.fq.zst")).split(b"\n")
+    recs = [r1[i:i + 4] for i in range(0, len(r1) - 1, 4)]
+    want = []
+    for i, ln in enumerate(ores.lines):
+        if not ln:
+            continue
+        f = ln.split("\t")
+        if f[2] == "*":
+            continue                                                # dropped: barcode not corrected
+        want.append((dataset["names1"][i], (f[2] + f[3] + f[5]).encode("latin-1"), (f[1] + f[4] + f[6]).encode("latin-1")))
+    assert len(recs) == len(want) > 1000
+    for r, (nm, s, q) in zip(recs, want):
+        assert r[0] == b"@" + nm and r[1] == s and r[2] == b"+" and r[3] == q
+
+
+def test_mismatched_names_are_rejected(dataset, tmp_path):
+    import copy
+    from precellar_b200 import _ffi
+    from precellar_b200.api import FastqProcessor
+    from precellar_b200.pipeline import HostBatch
+    bad = os.path.join(str(tmp_path), "R2_bad.fq")
+    full, n = dataset["full"], 50
+    names = [f"other{i}/2".encode() for i in range(n)]
+    write_fastq(bad, names, HostBatch(full[1].seq[:n], full[1].qual[:n], full[1].length[:n]), False)
+    a = copy.deepcopy(dataset["assay"])
+    a.update_read("R2", fastq=bad, min_len=1, max_len=60)
+    with pytest.raises(_ffi.PclError) as ei:
+        for _ in FastqProcessor(a).with_modality("rna").gen_barcoded_fastq(True):
+            pass
+    assert ei.value.code == _ffi.PCL_ERR_INPUT

@@ -162,3 +162,36 @@ def test_v3_full_size_2p5M_pairs_6p8M_whitelist():
     assert np.array_equal(g1.umi_key[0], np.where(valid, k, 0).astype(np.uint32))
     code_bc = (g1.fstatus.astype(np.uint32) >> 4) & 7
     assert (code_bc == _ffi.BC_CORRECTED).sum() > 100_000 and (code_bc == _ffi.BC_EXACT).sum() > 1_500_000
+
+
+@pytest.mark.parametrize("name", ["v3", "v2", "atac", "multiome_atac", "sci3", "share", "dsc", "k64_rev", "multi_umi"])
+def test_qc_fastq_counters(layouts, name):
+    """QcFastq (precellar/src/qc.rs:30-69): bases / Q30 bases / reads per category and per-file defects."""
+    from precellar_b200.pipeline import BarcodePipeline, HostBatch
+    layout = layouts[name]
+    rng = np.random.default_rng(abs(hash((name, "qc"))) % (2 ** 31))
+    multi = len(layout.region_ids) > 1
+    pipe = BarcodePipeline(layout, qc=True)
+    try:
+        strides = [pipe.stride(r) for r in range(len(layout.reads))]
+        n = 2500
+        full = U.gen_reads(rng, layout, n, strides, p_short=0.0 if multi else 0.03, p_tiny=0.03 if multi else 0.0,
+                           read_len=[p.max_len for p in layout.reads])
+        dev = U.narrow(full, strides)
+        ch = pipe.new_chunk(n)
+        ch.reset(n)
+        for r, b in enumerate(dev):
+            if pipe.infos[r].qual_only:
+                b = HostBatch(None, np.ascontiguousarray(full[r].qual[:, :strides[r]]) if full[r].qual.shape[1] >= strides[r]
+                              else np.pad(full[r].qual, ((0, 0), (0, strides[r] - full[r].qual.shape[1])), constant_values=33), b.length)
+            ch.upload(r, b)
+        pipe.count(ch)
+        pipe.qc_accumulate(ch)
+        cat = pipe.qc_categories()
+        per = pipe.qc()
+    finally:
+        pipe.close()
+    ores, _ = U.run_oracle(layout, full, correct=False, render_lines=False)
+    np.testing.assert_array_equal(cat, ores.qc_cat)
+    np.testing.assert_array_equal(per, ores.qc_per_file)
+    assert cat[1, 1] > 0 and cat[1, 2] > 0
