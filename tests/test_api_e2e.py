@@ -22,7 +22,7 @@ def region(rid, rtype, stype, seq, lo, hi, onlist=None):
     return d
 
 
-def write_spec(td, hp, rt):
+def write_spec(td, hp, rt, forward_insert=False):
     open(os.path.join(td, "hp.txt"), "wb").write(b"\n".join(hp))                 # no trailing newline, like the fixtures
     with gzip.open(os.path.join(td, "rt.txt.gz"), "wb") as fh:
         fh.write(b"\r\n".join(rt) + b"\r\n")
@@ -34,6 +34,7 @@ def write_spec(td, hp, rt):
         region("umi", "umi", "random", "N" * 8, 8, 8),
         region("rt_barcode", "barcode", "onlist", "N" * 10, 10, 10, "rt.txt.gz"),
         region("poly_t", "poly_t", "random", "T" * 30, 30, 32),
+        region("r2p", "custom_primer", "fixed", "GTCTCGTGGGCTCGGAGATG", 20, 20),
         region("cdna", "cdna", "random", "X", 1, 1000),
         region("me", "nextera_read2", "fixed", "CTGTCTCTTATACACATCTCCGAGCCCACGAGAC", 34, 34),
         region("p7", "illumina_p7", "fixed", "ATCTCGTATGCCGTCTTCTGCTTG", 24, 24),
@@ -43,10 +44,11 @@ def write_spec(td, hp, rt):
                 sequence_kit="x",
                 sequence_spec=[
                     dict(read_id="R1", name="R1", modality="rna", primer_id="i5_primer", min_len=34, max_len=34, strand="pos"),
-                    dict(read_id="R2", name="R2", modality="rna", primer_id="me", min_len=40, max_len=60, strand="neg")],
+                    dict(read_id="R2", name="R2", modality="rna", primer_id="r2p" if forward_insert else "me", min_len=40,
+                         max_len=60, strand="pos" if forward_insert else "neg")],
                 library_spec=[dict(region_id="rna", region_type="rna", name="rna", sequence_type="joined", sequence="",
                                    min_len=0, max_len=0, onlist=None, regions=regions)])
-    path = os.path.join(td, "spec.yaml")
+    path = os.path.join(td, "spec_fwd.yaml" if forward_insert else "spec.yaml")
     yaml.safe_dump(spec, open(path, "w"), sort_keys=False)
     return path
 
@@ -136,12 +138,23 @@ def test_gen_barcoded_fastq_matches_oracle(dataset, correct):
 
 
 def test_make_fastq(dataset, tmp_path):
-    from precellar_b200 import _zstd
+    """R1.fq.zst = corrected barcode + UMI + read1 (python/src/lib.rs:153-163); the insert is read on the pos strand."""
+    import copy
+    from precellar_b200 import Assay, _zstd, compile_layout
     from precellar_b200.api import make_fastq
+    td = dataset["td"]
+    spec = write_spec(td, [b"A"], [b"A"], forward_insert=True)       # whitelists are already on disk; only the YAML differs
+    a = Assay(spec)
+    for rid in ("hairpin_barcode", "rt_barcode"):
+        a._region_map[rid].onlist = copy.deepcopy(dataset["assay"]._region_map[rid].onlist)
+    a.update_read("R1", fastq=[os.path.join(td, "R1_a.fq.gz"), os.path.join(td, "R1_b.fq")])
+    a.update_read("R2", fastq=os.path.join(td, "R2.fq.gz"))
     out = str(tmp_path / "out")
-    make_fastq(dataset["assay"], modality="rna", out_dir=out, correct_barcode=True)
-    layout, ores = oracle_lines(dataset["assay"], dataset["full"], True, 0.975)
-    assert not os.path.exists(os.path.join(out, "R2.fq.zst"))      # is_paired_end quirk: no pos-strand target here
+    make_fastq(a, modality="rna", out_dir=out, correct_barcode=True)
+    layout = compile_layout(a, "rna", require_files=True)
+    assert [p.is_reverse for p in layout.reads] == [False, False]
+    ores, _ = U.run_oracle(layout, dataset["full"], correct=True, threshold=0.975)
+    assert not os.path.exists(os.path.join(out, "R2.fq.zst"))      # is_paired_end needs targets on both strands (fastq.rs:314-329)
     r1 = _zstd.decompress_file(os.path.join(out, "R1.fq.zst")).split(b"\n")
     recs = [r1[i:i + 4] for i in range(0, len(r1) - 1, 4)]
     want = []
@@ -155,6 +168,13 @@ def test_make_fastq(dataset, tmp_path):
     assert len(recs) == len(want) > 1000
     for r, (nm, s, q) in zip(recs, want):
         assert r[0] == b"@" + nm and r[1] == s and r[2] == b"+" and r[3] == q
+
+
+def test_make_fastq_without_read1_fails_like_the_reference(dataset, tmp_path):
+    """sci-RNA-seq3 has no pos-strand insert: `record.read1.unwrap()` panics in the reference (python/src/lib.rs:160)."""
+    from precellar_b200.api import make_fastq
+    with pytest.raises(RuntimeError):
+        make_fastq(dataset["assay"], modality="rna", out_dir=str(tmp_path / "o2"), correct_barcode=False)
 
 
 def test_mismatched_names_are_rejected(dataset, tmp_path):
