@@ -75,6 +75,10 @@ struct DTable {
     uint64_t empty;                     // key value marking an empty slot (never a whitelist key)
     uint32_t n_buckets;
     uint32_t mode;                      // PCL_TAB_*
+    // 32-bit tables only: the same keys in four more tables, table q bucketed by hash(key & ~(0xFF << 8q)).
+    // All keys that differ from a query only inside byte q of the packed key (4 bases) share the query's
+    // bucket there, so the 1-Hamming neighbourhood of a barcode is found with 4 bucket reads instead of 3*L.
+    const uint32_t *nkeys[4];
 };
 
 // ------------------------------------------------------------------------------------------
@@ -468,6 +472,14 @@ PCL_HD bool pcl_bucket32_any(const uint32_t *keys, uint32_t b, uint32_t k, uint3
     return (v0.x == k) | (v0.y == k) | (v0.z == k) | (v0.w == k) | (v1.x == k) | (v1.y == k) | (v1.z == k) | (v1.w == k);
 }
 
+PCL_HD uint32_t pcl_clz32(uint32_t x) {
+#ifdef __CUDA_ARCH__
+    return (uint32_t)__clz((int)x);
+#else
+    return (uint32_t)__builtin_clz(x);
+#endif
+}
+
 PCL_HD uint32_t pcl_ctz64(uint64_t x) {
 #ifdef __CUDA_ARCH__
     return (uint32_t)(__ffsll((long long)x) - 1);
@@ -494,6 +506,42 @@ PCL_HD uint32_t pcl_correct_one32(const DTable &t, uint32_t key32, uint32_t len,
     const uint32_t empty = (uint32_t)t.empty, nb = t.n_buckets;
     const uint32_t p0 = n_invalid == 1u ? inv_pos : 0u, p1 = n_invalid == 1u ? inv_pos + 1u : len;
     uint64_t pend = 0;
+    if (t.nkeys[0]) {
+        // neighbourhood tables: one bucket chain per byte of the key
+        const uint32_t inv_sh = 2u * (len - 1u - (n_invalid == 1u ? inv_pos : 0u));
+        const uint32_t q0 = n_invalid == 1u ? inv_sh >> 3 : 0u, q1 = n_invalid == 1u ? q0 + 1u : 4u;
+        for (uint32_t q = q0; q < q1; ++q) {
+            const uint32_t bm = 0xFFu << (8u * q);
+            if (len < 16u && (bm & ((1u << (2u * len)) - 1u)) == 0u) continue;        // byte q holds no base of this key
+            const uint32_t part = key32 & ~bm;
+            const uint32_t *nk = t.nkeys[q];
+            uint32_t b = pcl_hash32_bucket(part, nb);
+            for (;;) {
+                auto v0 = PCL_LDG128(nk + (uint64_t)b * 8);
+                auto v1 = PCL_LDG128(nk + (uint64_t)b * 8 + 4);
+                const uint32_t e[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+#ifdef __CUDA_ARCH__
+#pragma unroll
+#endif
+                for (int k = 0; k < 8; ++k) {
+                    const uint32_t x = e[k] ^ key32;
+                    if ((x & ~bm) != 0u || e[k] == empty) continue;                    // another neighbourhood / free slot
+                    const uint32_t d = (x | (x >> 1)) & 0x55555555u;                   // one bit per differing base
+                    if (n_invalid == 1u) {
+                        if (d & ~(1u << inv_sh)) continue;                             // may differ at the N position only
+                        pend |= 1ull << (4u * inv_pos + ((e[k] >> inv_sh) & 3u));
+                    } else {
+                        if (d == 0u || (d & (d - 1u)) != 0u) continue;                 // exactly one substitution
+                        const uint32_t sh = 31u - pcl_clz32(d);                        // even bit index of that base
+                        if (sh >= 2u * len) continue;                                  // the difference touches the length marker
+                        pend |= 1ull << (4u * (len - 1u - (sh >> 1)) + ((e[k] >> sh) & 3u));
+                    }
+                }
+                if (v1.w == empty) break;                                              // the chain ends at a bucket with a free slot
+                b = (b + 1u == nb) ? 0u : b + 1u;
+            }
+        }
+    } else
     for (uint32_t pos = p0; pos < p1; ++pos) {
         const uint32_t sh = 2u * (len - 1u - pos);
         const uint32_t existing = n_invalid == 1u ? 4u : ((key32 >> sh) & 3u);

@@ -166,6 +166,7 @@ struct HostTable {
     uint64_t n_buckets = 0, n_slots = 0, n_entries = 0, empty = 0;
     std::vector<uint32_t> tab32;
     std::vector<uint64_t> tab64;
+    std::vector<uint32_t> ntab32[4];         // neighbourhood tables (32-bit modes): bucketed by hash(key & ~(0xFF << 8q))
     std::vector<uint32_t> index_to_slot;     // whitelist index (dedup file order) -> slot
     const void *data() const { return mode == PCL_TAB_K64 ? (const void *)tab64.data() : (const void *)tab32.data(); }
     size_t key_bytes() const { return mode == PCL_TAB_K64 ? 8 : 4; }
@@ -231,6 +232,26 @@ inline int pcl_build_table(const uint8_t *bytes, const uint64_t *offsets, uint64
             }
             if (placed) break;
             b = (b + 1 == t.n_buckets) ? 0 : b + 1;
+        }
+    }
+    if (t.mode != PCL_TAB_K64) {
+        for (int q = 0; q < 4; ++q) {
+            const uint32_t bm = 0xFFu << (8 * q);
+            std::vector<uint32_t> &nt = t.ntab32[q];
+            nt.assign(t.n_slots, (uint32_t)t.empty);
+            for (uint64_t i = 0; i < m; ++i) {
+                const uint32_t k = (uint32_t)keys[i];
+                uint32_t b = pcl_hash32_bucket(k & ~bm, (uint32_t)t.n_buckets);
+                for (;;) {
+                    bool placed = false;
+                    for (uint32_t s = 0; s < spb && !placed; ++s) {
+                        const uint64_t idx = (uint64_t)b * spb + s;
+                        if (nt[idx] == (uint32_t)t.empty) { nt[idx] = k; placed = true; }
+                    }
+                    if (placed) break;
+                    b = (b + 1 == t.n_buckets) ? 0 : b + 1;
+                }
+            }
         }
     }
     *out = std::move(t);

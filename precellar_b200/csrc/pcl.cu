@@ -72,6 +72,7 @@ struct Table {
     void *d_keys = nullptr;
     uint32_t *d_counts = nullptr;
     uint32_t *d_index_to_slot = nullptr;
+    uint32_t *d_nkeys[4] = {nullptr, nullptr, nullptr, nullptr};
     unsigned long long *d_scalars = nullptr;   // [0] total, [1] mismatch
 };
 
@@ -108,6 +109,7 @@ struct pcl_ctx {
     uint64_t launches = 0;
     int sm_count = 148;
     bool force_generic = false;   // PCL_FORCE_GENERIC=1: only the generic kernels (tests compare both paths)
+    bool no_neighbour_tables = false;   // PCL_NO_NEIGHBOUR_TABLES=1: 3*L direct probes instead of the 4 neighbourhood tables
 };
 
 struct ReadBuf {
@@ -214,6 +216,7 @@ int pcl_ctx_create(pcl_ctx **out, int device) {
     ctx->device = device;
     ctx->sm_count = prop.multiProcessorCount;
     { const char *g = getenv("PCL_FORCE_GENERIC"); ctx->force_generic = g && g[0] == '1'; }
+    { const char *g = getenv("PCL_NO_NEIGHBOUR_TABLES"); ctx->no_neighbour_tables = g && g[0] == '1'; }
     memset(ctx->descs, 0, sizeof ctx->descs);
     memset(ctx->dreads, 0, sizeof ctx->dreads);
     memset(ctx->infos, 0, sizeof ctx->infos);
@@ -242,6 +245,7 @@ static void table_free(Table &t) {
     if (t.d_keys) cudaFree(t.d_keys);
     if (t.d_counts) cudaFree(t.d_counts);
     if (t.d_index_to_slot) cudaFree(t.d_index_to_slot);
+    for (int q = 0; q < 4; ++q) if (t.d_nkeys[q]) cudaFree(t.d_nkeys[q]);
     if (t.d_scalars) cudaFree(t.d_scalars);
     t = Table();
 }
@@ -357,6 +361,14 @@ int pcl_whitelist_load(pcl_ctx *ctx, int region_slot, const uint8_t *bytes, cons
     CU(ctx, cudaMemcpy(t.d_index_to_slot, ht.index_to_slot.data(), m * sizeof(uint32_t), cudaMemcpyHostToDevice));
     CU(ctx, cudaMemset(t.d_counts, 0, n_slots * sizeof(uint32_t)));
     CU(ctx, cudaMemset(t.d_scalars, 0, 2 * sizeof(unsigned long long)));
+    for (int q = 0; q < 4; ++q) {
+        t.d.nkeys[q] = nullptr;
+        if (ht.mode != PCL_TAB_K64 && !ctx->no_neighbour_tables) {
+            CU(ctx, cudaMalloc(&t.d_nkeys[q], n_slots * sizeof(uint32_t)));
+            CU(ctx, cudaMemcpy(t.d_nkeys[q], ht.ntab32[q].data(), n_slots * sizeof(uint32_t), cudaMemcpyHostToDevice));
+            t.d.nkeys[q] = t.d_nkeys[q];
+        }
+    }
     t.d.keys = t.d_keys;
     t.d.counts = t.d_counts;
     t.d.total = t.d_scalars;

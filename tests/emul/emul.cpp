@@ -66,6 +66,7 @@ int emu_run(const pcl_read_desc *reads, int n_reads, int n_regions, const uint8_
         dt[g].empty = ht[g].empty;
         dt[g].n_buckets = (uint32_t)ht[g].n_buckets;
         dt[g].mode = ht[g].mode;
+        for (int q = 0; q < 4; ++q) dt[g].nkeys[q] = (use_fast == 2 || ht[g].mode == PCL_TAB_K64) ? nullptr : ht[g].ntab32[q].data();
     }
     double lut[512];
     for (int q = 0; q < 256; ++q) {

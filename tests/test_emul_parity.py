@@ -86,9 +86,11 @@ NAMES = ["v3", "fast12_tail", "v2", "atac", "multiome_atac", "sci3", "share", "d
 
 
 @pytest.mark.parametrize("name", NAMES)
-@pytest.mark.parametrize("mode", ["correct", "nocorrect", "ee", "lower", "correct-generic"])
+@pytest.mark.parametrize("mode", ["correct", "nocorrect", "ee", "lower", "correct-generic", "correct-direct", "lower-direct"])
 def test_emul_matches_oracle(layouts, name, mode):
-    use_fast = mode != "correct-generic"          # the specialised paths are on by default
+    # default: specialised kernels + neighbourhood tables; "-generic": interpreter kernels only;
+    # "-direct": specialised kernels with the 3*L direct probes instead of the neighbourhood tables
+    use_fast = {"generic": 0, "direct": 2}.get(mode.split("-")[-1], 1)
     mode = mode.split("-")[0]
     layout = layouts[name]
     rng = np.random.default_rng(abs(hash((name, mode))) % (2 ** 31))

@@ -56,10 +56,12 @@ def run_gpu(layout, dev_batches, correct=True, threshold=0.975, max_expected_err
 
 
 @pytest.mark.parametrize("name", NAMES)
-@pytest.mark.parametrize("mode", ["correct", "nocorrect", "ee", "lower", "correct-generic"])
+@pytest.mark.parametrize("mode", ["correct", "nocorrect", "ee", "lower", "correct-generic", "correct-direct", "lower-direct"])
 def test_gpu_matches_oracle(layouts, name, mode, monkeypatch):
-    # the specialised kernels are the default; "-generic" forces the interpreter kernels on the same data
+    # the specialised kernels + neighbourhood tables are the default; "-generic" forces the interpreter kernels,
+    # "-direct" the 3*L direct probes, on the same data
     monkeypatch.setenv("PCL_FORCE_GENERIC", "1" if mode.endswith("-generic") else "0")
+    monkeypatch.setenv("PCL_NO_NEIGHBOUR_TABLES", "1" if mode.endswith("-direct") else "0")
     mode = mode.split("-")[0]
     layout = layouts[name]
     rng = np.random.default_rng(abs(hash((name, mode, "gpu"))) % (2 ** 31))
