@@ -241,6 +241,9 @@ __device__ __forceinline__ uint4 pcl_ld_stream(const uint4 *p) {
     return r;
 }
 
+__device__ __forceinline__ void pcl_st_stream(uint32_t *p, uint32_t v) { __stcs(p, v); }
+__device__ __forceinline__ void pcl_st_stream(uint16_t *p, uint16_t v) { __stcs(p, v); }
+
 __global__ void __launch_bounds__(PCL_BLOCK) k_count_fast(const __grid_constant__ CountParams p) {
     __shared__ uint32_t ck[PCL_HCACHE];
     __shared__ uint32_t cc[PCL_HCACHE];
@@ -256,23 +259,38 @@ __global__ void __launch_bounds__(PCL_BLOCK) k_count_fast(const __grid_constant_
     const uint32_t bc_end = (uint32_t)f.bc_start + f.bc_len, umi_end = (uint32_t)f.umi_start + f.umi_len;
     const bool len_ok = tab.mode == PCL_TAB_K32_L16 ? f.bc_len == 16 : (tab.mode == PCL_TAB_K32_MARKER && f.bc_len <= 15);
     const uint32_t absent_rest = (PCL_BC_ABSENT << 7) | (PCL_BC_ABSENT << 10) | (PCL_BC_ABSENT << 13);
+    const bool wide = rd.stride == 32u;
     uint32_t *bc_out = reinterpret_cast<uint32_t *>(p.bc_key[0]);
     uint32_t *umi_out = reinterpret_cast<uint32_t *>(p.umi_key[0]);
     unsigned long long n_total = 0, n_mis = 0;
     WlCursor wl = {0, 0};
 
-    for (uint64_t base = (uint64_t)blockIdx.x * blockDim.x + (threadIdx.x & ~31u); base < p.n; base += step) {
+    // software pipeline: the record of the NEXT iteration is in flight while the current one is processed
+    uint64_t base = (uint64_t)blockIdx.x * blockDim.x + (threadIdx.x & ~31u);
+    uint4 a = make_uint4(0u, 0u, 0u, 0u), b = make_uint4(0u, 0u, 0u, 0u);
+    uint32_t Lraw = 0;
+    if (base + lane < p.n) {
+        const uint4 *r = reinterpret_cast<const uint4 *>(p.seq + (base + lane) * (uint64_t)rd.stride);
+        a = pcl_ld_stream(r);
+        if (wide) b = pcl_ld_stream(r + 1);
+        Lraw = __ldcs(p.len + base + lane);
+    }
+    for (; base < p.n; base += step) {
         const uint64_t i = base + lane;
         const bool live = i < p.n;
+        const uint4 ca = a, cb = b;
+        uint32_t L = Lraw;
+        const uint64_t ni = i + step;
+        if (ni < p.n) {
+            const uint4 *r = reinterpret_cast<const uint4 *>(p.seq + ni * (uint64_t)rd.stride);
+            a = pcl_ld_stream(r);
+            if (wide) b = pcl_ld_stream(r + 1);
+            Lraw = __ldcs(p.len + ni);
+        }
         bool miss = false;
         if (live) {
-            uint32_t L = p.len[i];
             if (rd.max_len && L > rd.max_len) L = rd.max_len;
-            const uint4 *r = reinterpret_cast<const uint4 *>(p.seq + i * (uint64_t)rd.stride);
-            const uint4 a = pcl_ld_stream(r);
-            uint4 b = make_uint4(0u, 0u, 0u, 0u);                       // 16-byte records: the upper words are outside every mask
-            if (rd.stride == 32u) b = pcl_ld_stream(r + 1);
-            const uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+            const uint32_t w[8] = {ca.x, ca.y, ca.z, ca.w, cb.x, cb.y, cb.z, cb.w};
             uint32_t bk, uk;
             bool bbad, ubad;
             pcl_fast_extract(f, w, rev, &bk, &bbad, &uk, &ubad);
@@ -284,7 +302,7 @@ __global__ void __launch_bounds__(PCL_BLOCK) k_count_fast(const __grid_constant_
                     tc = ((uint32_t)f.t_start << 16) | (hi - f.t_start);
                     fs |= PCL_FSTATUS_TARGET;
                 }
-                p.tcoord[i] = tc;
+                pcl_st_stream(p.tcoord + i, tc);
             }
             uint32_t code = PCL_BC_ABSENT;
             if (bc_end <= L) {
@@ -303,9 +321,9 @@ __global__ void __launch_bounds__(PCL_BLOCK) k_count_fast(const __grid_constant_
                 bk = 0;
             }
             fs |= code << 4;
-            bc_out[i] = bk;
-            if (f.umi_len) umi_out[i] = umi_end <= L ? uk : PCL_KEY_ABSENT32;
-            p.fstatus[i] = (uint16_t)fs;
+            pcl_st_stream(bc_out + i, bk);
+            if (f.umi_len) pcl_st_stream(umi_out + i, umi_end <= L ? uk : PCL_KEY_ABSENT32);
+            pcl_st_stream(p.fstatus + i, (uint16_t)fs);
         }
         pcl_wl_push(p, wl, miss, pcl_wl_entry(i, f.bc_start, f.bc_len, 0u), lane);
     }
