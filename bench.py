@@ -278,11 +278,12 @@ def main():
     for kv in kern.values():
         kv["gbs"] = kv["alg_bytes"] / (kv["ms"] / 1e3) / 1e9 if kv["ms"] > 0 else None
     dom = max(kern, key=lambda k: kern[k]["ms"])
-    traffic = None
+    traffic = None                                   # DRAM bytes per launch of the dominant kernel, from the committed ncu capture
     tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
     if os.path.exists(tpath):
         try:
-            traffic = json.load(open(tpath)).get(dom)
+            ent = json.load(open(tpath)).get(dom)
+            traffic = float(ent["dram_bytes_per_pair"]) * n if ent else None
         except Exception:
             traffic = None
     step_alg_bytes = n * (108 + B_CORRECT_PER_MISS * f_mis)

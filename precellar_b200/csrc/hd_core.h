@@ -410,16 +410,19 @@ PCL_HD uint32_t pcl_brev32(uint32_t x) {
 #endif
 }
 
-// Four ASCII bytes -> four 2-bit codes packed into the low 8 bits (byte k -> bits 2k..2k+1), plus the
-// XOR of the word with the bytes those codes stand for (non-zero byte <=> not a base).
-PCL_HD uint32_t pcl_word_codes(uint32_t w, uint32_t *diff) {
-    const uint32_t c = ((w >> 1) ^ (w >> 2)) & 0x03030303u;              // A0 C1 G2 T3 per byte
-    const uint32_t m0 = c & 0x01010101u, m1 = (c >> 1) & 0x01010101u, a = m0 & m1;
-    // A 0x41  C 0x43  G 0x47  T 0x54 : bit6 | bit4 = c0&c1 | bit2 = c1 | bit1 = c0^c1 | bit0 = !(c0&c1)
-    const uint32_t expect = 0x40404040u | (a << 4) | (m1 << 2) | ((m0 ^ m1) << 1) | (a ^ 0x01010101u);
-    *diff = w ^ expect;
-    uint32_t t = c | (c >> 6);
-    return (t | (t >> 12)) & 0xFFu;
+// Four ASCII bytes -> four 2-bit codes packed into the low 8 bits (byte k -> bits 2k..2k+1), plus a word
+// whose byte k is non-zero iff byte k of w is not one of A C G T.
+//   codes : c = ((w>>1) ^ (w>>2)) & 3 per byte gives A0 C1 G2 T3; one multiply gathers the four fields
+//           (c * 0x01041040 puts c0|c1<<2|c2<<4|c3<<6 into the top byte without carries).
+//   valid : A 0100_0001  C 0100_0011  G 0100_0111  T 0101_0100.  Bits 7,6,5,3 must read 0,1,0,0; of the
+//           free bits (4,2,1,0) the four bases are exactly those with  b0 == !b4  and  (b2 & !b1) == b4.
+PCL_HD uint32_t pcl_word_codes(uint32_t w, uint32_t *bad) {
+    const uint32_t w1 = w >> 1, w2 = w >> 2, w4 = w >> 4;
+    const uint32_t c = (w1 ^ w2) & 0x03030303u;
+    const uint32_t t = (w2 & ~w1) ^ w4;                                   // bit 0 of each byte must be 0
+    const uint32_t u = (~(w4 ^ w)) | t;                                   // ... and b0 != b4
+    *bad = ((w & 0xE8E8E8E8u) ^ 0x40404040u) | (u & 0x01010101u);
+    return (c * 0x01041040u) >> 24;
 }
 
 // 2-bit little-endian-by-position field (base i at bits 2i) -> reported key:
@@ -445,6 +448,7 @@ PCL_HD void pcl_fast_extract(const FastLayout &f, const uint32_t *w, bool rev, u
 #pragma unroll
 #endif
     for (int k = 0; k < 8; ++k) {
+        if ((f.bc_mask[k] | f.umi_mask[k]) == 0u) continue;              // uniform: this word holds no barcode / UMI byte
         uint32_t d;
         const uint32_t c8 = pcl_word_codes(w[k] & fold, &d);
         codes |= (uint64_t)c8 << (8 * k);
