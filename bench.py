@@ -134,6 +134,14 @@ def run_reference_sample(wl, seq, qual, length, len2, n_threads, steps=1, warmup
 
 
 def main():
+    # stdout carries exactly one JSON line: libraries that print to fd 1 (e.g. NCCL's version banner) go to stderr
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(os.dup(2), "w")
+
+    def emit(obj):
+        os.write(json_fd, (json.dumps(obj) + "\n").encode())
+
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
@@ -175,7 +183,7 @@ def main():
         ms = 1e3 * float(np.mean(times))
         v = ns / (ms / 1e3)
         cfg = {"workload": workload, "sample_pairs_per_step": ns, "l2": "inputs >> L2 (host arm)"}
-        print(json.dumps({
+        emit({
             "impl": "reference", "metric": "barcode-corrected read-pairs/sec", "value": v, "unit": "read-pairs/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": min(args.warmup, 1), "ms_per_step": ms,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8/f64", "data": "synthetic",
@@ -184,7 +192,7 @@ def main():
                              "sample": f"{ns} read pairs per step: serial count pass + {host_cores}-thread correct pass "
                                        "(C++ restatement of the reference algorithm, in-memory SoA input)"},
             "e2e": {"value": v, "unit": "read-pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "gpu_launches": 0}))
+            "gpu_launches": 0})
         return 0
 
     # ------------------------------------------------------------------ our arm
@@ -337,12 +345,14 @@ def main():
                 ch.upload(0, HostBatch(seq_h[lo:hi], qual_h[lo:hi], len_h[lo:hi]))
                 ch.upload(1, HostBatch(None, None, len2_h[lo:hi]))
                 pipe.count(ch)
+                # UMI keys and insert coordinates are final after pass 1: they travel back while later chunks upload
+                ch.fetch(0, outs[c][0], wait=False, planes=("umi_key",))
+                ch.fetch(1, outs[c][1], wait=False)
             pipe.allreduce()
-            for ch in chunks:
-                pipe.correct(ch, THRESHOLD)
             for c, ch in enumerate(chunks):
-                ch.fetch(0, outs[c][0])
-                ch.fetch(1, outs[c][1])
+                pipe.correct(ch, THRESHOLD)
+                ch.fetch(0, outs[c][0], wait=False, planes=("fstatus", "bc_key"))
+            pipe.sync()
 
         for _ in range(2):
             step_e2e()
@@ -353,8 +363,9 @@ def main():
         pipe.sync()
         barrier()
         dt = max_over_ranks(time.perf_counter() - t0) / args.e2e_steps
-        e2e = {"value": n * world / dt, "unit": "read-pairs/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-               "ms_per_step": dt * 1e3, "chunks": nc,
+        e2e = {"value": n * world / dt, "unit": "read-pairs/s", "h2d_bytes_per_step": int(h2d) * world,
+               "d2h_bytes_per_step": int(d2h) * world, "h2d_bytes_per_step_per_gpu": int(h2d),
+               "d2h_bytes_per_step_per_gpu": int(d2h), "ms_per_step": dt * 1e3, "chunks": nc,
                "note": "pinned host SoA planes -> H2D -> count -> allreduce -> correct -> D2H of every result plane"}
 
         # ------------------------------------------------------------- CPU baseline + parity on a bounded sample
@@ -397,7 +408,7 @@ def main():
             "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": int(launches),
             "clocks": clocks.summary(), "parity": parity, "host_cores": host_cores,
         }
-        print(json.dumps(out))
+        emit(out)
     pipe.close()
     if world > 1:
         dist.destroy_process_group()

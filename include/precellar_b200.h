@@ -209,6 +209,10 @@ int pcl_correct(pcl_ctx *ctx, pcl_chunk *chunk, double threshold, double max_exp
 
 /* ---- outputs ------------------------------------------------------------------------------ */
 int pcl_chunk_fetch(pcl_chunk *chunk, int read_slot, const pcl_read_results *out);   /* D2H + wait */
+/* Same copies without the wait (stream-ordered on the chunk's stream; pcl_sync or a later pcl_chunk_fetch
+ * completes them).  UMI keys, coordinates and the split status are final after pcl_count, so they can travel
+ * back while later chunks are still uploading; fstatus barcode codes and bc_key are final after pcl_correct. */
+int pcl_chunk_fetch_async(pcl_chunk *chunk, int read_slot, const pcl_read_results *out);
 /* counts[i] for whitelist entry i (deduplicated file order); any pointer may be NULL. */
 int pcl_counts_fetch(pcl_ctx *ctx, int region_slot, uint64_t *counts, uint64_t *mismatch, uint64_t *total);
 /* per read file: num_reads, num_defect (2 * n_reads values) accumulated by pcl_count since the last reset */

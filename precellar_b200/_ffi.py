@@ -70,7 +70,7 @@ SYMBOLS = [
     "pcl_host_alloc", "pcl_host_free", "pcl_profile_enable", "pcl_profile_get", "pcl_profile_reset",
     "pcl_launch_count", "pcl_timer_start", "pcl_timer_stop_ms",
     "pcl_qc_enable", "pcl_qc_accumulate", "pcl_qc_fetch_categories",
-    "pcl_fastq_open", "pcl_fastq_close", "pcl_fastq_error", "pcl_fastq_read",
+    "pcl_fastq_open", "pcl_fastq_close", "pcl_fastq_error", "pcl_fastq_read", "pcl_chunk_fetch_async",
 ]
 
 _lib = None
@@ -111,6 +111,7 @@ def lib() -> C.CDLL:
         "pcl_counts_allreduce": (i32, [vp]),
         "pcl_correct": (i32, [vp, vp, f64, f64]),
         "pcl_chunk_fetch": (i32, [vp, i32, C.POINTER(ReadResults)]),
+        "pcl_chunk_fetch_async": (i32, [vp, i32, C.POINTER(ReadResults)]),
         "pcl_counts_fetch": (i32, [vp, i32, vp, C.POINTER(u64), C.POINTER(u64)]),
         "pcl_qc_fetch": (i32, [vp, vp]),
         "pcl_key_decode": (i32, [u64, C.c_char_p]),

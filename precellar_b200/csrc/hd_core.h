@@ -417,12 +417,22 @@ PCL_HD uint32_t pcl_brev32(uint32_t x) {
 //   valid : A 0100_0001  C 0100_0011  G 0100_0111  T 0101_0100.  Bits 7,6,5,3 must read 0,1,0,0; of the
 //           free bits (4,2,1,0) the four bases are exactly those with  b0 == !b4  and  (b2 & !b1) == b4.
 PCL_HD uint32_t pcl_word_codes(uint32_t w, uint32_t *bad) {
+#ifdef __CUDA_ARCH__
+    // the kernel is bound by the ALU pipe (shifts / logic); constant right shifts go to the FMA pipe as
+    // multiply-high, and the gather of the four 2-bit codes is one dot product
+    const uint32_t w1 = __umulhi(w, 0x80000000u), w2 = __umulhi(w, 0x40000000u), w4 = __umulhi(w, 0x10000000u);
+#else
     const uint32_t w1 = w >> 1, w2 = w >> 2, w4 = w >> 4;
+#endif
     const uint32_t c = (w1 ^ w2) & 0x03030303u;
     const uint32_t t = (w2 & ~w1) ^ w4;                                   // bit 0 of each byte must be 0
     const uint32_t u = (~(w4 ^ w)) | t;                                   // ... and b0 != b4
     *bad = ((w & 0xE8E8E8E8u) ^ 0x40404040u) | (u & 0x01010101u);
+#ifdef __CUDA_ARCH__
+    return (uint32_t)__dp4a(c, 0x40100401u, 0u);                          // c0 + 4 c1 + 16 c2 + 64 c3
+#else
     return (c * 0x01041040u) >> 24;
+#endif
 }
 
 // 2-bit little-endian-by-position field (base i at bits 2i) -> reported key:

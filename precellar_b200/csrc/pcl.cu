@@ -651,7 +651,7 @@ int pcl_correct(pcl_ctx *ctx, pcl_chunk *c, double threshold, double max_expecte
 // ------------------------------------------------------------------------------------------
 // outputs
 // ------------------------------------------------------------------------------------------
-int pcl_chunk_fetch(pcl_chunk *c, int read_slot, const pcl_read_results *out) {
+static int chunk_fetch(pcl_chunk *c, int read_slot, const pcl_read_results *out, bool wait) {
     if (!c || !out) return PCL_ERR_ARG;
     pcl_ctx *ctx = c->ctx;
     if (read_slot < 0 || read_slot >= ctx->n_reads) return fail(ctx, PCL_ERR_ARG, "bad read_slot");
@@ -673,9 +673,12 @@ int pcl_chunk_fetch(pcl_chunk *c, int read_slot, const pcl_read_results *out) {
         CU(ctx, D2H(out->umi_key[j], b.umi_key[j], n * inf.umi_key_bytes[j]));
         if (!inf.fixed_layout) CU(ctx, D2H(out->ucoord[j], b.ucoord[j], n * 4));
     }
-    CU(ctx, cudaStreamSynchronize(c->stream));
+    if (wait) CU(ctx, cudaStreamSynchronize(c->stream));
     return PCL_OK;
 }
+
+int pcl_chunk_fetch(pcl_chunk *c, int read_slot, const pcl_read_results *out) { return chunk_fetch(c, read_slot, out, true); }
+int pcl_chunk_fetch_async(pcl_chunk *c, int read_slot, const pcl_read_results *out) { return chunk_fetch(c, read_slot, out, false); }
 
 int pcl_counts_fetch(pcl_ctx *ctx, int region_slot, uint64_t *counts, uint64_t *mismatch, uint64_t *total) {
     if (!ctx || region_slot < 0 || region_slot >= PCL_MAX_REGIONS) return PCL_ERR_ARG;

@@ -88,25 +88,34 @@ class Chunk:
         check(self.pipe.ctx, lib().pcl_timer_stop_ms(self.h, C.byref(ms)))
         return ms.value
 
-    def fetch(self, read_slot: int, out: Optional[ReadResults] = None) -> ReadResults:
-        """Blocking D2H of one read file's results into (optionally caller-provided) host arrays."""
+    def fetch(self, read_slot: int, out: Optional[ReadResults] = None, *, wait: bool = True,
+              planes: Optional[Sequence[str]] = None) -> ReadResults:
+        """D2H of one read file's results into (optionally caller-provided) host arrays.
+        wait=False only enqueues the copies (``BarcodePipeline.sync`` completes them).  `planes` restricts the copy
+        to a subset of {"fstatus", "tcoord", "bc_key", "umi_key", "coords"}: everything except the barcode codes in
+        fstatus and bc_key is final right after ``count``."""
         info = self.pipe.infos[read_slot]
         n = self.n
         if out is None:
             out = self.pipe.alloc_results(read_slot, n)
+        want = (lambda k: True) if planes is None else (lambda k: k in planes)
         rr = _ffi.ReadResults()
-        rr.fstatus = out.fstatus.ctypes.data
-        if info.has_target:
+        if want("fstatus"):
+            rr.fstatus = out.fstatus.ctypes.data
+        if info.has_target and want("tcoord"):
             rr.tcoord = out.tcoord.ctypes.data
         for j in range(info.n_bc):
-            rr.bc_key[j] = out.bc_key[j].ctypes.data
-            if not info.fixed_layout:
+            if want("bc_key"):
+                rr.bc_key[j] = out.bc_key[j].ctypes.data
+            if not info.fixed_layout and want("coords"):
                 rr.bcoord[j] = out.bcoord[j].ctypes.data
         for j in range(info.n_umi):
-            rr.umi_key[j] = out.umi_key[j].ctypes.data
-            if not info.fixed_layout:
+            if want("umi_key"):
+                rr.umi_key[j] = out.umi_key[j].ctypes.data
+            if not info.fixed_layout and want("coords"):
                 rr.ucoord[j] = out.ucoord[j].ctypes.data
-        check(self.pipe.ctx, lib().pcl_chunk_fetch(self.h, read_slot, C.byref(rr)))
+        fn = lib().pcl_chunk_fetch if wait else lib().pcl_chunk_fetch_async
+        check(self.pipe.ctx, fn(self.h, read_slot, C.byref(rr)))
         return out
 
     def close(self) -> None:
