@@ -197,3 +197,84 @@ def test_qc_fastq_counters(layouts, name):
     np.testing.assert_array_equal(cat, ores.qc_cat)
     np.testing.assert_array_equal(per, ores.qc_per_file)
     assert cat[1, 1] > 0 and cat[1, 2] > 0
+
+
+def _bulk(layout, batches, n_threads=16, **kw):
+    """Run the CUDA path and the oracle on host batches; returns compare_bulk's mismatch table."""
+    from oracle import pyoracle as O
+    from precellar_b200.pipeline import BarcodePipeline
+    from tools.v3check import compare_bulk
+    pipe = BarcodePipeline(layout)
+    try:
+        results = pipe.run(batches, correct=True, threshold=kw.get("threshold", 0.975))
+        counts = {g: pipe.counts(g) for g in range(len(layout.region_ids))}
+        infos = pipe.infos
+        qc = pipe.qc()
+    finally:
+        pipe.close()
+    wl = {}
+    for g, rid in enumerate(layout.region_ids):
+        w = layout.whitelists[rid]
+        if isinstance(w, np.ndarray):
+            wl[g] = (w.reshape(-1), np.arange(len(w) + 1, dtype=np.uint64) * np.uint64(w.shape[1]), len(w))
+        else:
+            wl[g] = w
+    orc = O.Oracle(O.reads_from_layout(layout), wl)
+    for r, b in enumerate(batches):
+        orc.set_input(r, b.seq, b.qual, b.length, 0 if b.seq is None else b.seq.shape[1])
+    orc.count()
+    ores = orc.annotate(correct=True, threshold=kw.get("threshold", 0.975), n_threads=n_threads)
+    ocounts = {g: orc.counts(g) for g in range(len(layout.region_ids))}
+    fields = compare_bulk(layout, infos, results, counts, ores, ocounts)
+    assert np.array_equal(qc[:, 1], ores.qc_per_file[:, 1])
+    return fields, results, ores
+
+
+def test_atac_config_reverse_complemented_i2_737k_whitelist():
+    """BASELINE configs[1] shape (10x scATAC: neg-strand 16 nt I2, 737 K whitelist, read triples), 5 M triples."""
+    from tools import synth as S
+    from precellar_b200.configs import atac_layout
+    from precellar_b200.pipeline import HostBatch
+    n_wl, n = 737_000, 5_000_000
+    wl = S.make_whitelist(n_wl, 16, seed=0xA7AC)
+    syn = S.Synth(S.SynthSpec(n_wl, bc_len=16, umi_len=0, stride=16, reverse=True, seed=0x5EED0002), wl)
+    seq, qual, length = syn.host_arrays(0, n)
+    l1 = np.full(n, 50, np.uint16)
+    l2 = np.full(n, 50, np.uint16)
+    l2[::777] = 0
+    fields, results, ores = _bulk(atac_layout(wl, 50), [HostBatch(None, None, l1), HostBatch(seq, qual, length), HostBatch(None, None, l2)])
+    assert sum(fields.values()) == 0, fields
+    code = (results[1].fstatus.astype(np.uint32) >> 4) & 7
+    assert (code == _ffi.BC_EXACT).mean() > 0.7 and (code == _ffi.BC_CORRECTED).sum() > 100_000
+
+
+def test_multiome_atac_config_linker_plus_reverse_barcode():
+    """BASELINE configs[2], ATAC side: I2 = 8 nt linker + neg-strand 16 nt barcode (24 nt), 737 K whitelist."""
+    from tools import synth as S
+    from precellar_b200.configs import multiome_atac_layout
+    from precellar_b200.pipeline import HostBatch
+    n_wl, n = 737_000, 3_000_000
+    wl = S.make_whitelist(n_wl, 16, seed=0xA7AD)
+    syn = S.Synth(S.SynthSpec(n_wl, bc_len=16, umi_len=0, prefix_len=8, stride=32, reverse=True, seed=0x5EED0003), wl)
+    seq, qual, length = syn.host_arrays(0, n)
+    l1 = np.full(n, 50, np.uint16)
+    fields, results, ores = _bulk(multiome_atac_layout(wl, 50), [HostBatch(None, None, l1), HostBatch(seq, qual, length), HostBatch(None, None, l1)])
+    assert sum(fields.values()) == 0, fields
+
+
+def test_sci3_config_variable_hairpin_and_anchor():
+    """BASELINE configs[3] shape (sci-RNA-seq3: hairpin 9|10 + CAGAGC anchor + UMI 8 + RT 10), 3 M pairs through the
+    element-table interpreter kernel; includes anchor mismatches (defect records)."""
+    from tools import synth as S
+    from precellar_b200.configs import sci3_layout
+    from precellar_b200.pipeline import HostBatch
+    hp = S.make_mixed_whitelist(238, 146, 7)
+    rt = [bytes(r) for r in S.make_whitelist(384, 10, 99)]
+    gen = S.SynthSci3(hp, rt)
+    n = 3_000_000
+    seq, qual, length = gen.host_arrays(0, n)
+    l2 = np.full(n, 100, np.uint16)
+    fields, results, ores = _bulk(sci3_layout(hp, rt, 34, 100), [HostBatch(seq, qual, length), HostBatch(None, None, l2)])
+    assert sum(fields.values()) == 0, fields
+    assert (ores.fstatus[0] != 0).sum() > 1000          # PatternMismatch records exist and agree
+    assert (ores.bc_index[0] >= 0).mean() > 0.8 and (ores.bc_index[1] >= 0).mean() > 0.8

@@ -28,6 +28,11 @@ class _Params(C.Structure):
                 ("pad", C.c_uint32)]
 
 
+class _Params3(C.Structure):
+    _fields_ = [("seed", C.c_uint64), ("n_hp", C.c_uint32), ("n_rt", C.c_uint32), ("n_cells", C.c_uint32),
+                ("stride", C.c_uint32)]
+
+
 _lib = None
 
 
@@ -43,6 +48,11 @@ def lib():
         L.synth_fill_device.argtypes = [C.c_void_p, C.c_int, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.synth_fill_u16_device.argtypes = [C.c_int, C.c_void_p, C.c_uint16, C.c_uint64, C.c_void_p]
         L.synth_memcpy_d2h.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_uint64]
+        L.synth3_create.restype = C.c_void_p
+        L.synth3_create.argtypes = [C.POINTER(_Params3), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.synth3_destroy.argtypes = [C.c_void_p]
+        L.synth3_fill_host.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+        L.synth3_fill_device.argtypes = [C.c_void_p, C.c_int, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         _lib = L
     return _lib
 
@@ -140,4 +150,55 @@ class Synth:
     def close(self):
         if self.h:
             lib().synth_destroy(self.h)
+            self.h = None
+
+
+def make_mixed_whitelist(n9: int, n10: int, seed: int):
+    """Distinct 9-mers and 10-mers (sci-RNA-seq3 hairpin list: 238 x 9 + 146 x 10 in the reference's fixture),
+    shuffled; returns list[bytes]."""
+    rng = np.random.default_rng(seed)
+    a = [bytes(r) for r in make_whitelist(n9, 9, seed + 1)]
+    b = [bytes(r) for r in make_whitelist(n10, 10, seed + 2)]
+    items = a + b
+    rng.shuffle(items)
+    return items
+
+
+class SynthSci3:
+    """sci-RNA-seq3 R1 generator (hairpin 9|10 + CAGAGC + UMI 8 + RT 10, 34 nt)."""
+
+    def __init__(self, hp, rt, n_cells: int = 10000, stride: int = 48, seed: int = SEED):
+        self.hp, self.rt, self.stride = list(hp), list(rt), stride
+        hp10 = np.full((len(hp), 10), ord("A"), np.uint8)
+        hl = np.zeros(len(hp), np.uint8)
+        for i, x in enumerate(hp):
+            hp10[i, :len(x)] = np.frombuffer(x, np.uint8)
+            hl[i] = len(x)
+        rt10 = np.stack([np.frombuffer(x, np.uint8) for x in rt])
+        rng = np.random.default_rng(seed ^ 0x5C13)
+        n_cells = min(n_cells, len(hp) * len(rt))
+        combos = rng.permutation(len(hp) * len(rt))[:n_cells]
+        self.cells = ((combos // len(rt)).astype(np.uint32) << 16) | (combos % len(rt)).astype(np.uint32)
+        self.thr = zipf_thresholds(n_cells)
+        self._keep = (hp10, hl, rt10)
+        p = _Params3(seed, len(hp), len(rt), n_cells, stride)
+        self.h = C.c_void_p(lib().synth3_create(C.byref(p), hp10.ctypes.data, hl.ctypes.data, rt10.ctypes.data,
+                                                self.cells.ctypes.data, self.thr.ctypes.data))
+
+    def host_arrays(self, first: int, n: int, n_threads: int = 0):
+        seq = np.empty((n, self.stride), np.uint8)
+        qual = np.empty((n, self.stride), np.uint8)
+        length = np.empty(n, np.uint16)
+        lib().synth3_fill_host(self.h, first, n, seq.ctypes.data, qual.ctypes.data, length.ctypes.data,
+                               n_threads or os.cpu_count() or 1)
+        return seq, qual, length
+
+    def fill_device(self, device: int, first: int, n: int, seq_ptr: int, qual_ptr: int, len_ptr: int, stream: int = 0):
+        rc = lib().synth3_fill_device(self.h, device, first, n, seq_ptr, qual_ptr, len_ptr, stream)
+        if rc:
+            raise RuntimeError(f"synth3_fill_device: cudaError {rc}")
+
+    def close(self):
+        if self.h:
+            lib().synth3_destroy(self.h)
             self.h = None

@@ -110,6 +110,63 @@ __global__ void k_synth(synth_params p, const uint8_t *wl, const uint32_t *cells
     }
 }
 
+// sci-RNA-seq3 R1: hairpin barcode (9 or 10 nt) + CAGAGC + UMI 8 + RT barcode 10 (+ 'T' when the hairpin is
+// 9 nt, so that every R1 is 34 nt).  cells[] holds (hp_index << 16 | rt_index) pairs.
+struct synth_sci3_params {
+    uint64_t seed;
+    uint32_t n_hp, n_rt, n_cells, stride;
+};
+
+HD void synth_sci3_record(const synth_sci3_params &p, const uint8_t *hp, const uint8_t *hp_len, const uint8_t *rt,
+                          const uint32_t *cells, const uint64_t *zipf_thr, uint64_t i, uint8_t *seq, uint8_t *qual) {
+    const char ACGT[4] = {'A', 'C', 'G', 'T'};
+    const uint64_t r0 = rnd(p.seed, i, 0);
+    uint32_t hi, ri;
+    if ((uint32_t)(r0 >> 32) < 4080218931u) {
+        const uint64_t u = rnd(p.seed, i, 1);
+        uint32_t lo = 0, top = p.n_cells - 1;
+        while (lo < top) {
+            const uint32_t mid = (lo + top) >> 1;
+            if (zipf_thr[mid] > u) top = mid; else lo = mid + 1;
+        }
+        hi = cells[lo] >> 16; ri = cells[lo] & 0xFFFFu;
+    } else {
+        const uint64_t u = rnd(p.seed, i, 1);
+        hi = (uint32_t)(((u >> 32) * (uint64_t)p.n_hp) >> 32);
+        ri = (uint32_t)(((u & 0xFFFFFFFFull) * (uint64_t)p.n_rt) >> 32);
+    }
+    const uint32_t hl = hp_len[hi];
+    const char *linker = "CAGAGC";
+    for (uint32_t k = 0; k < 34u; ++k) {
+        const uint64_t r = rnd(p.seed, i, 2 + k);
+        uint8_t base;
+        if (k < hl) base = hp[hi * 10u + k];
+        else if (k < hl + 6u) base = (uint8_t)linker[k - hl];
+        else if (k < hl + 14u) base = (uint8_t)ACGT[(r >> 60) & 3u];
+        else if (k < hl + 24u) base = rt[ri * 10u + (k - hl - 14u)];
+        else base = 'T';
+        uint8_t q; bool sub, to_n; uint32_t shift;
+        qual_and_error(r, &q, &sub, &to_n, &shift);
+        if (to_n) base = 'N';
+        else if (sub) {
+            const uint32_t c = base == 'A' ? 0u : base == 'C' ? 1u : base == 'G' ? 2u : 3u;
+            base = (uint8_t)ACGT[(c + shift) & 3u];
+        }
+        seq[k] = base;
+        qual[k] = q;
+    }
+    for (uint32_t k = 34u; k < p.stride; ++k) { seq[k] = 'N'; qual[k] = '!'; }
+}
+
+__global__ void k_synth_sci3(synth_sci3_params p, const uint8_t *hp, const uint8_t *hp_len, const uint8_t *rt,
+                             const uint32_t *cells, const uint64_t *zipf_thr, uint64_t first, uint64_t n, uint8_t *seq,
+                             uint8_t *qual, uint16_t *len) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        synth_sci3_record(p, hp, hp_len, rt, cells, zipf_thr, first + i, seq + i * p.stride, qual + i * p.stride);
+        len[i] = 34;
+    }
+}
+
 __global__ void k_fill_u16(uint16_t *dst, uint16_t v, uint64_t n) {
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) dst[i] = v;
 }
@@ -176,6 +233,71 @@ int synth_fill_device(synth_t *s, int device, uint64_t first, uint64_t n, void *
     if (blocks > 148 * 16) blocks = 148 * 16;
     k_synth<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(s->p, s->d_wl, s->d_cells, s->d_thr, first, n, (uint8_t *)seq,
                                                                (uint8_t *)qual, (uint16_t *)len);
+    return (int)cudaGetLastError();
+}
+
+struct synth3_t {
+    synth_sci3_params p;
+    std::vector<uint8_t> hp, hp_len, rt;
+    std::vector<uint32_t> cells;
+    std::vector<uint64_t> thr;
+    uint8_t *d_hp = nullptr, *d_hl = nullptr, *d_rt = nullptr;
+    uint32_t *d_cells = nullptr;
+    uint64_t *d_thr = nullptr;
+};
+
+synth3_t *synth3_create(const synth_sci3_params *p, const uint8_t *hp10, const uint8_t *hp_len, const uint8_t *rt10,
+                        const uint32_t *cells, const uint64_t *zipf_thr) {
+    synth3_t *s = new synth3_t();
+    s->p = *p;
+    s->hp.assign(hp10, hp10 + (size_t)p->n_hp * 10);
+    s->hp_len.assign(hp_len, hp_len + p->n_hp);
+    s->rt.assign(rt10, rt10 + (size_t)p->n_rt * 10);
+    s->cells.assign(cells, cells + p->n_cells);
+    s->thr.assign(zipf_thr, zipf_thr + p->n_cells);
+    return s;
+}
+
+void synth3_destroy(synth3_t *s) {
+    if (!s) return;
+    cudaFree(s->d_hp); cudaFree(s->d_hl); cudaFree(s->d_rt); cudaFree(s->d_cells); cudaFree(s->d_thr);
+    delete s;
+}
+
+int synth3_fill_host(synth3_t *s, uint64_t first, uint64_t n, uint8_t *seq, uint8_t *qual, uint16_t *len, int n_threads) {
+    if (n_threads < 1) n_threads = 1;
+    auto work = [&](int t) {
+        uint64_t lo = n * t / n_threads, hi = n * (t + 1) / n_threads;
+        for (uint64_t i = lo; i < hi; ++i) {
+            synth_sci3_record(s->p, s->hp.data(), s->hp_len.data(), s->rt.data(), s->cells.data(), s->thr.data(), first + i,
+                              seq + i * s->p.stride, qual + i * s->p.stride);
+            len[i] = 34;
+        }
+    };
+    std::vector<std::thread> th;
+    for (int t = 0; t < n_threads; ++t) th.emplace_back(work, t);
+    for (auto &t : th) t.join();
+    return 0;
+}
+
+int synth3_fill_device(synth3_t *s, int device, uint64_t first, uint64_t n, void *seq, void *qual, void *len, void *stream) {
+    cudaError_t e = cudaSetDevice(device);
+    if (e != cudaSuccess) return (int)e;
+    if (!s->d_hp) {
+        cudaMalloc(&s->d_hp, s->hp.size()); cudaMalloc(&s->d_hl, s->hp_len.size()); cudaMalloc(&s->d_rt, s->rt.size());
+        cudaMalloc(&s->d_cells, s->cells.size() * 4); cudaMalloc(&s->d_thr, s->thr.size() * 8);
+        cudaMemcpy(s->d_hp, s->hp.data(), s->hp.size(), cudaMemcpyHostToDevice);
+        cudaMemcpy(s->d_hl, s->hp_len.data(), s->hp_len.size(), cudaMemcpyHostToDevice);
+        cudaMemcpy(s->d_rt, s->rt.data(), s->rt.size(), cudaMemcpyHostToDevice);
+        cudaMemcpy(s->d_cells, s->cells.data(), s->cells.size() * 4, cudaMemcpyHostToDevice);
+        cudaMemcpy(s->d_thr, s->thr.data(), s->thr.size() * 8, cudaMemcpyHostToDevice);
+        if ((e = cudaGetLastError()) != cudaSuccess) return (int)e;
+    }
+    if (n == 0) return 0;
+    uint64_t blocks = (n + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    k_synth_sci3<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(s->p, s->d_hp, s->d_hl, s->d_rt, s->d_cells, s->d_thr, first, n,
+                                                                    (uint8_t *)seq, (uint8_t *)qual, (uint16_t *)len);
     return (int)cudaGetLastError();
 }
 
