@@ -133,6 +133,52 @@ def run_reference_sample(wl, seq, qual, length, len2, n_threads, steps=1, warmup
     return times, res, counts
 
 
+def measure_ingest(syn, n_pairs: int, tmpdir: str) -> dict:
+    """Host ingest reported separately from the device path: FASTQ text (plain and gzip) -> pinned-ready SoA planes
+    through the C++ reader (csrc/ingest.cpp), one decoding thread per file like the reference's readers."""
+    import gzip
+    import shutil
+    from precellar_b200.ingest import GroupReader
+    seq, qual, length = syn.host_arrays(0, n_pairs)
+    rng = np.random.default_rng(1)
+    ins = rng.choice(np.frombuffer(b"ACGT", np.uint8), (n_pairs, R2_LEN))
+    insq = np.full((n_pairs, R2_LEN), ord("F"), np.uint8)
+    def fq(path, s, q, L, tag):
+        nl = np.full((n_pairs, 1), 10, np.uint8)
+        names = np.char.add(np.char.add("@r", np.arange(n_pairs).astype(str)), tag).astype("S")
+        w = names.dtype.itemsize
+        name_arr = np.frombuffer(names.tobytes(), np.uint8).reshape(n_pairs, w).copy()
+        name_arr[name_arr == 0] = ord(" ")              # pad with blanks: part of the description, ignored by the name check
+        plus = np.full((n_pairs, 1), ord("+"), np.uint8)
+        rec = np.concatenate([name_arr, nl, s[:, :L], nl, plus, nl, q[:, :L], nl], axis=1)
+        with open(path, "wb") as fh:
+            fh.write(rec.tobytes())
+    p1, p2 = os.path.join(tmpdir, "R1.fq"), os.path.join(tmpdir, "R2.fq")
+    fq(p1, seq, qual, 28, "/1")
+    fq(p2, ins, insq, R2_LEN, "/2")
+    out = {"pairs": n_pairs, "threads": 2, "note": "FASTQ text -> SoA planes (R1 32 B rows + lengths, R2 lengths), one decoder thread per file"}
+    for kind in ("plain", "gzip"):
+        a, b = p1, p2
+        if kind == "gzip":
+            for p in (p1, p2):
+                with open(p, "rb") as fi, gzip.open(p + ".gz", "wb", compresslevel=1) as fo:
+                    shutil.copyfileobj(fi, fo, 1 << 24)
+            a, b = p1 + ".gz", p2 + ".gz"
+        rd = GroupReader([[a], [b]], [32, 0], [False, False])
+        t0 = time.perf_counter()
+        got = 0
+        while True:
+            g = rd.next(1 << 20)
+            if g is None:
+                break
+            got += len(g[0].batch.length)
+        dt = time.perf_counter() - t0
+        rd.close()
+        assert got == n_pairs
+        out[f"{kind}_fastq_pairs_per_s"] = n_pairs / dt
+    return out
+
+
 def main():
     # stdout carries exactly one JSON line: libraries that print to fd 1 (e.g. NCCL's version banner) go to stderr
     json_fd = os.dup(1)
@@ -153,6 +199,7 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=2_500_000)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--ingest-sample", type=int, default=1_000_000)
     args = ap.parse_args()
 
     rank, local_rank, world = env_int("RANK", 0), env_int("LOCAL_RANK", 0), env_int("WORLD_SIZE", 1)
@@ -396,6 +443,12 @@ def main():
     else:
         cpu_baseline = None
 
+    ingest = None
+    if rank == 0 and world == 1 and not args.no_cpu and args.ingest_sample > 0:
+        import tempfile
+        with tempfile.TemporaryDirectory() as td:
+            ingest = measure_ingest(syn, args.ingest_sample, td)
+
     if rank == 0:
         out = {
             "metric": "barcode-corrected read-pairs/sec", "value": value, "unit": "read-pairs/s", "n_gpus": world,
@@ -406,7 +459,7 @@ def main():
                        "whitelist replicated, one NCCL allreduce of the counts",
                        "l2": "inputs (8.3 GB per GPU) are far larger than L2; no flush needed"},
             "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": int(launches),
-            "clocks": clocks.summary(), "parity": parity, "host_cores": host_cores,
+            "clocks": clocks.summary(), "parity": parity, "host_cores": host_cores, "host_ingest": ingest,
         }
         emit(out)
     pipe.close()
