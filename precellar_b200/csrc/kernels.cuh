@@ -255,77 +255,129 @@ __global__ void __launch_bounds__(PCL_BLOCK) k_count_fast(const __grid_constant_
     const DTable &tab = p.tab[0];
     const bool rev = rd.is_reverse != 0;
     const uint32_t lane = threadIdx.x & 31u;
-    const uint64_t step = (uint64_t)gridDim.x * blockDim.x;
+    const uint32_t step = gridDim.x * blockDim.x;
+    const uint32_t n = (uint32_t)p.n;                                   // chunks hold < 2^32 records
     const uint32_t bc_end = (uint32_t)f.bc_start + f.bc_len, umi_end = (uint32_t)f.umi_start + f.umi_len;
     const bool len_ok = tab.mode == PCL_TAB_K32_L16 ? f.bc_len == 16 : (tab.mode == PCL_TAB_K32_MARKER && f.bc_len <= 15);
     const uint32_t absent_rest = (PCL_BC_ABSENT << 7) | (PCL_BC_ABSENT << 10) | (PCL_BC_ABSENT << 13);
     const bool wide = rd.stride == 32u;
+    const uint32_t *keys = reinterpret_cast<const uint32_t *>(tab.keys);
+    const uint32_t empty = (uint32_t)tab.empty, nb = tab.n_buckets;
     uint32_t *bc_out = reinterpret_cast<uint32_t *>(p.bc_key[0]);
     uint32_t *umi_out = reinterpret_cast<uint32_t *>(p.umi_key[0]);
     unsigned long long n_total = 0, n_mis = 0;
     WlCursor wl = {0, 0};
 
-    // software pipeline: the record of the NEXT iteration is in flight while the current one is processed
-    uint64_t base = (uint64_t)blockIdx.x * blockDim.x + (threadIdx.x & ~31u);
+    // Three-stage software pipeline over the records of a lane (k = iteration):
+    //   load    record k+1 : two streaming 128-bit loads + the length              (in flight during k)
+    //   probe   record k   : SWAR extraction, hash, issue the bucket loads          (in flight during k+1's extraction)
+    //   retire  record k-1 : compare the bucket, histogram, result stores, worklist
+    uint32_t base = blockIdx.x * blockDim.x + (threadIdx.x & ~31u);
     uint4 a = make_uint4(0u, 0u, 0u, 0u), b = make_uint4(0u, 0u, 0u, 0u);
     uint32_t Lraw = 0;
-    if (base + lane < p.n) {
-        const uint4 *r = reinterpret_cast<const uint4 *>(p.seq + (base + lane) * (uint64_t)rd.stride);
+    if (base < n && base + lane < n) {
+        const uint4 *r = reinterpret_cast<const uint4 *>(p.seq + (uint64_t)(base + lane) * rd.stride);
         a = pcl_ld_stream(r);
         if (wide) b = pcl_ld_stream(r + 1);
         Lraw = __ldcs(p.len + base + lane);
     }
-    for (; base < p.n; base += step) {
-        const uint64_t i = base + lane;
-        const bool live = i < p.n;
-        const uint4 ca = a, cb = b;
-        uint32_t L = Lraw;
-        const uint64_t ni = i + step;
-        if (ni < p.n) {
-            const uint4 *r = reinterpret_cast<const uint4 *>(p.seq + ni * (uint64_t)rd.stride);
-            a = pcl_ld_stream(r);
-            if (wide) b = pcl_ld_stream(r + 1);
-            Lraw = __ldcs(p.len + ni);
-        }
-        bool miss = false;
-        if (live) {
-            if (rd.max_len && L > rd.max_len) L = rd.max_len;
-            const uint32_t w[8] = {ca.x, ca.y, ca.z, ca.w, cb.x, cb.y, cb.z, cb.w};
-            uint32_t bk, uk;
-            bool bbad, ubad;
-            pcl_fast_extract(f, w, rev, &bk, &bbad, &uk, &ubad);
-            uint32_t fs = PCL_SPLIT_OK | absent_rest;
-            if (f.has_tail_target) {
-                uint32_t tc = PCL_COORD_ABSENT;
-                if (f.t_start < L && (uint32_t)f.t_start + f.t_min <= L) {
-                    const uint32_t hi = (uint32_t)f.t_start + f.t_max < L ? (uint32_t)f.t_start + f.t_max : L;
-                    tc = ((uint32_t)f.t_start << 16) | (hi - f.t_start);
-                    fs |= PCL_FSTATUS_TARGET;
-                }
-                pcl_st_stream(p.tcoord + i, tc);
+    // pending (probed, not yet retired) record
+    uint4 pv0 = make_uint4(0u, 0u, 0u, 0u), pv1 = pv0;
+    uint32_t p_i = 0, p_bk = 0, p_uk = 0, p_fs = 0, p_bucket = 0;
+    uint32_t p_flags = 0;                       // bit0 live, bit1 barcode present, bit2 probe issued, bit3 UMI present
+    bool have_pending = false;
+
+    for (;; base += step) {
+        const bool more = base < n;             // warp-uniform
+        // ---- probe stage for record k ----
+        uint32_t c_i = base + lane, c_bk = 0, c_uk = 0, c_fs = 0, c_flags = 0, c_bucket = 0;
+        uint4 cv0 = make_uint4(0u, 0u, 0u, 0u), cv1 = cv0;
+        if (more) {
+            const uint4 ca = a, cb = b;
+            uint32_t L = Lraw;
+            const uint32_t ni = c_i + step;
+            if (ni < n && ni >= c_i) {          // ---- load stage for record k+1 ----
+                const uint4 *r = reinterpret_cast<const uint4 *>(p.seq + (uint64_t)ni * rd.stride);
+                a = pcl_ld_stream(r);
+                if (wide) b = pcl_ld_stream(r + 1);
+                Lraw = __ldcs(p.len + ni);
             }
-            uint32_t code = PCL_BC_ABSENT;
-            if (bc_end <= L) {
-                ++n_total;
-                uint32_t slot = 0xFFFFFFFFu;
-                if (!bbad && len_ok) slot = pcl_probe32(tab, bk);
-                if (slot != 0xFFFFFFFFu) {
-                    code = PCL_BC_EXACT;
-                    pcl_hist_add(ck, cc, 0u, slot, tab.counts);
+            if (c_i < n) {
+                if (rd.max_len && L > rd.max_len) L = rd.max_len;
+                const uint32_t w[8] = {ca.x, ca.y, ca.z, ca.w, cb.x, cb.y, cb.z, cb.w};
+                bool bbad, ubad;
+                pcl_fast_extract(f, w, rev, &c_bk, &bbad, &c_uk, &ubad);
+                c_fs = PCL_SPLIT_OK | absent_rest;
+                c_flags = 1u;
+                if (f.has_tail_target) {
+                    uint32_t tc = PCL_COORD_ABSENT;
+                    if (f.t_start < L && (uint32_t)f.t_start + f.t_min <= L) {
+                        const uint32_t hi = (uint32_t)f.t_start + f.t_max < L ? (uint32_t)f.t_start + f.t_max : L;
+                        tc = ((uint32_t)f.t_start << 16) | (hi - f.t_start);
+                        c_fs |= PCL_FSTATUS_TARGET;
+                    }
+                    pcl_st_stream(p.tcoord + c_i, tc);
+                }
+                if (umi_end <= L) c_flags |= 8u;
+                if (bc_end <= L) {
+                    c_flags |= 2u;
+                    if (!bbad && len_ok && c_bk != empty) {
+                        c_flags |= 4u;
+                        c_bucket = pcl_hash32_bucket(c_bk, nb);
+                        cv0 = __ldg(reinterpret_cast<const uint4 *>(keys + (uint64_t)c_bucket * 8));
+                        cv1 = __ldg(reinterpret_cast<const uint4 *>(keys + (uint64_t)c_bucket * 8 + 4));
+                    }
                 } else {
-                    code = PCL_BC_NO_MATCH;
-                    ++n_mis;
-                    miss = true;
+                    c_bk = 0;
                 }
-            } else {
-                bk = 0;
             }
-            fs |= code << 4;
-            pcl_st_stream(bc_out + i, bk);
-            if (f.umi_len) pcl_st_stream(umi_out + i, umi_end <= L ? uk : PCL_KEY_ABSENT32);
-            pcl_st_stream(p.fstatus + i, (uint16_t)fs);
         }
-        pcl_wl_push(p, wl, miss, pcl_wl_entry(i, f.bc_start, f.bc_len, 0u), lane);
+        // ---- retire stage for record k-1 ----
+        if (have_pending) {
+            bool miss = false;
+            if (p_flags & 1u) {
+                uint32_t code = PCL_BC_ABSENT;
+                if (p_flags & 2u) {
+                    ++n_total;
+                    uint32_t slot = 0xFFFFFFFFu;
+                    if (p_flags & 4u) {
+                        uint32_t j = 8;
+                        j = (pv1.w == p_bk) ? 7u : j;
+                        j = (pv1.z == p_bk) ? 6u : j;
+                        j = (pv1.y == p_bk) ? 5u : j;
+                        j = (pv1.x == p_bk) ? 4u : j;
+                        j = (pv0.w == p_bk) ? 3u : j;
+                        j = (pv0.z == p_bk) ? 2u : j;
+                        j = (pv0.y == p_bk) ? 1u : j;
+                        j = (pv0.x == p_bk) ? 0u : j;
+                        if (j < 8u) slot = p_bucket * 8u + j;
+                        else if (pv1.w != empty) {                      // full bucket: the chain continues (rare)
+                            uint32_t bb = p_bucket;
+                            bool full = true;
+                            while (slot == 0xFFFFFFFFu && full) {
+                                bb = (bb + 1u == nb) ? 0u : bb + 1u;
+                                slot = pcl_bucket32(keys, bb, p_bk, empty, &full);
+                            }
+                        }
+                    }
+                    if (slot != 0xFFFFFFFFu) {
+                        code = PCL_BC_EXACT;
+                        pcl_hist_add(ck, cc, 0u, slot, tab.counts);
+                    } else {
+                        code = PCL_BC_NO_MATCH;
+                        ++n_mis;
+                        miss = true;
+                    }
+                }
+                pcl_st_stream(bc_out + p_i, p_bk);
+                if (f.umi_len) pcl_st_stream(umi_out + p_i, (p_flags & 8u) ? p_uk : PCL_KEY_ABSENT32);
+                pcl_st_stream(p.fstatus + p_i, (uint16_t)(p_fs | (code << 4)));
+            }
+            pcl_wl_push(p, wl, miss, pcl_wl_entry(p_i, f.bc_start, f.bc_len, 0u), lane);
+        }
+        if (!more) break;
+        pv0 = cv0; pv1 = cv1; p_i = c_i; p_bk = c_bk; p_uk = c_uk; p_fs = c_fs; p_flags = c_flags; p_bucket = c_bucket;
+        have_pending = true;
     }
     pcl_wl_finish(p, wl, lane);
     for (int o = 16; o > 0; o >>= 1) {

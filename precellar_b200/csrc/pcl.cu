@@ -562,7 +562,8 @@ int pcl_count(pcl_ctx *ctx, pcl_chunk *c) {
         p.num_defect = ctx->d_qc + r;
         CU(ctx, cudaMemsetAsync(b.wl_count, 0, sizeof(unsigned long long), c->stream));
         const DRead &d = ctx->dreads[r];
-        const bool fast = d.fast.enabled && ctx->tables[ctx->bc_region[r][0]].d.mode != PCL_TAB_K64 && !ctx->force_generic;
+        const bool fast = d.fast.enabled && ctx->tables[ctx->bc_region[r][0]].d.mode != PCL_TAB_K64 && !ctx->force_generic &&
+                          c->n < 0xFF000000ull;      // 32-bit record indices inside k_count_fast
         const bool lenonly = !d.needs_payload && d.fixed_layout && !ctx->force_generic;
         prof_begin(ctx, c->stream, d.needs_payload ? PCL_K_COUNT : PCL_K_COUNT_LENONLY);
         if (fast) k_count_fast<<<grid_for(ctx, c->n, 6), PCL_BLOCK, 0, c->stream>>>(p);
