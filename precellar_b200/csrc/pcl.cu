@@ -108,6 +108,7 @@ struct pcl_ctx {
     uint64_t prof_n[PCL_K_MAX] = {0};
     uint64_t launches = 0;
     int sm_count = 148;
+    int occ[8] = {1, 1, 1, 1, 1, 1, 1, 1};   // resident CTAs per SM of each kernel (see OCC_*)
     bool force_generic = false;   // PCL_FORCE_GENERIC=1: only the generic kernels (tests compare both paths)
     bool no_neighbour_tables = false;   // PCL_NO_NEIGHBOUR_TABLES=1: 3*L direct probes instead of the 4 neighbourhood tables
 };
@@ -177,6 +178,8 @@ void prof_end(pcl_ctx *ctx, cudaStream_t s) {
     cudaEventRecord(ctx->evs.back().b, s);
 }
 
+enum { OCC_COUNT = 0, OCC_COUNT_FAST, OCC_COUNT_LENONLY, OCC_ENUM, OCC_CORRECT_FAST, OCC_CORRECT, OCC_QC, OCC_GATHER };
+
 int grid_for(const pcl_ctx *ctx, uint64_t n_threads_wanted, int blocks_per_sm) {
     uint64_t blocks = (n_threads_wanted + PCL_BLOCK - 1) / PCL_BLOCK;
     uint64_t cap = (uint64_t)ctx->sm_count * blocks_per_sm;
@@ -237,6 +240,22 @@ int pcl_ctx_create(pcl_ctx **out, int device) {
     }
     if ((e = cudaMemcpy(ctx->d_lut, lut, sizeof lut, cudaMemcpyHostToDevice)) != cudaSuccess) return bail("cudaMemcpy", e);
     if ((e = cudaMemset(ctx->d_qc, 0, (PCL_MAX_READS + 12) * sizeof(unsigned long long))) != cudaSuccess) return bail("cudaMemset", e);
+    // persistent grids are exactly one resident wave: CTAs per SM come from the compiled kernels' real occupancy
+    {
+        auto occ = [&](const void *fn) {
+            int nblk = 0;
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nblk, fn, PCL_BLOCK, 0) != cudaSuccess || nblk < 1) { cudaGetLastError(); nblk = 1; }
+            return nblk;
+        };
+        ctx->occ[OCC_COUNT] = occ((const void *)k_count);
+        ctx->occ[OCC_COUNT_FAST] = occ((const void *)k_count_fast);
+        ctx->occ[OCC_COUNT_LENONLY] = occ((const void *)k_count_lenonly);
+        ctx->occ[OCC_ENUM] = occ((const void *)k_enum_all);
+        ctx->occ[OCC_CORRECT_FAST] = occ((const void *)k_correct<true>);
+        ctx->occ[OCC_CORRECT] = occ((const void *)k_correct<false>);
+        ctx->occ[OCC_QC] = occ((const void *)k_qc);
+        ctx->occ[OCC_GATHER] = occ((const void *)k_gather_counts);
+    }
     *out = ctx;
     return PCL_OK;
 }
@@ -566,9 +585,9 @@ int pcl_count(pcl_ctx *ctx, pcl_chunk *c) {
                           c->n < 0xFF000000ull;      // 32-bit record indices inside k_count_fast
         const bool lenonly = !d.needs_payload && d.fixed_layout && !ctx->force_generic;
         prof_begin(ctx, c->stream, d.needs_payload ? PCL_K_COUNT : PCL_K_COUNT_LENONLY);
-        if (fast) k_count_fast<<<grid_for(ctx, c->n, 6), PCL_BLOCK, 0, c->stream>>>(p);
-        else if (lenonly) k_count_lenonly<<<grid_for(ctx, c->n, 8), PCL_BLOCK, 0, c->stream>>>(p);
-        else k_count<<<grid_for(ctx, c->n, 6), PCL_BLOCK, 0, c->stream>>>(p);
+        if (fast) k_count_fast<<<grid_for(ctx, c->n, ctx->occ[OCC_COUNT_FAST]), PCL_BLOCK, 0, c->stream>>>(p);
+        else if (lenonly) k_count_lenonly<<<grid_for(ctx, c->n, ctx->occ[OCC_COUNT_LENONLY]), PCL_BLOCK, 0, c->stream>>>(p);
+        else k_count<<<grid_for(ctx, c->n, ctx->occ[OCC_COUNT]), PCL_BLOCK, 0, c->stream>>>(p);
         prof_end(ctx, c->stream);
         CU(ctx, cudaGetLastError());
         ctx->qc_reads[r] += c->n;
@@ -629,18 +648,20 @@ int pcl_correct(pcl_ctx *ctx, pcl_chunk *c, double threshold, double max_expecte
         if (check_ee) {
             CU(ctx, cudaMemsetAsync(b.wl_count, 0, sizeof(unsigned long long), c->stream));
             prof_begin(ctx, c->stream, PCL_K_ENUM);
-            k_enum_all<<<grid_for(ctx, c->n, 8), PCL_BLOCK, 0, c->stream>>>(p);
+            k_enum_all<<<grid_for(ctx, c->n, ctx->occ[OCC_ENUM]), PCL_BLOCK, 0, c->stream>>>(p);
             prof_end(ctx, c->stream);
             CU(ctx, cudaGetLastError());
         }
         // the worklist size lives on the device; size the grid for the worst case and let idle CTAs exit
-        const int grid = grid_for(ctx, check_ee ? c->n * inf.n_bc : (c->n * inf.n_bc + 3) / 4 + 4096, 8);
-        prof_begin(ctx, c->stream, PCL_K_CORRECT);
         bool all32 = !check_ee && !ctx->force_generic;
         for (int j = 0; j < inf.n_bc; ++j) {
             all32 = all32 && ctx->tables[ctx->bc_region[r][j]].d.mode != PCL_TAB_K64;
             all32 = all32 && inf.bc_key_bytes[j] == 4;
         }
+        // the worklist size lives on the device; size the grid for the worst case and let idle CTAs exit
+        const int grid = grid_for(ctx, check_ee ? c->n * inf.n_bc : (c->n * inf.n_bc + 3) / 4 + 4096,
+                                  ctx->occ[all32 ? OCC_CORRECT_FAST : OCC_CORRECT]);
+        prof_begin(ctx, c->stream, PCL_K_CORRECT);
         if (all32) k_correct<true><<<grid, PCL_BLOCK, 0, c->stream>>>(p);
         else k_correct<false><<<grid, PCL_BLOCK, 0, c->stream>>>(p);
         prof_end(ctx, c->stream);
@@ -690,7 +711,7 @@ int pcl_counts_fetch(pcl_ctx *ctx, int region_slot, uint64_t *counts, uint64_t *
         unsigned long long *d_out = nullptr;
         CU(ctx, cudaMalloc(&d_out, t.n_entries * sizeof(unsigned long long)));
         ctx->launches += 1;
-        k_gather_counts<<<grid_for(ctx, t.n_entries, 8), PCL_BLOCK, 0, ctx->stream>>>(t.d_counts, t.d_index_to_slot, d_out, t.n_entries);
+        k_gather_counts<<<grid_for(ctx, t.n_entries, ctx->occ[OCC_GATHER]), PCL_BLOCK, 0, ctx->stream>>>(t.d_counts, t.d_index_to_slot, d_out, t.n_entries);
         cudaError_t e = cudaMemcpyAsync(counts, d_out, t.n_entries * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream);
         if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
         cudaFree(d_out);
@@ -732,7 +753,7 @@ int pcl_qc_accumulate(pcl_ctx *ctx, pcl_chunk *c) {
         memcpy(p.static_start, inf.static_start, sizeof p.static_start);
         p.cat = ctx->d_qc + PCL_MAX_READS;
         prof_begin(ctx, c->stream, PCL_K_QC);
-        k_qc<<<grid_for(ctx, c->n, 8), PCL_BLOCK, 0, c->stream>>>(p);
+        k_qc<<<grid_for(ctx, c->n, ctx->occ[OCC_QC]), PCL_BLOCK, 0, c->stream>>>(p);
         prof_end(ctx, c->stream);
         CU(ctx, cudaGetLastError());
     }
