@@ -451,7 +451,11 @@ int pcl_chunk_create(pcl_ctx *ctx, uint64_t capacity_records, pcl_chunk **out) {
             if (!inf.fixed_layout) A((void **)&b.ucoord[j], cap * 4);
         }
         // misses + the unused tails of the per-warp reservations (largest grid: 3 waves of <= 8 CTAs per SM, 8 warps each)
-        if (inf.n_bc) A((void **)&b.worklist, (cap * inf.n_bc + (uint64_t)ctx->sm_count * 24 * (PCL_BLOCK / 32) * PCL_WL_BATCH * inf.n_bc) * 8);
+        if (inf.n_bc) {
+            uint64_t warps = (uint64_t)ctx->sm_count * 24 * (PCL_BLOCK / 32), by_size = (cap + 31) / 32 + PCL_BLOCK / 32;
+            if (warps > by_size) warps = by_size;             // a grid never has more warps than the chunk has records / 32
+            A((void **)&b.worklist, (cap + warps * PCL_WL_BATCH) * inf.n_bc * 8);
+        }
         A((void **)&b.wl_count, 16);
     }
     if (rc != PCL_OK) {
