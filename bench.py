@@ -34,7 +34,7 @@ N_WHITELIST = 6_800_000
 R2_LEN = 91
 THRESHOLD = 0.975          # make_fastq default (precellar/src/align/fastq.rs:39)
 # algorithmic bytes per read pair (SURVEY.md 8d / DESIGN.md): B = 108 + 1536 * f_mis, split per kernel launch
-B_COUNT_R1 = 58 + 32 + 10  # R1 seq+qual+len, one 32 B probe sector, fstatus+bc_key+umi_key
+B_COUNT_R1 = 58 + 32 + 10  # R1 seq+qual+len (SURVEY's figure; the kernel itself never reads qual), one probe sector, results
 B_COUNT_R2 = 2 + 6         # R2 len, fstatus+tcoord
 B_CORRECT_PER_MISS = 1536  # 3 * 16 neighbour probes * 32 B
 
@@ -278,7 +278,7 @@ def main():
     big.reset(n)
     s1, q1, l1 = big.device_ptrs(0)
     _, _, l2 = big.device_ptrs(1)
-    syn.fill_device(local_rank, first, n, s1, q1, l1, big.stream)
+    syn.fill_device(local_rank, first, n, s1, q1, l1, big.stream, qual_window=pipe.qual_window(0))
     syn.fill_u16_device(local_rank, l2, R2_LEN, n, big.stream)
     pipe.sync()
 
@@ -359,8 +359,9 @@ def main():
         nc = max(1, args.e2e_chunks)
         bounds = np.linspace(0, n, nc + 1).astype(np.int64)
         cap = int(np.max(np.diff(bounds)))
+        qo, qs = pipe.qual_window(0)             # the quality plane only covers the barcode bases (16 of 28 bytes)
         seq_h, _p1 = pinned(n * 32, np.uint8, (n, 32))
-        qual_h, _p2 = pinned(n * 32, np.uint8, (n, 32))
+        qual_h, _p2 = pinned(n * qs, np.uint8, (n, qs))
         len_h, _p3 = pinned(n * 2, np.uint16, (n,))
         len2_h, _p4 = pinned(n * 2, np.uint16, (n,))
         fs1_h, _p5 = pinned(n * 2, np.uint16, (n,))
@@ -370,7 +371,7 @@ def main():
         tc2_h, _p9 = pinned(n * 4, np.uint32, (n,))
         # same bytes as the resident shard: copy them out of the device planes (generator parity is tested separately)
         syn.memcpy_d2h(local_rank, seq_h.ctypes.data, s1, n * 32)
-        syn.memcpy_d2h(local_rank, qual_h.ctypes.data, q1, n * 32)
+        syn.memcpy_d2h(local_rank, qual_h.ctypes.data, q1, n * qs)
         syn.memcpy_d2h(local_rank, len_h.ctypes.data, l1, n * 2)
         syn.memcpy_d2h(local_rank, len2_h.ctypes.data, l2, n * 2)
         chunks = [pipe.new_chunk(cap) for _ in range(nc)]
@@ -381,7 +382,7 @@ def main():
             r1 = ReadResults(pipe.infos[0], fs1_h[lo:hi], None, [bck_h[lo:hi]], [umi_h[lo:hi]], [None], [None])
             r2 = ReadResults(pipe.infos[1], fs2_h[lo:hi], tc2_h[lo:hi], [], [], [], [])
             outs.append((r1, r2))
-        h2d = n * (32 + 32 + 2 + 2)
+        h2d = n * (32 + qs + 2 + 2)
         d2h = n * (2 + 4 + 4 + 2 + 4)
 
         def step_e2e():
@@ -419,17 +420,19 @@ def main():
         if rank == 0 and world == 1 and not args.no_cpu:
             ns = min(args.cpu_sample, n)
             # GPU results for exactly this sample (counts are global, so rerun the path on the sample alone)
+            seq_s, qual_s, len_s = syn.host_arrays(first, ns)          # same bytes as the device generator (tested)
+            len2_s = np.full(ns, R2_LEN, np.uint16)
             small = pipe.new_chunk(ns)
             pipe.reset_counts()
             small.reset(ns)
-            small.upload(0, HostBatch(seq_h[:ns], qual_h[:ns], len_h[:ns]))
-            small.upload(1, HostBatch(None, None, len2_h[:ns]))
+            small.upload(0, pipe.host_planes(0, seq_s, qual_s, len_s))
+            small.upload(1, HostBatch(None, None, len2_s))
             pipe.count(small)
             pipe.allreduce()
             pipe.correct(small, THRESHOLD)
             g1, g2 = small.fetch(0), small.fetch(1)
             gcnt, gmm, gtot = pipe.counts(0)
-            times, ores, ocounts = run_reference_sample(wl, seq_h[:ns], qual_h[:ns], len_h[:ns], len2_h[:ns], host_cores,
+            times, ores, ocounts = run_reference_sample(wl, seq_s, qual_s, len_s, len2_s, host_cores,
                                                         steps=1, warmup=0, want_outputs=True)
             cpu_v = ns / float(np.mean(times))
             from tools.v3check import compare_v3
@@ -457,7 +460,7 @@ def main():
             "config": {"workload": workload, "pairs_per_gpu": n, "whitelist": N_WHITELIST, "n_cells": 10000,
                        "f_mis": f_mis_global, "threshold": THRESHOLD, "parallelism": f"reads sharded over {world} GPU(s), "
                        "whitelist replicated, one NCCL allreduce of the counts",
-                       "l2": "inputs (8.3 GB per GPU) are far larger than L2; no flush needed"},
+                       "l2": "inputs (6.3 GB per GPU) are far larger than L2; no flush needed"},
             "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": int(launches),
             "clocks": clocks.summary(), "parity": parity, "host_cores": host_cores, "host_ingest": ingest,
         }

@@ -144,6 +144,8 @@ typedef struct {
     uint8_t umi_elem[PCL_MAX_UMI_PER_READ];      /* element index of each UMI element                 */
     uint8_t umi_key_bytes[PCL_MAX_UMI_PER_READ]; /* 4 or 8                                            */
     uint16_t static_start[PCL_MAX_ELEMS];  /* fixed_layout: start of every element                    */
+    uint16_t qual_offset;                  /* the quality plane holds record bytes [qual_offset,       */
+    uint16_t qual_stride;                  /*   qual_offset + qual_stride) of every record             */
 } pcl_read_info;
 
 /* Host-side views handed to pcl_chunk_fetch; any pointer may be NULL to skip that array.
@@ -193,7 +195,10 @@ int pcl_chunk_destroy(pcl_chunk *chunk);
 int pcl_chunk_reset(pcl_chunk *chunk, uint64_t n_records);
 /* Record slot size (multiple of 16) the ctx uses for this read's seq/qual planes. */
 uint32_t pcl_read_stride(const pcl_ctx *ctx, int read_slot);
-/* Asynchronous H2D of one read file's SoA planes: record i occupies [i*stride, i*stride+len[i]).
+/* Asynchronous H2D of one read file's SoA planes: record i occupies [i*stride, i*stride+len[i]) of seq.
+ * The quality plane only has to cover what the correction pass reads -- the barcode bases: row i holds the
+ * quality bytes [qual_offset, qual_offset + qual_stride) of record i (pcl_read_info; for v3 that is 16 of the 28
+ * bytes).  Variable layouts and QC mode use the whole record (qual_offset 0, qual_stride == stride).
  * seq/qual may be NULL when !needs_payload.  Host buffers should be pinned (pcl_host_alloc) and must
  * stay valid until the next blocking call on the chunk. */
 int pcl_chunk_upload(pcl_chunk *chunk, int read_slot, const uint8_t *seq, const uint8_t *qual, const uint16_t *len);
@@ -235,8 +240,9 @@ const char *pcl_fastq_error(const pcl_fastq *r);
  * BatchedFqReader compares across files).  text/off (optional) keep definition, sequence and quality of every
  * record: off[3i] .. off[3i+3] delimit them inside text; *text_used is advanced.  Returns the number of records
  * (0 at end of input) or a negative pcl_status (pcl_fastq_error has the message). */
-int64_t pcl_fastq_read(pcl_fastq *r, uint64_t max_records, uint32_t stride, uint8_t *seq, uint8_t *qual, uint16_t *len,
-                       uint64_t *name_hash, uint8_t *text, uint64_t text_cap, uint64_t *off, uint64_t *text_used);
+int64_t pcl_fastq_read(pcl_fastq *r, uint64_t max_records, uint32_t stride, uint32_t qual_offset, uint32_t qual_stride,
+                       uint8_t *seq, uint8_t *qual, uint16_t *len, uint64_t *name_hash, uint8_t *text, uint64_t text_cap,
+                       uint64_t *off, uint64_t *text_used);
 
 /* ---- pinned host memory ------------------------------------------------------------------- */
 void *pcl_host_alloc(uint64_t bytes);

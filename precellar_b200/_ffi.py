@@ -45,7 +45,7 @@ class ReadInfo(C.Structure):
                 ("needs_payload", C.c_uint8), ("qual_only", C.c_uint8), ("reserved", C.c_uint8 * 2),
                 ("bc_elem", C.c_uint8 * PCL_MAX_BC_PER_READ), ("bc_key_bytes", C.c_uint8 * PCL_MAX_BC_PER_READ),
                 ("umi_elem", C.c_uint8 * PCL_MAX_UMI_PER_READ), ("umi_key_bytes", C.c_uint8 * PCL_MAX_UMI_PER_READ),
-                ("static_start", C.c_uint16 * PCL_MAX_ELEMS)]
+                ("static_start", C.c_uint16 * PCL_MAX_ELEMS), ("qual_offset", C.c_uint16), ("qual_stride", C.c_uint16)]
 
 
 class ReadResults(C.Structure):
@@ -129,7 +129,7 @@ def lib() -> C.CDLL:
         "pcl_fastq_open": (i32, [C.POINTER(C.c_char_p), i32, C.POINTER(vp)]),
         "pcl_fastq_close": (None, [vp]),
         "pcl_fastq_error": (C.c_char_p, [vp]),
-        "pcl_fastq_read": (C.c_int64, [vp, u64, u32, vp, vp, vp, vp, vp, u64, vp, C.POINTER(u64)]),
+        "pcl_fastq_read": (C.c_int64, [vp, u64, u32, u32, u32, vp, vp, vp, vp, vp, u64, vp, C.POINTER(u64)]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)

@@ -149,7 +149,7 @@ class FastqProcessor:
         # pass 1 (BarcodeAnalyzer::new): every batch is uploaded, counted and kept resident on the device
         chunks: List[Chunk] = []
         sizes: List[int] = []
-        rdr = GroupReader(files, strides, qonly, keep_text=False)
+        rdr = GroupReader(files, strides, qonly, keep_text=False, qual_windows=[pipe.qual_window(r) for r in range(n_reads)])
         try:
             while True:
                 got = rdr.next(per_chunk)
@@ -176,7 +176,7 @@ class FastqProcessor:
         pipe.allreduce()
 
         # pass 2 (AnnotatedFastqReader): correct, fetch, and rebuild the records from a second read of the files
-        rdr = GroupReader(files, [0] * n_reads, [False] * n_reads, keep_text=True,
+        rdr = GroupReader(files, [0] * n_reads, [False] * n_reads, keep_text=True, qual_windows=[(0, 0)] * n_reads,
                           text_bytes=[2 * max(p.max_len, 1024) + 256 for p in layout.reads])
         try:
             for ch, n in zip(chunks, sizes):

@@ -60,6 +60,7 @@ struct DRead {
     uint32_t stride;     // bytes per record slot
     uint8_t n_bc, n_umi, has_target, needs_payload;
     uint8_t qual_only, pad0[3];   // QC mode: insert read that carries only a quality plane
+    uint32_t qoff, qstride;       // the quality plane holds record bytes [qoff, qoff + qstride) per record
     DElem elems[PCL_MAX_ELEMS];
     FastLayout fast;
 };

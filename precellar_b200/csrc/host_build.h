@@ -110,6 +110,21 @@ inline int pcl_build_read(int r, const pcl_read_desc &rd, DRead *out, pcl_read_i
         return pcl_build_fail(err, PCL_ERR_UNSUPPORTED, "read %d: %u payload bytes per record exceed %d", r, stride, PCL_MAX_STRIDE);
     if (start > 0xFFFF) return pcl_build_fail(err, PCL_ERR_UNSUPPORTED, "read %d: layout longer than 65535", r);
     d.stride = stride;
+    // quality window: only barcode bases are read by the correction pass
+    d.qoff = 0; d.qstride = stride;
+    if (!qc && fixed && info.n_bc >= 1) {
+        uint32_t lo = 0xFFFFFFFFu, hi = 0;
+        for (int j = 0; j < info.n_bc; ++j) {
+            const uint32_t s0 = info.static_start[info.bc_elem[j]], e0 = s0 + rd.elems[info.bc_elem[j]].max_len;
+            if (s0 < lo) lo = s0;
+            if (e0 > hi) hi = e0;
+        }
+        if (hi > stride) hi = stride;
+        if (lo < hi) { d.qoff = lo; d.qstride = ((hi - lo + 15u) / 16u) * 16u; }
+    }
+    if (!info.n_bc && !qc) d.qstride = 0;               // no barcode: the quality plane is never read
+    info.qual_offset = (uint16_t)d.qoff;
+    info.qual_stride = (uint16_t)d.qstride;
     d.qual_only = qual_only ? 1 : 0;
     info.qual_only = d.qual_only;
     d.fixed_layout = fixed ? 1 : 0;

@@ -109,8 +109,9 @@ const char *pcl_fastq_error(const pcl_fastq *r) { return r ? r->err.c_str() : ""
 //   text/off : optional arena keeping definition, sequence and quality of every record:
 //              off[3*i], off[3*i+1], off[3*i+2], off[3*i+3] delimit them; *text_used is updated.
 // Returns the number of records read (0 at end of input) or a negative pcl_status.
-int64_t pcl_fastq_read(pcl_fastq *r, uint64_t max_records, uint32_t stride, uint8_t *seq, uint8_t *qual, uint16_t *len,
-                       uint64_t *name_hash, uint8_t *text, uint64_t text_cap, uint64_t *off, uint64_t *text_used) {
+int64_t pcl_fastq_read(pcl_fastq *r, uint64_t max_records, uint32_t stride, uint32_t qual_offset, uint32_t qual_stride,
+                       uint8_t *seq, uint8_t *qual, uint16_t *len, uint64_t *name_hash, uint8_t *text, uint64_t text_cap,
+                       uint64_t *off, uint64_t *text_used) {
     if (!r || !len) return PCL_ERR_ARG;
     uint64_t n = 0, used = text_used ? *text_used : 0;
     if (off && n == 0) off[0] = used;
@@ -129,10 +130,16 @@ int64_t pcl_fastq_read(pcl_fastq *r, uint64_t max_records, uint32_t stride, uint
         len[n] = (uint16_t)(L > 65535 ? 65535 : L);
         if (seq && stride) {
             const size_t c = L < stride ? L : stride;
-            uint8_t *ds = seq + n * (uint64_t)stride, *dq = qual + n * (uint64_t)stride;
+            uint8_t *ds = seq + n * (uint64_t)stride;
             memcpy(ds, s.data(), c);
-            memcpy(dq, q.data(), c);
-            if (c < stride) { memset(ds + c, 'N', stride - c); memset(dq + c, '!', stride - c); }
+            if (c < stride) memset(ds + c, 'N', stride - c);
+        }
+        if (qual && qual_stride) {
+            const size_t avail = L > qual_offset ? L - qual_offset : 0;
+            const size_t c = avail < qual_stride ? avail : qual_stride;
+            uint8_t *dq = qual + n * (uint64_t)qual_stride;
+            if (c) memcpy(dq, q.data() + qual_offset, c);
+            if (c < qual_stride) memset(dq + c, '!', qual_stride - c);
         }
         if (name_hash) {
             size_t e = 1;

@@ -476,7 +476,7 @@ __global__ void __launch_bounds__(PCL_BLOCK) k_correct(const __grid_constant__ C
         const uint32_t start = (uint32_t)(ent >> 32) & 0xFFFFu, blen = (uint32_t)(ent >> 48) & 0xFFu,
                        j = (uint32_t)(ent >> 56);
         const uint8_t *rec = p.seq + rec_i * (uint64_t)rd.stride;
-        const uint8_t *ql = p.qual + rec_i * (uint64_t)rd.stride;
+        const uint8_t *ql = p.qual + rec_i * (uint64_t)rd.qstride - rd.qoff;     // record-relative indexing inside the window
         uint32_t ninv, ipos;
         const uint64_t key = pcl_pack_key(rec, start, blen, rev, &ninv, &ipos);
         uint32_t code;
@@ -551,7 +551,7 @@ __global__ void __launch_bounds__(PCL_BLOCK) k_qc(const __grid_constant__ QcPara
         if ((fs & 3u) != PCL_SPLIT_OK) continue;          // defect records contribute no segment (fastq.rs:369-374)
         uint32_t L = p.len[i];
         if (rd.max_len && L > rd.max_len) L = rd.max_len;
-        const uint8_t *row = p.qual + i * (uint64_t)rd.stride;
+        const uint8_t *row = p.qual + i * (uint64_t)rd.qstride;               // QC mode: qoff == 0, whole record
         for (uint32_t j = 0; j < rd.n_bc; ++j) {
             if (PCL_BC_CODE(fs, j) == PCL_BC_ABSENT) continue;
             const uint32_t c = rd.fixed_layout ? pcl_static_coord(rd, p.static_start, p.bc_elem[j], L) : p.bcoord[j][i];

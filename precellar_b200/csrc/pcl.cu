@@ -438,7 +438,7 @@ int pcl_chunk_create(pcl_ctx *ctx, uint64_t capacity_records, pcl_chunk **out) {
         const pcl_read_info &inf = ctx->infos[r];
         ReadBuf &b = c->rb[r];
         if (d.needs_payload) A((void **)&b.seq, cap * d.stride);
-        if (d.needs_payload || d.qual_only) A((void **)&b.qual, cap * d.stride);
+        if ((d.needs_payload || d.qual_only) && d.qstride) A((void **)&b.qual, cap * d.qstride);
         A((void **)&b.len, cap * 2 + 16);
         A((void **)&b.fstatus, cap * 2 + 16);
         if (inf.has_target) A((void **)&b.tcoord, cap * 4);
@@ -500,13 +500,13 @@ int pcl_chunk_upload(pcl_chunk *c, int read_slot, const uint8_t *seq, const uint
     const DRead &d = ctx->dreads[read_slot];
     ReadBuf &b = c->rb[read_slot];
     if (d.needs_payload) {
-        if (!seq || !qual) return fail(ctx, PCL_ERR_ARG, "read %d needs seq and qual planes", read_slot);
+        if (!seq || (!qual && d.qstride)) return fail(ctx, PCL_ERR_ARG, "read %d needs seq and qual planes", read_slot);
         CU(ctx, cudaMemcpyAsync(b.seq, seq, c->n * d.stride, cudaMemcpyHostToDevice, c->stream));
-        CU(ctx, cudaMemcpyAsync(b.qual, qual, c->n * d.stride, cudaMemcpyHostToDevice, c->stream));
+        if (d.qstride) CU(ctx, cudaMemcpyAsync(b.qual, qual, c->n * d.qstride, cudaMemcpyHostToDevice, c->stream));
     }
     if (d.qual_only) {
         if (!qual) return fail(ctx, PCL_ERR_ARG, "read %d needs its quality plane (FASTQ QC is enabled)", read_slot);
-        CU(ctx, cudaMemcpyAsync(b.qual, qual, c->n * d.stride, cudaMemcpyHostToDevice, c->stream));
+        CU(ctx, cudaMemcpyAsync(b.qual, qual, c->n * d.qstride, cudaMemcpyHostToDevice, c->stream));
     }
     CU(ctx, cudaMemcpyAsync(b.len, len, c->n * 2, cudaMemcpyHostToDevice, c->stream));
     b.filled = true;

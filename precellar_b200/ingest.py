@@ -46,10 +46,11 @@ class FastqReader:
         self.paths = list(paths)
 
     def read(self, max_records: int, stride: int, keep_text: bool = False, text_bytes_per_record: int = 512,
-             qual_only: bool = False) -> Optional[FastqBatch]:
+             qual_only: bool = False, qual_window=None) -> Optional[FastqBatch]:
         n = int(max_records)
-        seq = np.empty((n, stride), np.uint8) if stride else None
-        qual = np.empty((n, stride), np.uint8) if stride else None
+        qoff, qstride = qual_window if qual_window is not None else (0, stride)
+        seq = np.empty((n, stride), np.uint8) if (stride and not qual_only) else None
+        qual = np.empty((n, qstride), np.uint8) if qstride else None
         length = np.empty(n, np.uint16)
         nh = np.empty(n, np.uint64)
         text = off = None
@@ -57,8 +58,8 @@ class FastqReader:
         if keep_text:
             text = np.empty(n * text_bytes_per_record, np.uint8)
             off = np.zeros(3 * n + 1, np.uint64)
-        got = lib().pcl_fastq_read(self.h, n, stride, seq.ctypes.data if stride else None,
-                                   qual.ctypes.data if stride else None, length.ctypes.data, nh.ctypes.data,
+        got = lib().pcl_fastq_read(self.h, n, stride, qoff, qstride, seq.ctypes.data if seq is not None else None,
+                                   qual.ctypes.data if qual is not None else None, length.ctypes.data, nh.ctypes.data,
                                    text.ctypes.data if keep_text else None, len(text) if keep_text else 0,
                                    off.ctypes.data if keep_text else None, C.byref(used))
         if got < 0:
@@ -66,7 +67,7 @@ class FastqReader:
         if got == 0:
             return None
         g = int(got)
-        hb = HostBatch(None if (seq is None or qual_only) else seq[:g], None if qual is None else qual[:g], length[:g])
+        hb = HostBatch(None if seq is None else seq[:g], None if qual is None else qual[:g], length[:g])
         return FastqBatch(hb, nh[:g], text[:used.value] if keep_text else None, off[:3 * g + 1] if keep_text else None)
 
     def close(self):
@@ -86,17 +87,18 @@ class GroupReader:
     equal names (after stripping /1 /2) across the files are enforced."""
 
     def __init__(self, files_per_read: Sequence[Sequence[str]], strides: Sequence[int], qual_only: Sequence[bool],
-                 keep_text: bool = False, text_bytes: Optional[Sequence[int]] = None):
+                 keep_text: bool = False, text_bytes: Optional[Sequence[int]] = None, qual_windows=None):
         self.readers = [FastqReader(f) for f in files_per_read]
         self.strides = list(strides)
         self.qual_only = list(qual_only)
         self.keep_text = keep_text
+        self.qual_windows = list(qual_windows) if qual_windows is not None else [(0, st) for st in self.strides]
         self.text_bytes = list(text_bytes) if text_bytes is not None else [2304] * len(self.readers)
         self.pool = ThreadPoolExecutor(max_workers=max(1, len(self.readers)))
 
     def next(self, max_records: int) -> Optional[List[FastqBatch]]:
-        futs = [self.pool.submit(r.read, max_records, st, self.keep_text, tb, qo)
-                for r, st, qo, tb in zip(self.readers, self.strides, self.qual_only, self.text_bytes)]
+        futs = [self.pool.submit(r.read, max_records, st, self.keep_text, tb, qo, qw)
+                for r, st, qo, tb, qw in zip(self.readers, self.strides, self.qual_only, self.text_bytes, self.qual_windows)]
         out = [f.result() for f in futs]
         if all(b is None for b in out):
             return None

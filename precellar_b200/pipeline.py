@@ -64,9 +64,11 @@ class Chunk:
             assert batch.seq is not None and batch.qual is not None
             assert batch.seq.dtype == np.uint8 and batch.seq.shape == (self.n, stride) and batch.seq.flags.c_contiguous
             sp = batch.seq.ctypes.data
-        if info.needs_payload or info.qual_only:
+        if (info.needs_payload or info.qual_only) and info.qual_stride:
+            # the quality plane covers record bytes [qual_offset, qual_offset + qual_stride) only (the barcode bases)
             assert batch.qual is not None, "this read needs its quality plane"
-            assert batch.qual.dtype == np.uint8 and batch.qual.shape == (self.n, stride) and batch.qual.flags.c_contiguous
+            assert batch.qual.dtype == np.uint8 and batch.qual.shape == (self.n, info.qual_stride) and batch.qual.flags.c_contiguous, \
+                f"quality plane must be [n, {info.qual_stride}] (record bytes from {info.qual_offset})"
             qp = batch.qual.ctypes.data
         self._keep.append((batch, length))
         check(self.pipe.ctx, lib().pcl_chunk_upload(self.h, read_slot, sp, qp, length.ctypes.data))
@@ -187,6 +189,28 @@ class BarcodePipeline:
 
     def stride(self, read_slot: int) -> int:
         return lib().pcl_read_stride(self.ctx, read_slot)
+
+    def qual_window(self, read_slot: int):
+        """(offset, stride) of the quality plane: row i = quality bytes [offset, offset + stride) of record i."""
+        info = self.infos[read_slot]
+        return int(info.qual_offset), int(info.qual_stride)
+
+    def host_planes(self, read_slot: int, seq_full: np.ndarray, qual_full: np.ndarray, length: np.ndarray) -> "HostBatch":
+        """Cut full-width [n, W] sequence / quality arrays down to the planes this read uploads."""
+        info = self.infos[read_slot]
+        st, (qo, qs) = self.stride(read_slot), self.qual_window(read_slot)
+
+        def cut(a, lo, w, fill):
+            if a is None or w == 0:
+                return None
+            out = np.full((a.shape[0], w), fill, np.uint8)
+            hi = min(a.shape[1], lo + w)
+            if hi > lo:
+                out[:, :hi - lo] = a[:, lo:hi]
+            return out
+        seq = cut(seq_full, 0, st, ord("N")) if info.needs_payload else None
+        qual = cut(qual_full, qo, qs, ord("!")) if (info.needs_payload or info.qual_only) else None
+        return HostBatch(seq, qual, length)
 
     def whitelist_size(self, slot: int) -> int:
         return lib().pcl_whitelist_size(self.ctx, slot)

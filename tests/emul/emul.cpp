@@ -234,7 +234,7 @@ int emu_run(const pcl_read_desc *reads, int n_reads, int n_regions, const uint8_
             for (uint32_t j = 0; j < rd.n_bc; ++j) all32 = all32 && dt[bcr[r][j]].mode != PCL_TAB_K64 && in.bc_key_bytes[j] == 4;
             for (const Work &w : work[r]) {
                 const uint8_t *rec = io[r].seq + w.rec * (uint64_t)rd.stride;
-                const uint8_t *ql = io[r].qual + w.rec * (uint64_t)rd.stride;
+                const uint8_t *ql = io[r].qual + w.rec * (uint64_t)rd.qstride - rd.qoff;
                 uint32_t ninv, ipos;
                 uint64_t key = pcl_pack_key(rec, w.start, w.len, rev, &ninv, &ipos);
                 bool is_exact = PCL_BC_CODE((uint32_t)io[r].fstatus[w.rec], w.j) == PCL_BC_EXACT;

@@ -34,7 +34,7 @@ for name in ("v3", "sci3", "atac"):
     full = U.gen_reads(rng, layout, n, strides, p_short=0.0 if multi else 0.03, p_tiny=0.03 if multi else 0.0)
     lo, hi = shard_bounds(n, world)[rank]
     mine = [HostBatch(b.seq[lo:hi], b.qual[lo:hi], b.length[lo:hi]) for b in full]
-    dev = U.narrow(mine, strides)
+    dev = U.narrow(mine, strides, infos)
     # pass 1 on the shard, then ONE sum over ranks of counts (+ mismatch/total), as pcl_counts_allreduce does
     _, _, counts, defects = U.run_emul(layout, dev, correct=False)
     gcounts = {}

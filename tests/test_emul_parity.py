@@ -101,7 +101,7 @@ def test_emul_matches_oracle(layouts, name, mode):
     multi = len(layout.region_ids) > 1
     full = U.gen_reads(rng, layout, n, strides, p_lower=0.02 if mode == "lower" else 0.0,
                        p_short=0.0 if multi else 0.03, p_tiny=0.03 if multi else 0.0)
-    dev = U.narrow(full, strides)
+    dev = U.narrow(full, strides, infos)
     kw = dict(correct=mode != "nocorrect", threshold=0.975 if mode != "lower" else 0.6,
               max_expected_errors=1.5 if mode == "ee" else _ffi.F64_MAX)
     infos, results, counts, defects = U.run_emul(layout, dev, use_fast=use_fast, **kw)
@@ -140,7 +140,7 @@ def test_reference_vectors_through_device_split():
         sq = np.full((1, w), ord("N"), np.uint8); sq[0, :len(seq)] = np.frombuffer(seq, np.uint8)
         ql = np.full((1, w), ord("@"), np.uint8)
         full = [U.HostBatch(sq, ql, np.array([len(seq)], np.uint16))]
-        infos, results, counts, defects = U.run_emul(layout, U.narrow(full, strides))
+        infos, results, counts, defects = U.run_emul(layout, U.narrow(full, strides, infos))
         ores, ocounts = U.run_oracle(layout, full)
         U.compare_with_oracle(layout, infos, full, results, counts, defects, ores, ocounts)
         # and the segments named in the expected string are where the device says they are

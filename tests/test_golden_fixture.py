@@ -40,7 +40,7 @@ def test_oracle_reproduces_fixture(golden, name):
 def test_device_functions_reproduce_fixture(golden, name):
     c = golden[name]
     infos, strides = U.emul_infos(c["layout"])
-    infos, results, counts, _ = U.run_emul(c["layout"], U.narrow(c["full"], strides), correct=True, threshold=0.975)
+    infos, results, counts, _ = U.run_emul(c["layout"], U.narrow(c["full"], strides, infos), correct=True, threshold=0.975)
     check(c["layout"], infos, c["full"], results, counts, c)
 
 
@@ -50,6 +50,6 @@ def test_cuda_path_reproduces_fixture(golden, name):
     from tests.test_gpu_parity import run_gpu
     c = golden[name]
     infos, strides = U.emul_infos(c["layout"])
-    ginfos, results, counts, defects, _ = run_gpu(c["layout"], U.narrow(c["full"], strides), correct=True, threshold=0.975)
+    ginfos, results, counts, defects, _ = run_gpu(c["layout"], U.narrow(c["full"], strides, infos), correct=True, threshold=0.975)
     check(c["layout"], ginfos, c["full"], results, counts, c)
     np.testing.assert_array_equal(defects, c["qc_per_file"][:, 1])

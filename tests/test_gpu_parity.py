@@ -70,7 +70,7 @@ def test_gpu_matches_oracle(layouts, name, mode, monkeypatch):
     multi = len(layout.region_ids) > 1
     full = U.gen_reads(rng, layout, n, strides, p_lower=0.02 if mode == "lower" else 0.0,
                        p_short=0.0 if multi else 0.03, p_tiny=0.03 if multi else 0.0)
-    dev = U.narrow(full, strides)
+    dev = U.narrow(full, strides, infos)
     kw = dict(correct=mode != "nocorrect", threshold=0.975 if mode != "lower" else 0.6,
               max_expected_errors=1.5 if mode == "ee" else _ffi.F64_MAX)
     ginfos, results, counts, defects, nreads = run_gpu(layout, dev, n_chunks=3 if mode == "correct" else 1, **kw)
@@ -87,7 +87,7 @@ def test_empty_and_single_record(layouts):
     rng = np.random.default_rng(5)
     for n in (1, 31, 33):
         full = U.gen_reads(rng, layout, n, strides)
-        ginfos, results, counts, defects, _ = run_gpu(layout, U.narrow(full, strides))
+        ginfos, results, counts, defects, _ = run_gpu(layout, U.narrow(full, strides, infos))
         ores, ocounts = U.run_oracle(layout, full)
         U.compare_with_oracle(layout, ginfos, full, results, counts, defects, ores, ocounts)
 
@@ -114,14 +114,16 @@ def test_synth_host_and_device_generate_the_same_bytes():
         ch = pipe.new_chunk(n)
         ch.reset(n)
         s1, q1, l1 = ch.device_ptrs(0)
-        syn.fill_device(0, 1234, n, s1, q1, l1, ch.stream)
+        syn.fill_device(0, 1234, n, s1, q1, l1, ch.stream, qual_window=pipe.qual_window(0))
         pipe.sync()
-        seq_d, qual_d, len_d = np.empty((n, 32), np.uint8), np.empty((n, 32), np.uint8), np.empty(n, np.uint16)
+        qo, qs = pipe.qual_window(0)
+        assert (qo, qs) == (0, 16)                    # v3: only the 16 barcode qualities are uploaded
+        seq_d, qual_d, len_d = np.empty((n, 32), np.uint8), np.empty((n, qs), np.uint8), np.empty(n, np.uint16)
         syn.memcpy_d2h(0, seq_d.ctypes.data, s1, n * 32)
-        syn.memcpy_d2h(0, qual_d.ctypes.data, q1, n * 32)
+        syn.memcpy_d2h(0, qual_d.ctypes.data, q1, n * qs)
         syn.memcpy_d2h(0, len_d.ctypes.data, l1, n * 2)
         seq_h, qual_h, len_h = syn.host_arrays(1234, n)
-        assert np.array_equal(seq_d, seq_h) and np.array_equal(qual_d, qual_h) and np.array_equal(len_d, len_h)
+        assert np.array_equal(seq_d, seq_h) and np.array_equal(qual_d, qual_h[:, qo:qo + qs]) and np.array_equal(len_d, len_h)
     finally:
         pipe.close()
 
@@ -143,7 +145,7 @@ def test_v3_full_size_2p5M_pairs_6p8M_whitelist():
     layout = v3_layout(wl, 91)
     pipe = BarcodePipeline(layout)
     try:
-        g1, g2 = pipe.run([HostBatch(seq, qual, length), HostBatch(None, None, len2)], correct=True, threshold=0.975)
+        g1, g2 = pipe.run([pipe.host_planes(0, seq, qual, length), HostBatch(None, None, len2)], correct=True, threshold=0.975)
         gcounts = pipe.counts(0)
     finally:
         pipe.close()
@@ -179,14 +181,10 @@ def test_qc_fastq_counters(layouts, name):
         n = 2500
         full = U.gen_reads(rng, layout, n, strides, p_short=0.0 if multi else 0.03, p_tiny=0.03 if multi else 0.0,
                            read_len=[p.max_len for p in layout.reads])
-        dev = U.narrow(full, strides)
         ch = pipe.new_chunk(n)
         ch.reset(n)
-        for r, b in enumerate(dev):
-            if pipe.infos[r].qual_only:
-                b = HostBatch(None, np.ascontiguousarray(full[r].qual[:, :strides[r]]) if full[r].qual.shape[1] >= strides[r]
-                              else np.pad(full[r].qual, ((0, 0), (0, strides[r] - full[r].qual.shape[1])), constant_values=33), b.length)
-            ch.upload(r, b)
+        for r in range(len(layout.reads)):
+            ch.upload(r, pipe.host_planes(r, full[r].seq, full[r].qual, full[r].length))
         pipe.count(ch)
         pipe.qc_accumulate(ch)
         cat = pipe.qc_categories()
@@ -206,7 +204,8 @@ def _bulk(layout, batches, n_threads=16, **kw):
     from tools.v3check import compare_bulk
     pipe = BarcodePipeline(layout)
     try:
-        results = pipe.run(batches, correct=True, threshold=kw.get("threshold", 0.975))
+        dev = [pipe.host_planes(r, b.seq, b.qual, b.length) if b.seq is not None else b for r, b in enumerate(batches)]
+        results = pipe.run(dev, correct=True, threshold=kw.get("threshold", 0.975))
         counts = {g: pipe.counts(g) for g in range(len(layout.region_ids))}
         infos = pipe.infos
         qc = pipe.qc()

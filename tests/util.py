@@ -145,22 +145,24 @@ def gen_reads(rng: np.random.Generator, layout: CompiledLayout, n: int, stride_o
     return batches
 
 
-def narrow(batches: Sequence[HostBatch], strides: Sequence[int]) -> List[HostBatch]:
-    """The planes the device consumes: the first `stride` bytes of every record (None when stride == 0)."""
+def narrow(batches: Sequence[HostBatch], strides: Sequence[int], infos=None) -> List[HostBatch]:
+    """The planes the device consumes: the first `stride` sequence bytes of every record and the quality
+    window [qual_offset, qual_offset + qual_stride) given by pcl_read_info (None where a plane is not used)."""
+    if infos is None:
+        raise TypeError("narrow() needs the pcl_read_info list (quality windows)")
     out = []
-    for b, st in zip(batches, strides):
-        if st == 0:
-            out.append(HostBatch(None, None, b.length))
-        else:
-            w = b.seq.shape[1]
-            if w >= st:
-                out.append(HostBatch(np.ascontiguousarray(b.seq[:, :st]), np.ascontiguousarray(b.qual[:, :st]), b.length))
-            else:
-                sq = np.full((len(b.length), st), ord("N"), np.uint8)
-                ql = np.full((len(b.length), st), ord("!"), np.uint8)
-                sq[:, :w] = b.seq
-                ql[:, :w] = b.qual
-                out.append(HostBatch(sq, ql, b.length))
+    for b, st, info in zip(batches, strides, infos):
+        def cut(a, lo, w, fill):
+            if a is None or w == 0:
+                return None
+            o = np.full((a.shape[0], w), fill, np.uint8)
+            hi = min(a.shape[1], lo + w)
+            if hi > lo:
+                o[:, :hi - lo] = a[:, lo:hi]
+            return o
+        seq = cut(b.seq, 0, st, ord("N")) if info.needs_payload else None
+        qual = cut(b.qual, int(info.qual_offset), int(info.qual_stride), ord("!")) if (info.needs_payload or info.qual_only) else None
+        out.append(HostBatch(seq, qual, b.length))
     return out
 
 
@@ -232,8 +234,11 @@ def run_emul(layout: CompiledLayout, batches: Sequence[HostBatch], correct=True,
         ln = np.ascontiguousarray(b.length, np.uint16)
         keep.append(ln)
         if infos[r].needs_payload:
-            assert b.seq is not None and b.seq.shape[1] == strides[r], "pass narrow(batches, strides)"
-            io[r].seq, io[r].qual = b.seq.ctypes.data, b.qual.ctypes.data
+            assert b.seq is not None and b.seq.shape[1] == strides[r], "pass narrow(batches, strides, infos)"
+            io[r].seq = b.seq.ctypes.data
+            if b.qual is not None:
+                assert b.qual.shape[1] == infos[r].qual_stride
+                io[r].qual = b.qual.ctypes.data
         io[r].len = ln.ctypes.data
         io[r].fstatus = res.fstatus.ctypes.data
         if res.tcoord is not None:

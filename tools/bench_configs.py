@@ -68,7 +68,7 @@ def main():
 
         def fill(pipe, ch):
             s, q, l = ch.device_ptrs(1)
-            syn.fill_device(0, 0, n, s, q, l, ch.stream)
+            syn.fill_device(0, 0, n, s, q, l, ch.stream, qual_window=pipe.qual_window(1))
             fill_len(pipe, ch, 0, 50)
             fill_len(pipe, ch, 2, 50)
         run("10x_atac (I2 16nt neg strand, 737K whitelist, read triples)", configs.atac_layout(wl, 50), fill, n, a.steps)
@@ -78,7 +78,7 @@ def main():
 
         def fill(pipe, ch):
             s, q, l = ch.device_ptrs(1)
-            syn.fill_device(0, 0, n, s, q, l, ch.stream)
+            syn.fill_device(0, 0, n, s, q, l, ch.stream, qual_window=pipe.qual_window(1))
             fill_len(pipe, ch, 0, 50)
             fill_len(pipe, ch, 2, 50)
         run("10x_multiome ATAC side (I2 = linker8 + 16nt neg strand)", configs.multiome_atac_layout(wl, 50), fill, n, a.steps)

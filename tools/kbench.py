@@ -11,7 +11,7 @@ syn = S.Synth(S.SynthSpec(6_800_000), wl)
 pipe = BarcodePipeline(configs.v3_layout(wl, 91))
 ch = pipe.new_chunk(n); ch.reset(n)
 s, q, l = ch.device_ptrs(0); _, _, l2 = ch.device_ptrs(1)
-syn.fill_device(0, 0, n, s, q, l, ch.stream); syn.fill_u16_device(0, l2, 91, n, ch.stream); pipe.sync()
+syn.fill_device(0, 0, n, s, q, l, ch.stream, qual_window=pipe.qual_window(0)); syn.fill_u16_device(0, l2, 91, n, ch.stream); pipe.sync()
 def step():
     pipe.reset_counts(); pipe.count(ch); pipe.allreduce(); pipe.correct(ch, 0.975)
 for _ in range(3): step()

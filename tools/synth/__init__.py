@@ -45,7 +45,8 @@ def lib():
         L.synth_create.argtypes = [C.POINTER(_Params), C.c_void_p, C.c_void_p, C.c_void_p]
         L.synth_destroy.argtypes = [C.c_void_p]
         L.synth_fill_host.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
-        L.synth_fill_device.argtypes = [C.c_void_p, C.c_int, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.synth_fill_device.argtypes = [C.c_void_p, C.c_int, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                        C.c_uint32, C.c_uint32]
         L.synth_fill_u16_device.argtypes = [C.c_int, C.c_void_p, C.c_uint16, C.c_uint64, C.c_void_p]
         L.synth_memcpy_d2h.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_uint64]
         L.synth3_create.restype = C.c_void_p
@@ -130,8 +131,11 @@ class Synth:
         self.fill_host(first, n, seq, qual, length, n_threads)
         return seq, qual, length
 
-    def fill_device(self, device: int, first: int, n: int, seq_ptr: int, qual_ptr: int, len_ptr: int, stream: int = 0):
-        rc = lib().synth_fill_device(self.h, device, first, n, seq_ptr, qual_ptr, len_ptr, stream)
+    def fill_device(self, device: int, first: int, n: int, seq_ptr: int, qual_ptr: int, len_ptr: int, stream: int = 0,
+                    qual_window=None):
+        """qual_window = (offset, stride) of the device quality plane (BarcodePipeline.qual_window)."""
+        qoff, qstride = qual_window if qual_window is not None else (0, self.spec.stride)
+        rc = lib().synth_fill_device(self.h, device, first, n, seq_ptr, qual_ptr, len_ptr, stream, qoff, qstride)
         if rc:
             raise RuntimeError(f"synth_fill_device: cudaError {rc}")
 

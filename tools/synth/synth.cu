@@ -61,8 +61,9 @@ HD void qual_and_error(uint64_t r, uint8_t *q, bool *sub, bool *to_n, uint32_t *
 
 HD uint8_t comp_base(uint8_t b) { return b == 'A' ? 'T' : b == 'C' ? 'G' : b == 'G' ? 'C' : b == 'T' ? 'A' : b; }
 
+// qual receives the quality bytes [qoff, qoff + qstride) of the record (the plane layout of pcl_chunk_upload)
 HD void synth_record(const synth_params &p, const uint8_t *wl, const uint32_t *cells, const uint64_t *zipf_thr, uint64_t i,
-                     uint8_t *seq, uint8_t *qual) {
+                     uint8_t *seq, uint8_t *qual, uint32_t qoff, uint32_t qstride) {
     const char ACGT[4] = {'A', 'C', 'G', 'T'};
     // which barcode
     const uint64_t r0 = rnd(p.seed, i, 0);
@@ -97,15 +98,19 @@ HD void synth_record(const synth_params &p, const uint8_t *wl, const uint32_t *c
             base = (uint8_t)ACGT[(c + shift) & 3u];
         }
         seq[k] = base;
-        qual[k] = q;
+        if (k >= qoff && k - qoff < qstride) qual[k - qoff] = q;
     }
-    for (uint32_t k = total; k < p.stride; ++k) { seq[k] = 'N'; qual[k] = '!'; }
+    for (uint32_t k = total; k < p.stride; ++k) {
+        seq[k] = 'N';
+        if (k >= qoff && k - qoff < qstride) qual[k - qoff] = '!';
+    }
+    for (uint32_t k = p.stride > qoff ? p.stride - qoff : 0; k < qstride; ++k) qual[k] = '!';
 }
 
 __global__ void k_synth(synth_params p, const uint8_t *wl, const uint32_t *cells, const uint64_t *zipf_thr, uint64_t first,
-                        uint64_t n, uint8_t *seq, uint8_t *qual, uint16_t *len) {
+                        uint64_t n, uint8_t *seq, uint8_t *qual, uint16_t *len, uint32_t qoff, uint32_t qstride) {
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
-        synth_record(p, wl, cells, zipf_thr, first + i, seq + i * p.stride, qual + i * p.stride);
+        synth_record(p, wl, cells, zipf_thr, first + i, seq + i * p.stride, qual + i * (uint64_t)qstride, qoff, qstride);
         len[i] = (uint16_t)(p.prefix_len + p.bc_len + p.umi_len);
     }
 }
@@ -205,7 +210,8 @@ int synth_fill_host(synth_t *s, uint64_t first, uint64_t n, uint8_t *seq, uint8_
     auto work = [&](int t) {
         uint64_t lo = n * t / n_threads, hi = n * (t + 1) / n_threads;
         for (uint64_t i = lo; i < hi; ++i) {
-            synth_record(s->p, s->wl.data(), s->cells.data(), s->thr.data(), first + i, seq + i * s->p.stride, qual + i * s->p.stride);
+            synth_record(s->p, s->wl.data(), s->cells.data(), s->thr.data(), first + i, seq + i * s->p.stride, qual + i * s->p.stride,
+                         0, s->p.stride);
             len[i] = (uint16_t)(s->p.prefix_len + s->p.bc_len + s->p.umi_len);
         }
     };
@@ -217,7 +223,8 @@ int synth_fill_host(synth_t *s, uint64_t first, uint64_t n, uint8_t *seq, uint8_
 }
 
 // device pointers; stream is a cudaStream_t.  Returns 0 or a cudaError_t.
-int synth_fill_device(synth_t *s, int device, uint64_t first, uint64_t n, void *seq, void *qual, void *len, void *stream) {
+int synth_fill_device(synth_t *s, int device, uint64_t first, uint64_t n, void *seq, void *qual, void *len, void *stream,
+                      uint32_t qoff, uint32_t qstride) {
     cudaError_t e = cudaSetDevice(device);
     if (e != cudaSuccess) return (int)e;
     if (!s->d_wl) {
@@ -232,7 +239,7 @@ int synth_fill_device(synth_t *s, int device, uint64_t first, uint64_t n, void *
     uint64_t blocks = (n + 255) / 256;
     if (blocks > 148 * 16) blocks = 148 * 16;
     k_synth<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(s->p, s->d_wl, s->d_cells, s->d_thr, first, n, (uint8_t *)seq,
-                                                               (uint8_t *)qual, (uint16_t *)len);
+                                                               (uint8_t *)qual, (uint16_t *)len, qoff, qstride);
     return (int)cudaGetLastError();
 }
 
