@@ -61,7 +61,7 @@ class Chunk:
         sp = qp = None
         info = self.pipe.infos[read_slot]
         if info.needs_payload:
-            assert batch.seq is not None and batch.qual is not None
+            assert batch.seq is not None, "this read needs its sequence plane"
             assert batch.seq.dtype == np.uint8 and batch.seq.shape == (self.n, stride) and batch.seq.flags.c_contiguous
             sp = batch.seq.ctypes.data
         if (info.needs_payload or info.qual_only) and info.qual_stride:
