@@ -144,7 +144,9 @@ class FastqProcessor:
         qonly = [bool(pipe.infos[r].qual_only) for r in range(n_reads)]
         files = [p.files for p in layout.reads]
         bases = sum((p.max_len or 100) for p in layout.reads)
-        per_chunk = max(1024, int(chunk_size) // max(bases, 1))
+        # the reference batches >= chunk_size bases (fastq.rs:406-445); results do not depend on the batching, so the
+        # device chunks are at least 256 K read groups to keep launches and allocations few
+        per_chunk = max(262144, int(chunk_size) // max(bases, 1))
 
         # pass 1 (BarcodeAnalyzer::new): every batch is uploaded, counted and kept resident on the device
         chunks: List[Chunk] = []
