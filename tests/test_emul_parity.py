@@ -182,3 +182,45 @@ def test_fast_path_selection(layouts):
     assert sel("sci3") == [0, 2]
     assert sel("k64_rev") == [0, 0]
     assert sel("share") == [2, 0]
+
+
+def _dense_layouts(rng):
+    """Whitelists that stress the tables: every 6-mer (all buckets overflow, neighbourhood chains are long), 15- and
+    16-mers (marker vs marker-less 32-bit keys), a 15/16 mix (64-bit table), 31-mers (longest packable barcode)."""
+    import itertools
+    out = {}
+    all6 = [bytes(p) for p in itertools.product(b"ACGT", repeat=6)]
+    rng.shuffle(all6)
+    out["all6"] = make_layout([dict(read_id="R1", elems=[bc("cb", 6), umi(4)], max_len=10)], {"cb": all6[:4000]})
+    out["len15"] = make_layout([dict(read_id="R1", elems=[bc("cb", 15), umi(5)], max_len=20)], {"cb": U.gen_whitelist(rng, 500, 15)})
+    out["mix15_16"] = make_layout([dict(read_id="R1", elems=[bc("cb", 15, 16)], max_len=16)],
+                                  {"cb": U.gen_whitelist(rng, 300, 15) + U.gen_whitelist(rng, 300, 16)})
+    out["len31"] = make_layout([dict(read_id="R1", elems=[bc("cb", 31), umi(9)], max_len=40)], {"cb": U.gen_whitelist(rng, 300, 31)})
+    # near-duplicate whitelist: many entries within Hamming distance 1 of each other -> several candidates per barcode
+    base = U.gen_whitelist(rng, 40, 16)
+    near = []
+    for b in base:
+        near.append(b)
+        for pos in (0, 7, 15):
+            for c in b"ACGT":
+                v = bytearray(b); v[pos] = c
+                near.append(bytes(v))
+    out["near_dups"] = make_layout([dict(read_id="R1", elems=[bc("cb", 16), umi(12)], max_len=28)], {"cb": near})
+    return out
+
+
+@pytest.mark.parametrize("name", ["all6", "len15", "mix15_16", "len31", "near_dups"])
+@pytest.mark.parametrize("use_fast", [0, 1, 2])
+def test_emul_dense_and_boundary_whitelists(name, use_fast):
+    layout = _dense_layouts(np.random.default_rng(77))[name]
+    rng = np.random.default_rng(abs(hash((name, "dense"))) % (2 ** 31))
+    infos, strides = U.emul_infos(layout)
+    full = U.gen_reads(rng, layout, 1500, strides, p_sub=0.05, p_n=0.02, hot=10 ** 6)
+    dev = U.narrow(full, strides, infos)
+    infos, results, counts, defects = U.run_emul(layout, dev, threshold=0.6, use_fast=use_fast)
+    ores, ocounts = U.run_oracle(layout, full, threshold=0.6)
+    g = U.compare_with_oracle(layout, infos, full, results, counts, defects, ores, ocounts)
+    codes = g.bc[0]["code"]
+    assert (codes == _ffi.BC_CORRECTED).any() and (codes == _ffi.BC_EXACT).any()
+    if name in ("near_dups", "all6"):
+        assert (codes == _ffi.BC_LOW_CONF).any()          # several neighbours share the posterior

@@ -277,3 +277,50 @@ def test_sci3_config_variable_hairpin_and_anchor():
     assert sum(fields.values()) == 0, fields
     assert (ores.fstatus[0] != 0).sum() > 1000          # PatternMismatch records exist and agree
     assert (ores.bc_index[0] >= 0).mean() > 0.8 and (ores.bc_index[1] >= 0).mean() > 0.8
+
+
+@pytest.mark.parametrize("name", ["all6", "len15", "mix15_16", "len31", "near_dups"])
+@pytest.mark.parametrize("direct", [False, True])
+def test_gpu_dense_and_boundary_whitelists(name, direct, monkeypatch):
+    from tests.test_emul_parity import _dense_layouts
+    monkeypatch.setenv("PCL_FORCE_GENERIC", "0")
+    monkeypatch.setenv("PCL_NO_NEIGHBOUR_TABLES", "1" if direct else "0")
+    layout = _dense_layouts(np.random.default_rng(77))[name]
+    rng = np.random.default_rng(abs(hash((name, "dense-gpu"))) % (2 ** 31))
+    infos, strides = U.emul_infos(layout)
+    full = U.gen_reads(rng, layout, 6000, strides, p_sub=0.05, p_n=0.02, hot=10 ** 6)
+    ginfos, results, counts, defects, _ = run_gpu(layout, U.narrow(full, strides, infos), threshold=0.6, n_chunks=2)
+    ores, ocounts = U.run_oracle(layout, full, threshold=0.6)
+    U.compare_with_oracle(layout, ginfos, full, results, counts, defects, ores, ocounts)
+
+
+def test_empty_chunk_and_reuse():
+    """n = 0 chunks are legal; a chunk can be refilled (pcl_chunk_reset) with a different record count."""
+    from precellar_b200.configs import v3_layout
+    from precellar_b200.pipeline import BarcodePipeline, HostBatch
+    rng = np.random.default_rng(3)
+    wl = U.gen_whitelist(rng, 500, 16)
+    layout = v3_layout(wl, 91)
+    pipe = BarcodePipeline(layout)
+    try:
+        ch = pipe.new_chunk(5000)
+        ch.reset(0)
+        ch.upload(0, HostBatch(np.zeros((0, 32), np.uint8), np.zeros((0, 16), np.uint8), np.zeros(0, np.uint16)))
+        ch.upload(1, HostBatch(None, None, np.zeros(0, np.uint16)))
+        pipe.count(ch); pipe.allreduce(); pipe.correct(ch)
+        assert pipe.counts(0)[2] == 0
+        infos, strides = pipe.infos, [pipe.stride(r) for r in range(2)]
+        for n in (5000, 1234):
+            full = U.gen_reads(rng, layout, n, strides)
+            dev = U.narrow(full, strides, infos)
+            pipe.reset_counts()
+            ch.reset(n)
+            for r, b in enumerate(dev):
+                ch.upload(r, b)
+            pipe.count(ch); pipe.allreduce(); pipe.correct(ch)
+            results = [ch.fetch(r) for r in range(2)]
+            counts = {0: pipe.counts(0)}
+            ores, ocounts = U.run_oracle(layout, full)
+            U.compare_with_oracle(layout, infos, full, results, counts, pipe.qc()[:, 1], ores, ocounts)
+    finally:
+        pipe.close()
