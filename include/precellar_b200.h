@@ -244,6 +244,21 @@ int64_t pcl_fastq_read(pcl_fastq *r, uint64_t max_records, uint32_t stride, uint
                        uint8_t *seq, uint8_t *qual, uint16_t *len, uint64_t *name_hash, uint8_t *text, uint64_t text_cap,
                        uint64_t *off, uint64_t *text_used);
 
+/* ---- host-side record assembly for writers ------------------------------------------------------
+ * make_fastq's record loop (python/src/lib.rs:149-167) on top of FastqAnnotator::annotate / AnnotatedFastq::join /
+ * Barcode::extend (precellar/src/align/fastq.rs:474-604), for one fetched chunk: R1 = (corrected or raw) barcode +
+ * UMI + read1, R2 = read2; groups without a barcode are skipped and, with correct_barcode, so are groups whose
+ * barcode is not corrected.  Text is FASTQ ("@definition\nseq\n+\nqual\n"), appended at *r1_used / *r2_used. */
+typedef struct {
+    const uint8_t *text;         /* arena filled by pcl_fastq_read (definition, sequence, quality per record) */
+    const uint64_t *off;         /* 3 * n + 1 offsets into text                                               */
+    const uint16_t *len;         /* record lengths as uploaded                                                */
+    pcl_read_results res;        /* host copies of the result planes (pcl_chunk_fetch)                        */
+} pcl_host_read;
+int pcl_make_fastq_batch(pcl_ctx *ctx, const pcl_host_read *reads, uint64_t n, int correct_barcode, int paired,
+                         uint8_t *r1_out, uint64_t r1_cap, uint64_t *r1_used, uint8_t *r2_out, uint64_t r2_cap,
+                         uint64_t *r2_used, uint64_t *n_written);
+
 /* ---- pinned host memory ------------------------------------------------------------------- */
 void *pcl_host_alloc(uint64_t bytes);
 void pcl_host_free(void *p);

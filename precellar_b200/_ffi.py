@@ -54,6 +54,10 @@ class ReadResults(C.Structure):
                 ("bcoord", C.c_void_p * PCL_MAX_BC_PER_READ), ("ucoord", C.c_void_p * PCL_MAX_UMI_PER_READ)]
 
 
+class HostRead(C.Structure):
+    _fields_ = [("text", C.c_void_p), ("off", C.c_void_p), ("len", C.c_void_p), ("res", ReadResults)]
+
+
 class PclError(RuntimeError):
     def __init__(self, code: int, msg: str):
         super().__init__(f"precellar_b200 error {code}: {msg}")
@@ -71,6 +75,7 @@ SYMBOLS = [
     "pcl_launch_count", "pcl_timer_start", "pcl_timer_stop_ms",
     "pcl_qc_enable", "pcl_qc_accumulate", "pcl_qc_fetch_categories",
     "pcl_fastq_open", "pcl_fastq_close", "pcl_fastq_error", "pcl_fastq_read", "pcl_chunk_fetch_async",
+    "pcl_make_fastq_batch",
 ]
 
 _lib = None
@@ -126,6 +131,8 @@ def lib() -> C.CDLL:
         "pcl_qc_enable": (i32, [vp, i32]),
         "pcl_qc_accumulate": (i32, [vp, vp]),
         "pcl_qc_fetch_categories": (i32, [vp, vp]),
+        "pcl_make_fastq_batch": (i32, [vp, C.POINTER(HostRead), u64, i32, i32, vp, u64, C.POINTER(u64), vp, u64,
+                                       C.POINTER(u64), C.POINTER(u64)]),
         "pcl_fastq_open": (i32, [C.POINTER(C.c_char_p), i32, C.POINTER(vp)]),
         "pcl_fastq_close": (None, [vp]),
         "pcl_fastq_error": (C.c_char_p, [vp]),

@@ -101,6 +101,11 @@ class FastqProcessor:
     # ------------------------------------------------------------------------------------------
     def gen_barcoded_fastq(self, correct_barcode: bool, chunk_size: int = 1_000_000) -> Iterator[List[AnnotatedFastq]]:
         """Batches of annotated records, assays one after the other (fastq.rs:109-153, 243-255)."""
+        for layout, pipe, text, results in self._gen_chunks(correct_barcode, chunk_size):
+            yield self._annotate(layout, pipe, text, results, correct_barcode)
+
+    def _gen_chunks(self, correct_barcode: bool, chunk_size: int):
+        """(layout, pipeline, record text per read file, fetched result planes) per device chunk."""
         modality = self.modality()
         per_file = None
         cats = np.zeros((4, 3), np.uint64)
@@ -116,7 +121,8 @@ class FastqProcessor:
                     raise RuntimeError(f"Failed to open FASTQ file: {read.read_id}")
             pipe = BarcodePipeline(layout, device=self.device, qc=self.compute_qc)
             try:
-                yield from self._run_assay(pipe, layout, correct_barcode, chunk_size)
+                for text, results in self._run_assay(pipe, layout, correct_barcode, chunk_size):
+                    yield layout, pipe, text, results
                 q = pipe.qc()
                 cats += pipe.qc_categories() if self.compute_qc else 0
                 if per_file is None:
@@ -187,7 +193,7 @@ class FastqProcessor:
                 results = [ch.fetch(r) for r in range(n_reads)]
                 text = rdr.next(n)
                 assert text is not None and len(text[0].batch.length) == n
-                yield self._annotate(layout, pipe, text, results, correct_barcode)
+                yield text, results
                 ch.close()
                 pipe.chunks.remove(ch)
         finally:
@@ -266,29 +272,42 @@ def make_fastq(assay, *, modality: str, out_dir, correct_barcode: bool = False, 
     paired = proc.is_paired_end()
     w1 = _zstd.Writer(os.path.join(out_dir, "R1.fq.zst"))
     w2 = _zstd.Writer(os.path.join(out_dir, "R2.fq.zst")) if paired else None
+    import ctypes as C
+    L = _ffi.lib()
     try:
-        for batch in proc.gen_barcoded_fastq(correct_barcode, 1_000_000):
-            b1, b2 = bytearray(), bytearray()
-            for rec in batch:
-                bc = rec.barcode
-                if correct_barcode and bc.corrected is None:
-                    continue
-                raw = FastqRecord(bc.raw.definition, bc.corrected if bc.corrected is not None else bc.raw.sequence, bc.raw.quality)
-                if rec.umi is not None:
-                    raw.sequence += rec.umi.sequence
-                    raw.quality += rec.umi.quality
-                if rec.read1 is None:
-                    raise RuntimeError("called `Option::unwrap()` on a `None` value: read1")     # lib.rs:160
-                raw.sequence += rec.read1.sequence
-                raw.quality += rec.read1.quality
-                b1 += raw.to_bytes()
-                if w2 is not None:
-                    if rec.read2 is None:
-                        raise RuntimeError("called `Option::unwrap()` on a `None` value: read2") # lib.rs:164
-                    b2 += rec.read2.to_bytes()
-            w1.write(bytes(b1))
+        for layout, pipe, text, results in proc._gen_chunks(correct_barcode, 1_000_000):
+            n = len(text[0].batch.length)
+            hr = (_ffi.HostRead * len(text))()
+            keep = []
+            for r, (t, res) in enumerate(zip(text, results)):
+                ln = np.ascontiguousarray(t.batch.length, np.uint16)
+                keep.append(ln)
+                hr[r].text, hr[r].off, hr[r].len = t.text.ctypes.data, t.off.ctypes.data, ln.ctypes.data
+                hr[r].res.fstatus = res.fstatus.ctypes.data
+                if res.tcoord is not None:
+                    hr[r].res.tcoord = res.tcoord.ctypes.data
+                for j, k in enumerate(res.bc_key):
+                    hr[r].res.bc_key[j] = k.ctypes.data
+                    if res.bcoord[j] is not None:
+                        hr[r].res.bcoord[j] = res.bcoord[j].ctypes.data
+                for j, k in enumerate(res.umi_key):
+                    if res.ucoord[j] is not None:
+                        hr[r].res.ucoord[j] = res.ucoord[j].ctypes.data
+            cap1 = int(sum(len(t.text) for t in text)) + 8 * n + 64
+            cap2 = cap1 if paired else 0
+            o1 = np.empty(cap1, np.uint8)
+            o2 = np.empty(max(cap2, 1), np.uint8)
+            u1, u2, nw = C.c_uint64(0), C.c_uint64(0), C.c_uint64(0)
+            _ffi.check(pipe.ctx, L.pcl_make_fastq_batch(pipe.ctx, hr, n, int(correct_barcode), int(paired), o1.ctypes.data, cap1,
+                                                        C.byref(u1), o2.ctypes.data if paired else None, cap2,
+                                                        C.byref(u2) if paired else None, C.byref(nw)))
+            w1.write(o1[:u1.value].tobytes())
             if w2 is not None:
-                w2.write(bytes(b2))
+                w2.write(o2[:u2.value].tobytes())
+    except _ffi.PclError as e:
+        if "unwrap" in str(e):
+            raise RuntimeError(str(e)) from e
+        raise
     finally:
         w1.close()
         if w2 is not None:

@@ -788,6 +788,145 @@ int pcl_key_decode(uint64_t key, char *out32) {
     return L;
 }
 
+// ------------------------------------------------------------------------------------------
+// host-side assembly of make_fastq records from the result planes and the record text
+// ------------------------------------------------------------------------------------------
+static inline void rc_append(std::string &dst, const uint8_t *p, uint32_t n) {       // precellar::utils::rev_compl
+    for (uint32_t i = 0; i < n; ++i) {
+        uint8_t x = p[n - 1 - i];
+        switch (x) {
+            case 'A': case 'a': x = 'T'; break;
+            case 'T': case 't': x = 'A'; break;
+            case 'C': case 'c': x = 'G'; break;
+            case 'G': case 'g': x = 'C'; break;
+            default: break;
+        }
+        dst.push_back((char)x);
+    }
+}
+static inline void rev_append(std::string &dst, const uint8_t *p, uint32_t n) {
+    for (uint32_t i = 0; i < n; ++i) dst.push_back((char)p[n - 1 - i]);
+}
+static inline uint32_t static_coord(const pcl_read_desc &rd, const pcl_read_info &inf, uint32_t e, uint32_t L) {
+    const uint32_t s = inf.static_start[e], mn = rd.elems[e].min_len, mx = rd.elems[e].max_len;
+    if (s >= L || s + mn > L) return PCL_COORD_ABSENT;
+    const uint32_t hi = s + mx < L ? s + mx : L;
+    return (s << 16) | (hi - s);
+}
+
+int pcl_make_fastq_batch(pcl_ctx *ctx, const pcl_host_read *reads, uint64_t n, int correct_barcode, int paired,
+                         uint8_t *r1_out, uint64_t r1_cap, uint64_t *r1_used, uint8_t *r2_out, uint64_t r2_cap,
+                         uint64_t *r2_used, uint64_t *n_written) {
+    if (!ctx || !reads || !r1_out || !r1_used) return PCL_ERR_ARG;
+    if (paired && (!r2_out || !r2_used)) return PCL_ERR_ARG;
+    const int nr = ctx->n_reads;
+    uint64_t u1 = *r1_used, u2 = r2_used ? *r2_used : 0, written = 0;
+    std::string bseq, bqual, corr, useq, uqual, piece;
+    for (uint64_t i = 0; i < n; ++i) {
+        bseq.clear(); bqual.clear(); corr.clear(); useq.clear(); uqual.clear();
+        bool has_bc = false, all_ok = true;
+        int bc_def = -1, r1_file = -1, r2_file = -1;
+        uint32_t r1c = 0, r2c = 0;
+        for (int r = 0; r < nr; ++r) {
+            const pcl_read_desc &rd = ctx->descs[r];
+            const pcl_read_info &inf = ctx->infos[r];
+            const pcl_host_read &h = reads[r];
+            const uint32_t fs = h.res.fstatus[i];
+            const uint32_t st = fs & 3u;
+            if (st == PCL_SPLIT_MULTI_TARGET) return fail(ctx, PCL_ERR_INPUT, "Multiple target regions found in one fastq record!");
+            if (st != PCL_SPLIT_OK) continue;                                    // a defect file contributes nothing
+            uint32_t L = h.len[i];
+            if (rd.max_len && L > rd.max_len) L = rd.max_len;
+            const uint8_t *seq = h.text + h.off[3 * i + 1], *qual = h.text + h.off[3 * i + 2];
+            for (int j = 0; j < inf.n_bc; ++j) {
+                const uint32_t code = PCL_BC_CODE(fs, j);
+                if (code == PCL_BC_ABSENT) continue;
+                const uint32_t e = inf.bc_elem[j];
+                const uint32_t c = inf.fixed_layout ? static_coord(rd, inf, e, L) : h.res.bcoord[j][i];
+                if (c == PCL_COORD_ABSENT) return fail(ctx, PCL_ERR_INPUT, "inconsistent barcode coordinates");
+                const uint32_t s0 = c >> 16, ln = c & 0xFFFFu;
+                piece.clear();
+                if (rd.is_reverse) { rc_append(piece, seq + s0, ln); rev_append(bqual, qual + s0, ln); }
+                else { piece.assign((const char *)seq + s0, ln); bqual.append((const char *)qual + s0, ln); }
+                bseq += piece;
+                if (bc_def < 0) bc_def = r;
+                has_bc = true;
+                if (!correct_barcode || code == PCL_BC_EXACT) corr += piece;
+                else if (code == PCL_BC_CORRECTED) {
+                    uint64_t key = inf.bc_key_bytes[j] == 4 ? ((const uint32_t *)h.res.bc_key[j])[i] : ((const uint64_t *)h.res.bc_key[j])[i];
+                    if (inf.bc_key_bytes[j] == 4 && rd.elems[e].min_len == 16 && rd.elems[e].max_len == 16) key |= 1ull << 32;
+                    char buf[40];
+                    const int kl = pcl_key_decode(key, buf);
+                    if (kl < 0) return fail(ctx, PCL_ERR_INPUT, "corrupt corrected key");
+                    corr.append(buf, kl);
+                } else all_ok = false;
+            }
+            uint32_t uc = PCL_COORD_ABSENT;                                      // the last UMI segment of a file wins (fastq.rs:502)
+            for (int j = 0; j < inf.n_umi; ++j) {
+                const uint32_t c = inf.fixed_layout ? static_coord(rd, inf, inf.umi_elem[j], L) : h.res.ucoord[j][i];
+                if (c != PCL_COORD_ABSENT) uc = c;
+            }
+            if (uc != PCL_COORD_ABSENT) {
+                const uint32_t s0 = uc >> 16, ln = uc & 0xFFFFu;
+                if (rd.is_reverse) { rc_append(useq, seq + s0, ln); rev_append(uqual, qual + s0, ln); }
+                else { useq.append((const char *)seq + s0, ln); uqual.append((const char *)qual + s0, ln); }
+            }
+            if (inf.has_target && (fs & PCL_FSTATUS_TARGET)) {
+                if (rd.is_reverse) {
+                    if (r2_file >= 0) return fail(ctx, PCL_ERR_INPUT, "Read2 already exists");
+                    r2_file = r; r2c = h.res.tcoord[i];
+                } else {
+                    if (r1_file >= 0) return fail(ctx, PCL_ERR_INPUT, "Read1 already exists");
+                    r1_file = r; r1c = h.res.tcoord[i];
+                }
+            }
+        }
+        if (!has_bc) continue;                                                   // dropped by process_chunk (fastq.rs:381-385)
+        if (correct_barcode && !all_ok) continue;                                // lib.rs:154
+        if (r1_file < 0) return fail(ctx, PCL_ERR_INPUT, "called `Option::unwrap()` on a `None` value: read1");
+        if (paired && r2_file < 0) return fail(ctx, PCL_ERR_INPUT, "called `Option::unwrap()` on a `None` value: read2");
+        {
+            const pcl_host_read &hb = reads[bc_def], &h1 = reads[r1_file];
+            const uint8_t *def = hb.text + hb.off[3 * i];
+            const uint64_t dl = hb.off[3 * i + 1] - hb.off[3 * i];
+            const uint32_t s0 = r1c >> 16, ln = r1c & 0xFFFFu;
+            const uint64_t need = 1 + dl + 1 + corr.size() + useq.size() + ln + 3 + bqual.size() + uqual.size() + ln + 1;
+            if (u1 + need > r1_cap) return fail(ctx, PCL_ERR_NOMEM, "R1 output buffer too small");
+            uint8_t *o = r1_out + u1;
+            *o++ = '@'; memcpy(o, def, dl); o += dl; *o++ = '\n';
+            memcpy(o, corr.data(), corr.size()); o += corr.size();
+            memcpy(o, useq.data(), useq.size()); o += useq.size();
+            memcpy(o, h1.text + h1.off[3 * i + 1] + s0, ln); o += ln;
+            *o++ = '\n'; *o++ = '+'; *o++ = '\n';
+            memcpy(o, bqual.data(), bqual.size()); o += bqual.size();
+            memcpy(o, uqual.data(), uqual.size()); o += uqual.size();
+            memcpy(o, h1.text + h1.off[3 * i + 2] + s0, ln); o += ln;
+            *o++ = '\n';
+            u1 += need;
+        }
+        if (paired) {
+            const pcl_host_read &h2 = reads[r2_file];
+            const uint8_t *def = h2.text + h2.off[3 * i];
+            const uint64_t dl = h2.off[3 * i + 1] - h2.off[3 * i];
+            const uint32_t s0 = r2c >> 16, ln = r2c & 0xFFFFu;
+            const uint64_t need = 1 + dl + 1 + ln + 3 + ln + 1;
+            if (u2 + need > r2_cap) return fail(ctx, PCL_ERR_NOMEM, "R2 output buffer too small");
+            uint8_t *o = r2_out + u2;
+            *o++ = '@'; memcpy(o, def, dl); o += dl; *o++ = '\n';
+            memcpy(o, h2.text + h2.off[3 * i + 1] + s0, ln); o += ln;
+            *o++ = '\n'; *o++ = '+'; *o++ = '\n';
+            memcpy(o, h2.text + h2.off[3 * i + 2] + s0, ln); o += ln;
+            *o++ = '\n';
+            u2 += need;
+        }
+        ++written;
+    }
+    *r1_used = u1;
+    if (r2_used) *r2_used = u2;
+    if (n_written) *n_written = written;
+    return PCL_OK;
+}
+
 void *pcl_host_alloc(uint64_t bytes) {
     void *p = nullptr;
     if (cudaHostAlloc(&p, bytes ? bytes : 16, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); return nullptr; }

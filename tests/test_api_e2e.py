@@ -191,3 +191,60 @@ def test_mismatched_names_are_rejected(dataset, tmp_path):
         for _ in FastqProcessor(a).with_modality("rna").gen_barcoded_fastq(True):
             pass
     assert ei.value.code == _ffi.PCL_ERR_INPUT
+
+
+def test_make_fastq_paired_end_atac_like(tmp_path):
+    """Paired-end layout (targets on both strands): R1.fq.zst and R2.fq.zst, neg-strand barcode read (I2)."""
+    from precellar_b200 import Assay, _zstd, compile_layout
+    from precellar_b200.api import make_fastq
+    td = str(tmp_path)
+    rng = np.random.default_rng(21)
+    wl = U.gen_whitelist(rng, 200, 16)
+    open(os.path.join(td, "wl.txt"), "wb").write(b"\n".join(wl) + b"\n")
+    regions = [
+        region("p5", "illumina_p5", "fixed", "AATGATACGGCGACCACCGAGATCTACAC", 29, 29),
+        region("cell_bc", "barcode", "onlist", "N" * 16, 16, 16, os.path.join(td, "wl.txt")),
+        region("r1p", "nextera_read1", "fixed", "TCGTCGGCAGCGTCAGATGTGTATAAGAGACAG", 33, 33),
+        region("gdna", "gdna", "random", "X", 1, 1000),
+        region("r2p", "nextera_read2", "fixed", "CTGTCTCTTATACACATCTCCGAGCCCACGAGAC", 34, 34),
+        region("p7", "illumina_p7", "fixed", "ATCTCGTATGCCGTCTTCTGCTTG", 24, 24),
+    ]
+    spec = dict(seqspec_version="0.3.0", assay_id="atac-test", name="x", doi="", date="", description="", modalities=["atac"],
+                lib_struct="", library_protocol="x", library_kit="x", sequence_protocol="x", sequence_kit="x", sequence_spec=[],
+                library_spec=[dict(region_id="atac", region_type="atac", name="atac", sequence_type="joined", sequence="",
+                                   min_len=0, max_len=0, onlist=None, regions=regions)])
+    path = os.path.join(td, "atac.yaml")
+    yaml.safe_dump(spec, open(path, "w"), sort_keys=False)
+    a = Assay(path)
+    a.add_illumina_reads("atac", forward_strand_workflow=False)
+    assert sorted(a.sequence_spec) == ["atac-I2", "atac-R1", "atac-R2"]
+    for rid, ln in (("atac-R1", 40), ("atac-R2", 40)):
+        a.update_read(rid, min_len=ln, max_len=ln)
+    layout0 = compile_layout(a, "atac")
+    n = 3000
+    full = U.gen_reads(rng, layout0, n, [64] * 3, p_short=0.0, read_len=[p.max_len for p in layout0.reads])
+    for b in full:
+        b.length[:] = np.maximum(b.length, 1)
+    order = [p.read_id for p in layout0.reads]
+    for r, rid in enumerate(order):
+        names = [f"q{i}/{1 if rid != 'atac-R2' else 2}".encode() for i in range(n)]
+        write_fastq(os.path.join(td, rid + ".fq.gz"), names, full[r], True)
+        a.update_read(rid, fastq=os.path.join(td, rid + ".fq.gz"))
+    out = os.path.join(td, "out")
+    make_fastq(a, modality="atac", out_dir=out, correct_barcode=True)
+    layout = compile_layout(a, "atac", require_files=True)
+    ores, _ = U.run_oracle(layout, full, correct=True, threshold=0.975)
+    r1 = _zstd.decompress_file(os.path.join(out, "R1.fq.zst")).split(b"\n")
+    r2 = _zstd.decompress_file(os.path.join(out, "R2.fq.zst")).split(b"\n")
+    want1, want2 = [], []
+    for ln in ores.lines:
+        if not ln:
+            continue
+        f = ln.split("\t")
+        if f[2] == "*":
+            continue
+        want1.append(((f[2] + f[3] + f[5]).encode("latin-1"), (f[1] + f[4] + f[6]).encode("latin-1")))
+        want2.append((f[7].encode("latin-1"), f[8].encode("latin-1")))
+    got1 = [(r1[i + 1], r1[i + 3]) for i in range(0, len(r1) - 1, 4)]
+    got2 = [(r2[i + 1], r2[i + 3]) for i in range(0, len(r2) - 1, 4)]
+    assert got1 == want1 and got2 == want2 and len(want1) > 1500
