@@ -54,6 +54,21 @@ class AnnotatedFastq:                            # fastq.rs:549-556
     read1: Optional[FastqRecord]
     read2: Optional[FastqRecord]
 
+    def tags(self) -> dict:
+        """The SAM tags the aligner adapters attach to every alignment of this read
+        (add_cell_barcode / add_umi, precellar/src/align/aligners.rs:347-372): CB corrected barcode (absent when not
+        corrected), CR / CY raw barcode and its qualities, UR / UY UMI and its qualities."""
+        out = {}
+        if self.barcode is not None:
+            if self.barcode.corrected is not None:
+                out["CB"] = self.barcode.corrected
+            out["CR"] = self.barcode.raw.sequence
+            out["CY"] = self.barcode.raw.quality
+        if self.umi is not None:
+            out["UR"] = self.umi.sequence
+            out["UY"] = self.umi.quality
+        return out
+
 
 def _as_assays(assay) -> List[Assay]:
     """extract_assays (python/src/pyseqspec.rs:12-27): a path, an Assay, or a list of either."""

@@ -11,6 +11,7 @@
 //
 // FASTQ dialect: what noodles-fastq reads -- four lines per record, single-line sequence and quality,
 // "@name[ description]"; \r\n tolerated.
+#include <dlfcn.h>
 #include <zlib.h>
 
 #include <cstdint>
@@ -21,10 +22,43 @@
 
 #include "../../include/precellar_b200.h"
 
+// libzstd has no headers in this image: the few stable entry points are resolved at run time.
+namespace {
+struct ZBuf { void *p; size_t size, pos; };
+struct ZstdApi {
+    void *h = nullptr;
+    void *(*createDStream)() = nullptr;
+    size_t (*freeDStream)(void *) = nullptr;
+    size_t (*initDStream)(void *) = nullptr;
+    size_t (*decompressStream)(void *, ZBuf *, ZBuf *) = nullptr;
+    unsigned (*isError)(size_t) = nullptr;
+    bool ok = false;
+};
+ZstdApi &zstd() {
+    static ZstdApi a;
+    static bool tried = false;
+    if (tried) return a;
+    tried = true;
+    a.h = dlopen("libzstd.so.1", RTLD_NOW);
+    if (!a.h) return a;
+    a.createDStream = (void *(*)())dlsym(a.h, "ZSTD_createDStream");
+    a.freeDStream = (size_t(*)(void *))dlsym(a.h, "ZSTD_freeDStream");
+    a.initDStream = (size_t(*)(void *))dlsym(a.h, "ZSTD_initDStream");
+    a.decompressStream = (size_t(*)(void *, ZBuf *, ZBuf *))dlsym(a.h, "ZSTD_decompressStream");
+    a.isError = (unsigned (*)(size_t))dlsym(a.h, "ZSTD_isError");
+    a.ok = a.createDStream && a.freeDStream && a.initDStream && a.decompressStream && a.isError;
+    return a;
+}
+}  // namespace
+
 struct pcl_fastq {
     std::vector<std::string> paths;
     size_t cur = 0;
     gzFile gz = nullptr;
+    FILE *zf = nullptr;                 // .zst input
+    void *zds = nullptr;
+    std::vector<uint8_t> zin;
+    size_t zin_pos = 0, zin_end = 0;
     std::vector<uint8_t> buf;
     size_t pos = 0, end = 0;
     bool eof_all = false;
@@ -32,21 +66,59 @@ struct pcl_fastq {
     uint64_t n_records = 0;
     std::string line[4];
 
-    bool open_next() {
+    static bool is_zst(const std::string &p) { return p.size() > 4 && p.compare(p.size() - 4, 4, ".zst") == 0; }
+    void close_cur() {
         if (gz) { gzclose(gz); gz = nullptr; }
+        if (zf) { fclose(zf); zf = nullptr; }
+        if (zds) { zstd().freeDStream(zds); zds = nullptr; }
+    }
+    bool open_next() {
+        close_cur();
         if (cur >= paths.size()) { eof_all = true; return false; }
-        gz = gzopen(paths[cur].c_str(), "rb");       // transparent for uncompressed files
-        if (!gz) { err = "cannot open file: " + paths[cur]; eof_all = true; return false; }
-        gzbuffer(gz, 1u << 20);
+        const std::string &path = paths[cur];
+        // open_file (seqspec/src/utils.rs:44-56): gzip by magic, zstd by the .zst extension, else plain
+        bool gzip_magic = false;
+        if (FILE *f = fopen(path.c_str(), "rb")) {
+            unsigned char m[2] = {0, 0};
+            gzip_magic = fread(m, 1, 2, f) == 2 && m[0] == 0x1f && m[1] == 0x8b;
+            fclose(f);
+        }
+        if (!gzip_magic && is_zst(path)) {
+            if (!zstd().ok) { err = "libzstd.so.1 is not available: cannot read " + path; eof_all = true; return false; }
+            zf = fopen(path.c_str(), "rb");
+            if (!zf) { err = "cannot open file: " + path; eof_all = true; return false; }
+            zds = zstd().createDStream();
+            zstd().initDStream(zds);
+            zin.resize(1u << 20);
+            zin_pos = zin_end = 0;
+        } else {
+            gz = gzopen(path.c_str(), "rb");       // transparent for uncompressed files
+            if (!gz) { err = "cannot open file: " + path; eof_all = true; return false; }
+            gzbuffer(gz, 1u << 20);
+        }
         ++cur;
         return true;
     }
     bool fill() {
         for (;;) {
-            if (!gz && !open_next()) return false;
+            if (!gz && !zf && !open_next()) return false;
+            if (zf) {
+                if (zin_pos == zin_end) {
+                    zin_end = fread(zin.data(), 1, zin.size(), zf);
+                    zin_pos = 0;
+                    if (zin_end == 0) { close_cur(); continue; }              // next file of the same read
+                }
+                ZBuf in{zin.data(), zin_end, zin_pos}, out{buf.data(), buf.size(), 0};
+                size_t rc = zstd().decompressStream(zds, &out, &in);
+                if (zstd().isError(rc)) { err = "zstd error in " + paths[cur - 1]; eof_all = true; return false; }
+                zin_pos = in.pos;
+                if (out.pos == 0) continue;
+                pos = 0; end = out.pos;
+                return true;
+            }
             int n = gzread(gz, buf.data(), (unsigned)buf.size());
             if (n < 0) { int e; err = std::string("gzip error: ") + gzerror(gz, &e); eof_all = true; return false; }
-            if (n == 0) { gzclose(gz); gz = nullptr; continue; }    // next file of the same read (read.rs:148-149)
+            if (n == 0) { close_cur(); continue; }    // next file of the same read (read.rs:148-149)
             pos = 0; end = (size_t)n;
             return true;
         }
@@ -95,7 +167,7 @@ int pcl_fastq_open(const char *const *paths, int n_paths, pcl_fastq **out) {
 
 void pcl_fastq_close(pcl_fastq *r) {
     if (!r) return;
-    if (r->gz) gzclose(r->gz);
+    r->close_cur();
     delete r;
 }
 

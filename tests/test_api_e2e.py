@@ -122,6 +122,10 @@ def test_gen_barcoded_fastq_matches_oracle(dataset, correct):
                 rec.read1.sequence if rec.read1 else b"", rec.read1.quality if rec.read1 else b"",
                 rec.read2.sequence if rec.read2 else b"", rec.read2.quality if rec.read2 else b""]
         assert [m.decode("latin-1") for m in mine] == f
+    # the SAM tags an aligner adapter would attach (aligners.rs:347-372)
+    t = got[0].tags()
+    assert t["CR"] == got[0].barcode.raw.sequence and t["CY"] == got[0].barcode.raw.quality and t["UR"] == got[0].umi.sequence
+    assert ("CB" in t) == (got[0].barcode.corrected is not None)
     # definitions: barcode/umi carry R1's definition line, read2 its own
     k = next(i for i, ln in enumerate(ores.lines) if ln)
     assert got[0].barcode.raw.definition == dataset["names1"][k] and got[0].read2.definition == dataset["names2"][k]

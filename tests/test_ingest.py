@@ -1,0 +1,112 @@
+"""CPU tier: the C++ FASTQ reader behind pcl_fastq_* (no GPU needed): plain / gzip / multi-member gzip / zstd input,
+concatenated files, CRLF, SoA planes with a quality window, record text arena, name hashes and the cross-file
+checks of BatchedFqReader (precellar/src/align/fastq.rs:400-448,612-621)."""
+import gzip
+import os
+
+import numpy as np
+import pytest
+
+from precellar_b200 import _ffi, _zstd
+from precellar_b200.ingest import FastqReader, GroupReader
+
+
+def make_records(n, tag="/1"):
+    rng = np.random.default_rng(4)
+    out = []
+    for i in range(n):
+        L = int(rng.integers(1, 60))
+        s = bytes(rng.choice(np.frombuffer(b"ACGTN", np.uint8), L))
+        q = bytes(rng.choice(np.frombuffer(b"F:,#", np.uint8), L))
+        out.append((f"read{i}{tag} extra:{i}".encode(), s, q))
+    return out
+
+
+def text_of(recs, eol=b"\n"):
+    return b"".join(b"@" + d + eol + s + eol + b"+" + eol + q + eol for d, s, q in recs)
+
+
+@pytest.fixture(scope="module")
+def files(tmp_path_factory):
+    td = str(tmp_path_factory.mktemp("ingest"))
+    recs = make_records(3000)
+    paths = {}
+    open(os.path.join(td, "a.fq"), "wb").write(text_of(recs[:1000]))
+    with open(os.path.join(td, "b.fq.gz"), "wb") as fh:                    # two gzip members in one file
+        fh.write(gzip.compress(text_of(recs[1000:1500])))
+        fh.write(gzip.compress(text_of(recs[1500:2000], b"\r\n")))
+    w = _zstd.Writer(os.path.join(td, "c.fq.zst"), block=30000)
+    w.write(text_of(recs[2000:]))
+    w.close()
+    paths["all"] = [os.path.join(td, f) for f in ("a.fq", "b.fq.gz", "c.fq.zst")]
+    return td, recs, paths
+
+
+def test_reads_every_format_and_concatenates(files):
+    td, recs, paths = files
+    r = FastqReader(paths["all"])
+    got = 0
+    while True:
+        b = r.read(700, 32, keep_text=True, qual_window=(4, 16))
+        if b is None:
+            break
+        for i in range(len(b.batch.length)):
+            d, s, q = recs[got + i]
+            assert b.record(i) == (d, s, q)
+            L = len(s)
+            assert b.batch.length[i] == L
+            row = b.batch.seq[i].tobytes()
+            assert row[:min(L, 32)] == s[:32] and row[min(L, 32):] == b"N" * (32 - min(L, 32))
+            qrow = b.batch.qual[i].tobytes()                                 # quality bytes [4, 20) of the record
+            want = q[4:20]
+            assert qrow[:len(want)] == want and qrow[len(want):] == b"!" * (16 - len(want))
+        got += len(b.batch.length)
+    assert got == len(recs)
+    r.close()
+
+
+def test_group_reader_checks(files, tmp_path):
+    td, recs, paths = files
+    mates = [(d.replace(b"/1", b"/2"), s[::-1], q) for d, s, q in recs]
+    p2 = str(tmp_path / "mate.fq")
+    open(p2, "wb").write(text_of(mates))
+    g = GroupReader([paths["all"], [p2]], [16, 0], [False, False])
+    n = 0
+    while True:
+        got = g.next(1024)
+        if got is None:
+            break
+        n += len(got[0].batch.length)
+        assert got[1].batch.seq is None and np.array_equal(got[0].name_hash, got[1].name_hash)   # /1 and /2 stripped
+    assert n == len(recs)
+    g.close()
+    # unequal record counts
+    p3 = str(tmp_path / "short.fq")
+    open(p3, "wb").write(text_of(mates[:2500]))
+    g = GroupReader([paths["all"], [p3]], [16, 0], [False, False])
+    with pytest.raises(_ffi.PclError) as ei:
+        while g.next(1024) is not None:
+            pass
+    assert ei.value.code == _ffi.PCL_ERR_INPUT and "Unequal" in str(ei.value)
+    # different names at the same position
+    p4 = str(tmp_path / "other.fq")
+    open(p4, "wb").write(text_of([(b"x" + d, s, q) for d, s, q in mates]))
+    g = GroupReader([paths["all"], [p4]], [16, 0], [False, False])
+    with pytest.raises(_ffi.PclError) as ei:
+        g.next(100)
+    assert "names mismatch" in str(ei.value)
+
+
+def test_malformed_input_is_an_error(tmp_path):
+    p = str(tmp_path / "bad.fq")
+    open(p, "wb").write(b"@r1\nACGT\n+\nFFF\n")                                # quality shorter than the sequence
+    with pytest.raises(_ffi.PclError):
+        FastqReader([p]).read(10, 16)
+    open(p, "wb").write(b"r1\nACGT\n+\nFFFF\n")
+    with pytest.raises(_ffi.PclError):
+        FastqReader([p]).read(10, 16)
+    open(p, "wb").write(b"@r1\nACGT\n+\n")
+    with pytest.raises(_ffi.PclError):
+        FastqReader([p]).read(10, 16)
+    with pytest.raises(_ffi.PclError):
+        FastqReader([str(tmp_path / "missing.fq")])
