@@ -39,6 +39,8 @@ struct DElem {
     int8_t umi_j;        // index among the read's UMI elements, else -1
     uint8_t pad[2];
     uint8_t seq[PCL_MAX_ANCHOR];
+    uint64_t a_code;     // anchors of <= 32 upper-case ACGT bases: 2-bit codes, base i at bits 2i ...
+    uint64_t a_rc;       // ... and the same for the reverse complement of the anchor
 };
 
 // Register-resident path for the common short barcode reads (10x v2/v3 R1, ATAC / multiome I2 ...):
@@ -59,7 +61,7 @@ struct DRead {
     uint32_t max_len;    // reader truncation, 0 = none
     uint32_t stride;     // bytes per record slot
     uint8_t n_bc, n_umi, has_target, needs_payload;
-    uint8_t qual_only, pad0[3];   // QC mode: insert read that carries only a quality plane
+    uint8_t qual_only, codes_ok, pad0[2];   // qual_only: QC-mode insert read; codes_ok: pcl_split_codes / pcl_pack_codes apply
     uint32_t qoff, qstride;       // the quality plane holds record bytes [qoff, qoff + qstride) per record
     DElem elems[PCL_MAX_ELEMS];
     FastLayout fast;
@@ -280,7 +282,9 @@ PCL_HD void pcl_consume(const DRead &rd, SplitOut &o, int b0, int b1, uint32_t l
     }
 }
 
-PCL_HD void pcl_split(const DRead &rd, const uint8_t *rec, uint32_t len, SplitOut &o) {
+// Matcher: bool operator()(const DElem &el, uint32_t wstart, uint32_t wn, uint32_t *pos, uint32_t *mis)
+template <class Matcher>
+PCL_HD void pcl_split_t(const DRead &rd, uint32_t len, SplitOut &o, const Matcher &match) {
     for (int e = 0; e < PCL_MAX_ELEMS; ++e) o.seg[e] = PCL_COORD_ABSENT;
     o.tcoord = PCL_COORD_ABSENT;
     o.status = PCL_SPLIT_OK;
@@ -296,7 +300,7 @@ PCL_HD void pcl_split(const DRead &rd, const uint8_t *rec, uint32_t len, SplitOu
                 if (el.is_anchor) {                                              // segment.rs:254-311
                     uint32_t wend = max_off + mx < len ? max_off + mx : len;
                     uint32_t pos = 0, mis = 0;
-                    if (!pcl_best_match(rec + min_off, wend - min_off, el.seq, el.seq_len, rd.is_reverse != 0, &pos, &mis)) {
+                    if (!match(el, min_off, wend - min_off, &pos, &mis)) {
                         o.status = PCL_SPLIT_ANCHOR_NOT_FOUND;
                         return;
                     }
@@ -334,6 +338,19 @@ PCL_HD void pcl_split(const DRead &rd, const uint8_t *rec, uint32_t len, SplitOu
         pcl_consume(rd, o, buf_start, buf_end, min_off - buf_sum_min, hi, &n_target);
     }
     if (n_target > 1u) o.status = PCL_SPLIT_MULTI_TARGET;                        // fastq.rs:505-506 panics
+}
+
+struct ByteMatcher {            // anchor search on the record bytes (any anchor, any record length)
+    const uint8_t *rec;
+    bool rev;
+    PCL_HD bool operator()(const DElem &el, uint32_t wstart, uint32_t wn, uint32_t *pos, uint32_t *mis) const {
+        return pcl_best_match(rec + wstart, wn, el.seq, el.seq_len, rev, pos, mis);
+    }
+};
+
+PCL_HD void pcl_split(const DRead &rd, const uint8_t *rec, uint32_t len, SplitOut &o) {
+    ByteMatcher m{rec, rd.is_reverse != 0};
+    pcl_split_t(rd, len, o, m);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -598,6 +615,112 @@ PCL_HD uint32_t pcl_correct_one32(const DTable &t, uint32_t key32, uint32_t len,
     if (prob <= 0.0) return PCL_BC_NO_MATCH;
     if (prob >= threshold) { *out_key = best_key; return PCL_BC_CORRECTED; }
     return PCL_BC_LOW_CONF;
+}
+
+// ------------------------------------------------------------------------------------------
+// whole-record 2-bit representation (records of up to 64 bytes): general layouts without byte loops
+// ------------------------------------------------------------------------------------------
+struct RecCodes {
+    uint64_t lo, hi;        // 2-bit code of base i at bits 2i (i < 32: lo, else hi)
+    uint64_t bad_lo, bad_hi;   // bit 2i set: byte i is not a base for barcodes / UMIs (case folded on neg-strand reads)
+    uint64_t sb_lo, sb_hi;     // bit 2i set: byte i is not upper-case ACGT (anchor comparison, seqspec::utils::rev_compl)
+};
+
+// w: n_words 32-bit words of the record (n_words <= 16)
+PCL_HD void pcl_rec_codes(const uint32_t *w, int n_words, bool rev, RecCodes &rc) {
+    rc.lo = rc.hi = rc.bad_lo = rc.bad_hi = rc.sb_lo = rc.sb_hi = 0;
+#ifdef __CUDA_ARCH__
+#pragma unroll
+#endif
+    for (int k = 0; k < 16; ++k) {
+        if (k >= n_words) break;
+        uint32_t bad, sbad;
+        const uint32_t c8 = pcl_word_codes(rev ? (w[k] & 0xDFDFDFDFu) : w[k], &bad);
+        if (rev) { (void)pcl_word_codes(w[k], &sbad); } else sbad = bad;
+        // non-zero byte -> one flag bit per base at the even bit positions of an 8-bit field
+        const uint32_t nb = ((((bad & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | bad) & 0x80808080u) >> 7;
+        const uint32_t ns = ((((sbad & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | sbad) & 0x80808080u) >> 7;
+        const uint64_t b8 = (nb * 0x01041040u) >> 24, s8 = (ns * 0x01041040u) >> 24;
+        const int sh = 8 * (k & 7);
+        if (k < 8) { rc.lo |= (uint64_t)c8 << sh; rc.bad_lo |= b8 << sh; rc.sb_lo |= s8 << sh; }
+        else { rc.hi |= (uint64_t)c8 << sh; rc.bad_hi |= b8 << sh; rc.sb_hi |= s8 << sh; }
+    }
+}
+
+// 2*len bits starting at base `start` of a 128-bit field (len <= 32, start + len <= 64)
+PCL_HD uint64_t pcl_bits128(uint64_t lo, uint64_t hi, uint32_t start, uint32_t len) {
+    const uint32_t bp = 2u * start;
+    uint64_t v;
+    if (bp == 0u) v = lo;
+    else if (bp < 64u) v = (lo >> bp) | (hi << (64u - bp));
+    else v = hi >> (bp - 64u);
+    return len >= 32u ? v : (v & ((1ull << (2u * len)) - 1ull));
+}
+
+PCL_HD uint32_t pcl_popc64(uint64_t x) {
+#ifdef __CUDA_ARCH__
+    return (uint32_t)__popcll(x);
+#else
+    return (uint32_t)__builtin_popcountll(x);
+#endif
+}
+
+PCL_HD uint64_t pcl_brev64(uint64_t x) {
+#ifdef __CUDA_ARCH__
+    return __brevll(x);
+#else
+    return ((uint64_t)pcl_brev32((uint32_t)x) << 32) | pcl_brev32((uint32_t)(x >> 32));
+#endif
+}
+
+// pcl_pack_key on the code representation: key in marker form, *n_invalid = bases that are not bases.
+PCL_HD uint64_t pcl_pack_codes(const RecCodes &rc, uint32_t start, uint32_t len, bool rev, uint32_t *n_invalid) {
+    if (len > PCL_MAX_KEY_LEN) { *n_invalid = len; return 0; }
+    if (len == 0u) { *n_invalid = 0; return 1; }
+    const uint64_t bad = pcl_bits128(rc.bad_lo, rc.bad_hi, start, len);
+    *n_invalid = pcl_popc64(bad);
+    uint64_t f = pcl_bits128(rc.lo, rc.hi, start, len);
+    f &= ~(bad | (bad << 1));                                        // invalid positions contribute 0, like pcl_pack_key
+    const uint64_t mask = (1ull << (2u * len)) - 1ull;
+    uint64_t key;
+    if (rev) {
+        key = (~f) & mask & ~(bad | (bad << 1));                     // reverse complement == complement read big-endian
+    } else {
+        uint64_t r = pcl_brev64(f);
+        r = ((r >> 1) & 0x5555555555555555ull) | ((r & 0x5555555555555555ull) << 1);
+        key = r >> (64u - 2u * len);
+    }
+    return key | (1ull << (2u * len));
+}
+
+// find_best_pattern_match in code space (anchors of <= 32 upper-case ACGT bases)
+struct CodeMatcher {
+    const RecCodes *rc;
+    bool rev;
+    PCL_HD bool operator()(const DElem &el, uint32_t wstart, uint32_t wn, uint32_t *pos, uint32_t *mis) const {
+        const uint32_t m = el.seq_len;
+        if (m == 0u || wn == 0u || m > wn) return false;
+        const uint64_t needle = rev ? el.a_rc : el.a_code;
+        const uint64_t even = m >= 32u ? 0x5555555555555555ull : (0x5555555555555555ull & ((1ull << (2u * m)) - 1ull));
+        uint32_t best = 0xFFFFFFFFu, bpos = 0;
+        for (uint32_t i = 0; i + m <= wn; ++i) {
+            // neg-strand reads search rev_compl(window): haystack position i is the forward position wn - m - i
+            const uint32_t p = wstart + (rev ? wn - m - i : i);
+            const uint64_t x = pcl_bits128(rc->lo, rc->hi, p, m) ^ needle;
+            const uint64_t d = ((x | (x >> 1)) | pcl_bits128(rc->sb_lo, rc->sb_hi, p, m)) & even;
+            const uint32_t c = pcl_popc64(d);
+            if (c < best) { best = c; bpos = i; if (c == 0u) break; }
+        }
+        if (m == 1u && best != 0u) return false;
+        *pos = bpos;
+        *mis = best;
+        return true;
+    }
+};
+
+PCL_HD void pcl_split_codes(const DRead &rd, const RecCodes &rc, uint32_t len, SplitOut &o) {
+    CodeMatcher m{&rc, rd.is_reverse != 0};
+    pcl_split_t(rd, len, o, m);
 }
 
 // Store a key in its device width (see precellar_b200.h).

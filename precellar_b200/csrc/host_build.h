@@ -42,7 +42,7 @@ inline int pcl_build_read(int r, const pcl_read_desc &rd, DRead *out, pcl_read_i
     d.n_elems = rd.n_elems;
     d.is_reverse = rd.is_reverse ? 1 : 0;
     d.max_len = rd.max_len;
-    bool fixed = true, payload = false;
+    bool fixed = true, payload = false, anchors_codable = true;
     uint32_t reach = 0, start = 0;
     for (int e = 0; e < rd.n_elems; ++e) {
         const pcl_elem_desc &el = rd.elems[e];
@@ -60,6 +60,17 @@ inline int pcl_build_read(int r, const pcl_read_desc &rd, DRead *out, pcl_read_i
             uint32_t k = 0;                                   // `mis as f64 <= 0.2 * len as f64` (segment.rs:267)
             while ((double)(k + 1) <= 0.2 * (double)el.seq_len) ++k;
             de.max_mis = (uint8_t)k;
+            // code-space form of the anchor (register-resident general path)
+            bool pure = el.seq_len <= 32;
+            uint64_t ac = 0, arc = 0;
+            for (uint32_t t = 0; t < el.seq_len && pure; ++t) {
+                const uint32_t c = pcl_base_code((uint8_t)el.sequence[t], false);
+                if (c > 3u) { pure = false; break; }
+                ac |= (uint64_t)c << (2u * t);
+                arc |= (uint64_t)(3u - c) << (2u * (el.seq_len - 1u - t));
+            }
+            de.a_code = ac; de.a_rc = arc;
+            if (!pure) anchors_codable = false;
         }
         const bool may_anchor = !fixed && el.is_fixed_seq && fixed_len;   // a variable run precedes it
         if (may_anchor) {
@@ -126,6 +137,7 @@ inline int pcl_build_read(int r, const pcl_read_desc &rd, DRead *out, pcl_read_i
     info.qual_offset = (uint16_t)d.qoff;
     info.qual_stride = (uint16_t)d.qstride;
     d.qual_only = qual_only ? 1 : 0;
+    d.codes_ok = (payload && stride >= 16 && stride <= 64 && anchors_codable) ? 1 : 0;
     info.qual_only = d.qual_only;
     d.fixed_layout = fixed ? 1 : 0;
     d.n_bc = info.n_bc; d.n_umi = info.n_umi; d.has_target = info.has_target; d.needs_payload = payload ? 1 : 0;

@@ -116,6 +116,15 @@ __device__ __forceinline__ void pcl_hist_add(uint32_t *ck, uint32_t *cc, uint32_
     else atomicAdd(&gcounts[slot], 1u);
 }
 
+__device__ __forceinline__ uint4 pcl_ld_stream(const uint4 *p) {
+    uint4 r;
+    asm volatile("ld.global.cs.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    return r;
+}
+
+// kCodes: the record (<= 64 bytes) is converted once to 2-bit codes in registers; anchors are matched and fields
+// are cut in code space (pcl_split_codes / pcl_pack_codes).  Otherwise the record bytes are read on demand.
+template <bool kCodes>
 __global__ void __launch_bounds__(PCL_BLOCK) k_count(const __grid_constant__ CountParams p) {
     __shared__ uint32_t ck[PCL_HCACHE];
     __shared__ uint32_t cc[PCL_HCACHE];
@@ -145,7 +154,21 @@ __global__ void __launch_bounds__(PCL_BLOCK) k_count(const __grid_constant__ Cou
             if (rd.max_len && L > rd.max_len) L = rd.max_len;          // FastqReader::read_record (read.rs:98-103)
             const uint8_t *rec = p.seq + i * (uint64_t)rd.stride;
             SplitOut so;
-            pcl_split(rd, rec, L, so);
+            RecCodes rc;
+            if (kCodes) {
+                uint32_t w[16];
+                const uint4 *r4 = reinterpret_cast<const uint4 *>(rec);
+#pragma unroll
+                for (int v = 0; v < 4; ++v) {
+                    uint4 t = make_uint4(0u, 0u, 0u, 0u);
+                    if ((uint32_t)v * 16u < rd.stride) t = pcl_ld_stream(r4 + v);
+                    w[4 * v] = t.x; w[4 * v + 1] = t.y; w[4 * v + 2] = t.z; w[4 * v + 3] = t.w;
+                }
+                pcl_rec_codes(w, (int)(rd.stride >> 2), rev, rc);
+                pcl_split_codes(rd, rc, L, so);
+            } else {
+                pcl_split(rd, rec, L, so);
+            }
             uint32_t fs = so.status;
             const bool ok = so.status == PCL_SPLIT_OK;
             if (so.status == PCL_SPLIT_ANCHOR_NOT_FOUND || so.status == PCL_SPLIT_PATTERN_MISMATCH) ++n_defect;
@@ -162,7 +185,7 @@ __global__ void __launch_bounds__(PCL_BLOCK) k_count(const __grid_constant__ Cou
                 if (c != PCL_COORD_ABSENT) {
                     const uint32_t start = c >> 16, blen = c & 0xFFFFu;
                     uint32_t ninv, ipos;
-                    key = pcl_pack_key(rec, start, blen, rev, &ninv, &ipos);
+                    key = kCodes ? pcl_pack_codes(rc, start, blen, rev, &ninv) : pcl_pack_key(rec, start, blen, rev, &ninv, &ipos);
                     uint32_t slot = 0xFFFFFFFFu;
                     if (ninv == 0u) slot = pcl_probe(p.tab[j], key, blen);
                     ++n_total[j];                                      // WhitelistBuilder::add (barcode.rs:410-426)
@@ -187,7 +210,8 @@ __global__ void __launch_bounds__(PCL_BLOCK) k_count(const __grid_constant__ Cou
                 uint64_t key = PCL_KEY_ABSENT64;
                 if (c != PCL_COORD_ABSENT) {
                     uint32_t ninv, ipos;
-                    key = pcl_pack_key(rec, c >> 16, c & 0xFFFFu, rev, &ninv, &ipos);
+                    key = kCodes ? pcl_pack_codes(rc, c >> 16, c & 0xFFFFu, rev, &ninv)
+                                 : pcl_pack_key(rec, c >> 16, c & 0xFFFFu, rev, &ninv, &ipos);
                     if (ninv) key = 0;
                 }
                 pcl_store_key(p.umi_key[j], p.umi_key_bytes[j], i, key);
@@ -235,12 +259,6 @@ __global__ void __launch_bounds__(PCL_BLOCK) k_count(const __grid_constant__ Cou
 // One thread per record; the 32 record bytes arrive as two 128-bit streaming loads and stay in registers;
 // SWAR conversion to 2-bit codes; one bucket probe of the 32-bit key table.
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint4 pcl_ld_stream(const uint4 *p) {
-    uint4 r;
-    asm volatile("ld.global.cs.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
-    return r;
-}
-
 __device__ __forceinline__ void pcl_st_stream(uint32_t *p, uint32_t v) { __stcs(p, v); }
 __device__ __forceinline__ void pcl_st_stream(uint16_t *p, uint16_t v) { __stcs(p, v); }
 

@@ -108,7 +108,7 @@ struct pcl_ctx {
     uint64_t prof_n[PCL_K_MAX] = {0};
     uint64_t launches = 0;
     int sm_count = 148;
-    int occ[8] = {1, 1, 1, 1, 1, 1, 1, 1};   // resident CTAs per SM of each kernel (see OCC_*)
+    int occ[12] = {1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1};   // resident CTAs per SM of each kernel (see OCC_*)
     bool force_generic = false;   // PCL_FORCE_GENERIC=1: only the generic kernels (tests compare both paths)
     bool no_neighbour_tables = false;   // PCL_NO_NEIGHBOUR_TABLES=1: 3*L direct probes instead of the 4 neighbourhood tables
 };
@@ -178,7 +178,7 @@ void prof_end(pcl_ctx *ctx, cudaStream_t s) {
     cudaEventRecord(ctx->evs.back().b, s);
 }
 
-enum { OCC_COUNT = 0, OCC_COUNT_FAST, OCC_COUNT_LENONLY, OCC_ENUM, OCC_CORRECT_FAST, OCC_CORRECT, OCC_QC, OCC_GATHER };
+enum { OCC_COUNT = 0, OCC_COUNT_FAST, OCC_COUNT_LENONLY, OCC_ENUM, OCC_CORRECT_FAST, OCC_CORRECT, OCC_QC, OCC_GATHER, OCC_COUNT_CODES };
 
 int grid_for(const pcl_ctx *ctx, uint64_t n_threads_wanted, int blocks_per_sm) {
     uint64_t blocks = (n_threads_wanted + PCL_BLOCK - 1) / PCL_BLOCK;
@@ -247,7 +247,8 @@ int pcl_ctx_create(pcl_ctx **out, int device) {
             if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nblk, fn, PCL_BLOCK, 0) != cudaSuccess || nblk < 1) { cudaGetLastError(); nblk = 1; }
             return nblk;
         };
-        ctx->occ[OCC_COUNT] = occ((const void *)k_count);
+        ctx->occ[OCC_COUNT] = occ((const void *)k_count<false>);
+        ctx->occ[OCC_COUNT_CODES] = occ((const void *)k_count<true>);
         ctx->occ[OCC_COUNT_FAST] = occ((const void *)k_count_fast);
         ctx->occ[OCC_COUNT_LENONLY] = occ((const void *)k_count_lenonly);
         ctx->occ[OCC_ENUM] = occ((const void *)k_enum_all);
@@ -594,7 +595,8 @@ int pcl_count(pcl_ctx *ctx, pcl_chunk *c) {
         // 2.49 ms at three, 125 M records; more waves only add worklist holes for pass 2).
         if (fast) k_count_fast<<<grid_for(ctx, c->n, 3 * ctx->occ[OCC_COUNT_FAST]), PCL_BLOCK, 0, c->stream>>>(p);
         else if (lenonly) k_count_lenonly<<<grid_for(ctx, c->n, ctx->occ[OCC_COUNT_LENONLY]), PCL_BLOCK, 0, c->stream>>>(p);
-        else k_count<<<grid_for(ctx, c->n, 3 * ctx->occ[OCC_COUNT]), PCL_BLOCK, 0, c->stream>>>(p);
+        else if (d.codes_ok && !ctx->force_generic) k_count<true><<<grid_for(ctx, c->n, 3 * ctx->occ[OCC_COUNT_CODES]), PCL_BLOCK, 0, c->stream>>>(p);
+        else k_count<false><<<grid_for(ctx, c->n, 3 * ctx->occ[OCC_COUNT]), PCL_BLOCK, 0, c->stream>>>(p);
         prof_end(ctx, c->stream);
         CU(ctx, cudaGetLastError());
         ctx->qc_reads[r] += c->n;

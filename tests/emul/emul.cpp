@@ -153,7 +153,16 @@ int emu_run(const pcl_read_desc *reads, int n_reads, int n_regions, const uint8_
             if (rd.max_len && L > rd.max_len) L = rd.max_len;
             const uint8_t *rec = io[r].seq ? io[r].seq + i * (uint64_t)rd.stride : nullptr;
             SplitOut so;
-            pcl_split(rd, rec, L, so);
+            RecCodes rc;
+            const bool codes = use_fast && rd.codes_ok;                    // mirrors k_count<true>
+            if (codes) {
+                uint32_t w[16] = {0};
+                memcpy(w, rec, rd.stride);
+                pcl_rec_codes(w, (int)(rd.stride >> 2), rev, rc);
+                pcl_split_codes(rd, rc, L, so);
+            } else {
+                pcl_split(rd, rec, L, so);
+            }
             uint32_t fs = so.status;
             const bool ok = so.status == PCL_SPLIT_OK;
             if (so.status == PCL_SPLIT_ANCHOR_NOT_FOUND || so.status == PCL_SPLIT_PATTERN_MISMATCH) defects_out[r]++;
@@ -167,7 +176,7 @@ int emu_run(const pcl_read_desc *reads, int n_reads, int n_regions, const uint8_
                 uint64_t key = 0;
                 if (c != PCL_COORD_ABSENT) {
                     uint32_t ninv, ipos;
-                    key = pcl_pack_key(rec, c >> 16, c & 0xFFFFu, rev, &ninv, &ipos);
+                    key = codes ? pcl_pack_codes(rc, c >> 16, c & 0xFFFFu, rev, &ninv) : pcl_pack_key(rec, c >> 16, c & 0xFFFFu, rev, &ninv, &ipos);
                     DTable &t = dt[bcr[r][j]];
                     uint32_t slot = 0xFFFFFFFFu;
                     if (ninv == 0) slot = pcl_probe(t, key, c & 0xFFFFu);
@@ -184,7 +193,7 @@ int emu_run(const pcl_read_desc *reads, int n_reads, int n_regions, const uint8_
                 uint64_t key = PCL_KEY_ABSENT64;
                 if (c != PCL_COORD_ABSENT) {
                     uint32_t ninv, ipos;
-                    key = pcl_pack_key(rec, c >> 16, c & 0xFFFFu, rev, &ninv, &ipos);
+                    key = codes ? pcl_pack_codes(rc, c >> 16, c & 0xFFFFu, rev, &ninv) : pcl_pack_key(rec, c >> 16, c & 0xFFFFu, rev, &ninv, &ipos);
                     if (ninv) key = 0;
                 }
                 pcl_store_key(io[r].umi_key[j], in.umi_key_bytes[j], i, key);
