@@ -626,25 +626,38 @@ struct RecCodes {
     uint64_t sb_lo, sb_hi;     // bit 2i set: byte i is not upper-case ACGT (anchor comparison, seqspec::utils::rev_compl)
 };
 
-// w: n_words 32-bit words of the record (n_words <= 16)
-PCL_HD void pcl_rec_codes(const uint32_t *w, int n_words, bool rev, RecCodes &rc) {
-    rc.lo = rc.hi = rc.bad_lo = rc.bad_hi = rc.sb_lo = rc.sb_hi = 0;
+// w: n_words 32-bit words of the record (n_words <= 16).  kRev: neg-strand read (case folding for barcodes / UMIs,
+// a separate strict mask for anchors); forward reads share one mask.
+template <bool kRev>
+PCL_HD void pcl_rec_codes_t(const uint32_t *w, int n_words, RecCodes &rc) {
+    uint32_t c32[4] = {0, 0, 0, 0}, b32[4] = {0, 0, 0, 0}, s32[4] = {0, 0, 0, 0};   // 16 bases per word
 #ifdef __CUDA_ARCH__
 #pragma unroll
 #endif
     for (int k = 0; k < 16; ++k) {
         if (k >= n_words) break;
-        uint32_t bad, sbad;
-        const uint32_t c8 = pcl_word_codes(rev ? (w[k] & 0xDFDFDFDFu) : w[k], &bad);
-        if (rev) { (void)pcl_word_codes(w[k], &sbad); } else sbad = bad;
+        uint32_t bad, sbad = 0;
+        const uint32_t c8 = pcl_word_codes(kRev ? (w[k] & 0xDFDFDFDFu) : w[k], &bad);
         // non-zero byte -> one flag bit per base at the even bit positions of an 8-bit field
         const uint32_t nb = ((((bad & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | bad) & 0x80808080u) >> 7;
-        const uint32_t ns = ((((sbad & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | sbad) & 0x80808080u) >> 7;
-        const uint64_t b8 = (nb * 0x01041040u) >> 24, s8 = (ns * 0x01041040u) >> 24;
-        const int sh = 8 * (k & 7);
-        if (k < 8) { rc.lo |= (uint64_t)c8 << sh; rc.bad_lo |= b8 << sh; rc.sb_lo |= s8 << sh; }
-        else { rc.hi |= (uint64_t)c8 << sh; rc.bad_hi |= b8 << sh; rc.sb_hi |= s8 << sh; }
+        c32[k >> 2] |= c8 << (8 * (k & 3));
+        b32[k >> 2] |= ((nb * 0x01041040u) >> 24) << (8 * (k & 3));
+        if (kRev) {
+            (void)pcl_word_codes(w[k], &sbad);
+            const uint32_t ns = ((((sbad & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | sbad) & 0x80808080u) >> 7;
+            s32[k >> 2] |= ((ns * 0x01041040u) >> 24) << (8 * (k & 3));
+        }
     }
+    rc.lo = ((uint64_t)c32[1] << 32) | c32[0];
+    rc.hi = ((uint64_t)c32[3] << 32) | c32[2];
+    rc.bad_lo = ((uint64_t)b32[1] << 32) | b32[0];
+    rc.bad_hi = ((uint64_t)b32[3] << 32) | b32[2];
+    if (kRev) { rc.sb_lo = ((uint64_t)s32[1] << 32) | s32[0]; rc.sb_hi = ((uint64_t)s32[3] << 32) | s32[2]; }
+    else { rc.sb_lo = rc.bad_lo; rc.sb_hi = rc.bad_hi; }
+}
+
+PCL_HD void pcl_rec_codes(const uint32_t *w, int n_words, bool rev, RecCodes &rc) {
+    if (rev) pcl_rec_codes_t<true>(w, n_words, rc); else pcl_rec_codes_t<false>(w, n_words, rc);
 }
 
 // 2*len bits starting at base `start` of a 128-bit field (len <= 32, start + len <= 64)

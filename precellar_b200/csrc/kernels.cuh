@@ -164,7 +164,9 @@ __global__ void __launch_bounds__(PCL_BLOCK) k_count(const __grid_constant__ Cou
                     if ((uint32_t)v * 16u < rd.stride) t = pcl_ld_stream(r4 + v);
                     w[4 * v] = t.x; w[4 * v + 1] = t.y; w[4 * v + 2] = t.z; w[4 * v + 3] = t.w;
                 }
-                pcl_rec_codes(w, (int)(rd.stride >> 2), rev, rc);
+                // only the words that hold record bytes (bytes past the record end are never addressed by split)
+                const uint32_t nbytes = L < rd.stride ? L : rd.stride;
+                pcl_rec_codes(w, (int)((nbytes + 3u) >> 2), rev, rc);
                 pcl_split_codes(rd, rc, L, so);
             } else {
                 pcl_split(rd, rec, L, so);

@@ -158,7 +158,8 @@ int emu_run(const pcl_read_desc *reads, int n_reads, int n_regions, const uint8_
             if (codes) {
                 uint32_t w[16] = {0};
                 memcpy(w, rec, rd.stride);
-                pcl_rec_codes(w, (int)(rd.stride >> 2), rev, rc);
+                const uint32_t nbytes = L < rd.stride ? L : rd.stride;
+                pcl_rec_codes(w, (int)((nbytes + 3u) >> 2), rev, rc);
                 pcl_split_codes(rd, rc, L, so);
             } else {
                 pcl_split(rd, rec, L, so);

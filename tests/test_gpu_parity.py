@@ -64,7 +64,7 @@ def test_gpu_matches_oracle(layouts, name, mode, monkeypatch):
     monkeypatch.setenv("PCL_NO_NEIGHBOUR_TABLES", "1" if mode.endswith("-direct") else "0")
     mode = mode.split("-")[0]
     layout = layouts[name]
-    rng = np.random.default_rng(abs(hash((name, mode, "gpu"))) % (2 ** 31))
+    rng = np.random.default_rng(U.seed_of(name, mode, "gpu"))
     infos, strides = U.emul_infos(layout)
     n = 3000
     multi = len(layout.region_ids) > 1
@@ -173,7 +173,7 @@ def test_qc_fastq_counters(layouts, name):
     """QcFastq (precellar/src/qc.rs:30-69): bases / Q30 bases / reads per category and per-file defects."""
     from precellar_b200.pipeline import BarcodePipeline, HostBatch
     layout = layouts[name]
-    rng = np.random.default_rng(abs(hash((name, "qc"))) % (2 ** 31))
+    rng = np.random.default_rng(U.seed_of(name, "qc"))
     multi = len(layout.region_ids) > 1
     pipe = BarcodePipeline(layout, qc=True)
     try:
@@ -286,7 +286,7 @@ def test_gpu_dense_and_boundary_whitelists(name, direct, monkeypatch):
     monkeypatch.setenv("PCL_FORCE_GENERIC", "0")
     monkeypatch.setenv("PCL_NO_NEIGHBOUR_TABLES", "1" if direct else "0")
     layout = _dense_layouts(np.random.default_rng(77))[name]
-    rng = np.random.default_rng(abs(hash((name, "dense-gpu"))) % (2 ** 31))
+    rng = np.random.default_rng(U.seed_of(name, "dense-gpu"))
     infos, strides = U.emul_infos(layout)
     full = U.gen_reads(rng, layout, 6000, strides, p_sub=0.05, p_n=0.02, hot=10 ** 6)
     ginfos, results, counts, defects, _ = run_gpu(layout, U.narrow(full, strides, infos), threshold=0.6, n_chunks=2)

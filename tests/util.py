@@ -8,6 +8,7 @@ import subprocess
 from typing import Dict, List, Optional, Sequence
 
 import numpy as np
+import zlib
 
 from oracle import pyoracle as O
 from precellar_b200 import _ffi
@@ -378,3 +379,8 @@ def compare_with_oracle(layout: CompiledLayout, infos, batches, results: Sequenc
             mine = render(layout, batches, g, i, correct=correct)
             assert mine == ores.lines[i], f"record {i}:\n  got      {mine!r}\n  expected {ores.lines[i]!r}"
     return g
+
+
+def seed_of(*parts):
+    """Stable per-case RNG seed (str hashes differ between interpreter runs)."""
+    return zlib.crc32("/".join(str(p) for p in parts).encode()) & 0x7FFFFFFF
