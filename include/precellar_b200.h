@@ -259,12 +259,41 @@ int pcl_make_fastq_batch(pcl_ctx *ctx, const pcl_host_read *reads, uint64_t n, i
                          uint8_t *r1_out, uint64_t r1_cap, uint64_t *r1_used, uint8_t *r2_out, uint64_t r2_cap,
                          uint64_t *r2_used, uint64_t *n_written);
 
+/* ---- device ingest: raw FASTQ text -> SoA planes, parsed on the GPU ------------------------------------
+ * Alternative to pcl_fastq_read + pcl_chunk_upload for pass 1: the host only moves
+ * uncompressed text; no host core touches individual records.  Replaces FastqReader::read_record
+ * (seqspec/src/read.rs:137-155) and the name check of BatchedFqReader::next (precellar/src/align/fastq.rs:417-431)
+ * for that pass.  Dialect: exactly four '\n'-terminated lines per record, "\r\n" tolerated, no blank lines
+ * between records (pcl_fastq_read skips those; here they are reported as a malformed record).
+ *
+ * Per chunk and read file:
+ *   pcl_text_scan(chunk, slot, text, n)   copy a block of text that STARTS AT A RECORD BOUNDARY to the device and
+ *                                         index its line ends (asynchronous; text must stay valid until
+ *                                         pcl_text_lines returns; n < 4 GiB - 4 KiB)
+ *   pcl_text_lines(chunk, slot, &lines)   number of complete lines indexed (blocks).  lines / 4 complete records are
+ *                                         available; the caller picks n_records <= min over the read files and
+ *                                         calls pcl_chunk_reset(chunk, n_records)
+ *   pcl_text_fill(chunk, slot, &used)     fill the slot's seq / qual / len planes with the first n_records records
+ *                                         (same bytes as pcl_fastq_read would produce, incl. the quality window and
+ *                                         the 'N' / '!' padding); *used = bytes of text consumed, the remainder is
+ *                                         the head of the caller's next block.  PCL_ERR_INPUT for a malformed record.
+ *   pcl_text_names_check(chunk, &bad)     first group whose read names differ between the text-filled read files
+ *                                         (names compared after stripping a trailing /1 or /2), or -1
+ *   pcl_text_line_ends(chunk, slot, out, n) byte offset of the end of each of the first n lines (for writers that
+ *                                         slice names / records out of the host copy of the text)              */
+int pcl_text_scan(pcl_chunk *chunk, int read_slot, const uint8_t *text, uint64_t n_bytes);
+int pcl_text_lines(pcl_chunk *chunk, int read_slot, uint64_t *n_lines);
+int pcl_text_fill(pcl_chunk *chunk, int read_slot, uint64_t *consumed);
+int pcl_text_names_check(pcl_chunk *chunk, int64_t *first_bad);
+int pcl_text_line_ends(pcl_chunk *chunk, int read_slot, uint32_t *out, uint64_t n_lines);
+
 /* ---- pinned host memory ------------------------------------------------------------------- */
 void *pcl_host_alloc(uint64_t bytes);
 void pcl_host_free(void *p);
 
 /* ---- instrumentation (used by bench.py; CUDA events on the launching stream) --------------- */
-enum { PCL_K_COUNT = 0, PCL_K_CORRECT = 1, PCL_K_COUNT_LENONLY = 2, PCL_K_ENUM = 3, PCL_K_QC = 4, PCL_K_MAX = 6 };
+enum { PCL_K_COUNT = 0, PCL_K_CORRECT = 1, PCL_K_COUNT_LENONLY = 2, PCL_K_ENUM = 3, PCL_K_QC = 4, PCL_K_TEXT_INDEX = 5,
+       PCL_K_TEXT_FILL = 6, PCL_K_MAX = 8 };
 int pcl_profile_enable(pcl_ctx *ctx, int on);                    /* bracket every kernel with events */
 /* accumulated ms and launches of kernel k since the last pcl_profile_reset (syncs the ctx) */
 int pcl_profile_get(pcl_ctx *ctx, int k, double *ms, uint64_t *launches);

@@ -76,6 +76,7 @@ SYMBOLS = [
     "pcl_qc_enable", "pcl_qc_accumulate", "pcl_qc_fetch_categories",
     "pcl_fastq_open", "pcl_fastq_close", "pcl_fastq_error", "pcl_fastq_read", "pcl_chunk_fetch_async",
     "pcl_make_fastq_batch",
+    "pcl_text_scan", "pcl_text_lines", "pcl_text_fill", "pcl_text_names_check", "pcl_text_line_ends",
 ]
 
 _lib = None
@@ -133,6 +134,11 @@ def lib() -> C.CDLL:
         "pcl_qc_fetch_categories": (i32, [vp, vp]),
         "pcl_make_fastq_batch": (i32, [vp, C.POINTER(HostRead), u64, i32, i32, vp, u64, C.POINTER(u64), vp, u64,
                                        C.POINTER(u64), C.POINTER(u64)]),
+        "pcl_text_scan": (i32, [vp, i32, vp, u64]),
+        "pcl_text_lines": (i32, [vp, i32, C.POINTER(u64)]),
+        "pcl_text_fill": (i32, [vp, i32, C.POINTER(u64)]),
+        "pcl_text_names_check": (i32, [vp, C.POINTER(C.c_int64)]),
+        "pcl_text_line_ends": (i32, [vp, i32, vp, u64]),
         "pcl_fastq_open": (i32, [C.POINTER(C.c_char_p), i32, C.POINTER(vp)]),
         "pcl_fastq_close": (None, [vp]),
         "pcl_fastq_error": (C.c_char_p, [vp]),

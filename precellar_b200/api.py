@@ -79,9 +79,12 @@ def _as_assays(assay) -> List[Assay]:
 class FastqProcessor:
     """Barcode counting, correction and annotation of the FASTQ files named by one or more assays."""
 
-    def __init__(self, assay, device: int = 0):
+    def __init__(self, assay, device: int = 0, device_parse: bool = False):
         self.assays = _as_assays(assay)
         self.device = device
+        # pass 1 reads the FASTQ text on the device (textingest.TextGroupReader) instead of the host record reader;
+        # stricter dialect: no blank lines between records
+        self.device_parse = bool(device_parse)
         self.current_modality: Optional[str] = None
         self.barcode_correct_prob = 0.975        # fastq.rs:39
         self.mismatch_in_barcode = 1             # fastq.rs:40 (no setter in the reference either)
@@ -172,9 +175,27 @@ class FastqProcessor:
         # pass 1 (BarcodeAnalyzer::new): every batch is uploaded, counted and kept resident on the device
         chunks: List[Chunk] = []
         sizes: List[int] = []
+        if self.device_parse:
+            from .textingest import TextGroupReader
+            trdr = TextGroupReader(pipe, files, per_chunk, [2 * (p.max_len or 150) + 80 for p in layout.reads])
+            try:
+                while True:
+                    ch = pipe.new_chunk(per_chunk)
+                    n = trdr.next_into(ch)
+                    if n == 0:
+                        ch.close()
+                        pipe.chunks.remove(ch)
+                        break
+                    pipe.count(ch)
+                    if self.compute_qc:
+                        pipe.qc_accumulate(ch)
+                    chunks.append(ch)
+                    sizes.append(n)
+            finally:
+                trdr.close()
         rdr = GroupReader(files, strides, qonly, keep_text=False, qual_windows=[pipe.qual_window(r) for r in range(n_reads)])
         try:
-            while True:
+            while not self.device_parse:
                 got = rdr.next(per_chunk)
                 if got is None:
                     break

@@ -6,6 +6,7 @@
 #include <cuda_runtime.h>
 #include <dlfcn.h>
 
+#include <algorithm>
 #include <cfloat>
 #include <cmath>
 #include <cstdarg>
@@ -18,6 +19,7 @@
 
 #include "host_build.h"
 #include "kernels.cuh"
+#include "textparse.cuh"
 
 // ------------------------------------------------------------------------------------------
 // NCCL through dlopen: the library has no link-time dependency on libnccl, and inside a process
@@ -82,6 +84,15 @@ struct EvPair { cudaEvent_t a, b; int k; };
 
 struct pcl_chunk;
 
+// Staging of one read file's text block (pcl_text_*): shared by the chunks of a ctx, one block per read file in
+// flight (pcl_text_fill blocks, so the next pcl_text_scan of the same read file finds it free).
+struct TextStage {
+    uint8_t *d_text = nullptr;
+    uint32_t *d_nl = nullptr, *d_tile_cnt = nullptr, *d_tile_off = nullptr;
+    uint64_t text_cap = 0, nl_cap = 0, text_bytes = 0;
+    pcl_chunk *owner = nullptr;
+};
+
 struct pcl_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
@@ -98,6 +109,7 @@ struct pcl_ctx {
     bool qc_enabled = false;
     uint64_t qc_reads[PCL_MAX_READS] = {0};
     std::vector<pcl_chunk *> chunks;
+    TextStage text[PCL_MAX_READS];
     // nccl
     NcclComm comm = nullptr;
     int nranks = 1, rank = 0;
@@ -125,6 +137,12 @@ struct ReadBuf {
     unsigned long long *worklist = nullptr;
     unsigned long long *wl_count = nullptr;
     bool filled = false;
+    // device-side text parse (pcl_text_*): name hashes and the small result words of this chunk's parse
+    uint64_t *d_hash = nullptr;
+    unsigned long long *d_tmeta = nullptr;    // device: [0] newline total, [1] first bad record << 8 | code
+    unsigned long long *h_tmeta = nullptr;    // pinned: [0] total, [1] err, [2] end of the last consumed line
+    uint64_t text_lines = 0;
+    bool text_scanned = false, text_filled = false;
 };
 
 struct pcl_chunk {
@@ -276,6 +294,7 @@ int pcl_ctx_destroy(pcl_ctx *ctx) {
     cudaDeviceSynchronize();
     while (!ctx->chunks.empty()) pcl_chunk_destroy(ctx->chunks.back());
     for (Table &t : ctx->tables) table_free(t);
+    for (TextStage &t : ctx->text) { cudaFree(t.d_text); cudaFree(t.d_nl); cudaFree(t.d_tile_cnt); cudaFree(t.d_tile_off); }
     for (EvPair &p : ctx->evs) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
     if (ctx->comm && nccl().ok) nccl().CommDestroy(ctx->comm);
     if (ctx->d_lut) cudaFree(ctx->d_lut);
@@ -410,6 +429,11 @@ uint64_t pcl_whitelist_size(const pcl_ctx *ctx, int region_slot) {
 // ------------------------------------------------------------------------------------------
 // chunks
 // ------------------------------------------------------------------------------------------
+static void stage_free(TextStage &t) {
+    cudaFree(t.d_text); cudaFree(t.d_nl); cudaFree(t.d_tile_cnt); cudaFree(t.d_tile_off);
+    t = TextStage();
+}
+
 static int chunk_alloc(pcl_chunk *c, void **p, size_t bytes) {
     if (bytes == 0) bytes = 16;
     cudaError_t e = cudaMalloc(p, bytes);
@@ -476,6 +500,12 @@ int pcl_chunk_destroy(pcl_chunk *c) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(c->stream);
     for (void *p : c->allocs) cudaFree(p);
+    for (int r = 0; r < PCL_MAX_READS; ++r) {
+        ReadBuf &b = c->rb[r];
+        cudaFree(b.d_hash); cudaFree(b.d_tmeta);
+        if (b.h_tmeta) cudaFreeHost(b.h_tmeta);
+        if (ctx->text[r].owner == c) ctx->text[r].owner = nullptr;
+    }
     cudaEventDestroy(c->ev); cudaEventDestroy(c->t0); cudaEventDestroy(c->t1);
     cudaStreamDestroy(c->stream);
     for (size_t i = 0; i < ctx->chunks.size(); ++i)
@@ -488,7 +518,7 @@ int pcl_chunk_reset(pcl_chunk *c, uint64_t n_records) {
     if (!c) return PCL_ERR_ARG;
     if (n_records > c->cap) return fail(c->ctx, PCL_ERR_ARG, "n_records %llu exceeds chunk capacity %llu", (unsigned long long)n_records, (unsigned long long)c->cap);
     c->n = n_records;
-    for (int r = 0; r < c->ctx->n_reads; ++r) c->rb[r].filled = false;
+    for (int r = 0; r < c->ctx->n_reads; ++r) c->rb[r].filled = c->rb[r].text_filled = false;
     return PCL_OK;
 }
 
@@ -526,6 +556,166 @@ int pcl_chunk_device_ptrs(pcl_chunk *c, int read_slot, void **seq, void **qual, 
 }
 
 void *pcl_chunk_stream(pcl_chunk *c) { return c ? (void *)c->stream : nullptr; }
+
+// ------------------------------------------------------------------------------------------
+// device-side FASTQ text parse (textparse.cuh)
+
+static int text_reserve(pcl_chunk *c, ReadBuf &b, TextStage &t, uint64_t n_bytes) {
+    pcl_ctx *ctx = c->ctx;
+    if (!b.d_tmeta) {
+        CU(ctx, cudaMalloc((void **)&b.d_tmeta, 16));
+        CU(ctx, cudaMallocHost((void **)&b.h_tmeta, 32));
+        CU(ctx, cudaMalloc((void **)&b.d_hash, c->cap * 8 + 16));
+    }
+    if (n_bytes + 16 <= t.text_cap) return PCL_OK;
+    if (t.owner) CU(ctx, cudaStreamSynchronize(t.owner->stream));
+    stage_free(t);
+    const uint64_t cap = ((n_bytes + n_bytes / 8 + 16 + 4095) / 4096) * 4096;      // some head room: blocks vary a little
+    const uint64_t tiles = cap / PCL_TEXT_TILE + 1;
+    // one index entry per 8 bytes of text: a record needs >= 8 bytes for its four lines, real data ~30 per line;
+    // denser input is consumed in several calls (the index is simply cut off at nl_cap)
+    const uint64_t nl_cap = cap / 8 + 16;
+    cudaError_t e = cudaMalloc((void **)&t.d_text, cap);
+    if (e == cudaSuccess) e = cudaMalloc((void **)&t.d_nl, nl_cap * 4);
+    if (e == cudaSuccess) e = cudaMalloc((void **)&t.d_tile_cnt, tiles * 4);
+    if (e == cudaSuccess) e = cudaMalloc((void **)&t.d_tile_off, tiles * 4);
+    if (e != cudaSuccess) {
+        stage_free(t);
+        return fail(ctx, e == cudaErrorMemoryAllocation ? PCL_ERR_NOMEM : PCL_ERR_CUDA, "text staging (%llu bytes): %s",
+                    (unsigned long long)cap, cudaGetErrorString(e));
+    }
+    t.text_cap = cap;
+    t.nl_cap = nl_cap;
+    return PCL_OK;
+}
+
+int pcl_text_scan(pcl_chunk *c, int read_slot, const uint8_t *text, uint64_t n_bytes) {
+    if (!c) return PCL_ERR_ARG;
+    pcl_ctx *ctx = c->ctx;
+    if (read_slot < 0 || read_slot >= ctx->n_reads) return fail(ctx, PCL_ERR_ARG, "bad read_slot");
+    if (!text && n_bytes) return fail(ctx, PCL_ERR_ARG, "text is NULL");
+    if (n_bytes >= (1ull << 32) - 4096) return fail(ctx, PCL_ERR_ARG, "a text block must be smaller than 4 GiB");
+    if (int r = bind(ctx)) return r;
+    ReadBuf &b = c->rb[read_slot];
+    TextStage &t = ctx->text[read_slot];
+    if (int r = text_reserve(c, b, t, n_bytes)) return r;
+    cudaStream_t s = c->stream;
+    // the previous user of the staging buffers has finished its fill (pcl_text_fill blocks) unless it never filled
+    if (t.owner && t.owner != c) { CU(ctx, cudaStreamSynchronize(t.owner->stream)); t.owner->rb[read_slot].text_scanned = false; }
+    t.owner = c;
+    if (n_bytes) CU(ctx, cudaMemcpyAsync(t.d_text, text, n_bytes, cudaMemcpyHostToDevice, s));
+    CU(ctx, cudaMemsetAsync(t.d_text + n_bytes, 0, 16, s));
+    const uint64_t n_tiles = (n_bytes + PCL_TEXT_TILE - 1) / PCL_TEXT_TILE;
+    const int grid = (int)std::min<uint64_t>(std::max<uint64_t>(n_tiles, 1), (uint64_t)ctx->sm_count * 8);
+    prof_begin(ctx, s, PCL_K_TEXT_INDEX);
+    k_text_count<<<grid, PCL_TEXT_BLOCK, 0, s>>>(t.d_text, n_bytes, n_tiles, t.d_tile_cnt);
+    k_text_scan<<<1, 1024, 0, s>>>(t.d_tile_cnt, n_tiles, t.d_tile_off, b.d_tmeta);
+    k_text_index<<<grid, PCL_TEXT_BLOCK, 0, s>>>(t.d_text, n_bytes, n_tiles, t.d_tile_off, t.d_nl, t.nl_cap);
+    prof_end(ctx, s);
+    ctx->launches += 2;
+    CU(ctx, cudaGetLastError());
+    CU(ctx, cudaMemcpyAsync(b.h_tmeta, b.d_tmeta, 8, cudaMemcpyDeviceToHost, s));
+    t.text_bytes = n_bytes;
+    b.text_scanned = true;
+    b.text_lines = ~0ull;
+    return PCL_OK;
+}
+
+int pcl_text_lines(pcl_chunk *c, int read_slot, uint64_t *n_lines) {
+    if (!c) return PCL_ERR_ARG;
+    pcl_ctx *ctx = c->ctx;
+    if (read_slot < 0 || read_slot >= ctx->n_reads || !n_lines) return fail(ctx, PCL_ERR_ARG, "bad argument");
+    ReadBuf &b = c->rb[read_slot];
+    const TextStage &t = ctx->text[read_slot];
+    if (!b.text_scanned || t.owner != c) return fail(ctx, PCL_ERR_ARG, "pcl_text_scan must be called first (one text block per read file in flight)");
+    if (int r = bind(ctx)) return r;
+    if (b.text_lines == ~0ull) {
+        CU(ctx, cudaStreamSynchronize(c->stream));
+        b.text_lines = b.h_tmeta[0] < t.nl_cap ? b.h_tmeta[0] : t.nl_cap;
+    }
+    *n_lines = b.text_lines;
+    return PCL_OK;
+}
+
+int pcl_text_fill(pcl_chunk *c, int read_slot, uint64_t *consumed) {
+    if (!c) return PCL_ERR_ARG;
+    pcl_ctx *ctx = c->ctx;
+    if (read_slot < 0 || read_slot >= ctx->n_reads) return fail(ctx, PCL_ERR_ARG, "bad read_slot");
+    ReadBuf &b = c->rb[read_slot];
+    uint64_t lines = 0;
+    if (int r = pcl_text_lines(c, read_slot, &lines)) return r;
+    if (4 * c->n > lines) return fail(ctx, PCL_ERR_ARG, "chunk holds %llu records but the text block has only %llu complete lines",
+                                      (unsigned long long)c->n, (unsigned long long)lines);
+    const DRead &d = ctx->dreads[read_slot];
+    const TextStage &t = ctx->text[read_slot];
+    cudaStream_t s = c->stream;
+    b.h_tmeta[2] = 0;
+    if (c->n) {
+        TextFillParams p;
+        p.text = t.d_text; p.nl = t.d_nl; p.n = c->n;
+        p.stride = d.stride; p.qoff = d.qoff; p.qstride = d.qstride;
+        p.seq = d.needs_payload ? b.seq : nullptr;
+        p.qual = ((d.needs_payload || d.qual_only) && d.qstride) ? b.qual : nullptr;
+        p.len = b.len; p.name_hash = b.d_hash; p.err = b.d_tmeta + 1;
+        CU(ctx, cudaMemsetAsync(b.d_tmeta + 1, 0xFF, 8, s));
+        prof_begin(ctx, s, PCL_K_TEXT_FILL);
+        k_text_fill<<<grid_for(ctx, c->n, 8), PCL_TEXT_BLOCK, 0, s>>>(p);
+        prof_end(ctx, s);
+        CU(ctx, cudaGetLastError());
+        CU(ctx, cudaMemcpyAsync(b.h_tmeta + 1, b.d_tmeta + 1, 8, cudaMemcpyDeviceToHost, s));
+        CU(ctx, cudaMemcpyAsync(b.h_tmeta + 2, t.d_nl + (4 * c->n - 1), 4, cudaMemcpyDeviceToHost, s));
+        CU(ctx, cudaStreamSynchronize(s));
+        if (b.h_tmeta[1] != ~0ull) {
+            static const char *const what[] = {"", "does not start with '@'", "missing '+' line", "sequence and quality lengths differ"};
+            const unsigned code = (unsigned)(b.h_tmeta[1] & 0xFF);
+            return fail(ctx, PCL_ERR_INPUT, "FASTQ record %llu of the text block (read %d): %s", (unsigned long long)(b.h_tmeta[1] >> 8),
+                        read_slot, what[code < 4 ? code : 0]);
+        }
+    }
+    if (consumed) *consumed = c->n ? (b.h_tmeta[2] & 0xFFFFFFFFull) + 1 : 0;
+    b.filled = true;
+    b.text_filled = true;
+    return PCL_OK;
+}
+
+int pcl_text_names_check(pcl_chunk *c, int64_t *first_bad) {
+    if (!c || !first_bad) return PCL_ERR_ARG;
+    pcl_ctx *ctx = c->ctx;
+    if (int r = bind(ctx)) return r;
+    NamesCheckParams p;
+    p.n_reads = 0;
+    p.n = c->n;
+    ReadBuf *first = nullptr;
+    for (int r = 0; r < ctx->n_reads; ++r)
+        if (c->rb[r].text_filled) { if (!first) first = &c->rb[r]; p.hash[p.n_reads++] = c->rb[r].d_hash; }
+    *first_bad = -1;
+    if (p.n_reads < 2 || c->n == 0) return PCL_OK;
+    p.bad = first->d_tmeta + 1;
+    cudaStream_t s = c->stream;
+    CU(ctx, cudaMemsetAsync(p.bad, 0xFF, 8, s));
+    prof_begin(ctx, s, PCL_K_TEXT_FILL);
+    k_names_check<<<grid_for(ctx, c->n, 8), PCL_TEXT_BLOCK, 0, s>>>(p);
+    prof_end(ctx, s);
+    CU(ctx, cudaGetLastError());
+    CU(ctx, cudaMemcpyAsync(first->h_tmeta + 1, p.bad, 8, cudaMemcpyDeviceToHost, s));
+    CU(ctx, cudaStreamSynchronize(s));
+    if (first->h_tmeta[1] != ~0ull) *first_bad = (int64_t)first->h_tmeta[1];
+    return PCL_OK;
+}
+
+int pcl_text_line_ends(pcl_chunk *c, int read_slot, uint32_t *out, uint64_t n_lines) {
+    if (!c) return PCL_ERR_ARG;
+    pcl_ctx *ctx = c->ctx;
+    if (read_slot < 0 || read_slot >= ctx->n_reads || (!out && n_lines)) return fail(ctx, PCL_ERR_ARG, "bad argument");
+    uint64_t lines = 0;
+    if (int r = pcl_text_lines(c, read_slot, &lines)) return r;
+    if (n_lines > lines) return fail(ctx, PCL_ERR_ARG, "only %llu lines are indexed", (unsigned long long)lines);
+    if (n_lines) {
+        CU(ctx, cudaMemcpyAsync(out, ctx->text[read_slot].d_nl, n_lines * 4, cudaMemcpyDeviceToHost, c->stream));
+        CU(ctx, cudaStreamSynchronize(c->stream));
+    }
+    return PCL_OK;
+}
 
 // ------------------------------------------------------------------------------------------
 // stages

@@ -73,6 +73,35 @@ class Chunk:
         self._keep.append((batch, length))
         check(self.pipe.ctx, lib().pcl_chunk_upload(self.h, read_slot, sp, qp, length.ctypes.data))
 
+    # -- device-side FASTQ parse (pcl_text_*) ----------------------------------------------------------
+    def text_scan(self, read_slot: int, text: np.ndarray, n_bytes: Optional[int] = None) -> None:
+        """Copy a block of uncompressed FASTQ text (uint8, starting at a record boundary) to the device and index
+        its lines.  Asynchronous: ``text`` must stay untouched until ``text_lines`` returns."""
+        assert text.dtype == np.uint8 and text.flags.c_contiguous
+        n = len(text) if n_bytes is None else int(n_bytes)
+        check(self.pipe.ctx, lib().pcl_text_scan(self.h, read_slot, text.ctypes.data if n else None, n))
+
+    def text_lines(self, read_slot: int) -> int:
+        v = C.c_uint64()
+        check(self.pipe.ctx, lib().pcl_text_lines(self.h, read_slot, C.byref(v)))
+        return v.value
+
+    def text_fill(self, read_slot: int) -> int:
+        """Fill the read's planes with the first ``n`` records of the scanned text; returns the bytes consumed."""
+        v = C.c_uint64()
+        check(self.pipe.ctx, lib().pcl_text_fill(self.h, read_slot, C.byref(v)))
+        return v.value
+
+    def text_names_check(self) -> int:
+        v = C.c_int64()
+        check(self.pipe.ctx, lib().pcl_text_names_check(self.h, C.byref(v)))
+        return v.value
+
+    def text_line_ends(self, read_slot: int, n_lines: int) -> np.ndarray:
+        out = np.empty(int(n_lines), np.uint32)
+        check(self.pipe.ctx, lib().pcl_text_line_ends(self.h, read_slot, out.ctypes.data, int(n_lines)))
+        return out
+
     def device_ptrs(self, read_slot: int):
         s, q, l = C.c_void_p(), C.c_void_p(), C.c_void_p()
         check(self.pipe.ctx, lib().pcl_chunk_device_ptrs(self.h, read_slot, C.byref(s), C.byref(q), C.byref(l)))

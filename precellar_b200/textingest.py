@@ -1,0 +1,213 @@
+"""Device ingest: raw FASTQ text -> chunk planes, parsed on the GPU (csrc/textparse.cuh).
+
+The host side only moves bytes: the (decompressed) text of every read file is streamed into pinned blocks, the
+device indexes the lines and fills the SoA planes (``pcl_text_scan`` / ``pcl_text_fill``).  What
+``BatchedFqReader::next`` enforces (precellar/src/align/fastq.rs:400-448: the same number of records in every
+file, equal names after stripping /1 /2) is enforced here too, the names by a device-side hash compare.
+
+Blocks are double-buffered: while the device parses block k, a worker thread already reads block k+1 behind a
+reserved gap, into which the unconsumed tail of block k is copied once it is known.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import gzip
+from concurrent.futures import ThreadPoolExecutor
+from typing import List, Optional, Sequence
+
+import numpy as np
+
+from . import _ffi
+from ._ffi import lib
+from .pipeline import BarcodePipeline, Chunk
+
+
+def _pinned(nbytes: int) -> np.ndarray:
+    p = lib().pcl_host_alloc(int(nbytes))
+    if not p:
+        raise MemoryError(f"pinned allocation of {nbytes} bytes failed")
+    return np.frombuffer((C.c_uint8 * int(nbytes)).from_address(p), dtype=np.uint8), p
+
+
+def _open_raw(path: str):
+    """open_file (seqspec/src/utils.rs:44-56): gzip by magic, zstd by extension, else plain."""
+    with open(path, "rb") as f:
+        magic = f.read(2)
+    if magic == b"\x1f\x8b":
+        return gzip.open(path, "rb")
+    if path.endswith(".zst"):
+        import io
+        from . import _zstd
+        return io.BytesIO(_zstd.decompress_file(path))
+    return open(path, "rb", buffering=0)
+
+
+class TextSource:
+    """The concatenated, decompressed bytes of the files of one read, as a sliding block in pinned memory."""
+
+    def __init__(self, paths: Sequence[str], block_bytes: int):
+        if not paths:
+            raise _ffi.PclError(_ffi.PCL_ERR_INPUT, "no FASTQ files")
+        self.paths = list(paths)
+        self.next_path = 0
+        self.fh = None
+        self.last_byte = 0x0A
+        self.eof = False
+        self.cap = int(block_bytes)
+        self._alloc(2 * self.cap)
+        self.cur = 0
+        self.start = self.end = self.reserve
+        self.pending = None
+
+    def _alloc(self, size: int) -> None:
+        self.size = int(size)
+        self.reserve = self.size // 2
+        self.bufs, self.ptrs = [], []
+        for _ in range(2):
+            a, p = _pinned(self.size)
+            self.bufs.append(a)
+            self.ptrs.append(p)
+
+    def close(self) -> None:
+        if self.pending is not None:
+            try:
+                self.pending.result()
+            except Exception:
+                pass
+            self.pending = None
+        if self.fh is not None:
+            self.fh.close()
+            self.fh = None
+        for p in self.ptrs:
+            lib().pcl_host_free(p)
+        self.ptrs, self.bufs = [], []
+
+    def _read_into(self, which: int, offset: int, want: int) -> int:
+        """Read up to `want` bytes into bufs[which][offset:]; a file that does not end in a newline gets one, so the
+        next file of the read starts on its own line (Read::open chains the files, read.rs:98-108)."""
+        mv = memoryview(self.bufs[which])
+        got = 0
+        while got < want and not self.eof:
+            if self.fh is None:
+                if self.next_path >= len(self.paths):
+                    self.eof = True
+                    break
+                self.fh = _open_raw(self.paths[self.next_path])
+                self.next_path += 1
+            n = self.fh.readinto(mv[offset + got:offset + want])
+            if not n:
+                self.fh.close()
+                self.fh = None
+                if self.last_byte != 0x0A:
+                    mv[offset + got] = 0x0A
+                    got += 1
+                    self.last_byte = 0x0A
+                continue
+            got += n
+            self.last_byte = mv[offset + got - 1]
+        return got
+
+    def block(self) -> np.ndarray:
+        return self.bufs[self.cur][self.start:self.end]
+
+    def prefetch(self, pool: ThreadPoolExecutor, want: int) -> None:
+        """Start reading the next block into the other buffer, behind the gap kept for the tail of this one."""
+        assert self.pending is None
+        want = max(0, min(int(want), self.size - self.reserve))
+        self.pending = pool.submit(self._read_into, 1 - self.cur, self.reserve, want)
+
+    def advance(self, used: int) -> None:
+        """Drop `used` bytes from the front of the block and append what the prefetch read."""
+        got = self.pending.result() if self.pending is not None else 0
+        self.pending = None
+        cur, other = self.bufs[self.cur], self.bufs[1 - self.cur]
+        lo = self.start + int(used)
+        tail = self.end - lo
+        if tail <= self.reserve:
+            other[self.reserve - tail:self.reserve] = cur[lo:self.end]
+            self.start, self.end = self.reserve - tail, self.reserve + got
+            self.cur = 1 - self.cur
+            return
+        # this read is far ahead of the others: rebuild the block at the front of a (possibly larger) buffer
+        need = tail + got
+        fresh = np.concatenate([cur[lo:self.end], other[self.reserve:self.reserve + got]])
+        if need > self.size - self.size // 2:
+            old = self.ptrs
+            self._alloc(4 * max(need, self.cap))
+            for p in old:
+                lib().pcl_host_free(p)
+            self.cur = 0
+        else:
+            self.cur = 1 - self.cur
+        self.bufs[self.cur][self.reserve - 0:self.reserve + need] = fresh
+        self.start, self.end = self.reserve, self.reserve + need
+
+
+class TextGroupReader:
+    """Fills chunks of a pipeline from the FASTQ files of a read-group, one record per file per group."""
+
+    def __init__(self, pipe: BarcodePipeline, files_per_read: Sequence[Sequence[str]], records_per_chunk: int,
+                 bytes_per_record: Optional[Sequence[int]] = None):
+        self.pipe = pipe
+        self.n_reads = len(files_per_read)
+        self.target = int(records_per_chunk)
+        guess = list(bytes_per_record) if bytes_per_record is not None else [400] * self.n_reads
+        self.bpr = [float(g) for g in guess]
+        self.pool = ThreadPoolExecutor(max_workers=max(1, self.n_reads))
+        self.sources = [TextSource(f, int(self.target * b * 1.25) + (1 << 16)) for f, b in zip(files_per_read, self.bpr)]
+        self.first = True
+        self.records = 0
+
+    def close(self) -> None:
+        for s in self.sources:
+            s.close()
+        self.pool.shutdown(wait=True)
+
+    def _want(self, r: int, blocks_ahead: int = 1) -> int:
+        """Bytes to read so that, after `blocks_ahead - 1` chunks were cut off the front, a full chunk is buffered."""
+        have = self.sources[r].end - self.sources[r].start
+        per = self.target * self.bpr[r]
+        return max(0, int(per * (blocks_ahead + 0.03)) + 4096 - have)
+
+    def next_into(self, chunk: Chunk) -> int:
+        """Parse the next records into `chunk` (at most its capacity / the reader's target); 0 at the end of input."""
+        cap = min(chunk.capacity, self.target)
+        if self.first:                                   # nothing read yet: fetch the first blocks synchronously
+            for r, s in enumerate(self.sources):
+                s.prefetch(self.pool, self._want(r))
+            for s in self.sources:
+                s.advance(0)
+            self.first = False
+        grow = 1
+        while True:
+            blocks = [s.block() for s in self.sources]
+            for r, s in enumerate(self.sources):
+                if s.pending is None:
+                    s.prefetch(self.pool, self._want(r, 2) if grow == 1 else grow * (1 << 20))
+            for r, b in enumerate(blocks):
+                chunk.text_scan(r, b)
+            lines = [chunk.text_lines(r) for r in range(self.n_reads)]
+            n = min(min(l // 4 for l in lines), cap)
+            if n > 0:
+                break
+            # no complete group in the blocks: either the input ended or a record is larger than the block
+            for s in self.sources:
+                s.advance(0)
+            if all(s.eof for s in self.sources):
+                rest = [bytes(s.block()).strip() for s in self.sources]
+                if all(not x for x in rest):
+                    return 0
+                if any(not x for x in rest) or any(l // 4 for l in lines):
+                    raise _ffi.PclError(_ffi.PCL_ERR_INPUT, "Unequal number of reads in the chunk")     # fastq.rs:435-436
+                raise _ffi.PclError(_ffi.PCL_ERR_INPUT, "truncated FASTQ record at the end of the input")
+            grow *= 2
+        chunk.reset(n)
+        used = [chunk.text_fill(r) for r in range(self.n_reads)]
+        bad = chunk.text_names_check()
+        if bad >= 0:
+            raise _ffi.PclError(_ffi.PCL_ERR_INPUT, f"read names mismatch (group {self.records + bad})")   # fastq.rs:438-442
+        for r, (s, u) in enumerate(zip(self.sources, used)):
+            self.bpr[r] = 0.5 * self.bpr[r] + 0.5 * (u / n)
+            s.advance(u)
+        self.records += n
+        return n

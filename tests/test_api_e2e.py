@@ -105,10 +105,11 @@ def test_update_read_inferred_lengths(dataset):
     assert (r2.min_len, r2.max_len) == (int(L2.min()), int(L2.max()))
 
 
+@pytest.mark.parametrize("device_parse", [False, True])
 @pytest.mark.parametrize("correct", [False, True])
-def test_gen_barcoded_fastq_matches_oracle(dataset, correct):
+def test_gen_barcoded_fastq_matches_oracle(dataset, correct, device_parse):
     from precellar_b200.api import FastqProcessor
-    proc = FastqProcessor(dataset["assay"]).with_modality("rna").with_barcode_correct_prob(0.9)
+    proc = FastqProcessor(dataset["assay"], device_parse=device_parse).with_modality("rna").with_barcode_correct_prob(0.9)
     got = []
     for batch in proc.gen_barcoded_fastq(correct, chunk_size=100_000):      # several chunks
         got.extend(batch)
@@ -180,7 +181,8 @@ def test_make_fastq_without_read1_fails_like_the_reference(dataset, tmp_path):
         make_fastq(dataset["assay"], modality="rna", out_dir=str(tmp_path / "o2"), correct_barcode=False)
 
 
-def test_mismatched_names_are_rejected(dataset, tmp_path):
+@pytest.mark.parametrize("device_parse", [False, True])
+def test_mismatched_names_are_rejected(dataset, tmp_path, device_parse):
     import copy
     from precellar_b200 import _ffi
     from precellar_b200.api import FastqProcessor
@@ -192,7 +194,7 @@ def test_mismatched_names_are_rejected(dataset, tmp_path):
     a = copy.deepcopy(dataset["assay"])
     a.update_read("R2", fastq=bad, min_len=1, max_len=60)
     with pytest.raises(_ffi.PclError) as ei:
-        for _ in FastqProcessor(a).with_modality("rna").gen_barcoded_fastq(True):
+        for _ in FastqProcessor(a, device_parse=device_parse).with_modality("rna").gen_barcoded_fastq(True):
             pass
     assert ei.value.code == _ffi.PCL_ERR_INPUT
 
