@@ -133,7 +133,84 @@ def run_reference_sample(wl, seq, qual, length, len2, n_threads, steps=1, warmup
     return times, res, counts
 
 
-def measure_ingest(syn, n_pairs: int, tmpdir: str) -> dict:
+def measure_device_ingest(pipe, p1: str, p2: str, n_pairs: int) -> dict:
+    """FASTQ text -> chunk planes parsed on the GPU (pcl_text_*): from pinned host memory (PCIe + parse kernels) and
+    from the plain files on disk through textingest.TextGroupReader (adds the host's file reads)."""
+    from precellar_b200 import _ffi
+    from precellar_b200.textingest import TextGroupReader
+    L = _ffi.lib()
+    texts, ptrs = [], []
+    for p in (p1, p2):
+        sz = os.path.getsize(p)
+        arr, ptr = pinned(sz, np.uint8, (sz,))
+        with open(p, "rb", buffering=0) as fh:
+            got = 0
+            mv = memoryview(arr)
+            while got < sz:
+                got += fh.readinto(mv[got:])
+        texts.append(arr)
+        ptrs.append(ptr)
+    ch = pipe.new_chunk(n_pairs)
+    out = {}
+    try:
+        best = None
+        for it in range(4):
+            if it == 1:
+                L.pcl_profile_reset(pipe.ctx)
+                L.pcl_profile_enable(pipe.ctx, 1)
+            t0 = time.perf_counter()
+            for r in range(2):
+                ch.text_scan(r, texts[r])
+            n = min(ch.text_lines(r) // 4 for r in range(2))
+            ch.reset(n)
+            used = [ch.text_fill(r) for r in range(2)]
+            bad = ch.text_names_check()
+            dt = time.perf_counter() - t0
+            assert n == n_pairs and bad == -1 and used == [len(t) for t in texts]
+            if it >= 1:
+                best = dt if best is None else min(best, dt)
+        ms_i, ms_f, k = C.c_double(), C.c_double(), C.c_uint64()
+        L.pcl_profile_get(pipe.ctx, _ffi.K_TEXT_INDEX, C.byref(ms_i), C.byref(k))
+        L.pcl_profile_get(pipe.ctx, _ffi.K_TEXT_FILL, C.byref(ms_f), C.byref(k))
+        L.pcl_profile_enable(pipe.ctx, 0)
+        L.pcl_profile_reset(pipe.ctx)
+        nbytes = sum(len(t) for t in texts)
+        out["text_bytes_per_pair"] = nbytes / n_pairs
+        out["pinned_text_pairs_per_s"] = n_pairs / best
+        out["pinned_text_GBps"] = nbytes / best / 1e9
+        out["kernels_ms_per_call"] = {"index": ms_i.value / 3, "fill_and_names": ms_f.value / 3}
+        out["kernels_text_GBps"] = nbytes / ((ms_i.value + ms_f.value) / 3 * 1e-3) / 1e9
+    finally:
+        ch.close()
+        pipe.chunks.remove(ch)
+        for ptr in ptrs:
+            L.pcl_host_free(ptr)
+    per = 1 << 19
+    rdr = TextGroupReader(pipe, [[p1], [p2]], per, [80, 210])
+    chs = [pipe.new_chunk(per) for _ in range(2)]
+    try:
+        t0 = time.perf_counter()
+        got = k = 0
+        while True:
+            n = rdr.next_into(chs[k & 1])
+            if n == 0:
+                break
+            got += n
+            k += 1
+        dt = time.perf_counter() - t0
+        assert got == n_pairs
+        out["plain_files_pairs_per_s"] = n_pairs / dt
+    finally:
+        rdr.close()
+        for c in chs:
+            c.close()
+            pipe.chunks.remove(c)
+    out["note"] = ("raw text -> device; line index and SoA planes (R1 32 B rows + 16 B quality window + lengths, R2 lengths, "
+                   "name hashes) built by k_text_* kernels; host cores only move bytes")
+    return out
+
+
+def measure_ingest(syn, n_pairs: int, tmpdir: str, pipe=None) -> dict:
     """Host ingest reported separately from the device path: FASTQ text (plain and gzip) -> pinned-ready SoA planes
     through the C++ reader (csrc/ingest.cpp), one decoding thread per file like the reference's readers."""
     import gzip
@@ -176,6 +253,8 @@ def measure_ingest(syn, n_pairs: int, tmpdir: str) -> dict:
         rd.close()
         assert got == n_pairs
         out[f"{kind}_fastq_pairs_per_s"] = n_pairs / dt
+    if pipe is not None:
+        out["device_parse"] = measure_device_ingest(pipe, p1, p2, n_pairs)
     return out
 
 
@@ -450,7 +529,7 @@ def main():
     if rank == 0 and world == 1 and not args.no_cpu and args.ingest_sample > 0:
         import tempfile
         with tempfile.TemporaryDirectory() as td:
-            ingest = measure_ingest(syn, args.ingest_sample, td)
+            ingest = measure_ingest(syn, args.ingest_sample, td, pipe)
 
     if rank == 0:
         out = {

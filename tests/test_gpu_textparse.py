@@ -117,10 +117,13 @@ def write(path, data):
 
 
 @pytest.mark.parametrize("target", [700, 4096, 100000])
-def test_group_reader_matches_host_reader_end_to_end(tmp_path, target):
+def test_group_reader_matches_host_reader_end_to_end(tmp_path, target, monkeypatch):
     """Concatenated plain + gzip files, the last one without a trailing newline; chunk targets that force many
     carried-over tails; counts, keys and statuses must equal the host-reader path."""
+    from precellar_b200 import textingest
     from precellar_b200.ingest import GroupReader
+    if target != 700:
+        monkeypatch.setattr(textingest, "_IO_SLICE", 10007)        # plain files are read in parallel slices
     from precellar_b200.pipeline import BarcodePipeline
     from precellar_b200.textingest import TextGroupReader
     rng = np.random.default_rng(23)
