@@ -36,6 +36,8 @@ struct CountParams {
     unsigned long long *worklist;        // entries: rec | start<<32 | len<<48 | j<<56
     unsigned long long *wl_count;
     unsigned long long *num_defect;
+    uint32_t hist_admit_mask;            // k_count_fast: admit a new key to the histogram cache on 1 of (mask + 1) sightings
+    uint32_t hist_two_choice;            // k_count_fast: two candidate cache lines per key
 };
 
 struct CorrectParams {
@@ -104,9 +106,10 @@ __device__ __forceinline__ void pcl_wl_finish(const P &p, const WlCursor &cur, u
 // Per-CTA histogram cache: a direct-mapped table in shared memory keyed on (j, slot).  Zipf-distributed
 // barcodes send a large share of the reads to a few counters; the cache turns those into shared-memory
 // atomics and one global atomic per cached key at the end of the CTA's life.
+template <int kBits = PCL_HCACHE_BITS>
 __device__ __forceinline__ void pcl_hist_add(uint32_t *ck, uint32_t *cc, uint32_t j, uint32_t slot, uint32_t *gcounts) {
     const uint32_t id = (j << 29) | slot;
-    const uint32_t h = (id * 2654435761u) >> (32 - PCL_HCACHE_BITS);
+    const uint32_t h = (id * 2654435761u) >> (32 - kBits);
     uint32_t cur = ((volatile uint32_t *)ck)[h];
     if (cur == PCL_HEMPTY) {
         uint32_t old = atomicCAS(&ck[h], PCL_HEMPTY, id);
@@ -114,6 +117,37 @@ __device__ __forceinline__ void pcl_hist_add(uint32_t *ck, uint32_t *cc, uint32_
     }
     if (cur == id) atomicAdd(&cc[h], 1u);
     else atomicAdd(&gcounts[slot], 1u);
+}
+
+// Variant for the fast kernel: two candidate lines per key and an admission filter.  A line never changes its
+// owner, so every increment lands in exactly one counter that belongs to its key whatever the interleaving;
+// the policy only decides how many increments stay in shared memory.  `salt` varies per record: a key is
+// admitted to a free line on 1 of (admit_mask + 1) sightings, which keeps one-off (ambient) barcodes from
+// filling the cache before the frequent ones have claimed their lines.
+template <int kBits>
+__device__ __forceinline__ void pcl_hist_add2(uint32_t *ck, uint32_t *cc, uint32_t slot, uint32_t *gcounts, uint32_t salt,
+                                              uint32_t admit_mask, bool two_choice) {
+    const uint32_t id = slot;
+    const uint32_t h1 = (id * 2654435761u) >> (32 - kBits);
+    uint32_t c1 = ((volatile uint32_t *)ck)[h1];
+    if (c1 == id) { atomicAdd(&cc[h1], 1u); return; }
+    const uint32_t h2 = (id * 0x85EBCA6Bu + 0x6A09E667u) >> (32 - kBits);
+    uint32_t c2 = PCL_HEMPTY - 1u;
+    if (two_choice) {
+        c2 = ((volatile uint32_t *)ck)[h2];
+        if (c2 == id) { atomicAdd(&cc[h2], 1u); return; }
+    }
+    if ((((salt * 0x9E3779B1u) >> 20) & admit_mask) == 0u) {
+        if (c1 == PCL_HEMPTY) {
+            c1 = atomicCAS(&ck[h1], PCL_HEMPTY, id);
+            if (c1 == PCL_HEMPTY || c1 == id) { atomicAdd(&cc[h1], 1u); return; }
+        }
+        if (two_choice && c2 == PCL_HEMPTY) {
+            c2 = atomicCAS(&ck[h2], PCL_HEMPTY, id);
+            if (c2 == PCL_HEMPTY || c2 == id) { atomicAdd(&cc[h2], 1u); return; }
+        }
+    }
+    atomicAdd(&gcounts[slot], 1u);
 }
 
 __device__ __forceinline__ uint4 pcl_ld_stream(const uint4 *p) {
@@ -264,10 +298,12 @@ __global__ void __launch_bounds__(PCL_BLOCK) k_count(const __grid_constant__ Cou
 __device__ __forceinline__ void pcl_st_stream(uint32_t *p, uint32_t v) { __stcs(p, v); }
 __device__ __forceinline__ void pcl_st_stream(uint16_t *p, uint16_t v) { __stcs(p, v); }
 
-__global__ void __launch_bounds__(PCL_BLOCK) k_count_fast(const __grid_constant__ CountParams p) {
-    __shared__ uint32_t ck[PCL_HCACHE];
-    __shared__ uint32_t cc[PCL_HCACHE];
-    for (uint32_t h = threadIdx.x; h < PCL_HCACHE; h += blockDim.x) { ck[h] = PCL_HEMPTY; cc[h] = 0; }
+// kBits: log2 of the histogram cache entries; the CTA has 256 << (kBits - 12) threads (same cache per thread).
+template <int kBits>
+__global__ void __launch_bounds__(PCL_BLOCK << (kBits - PCL_HCACHE_BITS)) k_count_fast(const __grid_constant__ CountParams p) {
+    extern __shared__ uint32_t pcl_hist_smem[];
+    uint32_t *ck = pcl_hist_smem, *cc = pcl_hist_smem + (1u << kBits);
+    for (uint32_t h = threadIdx.x; h < (1u << kBits); h += blockDim.x) { ck[h] = PCL_HEMPTY; cc[h] = 0; }
     __syncthreads();
 
     const DRead &rd = p.rd;
@@ -382,7 +418,7 @@ __global__ void __launch_bounds__(PCL_BLOCK) k_count_fast(const __grid_constant_
                     }
                     if (slot != 0xFFFFFFFFu) {
                         code = PCL_BC_EXACT;
-                        pcl_hist_add(ck, cc, 0u, slot, tab.counts);
+                        pcl_hist_add2<kBits>(ck, cc, slot, tab.counts, p_i, p.hist_admit_mask, p.hist_two_choice != 0);
                     } else {
                         code = PCL_BC_NO_MATCH;
                         ++n_mis;
@@ -409,7 +445,7 @@ __global__ void __launch_bounds__(PCL_BLOCK) k_count_fast(const __grid_constant_
         if (n_mis) atomicAdd(tab.mismatch, n_mis);
     }
     __syncthreads();
-    for (uint32_t h = threadIdx.x; h < PCL_HCACHE; h += blockDim.x) {
+    for (uint32_t h = threadIdx.x; h < (1u << kBits); h += blockDim.x) {
         const uint32_t id = ck[h], c = cc[h];
         if (id != PCL_HEMPTY && c) atomicAdd(&tab.counts[id & 0x1FFFFFFFu], c);
     }

@@ -121,6 +121,8 @@ struct pcl_ctx {
     uint64_t launches = 0;
     int sm_count = 148;
     int occ[12] = {1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1};   // resident CTAs per SM of each kernel (see OCC_*)
+    int fast_bits = 14, fast_waves = 1;
+    uint32_t hist_admit_mask = 7, hist_two_choice = 1;
     bool force_generic = false;   // PCL_FORCE_GENERIC=1: only the generic kernels (tests compare both paths)
     bool no_neighbour_tables = false;   // PCL_NO_NEIGHBOUR_TABLES=1: 3*L direct probes instead of the 4 neighbourhood tables
 };
@@ -267,7 +269,24 @@ int pcl_ctx_create(pcl_ctx **out, int device) {
         };
         ctx->occ[OCC_COUNT] = occ((const void *)k_count<false>);
         ctx->occ[OCC_COUNT_CODES] = occ((const void *)k_count<true>);
-        ctx->occ[OCC_COUNT_FAST] = occ((const void *)k_count_fast);
+        {
+            // k_count_fast: 1024-thread CTAs with a 16 K-entry histogram cache (128 KB), one resident wave, two
+            // candidate lines per key, a new key admitted on 1 of 8 sightings.  Measured on 125 M v3 records:
+            // 2.09 ms against 2.49 ms for 256 threads / 4 K entries / 3 waves / first-come lines (profiles/).
+            // The environment overrides exist for experiments (tools/kbench.py).
+            const char *fb = getenv("PCL_FAST_BITS"), *fw = getenv("PCL_WAVES"), *fa = getenv("PCL_ADMIT"), *ft = getenv("PCL_TWO");
+            ctx->fast_bits = fb ? atoi(fb) : 14;
+            if (ctx->fast_bits < 12 || ctx->fast_bits > 14) ctx->fast_bits = 14;
+            ctx->fast_waves = fw ? std::max(1, atoi(fw)) : 1;
+            ctx->hist_admit_mask = fa ? (uint32_t)atoi(fa) : 7u;
+            ctx->hist_two_choice = ft ? (uint32_t)atoi(ft) : 1u;
+            const void *fn = ctx->fast_bits == 12 ? (const void *)k_count_fast<12> : ctx->fast_bits == 13 ? (const void *)k_count_fast<13> : (const void *)k_count_fast<14>;
+            const int smem = 8 << ctx->fast_bits, threads = PCL_BLOCK << (ctx->fast_bits - 12);
+            cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+            int nb = 1;
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, fn, threads, smem) != cudaSuccess || nb < 1) nb = 1;
+            ctx->occ[OCC_COUNT_FAST] = nb;
+        }
         ctx->occ[OCC_COUNT_LENONLY] = occ((const void *)k_count_lenonly);
         ctx->occ[OCC_ENUM] = occ((const void *)k_enum_all);
         ctx->occ[OCC_CORRECT_FAST] = occ((const void *)k_correct<true>);
@@ -477,7 +496,7 @@ int pcl_chunk_create(pcl_ctx *ctx, uint64_t capacity_records, pcl_chunk **out) {
         }
         // misses + the unused tails of the per-warp reservations (largest grid: 3 waves of <= 8 CTAs per SM, 8 warps each)
         if (inf.n_bc) {
-            uint64_t warps = (uint64_t)ctx->sm_count * 24 * (PCL_BLOCK / 32), by_size = (cap + 31) / 32 + PCL_BLOCK / 32;
+            uint64_t warps = (uint64_t)ctx->sm_count * 24 * (PCL_BLOCK / 32), by_size = (cap + 31) / 32 + 32;
             if (warps > by_size) warps = by_size;             // a grid never has more warps than the chunk has records / 32
             A((void **)&b.worklist, (cap + warps * PCL_WL_BATCH) * inf.n_bc * 8);
         }
@@ -780,10 +799,20 @@ int pcl_count(pcl_ctx *ctx, pcl_chunk *c) {
                           c->n < 0xFF000000ull;      // 32-bit record indices inside k_count_fast
         const bool lenonly = !d.needs_payload && d.fixed_layout && !ctx->force_generic;
         prof_begin(ctx, c->stream, d.needs_payload ? PCL_K_COUNT : PCL_K_COUNT_LENONLY);
-        // The counting kernels run THREE resident waves rather than one: a CTA's shared-memory histogram cache sees a
-        // third of the distinct barcodes, so fewer hits fall through to global atomics (measured: 2.79 ms at one wave,
-        // 2.49 ms at three, 125 M records; more waves only add worklist holes for pass 2).
-        if (fast) k_count_fast<<<grid_for(ctx, c->n, 3 * ctx->occ[OCC_COUNT_FAST]), PCL_BLOCK, 0, c->stream>>>(p);
+        // The generic counting kernels run THREE resident waves rather than one: with first-come cache lines a CTA
+        // that lives a third as long lets fewer one-off barcodes occupy lines (measured on the former fast kernel:
+        // 2.79 ms at one wave, 2.49 ms at three).  k_count_fast has an admission filter instead and runs one wave.
+        if (fast) {
+            p.hist_admit_mask = ctx->hist_admit_mask;
+            p.hist_two_choice = ctx->hist_two_choice;
+            const int threads = PCL_BLOCK << (ctx->fast_bits - 12), smem = 8 << ctx->fast_bits;
+            uint64_t blocks = (c->n + threads - 1) / threads, cap = (uint64_t)ctx->sm_count * ctx->fast_waves * ctx->occ[OCC_COUNT_FAST];
+            cap = std::min<uint64_t>(cap, (uint64_t)ctx->sm_count * 24 * (PCL_BLOCK / 32) / (threads / 32));   // worklist slack (pcl_chunk_create)
+            const int grid = (int)std::max<uint64_t>(1, std::min(blocks, cap));
+            if (ctx->fast_bits == 12) k_count_fast<12><<<grid, threads, smem, c->stream>>>(p);
+            else if (ctx->fast_bits == 13) k_count_fast<13><<<grid, threads, smem, c->stream>>>(p);
+            else k_count_fast<14><<<grid, threads, smem, c->stream>>>(p);
+        }
         else if (lenonly) k_count_lenonly<<<grid_for(ctx, c->n, ctx->occ[OCC_COUNT_LENONLY]), PCL_BLOCK, 0, c->stream>>>(p);
         else if (d.codes_ok && !ctx->force_generic) k_count<true><<<grid_for(ctx, c->n, 3 * ctx->occ[OCC_COUNT_CODES]), PCL_BLOCK, 0, c->stream>>>(p);
         else k_count<false><<<grid_for(ctx, c->n, 3 * ctx->occ[OCC_COUNT]), PCL_BLOCK, 0, c->stream>>>(p);
