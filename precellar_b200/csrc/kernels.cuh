@@ -297,6 +297,7 @@ __global__ void __launch_bounds__(PCL_BLOCK) k_count(const __grid_constant__ Cou
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void pcl_st_stream(uint32_t *p, uint32_t v) { __stcs(p, v); }
 __device__ __forceinline__ void pcl_st_stream(uint16_t *p, uint16_t v) { __stcs(p, v); }
+__device__ __forceinline__ void pcl_st_stream(uint4 *p, uint4 v) { __stcs(p, v); }
 
 // kBits: log2 of the histogram cache entries; the CTA has 256 << (kBits - 12) threads (same cache per thread).
 template <int kBits>
@@ -455,24 +456,49 @@ __global__ void __launch_bounds__(PCL_BLOCK << (kBits - PCL_HCACHE_BITS)) k_coun
 // k_count_lenonly: pass 1 for fixed-layout reads without barcode / UMI / anchor (insert reads): only the
 // record length is read; emits fstatus and the insert coordinates.
 // ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void pcl_lenonly_one(const DRead &rd, int ne, uint32_t absent_all, uint32_t L, uint32_t *fs_out, uint32_t *tc_out) {
+    if (rd.max_len && L > rd.max_len) L = rd.max_len;
+    uint32_t off = 0, tc = PCL_COORD_ABSENT, n_t = 0;
+    for (int e = 0; e < ne; ++e) {
+        const uint32_t mn = rd.elems[e].min_len, mx = rd.elems[e].max_len;
+        if (off >= L || off + mn > L) break;                       // segment.rs:245-248
+        const uint32_t hi = off + mx < L ? off + mx : L;           // a fixed element fits entirely; the trailing variable one is clipped
+        if (rd.elems[e].kind == PCL_KIND_TARGET) { tc = (off << 16) | (hi - off); ++n_t; }
+        off += mx;
+    }
+    uint32_t fs = absent_all | (n_t > 1u ? PCL_SPLIT_MULTI_TARGET : PCL_SPLIT_OK);
+    if (n_t == 1u) fs |= PCL_FSTATUS_TARGET;
+    *fs_out = fs;
+    *tc_out = n_t == 1u ? tc : PCL_COORD_ABSENT;
+}
+
+// Eight records per thread: one 128-bit load of the lengths, one 128-bit store of fstatus, two of tcoord.
 __global__ void __launch_bounds__(PCL_BLOCK) k_count_lenonly(const __grid_constant__ CountParams p) {
     const DRead &rd = p.rd;
     const uint32_t absent_all = (PCL_BC_ABSENT << 4) | (PCL_BC_ABSENT << 7) | (PCL_BC_ABSENT << 10) | (PCL_BC_ABSENT << 13);
     const int ne = rd.n_elems;
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < p.n; i += (uint64_t)gridDim.x * blockDim.x) {
-        uint32_t L = p.len[i];
-        if (rd.max_len && L > rd.max_len) L = rd.max_len;
-        uint32_t off = 0, tc = PCL_COORD_ABSENT, n_t = 0;
-        for (int e = 0; e < ne; ++e) {
-            const uint32_t mn = rd.elems[e].min_len, mx = rd.elems[e].max_len;
-            if (off >= L || off + mn > L) break;                       // segment.rs:245-248
-            const uint32_t hi = off + mx < L ? off + mx : L;           // a fixed element fits entirely; the trailing variable one is clipped
-            if (rd.elems[e].kind == PCL_KIND_TARGET) { tc = (off << 16) | (hi - off); ++n_t; }
-            off += mx;
+    const uint64_t n8 = p.n >> 3;
+    const uint4 *len8 = reinterpret_cast<const uint4 *>(p.len);
+    uint4 *fs8 = reinterpret_cast<uint4 *>(p.fstatus);
+    uint4 *tc4 = reinterpret_cast<uint4 *>(p.tcoord);
+    for (uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; g < n8; g += (uint64_t)gridDim.x * blockDim.x) {
+        const uint4 lv = pcl_ld_stream(len8 + g);
+        const uint32_t lw[4] = {lv.x, lv.y, lv.z, lv.w};
+        uint32_t fs[8], tc[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) pcl_lenonly_one(rd, ne, absent_all, (lw[k >> 1] >> (16 * (k & 1))) & 0xFFFFu, &fs[k], &tc[k]);
+        pcl_st_stream(fs8 + g, make_uint4(fs[0] | (fs[1] << 16), fs[2] | (fs[3] << 16), fs[4] | (fs[5] << 16), fs[6] | (fs[7] << 16)));
+        if (rd.has_target) {
+            pcl_st_stream(tc4 + 2 * g, make_uint4(tc[0], tc[1], tc[2], tc[3]));
+            pcl_st_stream(tc4 + 2 * g + 1, make_uint4(tc[4], tc[5], tc[6], tc[7]));
         }
-        uint32_t fs = absent_all | (n_t > 1u ? PCL_SPLIT_MULTI_TARGET : PCL_SPLIT_OK);
-        if (n_t == 1u) fs |= PCL_FSTATUS_TARGET;
-        if (rd.has_target) p.tcoord[i] = n_t == 1u ? tc : PCL_COORD_ABSENT;
+    }
+    // the last n % 8 records
+    const uint64_t i = (n8 << 3) + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < p.n) {
+        uint32_t fs, tc;
+        pcl_lenonly_one(rd, ne, absent_all, p.len[i], &fs, &tc);
+        if (rd.has_target) p.tcoord[i] = tc;
         p.fstatus[i] = (uint16_t)fs;
     }
 }

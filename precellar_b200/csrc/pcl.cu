@@ -813,7 +813,7 @@ int pcl_count(pcl_ctx *ctx, pcl_chunk *c) {
             else if (ctx->fast_bits == 13) k_count_fast<13><<<grid, threads, smem, c->stream>>>(p);
             else k_count_fast<14><<<grid, threads, smem, c->stream>>>(p);
         }
-        else if (lenonly) k_count_lenonly<<<grid_for(ctx, c->n, ctx->occ[OCC_COUNT_LENONLY]), PCL_BLOCK, 0, c->stream>>>(p);
+        else if (lenonly) k_count_lenonly<<<grid_for(ctx, c->n / 8 + 8, ctx->occ[OCC_COUNT_LENONLY]), PCL_BLOCK, 0, c->stream>>>(p);
         else if (d.codes_ok && !ctx->force_generic) k_count<true><<<grid_for(ctx, c->n, 3 * ctx->occ[OCC_COUNT_CODES]), PCL_BLOCK, 0, c->stream>>>(p);
         else k_count<false><<<grid_for(ctx, c->n, 3 * ctx->occ[OCC_COUNT]), PCL_BLOCK, 0, c->stream>>>(p);
         prof_end(ctx, c->stream);
