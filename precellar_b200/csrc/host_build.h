@@ -188,6 +188,8 @@ inline int pcl_build_read(int r, const pcl_read_desc &rd, DRead *out, pcl_read_i
     return PCL_OK;
 }
 
+#define PCL_TABLE_LOAD_PCT 35
+
 struct HostTable {
     uint32_t mode = 0, slots_per_bucket = 8;
     uint64_t n_buckets = 0, n_slots = 0, n_entries = 0, empty = 0;
@@ -231,7 +233,10 @@ inline int pcl_build_table(const uint8_t *bytes, const uint64_t *offsets, uint64
     t.mode = all_le15 ? PCL_TAB_K32_MARKER : (all16 ? PCL_TAB_K32_L16 : PCL_TAB_K64);
     t.slots_per_bucket = t.mode == PCL_TAB_K64 ? 4 : 8;
     const uint32_t spb = t.slots_per_bucket;
-    t.n_buckets = (2 * m + spb - 1) / spb;                     // load factor <= 0.5
+    // Load factor 0.35: a probe (and above all the unsuccessful neighbourhood probes of pass 2) ends at the first
+    // bucket with a free slot, so full buckets cost extra random sectors.  Measured on 125 M v3 pairs: count / correct
+    // 2.11 / 1.81 ms at 0.5, 2.04 / 1.71 ms at 0.35, no further gain at 0.25, and 2.9 / 4.1 ms at 0.8.
+    t.n_buckets = (100 * m / PCL_TABLE_LOAD_PCT + spb - 1) / spb;
     if (t.n_buckets < 2) t.n_buckets = 2;
     t.n_slots = t.n_buckets * spb;
     if (t.n_slots >= (1ull << 29))
