@@ -348,7 +348,9 @@ def main():
     from precellar_b200.dist import exchange_unique_id
     uid = exchange_unique_id(BarcodePipeline.new_unique_id, rank, world)
     layout = v3_layout(wl, R2_LEN)
+    t_setup = time.perf_counter()
     pipe = BarcodePipeline(layout, device=local_rank, nranks=world, rank=rank, nccl_uid=uid)
+    t_setup = time.perf_counter() - t_setup          # ctx + layout + whitelist tables (host build and upload) + NCCL init
     syn = S.Synth(spec, wl)
     first = rank * n
 
@@ -542,6 +544,7 @@ def main():
                        "l2": "inputs (6.3 GB per GPU) are far larger than L2; no flush needed"},
             "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": int(launches),
             "clocks": clocks.summary(), "parity": parity, "host_cores": host_cores, "host_ingest": ingest,
+            "setup_s": {"pipeline_create_incl_whitelist_tables": t_setup},
         }
         emit(out)
     pipe.close()
