@@ -92,3 +92,73 @@ def test_counts_match_independent_restatement(is_reverse):
     counts, mismatch, total = ocounts[0]
     assert total == ref.total_count and mismatch == ref.mismatch_count and ref.mismatch_count > 0
     assert [int(c) for c in counts] == [ref.barcode_counts.counts[b] for b in wl]
+
+
+# ---------------------------------------------------------------------------------------------------
+# split_with_tolerance: oracle vs the independent transcription, on random element tables and reads
+# ---------------------------------------------------------------------------------------------------
+LABEL = {O.OTHER: "O", O.BARCODE: "B", O.UMI: "U", O.TARGET: "T", O.PRIMER: "P"}
+
+
+def random_elems(rng):
+    elems = []
+    for _ in range(int(rng.integers(1, 8))):
+        kind = rng.random()
+        rtype = int(rng.choice([O.OTHER, O.BARCODE, O.UMI, O.TARGET, O.PRIMER]))
+        if kind < 0.35:                                   # fixed length, random sequence
+            n = int(rng.integers(1, 9))
+            elems.append(O.Elem(rtype, n, n))
+        elif kind < 0.6:                                  # fixed sequence (anchor / linker)
+            n = int(rng.integers(1, 8))
+            seq = bytes(rng.choice(ACGT, n)).decode()
+            elems.append(O.Elem(rtype, n, n, True, seq))
+        else:                                             # variable length
+            a = int(rng.integers(0, 6))
+            b = a + int(rng.integers(1, 12))
+            elems.append(O.Elem(rtype, a, b))
+    return elems
+
+
+def random_read(rng, elems, is_reverse):
+    """Mostly a plausible instance of the element table (anchors present, sometimes mutated), sometimes noise."""
+    if rng.random() < 0.15:
+        return bytes(rng.choice(ACGT, int(rng.integers(0, 60))))
+    out = bytearray()
+    for e in elems:
+        n = int(rng.integers(e.min_len, e.max_len + 1))
+        if e.seq_fixed:
+            s = bytearray(e.sequence.encode())
+            if is_reverse:
+                s = bytearray(R.seqspec_rev_compl(bytes(s)))
+            if rng.random() < 0.3 and len(s):
+                s[int(rng.integers(len(s)))] = int(rng.choice(np.frombuffer(b"ACGTNa", np.uint8)))
+            out += s
+        else:
+            out += bytes(rng.choice(ACGT, n))
+    cut = int(rng.integers(0, len(out) + 8)) if rng.random() < 0.4 else len(out) + int(rng.integers(0, 10))
+    out = out[:cut] + bytes(rng.choice(ACGT, max(0, cut - len(out))))
+    return bytes(out)
+
+
+@pytest.mark.parametrize("is_reverse", [False, True])
+@pytest.mark.parametrize("tols", [(1.0, 0.2), (0.5, 0.0), (0.0, 0.34)])
+def test_split_matches_independent_restatement(is_reverse, tols):
+    rng = np.random.default_rng(U.seed_of("indep-split", is_reverse, tols))
+    seen = set()
+    for _ in range(400):
+        elems = random_elems(rng)
+        ref_elems = [R.SegElem(LABEL[e.rtype], e.min_len, e.max_len, e.seq_fixed, e.sequence.encode()) for e in elems]
+        for _ in range(12):
+            read = random_read(rng, elems, is_reverse)
+            st, text = O.split_str(elems, read, is_reverse, tols[0], tols[1])
+            try:
+                want = ("ok", R.render(R.split_with_tolerance(ref_elems, is_reverse, read, tols[0], tols[1])))
+            except R.SplitError as e:
+                want = (e.kind, "")
+            except R.RustPanic:
+                want = ("panic", "")
+            got = {O.SPLIT_OK: "ok", O.SPLIT_ANCHOR_NOT_FOUND: "anchor_not_found", O.SPLIT_PATTERN_MISMATCH: "pattern_mismatch",
+                   -100: "panic"}[st]
+            assert (got, text if got == "ok" else "") == want, (elems, read, is_reverse)
+            seen.add(got)
+    assert {"ok", "pattern_mismatch"} <= seen
