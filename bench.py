@@ -205,6 +205,47 @@ def measure_device_ingest(pipe, p1: str, p2: str, n_pairs: int) -> dict:
         for c in chs:
             c.close()
             pipe.chunks.remove(c)
+    # the same through gzip: ordinary single-member files (one zlib stream per file) and BGZF (blocks inflated in parallel)
+    import struct
+    import zlib
+
+    def bgzf(src, dst, block=65280):
+        with open(src, "rb") as fi, open(dst, "wb") as fo:
+            while True:
+                c = fi.read(block)
+                co = zlib.compressobj(1, zlib.DEFLATED, -15)
+                body = co.compress(c) + co.flush()
+                fo.write(b"\x1f\x8b\x08\x04\0\0\0\0\x00\xff" + struct.pack("<H", 6) + b"BC" + struct.pack("<HH", 2, 18 + len(body) + 8 - 1))
+                fo.write(body + struct.pack("<II", zlib.crc32(c) & 0xFFFFFFFF, len(c)))
+                if not c:
+                    break
+    variants = []
+    if os.path.exists(p1 + ".gz") and os.path.exists(p2 + ".gz"):
+        variants.append(("gzip_files_pairs_per_s", p1 + ".gz", p2 + ".gz"))
+    bgzf(p1, p1 + ".bgz")
+    bgzf(p2, p2 + ".bgz")
+    variants.append(("bgzf_files_pairs_per_s", p1 + ".bgz", p2 + ".bgz"))
+    for key, a, b in variants:
+        rdr = TextGroupReader(pipe, [[a], [b]], per, [80, 210])
+        chs = [pipe.new_chunk(per) for _ in range(2)]
+        try:
+            t0 = time.perf_counter()
+            got = k = 0
+            while True:
+                n = rdr.next_into(chs[k & 1])
+                if n == 0:
+                    break
+                got += n
+                k += 1
+            dt = time.perf_counter() - t0
+            assert got == n_pairs
+            out[key] = n_pairs / dt
+        finally:
+            rdr.close()
+            for c in chs:
+                c.close()
+                pipe.chunks.remove(c)
+    out["inflate_threads_per_file"] = max(1, min(8, (os.cpu_count() or 2) // 2))
     out["note"] = ("raw text -> device; line index and SoA planes (R1 32 B rows + 16 B quality window + lengths, R2 lengths, "
                    "name hashes) built by k_text_* kernels; host cores only move bytes")
     return out

@@ -287,6 +287,18 @@ int pcl_text_fill(pcl_chunk *chunk, int read_slot, uint64_t *consumed);
 int pcl_text_names_check(pcl_chunk *chunk, int64_t *first_bad);
 int pcl_text_line_ends(pcl_chunk *chunk, int read_slot, uint32_t *out, uint64_t n_lines);
 
+/* ---- decompressed byte stream of one gzip file (feeds pcl_text_scan) ---------------------------------
+ * Replaces open_file's MultiGzDecoder (seqspec/src/utils.rs:44-56) for the text path.  BGZF files (independent
+ * <= 64 KB members with their sizes in the header) are inflated by n_threads threads straight into the caller's
+ * buffer; any other gzip file (single or multi-member) is one sequential zlib stream.
+ * pcl_gzsrc_read returns the bytes produced (0 at the end of the file) or a negative pcl_status. */
+typedef struct pcl_gzsrc pcl_gzsrc;
+int pcl_gzsrc_open(const char *path, int n_threads, pcl_gzsrc **out);
+int64_t pcl_gzsrc_read(pcl_gzsrc *src, uint8_t *dst, uint64_t cap);
+int pcl_gzsrc_is_bgzf(const pcl_gzsrc *src);
+const char *pcl_gzsrc_error(const pcl_gzsrc *src);
+void pcl_gzsrc_close(pcl_gzsrc *src);
+
 /* ---- pinned host memory ------------------------------------------------------------------- */
 void *pcl_host_alloc(uint64_t bytes);
 void pcl_host_free(void *p);

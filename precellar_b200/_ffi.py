@@ -77,6 +77,7 @@ SYMBOLS = [
     "pcl_fastq_open", "pcl_fastq_close", "pcl_fastq_error", "pcl_fastq_read", "pcl_chunk_fetch_async",
     "pcl_make_fastq_batch",
     "pcl_text_scan", "pcl_text_lines", "pcl_text_fill", "pcl_text_names_check", "pcl_text_line_ends",
+    "pcl_gzsrc_open", "pcl_gzsrc_read", "pcl_gzsrc_is_bgzf", "pcl_gzsrc_error", "pcl_gzsrc_close",
 ]
 
 _lib = None
@@ -139,6 +140,11 @@ def lib() -> C.CDLL:
         "pcl_text_fill": (i32, [vp, i32, C.POINTER(u64)]),
         "pcl_text_names_check": (i32, [vp, C.POINTER(C.c_int64)]),
         "pcl_text_line_ends": (i32, [vp, i32, vp, u64]),
+        "pcl_gzsrc_open": (i32, [C.c_char_p, i32, C.POINTER(vp)]),
+        "pcl_gzsrc_read": (C.c_int64, [vp, vp, u64]),
+        "pcl_gzsrc_is_bgzf": (i32, [vp]),
+        "pcl_gzsrc_error": (C.c_char_p, [vp]),
+        "pcl_gzsrc_close": (None, [vp]),
         "pcl_fastq_open": (i32, [C.POINTER(C.c_char_p), i32, C.POINTER(vp)]),
         "pcl_fastq_close": (None, [vp]),
         "pcl_fastq_error": (C.c_char_p, [vp]),

@@ -1,0 +1,235 @@
+// gzsrc.cpp -- decompressed byte stream of one gzip file for the device text parser (textparse.cuh).
+//
+// Replaces, for this path: open_file's MultiGzDecoder (seqspec/src/utils.rs:44-56) -- the reference inflates every
+// FASTQ file on one thread, twice per run.  Here the stream only has to be turned into bytes (records are cut on the
+// GPU), so the inflate is all the host does, and it is parallel where the format allows it:
+//   * BGZF (bgzip, and what several demultiplexers write): every <= 64 KB block is an independent gzip member whose
+//     compressed size is in its header ('BC' extra field) and whose inflated size is in its trailer, so a batch of
+//     blocks is inflated by several threads straight into place in the caller's (pinned) buffer;
+//   * any other gzip file (single or multi-member): one zlib stream, sequentially.
+#include <zlib.h>
+
+#include <algorithm>
+#include <atomic>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "../../include/precellar_b200.h"
+
+namespace {
+struct Block { uint64_t src_off; uint32_t csize, isize; uint64_t dst_off; };
+
+inline uint32_t rd16(const uint8_t *p) { return (uint32_t)p[0] | ((uint32_t)p[1] << 8); }
+inline uint32_t rd32(const uint8_t *p) { return (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24); }
+
+// total size of the BGZF block that starts at p (n bytes available), 0 if p is not a BGZF block header
+uint32_t bgzf_block_size(const uint8_t *p, size_t n) {
+    if (n < 18 || p[0] != 0x1f || p[1] != 0x8b || p[2] != 8 || !(p[3] & 4)) return 0;
+    const uint32_t xlen = rd16(p + 10);
+    if (12 + (size_t)xlen > n) return 0;
+    for (uint32_t o = 0; o + 4 <= xlen;) {
+        const uint8_t *f = p + 12 + o;
+        const uint32_t slen = rd16(f + 2);
+        if (f[0] == 'B' && f[1] == 'C' && slen == 2 && o + 6 <= xlen) return rd16(f + 4) + 1;
+        o += 4 + slen;
+    }
+    return 0;
+}
+}  // namespace
+
+struct pcl_gzsrc {
+    FILE *f = nullptr;
+    std::string path, err;
+    int n_threads = 1;
+    bool bgzf = false, eof = false;
+    // BGZF: compressed bytes not yet consumed
+    std::vector<uint8_t> cbuf;
+    size_t cpos = 0, cend = 0;
+    std::vector<uint8_t> carry;          // BGZF: inflated bytes of a block that did not fit the caller's buffer
+    size_t carry_pos = 0;
+    // plain gzip: one zlib stream
+    z_stream zs;
+    bool zs_open = false, mid_member = false;
+    std::vector<uint8_t> zin;
+
+    bool fill_c() {             // keep the unconsumed tail, read more
+        if (cpos && cpos < cend) memmove(cbuf.data(), cbuf.data() + cpos, cend - cpos);
+        cend -= cpos;
+        cpos = 0;
+        const size_t got = fread(cbuf.data() + cend, 1, cbuf.size() - cend, f);
+        cend += got;
+        return got > 0;
+    }
+};
+
+extern "C" {
+
+int pcl_gzsrc_open(const char *path, int n_threads, pcl_gzsrc **out) {
+    if (!path || !out) return PCL_ERR_ARG;
+    *out = nullptr;
+    FILE *f = fopen(path, "rb");
+    if (!f) return PCL_ERR_INPUT;
+    pcl_gzsrc *s = new pcl_gzsrc();
+    s->f = f;
+    s->path = path;
+    s->n_threads = n_threads < 1 ? 1 : n_threads;
+    s->cbuf.resize(64u << 20);
+    s->cend = fread(s->cbuf.data(), 1, s->cbuf.size(), f);
+    s->bgzf = bgzf_block_size(s->cbuf.data(), s->cend) != 0;
+    if (!s->bgzf) {
+        memset(&s->zs, 0, sizeof s->zs);
+        if (inflateInit2(&s->zs, 15 + 32) != Z_OK) { fclose(f); delete s; return PCL_ERR_INPUT; }   // gzip or zlib header
+        s->zs_open = true;
+        s->zs.next_in = s->cbuf.data();              // the bytes read for the format probe
+        s->zs.avail_in = (uInt)s->cend;
+    }
+    *out = s;
+    return PCL_OK;
+}
+
+void pcl_gzsrc_close(pcl_gzsrc *s) {
+    if (!s) return;
+    if (s->zs_open) inflateEnd(&s->zs);
+    if (s->f) fclose(s->f);
+    delete s;
+}
+
+const char *pcl_gzsrc_error(const pcl_gzsrc *s) { return s ? s->err.c_str() : ""; }
+int pcl_gzsrc_is_bgzf(const pcl_gzsrc *s) { return s && s->bgzf; }
+
+// Inflate up to `cap` bytes into dst; returns the bytes produced (0 at the end of the file) or a negative pcl_status.
+int64_t pcl_gzsrc_read(pcl_gzsrc *s, uint8_t *dst, uint64_t cap) {
+    if (!s || (!dst && cap)) return PCL_ERR_ARG;
+    if (s->eof || cap == 0) return 0;
+    if (!s->bgzf) {
+        s->zs.next_out = dst;
+        uint64_t produced = 0;
+        while (produced < cap) {
+            if (s->zs.avail_in == 0) {
+                s->cpos = 0;
+                s->cend = fread(s->cbuf.data(), 1, s->cbuf.size(), s->f);
+                if (s->cend == 0) {
+                    if (s->mid_member) { s->err = "truncated gzip stream: " + s->path; return PCL_ERR_INPUT; }
+                    s->eof = true;
+                    break;
+                }
+                s->zs.next_in = s->cbuf.data();
+                s->zs.avail_in = (uInt)s->cend;
+            }
+            const uint64_t room = cap - produced;
+            s->zs.avail_out = (uInt)(room > (1u << 30) ? (1u << 30) : room);
+            const uInt before = s->zs.avail_out;
+            const int rc = inflate(&s->zs, Z_NO_FLUSH);
+            produced += before - s->zs.avail_out;
+            s->mid_member = rc != Z_STREAM_END;
+            if (rc == Z_STREAM_END) {                               // next member of a multi-member file, if any
+                if (s->zs.avail_in == 0) {
+                    s->cend = fread(s->cbuf.data(), 1, s->cbuf.size(), s->f);
+                    if (s->cend == 0) { s->eof = true; break; }
+                    s->zs.next_in = s->cbuf.data();
+                    s->zs.avail_in = (uInt)s->cend;
+                }
+                if (inflateReset2(&s->zs, 15 + 32) != Z_OK) { s->err = "zlib reset failed: " + s->path; return PCL_ERR_INPUT; }
+            } else if (rc != Z_OK && rc != Z_BUF_ERROR) {
+                s->err = std::string("gzip error in ") + s->path + ": " + (s->zs.msg ? s->zs.msg : "corrupt stream");
+                return PCL_ERR_INPUT;
+            } else if (rc == Z_BUF_ERROR && s->zs.avail_in == 0 && feof(s->f)) {
+                s->err = "truncated gzip stream: " + s->path;
+                return PCL_ERR_INPUT;
+            }
+        }
+        return (int64_t)produced;
+    }
+    // BGZF: collect whole blocks whose output fits, then inflate them in parallel; a block that straddles the end of
+    // the caller's buffer is inflated into `carry` and handed out in two parts, so a read is short only at the end
+    uint64_t produced = 0;
+    auto inflate_block = [&](const uint8_t *hp, uint32_t csize, uint32_t isize, uint8_t *out, z_stream &z) -> bool {
+        const uint32_t hdr = 12 + rd16(hp + 10);
+        if (csize < hdr + 8) return false;
+        if (isize == 0) return true;                                                    // the empty end-of-file marker block
+        inflateReset(&z);
+        z.next_in = const_cast<uint8_t *>(hp + hdr);
+        z.avail_in = csize - hdr - 8;
+        z.next_out = out;
+        z.avail_out = isize;
+        const int rc = inflate(&z, Z_FINISH);
+        return rc == Z_STREAM_END && z.avail_out == 0 && (uint32_t)crc32(0L, out, isize) == rd32(hp + csize - 8);
+    };
+    while (produced < cap) {
+        if (s->carry_pos < s->carry.size()) {
+            const size_t n = std::min<size_t>(s->carry.size() - s->carry_pos, cap - produced);
+            memcpy(dst + produced, s->carry.data() + s->carry_pos, n);
+            s->carry_pos += n;
+            produced += n;
+            continue;
+        }
+        if (s->eof) break;
+        std::vector<Block> blocks;
+        uint64_t out_off = produced;
+        size_t p = s->cpos;
+        bool straddle = false;
+        for (;;) {
+            const uint32_t bs = bgzf_block_size(s->cbuf.data() + p, s->cend - p);
+            if (bs == 0 || p + bs > s->cend) break;                                     // need more compressed bytes
+            const uint32_t isize = rd32(s->cbuf.data() + p + bs - 4);
+            if (out_off + isize > cap) { straddle = true; break; }
+            blocks.push_back({p, bs, isize, out_off});
+            out_off += isize;
+            p += bs;
+        }
+        if (blocks.empty() && !straddle) {
+            const size_t before = s->cend - s->cpos;
+            if (!s->fill_c()) {
+                if (before == 0) { s->eof = true; break; }
+                s->err = "truncated or non-BGZF block in " + s->path;
+                return PCL_ERR_INPUT;
+            }
+            continue;
+        }
+        std::atomic<size_t> next{0};
+        std::atomic<int> bad{0};
+        const uint8_t *src = s->cbuf.data();
+        auto work = [&]() {
+            z_stream z;
+            memset(&z, 0, sizeof z);
+            if (inflateInit2(&z, -15) != Z_OK) { bad = 1; return; }
+            for (;;) {
+                const size_t k = next.fetch_add(1);
+                if (k >= blocks.size()) break;
+                const Block &b = blocks[k];
+                if (!inflate_block(src + b.src_off, b.csize, b.isize, dst + b.dst_off, z)) { bad = 1; break; }
+            }
+            inflateEnd(&z);
+        };
+        if (!blocks.empty()) {
+            const int nt = (int)std::min<size_t>((size_t)s->n_threads, blocks.size());
+            std::vector<std::thread> th;
+            for (int t = 1; t < nt; ++t) th.emplace_back(work);
+            work();
+            for (auto &t : th) t.join();
+            if (bad) { s->err = "corrupt BGZF block in " + s->path; return PCL_ERR_INPUT; }
+            produced = out_off;
+            s->cpos = p;
+        }
+        if (straddle) {
+            const uint32_t bs = bgzf_block_size(s->cbuf.data() + s->cpos, s->cend - s->cpos);
+            const uint32_t isize = rd32(s->cbuf.data() + s->cpos + bs - 4);
+            s->carry.resize(isize);
+            s->carry_pos = 0;
+            z_stream z;
+            memset(&z, 0, sizeof z);
+            bool ok = inflateInit2(&z, -15) == Z_OK;
+            ok = ok && inflate_block(s->cbuf.data() + s->cpos, bs, isize, s->carry.data(), z);
+            inflateEnd(&z);
+            if (!ok) { s->err = "corrupt BGZF block in " + s->path; return PCL_ERR_INPUT; }
+            s->cpos += bs;
+        }
+    }
+    return (int64_t)produced;
+}
+
+}  // extern "C"

@@ -11,7 +11,6 @@ reserved gap, into which the unconsumed tail of block k is copied once it is kno
 from __future__ import annotations
 
 import ctypes as C
-import gzip
 import io
 import os
 from concurrent.futures import ThreadPoolExecutor
@@ -31,12 +30,41 @@ def _pinned(nbytes: int) -> np.ndarray:
     return np.frombuffer((C.c_uint8 * int(nbytes)).from_address(p), dtype=np.uint8), p
 
 
+class GzSource:
+    """Decompressed bytes of one gzip file through pcl_gzsrc_* (csrc/gzsrc.cpp): BGZF blocks are inflated by
+    several threads straight into the destination, any other gzip file by one zlib stream."""
+
+    def __init__(self, path: str, n_threads: Optional[int] = None):
+        h = C.c_void_p()
+        nt = n_threads if n_threads is not None else max(1, min(8, (os.cpu_count() or 2) // 2))
+        rc = lib().pcl_gzsrc_open(path.encode(), nt, C.byref(h))
+        if rc < 0:
+            raise _ffi.PclError(rc, f"cannot open file: {path}")
+        self.h = h
+        self.bgzf = bool(lib().pcl_gzsrc_is_bgzf(h))
+
+    def readinto(self, mv) -> int:
+        n = len(mv)
+        if n == 0:
+            return 0
+        buf = (C.c_uint8 * n).from_buffer(mv)
+        got = lib().pcl_gzsrc_read(self.h, C.addressof(buf), n)
+        if got < 0:
+            raise _ffi.PclError(int(got), lib().pcl_gzsrc_error(self.h).decode())
+        return int(got)
+
+    def close(self) -> None:
+        if self.h:
+            lib().pcl_gzsrc_close(self.h)
+            self.h = None
+
+
 def _open_raw(path: str):
     """open_file (seqspec/src/utils.rs:44-56): gzip by magic, zstd by extension, else plain."""
     with open(path, "rb") as f:
         magic = f.read(2)
     if magic == b"\x1f\x8b":
-        return gzip.open(path, "rb")
+        return GzSource(path)
     if path.endswith(".zst"):
         from . import _zstd
         return io.BytesIO(_zstd.decompress_file(path))

@@ -110,3 +110,75 @@ def test_malformed_input_is_an_error(tmp_path):
         FastqReader([p]).read(10, 16)
     with pytest.raises(_ffi.PclError):
         FastqReader([str(tmp_path / "missing.fq")])
+
+
+# ---------------------------------------------------------------------------------------------------
+# pcl_gzsrc_*: decompressed byte stream of a gzip file (BGZF blocks inflated in parallel)
+# ---------------------------------------------------------------------------------------------------
+def bgzf_bytes(data: bytes, block: int = 60000, eof_marker: bool = True) -> bytes:
+    import struct
+    import zlib
+    out = bytearray()
+    chunks = [data[i:i + block] for i in range(0, len(data), block)] + ([b""] if eof_marker else [])
+    for c in chunks:
+        co = zlib.compressobj(6, zlib.DEFLATED, -15)
+        body = co.compress(c) + co.flush()
+        bsize = 18 + len(body) + 8 - 1
+        out += b"\x1f\x8b\x08\x04" + b"\0\0\0\0" + b"\x00\xff" + struct.pack("<H", 6) + b"BC" + struct.pack("<HH", 2, bsize)
+        out += body + struct.pack("<II", zlib.crc32(c) & 0xFFFFFFFF, len(c))
+    return bytes(out)
+
+
+def gz_read_all(path, sizes, n_threads=4):
+    from precellar_b200.textingest import GzSource
+    src = GzSource(path, n_threads)
+    out = bytearray()
+    k = 0
+    while True:
+        buf = bytearray(sizes[k % len(sizes)])
+        k += 1
+        n = src.readinto(memoryview(buf))
+        if n == 0:
+            break
+        assert n == len(buf) or src.readinto(memoryview(bytearray(16))) == 0       # short only at the end of the file
+        out += buf[:n]
+    is_bgzf = src.bgzf
+    src.close()
+    return bytes(out), is_bgzf
+
+
+@pytest.mark.parametrize("sizes", [[1 << 20], [7, 100000, 1, 65536, 333]])
+def test_gzsrc_bgzf_and_plain_gzip(tmp_path, sizes):
+    rng = np.random.default_rng(8)
+    data = text_of(make_records(20000)) + bytes(rng.integers(0, 256, 70000, dtype=np.uint8))
+    p = str(tmp_path / "x.bgz")
+    open(p, "wb").write(bgzf_bytes(data, block=int(rng.integers(2000, 65000))))
+    got, is_bgzf = gz_read_all(p, sizes)
+    assert is_bgzf and got == data
+    open(p, "wb").write(bgzf_bytes(data, eof_marker=False))
+    assert gz_read_all(p, sizes, n_threads=1) == (data, True)
+    p2 = str(tmp_path / "y.gz")                                   # ordinary gzip: single member, then two members
+    open(p2, "wb").write(gzip.compress(data))
+    assert gz_read_all(p2, sizes) == (data, False)
+    open(p2, "wb").write(gzip.compress(data[:50000]) + gzip.compress(data[50000:]))
+    assert gz_read_all(p2, sizes) == (data, False)
+
+
+def test_gzsrc_errors(tmp_path):
+    data = text_of(make_records(3000))
+    good = bgzf_bytes(data, block=5000)
+    p = str(tmp_path / "bad.bgz")
+    bad = bytearray(good)
+    bad[len(bad) // 2] ^= 0x55                                     # a flipped bit inside some block
+    open(p, "wb").write(bytes(bad))
+    with pytest.raises(_ffi.PclError):
+        gz_read_all(p, [1 << 20])
+    open(p, "wb").write(good[:len(good) // 2])                      # cut inside a block
+    with pytest.raises(_ffi.PclError):
+        gz_read_all(p, [1 << 20])
+    open(p, "wb").write(gzip.compress(data)[:-20])                  # truncated ordinary gzip
+    with pytest.raises(_ffi.PclError):
+        gz_read_all(p, [1 << 20])
+    with pytest.raises(_ffi.PclError):
+        from precellar_b200.textingest import GzSource
+        GzSource(str(tmp_path / "missing.gz"))
