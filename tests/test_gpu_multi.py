@@ -1,0 +1,23 @@
+"""GPU tier, N > 1: the real NCCL path.  Two (or more) processes, one per GPU, each on its contiguous shard;
+the concatenated results and the all-reduced counts must equal the single-process oracle on the whole input
+(v3, sci-RNA-seq3 and ATAC-like layouts, two chunks per rank).  Skipped on a box with one GPU."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_two_gpus_reproduce_the_single_process_oracle():
+    import torch
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("needs at least two GPUs")
+    world = 2 if n < 4 else 4
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
+           "--master-port", "29533", os.path.join(ROOT, "tests", "multi_gpu_worker.py")]
+    p = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=900)
+    assert p.returncode == 0 and "MULTI_GPU_PARITY_OK" in p.stdout, p.stdout[-3000:] + p.stderr[-3000:]
