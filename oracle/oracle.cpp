@@ -4,8 +4,9 @@
 // fp64, on purpose: the point is to follow the reference line by line, not to be fast.
 // All citations are relative to the precellar repository root.
 //
-// Parity status: split() pinned by the reference's 11 known-answer vectors; counting and
-// correction are "parity unpinned" (the reference has no test for them).
+// Parity status: split() pinned by the reference's 11 known-answer vectors and, end to end, by its golden
+// output files test{2,3,4}.out.gz; counting and correction are "parity unpinned" (the reference has no
+// test for them; a second independent restatement must agree, tests/test_oracle_independent.py).
 
 #include "oracle.h"
 

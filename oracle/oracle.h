@@ -12,10 +12,14 @@
  * (paths relative to the precellar repository root).
  *
  * Parity pinning: split() is pinned by the reference's own 11 known-answer vectors
- * (seqspec/src/read/segment.rs:617-705) -- see tests/test_oracle_golden.py.
+ * (seqspec/src/read/segment.rs:617-705) -- see tests/test_oracle_golden.py -- and the
+ * extraction end to end (YAML -> region table -> split -> barcode join -> read1/read2) by the
+ * reference's golden output files precellar/data/test{2,3,4}.out.gz (750 lines of three real
+ * assays; inputs rebuilt from the outputs, tests/test_reference_outputs.py).
  * Counting / correction have no test in the reference: "parity unpinned" for
  * WhitelistBuilder, likelihood1 and correct_barcode (restatement reviewed line by line,
- * exercised with hand-computed cases in tests/test_oracle_correction.py).
+ * exercised with hand-computed cases in tests/test_oracle_correction.py, and required to
+ * agree bit for bit with a second, independent restatement, tests/test_oracle_independent.py).
  */
 #ifndef PRECELLAR_ORACLE_H
 #define PRECELLAR_ORACLE_H
