@@ -183,12 +183,17 @@ def emul_lib():
     global _emul
     if _emul is None:
         src = os.path.join(HERE, "emul", "emul.cpp")
-        so = os.path.join(HERE, "emul", "libemul.so")
+        # PCL_EMUL_SANITIZE=1: build the host copy of the device code with ASan + UBSan (run pytest with
+        # LD_PRELOAD=$(gcc -print-file-name=libasan.so)); compute-sanitizer is not available on the GPU pool, so this is
+        # how out-of-bounds accesses in the __host__ __device__ record logic are hunted
+        san = os.environ.get("PCL_EMUL_SANITIZE") == "1"
+        so = os.path.join(HERE, "emul", "libemul_san.so" if san else "libemul.so")
         deps = [src] + [os.path.join(HERE, "..", "precellar_b200", "csrc", f) for f in ("hd_core.h", "host_build.h")] + \
                [os.path.join(HERE, "..", "include", "precellar_b200.h")]
         if not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
-            subprocess.check_call(["g++", "-O2", "-g", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off",
-                                   "-o", so, src])
+            subprocess.check_call(["g++", "-O1" if san else "-O2", "-g", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off"] +
+                                  (["-fsanitize=address,undefined", "-fno-sanitize-recover=undefined", "-fno-omit-frame-pointer"] if san else []) +
+                                  ["-o", so, src])
         _emul = C.CDLL(so)
     return _emul
 
