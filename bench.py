@@ -482,7 +482,8 @@ def main():
         bounds = np.linspace(0, n, nc + 1).astype(np.int64)
         cap = int(np.max(np.diff(bounds)))
         qo, qs = pipe.qual_window(0)             # the quality plane only covers the barcode bases (16 of 28 bytes)
-        seq_h, _p1 = pinned(n * 32, np.uint8, (n, 32))
+        st1 = pipe.payload_bytes(0)              # compact upload rows: the 28 bytes of R1 the layout uses (device rows are 32)
+        seq_h, _p1 = pinned(n * st1, np.uint8, (n, st1))
         qual_h, _p2 = pinned(n * qs, np.uint8, (n, qs))
         len_h, _p3 = pinned(n * 2, np.uint16, (n,))
         len2_h, _p4 = pinned(n * 2, np.uint16, (n,))
@@ -492,7 +493,13 @@ def main():
         fs2_h, _p8 = pinned(n * 2, np.uint16, (n,))
         tc2_h, _p9 = pinned(n * 4, np.uint32, (n,))
         # same bytes as the resident shard: copy them out of the device planes (generator parity is tested separately)
-        syn.memcpy_d2h(local_rank, seq_h.ctypes.data, s1, n * 32)
+        dst1 = pipe.stride(0)
+        for lo in range(0, n, 1 << 24):          # device rows (32 B) -> host rows (28 B), in slices
+            hi = min(n, lo + (1 << 24))
+            tmp = np.empty((hi - lo, dst1), np.uint8)
+            syn.memcpy_d2h(local_rank, tmp.ctypes.data, s1 + lo * dst1, (hi - lo) * dst1)
+            seq_h[lo:hi] = tmp[:, :st1]
+        del tmp
         syn.memcpy_d2h(local_rank, qual_h.ctypes.data, q1, n * qs)
         syn.memcpy_d2h(local_rank, len_h.ctypes.data, l1, n * 2)
         syn.memcpy_d2h(local_rank, len2_h.ctypes.data, l2, n * 2)
@@ -504,7 +511,7 @@ def main():
             r1 = ReadResults(pipe.infos[0], fs1_h[lo:hi], None, [bck_h[lo:hi]], [umi_h[lo:hi]], [None], [None])
             r2 = ReadResults(pipe.infos[1], fs2_h[lo:hi], tc2_h[lo:hi], [], [], [], [])
             outs.append((r1, r2))
-        h2d = n * (32 + qs + 2 + 2)
+        h2d = n * (st1 + qs + 2 + 2)
         d2h = n * (2 + 4 + 4 + 2 + 4)
 
         def step_e2e():
@@ -512,7 +519,7 @@ def main():
             for c, ch in enumerate(chunks):
                 lo, hi = int(bounds[c]), int(bounds[c + 1])
                 ch.reset(hi - lo)
-                ch.upload(0, HostBatch(seq_h[lo:hi], qual_h[lo:hi], len_h[lo:hi]))
+                ch.upload_compact(0, HostBatch(seq_h[lo:hi], qual_h[lo:hi], len_h[lo:hi]))
                 ch.upload(1, HostBatch(None, None, len2_h[lo:hi]))
                 pipe.count(ch)
                 # UMI keys and insert coordinates are final after pass 1: they travel back while later chunks upload
@@ -536,7 +543,7 @@ def main():
         e2e = {"value": n * world / dt, "unit": "read-pairs/s", "h2d_bytes_per_step": int(h2d) * world,
                "d2h_bytes_per_step": int(d2h) * world, "h2d_bytes_per_step_per_gpu": int(h2d),
                "d2h_bytes_per_step_per_gpu": int(d2h), "ms_per_step": dt * 1e3, "chunks": nc,
-               "note": "pinned host SoA planes -> H2D -> count -> allreduce -> correct -> D2H of every result plane"}
+               "note": "pinned host SoA planes (R1 rows of the 28 bytes the layout uses, widened to 32 on the device) -> H2D -> count -> allreduce -> correct -> D2H of every result plane"}
 
         # ------------------------------------------------------------- CPU baseline + parity on a bounded sample
         if rank == 0 and world == 1 and not args.no_cpu:

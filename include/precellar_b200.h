@@ -202,6 +202,13 @@ uint32_t pcl_read_stride(const pcl_ctx *ctx, int read_slot);
  * seq/qual may be NULL when !needs_payload.  Host buffers should be pinned (pcl_host_alloc) and must
  * stay valid until the next blocking call on the chunk. */
 int pcl_chunk_upload(pcl_chunk *chunk, int read_slot, const uint8_t *seq, const uint8_t *qual, const uint16_t *len);
+/* The same with sequence rows of `row_bytes` instead of pcl_read_stride bytes: the host-to-device copy bounds the
+ * end-to-end rate, so a caller may hand over only the bytes the layout can touch (pcl_read_payload_bytes, a multiple
+ * of 4: 28 instead of 32 for 10x v3 R1); the rows are widened on the device.  row_bytes must be a multiple of 4 in
+ * [pcl_read_payload_bytes, pcl_read_stride].  The quality and length planes are as for pcl_chunk_upload. */
+int pcl_chunk_upload_compact(pcl_chunk *chunk, int read_slot, const uint8_t *seq, uint32_t row_bytes, const uint8_t *qual,
+                             const uint16_t *len);
+uint32_t pcl_read_payload_bytes(const pcl_ctx *ctx, int read_slot);
 /* Zero-copy producers (a GPU-side decoder or generator) may fill the device planes directly. */
 int pcl_chunk_device_ptrs(pcl_chunk *chunk, int read_slot, void **seq, void **qual, void **len);
 void *pcl_chunk_stream(pcl_chunk *chunk);                        /* cudaStream_t of the chunk        */

@@ -77,6 +77,7 @@ SYMBOLS = [
     "pcl_fastq_open", "pcl_fastq_close", "pcl_fastq_error", "pcl_fastq_read", "pcl_chunk_fetch_async",
     "pcl_make_fastq_batch",
     "pcl_text_scan", "pcl_text_lines", "pcl_text_fill", "pcl_text_names_check", "pcl_text_line_ends",
+    "pcl_chunk_upload_compact", "pcl_read_payload_bytes",
     "pcl_gzsrc_open", "pcl_gzsrc_read", "pcl_gzsrc_is_bgzf", "pcl_gzsrc_error", "pcl_gzsrc_close",
 ]
 
@@ -111,6 +112,8 @@ def lib() -> C.CDLL:
         "pcl_chunk_reset": (i32, [vp, u64]),
         "pcl_read_stride": (u32, [vp, i32]),
         "pcl_chunk_upload": (i32, [vp, i32, vp, vp, vp]),
+        "pcl_chunk_upload_compact": (i32, [vp, i32, vp, u32, vp, vp]),
+        "pcl_read_payload_bytes": (u32, [vp, i32]),
         "pcl_chunk_device_ptrs": (i32, [vp, i32, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]),
         "pcl_chunk_stream": (vp, [vp]),
         "pcl_counts_reset": (i32, [vp]),

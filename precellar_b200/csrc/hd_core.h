@@ -61,7 +61,8 @@ struct DRead {
     uint32_t max_len;    // reader truncation, 0 = none
     uint32_t stride;     // bytes per record slot
     uint8_t n_bc, n_umi, has_target, needs_payload;
-    uint8_t qual_only, codes_ok, pad0[2];   // qual_only: QC-mode insert read; codes_ok: pcl_split_codes / pcl_pack_codes apply
+    uint8_t qual_only, codes_ok;            // qual_only: QC-mode insert read; codes_ok: pcl_split_codes / pcl_pack_codes apply
+    uint16_t payload_bytes;                 // record bytes the path can touch, rounded up to 4 (<= stride): the compact upload row
     uint32_t qoff, qstride;       // the quality plane holds record bytes [qoff, qoff + qstride) per record
     DElem elems[PCL_MAX_ELEMS];
     FastLayout fast;

@@ -121,6 +121,7 @@ inline int pcl_build_read(int r, const pcl_read_desc &rd, DRead *out, pcl_read_i
         return pcl_build_fail(err, PCL_ERR_UNSUPPORTED, "read %d: %u payload bytes per record exceed %d", r, stride, PCL_MAX_STRIDE);
     if (start > 0xFFFF) return pcl_build_fail(err, PCL_ERR_UNSUPPORTED, "read %d: layout longer than 65535", r);
     d.stride = stride;
+    d.payload_bytes = (uint16_t)(((need + 3u) / 4u) * 4u);
     // quality window: only barcode bases are read by the correction pass
     d.qoff = 0; d.qstride = stride;
     if (!qc && fixed && info.n_bc >= 1) {

@@ -680,4 +680,16 @@ __global__ void k_gather_counts(const uint32_t *__restrict__ counts, const uint3
         out[i] = counts[index_to_slot[i]];
 }
 
+// pcl_chunk_upload_compact: rows of `src_bytes` (a multiple of 4) -> rows of `dst_bytes` (the device stride), the tail
+// filled with 'N' like the host reader does.  One 32-bit word per thread, coalesced on both sides.
+__global__ void __launch_bounds__(PCL_BLOCK) k_repack_rows(const uint32_t *__restrict__ src, uint32_t src_words,
+                                                           uint32_t *__restrict__ dst, uint32_t dst_words, uint64_t n_rows) {
+    const uint64_t total = n_rows * dst_words;
+    for (uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t row = g / dst_words;
+        const uint32_t k = (uint32_t)(g - row * dst_words);
+        dst[g] = k < src_words ? __ldcs(src + row * src_words + k) : 0x4E4E4E4Eu;
+    }
+}
+
 #endif  // PCL_KERNELS_CUH

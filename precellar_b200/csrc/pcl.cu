@@ -138,6 +138,7 @@ struct ReadBuf {
     uint32_t *ucoord[PCL_MAX_UMI_PER_READ] = {nullptr};
     unsigned long long *worklist = nullptr;
     unsigned long long *wl_count = nullptr;
+    uint8_t *seq_stage = nullptr;             // pcl_chunk_upload_compact: the rows as uploaded, before k_repack_rows
     bool filled = false;
     // device-side text parse (pcl_text_*): name hashes and the small result words of this chunk's parse
     uint64_t *d_hash = nullptr;
@@ -391,6 +392,11 @@ int pcl_read_info_get(const pcl_ctx *ctx, int read_slot, pcl_read_info *out) {
     return PCL_OK;
 }
 
+uint32_t pcl_read_payload_bytes(const pcl_ctx *ctx, int read_slot) {
+    if (!ctx || read_slot < 0 || read_slot >= ctx->n_reads) return 0;
+    return ctx->dreads[read_slot].needs_payload ? ctx->dreads[read_slot].payload_bytes : 0;
+}
+
 uint32_t pcl_read_stride(const pcl_ctx *ctx, int read_slot) {
     if (!ctx || read_slot < 0 || read_slot >= ctx->n_reads) return 0;
     return ctx->dreads[read_slot].stride;
@@ -558,6 +564,33 @@ int pcl_chunk_upload(pcl_chunk *c, int read_slot, const uint8_t *seq, const uint
         if (!qual) return fail(ctx, PCL_ERR_ARG, "read %d needs its quality plane (FASTQ QC is enabled)", read_slot);
         CU(ctx, cudaMemcpyAsync(b.qual, qual, c->n * d.qstride, cudaMemcpyHostToDevice, c->stream));
     }
+    CU(ctx, cudaMemcpyAsync(b.len, len, c->n * 2, cudaMemcpyHostToDevice, c->stream));
+    b.filled = true;
+    return PCL_OK;
+}
+
+int pcl_chunk_upload_compact(pcl_chunk *c, int read_slot, const uint8_t *seq, uint32_t row_bytes, const uint8_t *qual,
+                             const uint16_t *len) {
+    if (!c) return PCL_ERR_ARG;
+    pcl_ctx *ctx = c->ctx;
+    if (read_slot < 0 || read_slot >= ctx->n_reads) return fail(ctx, PCL_ERR_ARG, "bad read_slot");
+    const DRead &d = ctx->dreads[read_slot];
+    if (!d.needs_payload || row_bytes == d.stride) return pcl_chunk_upload(c, read_slot, seq, qual, len);
+    if ((row_bytes & 3u) || row_bytes < d.payload_bytes || row_bytes > d.stride)
+        return fail(ctx, PCL_ERR_ARG, "read %d: compact rows must be a multiple of 4 bytes in [%u, %u]", read_slot,
+                    (unsigned)d.payload_bytes, d.stride);
+    if (!seq || !len || (!qual && d.qstride)) return fail(ctx, PCL_ERR_ARG, "read %d needs seq, qual and len planes", read_slot);
+    if (int r = bind(ctx)) return r;
+    ReadBuf &b = c->rb[read_slot];
+    if (!b.seq_stage) if (int r = chunk_alloc(c, (void **)&b.seq_stage, c->cap * (uint64_t)d.stride)) return r;
+    CU(ctx, cudaMemcpyAsync(b.seq_stage, seq, c->n * (uint64_t)row_bytes, cudaMemcpyHostToDevice, c->stream));
+    if (c->n) {
+        k_repack_rows<<<grid_for(ctx, c->n * (d.stride / 4), 8), PCL_BLOCK, 0, c->stream>>>(
+            reinterpret_cast<const uint32_t *>(b.seq_stage), row_bytes / 4, reinterpret_cast<uint32_t *>(b.seq), d.stride / 4, c->n);
+        ctx->launches += 1;
+        CU(ctx, cudaGetLastError());
+    }
+    if (d.qstride) CU(ctx, cudaMemcpyAsync(b.qual, qual, c->n * (uint64_t)d.qstride, cudaMemcpyHostToDevice, c->stream));
     CU(ctx, cudaMemcpyAsync(b.len, len, c->n * 2, cudaMemcpyHostToDevice, c->stream));
     b.filled = true;
     return PCL_OK;

@@ -73,6 +73,23 @@ class Chunk:
         self._keep.append((batch, length))
         check(self.pipe.ctx, lib().pcl_chunk_upload(self.h, read_slot, sp, qp, length.ctypes.data))
 
+    def upload_compact(self, read_slot: int, batch: HostBatch) -> None:
+        """``upload`` with sequence rows narrower than the device stride (any multiple of 4 bytes from
+        ``BarcodePipeline.payload_bytes`` up): fewer bytes over PCIe, widened on the device."""
+        length = np.ascontiguousarray(batch.length, dtype=np.uint16)
+        assert len(length) == self.n
+        info = self.pipe.infos[read_slot]
+        if not info.needs_payload:
+            return self.upload(read_slot, batch)
+        assert batch.seq is not None and batch.seq.dtype == np.uint8 and batch.seq.flags.c_contiguous and batch.seq.shape[0] == self.n
+        qp = None
+        if info.qual_stride:
+            assert batch.qual is not None and batch.qual.shape == (self.n, info.qual_stride) and batch.qual.flags.c_contiguous
+            qp = batch.qual.ctypes.data
+        self._keep.append((batch, length))
+        check(self.pipe.ctx, lib().pcl_chunk_upload_compact(self.h, read_slot, batch.seq.ctypes.data, batch.seq.shape[1], qp,
+                                                            length.ctypes.data))
+
     # -- device-side FASTQ parse (pcl_text_*) ----------------------------------------------------------
     def text_scan(self, read_slot: int, text: np.ndarray, n_bytes: Optional[int] = None) -> None:
         """Copy a block of uncompressed FASTQ text (uint8, starting at a record boundary) to the device and index
@@ -240,6 +257,10 @@ class BarcodePipeline:
         seq = cut(seq_full, 0, st, ord("N")) if info.needs_payload else None
         qual = cut(qual_full, qo, qs, ord("!")) if (info.needs_payload or info.qual_only) else None
         return HostBatch(seq, qual, length)
+
+    def payload_bytes(self, read_slot: int) -> int:
+        """Record bytes the path can touch, rounded up to 4: the narrowest row ``Chunk.upload_compact`` accepts."""
+        return lib().pcl_read_payload_bytes(self.ctx, read_slot)
 
     def whitelist_size(self, slot: int) -> int:
         return lib().pcl_whitelist_size(self.ctx, slot)

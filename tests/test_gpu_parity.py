@@ -324,3 +324,59 @@ def test_empty_chunk_and_reuse():
             U.compare_with_oracle(layout, infos, full, results, counts, pipe.qc()[:, 1], ores, ocounts)
     finally:
         pipe.close()
+
+
+@pytest.mark.parametrize("name", ["v3", "fast12_tail", "v2", "atac", "sci3"])
+def test_compact_upload_gives_the_same_results(layouts, name):
+    """pcl_chunk_upload_compact: sequence rows cut down to pcl_read_payload_bytes (and one size in between) are widened
+    on the device; every result plane and count equals the full-stride upload."""
+    from precellar_b200.pipeline import BarcodePipeline, HostBatch
+    layout = layouts[name]
+    rng = np.random.default_rng(U.seed_of(name, "compact"))
+    infos, strides = U.emul_infos(layout)
+    n = 2500
+    multi = len(layout.region_ids) > 1
+    full = U.gen_reads(rng, layout, n, strides, p_short=0.0 if multi else 0.03, p_tiny=0.03 if multi else 0.0)
+    dev = U.narrow(full, strides, infos)
+    ref = run_gpu(layout, dev)
+
+    def run(width_of):
+        pipe = BarcodePipeline(layout)
+        try:
+            ch = pipe.new_chunk(n)
+            ch.reset(n)
+            for r, b in enumerate(dev):
+                if b.seq is None:
+                    ch.upload(r, b)
+                    continue
+                w = width_of(pipe, r)
+                assert pipe.payload_bytes(r) <= w <= pipe.stride(r) and w % 4 == 0
+                ch.upload_compact(r, HostBatch(np.ascontiguousarray(b.seq[:, :w]), b.qual, b.length))
+            pipe.count(ch)
+            pipe.allreduce()
+            pipe.correct(ch, 0.975)
+            return [ch.fetch(r) for r in range(len(dev))], {g: pipe.counts(g) for g in range(len(layout.region_ids))}
+        finally:
+            pipe.close()
+    for width_of in (lambda p, r: p.payload_bytes(r), lambda p, r: min(p.stride(r), p.payload_bytes(r) + 4)):
+        res, counts = run(width_of)
+        for a, b in zip(res, ref[1]):
+            assert np.array_equal(a.fstatus, b.fstatus)
+            for x, y in zip(a.bc_key + a.umi_key, b.bc_key + b.umi_key):
+                assert np.array_equal(x, y)
+            for x, y in zip([a.tcoord] + a.bcoord + a.ucoord, [b.tcoord] + b.bcoord + b.ucoord):
+                assert (x is None and y is None) or np.array_equal(x, y)
+        for g in counts:
+            assert np.array_equal(counts[g][0], ref[2][g][0]) and counts[g][1:] == ref[2][g][1:]
+    # rows outside [payload_bytes, stride] or not a multiple of 4 are rejected
+    pipe = BarcodePipeline(layout)
+    try:
+        r = next(i for i, b in enumerate(dev) if b.seq is not None)
+        ch = pipe.new_chunk(8)
+        ch.reset(8)
+        bad = HostBatch(np.zeros((8, pipe.payload_bytes(r) - 4 if pipe.payload_bytes(r) > 4 else 2), np.uint8),
+                        None if dev[r].qual is None else np.ascontiguousarray(dev[r].qual[:8]), dev[r].length[:8])
+        with pytest.raises(_ffi.PclError):
+            ch.upload_compact(r, bad)
+    finally:
+        pipe.close()
