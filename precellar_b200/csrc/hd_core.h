@@ -54,6 +54,18 @@ struct FastLayout {
     uint32_t bc_mask[8], umi_mask[8];               // byte masks of the two regions over the 8 record words
 };
 
+// Layouts of the shape  [fixed ...] [ONE variable element] [anchor] [fixed ...] [optional trailing variable element]
+// with <= 16-base barcodes / anchors and <= 15-base UMIs (sci-RNA-seq3 R1, dscATAC R1 ...): everything but the anchor
+// position is known when the layout is compiled, so split() collapses to a handful of comparisons (pcl_anchor_split)
+// and every field is cut out of the record's code string at a warp-uniform offset (k_count_anchor).
+struct AnchorPlan {
+    uint8_t enabled;
+    uint8_t v;                       // index of the variable element; the anchor is element v + 1
+    uint8_t has_t;                   // the last element is variable too
+    uint8_t t_elem;                  // the (only) target element, 0xFF if none
+    uint8_t ustart[PCL_MAX_ELEMS];   // start of element e when the variable element has its minimal length
+};
+
 struct DRead {
     uint16_t n_elems;
     uint8_t is_reverse;
@@ -66,6 +78,7 @@ struct DRead {
     uint32_t qoff, qstride;       // the quality plane holds record bytes [qoff, qoff + qstride) per record
     DElem elems[PCL_MAX_ELEMS];
     FastLayout fast;
+    AnchorPlan plan;
 };
 
 // Whitelist hash table of one barcode region: buckets of 32 bytes (one DRAM/L2 sector) holding
@@ -735,6 +748,177 @@ struct CodeMatcher {
 PCL_HD void pcl_split_codes(const DRead &rd, const RecCodes &rc, uint32_t len, SplitOut &o) {
     CodeMatcher m{&rc, rd.is_reverse != 0};
     pcl_split_t(rd, len, o, m);
+}
+
+// ------------------------------------------------------------------------------------------
+// AnchorPlan path: 32-bit code strings (16 bases per word) and the collapsed split
+// ------------------------------------------------------------------------------------------
+struct Codes32 {
+    uint32_t c[4];      // 2-bit code of base i at bits 2(i % 16) of word i / 16
+    uint32_t bd[4];     // bit 2(i % 16) set: byte i is not a base for barcodes / UMIs (case folded on neg-strand reads)
+    uint32_t sb[4];     // the same with the strict upper-case test used for anchors (== bd on forward reads)
+};
+
+template <bool kRev>
+PCL_HD void pcl_codes32_t(const uint32_t *w, int n_words, Codes32 &k) {
+#ifdef __CUDA_ARCH__
+#pragma unroll
+#endif
+    for (int g = 0; g < 4; ++g) {
+        uint32_t c = 0, b = 0, sb = 0;
+        if (4 * g < n_words) {                                    // warp-uniform: the record's words come in groups of four
+#ifdef __CUDA_ARCH__
+#pragma unroll
+#endif
+            for (int q = 0; q < 4; ++q) {
+                const uint32_t x = w[4 * g + q];
+                uint32_t bad;
+                const uint32_t c8 = pcl_word_codes(kRev ? (x & 0xDFDFDFDFu) : x, &bad);
+                const uint32_t nb = ((((bad & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | bad) & 0x80808080u) >> 7;
+                c |= c8 << (8 * q);
+                b |= ((nb * 0x01041040u) >> 24) << (8 * q);
+                if (kRev) {
+                    uint32_t sbad;
+                    (void)pcl_word_codes(x, &sbad);
+                    const uint32_t ns = ((((sbad & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | sbad) & 0x80808080u) >> 7;
+                    sb |= ((ns * 0x01041040u) >> 24) << (8 * q);
+                }
+            }
+        }
+        k.c[g] = c; k.bd[g] = b; k.sb[g] = kRev ? sb : b;
+    }
+}
+
+// bases [start, start + len) of a code string as a 32-bit field (len <= 16, start + len <= 64)
+PCL_HD uint32_t pcl_win32(const uint32_t *c, uint32_t start, uint32_t len) {
+    const uint32_t wi = start >> 4, sh = (start & 15u) * 2u;
+    const uint32_t a = wi == 0u ? c[0] : wi == 1u ? c[1] : wi == 2u ? c[2] : c[3];
+    const uint32_t b = wi == 0u ? c[1] : wi == 1u ? c[2] : wi == 2u ? c[3] : 0u;
+#ifdef __CUDA_ARCH__
+    const uint32_t v = __funnelshift_r(a, b, sh);
+#else
+    const uint32_t v = sh ? (a >> sh) | (b << (32u - sh)) : a;
+#endif
+    return len >= 16u ? v : (v & ((1u << (2u * len)) - 1u));
+}
+
+// the whole string shifted down by `bases` (< 16) bases
+PCL_HD void pcl_shr_bases(const uint32_t *in, uint32_t bases, uint32_t *out) {
+    const uint32_t sh = 2u * bases;
+#ifdef __CUDA_ARCH__
+    out[0] = __funnelshift_r(in[0], in[1], sh); out[1] = __funnelshift_r(in[1], in[2], sh);
+    out[2] = __funnelshift_r(in[2], in[3], sh); out[3] = in[3] >> sh;
+#else
+    for (int k = 0; k < 4; ++k) out[k] = sh ? (in[k] >> sh) | ((k < 3 ? in[k + 1] : 0u) << (32u - sh)) : in[k];
+#endif
+}
+
+struct AnchorSplit {
+    uint32_t status;     // PCL_SPLIT_OK / ANCHOR_NOT_FOUND / PATTERN_MISMATCH
+    uint32_t reach;      // elements [0, reach) have a segment
+    uint32_t pos;        // anchor position inside its window (0 unless the anchor matched)
+    uint32_t v_len;      // length of the variable element's segment
+    uint32_t t_len;      // length of the trailing variable element's segment
+};
+
+// split_with_tolerance (segment.rs:180-368) for an AnchorPlan layout; same control flow as pcl_split_t, element by element
+PCL_HD void pcl_anchor_split(const DRead &rd, const Codes32 &k, uint32_t len, AnchorSplit &s) {
+    const AnchorPlan &pl = rd.plan;
+    const uint32_t v = pl.v, a = v + 1u, n = rd.n_elems;
+    const bool rev = rd.is_reverse != 0;
+    s.status = PCL_SPLIT_OK; s.reach = 0; s.pos = 0; s.v_len = 0; s.t_len = 0;
+    uint32_t off = 0;
+    for (uint32_t e = 0; e < v; ++e) {                                            // fixed elements, empty buffer (segment.rs:315-344)
+        const uint32_t l = rd.elems[e].max_len;
+        if (off >= len || off + l > len) return;                                  // :245-248
+        s.reach = e + 1u;
+        off += l;
+    }
+    const uint32_t vmin = rd.elems[v].min_len, vmax = rd.elems[v].max_len;
+    if (off >= len || off + vmin > len) return;
+    const uint32_t min_off = off + vmin, max_off = off + vmax;                    // buffer = [v]
+    const uint32_t m = rd.elems[a].max_len;                                       // == seq_len
+    const uint32_t tail_hi = max_off < len ? max_off : len;
+    if (max_off >= len || min_off + m > len) {                                    // the loop breaks at the anchor: tail consume_buf (:353-365)
+        s.reach = v + 1u; s.v_len = tail_hi - off;
+        return;
+    }
+    const uint32_t wend = max_off + m < len ? max_off + m : len, wn = wend - min_off;      // :258-262, wn >= m
+    const uint32_t needle = (uint32_t)(rev ? rd.elems[a].a_rc : rd.elems[a].a_code);
+    const uint32_t even = m >= 16u ? 0x55555555u : (0x55555555u & ((1u << (2u * m)) - 1u));
+    uint32_t best = 0xFFFFFFFFu, bpos = 0;
+    for (uint32_t i = 0; i + m <= wn; ++i) {                                      // find_best_pattern_match (:496-535)
+        const uint32_t p = min_off + (rev ? wn - m - i : i);                      // neg strand: position i of rev_compl(window)
+        const uint32_t x = pcl_win32(k.c, p, m) ^ needle;
+        const uint32_t d = ((x | (x >> 1)) | pcl_win32(k.sb, p, m)) & even;
+#ifdef __CUDA_ARCH__
+        const uint32_t cnt = (uint32_t)__popc(d);
+#else
+        const uint32_t cnt = (uint32_t)__builtin_popcount(d);
+#endif
+        if (cnt < best) { best = cnt; bpos = i; if (cnt == 0u) break; }
+    }
+    if (m == 1u && best != 0u) { s.status = PCL_SPLIT_ANCHOR_NOT_FOUND; return; } // (None, 1) (:508-512)
+    if (best > rd.elems[a].max_mis) {
+        if (max_off + m > len) { s.reach = v + 1u; s.v_len = tail_hi - off; return; }       // :303-305, then the tail consume
+        s.status = PCL_SPLIT_PATTERN_MISMATCH;                                    // :306-308
+        return;
+    }
+    s.pos = bpos;
+    s.v_len = vmin + bpos;                                                        // [offset_left, offset_right)
+    s.reach = a + 1u;
+    off = min_off + bpos + m;
+    const uint32_t n_fixed_end = pl.has_t ? n - 1u : n;
+    for (uint32_t e = a + 1u; e < n_fixed_end; ++e) {
+        const uint32_t l = rd.elems[e].max_len;
+        if (off >= len || off + l > len) return;
+        s.reach = e + 1u;
+        off += l;
+    }
+    if (pl.has_t) {
+        const uint32_t tmin = rd.elems[n - 1u].min_len, tmax = rd.elems[n - 1u].max_len;
+        if (off >= len || off + tmin > len) return;
+        s.reach = n;
+        s.t_len = (off + tmax < len ? off + tmax : len) - off;                    // tail consume_buf
+    }
+}
+
+// (start << 16 | len) of element e after pcl_anchor_split, or PCL_COORD_ABSENT
+PCL_HD uint32_t pcl_anchor_coord(const DRead &rd, const AnchorSplit &s, uint32_t e) {
+    if (s.status != PCL_SPLIT_OK || e >= s.reach) return PCL_COORD_ABSENT;
+    const AnchorPlan &pl = rd.plan;
+    const uint32_t start = pl.ustart[e] + (e > pl.v ? s.pos : 0u);
+    const uint32_t l = e == pl.v ? s.v_len : (pl.has_t && e + 1u == rd.n_elems) ? s.t_len : rd.elems[e].max_len;
+    return (start << 16) | l;
+}
+
+// Device-form 32-bit key (marker kept below 16 bases) of the field at coordinate `coord`; `k2` holds the strings
+// shifted down by s.pos bases, so that elements behind the anchor sit at the warp-uniform offset ustart[e].
+PCL_HD uint32_t pcl_anchor_key(const DRead &rd, const Codes32 &k, const uint32_t *c2, const uint32_t *bd2, uint32_t e, uint32_t coord,
+                               uint32_t *n_invalid) {
+    const uint32_t len = coord & 0xFFFFu, us = rd.plan.ustart[e];
+    const bool behind = e > rd.plan.v;
+    const uint32_t wlen = len > 16u ? 16u : len;
+    if (wlen == 0u) { *n_invalid = 0; return 1u; }                                // an empty field: marker only, like pcl_pack_key
+    uint32_t f = pcl_win32(behind ? c2 : k.c, us, wlen);
+    const uint32_t bad = pcl_win32(behind ? bd2 : k.bd, us, wlen);
+#ifdef __CUDA_ARCH__
+    *n_invalid = (uint32_t)__popc(bad);
+#else
+    *n_invalid = (uint32_t)__builtin_popcount(bad);
+#endif
+    const uint32_t bad2 = bad | (bad << 1);
+    const bool rev = rd.is_reverse != 0;
+    uint32_t key;
+    if (rev) {
+        const uint32_t mask = wlen >= 16u ? 0xFFFFFFFFu : ((1u << (2u * wlen)) - 1u);
+        key = (~f) & mask & ~bad2;                                               // reverse complement == complement read big-endian
+    } else {
+        f &= ~bad2;                                                               // an invalid base reads as 0, like pcl_pack_key
+        key = pcl_field_to_key(f, 0u, wlen, false);
+    }
+    if (wlen < 16u) key |= 1u << (2u * wlen);
+    return key;
 }
 
 // Store a key in its device width (see precellar_b200.h).

@@ -44,6 +44,7 @@ inline int pcl_build_read(int r, const pcl_read_desc &rd, DRead *out, pcl_read_i
     d.max_len = rd.max_len;
     bool fixed = true, payload = false, anchors_codable = true;
     uint32_t reach = 0, start = 0;
+    bool buffered = false;     // the reference's buffer of unresolved elements is non-empty when the walk reaches this element
     for (int e = 0; e < rd.n_elems; ++e) {
         const pcl_elem_desc &el = rd.elems[e];
         DElem &de = d.elems[e];
@@ -72,7 +73,10 @@ inline int pcl_build_read(int r, const pcl_read_desc &rd, DRead *out, pcl_read_i
             de.a_code = ac; de.a_rc = arc;
             if (!pure) anchors_codable = false;
         }
-        const bool may_anchor = !fixed && el.is_fixed_seq && fixed_len;   // a variable run precedes it
+        // A fixed sequence is searched for only while the buffer holds a variable run (segment.rs:251-254); a match
+        // empties the buffer, so the fixed sequences behind it are taken at face value and their bytes never read.
+        const bool may_anchor = buffered && el.is_fixed_seq && fixed_len;
+        if (may_anchor) buffered = false; else if (!fixed_len) buffered = true;
         if (may_anchor) {
             payload = true;
             if (el.seq_len != el.max_len)
@@ -182,6 +186,47 @@ inline int pcl_build_read(int r, const pcl_read_desc &rd, DRead *out, pcl_read_i
                 f.t_min = last.min_len;
                 f.t_max = last.max_len;
             }
+        }
+    }
+    // AnchorPlan (see hd_core.h): [fixed ...] [one variable] [anchor] [fixed ...] [optional trailing variable]
+    {
+        AnchorPlan &pl = d.plan;
+        const int ne = rd.n_elems;
+        int v = -1;
+        for (int e = 0; e < ne; ++e) if (rd.elems[e].min_len != rd.elems[e].max_len) { v = e; break; }
+        bool ok = !fixed && payload && d.codes_ok && !qc && v >= 0 && v + 1 < ne;
+        if (ok) {
+            const pcl_elem_desc &ve = rd.elems[v], &ae = rd.elems[v + 1];
+            ok = ve.max_len - ve.min_len <= 15 && ae.min_len == ae.max_len && ae.is_fixed_seq && ae.seq_len == ae.max_len &&
+                 ae.seq_len >= 1 && ae.seq_len <= 16;
+        }
+        bool has_t = false;
+        for (int e = v + 2; ok && e < ne; ++e) {
+            if (rd.elems[e].min_len != rd.elems[e].max_len) {
+                if (e == ne - 1) has_t = true; else ok = false;
+            }
+        }
+        int n_t = 0;
+        for (int e = 0; ok && e < ne; ++e) {
+            const pcl_elem_desc &el = rd.elems[e];
+            n_t += el.kind == PCL_KIND_TARGET;
+            if (el.kind == PCL_KIND_BARCODE && (el.max_len > 16 || (el.min_len != el.max_len && el.max_len > 15))) ok = false;
+            if (el.kind == PCL_KIND_UMI && el.max_len > 15) ok = false;
+        }
+        for (int j = 0; ok && j < info.n_bc; ++j) ok = info.bc_key_bytes[j] == 4;
+        for (int j = 0; ok && j < info.n_umi; ++j) ok = info.umi_key_bytes[j] == 4;
+        if (ok && n_t > 1) ok = false;
+        if (ok) {
+            uint32_t off = 0;
+            for (int e = 0; e < ne; ++e) {
+                if (off > 255) { ok = false; break; }
+                pl.ustart[e] = (uint8_t)off;
+                off += e == v ? rd.elems[e].min_len : rd.elems[e].max_len;       // the trailing variable element is last: its length is not needed
+            }
+        }
+        if (ok) {
+            pl.enabled = 1; pl.v = (uint8_t)v; pl.has_t = has_t ? 1 : 0; pl.t_elem = 0xFF;
+            for (int e = 0; e < ne; ++e) if (rd.elems[e].kind == PCL_KIND_TARGET) pl.t_elem = (uint8_t)e;
         }
     }
     *out = d;

@@ -156,10 +156,13 @@ __device__ __forceinline__ uint4 pcl_ld_stream(const uint4 *p) {
     return r;
 }
 
-// kCodes: the record (<= 64 bytes) is converted once to 2-bit codes in registers; anchors are matched and fields
-// are cut in code space (pcl_split_codes / pcl_pack_codes).  Otherwise the record bytes are read on demand.
-template <bool kCodes>
+// kMode 1: the record (<= 64 bytes) is converted once to 2-bit codes in registers; anchors are matched and fields
+// are cut in code space (pcl_split_codes / pcl_pack_codes).  kMode 2: the same for AnchorPlan layouts with 32-bit
+// strings, the collapsed split and warp-uniform field offsets (hd_core.h).  kMode 0: the record bytes are read on demand.
+template <int kMode>
 __global__ void __launch_bounds__(PCL_BLOCK) k_count(const __grid_constant__ CountParams p) {
+    constexpr bool kCodes = kMode == 1;
+    constexpr bool kPlan = kMode == 2;
     __shared__ uint32_t ck[PCL_HCACHE];
     __shared__ uint32_t cc[PCL_HCACHE];
     const DRead &rd = p.rd;
@@ -187,6 +190,74 @@ __global__ void __launch_bounds__(PCL_BLOCK) k_count(const __grid_constant__ Cou
             uint32_t L = p.len[i];
             if (rd.max_len && L > rd.max_len) L = rd.max_len;          // FastqReader::read_record (read.rs:98-103)
             const uint8_t *rec = p.seq + i * (uint64_t)rd.stride;
+            uint32_t fs;
+            if (kPlan) {
+                uint32_t w[16];
+                const uint4 *r4 = reinterpret_cast<const uint4 *>(rec);
+#pragma unroll
+                for (int v = 0; v < 4; ++v) {
+                    uint4 t = make_uint4(0u, 0u, 0u, 0u);
+                    if ((uint32_t)v * 16u < rd.stride) t = pcl_ld_stream(r4 + v);
+                    w[4 * v] = t.x; w[4 * v + 1] = t.y; w[4 * v + 2] = t.z; w[4 * v + 3] = t.w;
+                }
+                const uint32_t nbytes = L < rd.stride ? L : rd.stride;
+                Codes32 k;
+                if (rev) pcl_codes32_t<true>(w, (int)((nbytes + 3u) >> 2), k); else pcl_codes32_t<false>(w, (int)((nbytes + 3u) >> 2), k);
+                AnchorSplit sp;
+                pcl_anchor_split(rd, k, L, sp);
+                uint32_t c2[4], bd2[4];                                 // the strings behind the anchor, at uniform offsets
+                pcl_shr_bases(k.c, sp.pos, c2);
+                pcl_shr_bases(k.bd, sp.pos, bd2);
+                fs = sp.status;
+                if (sp.status != PCL_SPLIT_OK) ++n_defect;
+                if (rd.has_target) {
+                    const uint32_t tc = rd.plan.t_elem != 0xFFu ? pcl_anchor_coord(rd, sp, rd.plan.t_elem) : PCL_COORD_ABSENT;
+                    if (tc != PCL_COORD_ABSENT) fs |= PCL_FSTATUS_TARGET;
+                    p.tcoord[i] = tc;
+                }
+#pragma unroll
+                for (uint32_t j = 0; j < PCL_MAX_BC_PER_READ; ++j) {
+                    if (j >= rd.n_bc) { fs |= PCL_BC_ABSENT << (4 + 3 * j); continue; }
+                    const uint32_t e = p.bc_elem[j];
+                    const uint32_t c = pcl_anchor_coord(rd, sp, e);
+                    p.bcoord[j][i] = c;
+                    uint32_t code = PCL_BC_ABSENT, key = 0;
+                    if (c != PCL_COORD_ABSENT) {
+                        const uint32_t blen = c & 0xFFFFu;
+                        uint32_t ninv;
+                        key = pcl_anchor_key(rd, k, c2, bd2, e, c, &ninv);
+                        const DTable &t = p.tab[j];
+                        uint32_t slot = 0xFFFFFFFFu;
+                        if (ninv == 0u && (t.mode == PCL_TAB_K32_L16 ? blen == 16u : blen <= 15u)) slot = pcl_probe32(t, key);
+                        ++n_total[j];                                  // WhitelistBuilder::add (barcode.rs:410-426)
+                        if (slot != 0xFFFFFFFFu) {
+                            code = PCL_BC_EXACT;
+                            pcl_hist_add(ck, cc, j, slot, t.counts);
+                        } else {
+                            code = PCL_BC_NO_MATCH;
+                            ++n_mis[j];
+                            miss_mask_j |= 1u << j;
+                            miss_coord[j] = c;
+                        }
+                    }
+                    reinterpret_cast<uint32_t *>(p.bc_key[j])[i] = key;
+                    fs |= code << (4 + 3 * j);
+                }
+#pragma unroll
+                for (uint32_t j = 0; j < PCL_MAX_UMI_PER_READ; ++j) {
+                    if (j >= rd.n_umi) continue;
+                    const uint32_t e = p.umi_elem[j];
+                    const uint32_t c = pcl_anchor_coord(rd, sp, e);
+                    p.ucoord[j][i] = c;
+                    uint32_t key = PCL_KEY_ABSENT32;
+                    if (c != PCL_COORD_ABSENT) {
+                        uint32_t ninv;
+                        key = pcl_anchor_key(rd, k, c2, bd2, e, c, &ninv);
+                        if (ninv) key = 0;
+                    }
+                    reinterpret_cast<uint32_t *>(p.umi_key[j])[i] = key;
+                }
+            } else {
             SplitOut so;
             RecCodes rc;
             if (kCodes) {
@@ -205,7 +276,7 @@ __global__ void __launch_bounds__(PCL_BLOCK) k_count(const __grid_constant__ Cou
             } else {
                 pcl_split(rd, rec, L, so);
             }
-            uint32_t fs = so.status;
+            fs = so.status;
             const bool ok = so.status == PCL_SPLIT_OK;
             if (so.status == PCL_SPLIT_ANCHOR_NOT_FOUND || so.status == PCL_SPLIT_PATTERN_MISMATCH) ++n_defect;
             if (ok && so.tcoord != PCL_COORD_ABSENT) fs |= PCL_FSTATUS_TARGET;
@@ -251,6 +322,7 @@ __global__ void __launch_bounds__(PCL_BLOCK) k_count(const __grid_constant__ Cou
                     if (ninv) key = 0;
                 }
                 pcl_store_key(p.umi_key[j], p.umi_key_bytes[j], i, key);
+            }
             }
             p.fstatus[i] = (uint16_t)fs;
         }

@@ -123,6 +123,7 @@ struct pcl_ctx {
     int occ[12] = {1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1};   // resident CTAs per SM of each kernel (see OCC_*)
     int fast_bits = 14, fast_waves = 1;
     uint32_t hist_admit_mask = 7, hist_two_choice = 1;
+    bool no_plan = false;         // PCL_NO_PLAN=1: AnchorPlan layouts go through the interpreter kernels (tests compare both)
     bool force_generic = false;   // PCL_FORCE_GENERIC=1: only the generic kernels (tests compare both paths)
     bool no_neighbour_tables = false;   // PCL_NO_NEIGHBOUR_TABLES=1: 3*L direct probes instead of the 4 neighbourhood tables
 };
@@ -199,7 +200,7 @@ void prof_end(pcl_ctx *ctx, cudaStream_t s) {
     cudaEventRecord(ctx->evs.back().b, s);
 }
 
-enum { OCC_COUNT = 0, OCC_COUNT_FAST, OCC_COUNT_LENONLY, OCC_ENUM, OCC_CORRECT_FAST, OCC_CORRECT, OCC_QC, OCC_GATHER, OCC_COUNT_CODES };
+enum { OCC_COUNT = 0, OCC_COUNT_FAST, OCC_COUNT_LENONLY, OCC_ENUM, OCC_CORRECT_FAST, OCC_CORRECT, OCC_QC, OCC_GATHER, OCC_COUNT_CODES, OCC_COUNT_PLAN };
 
 int grid_for(const pcl_ctx *ctx, uint64_t n_threads_wanted, int blocks_per_sm) {
     uint64_t blocks = (n_threads_wanted + PCL_BLOCK - 1) / PCL_BLOCK;
@@ -240,6 +241,7 @@ int pcl_ctx_create(pcl_ctx **out, int device) {
     ctx->device = device;
     ctx->sm_count = prop.multiProcessorCount;
     { const char *g = getenv("PCL_FORCE_GENERIC"); ctx->force_generic = g && g[0] == '1'; }
+    { const char *g = getenv("PCL_NO_PLAN"); ctx->no_plan = g && g[0] == '1'; }
     { const char *g = getenv("PCL_NO_NEIGHBOUR_TABLES"); ctx->no_neighbour_tables = g && g[0] == '1'; }
     memset(ctx->descs, 0, sizeof ctx->descs);
     memset(ctx->dreads, 0, sizeof ctx->dreads);
@@ -268,8 +270,9 @@ int pcl_ctx_create(pcl_ctx **out, int device) {
             if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nblk, fn, PCL_BLOCK, 0) != cudaSuccess || nblk < 1) { cudaGetLastError(); nblk = 1; }
             return nblk;
         };
-        ctx->occ[OCC_COUNT] = occ((const void *)k_count<false>);
-        ctx->occ[OCC_COUNT_CODES] = occ((const void *)k_count<true>);
+        ctx->occ[OCC_COUNT] = occ((const void *)k_count<0>);
+        ctx->occ[OCC_COUNT_CODES] = occ((const void *)k_count<1>);
+        ctx->occ[OCC_COUNT_PLAN] = occ((const void *)k_count<2>);
         {
             // k_count_fast: 1024-thread CTAs with a 16 K-entry histogram cache (128 KB), one resident wave, two
             // candidate lines per key, a new key admitted on 1 of 8 sightings.  Measured on 125 M v3 records:
@@ -831,6 +834,8 @@ int pcl_count(pcl_ctx *ctx, pcl_chunk *c) {
         const bool fast = d.fast.enabled && ctx->tables[ctx->bc_region[r][0]].d.mode != PCL_TAB_K64 && !ctx->force_generic &&
                           c->n < 0xFF000000ull;      // 32-bit record indices inside k_count_fast
         const bool lenonly = !d.needs_payload && d.fixed_layout && !ctx->force_generic;
+        bool plan = d.plan.enabled && !ctx->force_generic && !ctx->no_plan;
+        for (int j = 0; j < inf.n_bc; ++j) plan = plan && ctx->tables[ctx->bc_region[r][j]].d.mode != PCL_TAB_K64;
         prof_begin(ctx, c->stream, d.needs_payload ? PCL_K_COUNT : PCL_K_COUNT_LENONLY);
         // The generic counting kernels run THREE resident waves rather than one: with first-come cache lines a CTA
         // that lives a third as long lets fewer one-off barcodes occupy lines (measured on the former fast kernel:
@@ -847,8 +852,9 @@ int pcl_count(pcl_ctx *ctx, pcl_chunk *c) {
             else k_count_fast<14><<<grid, threads, smem, c->stream>>>(p);
         }
         else if (lenonly) k_count_lenonly<<<grid_for(ctx, c->n / 8 + 8, ctx->occ[OCC_COUNT_LENONLY]), PCL_BLOCK, 0, c->stream>>>(p);
-        else if (d.codes_ok && !ctx->force_generic) k_count<true><<<grid_for(ctx, c->n, 3 * ctx->occ[OCC_COUNT_CODES]), PCL_BLOCK, 0, c->stream>>>(p);
-        else k_count<false><<<grid_for(ctx, c->n, 3 * ctx->occ[OCC_COUNT]), PCL_BLOCK, 0, c->stream>>>(p);
+        else if (plan) k_count<2><<<grid_for(ctx, c->n, 3 * ctx->occ[OCC_COUNT_PLAN]), PCL_BLOCK, 0, c->stream>>>(p);
+        else if (d.codes_ok && !ctx->force_generic) k_count<1><<<grid_for(ctx, c->n, 3 * ctx->occ[OCC_COUNT_CODES]), PCL_BLOCK, 0, c->stream>>>(p);
+        else k_count<0><<<grid_for(ctx, c->n, 3 * ctx->occ[OCC_COUNT]), PCL_BLOCK, 0, c->stream>>>(p);
         prof_end(ctx, c->stream);
         CU(ctx, cudaGetLastError());
         ctx->qc_reads[r] += c->n;

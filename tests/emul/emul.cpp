@@ -30,7 +30,7 @@ int emu_fast_enabled(const pcl_read_desc *rd) {
     int bcr[PCL_MAX_BC_PER_READ];
     std::string e;
     if (pcl_build_read(0, *rd, &d, &info, bcr, &e) != PCL_OK) return -1;
-    return d.fast.enabled ? 1 : ((!d.needs_payload && d.fixed_layout) ? 2 : 0);
+    return d.fast.enabled ? 1 : ((!d.needs_payload && d.fixed_layout) ? 2 : (d.plan.enabled ? 3 : 0));
 }
 
 struct emu_read_io {
@@ -152,6 +152,59 @@ int emu_run(const pcl_read_desc *reads, int n_reads, int n_regions, const uint8_
             uint32_t L = io[r].len[i];
             if (rd.max_len && L > rd.max_len) L = rd.max_len;
             const uint8_t *rec = io[r].seq ? io[r].seq + i * (uint64_t)rd.stride : nullptr;
+            bool plan = use_fast == 1 && rd.plan.enabled;                  // mirrors k_count<2>
+            for (uint32_t j = 0; j < rd.n_bc; ++j) plan = plan && dt[bcr[r][j]].mode != PCL_TAB_K64;
+            if (plan) {
+                uint32_t w[16] = {0};
+                memcpy(w, rec, rd.stride);
+                const uint32_t nbytes = L < rd.stride ? L : rd.stride;
+                Codes32 k;
+                if (rev) pcl_codes32_t<true>(w, (int)((nbytes + 3u) >> 2), k); else pcl_codes32_t<false>(w, (int)((nbytes + 3u) >> 2), k);
+                AnchorSplit sp;
+                pcl_anchor_split(rd, k, L, sp);
+                uint32_t c2[4], bd2[4];
+                pcl_shr_bases(k.c, sp.pos, c2);
+                pcl_shr_bases(k.bd, sp.pos, bd2);
+                uint32_t fs = sp.status;
+                if (sp.status != PCL_SPLIT_OK) defects_out[r]++;
+                if (rd.has_target) {
+                    const uint32_t tc = rd.plan.t_elem != 0xFFu ? pcl_anchor_coord(rd, sp, rd.plan.t_elem) : PCL_COORD_ABSENT;
+                    if (tc != PCL_COORD_ABSENT) fs |= PCL_FSTATUS_TARGET;
+                    io[r].tcoord[i] = tc;
+                }
+                for (uint32_t j = 0; j < PCL_MAX_BC_PER_READ; ++j) {
+                    if (j >= rd.n_bc) { fs |= PCL_BC_ABSENT << (4 + 3 * j); continue; }
+                    const uint32_t e = in.bc_elem[j], c = pcl_anchor_coord(rd, sp, e);
+                    io[r].bcoord[j][i] = c;
+                    uint32_t code = PCL_BC_ABSENT, key = 0;
+                    if (c != PCL_COORD_ABSENT) {
+                        const uint32_t blen = c & 0xFFFFu;
+                        uint32_t ninv;
+                        key = pcl_anchor_key(rd, k, c2, bd2, e, c, &ninv);
+                        DTable &t = dt[bcr[r][j]];
+                        uint32_t slot = 0xFFFFFFFFu;
+                        if (ninv == 0u && (t.mode == PCL_TAB_K32_L16 ? blen == 16u : blen <= 15u)) slot = pcl_probe32(t, key);
+                        ++*t.total;
+                        if (slot != 0xFFFFFFFFu) { code = PCL_BC_EXACT; t.counts[slot]++; }
+                        else { code = PCL_BC_NO_MATCH; ++*t.mismatch; work[r].push_back({i, c >> 16, c & 0xFFFFu, j}); }
+                    }
+                    reinterpret_cast<uint32_t *>(io[r].bc_key[j])[i] = key;
+                    fs |= code << (4 + 3 * j);
+                }
+                for (uint32_t j = 0; j < rd.n_umi; ++j) {
+                    const uint32_t e = in.umi_elem[j], c = pcl_anchor_coord(rd, sp, e);
+                    io[r].ucoord[j][i] = c;
+                    uint32_t key = PCL_KEY_ABSENT32;
+                    if (c != PCL_COORD_ABSENT) {
+                        uint32_t ninv;
+                        key = pcl_anchor_key(rd, k, c2, bd2, e, c, &ninv);
+                        if (ninv) key = 0;
+                    }
+                    reinterpret_cast<uint32_t *>(io[r].umi_key[j])[i] = key;
+                }
+                io[r].fstatus[i] = (uint16_t)fs;
+                continue;
+            }
             SplitOut so;
             RecCodes rc;
             const bool codes = use_fast && rd.codes_ok;                    // mirrors k_count<true>

@@ -169,7 +169,8 @@ def test_reference_vectors_through_device_split():
 
 
 def test_fast_path_selection(layouts):
-    """Which reads take the register-resident / length-only kernels (1 / 2) and which the generic one (0)."""
+    """Which reads take the register-resident / length-only kernels (1 / 2), the AnchorPlan kernel (3), and which
+    the interpreter (0)."""
     L = U.emul_lib()
     def sel(name):
         d = layouts[name].descs()
@@ -179,8 +180,9 @@ def test_fast_path_selection(layouts):
     assert sel("atac") == [2, 1, 2]
     assert sel("multiome_atac") == [2, 1, 2]
     assert sel("fast12_tail") == [1, 1]
-    assert sel("sci3") == [0, 2]
-    assert sel("k64_rev") == [0, 0]
+    assert sel("sci3") == [3, 2]                 # [variable barcode][anchor][UMI][barcode]
+    assert sel("k64_rev") == [0, 3]              # 64-bit keys -> interpreter; neg strand [variable][anchor][UMI][target] -> plan
+    assert sel("dsc") == [0, 2]                  # a fixed barcode between the variable run and the anchor: interpreter
     assert sel("share") == [2, 0]
 
 

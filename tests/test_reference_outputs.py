@@ -62,6 +62,10 @@ def test_layouts_are_what_the_survey_traced(name):
     if name == "test2":
         assert [k for k in kinds["atac-I1"] if k[0] == "barcode"] == [("barcode", 8, 8)] * 3
     assert len(lines) == 250 and all(len(b.length) == 250 for b in full)
+    if name in ("test3", "test4"):                        # dscATAC and sci-RNA-seq3 R1 run on the AnchorPlan kernel
+        import ctypes as C
+        d = layout.descs()
+        assert U.emul_lib().emu_fast_enabled(C.byref(d[0])) == 3
 
 
 @pytest.mark.parametrize("name", CASES)
