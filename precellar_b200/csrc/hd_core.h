@@ -759,6 +759,18 @@ struct Codes32 {
     uint32_t sb[4];     // the same with the strict upper-case test used for anchors (== bd on forward reads)
 };
 
+// Four bytes -> flags at bits 0, 2, 4, 6: byte k non-zero.  The high bit of ((x & 0x7F) + 0x7F) | x tells "non-zero";
+// one multiply-high by 2^25 + 2^19 + 2^13 + 2^7 moves bits 7, 15, 23, 31 to bits 32, 34, 36, 38 of the 64-bit product
+// (no two partial products share a bit, so there are no carries).
+PCL_HD uint32_t pcl_flags8(uint32_t x) {
+    const uint32_t hi = (((x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | x) & 0x80808080u;
+#ifdef __CUDA_ARCH__
+    return __umulhi(hi, 0x02082080u) & 0x55u;
+#else
+    return (uint32_t)(((uint64_t)hi * 0x02082080ull) >> 32) & 0x55u;
+#endif
+}
+
 template <bool kRev>
 PCL_HD void pcl_codes32_t(const uint32_t *w, int n_words, Codes32 &k) {
 #ifdef __CUDA_ARCH__
@@ -774,14 +786,12 @@ PCL_HD void pcl_codes32_t(const uint32_t *w, int n_words, Codes32 &k) {
                 const uint32_t x = w[4 * g + q];
                 uint32_t bad;
                 const uint32_t c8 = pcl_word_codes(kRev ? (x & 0xDFDFDFDFu) : x, &bad);
-                const uint32_t nb = ((((bad & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | bad) & 0x80808080u) >> 7;
                 c |= c8 << (8 * q);
-                b |= ((nb * 0x01041040u) >> 24) << (8 * q);
+                b |= pcl_flags8(bad) << (8 * q);
                 if (kRev) {
                     uint32_t sbad;
                     (void)pcl_word_codes(x, &sbad);
-                    const uint32_t ns = ((((sbad & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | sbad) & 0x80808080u) >> 7;
-                    sb |= ((ns * 0x01041040u) >> 24) << (8 * q);
+                    sb |= pcl_flags8(sbad) << (8 * q);
                 }
             }
         }
@@ -794,6 +804,25 @@ PCL_HD uint32_t pcl_win32(const uint32_t *c, uint32_t start, uint32_t len) {
     const uint32_t wi = start >> 4, sh = (start & 15u) * 2u;
     const uint32_t a = wi == 0u ? c[0] : wi == 1u ? c[1] : wi == 2u ? c[2] : c[3];
     const uint32_t b = wi == 0u ? c[1] : wi == 1u ? c[2] : wi == 2u ? c[3] : 0u;
+#ifdef __CUDA_ARCH__
+    const uint32_t v = __funnelshift_r(a, b, sh);
+#else
+    const uint32_t v = sh ? (a >> sh) | (b << (32u - sh)) : a;
+#endif
+    return len >= 16u ? v : (v & ((1u << (2u * len)) - 1u));
+}
+
+// pcl_win32 for a start that is the same in every lane of the warp: the word pair is picked by a (divergence-free)
+// branch instead of per-lane selects
+PCL_HD uint32_t pcl_win32u(const uint32_t *c, uint32_t start, uint32_t len) {
+    const uint32_t wi = start >> 4, sh = (start & 15u) * 2u;
+    uint32_t a, b;
+    switch (wi) {
+        case 0u: a = c[0]; b = c[1]; break;
+        case 1u: a = c[1]; b = c[2]; break;
+        case 2u: a = c[2]; b = c[3]; break;
+        default: a = c[3]; b = 0u; break;
+    }
 #ifdef __CUDA_ARCH__
     const uint32_t v = __funnelshift_r(a, b, sh);
 #else
@@ -849,8 +878,9 @@ PCL_HD void pcl_anchor_split(const DRead &rd, const Codes32 &k, uint32_t len, An
     uint32_t best = 0xFFFFFFFFu, bpos = 0;
     for (uint32_t i = 0; i + m <= wn; ++i) {                                      // find_best_pattern_match (:496-535)
         const uint32_t p = min_off + (rev ? wn - m - i : i);                      // neg strand: position i of rev_compl(window)
-        const uint32_t x = pcl_win32(k.c, p, m) ^ needle;
-        const uint32_t d = ((x | (x >> 1)) | pcl_win32(k.sb, p, m)) & even;
+        // forward reads: p is the same in every lane; neg strand: it depends on the record length through wn
+        const uint32_t x = (rev ? pcl_win32(k.c, p, m) : pcl_win32u(k.c, p, m)) ^ needle;
+        const uint32_t d = ((x | (x >> 1)) | (rev ? pcl_win32(k.sb, p, m) : pcl_win32u(k.sb, p, m))) & even;
 #ifdef __CUDA_ARCH__
         const uint32_t cnt = (uint32_t)__popc(d);
 #else
@@ -900,8 +930,8 @@ PCL_HD uint32_t pcl_anchor_key(const DRead &rd, const Codes32 &k, const uint32_t
     const bool behind = e > rd.plan.v;
     const uint32_t wlen = len > 16u ? 16u : len;
     if (wlen == 0u) { *n_invalid = 0; return 1u; }                                // an empty field: marker only, like pcl_pack_key
-    uint32_t f = pcl_win32(behind ? c2 : k.c, us, wlen);
-    const uint32_t bad = pcl_win32(behind ? bd2 : k.bd, us, wlen);
+    uint32_t f = pcl_win32u(behind ? c2 : k.c, us, wlen);                         // `us` and `behind` are warp-uniform
+    const uint32_t bad = pcl_win32u(behind ? bd2 : k.bd, us, wlen);
 #ifdef __CUDA_ARCH__
     *n_invalid = (uint32_t)__popc(bad);
 #else

@@ -91,7 +91,7 @@ def main():
             s, q, l = ch.device_ptrs(0)
             gen.fill_device(0, 0, n, s, q, l, ch.stream)
             fill_len(pipe, ch, 1, 100)
-        run("sci_rna_seq3 (hairpin 9|10 + CAGAGC + UMI8 + RT10, interpreter kernel)", configs.sci3_layout(hp, rt, 34, 100), fill, n, a.steps)
+        run("sci_rna_seq3 (hairpin 9|10 + CAGAGC + UMI8 + RT10, AnchorPlan kernel)", configs.sci3_layout(hp, rt, 34, 100), fill, n, a.steps)
 
 
 if __name__ == "__main__":
