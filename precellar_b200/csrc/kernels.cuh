@@ -160,7 +160,7 @@ __device__ __forceinline__ uint4 pcl_ld_stream(const uint4 *p) {
 // are cut in code space (pcl_split_codes / pcl_pack_codes).  kMode 2: the same for AnchorPlan layouts with 32-bit
 // strings, the collapsed split and warp-uniform field offsets (hd_core.h).  kMode 0: the record bytes are read on demand.
 template <int kMode>
-__global__ void __launch_bounds__(PCL_BLOCK) k_count(const __grid_constant__ CountParams p) {
+__global__ void __launch_bounds__(PCL_BLOCK, kMode == 2 ? 4 : 1) k_count(const __grid_constant__ CountParams p) {
     constexpr bool kCodes = kMode == 1;
     constexpr bool kPlan = kMode == 2;
     __shared__ uint32_t ck[PCL_HCACHE];
