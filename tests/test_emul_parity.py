@@ -226,3 +226,85 @@ def test_emul_dense_and_boundary_whitelists(name, use_fast):
     assert (codes == _ffi.BC_CORRECTED).any() and (codes == _ffi.BC_EXACT).any()
     if name in ("near_dups", "all6"):
         assert (codes == _ffi.BC_LOW_CONF).any()          # several neighbours share the posterior
+
+
+def _random_plan_layout(rng):
+    """[fixed ...][one variable element][anchor][fixed ...][optional trailing variable element], random kinds."""
+    wls, elems = {}, []
+    n_bc = n_umi = n_t = 0
+
+    def fixed_elem(k):
+        nonlocal n_bc, n_umi, n_t
+        u = rng.random()
+        if u < 0.35 and n_bc < 3:
+            L = int(rng.integers(4, 13))
+            rid = f"b{n_bc}_{k}"
+            wls[rid] = U.gen_whitelist(rng, int(rng.integers(20, 120)), L)
+            n_bc += 1
+            return bc(rid, L)
+        if u < 0.55 and n_umi < 2:
+            n_umi += 1
+            return umi(int(rng.integers(3, 13)), f"u{k}")
+        if u < 0.7:
+            return linker(bytes(rng.choice(np.frombuffer(b"ACGT", np.uint8), int(rng.integers(2, 9)))).decode(), f"l{k}")   # taken at face value
+        return U.E(f"o{k}", "linker", int(rng.integers(1, 7)))
+    for k in range(int(rng.integers(0, 3))):
+        elems.append(fixed_elem(k))
+    a = int(rng.integers(0, 9))
+    b = a + int(rng.integers(1, 7))
+    if rng.random() < 0.5 and n_bc < 3 and b <= 15 and a >= 4:
+        rid = f"vb{n_bc}"
+        wls[rid] = U.gen_whitelist(rng, 80, list(range(a, b + 1)))
+        n_bc += 1
+        elems.append(bc(rid, a, b))
+    else:
+        elems.append(var(a, b, "v"))
+    elems.append(linker(bytes(rng.choice(np.frombuffer(b"ACGT", np.uint8), int(rng.integers(1, 13)))).decode(), "anchor"))
+    for k in range(int(rng.integers(0, 4))):
+        elems.append(fixed_elem(10 + k))
+    if rng.random() < 0.5:
+        elems.append(cdna(1, 200) if rng.random() < 0.7 else var(0, 9, "tailv"))
+    if n_bc == 0:
+        wls["bx"] = U.gen_whitelist(rng, 50, 6)
+        elems.insert(0, bc("bx", 6))
+    total = sum(e.max_len for e in elems if e.max_len < 100)
+    if total > 60:
+        return None
+    return make_layout([dict(read_id="R1", elems=elems, is_reverse=bool(rng.random() < 0.4), max_len=int(rng.choice([0, 0, total, total - 3])))], wls)
+
+
+def test_emul_random_anchor_plan_layouts():
+    """Random layouts of the AnchorPlan shape (both strands, variable barcodes, trailing targets, fixed sequences behind the
+    anchor, Read.max_len cuts): the collapsed split + uniform-offset extraction must equal the oracle, and the
+    interpreter path (use_fast=2) on the same data too."""
+    import ctypes as C
+    rng = np.random.default_rng(U.seed_of("random-plans"))
+    L = U.emul_lib()
+    n_plan = 0
+    tries = 0
+    while n_plan < 40 and tries < 400:
+        tries += 1
+        layout = _random_plan_layout(rng)
+        if layout is None:
+            continue
+        d = layout.descs()
+        try:
+            infos, strides = U.emul_infos(layout)
+        except _ffi.PclError:
+            continue
+        if L.emu_fast_enabled(C.byref(d[0])) != 3:
+            continue
+        n_plan += 1
+        multi = len(layout.region_ids) > 1
+        full = U.gen_reads(rng, layout, 250, strides, p_sub=0.04, p_n=0.02, p_lower=0.02 if layout.reads[0].is_reverse else 0.0,
+                           p_short=0.0 if multi else 0.15, p_tiny=0.05 if multi else 0.0, p_anchor_mut=0.3)
+        dev = U.narrow(full, strides, infos)
+        try:
+            ores, ocounts = U.run_oracle(layout, full, threshold=0.8)
+        except Exception:
+            n_plan -= 1                                   # the reference asserts equal totals across whitelists: not a split question
+            continue
+        for use_fast in (1, 2):
+            infos2, results, counts, defects = U.run_emul(layout, dev, threshold=0.8, use_fast=use_fast)
+            U.compare_with_oracle(layout, infos2, full, results, counts, defects, ores, ocounts)
+    assert n_plan >= 25, (n_plan, tries)

@@ -380,3 +380,34 @@ def test_compact_upload_gives_the_same_results(layouts, name):
             ch.upload_compact(r, bad)
     finally:
         pipe.close()
+
+
+def test_gpu_random_anchor_plan_layouts():
+    """The AnchorPlan kernel (k_count<2>) on random layouts of its shape, against the oracle."""
+    import ctypes as C
+    from tests.test_emul_parity import _random_plan_layout
+    rng = np.random.default_rng(U.seed_of("random-plans-gpu"))
+    L = U.emul_lib()
+    done = tries = 0
+    while done < 12 and tries < 300:
+        tries += 1
+        layout = _random_plan_layout(rng)
+        if layout is None:
+            continue
+        try:
+            infos, strides = U.emul_infos(layout)
+        except _ffi.PclError:
+            continue
+        if L.emu_fast_enabled(C.byref(layout.descs()[0])) != 3:
+            continue
+        multi = len(layout.region_ids) > 1
+        full = U.gen_reads(rng, layout, 600, strides, p_sub=0.04, p_n=0.02, p_lower=0.02 if layout.reads[0].is_reverse else 0.0,
+                           p_short=0.0 if multi else 0.15, p_tiny=0.05 if multi else 0.0, p_anchor_mut=0.3)
+        try:
+            ores, ocounts = U.run_oracle(layout, full, threshold=0.8)
+        except Exception:
+            continue
+        ginfos, results, counts, defects, _ = run_gpu(layout, U.narrow(full, strides, infos), threshold=0.8)
+        U.compare_with_oracle(layout, ginfos, full, results, counts, defects, ores, ocounts)
+        done += 1
+    assert done >= 8
