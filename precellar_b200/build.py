@@ -60,6 +60,18 @@ def build_tools(force: bool = False) -> None:
     import importlib
     sys.path.insert(0, os.path.dirname(HERE))
     importlib.import_module("tools.synth").build(force)
+    build_examples(force)
+
+
+def build_examples(force: bool = False) -> str:
+    """examples/v3_demo: the hot path driven from C++ through the C ABI only (tests/test_gpu_cabi_demo.py runs it)."""
+    root = os.path.dirname(HERE)
+    src, exe = os.path.join(root, "examples", "v3_demo.cpp"), os.path.join(root, "examples", "v3_demo")
+    deps = [src, os.path.join(root, "include", "precellar_b200.h"), LIB_PATH]
+    if force or not os.path.exists(exe) or any(os.path.getmtime(d) > os.path.getmtime(exe) for d in deps):
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-I", os.path.join(root, "include"), src, "-o", exe, "-L", HERE,
+                               "-lprecellar_b200", "-Wl,-rpath,$ORIGIN/../precellar_b200"])
+    return exe
 
 
 if __name__ == "__main__":
