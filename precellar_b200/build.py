@@ -67,7 +67,7 @@ def build_examples(force: bool = False) -> str:
     """examples/v3_demo: the hot path driven from C++ through the C ABI only (tests/test_gpu_cabi_demo.py runs it)."""
     root = os.path.dirname(HERE)
     src, exe = os.path.join(root, "examples", "v3_demo.cpp"), os.path.join(root, "examples", "v3_demo")
-    deps = [src, os.path.join(root, "include", "precellar_b200.h"), LIB_PATH]
+    deps = [src, os.path.join(root, "include", "precellar_b200.h"), OUT]
     if force or not os.path.exists(exe) or any(os.path.getmtime(d) > os.path.getmtime(exe) for d in deps):
         subprocess.check_call(["g++", "-O2", "-std=c++17", "-I", os.path.join(root, "include"), src, "-o", exe, "-L", HERE,
                                "-lprecellar_b200", "-Wl,-rpath,$ORIGIN/../precellar_b200"])
