@@ -8,7 +8,7 @@
 //   BatchedFqReader::next name check    precellar/src/align/fastq.rs:417-431 (names agree after strip_fq_suffix,
 //                                        fastq.rs:612-621)
 //
-//   k_text_count   newline count of every 4 KB tile
+//   k_text_count   newline count of every 16 KB tile (64 contiguous bytes per thread)
 //   k_text_scan    exclusive scan of the tile counts (one CTA)
 //   k_text_index   byte offset of every newline, in order -> line index
 //   k_text_fill    line index -> seq / qual / len planes + name hash (+ record validation)
@@ -21,7 +21,8 @@
 #include <cstdint>
 
 #define PCL_TEXT_BLOCK 256
-#define PCL_TEXT_TILE (PCL_TEXT_BLOCK * 16)       // bytes per CTA iteration: one 16-byte load per thread
+#define PCL_TEXT_PER_THREAD 64                    // contiguous text bytes per thread: four 16-byte loads
+#define PCL_TEXT_TILE (PCL_TEXT_BLOCK * PCL_TEXT_PER_THREAD)       // bytes per CTA iteration (16 KB)
 
 // 16 bytes -> 16-bit mask of the positions holding '\n' (bit k = byte k)
 __device__ __forceinline__ uint32_t pcl_nl_mask16(const uint4 v) {
@@ -36,14 +37,21 @@ __device__ __forceinline__ uint32_t pcl_nl_mask16(const uint4 v) {
     return m;
 }
 
-__device__ __forceinline__ uint32_t pcl_tile_mask(const uint8_t *text, uint64_t n_bytes, uint64_t tile, uint32_t tid) {
-    const uint64_t pos = tile * PCL_TEXT_TILE + (uint64_t)tid * 16u;
-    if (pos >= n_bytes) return 0u;
-    const uint4 v = __ldg(reinterpret_cast<const uint4 *>(text + pos));       // the buffer is padded to 16 bytes with zeros
-    uint32_t m = pcl_nl_mask16(v);
-    const uint64_t left = n_bytes - pos;
-    if (left < 16u) m &= (1u << left) - 1u;
-    return m;
+// newline masks of the thread's 64 bytes (bit k of m[q] = byte 16q + k); the thread's bytes are contiguous, so the
+// newlines of a tile are ordered by (thread, q, bit) and one block scan per tile orders them all
+__device__ __forceinline__ void pcl_tile_masks(const uint8_t *text, uint64_t n_bytes, uint64_t tile, uint32_t tid, uint32_t m[4]) {
+    const uint64_t pos = tile * PCL_TEXT_TILE + (uint64_t)tid * PCL_TEXT_PER_THREAD;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const uint64_t p = pos + 16u * q;
+        m[q] = 0u;
+        if (p < n_bytes) {
+            const uint4 v = __ldg(reinterpret_cast<const uint4 *>(text + p));          // the buffer is padded to 16 bytes with zeros
+            m[q] = pcl_nl_mask16(v);
+            const uint64_t left = n_bytes - p;
+            if (left < 16u) m[q] &= (1u << left) - 1u;
+        }
+    }
 }
 
 __global__ void __launch_bounds__(PCL_TEXT_BLOCK) k_text_count(const uint8_t *__restrict__ text, uint64_t n_bytes,
@@ -51,7 +59,9 @@ __global__ void __launch_bounds__(PCL_TEXT_BLOCK) k_text_count(const uint8_t *__
     __shared__ uint32_t wsum[PCL_TEXT_BLOCK / 32];
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        uint32_t c = __popc(pcl_tile_mask(text, n_bytes, tile, tid));
+        uint32_t m[4];
+        pcl_tile_masks(text, n_bytes, tile, tid, m);
+        uint32_t c = __popc(m[0]) + __popc(m[1]) + __popc(m[2]) + __popc(m[3]);
         c = __reduce_add_sync(0xFFFFFFFFu, c);
         if (lane == 0) wsum[warp] = c;
         __syncthreads();
@@ -93,8 +103,9 @@ __global__ void __launch_bounds__(PCL_TEXT_BLOCK) k_text_index(const uint8_t *__
     __shared__ uint32_t wsum[PCL_TEXT_BLOCK / 32];
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        uint32_t m = pcl_tile_mask(text, n_bytes, tile, tid);
-        const uint32_t c = __popc(m);
+        uint32_t m[4];
+        pcl_tile_masks(text, n_bytes, tile, tid, m);
+        const uint32_t c = __popc(m[0]) + __popc(m[1]) + __popc(m[2]) + __popc(m[3]);
         uint32_t incl = c;                                   // inclusive warp scan
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
@@ -106,12 +117,16 @@ __global__ void __launch_bounds__(PCL_TEXT_BLOCK) k_text_index(const uint8_t *__
         uint32_t base = tile_off[tile];
         for (uint32_t k = 0; k < warp; ++k) base += wsum[k];
         uint64_t idx = (uint64_t)base + incl - c;
-        const uint32_t pos = (uint32_t)(tile * PCL_TEXT_TILE + (uint64_t)tid * 16u);
-        while (m) {
-            const uint32_t j = (uint32_t)__ffs((int)m) - 1u;
-            m &= m - 1u;
-            if (idx < nl_cap) nl[idx] = pos + j;
-            ++idx;
+        const uint32_t pos = (uint32_t)(tile * PCL_TEXT_TILE + (uint64_t)tid * PCL_TEXT_PER_THREAD);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            uint32_t mq = m[q];
+            while (mq) {
+                const uint32_t j = (uint32_t)__ffs((int)mq) - 1u;
+                mq &= mq - 1u;
+                if (idx < nl_cap) nl[idx] = pos + 16u * q + j;
+                ++idx;
+            }
         }
         __syncthreads();
     }
