@@ -34,7 +34,8 @@ N_WHITELIST = 6_800_000
 R2_LEN = 91
 THRESHOLD = 0.975          # make_fastq default (precellar/src/align/fastq.rs:39)
 # algorithmic bytes per read pair (SURVEY.md 8d / DESIGN.md): B = 108 + 1536 * f_mis, split per kernel launch
-B_COUNT_R1 = 58 + 32 + 10  # R1 seq+qual+len (SURVEY's figure; the kernel itself never reads qual), one probe sector, results
+B_COUNT_R1 = 30 + 32 + 10  # R1 seq + len, one probe sector, results (the count pass never reads qualities)
+B_CORRECT_QUAL = 28        # R1 qualities: SURVEY's B_in charges them for every pair; only the correction pass reads them
 B_COUNT_R2 = 2 + 6         # R2 len, fstatus+tcoord
 B_CORRECT_PER_MISS = 1536  # 3 * 16 neighbour probes * 32 B
 
@@ -449,7 +450,7 @@ def main():
     t_len = prof[_ffi.K_COUNT_LENONLY][0] / max(prof[_ffi.K_COUNT_LENONLY][1], 1)
     kern = {
         "k_count(R1)": {"ms": t_count, "alg_bytes": n * B_COUNT_R1},
-        "k_correct(R1)": {"ms": t_corr, "alg_bytes": n * f_mis * B_CORRECT_PER_MISS},
+        "k_correct(R1)": {"ms": t_corr, "alg_bytes": n * (B_CORRECT_QUAL + f_mis * B_CORRECT_PER_MISS)},
         "k_count(R2,len-only)": {"ms": t_len, "alg_bytes": n * B_COUNT_R2},
     }
     for kv in kern.values():

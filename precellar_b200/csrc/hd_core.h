@@ -46,10 +46,16 @@ struct DElem {
 // Register-resident path for the common short barcode reads (10x v2/v3 R1, ATAC / multiome I2 ...):
 // every element fixed-length (an optional trailing variable target), the whole record within 16 or 32 bytes,
 // exactly one barcode of <= 16 bases, at most one UMI of <= 15 bases.
+// Field geometries with compile-time instances of the extraction (a 16-base barcode and an optional UMI on word
+// boundaries): the byte masks, the 64-bit code string and its variable shifts fold away.
+enum { PCL_FAST_SPEC_NONE = 0, PCL_FAST_SPEC_B0_U16x12 = 1 /* 10x v3 R1 */, PCL_FAST_SPEC_B0 = 2 /* 16-nt index read */,
+       PCL_FAST_SPEC_B8 = 3 /* 8-nt linker + 16-nt barcode */ };
+
 struct FastLayout {
     uint8_t enabled;
     uint8_t bc_start, bc_len, umi_start, umi_len;   // umi_len == 0: no UMI
     uint8_t has_tail_target;                        // trailing variable target element
+    uint8_t spec;                                   // word-aligned field geometry the fast kernel is specialised for (PCL_FAST_SPEC_*)
     uint16_t t_start, t_min, t_max;
     uint32_t bc_mask[8], umi_mask[8];               // byte masks of the two regions over the 8 record words
 };
@@ -508,6 +514,50 @@ PCL_HD void pcl_fast_extract(const FastLayout &f, const uint32_t *w, bool rev, u
     }
     *umi_key = uk;
     *umi_bad = ubad != 0u;
+}
+
+// pcl_fast_extract for a 16-base barcode in words [kBcW, kBcW + 4) and a UMI of 4 * kUmiW bases in words
+// [kUmiW0, kUmiW0 + kUmiW) (kUmiW == 0: none): same results, everything about the geometry known at compile time.
+template <int kBcW, int kUmiW0, int kUmiW>
+PCL_HD void pcl_fast_extract_aligned(const uint32_t *w, bool rev, uint32_t *bc_key, bool *bc_bad, uint32_t *umi_key, bool *umi_bad) {
+    const uint32_t fold = rev ? 0xDFDFDFDFu : 0xFFFFFFFFu;
+    uint32_t bcodes = 0, bbad = 0;
+#ifdef __CUDA_ARCH__
+#pragma unroll
+#endif
+    for (int k = 0; k < 4; ++k) {
+        uint32_t d;
+        bcodes |= pcl_word_codes(w[kBcW + k] & fold, &d) << (8 * k);
+        bbad |= d;
+    }
+    *bc_key = pcl_field_to_key(bcodes, 0u, 16u, rev);
+    *bc_bad = bbad != 0u;
+    uint32_t uk = 0, ubad = 0;
+    if (kUmiW > 0) {
+        uint32_t ucodes = 0;
+#ifdef __CUDA_ARCH__
+#pragma unroll
+#endif
+        for (int k = 0; k < kUmiW; ++k) {
+            uint32_t d;
+            ucodes |= pcl_word_codes(w[kUmiW0 + k] & fold, &d) << (8 * k);
+            ubad |= d;
+        }
+        uk = pcl_field_to_key(ucodes, 0u, 4u * kUmiW, rev) | (1u << (8u * kUmiW));
+        if (ubad) uk = 0;
+    }
+    *umi_key = uk;
+    *umi_bad = ubad != 0u;
+}
+
+PCL_HD void pcl_fast_extract_spec(const FastLayout &f, const uint32_t *w, bool rev, uint32_t *bc_key, bool *bc_bad,
+                                  uint32_t *umi_key, bool *umi_bad) {
+    switch (f.spec) {
+        case PCL_FAST_SPEC_B0_U16x12: pcl_fast_extract_aligned<0, 4, 3>(w, rev, bc_key, bc_bad, umi_key, umi_bad); break;
+        case PCL_FAST_SPEC_B0: pcl_fast_extract_aligned<0, 0, 0>(w, rev, bc_key, bc_bad, umi_key, umi_bad); break;
+        case PCL_FAST_SPEC_B8: pcl_fast_extract_aligned<2, 0, 0>(w, rev, bc_key, bc_bad, umi_key, umi_bad); break;
+        default: pcl_fast_extract(f, w, rev, bc_key, bc_bad, umi_key, umi_bad); break;
+    }
 }
 
 // Any of the 8 keys of bucket b equal to k?  *full = the bucket has no free slot (a longer probe chain is possible).

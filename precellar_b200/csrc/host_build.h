@@ -180,6 +180,9 @@ inline int pcl_build_read(int r, const pcl_read_desc &rd, DRead *out, pcl_read_i
                 if (i >= f.bc_start && i < (uint32_t)f.bc_start + f.bc_len) f.bc_mask[i / 4] |= 0xFFu << (8 * (i % 4));
                 if (f.umi_len && i >= f.umi_start && i < (uint32_t)f.umi_start + f.umi_len) f.umi_mask[i / 4] |= 0xFFu << (8 * (i % 4));
             }
+            if (f.bc_len == 16 && f.bc_start == 0 && f.umi_len == 12 && f.umi_start == 16) f.spec = PCL_FAST_SPEC_B0_U16x12;
+            else if (f.bc_len == 16 && f.bc_start == 0 && f.umi_len == 0) f.spec = PCL_FAST_SPEC_B0;
+            else if (f.bc_len == 16 && f.bc_start == 8 && f.umi_len == 0) f.spec = PCL_FAST_SPEC_B8;
             if (tail_var) {
                 f.has_tail_target = 1;
                 f.t_start = info.static_start[ne - 1];

@@ -372,7 +372,8 @@ __device__ __forceinline__ void pcl_st_stream(uint16_t *p, uint16_t v) { __stcs(
 __device__ __forceinline__ void pcl_st_stream(uint4 *p, uint4 v) { __stcs(p, v); }
 
 // kBits: log2 of the histogram cache entries; the CTA has 256 << (kBits - 12) threads (same cache per thread).
-template <int kBits>
+// kSpec: PCL_FAST_SPEC_* instance of the field extraction (0: driven by the layout's byte masks).
+template <int kBits, int kSpec = 0>
 __global__ void __launch_bounds__(PCL_BLOCK << (kBits - PCL_HCACHE_BITS)) k_count_fast(const __grid_constant__ CountParams p) {
     extern __shared__ uint32_t pcl_hist_smem[];
     uint32_t *ck = pcl_hist_smem, *cc = pcl_hist_smem + (1u << kBits);
@@ -435,7 +436,10 @@ __global__ void __launch_bounds__(PCL_BLOCK << (kBits - PCL_HCACHE_BITS)) k_coun
                 if (rd.max_len && L > rd.max_len) L = rd.max_len;
                 const uint32_t w[8] = {ca.x, ca.y, ca.z, ca.w, cb.x, cb.y, cb.z, cb.w};
                 bool bbad, ubad;
-                pcl_fast_extract(f, w, rev, &c_bk, &bbad, &c_uk, &ubad);
+                if (kSpec == PCL_FAST_SPEC_B0_U16x12) pcl_fast_extract_aligned<0, 4, 3>(w, rev, &c_bk, &bbad, &c_uk, &ubad);
+                else if (kSpec == PCL_FAST_SPEC_B0) pcl_fast_extract_aligned<0, 0, 0>(w, rev, &c_bk, &bbad, &c_uk, &ubad);
+                else if (kSpec == PCL_FAST_SPEC_B8) pcl_fast_extract_aligned<2, 0, 0>(w, rev, &c_bk, &bbad, &c_uk, &ubad);
+                else pcl_fast_extract(f, w, rev, &c_bk, &bbad, &c_uk, &ubad);
                 c_fs = PCL_SPLIT_OK | absent_rest;
                 c_flags = 1u;
                 if (f.has_tail_target) {

@@ -123,6 +123,7 @@ struct pcl_ctx {
     int occ[12] = {1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1};   // resident CTAs per SM of each kernel (see OCC_*)
     int fast_bits = 14, fast_waves = 1;
     uint32_t hist_admit_mask = 7, hist_two_choice = 1;
+    bool no_fast_spec = false;    // PCL_NO_FAST_SPEC=1: the mask-driven instance of k_count_fast for every FastLayout
     bool no_plan = false;         // PCL_NO_PLAN=1: AnchorPlan layouts go through the interpreter kernels (tests compare both)
     bool force_generic = false;   // PCL_FORCE_GENERIC=1: only the generic kernels (tests compare both paths)
     bool no_neighbour_tables = false;   // PCL_NO_NEIGHBOUR_TABLES=1: 3*L direct probes instead of the 4 neighbourhood tables
@@ -242,6 +243,7 @@ int pcl_ctx_create(pcl_ctx **out, int device) {
     ctx->sm_count = prop.multiProcessorCount;
     { const char *g = getenv("PCL_FORCE_GENERIC"); ctx->force_generic = g && g[0] == '1'; }
     { const char *g = getenv("PCL_NO_PLAN"); ctx->no_plan = g && g[0] == '1'; }
+    { const char *g = getenv("PCL_NO_FAST_SPEC"); ctx->no_fast_spec = g && g[0] == '1'; }
     { const char *g = getenv("PCL_NO_NEIGHBOUR_TABLES"); ctx->no_neighbour_tables = g && g[0] == '1'; }
     memset(ctx->descs, 0, sizeof ctx->descs);
     memset(ctx->dreads, 0, sizeof ctx->dreads);
@@ -287,6 +289,11 @@ int pcl_ctx_create(pcl_ctx **out, int device) {
             const void *fn = ctx->fast_bits == 12 ? (const void *)k_count_fast<12> : ctx->fast_bits == 13 ? (const void *)k_count_fast<13> : (const void *)k_count_fast<14>;
             const int smem = 8 << ctx->fast_bits, threads = PCL_BLOCK << (ctx->fast_bits - 12);
             cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+            if (ctx->fast_bits == 14) {
+                cudaFuncSetAttribute((const void *)k_count_fast<14, PCL_FAST_SPEC_B0_U16x12>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+                cudaFuncSetAttribute((const void *)k_count_fast<14, PCL_FAST_SPEC_B0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+                cudaFuncSetAttribute((const void *)k_count_fast<14, PCL_FAST_SPEC_B8>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+            }
             int nb = 1;
             if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, fn, threads, smem) != cudaSuccess || nb < 1) nb = 1;
             ctx->occ[OCC_COUNT_FAST] = nb;
@@ -849,6 +856,9 @@ int pcl_count(pcl_ctx *ctx, pcl_chunk *c) {
             const int grid = (int)std::max<uint64_t>(1, std::min(blocks, cap));
             if (ctx->fast_bits == 12) k_count_fast<12><<<grid, threads, smem, c->stream>>>(p);
             else if (ctx->fast_bits == 13) k_count_fast<13><<<grid, threads, smem, c->stream>>>(p);
+            else if (d.fast.spec == PCL_FAST_SPEC_B0_U16x12 && !ctx->no_fast_spec) k_count_fast<14, PCL_FAST_SPEC_B0_U16x12><<<grid, threads, smem, c->stream>>>(p);
+            else if (d.fast.spec == PCL_FAST_SPEC_B0 && !ctx->no_fast_spec) k_count_fast<14, PCL_FAST_SPEC_B0><<<grid, threads, smem, c->stream>>>(p);
+            else if (d.fast.spec == PCL_FAST_SPEC_B8 && !ctx->no_fast_spec) k_count_fast<14, PCL_FAST_SPEC_B8><<<grid, threads, smem, c->stream>>>(p);
             else k_count_fast<14><<<grid, threads, smem, c->stream>>>(p);
         }
         else if (lenonly) k_count_lenonly<<<grid_for(ctx, c->n / 8 + 8, ctx->occ[OCC_COUNT_LENONLY]), PCL_BLOCK, 0, c->stream>>>(p);

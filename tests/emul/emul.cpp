@@ -102,7 +102,12 @@ int emu_run(const pcl_read_desc *reads, int n_reads, int n_regions, const uint8_
                 uint32_t w[8] = {0, 0, 0, 0, 0, 0, 0, 0};
                 memcpy(w, io[r].seq + i * (uint64_t)rd.stride, rd.stride);
                 uint32_t bk, uk; bool bbad, ubad;
-                pcl_fast_extract(f, w, rev, &bk, &bbad, &uk, &ubad);
+                pcl_fast_extract_spec(f, w, rev, &bk, &bbad, &uk, &ubad);
+                {   // the specialised instances must agree with the mask-driven extraction
+                    uint32_t bk2, uk2; bool bb2, ub2;
+                    pcl_fast_extract(f, w, rev, &bk2, &bb2, &uk2, &ub2);
+                    if (bk2 != bk || uk2 != uk || bb2 != bbad || ub2 != ubad) return PCL_ERR_INPUT;
+                }
                 uint32_t fs = PCL_SPLIT_OK | absent_rest;
                 if (f.has_tail_target) {
                     uint32_t tc = PCL_COORD_ABSENT;
