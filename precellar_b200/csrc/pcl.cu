@@ -155,6 +155,8 @@ struct pcl_chunk {
     uint64_t cap = 0, n = 0;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev = nullptr, t0 = nullptr, t1 = nullptr;
+    cudaEvent_t ev_counted = nullptr;    // recorded by pcl_count behind the last kernel that touches whitelist counts
+    bool counted = false;
     ReadBuf rb[PCL_MAX_READS];
     std::vector<void *> allocs;
 };
@@ -491,6 +493,7 @@ int pcl_chunk_create(pcl_ctx *ctx, uint64_t capacity_records, pcl_chunk **out) {
     auto A = [&](void **p, size_t bytes) { if (rc == PCL_OK) rc = chunk_alloc(c, p, bytes); };
     if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreateWithFlags(&c->ev, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&c->ev_counted, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreate(&c->t0) != cudaSuccess || cudaEventCreate(&c->t1) != cudaSuccess)
         rc = fail(ctx, PCL_ERR_CUDA, "stream/event creation failed: %s", cudaGetErrorString(cudaGetLastError()));
     for (int r = 0; r < ctx->n_reads && rc == PCL_OK; ++r) {
@@ -541,7 +544,7 @@ int pcl_chunk_destroy(pcl_chunk *c) {
         if (b.h_tmeta) cudaFreeHost(b.h_tmeta);
         if (ctx->text[r].owner == c) ctx->text[r].owner = nullptr;
     }
-    cudaEventDestroy(c->ev); cudaEventDestroy(c->t0); cudaEventDestroy(c->t1);
+    cudaEventDestroy(c->ev); cudaEventDestroy(c->ev_counted); cudaEventDestroy(c->t0); cudaEventDestroy(c->t1);
     cudaStreamDestroy(c->stream);
     for (size_t i = 0; i < ctx->chunks.size(); ++i)
         if (ctx->chunks[i] == c) { ctx->chunks.erase(ctx->chunks.begin() + i); break; }
@@ -817,7 +820,15 @@ int pcl_count(pcl_ctx *ctx, pcl_chunk *c) {
     if (int r = check_ready(ctx, c)) return r;
     if (int r = bind(ctx)) return r;
     if (c->n == 0) return PCL_OK;
-    for (int r = 0; r < ctx->n_reads; ++r) {
+    // Reads that hold barcodes first: the all-reduce of the counts only has to wait for their kernels (ev_counted), so it
+    // runs while the length-only kernels of the insert reads are still going.
+    int order[PCL_MAX_READS], n_order = 0, n_with_bc = 0;
+    for (int r = 0; r < ctx->n_reads; ++r) if (ctx->infos[r].n_bc) order[n_order++] = r;
+    n_with_bc = n_order;
+    for (int r = 0; r < ctx->n_reads; ++r) if (!ctx->infos[r].n_bc) order[n_order++] = r;
+    if (n_with_bc == 0) { CU(ctx, cudaEventRecord(c->ev_counted, c->stream)); c->counted = true; }
+    for (int oi = 0; oi < n_order; ++oi) {
+        const int r = order[oi];
         const pcl_read_info &inf = ctx->infos[r];
         ReadBuf &b = c->rb[r];
         CountParams p;
@@ -868,6 +879,7 @@ int pcl_count(pcl_ctx *ctx, pcl_chunk *c) {
         prof_end(ctx, c->stream);
         CU(ctx, cudaGetLastError());
         ctx->qc_reads[r] += c->n;
+        if (oi + 1 == n_with_bc) { CU(ctx, cudaEventRecord(c->ev_counted, c->stream)); c->counted = true; }
     }
     return PCL_OK;
 }
@@ -875,10 +887,15 @@ int pcl_count(pcl_ctx *ctx, pcl_chunk *c) {
 int pcl_counts_allreduce(pcl_ctx *ctx) {
     if (!ctx) return PCL_ERR_ARG;
     if (int r = bind(ctx)) return r;
-    // ctx stream waits for every chunk's count pass ...
+    // ctx stream waits for every chunk's count pass (for the kernels that touch the counts, when pcl_count marked them) ...
     for (pcl_chunk *c : ctx->chunks) {
-        CU(ctx, cudaEventRecord(c->ev, c->stream));
-        CU(ctx, cudaStreamWaitEvent(ctx->stream, c->ev, 0));
+        if (c->counted) {
+            CU(ctx, cudaStreamWaitEvent(ctx->stream, c->ev_counted, 0));
+            c->counted = false;
+        } else {
+            CU(ctx, cudaEventRecord(c->ev, c->stream));
+            CU(ctx, cudaStreamWaitEvent(ctx->stream, c->ev, 0));
+        }
     }
     if (ctx->nranks > 1) {
         if (!ctx->comm) return fail(ctx, PCL_ERR_NCCL, "communicator not initialised");
