@@ -182,3 +182,56 @@ def test_gzsrc_errors(tmp_path):
     with pytest.raises(_ffi.PclError):
         from precellar_b200.textingest import GzSource
         GzSource(str(tmp_path / "missing.gz"))
+
+
+# ---------------------------------------------------------------------------------------------------
+# textingest.TextSource: the sliding, double-buffered text block in front of the device parser (host logic only;
+# pinned memory is replaced by ordinary memory so that the tier needs no GPU)
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("seed", [0, 1, 2, 3])
+def test_text_source_reassembles_the_byte_stream(tmp_path, monkeypatch, seed):
+    from concurrent.futures import ThreadPoolExecutor
+    from precellar_b200 import textingest
+    monkeypatch.setattr(textingest, "_pinned", lambda n: (np.empty(int(n), np.uint8), 0))
+    monkeypatch.setattr(textingest, "_IO_SLICE", 4096)                 # plain files go through the sliced parallel reads
+    rng = np.random.default_rng(seed)
+    parts = [text_of(make_records(int(rng.integers(200, 1500)))) for _ in range(4)]
+    parts[1] = parts[1][:-1]                                           # a file without a final newline
+    paths = []
+    for k, data in enumerate(parts):
+        p = str(tmp_path / f"f{k}")
+        if k == 0:
+            p += ".fq"; open(p, "wb").write(data)
+        elif k == 1:
+            p += ".fq.gz"; open(p, "wb").write(gzip.compress(data))
+        elif k == 2:
+            p += ".bgz"; open(p, "wb").write(bgzf_bytes(data, block=3000))
+        else:
+            p += ".fq"; open(p, "wb").write(data)
+        paths.append(p)
+    want = parts[0] + parts[1] + b"\n" + parts[2] + parts[3]           # the missing newline is supplied between the files
+    cap = int(rng.integers(3000, 40000))
+    src = textingest.TextSource(paths, cap)
+    pool = ThreadPoolExecutor(max_workers=1)
+    got = bytearray()
+    try:
+        src.prefetch(pool, cap)
+        src.advance(0)
+        for _ in range(100000):
+            blk = src.block()
+            if len(blk) == 0 and src.eof:
+                break
+            # sometimes consume everything, sometimes very little (the tail then outgrows the reserved gap and the
+            # block is rebuilt, possibly in larger buffers), sometimes nothing at all
+            u = rng.random()
+            used = len(blk) if u < 0.3 else int(rng.integers(0, len(blk) + 1)) if u < 0.8 else int(rng.integers(0, min(len(blk), 50) + 1))
+            got += blk[:used].tobytes()
+            assert src.pending is None
+            src.prefetch(pool, int(rng.integers(0, 2 * cap)))
+            src.advance(used)
+        else:
+            raise AssertionError("the source did not reach the end of its input")
+        assert bytes(got) == want
+    finally:
+        src.close()
+        pool.shutdown()
