@@ -9,6 +9,7 @@
 #include <cstdio>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <unordered_map>
 #include <vector>
 
@@ -256,8 +257,17 @@ struct HostTable {
 inline int pcl_build_table(const uint8_t *bytes, const uint64_t *offsets, uint64_t n, HostTable *out, std::string *err) {
     std::vector<uint64_t> keys;
     keys.reserve(n);
-    std::unordered_map<uint64_t, uint32_t> seen;
-    seen.reserve(n * 2);
+    // set of the packed keys seen so far (marker-form keys are never 0): open addressing, load <= 0.5
+    uint64_t set_cap = 16;
+    while (set_cap < 2 * n + 2) set_cap <<= 1;
+    std::vector<uint64_t> seen(set_cap, 0ull);
+    auto seen_slot = [&](uint64_t key) -> uint64_t {
+        uint64_t h = key * 0x9E3779B97F4A7C15ull;
+        h ^= h >> 29;
+        uint64_t i = h & (set_cap - 1);
+        while (seen[i] != 0ull && seen[i] != key) i = (i + 1) & (set_cap - 1);
+        return i;
+    };
     bool all16 = true, all_le15 = true;
     for (uint64_t i = 0; i < n; ++i) {
         uint64_t a = offsets[i], b = offsets[i + 1];
@@ -270,7 +280,9 @@ inline int pcl_build_table(const uint8_t *bytes, const uint64_t *offsets, uint64
         uint64_t key = pcl_pack_key(bytes + a, 0, (uint32_t)L, false, &ninv, &ipos);
         if (ninv)
             return pcl_build_fail(err, PCL_ERR_UNSUPPORTED, "whitelist entry %llu contains a byte outside upper-case ACGT", (unsigned long long)i);
-        if (seen.emplace(key, (uint32_t)keys.size()).second) {
+        const uint64_t si = seen_slot(key);
+        if (seen[si] == 0ull) {
+            seen[si] = key;
             keys.push_back(key);
             all16 &= (L == 16);
             all_le15 &= (L <= 15);
@@ -294,7 +306,7 @@ inline int pcl_build_table(const uint8_t *bytes, const uint64_t *offsets, uint64
     // for marker-less 16-mers walk down from 0xFFFFFFFF until a free value is found (at most m steps).
     t.empty = t.mode == PCL_TAB_K64 ? 0xFFFFFFFFFFFFFFFFull : 0xFFFFFFFFull;
     if (t.mode == PCL_TAB_K32_L16)
-        while (seen.count((1ull << 32) | t.empty)) --t.empty;
+        while (seen[seen_slot((1ull << 32) | t.empty)] != 0ull) --t.empty;
     t.index_to_slot.resize(m);
     if (t.mode == PCL_TAB_K64) t.tab64.assign(t.n_slots, t.empty); else t.tab32.assign(t.n_slots, (uint32_t)t.empty);
     for (uint64_t i = 0; i < m; ++i) {
@@ -316,7 +328,8 @@ inline int pcl_build_table(const uint8_t *bytes, const uint64_t *offsets, uint64
         }
     }
     if (t.mode != PCL_TAB_K64) {
-        for (int q = 0; q < 4; ++q) {
+        // the four neighbourhood tables are independent: one host thread each (same result as a serial build)
+        auto build_q = [&](int q) {
             const uint32_t bm = 0xFFu << (8 * q);
             std::vector<uint32_t> &nt = t.ntab32[q];
             nt.assign(t.n_slots, (uint32_t)t.empty);
@@ -333,6 +346,14 @@ inline int pcl_build_table(const uint8_t *bytes, const uint64_t *offsets, uint64
                     b = (b + 1 == t.n_buckets) ? 0 : b + 1;
                 }
             }
+        };
+        if (m > 100000) {
+            std::thread th[3];
+            for (int q = 1; q < 4; ++q) th[q - 1] = std::thread(build_q, q);
+            build_q(0);
+            for (auto &x : th) x.join();
+        } else {
+            for (int q = 0; q < 4; ++q) build_q(q);
         }
     }
     *out = std::move(t);

@@ -308,3 +308,26 @@ def test_emul_random_anchor_plan_layouts():
             infos2, results, counts, defects = U.run_emul(layout, dev, threshold=0.8, use_fast=use_fast)
             U.compare_with_oracle(layout, infos2, full, results, counts, defects, ores, ocounts)
     assert n_plan >= 25, (n_plan, tries)
+
+
+def test_emul_whitelist_with_duplicates_keeps_file_order():
+    """WhitelistBuilder::new collects the barcodes into a map and Onlist::read into an IndexSet (file order, duplicates
+    dropped, region.rs:459-469): the table builder must number the entries the same way when it is handed duplicates."""
+    rng = np.random.default_rng(U.seed_of("dups"))
+    base = U.gen_whitelist(rng, 300, 16)
+    wl = []
+    for b in base:
+        wl.append(b)
+        if rng.random() < 0.3:
+            wl.append(base[int(rng.integers(len(base)))])          # an earlier (or later) entry again
+    layout = make_layout([dict(read_id="R1", elems=[bc("cb", 16), umi(10)], max_len=26)], {"cb": wl})
+    infos, strides = U.emul_infos(layout)
+    full = U.gen_reads(rng, layout, 3000, strides, p_sub=0.04, p_n=0.01, hot=10 ** 6)
+    dev = U.narrow(full, strides, infos)
+    ores, ocounts = U.run_oracle(layout, full, threshold=0.9)
+    uniq = list(dict.fromkeys(wl))
+    assert len(uniq) < len(wl) and len(ocounts[0][0]) == len(uniq)
+    for use_fast in (0, 1):
+        infos2, results, counts, defects = U.run_emul(layout, dev, threshold=0.9, use_fast=use_fast)
+        assert len(counts[0][0]) == len(uniq)
+        U.compare_with_oracle(layout, infos2, full, results, counts, defects, ores, ocounts)
