@@ -430,7 +430,7 @@ def main():
     ms_total = max_over_ranks(ms_total)
     ms_step = ms_total / args.steps
     value = n * world / (ms_step / 1e3)
-    prof = {k: pipe.profile_get(k) for k in (_ffi.K_COUNT, _ffi.K_CORRECT, _ffi.K_COUNT_LENONLY)}
+    prof = {k: pipe.profile_get(k) for k in (_ffi.K_COUNT, _ffi.K_CORRECT, _ffi.K_COUNT_LENONLY, _ffi.K_FILTER)}
     pipe.profile_enable(False)
     cnt, mismatch, total = pipe.counts(0)
     assert total == n * world, (total, n, world)                 # the allreduce summed every rank's shard
@@ -448,7 +448,9 @@ def main():
     t_count = prof[_ffi.K_COUNT][0] / max(prof[_ffi.K_COUNT][1], 1)
     t_corr = prof[_ffi.K_CORRECT][0] / max(prof[_ffi.K_CORRECT][1], 1)
     t_len = prof[_ffi.K_COUNT_LENONLY][0] / max(prof[_ffi.K_COUNT_LENONLY][1], 1)
+    t_filt = prof[_ffi.K_FILTER][0] / max(prof[_ffi.K_FILTER][1], 1)
     kern = {
+        "k_filter(R1)": {"ms": t_filt, "alg_bytes": n * f_mis * (20 + 4 * 32)},
         "k_count(R1)": {"ms": t_count, "alg_bytes": n * B_COUNT_R1},
         "k_correct(R1)": {"ms": t_corr, "alg_bytes": n * (B_CORRECT_QUAL + f_mis * B_CORRECT_PER_MISS)},
         "k_count(R2,len-only)": {"ms": t_len, "alg_bytes": n * B_COUNT_R2},

@@ -215,8 +215,13 @@ void *pcl_chunk_stream(pcl_chunk *chunk);                        /* cudaStream_t
 
 /* ---- the three stages --------------------------------------------------------------------- */
 int pcl_counts_reset(pcl_ctx *ctx);                             /* stream-ordered against every chunk (async) */
-int pcl_count(pcl_ctx *ctx, pcl_chunk *chunk);                   /* pass 1 on this chunk (async)     */
-int pcl_counts_allreduce(pcl_ctx *ctx);                          /* sums counts over ranks after every chunk's pass 1; later chunk work waits for it (async) */
+/* Pass 1 on this chunk (async).  For reads whose whitelists are 32-bit tables it also runs the stage of pass 2 that needs
+ * no counts (the 1-Hamming neighbourhood filter of the missed barcodes), so that it overlaps the all-reduce. */
+int pcl_count(pcl_ctx *ctx, pcl_chunk *chunk);
+/* Sums the counts over the ranks after every chunk's pass 1; later chunk work waits for it (async).  Once per round:
+ * with more than one rank a second call, or a pcl_count, before the next pcl_counts_reset is PCL_ERR_ARG (the counts
+ * already hold the global sums; adding to them or summing them again would multiply them by the number of ranks). */
+int pcl_counts_allreduce(pcl_ctx *ctx);
 int pcl_correct(pcl_ctx *ctx, pcl_chunk *chunk, double threshold, double max_expected_errors); /* pass 2 (async) */
 
 /* ---- outputs ------------------------------------------------------------------------------ */
@@ -312,7 +317,7 @@ void pcl_host_free(void *p);
 
 /* ---- instrumentation (used by bench.py; CUDA events on the launching stream) --------------- */
 enum { PCL_K_COUNT = 0, PCL_K_CORRECT = 1, PCL_K_COUNT_LENONLY = 2, PCL_K_ENUM = 3, PCL_K_QC = 4, PCL_K_TEXT_INDEX = 5,
-       PCL_K_TEXT_FILL = 6, PCL_K_MAX = 8 };
+       PCL_K_TEXT_FILL = 6, PCL_K_FILTER = 7, PCL_K_MAX = 16 };
 int pcl_profile_enable(pcl_ctx *ctx, int on);                    /* bracket every kernel with events */
 /* accumulated ms and launches of kernel k since the last pcl_profile_reset (syncs the ctx) */
 int pcl_profile_get(pcl_ctx *ctx, int k, double *ms, uint64_t *launches);

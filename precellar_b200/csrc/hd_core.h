@@ -22,8 +22,10 @@
 
 #ifdef __CUDACC__
 #define PCL_HD __host__ __device__ __forceinline__
+#define PCL_HD_COLD __host__ __device__ __noinline__      // rare paths: kept out of the hot loops' instruction stream
 #else
 #define PCL_HD inline
+#define PCL_HD_COLD inline
 #endif
 
 // ------------------------------------------------------------------------------------------
@@ -102,7 +104,20 @@ struct DTable {
     // All keys that differ from a query only inside byte q of the packed key (4 bases) share the query's
     // bucket there, so the 1-Hamming neighbourhood of a barcode is found with 4 bucket reads instead of 3*L.
     const uint32_t *nkeys[4];
+    // ... and one bitmap per neighbourhood table over the 24-bit index of (key with byte q removed): bit set iff some
+    // whitelist key has that partial key.  4 x 2 MB, L2-resident: a query whose partial key is absent (two of three
+    // "cold" partials of a typical miss) never touches the neighbourhood table in DRAM.
+    const uint32_t *nbits[4];
 };
+
+#define PCL_NBITS_WORDS (1u << 19)      // 2^24 bits per bitmap
+
+// 24-bit index of a 32-bit key with byte q taken out
+PCL_HD uint32_t pcl_partial_index(uint32_t key32, uint32_t q) {
+    const uint32_t lo = key32 & ((1u << (8u * q)) - 1u);
+    const uint32_t hi = q >= 3u ? 0u : ((key32 >> (8u * q + 8u)) << (8u * q));
+    return hi | lo;
+}
 
 // ------------------------------------------------------------------------------------------
 // base coding
@@ -139,6 +154,28 @@ PCL_HD uint64_t pcl_pack_key(const uint8_t *rec, uint32_t start, uint32_t len, b
     *inv_pos = ip;
     return key;
 }
+
+// ------------------------------------------------------------------------------------------
+// miss worklist entries: rec | start << 32 | len << 48 | j << 56 | one_invalid << 58 | inv_pos << 59
+// (inv_pos: position, in reported orientation, of the single non-ACGT base; barcodes with two or more such bases
+// never enter the list -- no single substitution reaches the whitelist, they stay PCL_BC_NO_MATCH)
+// ------------------------------------------------------------------------------------------
+PCL_HD unsigned long long pcl_wl_pack(uint64_t rec, uint32_t start, uint32_t len, uint32_t j, uint32_t n_invalid, uint32_t inv_pos) {
+    return (unsigned long long)rec | ((unsigned long long)(start & 0xFFFFu) << 32) | ((unsigned long long)(len & 0xFFu) << 48) |
+           ((unsigned long long)(j & 3u) << 56) | ((unsigned long long)(n_invalid == 1u ? 1u : 0u) << 58) |
+           ((unsigned long long)(n_invalid == 1u ? (inv_pos & 31u) : 0u) << 59);
+}
+#define PCL_WL_REC(e) ((uint64_t)((e) & 0xFFFFFFFFull))
+#define PCL_WL_START(e) ((uint32_t)((e) >> 32) & 0xFFFFu)
+#define PCL_WL_LEN(e) ((uint32_t)((e) >> 48) & 0xFFu)
+#define PCL_WL_J(e) ((uint32_t)((e) >> 56) & 3u)
+#define PCL_WL_NINV(e) ((uint32_t)((e) >> 58) & 1u)
+#define PCL_WL_IPOS(e) ((uint32_t)((e) >> 59) & 31u)
+// k_count_fast / k_count_spec do not locate the non-ACGT bases of a barcode (that would tax every warp for the sake of
+// a few lanes): such a barcode enters the list with this marker and k_filter re-derives key, count and position of its
+// invalid bases from the record bytes (positions are <= 15 on that path, so 31 is free).
+#define PCL_WL_REPACK_POS 31u
+#define PCL_WL_IS_REPACK(e) (PCL_WL_NINV(e) == 1u && PCL_WL_IPOS(e) == PCL_WL_REPACK_POS)
 
 // ------------------------------------------------------------------------------------------
 // whitelist table probe
@@ -485,31 +522,95 @@ PCL_HD uint32_t pcl_field_to_key(uint64_t codes, uint32_t start, uint32_t len, b
     return len >= 16u ? r : r >> (32u - 2u * len);
 }
 
+// Four bytes -> flags at bits 0, 2, 4, 6: byte k non-zero.  The high bit of ((x & 0x7F) + 0x7F) | x tells "non-zero";
+// one multiply-high by 2^25 + 2^19 + 2^13 + 2^7 moves bits 7, 15, 23, 31 to bits 32, 34, 36, 38 of the 64-bit product
+// (no two partial products share a bit, so there are no carries).
+PCL_HD uint32_t pcl_flags8(uint32_t x) {
+    const uint32_t hi = (((x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | x) & 0x80808080u;
+#ifdef __CUDA_ARCH__
+    return __umulhi(hi, 0x02082080u) & 0x55u;
+#else
+    return (uint32_t)(((uint64_t)hi * 0x02082080ull) >> 32) & 0x55u;
+#endif
+}
+
+PCL_HD uint32_t pcl_popc32(uint32_t x) {
+#ifdef __CUDA_ARCH__
+    return (uint32_t)__popc(x);
+#else
+    return (uint32_t)__builtin_popcount(x);
+#endif
+}
+
+PCL_HD uint32_t pcl_clz32(uint32_t x) {
+#ifdef __CUDA_ARCH__
+    return (uint32_t)__clz((int)x);
+#else
+    return x ? (uint32_t)__builtin_clz(x) : 32u;
+#endif
+}
+
+// Flag word of a field (bit 2i set: base i of the field, in RECORD order, is not a base) -> what pcl_pack_key reports:
+// the number of invalid positions and the position of the last one in REPORTED orientation.
+PCL_HD void pcl_flags_to_inv(uint32_t flags, uint32_t len, bool rev, uint32_t *n_invalid, uint32_t *inv_pos) {
+    *n_invalid = pcl_popc32(flags);
+    if (!flags) { *inv_pos = 0; return; }
+    // reported position p of record-order base i: forward p = i (last = highest set bit), reverse p = len-1-i (last = lowest)
+    const uint32_t hi = (31u - pcl_clz32(flags)) >> 1, lo = (31u - pcl_clz32(flags & (0u - flags))) >> 1;
+    *inv_pos = rev ? len - 1u - lo : hi;
+}
+
+// 2-bit field (base i at bits 2i, record order, already cut to `len` bases) -> reported key without marker; bases flagged
+// in `flags` contribute 0, like pcl_pack_key.
+PCL_HD uint32_t pcl_field32_to_key(uint32_t f, uint32_t len, bool rev, uint32_t flags) {
+    const uint32_t mask = len >= 16u ? 0xFFFFFFFFu : ((1u << (2u * len)) - 1u);
+    const uint32_t keep = ~(flags | (flags << 1));
+    if (rev) return (~f) & mask & keep;
+    uint32_t r = pcl_brev32(f & mask & keep);
+    r = ((r >> 1) & 0x55555555u) | ((r & 0x55555555u) << 1);
+    return len >= 16u ? r : r >> (32u - 2u * len);
+}
+
 // w[8]: the 32 record bytes.  Keys come back WITHOUT marker for 16-base fields and with it otherwise
-// (i.e. in their 4-byte device form); *_bad = the field holds a byte that is not a base.
-PCL_HD void pcl_fast_extract(const FastLayout &f, const uint32_t *w, bool rev, uint32_t *bc_key, bool *bc_bad,
-                             uint32_t *umi_key, bool *umi_bad) {
+// (i.e. in their 4-byte device form); *bc_flags: bit 2i set when base i (record order) of the barcode is not a base
+// (0 for a clean barcode); *umi_bad = the UMI holds a byte that is not a base.
+// want_flags == false (the count kernels): *bc_flags is only zero / non-zero and the key is not masked.
+PCL_HD void pcl_fast_extract(const FastLayout &f, const uint32_t *w, bool rev, uint32_t *bc_key, uint32_t *bc_flags,
+                             uint32_t *umi_key, bool *umi_bad, bool want_flags = true) {
     uint64_t codes = 0;
     uint32_t bbad = 0, ubad = 0;
+    uint32_t dd[8];
     const uint32_t fold = rev ? 0xDFDFDFDFu : 0xFFFFFFFFu;               // precellar::utils::rev_compl accepts lower case
 #ifdef __CUDA_ARCH__
 #pragma unroll
 #endif
     for (int k = 0; k < 8; ++k) {
+        dd[k] = 0u;
         if ((f.bc_mask[k] | f.umi_mask[k]) == 0u) continue;              // uniform: this word holds no barcode / UMI byte
         uint32_t d;
         const uint32_t c8 = pcl_word_codes(w[k] & fold, &d);
         codes |= (uint64_t)c8 << (8 * k);
-        bbad |= d & f.bc_mask[k];
+        dd[k] = d & f.bc_mask[k];
+        bbad |= dd[k];
         ubad |= d & f.umi_mask[k];
     }
-    uint32_t bk = pcl_field_to_key(codes, f.bc_start, f.bc_len, rev);
+    uint32_t flags = want_flags ? 0u : bbad;
+    if (bbad && want_flags) {                                             // locate the bytes that are not bases
+        uint64_t fl = 0;
+#ifdef __CUDA_ARCH__
+#pragma unroll
+#endif
+        for (int k = 0; k < 8; ++k) fl |= (uint64_t)pcl_flags8(dd[k]) << (8 * k);
+        flags = (uint32_t)(fl >> (2u * f.bc_start));
+        if (f.bc_len < 16u) flags &= (1u << (2u * f.bc_len)) - 1u;
+    }
+    uint32_t bk = pcl_field32_to_key((uint32_t)(codes >> (2u * f.bc_start)), f.bc_len, rev, want_flags ? flags : 0u);
     if (f.bc_len < 16u) bk |= 1u << (2u * f.bc_len);
     *bc_key = bk;
-    *bc_bad = bbad != 0u;
+    *bc_flags = flags;
     uint32_t uk = 0;
     if (f.umi_len) {
-        uk = pcl_field_to_key(codes, f.umi_start, f.umi_len, rev) | (1u << (2u * f.umi_len));
+        uk = pcl_field32_to_key((uint32_t)(codes >> (2u * f.umi_start)), f.umi_len, rev, 0u) | (1u << (2u * f.umi_len));
         if (ubad) uk = 0;
     }
     *umi_key = uk;
@@ -519,19 +620,22 @@ PCL_HD void pcl_fast_extract(const FastLayout &f, const uint32_t *w, bool rev, u
 // pcl_fast_extract for a 16-base barcode in words [kBcW, kBcW + 4) and a UMI of 4 * kUmiW bases in words
 // [kUmiW0, kUmiW0 + kUmiW) (kUmiW == 0: none): same results, everything about the geometry known at compile time.
 template <int kBcW, int kUmiW0, int kUmiW>
-PCL_HD void pcl_fast_extract_aligned(const uint32_t *w, bool rev, uint32_t *bc_key, bool *bc_bad, uint32_t *umi_key, bool *umi_bad) {
+PCL_HD void pcl_fast_extract_aligned(const uint32_t *w, bool rev, uint32_t *bc_key, uint32_t *bc_flags, uint32_t *umi_key, bool *umi_bad,
+                                     bool want_flags = true) {
     const uint32_t fold = rev ? 0xDFDFDFDFu : 0xFFFFFFFFu;
     uint32_t bcodes = 0, bbad = 0;
+    uint32_t d[4];
 #ifdef __CUDA_ARCH__
 #pragma unroll
 #endif
     for (int k = 0; k < 4; ++k) {
-        uint32_t d;
-        bcodes |= pcl_word_codes(w[kBcW + k] & fold, &d) << (8 * k);
-        bbad |= d;
+        bcodes |= pcl_word_codes(w[kBcW + k] & fold, &d[k]) << (8 * k);
+        bbad |= d[k];
     }
-    *bc_key = pcl_field_to_key(bcodes, 0u, 16u, rev);
-    *bc_bad = bbad != 0u;
+    uint32_t flags = want_flags ? 0u : bbad;
+    if (bbad && want_flags) flags = pcl_flags8(d[0]) | (pcl_flags8(d[1]) << 8) | (pcl_flags8(d[2]) << 16) | (pcl_flags8(d[3]) << 24);
+    *bc_key = pcl_field32_to_key(bcodes, 16u, rev, want_flags ? flags : 0u);
+    *bc_flags = flags;
     uint32_t uk = 0, ubad = 0;
     if (kUmiW > 0) {
         uint32_t ucodes = 0;
@@ -539,25 +643,50 @@ PCL_HD void pcl_fast_extract_aligned(const uint32_t *w, bool rev, uint32_t *bc_k
 #pragma unroll
 #endif
         for (int k = 0; k < kUmiW; ++k) {
-            uint32_t d;
-            ucodes |= pcl_word_codes(w[kUmiW0 + k] & fold, &d) << (8 * k);
-            ubad |= d;
+            uint32_t du;
+            ucodes |= pcl_word_codes(w[kUmiW0 + k] & fold, &du) << (8 * k);
+            ubad |= du;
         }
-        uk = pcl_field_to_key(ucodes, 0u, 4u * kUmiW, rev) | (1u << (8u * kUmiW));
+        uk = pcl_field32_to_key(ucodes, 4u * kUmiW, rev, 0u) | (1u << (8u * kUmiW));
         if (ubad) uk = 0;
     }
     *umi_key = uk;
     *umi_bad = ubad != 0u;
 }
 
-PCL_HD void pcl_fast_extract_spec(const FastLayout &f, const uint32_t *w, bool rev, uint32_t *bc_key, bool *bc_bad,
-                                  uint32_t *umi_key, bool *umi_bad) {
+PCL_HD void pcl_fast_extract_spec(const FastLayout &f, const uint32_t *w, bool rev, uint32_t *bc_key, uint32_t *bc_flags,
+                                  uint32_t *umi_key, bool *umi_bad, bool want_flags = true) {
     switch (f.spec) {
-        case PCL_FAST_SPEC_B0_U16x12: pcl_fast_extract_aligned<0, 4, 3>(w, rev, bc_key, bc_bad, umi_key, umi_bad); break;
-        case PCL_FAST_SPEC_B0: pcl_fast_extract_aligned<0, 0, 0>(w, rev, bc_key, bc_bad, umi_key, umi_bad); break;
-        case PCL_FAST_SPEC_B8: pcl_fast_extract_aligned<2, 0, 0>(w, rev, bc_key, bc_bad, umi_key, umi_bad); break;
-        default: pcl_fast_extract(f, w, rev, bc_key, bc_bad, umi_key, umi_bad); break;
+        case PCL_FAST_SPEC_B0_U16x12: pcl_fast_extract_aligned<0, 4, 3>(w, rev, bc_key, bc_flags, umi_key, umi_bad, want_flags); break;
+        case PCL_FAST_SPEC_B0: pcl_fast_extract_aligned<0, 0, 0>(w, rev, bc_key, bc_flags, umi_key, umi_bad, want_flags); break;
+        case PCL_FAST_SPEC_B8: pcl_fast_extract_aligned<2, 0, 0>(w, rev, bc_key, bc_flags, umi_key, umi_bad, want_flags); break;
+        default: pcl_fast_extract(f, w, rev, bc_key, bc_flags, umi_key, umi_bad, want_flags); break;
     }
+}
+
+// What k_filter does with a PCL_WL_REPACK entry: key (invalid bases read as 0), number of invalid bases and the position
+// of the last one in reported orientation.  pcl_repack16: a 16-base barcode in four aligned words (PCL_FAST_SPEC_*);
+// pcl_fast_repack: any FastLayout, from the record's words.
+PCL_HD uint32_t pcl_repack16(uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3, bool rev, uint32_t *n_invalid, uint32_t *inv_pos) {
+    const uint32_t fold = rev ? 0xDFDFDFDFu : 0xFFFFFFFFu;
+    uint32_t d0, d1, d2, d3;
+    const uint32_t codes = pcl_word_codes(w0 & fold, &d0) | (pcl_word_codes(w1 & fold, &d1) << 8) |
+                           (pcl_word_codes(w2 & fold, &d2) << 16) | (pcl_word_codes(w3 & fold, &d3) << 24);
+    const uint32_t flags = pcl_flags8(d0) | (pcl_flags8(d1) << 8) | (pcl_flags8(d2) << 16) | (pcl_flags8(d3) << 24);
+    pcl_flags_to_inv(flags, 16u, rev, n_invalid, inv_pos);
+    return pcl_field32_to_key(codes, 16u, rev, flags);
+}
+
+PCL_HD_COLD uint32_t pcl_fast_repack(const FastLayout &f, const uint32_t *w, bool rev, uint32_t *n_invalid, uint32_t *inv_pos) {
+    if (f.spec != PCL_FAST_SPEC_NONE) {
+        const uint32_t k = f.bc_start >> 2;
+        return pcl_repack16(w[k], w[k + 1], w[k + 2], w[k + 3], rev, n_invalid, inv_pos);
+    }
+    uint32_t key, flags, uk;
+    bool ub;
+    pcl_fast_extract(f, w, rev, &key, &flags, &uk, &ub, true);
+    pcl_flags_to_inv(flags, f.bc_len, rev, n_invalid, inv_pos);
+    return key;
 }
 
 // Any of the 8 keys of bucket b equal to k?  *full = the bucket has no free slot (a longer probe chain is possible).
@@ -566,14 +695,6 @@ PCL_HD bool pcl_bucket32_any(const uint32_t *keys, uint32_t b, uint32_t k, uint3
     auto v1 = PCL_LDG128(keys + (uint64_t)b * 8 + 4);
     *full = v1.w != empty;
     return (v0.x == k) | (v0.y == k) | (v0.z == k) | (v0.w == k) | (v1.x == k) | (v1.y == k) | (v1.z == k) | (v1.w == k);
-}
-
-PCL_HD uint32_t pcl_clz32(uint32_t x) {
-#ifdef __CUDA_ARCH__
-    return (uint32_t)__clz((int)x);
-#else
-    return (uint32_t)__builtin_clz(x);
-#endif
 }
 
 PCL_HD uint32_t pcl_ctz64(uint64_t x) {
@@ -585,59 +706,118 @@ PCL_HD uint32_t pcl_ctz64(uint64_t x) {
 }
 
 // correct_barcode / likelihood1 for barcodes of a 32-bit table (see pcl_correct_one for the semantics).
-// `key32` is the 4-byte device key (marker kept for < 16 bases, dropped for 16).
+// `key32` is the 4-byte device key (marker kept for < 16 bases, dropped for 16; an invalid base reads as 0).
 //
-// Two phases, so that the common case (a neighbour that is simply absent) is straight-line code:
-//   1. filter: one bucket per neighbour, branch-free; a neighbour survives when it is found or when its
-//      bucket is full (the probe chain may continue in the next bucket).  Survivors are bits of a 64-bit mask
+// Two stages, so that the common case (a neighbour that is simply absent) is straight-line code and so that the
+// stage that needs no counts can run before the counts of all ranks are known:
+//   1. pcl_filter32: the 1-Hamming neighbours of the query that may be whitelist members, as bits of a 64-bit mask
 //      indexed (pos << 2 | base), i.e. already in the reference's (pos, ACGT) order.
-//   2. resolve: the few survivors are probed completely, in mask order, and enter the fp64 posterior in that
-//      order (barcode.rs:319-334: sum order and first-maximum tie-break).
-PCL_HD uint32_t pcl_correct_one32(const DTable &t, uint32_t key32, uint32_t len, uint32_t n_invalid, uint32_t inv_pos,
-                                  const uint8_t *qual, uint32_t start, bool rev, double threshold, const double *lut_cap,
-                                  uint32_t *out_key) {
-    if (n_invalid > 1u) return PCL_BC_NO_MATCH;
-    if (t.mode == PCL_TAB_K32_L16 ? len != 16u : len > 15u) return PCL_BC_NO_MATCH;   // no entry of that length
-    const uint32_t *keys = reinterpret_cast<const uint32_t *>(t.keys);
-    const uint32_t empty = (uint32_t)t.empty, nb = t.n_buckets;
-    const uint32_t p0 = n_invalid == 1u ? inv_pos : 0u, p1 = n_invalid == 1u ? inv_pos + 1u : len;
-    uint64_t pend = 0;
-    if (t.nkeys[0]) {
-        // neighbourhood tables: one bucket chain per byte of the key
-        const uint32_t inv_sh = 2u * (len - 1u - (n_invalid == 1u ? inv_pos : 0u));
-        const uint32_t q0 = n_invalid == 1u ? inv_sh >> 3 : 0u, q1 = n_invalid == 1u ? q0 + 1u : 4u;
-        for (uint32_t q = q0; q < q1; ++q) {
-            const uint32_t bm = 0xFFu << (8u * q);
-            if (len < 16u && (bm & ((1u << (2u * len)) - 1u)) == 0u) continue;        // byte q holds no base of this key
-            const uint32_t part = key32 & ~bm;
-            const uint32_t *nk = t.nkeys[q];
-            uint32_t b = pcl_hash32_bucket(part, nb);
-            for (;;) {
-                auto v0 = PCL_LDG128(nk + (uint64_t)b * 8);
-                auto v1 = PCL_LDG128(nk + (uint64_t)b * 8 + 4);
-                const uint32_t e[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+//   2. pcl_resolve32: the few survivors are probed in the main table, in mask order, and enter the fp64 posterior in
+//      that order (barcode.rs:319-334: sum order and first-maximum tie-break).
+// Is table q worth a look?  Byte q must hold a base of this key, be the byte of the N when there is one, and some
+// whitelist key must share the query's other three bytes (bitmap; L2-resident).
+PCL_HD bool pcl_filter_live(const DTable &t, uint32_t key32, uint32_t len, uint32_t n_invalid, uint32_t inv_pos, uint32_t q) {
+    if (n_invalid == 1u && ((2u * (len - 1u - inv_pos)) >> 3) != q) return false;
+    if (len < 16u && ((0xFFu << (8u * q)) & ((1u << (2u * len)) - 1u)) == 0u) return false;   // byte q holds no base of this key
+    if (!t.nbits[q]) return true;
+    const uint32_t idx = pcl_partial_index(key32, q);
+#ifdef __CUDA_ARCH__
+    return (__ldg(t.nbits[q] + (idx >> 5)) >> (idx & 31u)) & 1u;
+#else
+    return (t.nbits[q][idx >> 5] >> (idx & 31u)) & 1u;
+#endif
+}
+
+// (bytes << 8) | byte q of e
+PCL_HD uint32_t pcl_push_byte(uint32_t bytes, uint32_t e, uint32_t q) {
+#ifdef __CUDA_ARCH__
+    return __byte_perm(bytes, e, 0x2100u | (4u + q));             // result bytes: [e.q, bytes.0, bytes.1, bytes.2]
+#else
+    return (bytes << 8) | ((e >> (8u * q)) & 0xFFu);
+#endif
+}
+
+// One candidate byte `eb` of table q against the query byte `qb`: its bit in the table's 16-bit sub-mask
+// (bit 4 * (3 - base_in_byte) + base_value), or 0 when the two bytes are not exactly one substitution apart
+// (with an N in the query: when they differ anywhere but at the N).
+PCL_HD uint32_t pcl_byte_candidate(uint32_t eb, uint32_t qb, bool has_n, uint32_t n_p2) {
+    const uint32_t xb = eb ^ qb;
+    const uint32_t d = (xb | (xb >> 1)) & 0x55u;                     // one bit per differing base of the byte
+    const bool one = has_n ? (d & ~(1u << n_p2)) == 0u : (d != 0u && (d & (d - 1u)) == 0u);
+    const uint32_t p2 = has_n ? n_p2 : 31u - pcl_clz32(d | 1u);      // bit index (0, 2, 4, 6) of the substituted base
+    return one ? 1u << (12u - 2u * p2 + ((eb >> p2) & 3u)) : 0u;
+}
+
+PCL_HD_COLD uint32_t pcl_bucket_candidates(uint32_t e0, uint32_t e1, uint32_t e2, uint32_t e3, uint32_t e4, uint32_t e5, uint32_t e6,
+                                           uint32_t e7, uint32_t key32, uint32_t keep, uint32_t sq, uint32_t qb, bool has_n, uint32_t n_p2) {
+    const uint32_t e[8] = {e0, e1, e2, e3, e4, e5, e6, e7};
+    uint32_t sub = 0;
 #ifdef __CUDA_ARCH__
 #pragma unroll
 #endif
-                for (int k = 0; k < 8; ++k) {
-                    const uint32_t x = e[k] ^ key32;
-                    if ((x & ~bm) != 0u || e[k] == empty) continue;                    // another neighbourhood / free slot
-                    const uint32_t d = (x | (x >> 1)) & 0x55555555u;                   // one bit per differing base
-                    if (n_invalid == 1u) {
-                        if (d & ~(1u << inv_sh)) continue;                             // may differ at the N position only
-                        pend |= 1ull << (4u * inv_pos + ((e[k] >> inv_sh) & 3u));
-                    } else {
-                        if (d == 0u || (d & (d - 1u)) != 0u) continue;                 // exactly one substitution
-                        const uint32_t sh = 31u - pcl_clz32(d);                        // even bit index of that base
-                        if (sh >= 2u * len) continue;                                  // the difference touches the length marker
-                        pend |= 1ull << (4u * (len - 1u - (sh >> 1)) + ((e[k] >> sh) & 3u));
-                    }
-                }
-                if (v1.w == empty) break;                                              // the chain ends at a bucket with a free slot
-                b = (b + 1u == nb) ? 0u : b + 1u;
-            }
-        }
-    } else
+    for (int k = 0; k < 8; ++k)
+        if (((e[k] ^ key32) & keep) == 0u) sub |= pcl_byte_candidate((e[k] >> sq) & 0xFFu, qb, has_n, n_p2);
+    return sub;
+}
+
+// One bucket of neighbourhood table q against the query: the table's 16-bit sub-mask of 1-Hamming neighbours found in
+// it (they differ from the query inside byte q only); *full = the chain continues in the next bucket.  The entries that
+// share the query's other three bytes are found with one compare each and their q-th bytes queued in a register (an
+// empty slot that happens to share them queues a byte too: the main-table probe of pcl_resolve32 drops that candidate);
+// the queued bytes -- one, seldom two -- go through the 1-Hamming test.  has_n: the query holds one non-ACGT base, at bit
+// n_p2 (0, 2, 4, 6) of byte q.
+PCL_HD uint32_t pcl_filter_bucket(const uint32_t *nk, uint32_t b, uint32_t key32, uint32_t q, uint32_t empty, bool has_n,
+                                  uint32_t n_p2, bool *full) {
+    const uint32_t sq = 8u * q, keep = ~(0xFFu << sq);
+    const uint32_t qb = (key32 >> sq) & 0xFFu;
+    auto v0 = PCL_LDG128(nk + (uint64_t)b * 8);
+    auto v1 = PCL_LDG128(nk + (uint64_t)b * 8 + 4);
+    const uint32_t e[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+    uint32_t n_match = 0, bytes = 0;
+#ifdef __CUDA_ARCH__
+#pragma unroll
+#endif
+    for (int k = 0; k < 8; ++k) {
+        const bool mk = ((e[k] ^ key32) & keep) == 0u;
+        bytes = mk ? pcl_push_byte(bytes, e[k], q) : bytes;
+        n_match += mk;
+    }
+    // (queue slots beyond n_match hold zeros: tested, counted only when filled)
+    const uint32_t c0 = pcl_byte_candidate(bytes & 0xFFu, qb, has_n, n_p2);
+    const uint32_t c1 = pcl_byte_candidate((bytes >> 8) & 0xFFu, qb, has_n, n_p2);
+    uint32_t sub = (n_match >= 1u ? c0 : 0u) | (n_match >= 2u ? c1 : 0u);
+    if (n_match > 2u) sub |= pcl_bucket_candidates(e[0], e[1], e[2], e[3], e[4], e[5], e[6], e[7], key32, keep, sq, qb, has_n, n_p2);   // rare
+    *full = v1.w != empty;                                 // the chain ends at a bucket with a free slot
+    return sub;
+}
+
+// Sub-mask of table q (bit 4 * (3 - base_in_byte) + base_value) -> bits (pos << 2 | base) of the candidate mask:
+// base p2/2 of byte q is position len - 1 - (4q + p2/2), so sub-mask bit 0 belongs to position len - 4 - 4q.  For keys
+// shorter than 16 bases the top byte holds fewer than four bases (and the marker): positions < 0 fall off.
+PCL_HD uint64_t pcl_filter_place(uint32_t sub, uint32_t len, uint32_t q) {
+    const int sh4 = 4 * ((int)len - 4 - 4 * (int)q);
+    return sh4 >= 0 ? (uint64_t)sub << sh4 : (uint64_t)(sub >> (-sh4));
+}
+
+PCL_HD uint64_t pcl_filter_scan(const DTable &t, uint32_t key32, uint32_t len, uint32_t n_invalid, uint32_t inv_pos, uint32_t q) {
+    const uint32_t nb = t.n_buckets;
+    const uint32_t n_p2 = (2u * (len - 1u - (n_invalid == 1u ? inv_pos : 0u))) & 7u;
+    uint32_t b = pcl_hash32_bucket(key32 & ~(0xFFu << (8u * q)), nb), sub = 0;
+    bool full = true;
+    while (full) {
+        sub |= pcl_filter_bucket(t.nkeys[q], b, key32, q, (uint32_t)t.empty, n_invalid == 1u, n_p2, &full);
+        b = (b + 1u == nb) ? 0u : b + 1u;
+    }
+    return pcl_filter_place(sub, len, q);
+}
+
+// Without neighbourhood tables (PCL_NO_NEIGHBOUR_TABLES, kept for tests): one bucket of the main table per neighbour,
+// branch-free; a neighbour survives when it is found or when its bucket is full (the probe chain may continue).
+PCL_HD_COLD uint64_t pcl_filter_direct(const DTable &t, uint32_t key32, uint32_t len, uint32_t n_invalid, uint32_t inv_pos) {
+    const uint32_t *keys = reinterpret_cast<const uint32_t *>(t.keys);
+    const uint32_t empty = (uint32_t)t.empty, nb = t.n_buckets;
+    uint64_t pend = 0;
+    const uint32_t p0 = n_invalid == 1u ? inv_pos : 0u, p1 = n_invalid == 1u ? inv_pos + 1u : len;
     for (uint32_t pos = p0; pos < p1; ++pos) {
         const uint32_t sh = 2u * (len - 1u - pos);
         const uint32_t existing = n_invalid == 1u ? 4u : ((key32 >> sh) & 3u);
@@ -657,6 +837,26 @@ PCL_HD uint32_t pcl_correct_one32(const DTable &t, uint32_t key32, uint32_t len,
         }
         pend |= (uint64_t)m4 << (4u * pos);
     }
+    return pend;
+}
+
+// no entry of that length in the table, or no single substitution can reach the whitelist
+PCL_HD bool pcl_filter_hopeless(const DTable &t, uint32_t len, uint32_t n_invalid) {
+    return n_invalid > 1u || (t.mode == PCL_TAB_K32_L16 ? len != 16u : len > 15u);
+}
+
+PCL_HD uint64_t pcl_filter32(const DTable &t, uint32_t key32, uint32_t len, uint32_t n_invalid, uint32_t inv_pos) {
+    if (pcl_filter_hopeless(t, len, n_invalid)) return 0;
+    if (!t.nkeys[0]) return pcl_filter_direct(t, key32, len, n_invalid, inv_pos);
+    uint64_t pend = 0;
+    for (uint32_t q = 0; q < 4u; ++q)
+        if (pcl_filter_live(t, key32, len, n_invalid, inv_pos, q)) pend |= pcl_filter_scan(t, key32, len, n_invalid, inv_pos, q);
+    return pend;
+}
+
+// `qual` points at the record's quality row in record-relative indexing (see pcl_correct_one).
+PCL_HD uint32_t pcl_resolve32(const DTable &t, uint32_t key32, uint32_t len, uint64_t pend, const uint8_t *qual, uint32_t start,
+                              bool rev, double threshold, const double *lut_cap, uint32_t *out_key) {
     bool have = false;
     double best_like = 0.0, total = 0.0;
     uint32_t best_key = 0;
@@ -679,6 +879,14 @@ PCL_HD uint32_t pcl_correct_one32(const DTable &t, uint32_t key32, uint32_t len,
     if (prob <= 0.0) return PCL_BC_NO_MATCH;
     if (prob >= threshold) { *out_key = best_key; return PCL_BC_CORRECTED; }
     return PCL_BC_LOW_CONF;
+}
+
+PCL_HD uint32_t pcl_correct_one32(const DTable &t, uint32_t key32, uint32_t len, uint32_t n_invalid, uint32_t inv_pos,
+                                  const uint8_t *qual, uint32_t start, bool rev, double threshold, const double *lut_cap,
+                                  uint32_t *out_key) {
+    const uint64_t pend = pcl_filter32(t, key32, len, n_invalid, inv_pos);
+    if (!pend) return PCL_BC_NO_MATCH;
+    return pcl_resolve32(t, key32, len, pend, qual, start, rev, threshold, lut_cap, out_key);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -751,11 +959,17 @@ PCL_HD uint64_t pcl_brev64(uint64_t x) {
 }
 
 // pcl_pack_key on the code representation: key in marker form, *n_invalid = bases that are not bases.
-PCL_HD uint64_t pcl_pack_codes(const RecCodes &rc, uint32_t start, uint32_t len, bool rev, uint32_t *n_invalid) {
+PCL_HD uint64_t pcl_pack_codes(const RecCodes &rc, uint32_t start, uint32_t len, bool rev, uint32_t *n_invalid,
+                               uint32_t *inv_pos = nullptr) {
+    if (inv_pos) *inv_pos = 0;
     if (len > PCL_MAX_KEY_LEN) { *n_invalid = len; return 0; }
     if (len == 0u) { *n_invalid = 0; return 1; }
     const uint64_t bad = pcl_bits128(rc.bad_lo, rc.bad_hi, start, len);
     *n_invalid = pcl_popc64(bad);
+    if (inv_pos && bad) {                                            // the last invalid position in reported orientation
+        const uint32_t lo = pcl_ctz64(bad) >> 1, hi = (63u - pcl_ctz64(pcl_brev64(bad))) >> 1;
+        *inv_pos = rev ? len - 1u - lo : hi;
+    }
     uint64_t f = pcl_bits128(rc.lo, rc.hi, start, len);
     f &= ~(bad | (bad << 1));                                        // invalid positions contribute 0, like pcl_pack_key
     const uint64_t mask = (1ull << (2u * len)) - 1ull;
@@ -808,18 +1022,6 @@ struct Codes32 {
     uint32_t bd[4];     // bit 2(i % 16) set: byte i is not a base for barcodes / UMIs (case folded on neg-strand reads)
     uint32_t sb[4];     // the same with the strict upper-case test used for anchors (== bd on forward reads)
 };
-
-// Four bytes -> flags at bits 0, 2, 4, 6: byte k non-zero.  The high bit of ((x & 0x7F) + 0x7F) | x tells "non-zero";
-// one multiply-high by 2^25 + 2^19 + 2^13 + 2^7 moves bits 7, 15, 23, 31 to bits 32, 34, 36, 38 of the 64-bit product
-// (no two partial products share a bit, so there are no carries).
-PCL_HD uint32_t pcl_flags8(uint32_t x) {
-    const uint32_t hi = (((x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | x) & 0x80808080u;
-#ifdef __CUDA_ARCH__
-    return __umulhi(hi, 0x02082080u) & 0x55u;
-#else
-    return (uint32_t)(((uint64_t)hi * 0x02082080ull) >> 32) & 0x55u;
-#endif
-}
 
 template <bool kRev>
 PCL_HD void pcl_codes32_t(const uint32_t *w, int n_words, Codes32 &k) {
@@ -975,18 +1177,16 @@ PCL_HD uint32_t pcl_anchor_coord(const DRead &rd, const AnchorSplit &s, uint32_t
 // Device-form 32-bit key (marker kept below 16 bases) of the field at coordinate `coord`; `k2` holds the strings
 // shifted down by s.pos bases, so that elements behind the anchor sit at the warp-uniform offset ustart[e].
 PCL_HD uint32_t pcl_anchor_key(const DRead &rd, const Codes32 &k, const uint32_t *c2, const uint32_t *bd2, uint32_t e, uint32_t coord,
-                               uint32_t *n_invalid) {
+                               uint32_t *n_invalid, uint32_t *inv_pos = nullptr) {
     const uint32_t len = coord & 0xFFFFu, us = rd.plan.ustart[e];
     const bool behind = e > rd.plan.v;
     const uint32_t wlen = len > 16u ? 16u : len;
+    if (inv_pos) *inv_pos = 0;
     if (wlen == 0u) { *n_invalid = 0; return 1u; }                                // an empty field: marker only, like pcl_pack_key
     uint32_t f = pcl_win32u(behind ? c2 : k.c, us, wlen);                         // `us` and `behind` are warp-uniform
     const uint32_t bad = pcl_win32u(behind ? bd2 : k.bd, us, wlen);
-#ifdef __CUDA_ARCH__
-    *n_invalid = (uint32_t)__popc(bad);
-#else
-    *n_invalid = (uint32_t)__builtin_popcount(bad);
-#endif
+    if (inv_pos) pcl_flags_to_inv(bad, wlen, rd.is_reverse != 0, n_invalid, inv_pos);
+    else *n_invalid = pcl_popc32(bad);
     const uint32_t bad2 = bad | (bad << 1);
     const bool rev = rd.is_reverse != 0;
     uint32_t key;

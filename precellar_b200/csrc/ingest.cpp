@@ -226,7 +226,16 @@ int64_t pcl_fastq_read(pcl_fastq *r, uint64_t max_records, uint32_t stride, uint
                 r->err = "text arena too small";
                 return PCL_ERR_NOMEM;
             }
-            memcpy(text + used, def.data() + 1, def.size() - 1); used += def.size() - 1; off[3 * n + 1] = used;
+            // BatchedFqReader strips a trailing /1 or /2 from the NAME of every record before anything downstream sees
+            // it (strip_fq_suffix, fastq.rs:421,612-621), so AnnotatedFastq and the make_fastq files carry the stripped
+            // name; the description stays.
+            size_t e = 1;
+            while (e < def.size() && def[e] != ' ' && def[e] != '\t') ++e;
+            size_t name_len = e - 1;
+            if (name_len > 2 && def[e - 2] == '/' && (def[e - 1] == '1' || def[e - 1] == '2')) name_len -= 2;
+            memcpy(text + used, def.data() + 1, name_len); used += name_len;
+            memcpy(text + used, def.data() + e, def.size() - e); used += def.size() - e;
+            off[3 * n + 1] = used;
             memcpy(text + used, s.data(), L); used += L; off[3 * n + 2] = used;
             memcpy(text + used, q.data(), L); used += L; off[3 * n + 3] = used;
         }

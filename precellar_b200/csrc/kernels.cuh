@@ -33,7 +33,8 @@ struct CountParams {
     uint8_t umi_key_bytes[PCL_MAX_UMI_PER_READ];
     uint8_t bc_elem[PCL_MAX_BC_PER_READ];
     uint8_t umi_elem[PCL_MAX_UMI_PER_READ];
-    unsigned long long *worklist;        // entries: rec | start<<32 | len<<48 | j<<56
+    unsigned long long *worklist;        // entries: pcl_wl_pack (hd_core.h)
+    uint32_t *wl_key;                    // the 4-byte device key of every entry (reads whose tables are all 32-bit), else NULL
     unsigned long long *wl_count;
     unsigned long long *num_defect;
     uint32_t hist_admit_mask;            // k_count_fast: admit a new key to the histogram cache on 1 of (mask + 1) sightings
@@ -54,6 +55,8 @@ struct CorrectParams {
     uint8_t bc_elem[PCL_MAX_BC_PER_READ];
     uint16_t static_start[PCL_MAX_ELEMS];
     unsigned long long *worklist;
+    uint32_t *wl_key;
+    unsigned long long *wl_cand;         // k_filter -> k_resolve: candidate mask of every entry, bit (pos << 2 | base)
     unsigned long long *wl_count;
     const double *lut_cap;
     const double *lut_raw;
@@ -62,10 +65,6 @@ struct CorrectParams {
     int check_ee;
 };
 
-__device__ __forceinline__ unsigned long long pcl_wl_entry(uint64_t rec, uint32_t start, uint32_t len, uint32_t j) {
-    return (unsigned long long)rec | ((unsigned long long)start << 32) | ((unsigned long long)len << 48) |
-           ((unsigned long long)j << 56);
-}
 
 // Worklist allocation.  A single global cursor bumped once per warp iteration serialises on one L2 address
 // (millions of same-address returning atomics per launch).  Each warp instead reserves PCL_WL_BATCH entries
@@ -78,23 +77,26 @@ __device__ __forceinline__ unsigned long long pcl_wl_entry(uint64_t rec, uint32_
 struct WlCursor { unsigned long long pos, end; };
 
 template <typename P>
-__device__ __forceinline__ void pcl_wl_push(const P &p, WlCursor &cur, bool m, unsigned long long entry, uint32_t lane) {
+__device__ __forceinline__ void pcl_wl_push(const P &p, WlCursor &cur, bool m, unsigned long long entry, uint32_t key, uint32_t lane) {
     const uint32_t ballot = __ballot_sync(0xFFFFFFFFu, m);
     if (!ballot) return;
     const unsigned long long need = __popc(ballot), rank = __popc(ballot & ((1u << lane) - 1u));
     const unsigned long long rem = cur.end - cur.pos;   // warp-uniform
+    unsigned long long at = cur.pos + rank;
     if (need > rem) {
         // finish the old reservation exactly (no holes in the middle of the list), continue in a new one
-        if (m && rank < rem) p.worklist[cur.pos + rank] = entry;
         unsigned long long b = 0;
         if (lane == 0) b = atomicAdd(p.wl_count, (unsigned long long)PCL_WL_BATCH);
         b = __shfl_sync(0xFFFFFFFFu, b, 0);
-        if (m && rank >= rem) p.worklist[b + rank - rem] = entry;
+        if (rank >= rem) at = b + rank - rem;
         cur.pos = b + need - rem;
         cur.end = b + PCL_WL_BATCH;
     } else {
-        if (m) p.worklist[cur.pos + rank] = entry;
         cur.pos += need;
+    }
+    if (m) {
+        p.worklist[at] = entry;
+        if (p.wl_key) p.wl_key[at] = key;
     }
 }
 
@@ -185,7 +187,8 @@ __global__ void __launch_bounds__(PCL_BLOCK, kMode == 2 ? 4 : 1) k_count(const _
         const uint64_t i = base + lane;
         const bool live = i < p.n;
         uint32_t miss_mask_j = 0;                 // bit j: barcode j of this record goes to the worklist
-        uint32_t miss_coord[PCL_MAX_BC_PER_READ];
+        unsigned long long miss_ent[PCL_MAX_BC_PER_READ];
+        uint32_t miss_key[PCL_MAX_BC_PER_READ];
         if (live) {
             uint32_t L = p.len[i];
             if (rd.max_len && L > rd.max_len) L = rd.max_len;          // FastqReader::read_record (read.rs:98-103)
@@ -224,8 +227,8 @@ __global__ void __launch_bounds__(PCL_BLOCK, kMode == 2 ? 4 : 1) k_count(const _
                     uint32_t code = PCL_BC_ABSENT, key = 0;
                     if (c != PCL_COORD_ABSENT) {
                         const uint32_t blen = c & 0xFFFFu;
-                        uint32_t ninv;
-                        key = pcl_anchor_key(rd, k, c2, bd2, e, c, &ninv);
+                        uint32_t ninv, ipos;
+                        key = pcl_anchor_key(rd, k, c2, bd2, e, c, &ninv, &ipos);
                         const DTable &t = p.tab[j];
                         uint32_t slot = 0xFFFFFFFFu;
                         if (ninv == 0u && (t.mode == PCL_TAB_K32_L16 ? blen == 16u : blen <= 15u)) slot = pcl_probe32(t, key);
@@ -236,8 +239,11 @@ __global__ void __launch_bounds__(PCL_BLOCK, kMode == 2 ? 4 : 1) k_count(const _
                         } else {
                             code = PCL_BC_NO_MATCH;
                             ++n_mis[j];
-                            miss_mask_j |= 1u << j;
-                            miss_coord[j] = c;
+                            if (ninv <= 1u) {                          // two or more non-ACGT bases: NoMatch is final
+                                miss_mask_j |= 1u << j;
+                                miss_ent[j] = pcl_wl_pack(i, c >> 16, blen, j, ninv, ipos);
+                                miss_key[j] = key;
+                            }
                         }
                     }
                     reinterpret_cast<uint32_t *>(p.bc_key[j])[i] = key;
@@ -292,7 +298,7 @@ __global__ void __launch_bounds__(PCL_BLOCK, kMode == 2 ? 4 : 1) k_count(const _
                 if (c != PCL_COORD_ABSENT) {
                     const uint32_t start = c >> 16, blen = c & 0xFFFFu;
                     uint32_t ninv, ipos;
-                    key = kCodes ? pcl_pack_codes(rc, start, blen, rev, &ninv) : pcl_pack_key(rec, start, blen, rev, &ninv, &ipos);
+                    key = kCodes ? pcl_pack_codes(rc, start, blen, rev, &ninv, &ipos) : pcl_pack_key(rec, start, blen, rev, &ninv, &ipos);
                     uint32_t slot = 0xFFFFFFFFu;
                     if (ninv == 0u) slot = pcl_probe(p.tab[j], key, blen);
                     ++n_total[j];                                      // WhitelistBuilder::add (barcode.rs:410-426)
@@ -302,8 +308,11 @@ __global__ void __launch_bounds__(PCL_BLOCK, kMode == 2 ? 4 : 1) k_count(const _
                     } else {
                         code = PCL_BC_NO_MATCH;
                         ++n_mis[j];
-                        miss_mask_j |= 1u << j;
-                        miss_coord[j] = c;
+                        if (ninv <= 1u) {                              // two or more non-ACGT bases (or an unpackable length): NoMatch is final
+                            miss_mask_j |= 1u << j;
+                            miss_ent[j] = pcl_wl_pack(i, start, blen, j, ninv, ipos);
+                            miss_key[j] = (uint32_t)key;
+                        }
                     }
                 }
                 pcl_store_key(p.bc_key[j], p.bc_key_bytes[j], i, key);
@@ -331,7 +340,7 @@ __global__ void __launch_bounds__(PCL_BLOCK, kMode == 2 ? 4 : 1) k_count(const _
         for (uint32_t j = 0; j < PCL_MAX_BC_PER_READ; ++j) {
             if (j >= rd.n_bc) break;
             const bool m = (miss_mask_j >> j) & 1u;
-            pcl_wl_push(p, wl, m, m ? pcl_wl_entry(i, miss_coord[j] >> 16, miss_coord[j] & 0xFFFFu, j) : 0ull, lane);
+            pcl_wl_push(p, wl, m, m ? miss_ent[j] : 0ull, m ? miss_key[j] : 0u, lane);
         }
     }
     pcl_wl_finish(p, wl, lane);
@@ -413,14 +422,14 @@ __global__ void __launch_bounds__(PCL_BLOCK << (kBits - PCL_HCACHE_BITS)) k_coun
     }
     // pending (probed, not yet retired) record
     uint4 pv0 = make_uint4(0u, 0u, 0u, 0u), pv1 = pv0;
-    uint32_t p_i = 0, p_bk = 0, p_uk = 0, p_fs = 0, p_bucket = 0;
+    uint32_t p_i = 0, p_bk = 0, p_uk = 0, p_fs = 0, p_bucket = 0, p_bad = 0;
     uint32_t p_flags = 0;                       // bit0 live, bit1 barcode present, bit2 probe issued, bit3 UMI present
     bool have_pending = false;
 
     for (;; base += step) {
         const bool more = base < n;             // warp-uniform
         // ---- probe stage for record k ----
-        uint32_t c_i = base + lane, c_bk = 0, c_uk = 0, c_fs = 0, c_flags = 0, c_bucket = 0;
+        uint32_t c_i = base + lane, c_bk = 0, c_uk = 0, c_fs = 0, c_flags = 0, c_bucket = 0, c_bad = 0;
         uint4 cv0 = make_uint4(0u, 0u, 0u, 0u), cv1 = cv0;
         if (more) {
             const uint4 ca = a, cb = b;
@@ -435,11 +444,11 @@ __global__ void __launch_bounds__(PCL_BLOCK << (kBits - PCL_HCACHE_BITS)) k_coun
             if (c_i < n) {
                 if (rd.max_len && L > rd.max_len) L = rd.max_len;
                 const uint32_t w[8] = {ca.x, ca.y, ca.z, ca.w, cb.x, cb.y, cb.z, cb.w};
-                bool bbad, ubad;
-                if (kSpec == PCL_FAST_SPEC_B0_U16x12) pcl_fast_extract_aligned<0, 4, 3>(w, rev, &c_bk, &bbad, &c_uk, &ubad);
-                else if (kSpec == PCL_FAST_SPEC_B0) pcl_fast_extract_aligned<0, 0, 0>(w, rev, &c_bk, &bbad, &c_uk, &ubad);
-                else if (kSpec == PCL_FAST_SPEC_B8) pcl_fast_extract_aligned<2, 0, 0>(w, rev, &c_bk, &bbad, &c_uk, &ubad);
-                else pcl_fast_extract(f, w, rev, &c_bk, &bbad, &c_uk, &ubad);
+                bool ubad;
+                if (kSpec == PCL_FAST_SPEC_B0_U16x12) pcl_fast_extract_aligned<0, 4, 3>(w, rev, &c_bk, &c_bad, &c_uk, &ubad, false);
+                else if (kSpec == PCL_FAST_SPEC_B0) pcl_fast_extract_aligned<0, 0, 0>(w, rev, &c_bk, &c_bad, &c_uk, &ubad, false);
+                else if (kSpec == PCL_FAST_SPEC_B8) pcl_fast_extract_aligned<2, 0, 0>(w, rev, &c_bk, &c_bad, &c_uk, &ubad, false);
+                else pcl_fast_extract(f, w, rev, &c_bk, &c_bad, &c_uk, &ubad, false);
                 c_fs = PCL_SPLIT_OK | absent_rest;
                 c_flags = 1u;
                 if (f.has_tail_target) {
@@ -454,7 +463,7 @@ __global__ void __launch_bounds__(PCL_BLOCK << (kBits - PCL_HCACHE_BITS)) k_coun
                 if (umi_end <= L) c_flags |= 8u;
                 if (bc_end <= L) {
                     c_flags |= 2u;
-                    if (!bbad && len_ok && c_bk != empty) {
+                    if (!c_bad && len_ok && c_bk != empty) {
                         c_flags |= 4u;
                         c_bucket = pcl_hash32_bucket(c_bk, nb);
                         cv0 = __ldg(reinterpret_cast<const uint4 *>(keys + (uint64_t)c_bucket * 8));
@@ -462,12 +471,14 @@ __global__ void __launch_bounds__(PCL_BLOCK << (kBits - PCL_HCACHE_BITS)) k_coun
                     }
                 } else {
                     c_bk = 0;
+                    c_bad = 0;
                 }
             }
         }
         // ---- retire stage for record k-1 ----
         if (have_pending) {
             bool miss = false;
+            unsigned long long ent = 0;
             if (p_flags & 1u) {
                 uint32_t code = PCL_BC_ABSENT;
                 if (p_flags & 2u) {
@@ -499,17 +510,18 @@ __global__ void __launch_bounds__(PCL_BLOCK << (kBits - PCL_HCACHE_BITS)) k_coun
                     } else {
                         code = PCL_BC_NO_MATCH;
                         ++n_mis;
-                        miss = true;
+                        miss = true;                                    // a barcode with non-ACGT bytes: k_filter looks at the record
+                        ent = pcl_wl_pack(p_i, f.bc_start, f.bc_len, 0u, p_bad ? 1u : 0u, PCL_WL_REPACK_POS);
                     }
                 }
                 pcl_st_stream(bc_out + p_i, p_bk);
                 if (f.umi_len) pcl_st_stream(umi_out + p_i, (p_flags & 8u) ? p_uk : PCL_KEY_ABSENT32);
                 pcl_st_stream(p.fstatus + p_i, (uint16_t)(p_fs | (code << 4)));
             }
-            pcl_wl_push(p, wl, miss, pcl_wl_entry(p_i, f.bc_start, f.bc_len, 0u), lane);
+            pcl_wl_push(p, wl, miss, ent, p_bk, lane);
         }
         if (!more) break;
-        pv0 = cv0; pv1 = cv1; p_i = c_i; p_bk = c_bk; p_uk = c_uk; p_fs = c_fs; p_flags = c_flags; p_bucket = c_bucket;
+        pv0 = cv0; pv1 = cv1; p_i = c_i; p_bk = c_bk; p_uk = c_uk; p_fs = c_fs; p_flags = c_flags; p_bucket = c_bucket; p_bad = c_bad;
         have_pending = true;
     }
     pcl_wl_finish(p, wl, lane);
@@ -520,6 +532,187 @@ __global__ void __launch_bounds__(PCL_BLOCK << (kBits - PCL_HCACHE_BITS)) k_coun
     if (lane == 0) {
         if (n_total) atomicAdd(tab.total, n_total);
         if (n_mis) atomicAdd(tab.mismatch, n_mis);
+    }
+    __syncthreads();
+    for (uint32_t h = threadIdx.x; h < (1u << kBits); h += blockDim.x) {
+        const uint32_t id = ck[h], c = cc[h];
+        if (id != PCL_HEMPTY && c) atomicAdd(&tab.counts[id & 0x1FFFFFFFu], c);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_count_spec: pass 1 for the word-aligned geometries of the BASELINE configurations (PCL_FAST_SPEC_*: a 16-base
+// barcode at byte 0 or 8, optionally a 12-base UMI at byte 16; no target in the read), strand known at compile time.
+//
+// The kernel is bound by instruction issue, not by HBM, so it is written for few instructions per record: straight-line
+// code over TWO records per thread and iteration (lanes take records base + lane and base + 32 + lane: every load and
+// store of a warp is one contiguous run), no software pipeline -- the 32 resident warps of the 1024-thread CTA hide the
+// two load latencies of an iteration (records, then buckets) --, loads of out-of-range lanes clamped to the last record
+// instead of branched around, 32-bit counters, one worklist reservation for both records.
+// Same results as k_count_fast on the same layouts (tests run both: PCL_OLD_FAST=1).
+// ------------------------------------------------------------------------------------------------
+template <bool kRev>
+__device__ __forceinline__ void pcl_spec_codes4(uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3, uint32_t *codes, uint32_t *bad) {
+    uint32_t d0, d1, d2, d3;
+    const uint32_t fold = kRev ? 0xDFDFDFDFu : 0xFFFFFFFFu;          // precellar::utils::rev_compl accepts lower case
+    const uint32_t c0 = pcl_word_codes(w0 & fold, &d0), c1 = pcl_word_codes(w1 & fold, &d1);
+    const uint32_t c2 = pcl_word_codes(w2 & fold, &d2), c3 = pcl_word_codes(w3 & fold, &d3);
+    *codes = c0 | (c1 << 8) | (c2 << 16) | (c3 << 24);
+    *bad = d0 | d1 | d2 | d3;
+}
+
+// both records' misses in one reservation step (see pcl_wl_push)
+template <typename P>
+__device__ __forceinline__ void pcl_wl_push2(const P &p, WlCursor &cur, bool m0, uint32_t hi0, uint32_t rec0, uint32_t key0, bool m1,
+                                             uint32_t hi1, uint32_t rec1, uint32_t key1, uint32_t lane) {
+    const uint32_t b0 = __ballot_sync(0xFFFFFFFFu, m0), b1 = __ballot_sync(0xFFFFFFFFu, m1);
+    if (!(b0 | b1)) return;
+    const uint32_t lt = (1u << lane) - 1u;
+    const uint32_t n0 = __popc(b0), need = n0 + __popc(b1);
+    const uint32_t r0 = __popc(b0 & lt), r1 = n0 + __popc(b1 & lt);
+    const unsigned long long rem = cur.end - cur.pos;   // warp-uniform
+    unsigned long long at0 = cur.pos + r0, at1 = cur.pos + r1;
+    if (need > rem) {
+        unsigned long long b = 0;
+        if (lane == 0) b = atomicAdd(p.wl_count, (unsigned long long)PCL_WL_BATCH);
+        b = __shfl_sync(0xFFFFFFFFu, b, 0);
+        if (r0 >= rem) at0 = b + r0 - rem;
+        if (r1 >= rem) at1 = b + r1 - rem;
+        cur.pos = b + need - rem;
+        cur.end = b + PCL_WL_BATCH;
+    } else {
+        cur.pos += need;
+    }
+    if (m0) { p.worklist[at0] = ((unsigned long long)hi0 << 32) | rec0; p.wl_key[at0] = key0; }
+    if (m1) { p.worklist[at1] = ((unsigned long long)hi1 << 32) | rec1; p.wl_key[at1] = key1; }
+}
+
+template <int kSpec, bool kRev, bool kPrefetch = true>
+__global__ void __launch_bounds__(1024) k_count_spec(const __grid_constant__ CountParams p) {
+    constexpr int kBits = 14;
+    constexpr bool kWide = kSpec != PCL_FAST_SPEC_B0;                    // 32-byte record rows (16 for the bare index read)
+    constexpr bool kUmi = kSpec == PCL_FAST_SPEC_B0_U16x12;
+    constexpr uint32_t kBcStart = kSpec == PCL_FAST_SPEC_B8 ? 8u : 0u, kBcEnd = kBcStart + 16u, kUmiEnd = 28u;
+    constexpr uint32_t kAhead = 1u;                                      // prefetch distance in iterations
+    extern __shared__ uint32_t pcl_hist_smem[];
+    uint32_t *ck = pcl_hist_smem, *cc = pcl_hist_smem + (1u << kBits);
+    for (uint32_t h = threadIdx.x; h < (1u << kBits); h += blockDim.x) { ck[h] = PCL_HEMPTY; cc[h] = 0; }
+    __syncthreads();
+
+    const DTable &tab = p.tab[0];
+    const uint32_t *keys = reinterpret_cast<const uint32_t *>(tab.keys);
+    const uint32_t empty = (uint32_t)tab.empty, nb = tab.n_buckets;
+    const bool len_ok = tab.mode == PCL_TAB_K32_L16;                     // only a table of 16-mers can hold a 16-base barcode
+    const uint32_t n = (uint32_t)p.n, last = n - 1u;                     // n >= 1
+    const uint32_t lcap = p.rd.max_len ? p.rd.max_len : 0xFFFFFFFFu;     // FastqReader::read_record truncation (read.rs:98-103)
+    const uint32_t lane = threadIdx.x & 31u;
+    // Grid-stride over 64-record slices: all warps together stream one region of the planes.  (A blocked partition -- every
+    // warp its own contiguous range, so that the worklist comes out in record order -- was measured: pass 2 did not get
+    // faster and this kernel lost 3 %.)
+    const uint32_t first = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * 64u, end = n;
+    const uint32_t step = gridDim.x * blockDim.x * 2u;
+    const uint32_t absent_rest = (PCL_BC_ABSENT << 7) | (PCL_BC_ABSENT << 10) | (PCL_BC_ABSENT << 13);
+    // high words of the two kinds of worklist entry: clean barcode / barcode with non-ACGT bytes (k_filter re-derives)
+    const uint32_t ent_hi = (uint32_t)(pcl_wl_pack(0, kBcStart, 16u, 0u, 0u, 0u) >> 32);
+    const uint32_t ent_hi_bad = (uint32_t)(pcl_wl_pack(0, kBcStart, 16u, 0u, 1u, PCL_WL_REPACK_POS) >> 32);
+    uint32_t *bc_out = reinterpret_cast<uint32_t *>(p.bc_key[0]);
+    uint32_t *umi_out = reinterpret_cast<uint32_t *>(p.umi_key[0]);
+    uint32_t n_total = 0, n_mis = 0;
+    WlCursor wl = {0, 0};
+
+    for (uint32_t base = first; base < end; base += step) {
+        uint32_t idx[2], L[2], bk[2], uk[2], bad[2], bucket[2];
+        uint4 v0[2], v1[2];
+        bool live[2], act[2];
+        // ---- records ----
+        uint4 a[2], b[2];
+        if (kPrefetch && base + kAhead * step < end) {
+            // rows a few iterations ahead travel from DRAM to L2 while this one is processed (no registers held)
+            const uint8_t *nx = p.seq + (uint64_t)(base + kAhead * step + lane) * (kWide ? 32u : 16u);
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(nx));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(nx + 32u * (kWide ? 32u : 16u)));
+        }
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            idx[r] = base + 32u * r + lane;
+            live[r] = idx[r] < n;
+            const uint32_t ld = live[r] ? idx[r] : last;                 // out-of-range lanes re-read the last record
+            const uint4 *rp = reinterpret_cast<const uint4 *>(p.seq + (uint64_t)ld * (kWide ? 32u : 16u));
+            a[r] = pcl_ld_stream(rp);
+            if (kWide) b[r] = pcl_ld_stream(rp + 1);
+            L[r] = __ldcs(p.len + ld);
+        }
+        // ---- extraction, probe issue ----
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            uint32_t codes;
+            if (kSpec == PCL_FAST_SPEC_B8) pcl_spec_codes4<kRev>(a[r].z, a[r].w, b[r].x, b[r].y, &codes, &bad[r]);
+            else pcl_spec_codes4<kRev>(a[r].x, a[r].y, a[r].z, a[r].w, &codes, &bad[r]);
+            bk[r] = pcl_field32_to_key(codes, 16u, kRev, 0u);
+            if (kUmi) {
+                uint32_t d4, d5, d6;
+                const uint32_t fold = kRev ? 0xDFDFDFDFu : 0xFFFFFFFFu;
+                const uint32_t uc = pcl_word_codes(b[r].x & fold, &d4) | (pcl_word_codes(b[r].y & fold, &d5) << 8) |
+                                    (pcl_word_codes(b[r].z & fold, &d6) << 16);
+                uk[r] = (d4 | d5 | d6) ? 0u : (pcl_field32_to_key(uc, 12u, kRev, 0u) | (1u << 24));
+            }
+            L[r] = min(L[r], lcap);
+            act[r] = (L[r] >= kBcEnd) & (bad[r] == 0u) & len_ok & (bk[r] != empty);
+            bucket[r] = pcl_hash32_bucket(bk[r], nb);
+            if (act[r]) {
+                v0[r] = __ldg(reinterpret_cast<const uint4 *>(keys + (uint64_t)bucket[r] * 8));
+                v1[r] = __ldg(reinterpret_cast<const uint4 *>(keys + (uint64_t)bucket[r] * 8 + 4));
+            }
+        }
+        // ---- retire ----
+        bool miss[2];
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            const bool present = live[r] & (L[r] >= kBcEnd);
+            uint32_t slot = 0xFFFFFFFFu;
+            if (act[r]) {
+                const uint32_t k = bk[r];
+                uint32_t j = 8;
+                j = (v1[r].w == k) ? 7u : j;
+                j = (v1[r].z == k) ? 6u : j;
+                j = (v1[r].y == k) ? 5u : j;
+                j = (v1[r].x == k) ? 4u : j;
+                j = (v0[r].w == k) ? 3u : j;
+                j = (v0[r].z == k) ? 2u : j;
+                j = (v0[r].y == k) ? 1u : j;
+                j = (v0[r].x == k) ? 0u : j;
+                if (j < 8u) slot = bucket[r] * 8u + j;
+                else if (v1[r].w != empty) {                              // full bucket: the chain continues (rare)
+                    uint32_t bb = bucket[r];
+                    bool full = true;
+                    while (slot == 0xFFFFFFFFu && full) {
+                        bb = (bb + 1u == nb) ? 0u : bb + 1u;
+                        slot = pcl_bucket32(keys, bb, k, empty, &full);
+                    }
+                }
+            }
+            const bool hit = present & (slot != 0xFFFFFFFFu);
+            if (hit) pcl_hist_add2<kBits>(ck, cc, slot, tab.counts, idx[r], p.hist_admit_mask, p.hist_two_choice != 0);
+            miss[r] = present & !hit;
+            n_total += present;                                          // WhitelistBuilder::add (barcode.rs:410-426)
+            n_mis += miss[r];
+            if (live[r]) {
+                const uint32_t code = !present ? PCL_BC_ABSENT : (hit ? PCL_BC_EXACT : PCL_BC_NO_MATCH);
+                pcl_st_stream(bc_out + idx[r], present ? bk[r] : 0u);
+                if (kUmi) pcl_st_stream(umi_out + idx[r], L[r] >= kUmiEnd ? uk[r] : PCL_KEY_ABSENT32);
+                pcl_st_stream(p.fstatus + idx[r], (uint16_t)(PCL_SPLIT_OK | absent_rest | (code << 4)));
+            }
+        }
+        pcl_wl_push2(p, wl, miss[0], bad[0] ? ent_hi_bad : ent_hi, idx[0], bk[0], miss[1], bad[1] ? ent_hi_bad : ent_hi, idx[1], bk[1], lane);
+    }
+    pcl_wl_finish(p, wl, lane);
+    for (int o = 16; o > 0; o >>= 1) {
+        n_total += __shfl_xor_sync(0xFFFFFFFFu, n_total, o);
+        n_mis += __shfl_xor_sync(0xFFFFFFFFu, n_mis, o);
+    }
+    if (lane == 0) {
+        if (n_total) atomicAdd(tab.total, (unsigned long long)n_total);
+        if (n_mis) atomicAdd(tab.mismatch, (unsigned long long)n_mis);
     }
     __syncthreads();
     for (uint32_t h = threadIdx.x; h < (1u << kBits); h += blockDim.x) {
@@ -606,9 +799,9 @@ __global__ void __launch_bounds__(PCL_BLOCK) k_enum_all(const __grid_constant__ 
                 } else {
                     c = p.bcoord[j][i];
                 }
-                entry = pcl_wl_entry(i, c >> 16, c & 0xFFFFu, j);
+                entry = pcl_wl_pack(i, c >> 16, c & 0xFFFFu, j, 0u, 0u);      // k_correct re-derives the key from the record
             }
-            pcl_wl_push(p, wl, m, entry, lane);
+            pcl_wl_push(p, wl, m, entry, 0u, lane);
         }
     }
     pcl_wl_finish(p, wl, lane);
@@ -620,8 +813,8 @@ __device__ __forceinline__ void pcl_fstatus_or(uint16_t *fstatus, uint64_t i, ui
     atomicOr(w, (a & 2) ? bits << 16 : bits);
 }
 
-// kFast32: every table of this read is a 32-bit table and no expected-error test is requested.
-template <bool kFast32>
+// Generic pass 2 (64-bit tables, or a finite max_expected_errors): thread per worklist entry, the barcode is re-packed
+// from the record bytes, 3 * L (4 at an N) neighbour probes in (pos, ACGT) order.
 __global__ void __launch_bounds__(PCL_BLOCK) k_correct(const __grid_constant__ CorrectParams p) {
     const DRead &rd = p.rd;
     const unsigned long long n_work = *p.wl_count;
@@ -630,26 +823,179 @@ __global__ void __launch_bounds__(PCL_BLOCK) k_correct(const __grid_constant__ C
     for (uint64_t w = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; w < n_work; w += step) {
         const unsigned long long ent = p.worklist[w];
         if (ent == PCL_WL_HOLE) continue;
-        const uint64_t rec_i = ent & 0xFFFFFFFFull;
-        const uint32_t start = (uint32_t)(ent >> 32) & 0xFFFFu, blen = (uint32_t)(ent >> 48) & 0xFFu,
-                       j = (uint32_t)(ent >> 56);
+        const uint64_t rec_i = PCL_WL_REC(ent);
+        const uint32_t start = PCL_WL_START(ent), blen = PCL_WL_LEN(ent), j = PCL_WL_J(ent);
         const uint8_t *rec = p.seq + rec_i * (uint64_t)rd.stride;
         const uint8_t *ql = p.qual + rec_i * (uint64_t)rd.qstride - rd.qoff;     // record-relative indexing inside the window
         uint32_t ninv, ipos;
         const uint64_t key = pcl_pack_key(rec, start, blen, rev, &ninv, &ipos);
-        uint32_t code;
-        if (kFast32) {
-            uint32_t out32 = 0;
-            code = pcl_correct_one32(p.tab[j], (uint32_t)key, blen, ninv, ipos, ql, start, rev, p.threshold, p.lut_cap, &out32);
-            if (code == PCL_BC_CORRECTED) reinterpret_cast<uint32_t *>(p.bc_key[j])[rec_i] = out32;
-        } else {
-            const bool is_exact = PCL_BC_CODE((uint32_t)p.fstatus[rec_i], j) == PCL_BC_EXACT;
-            uint64_t out_key = 0;
-            code = pcl_correct_one(p.tab[j], key, blen, ninv, ipos, ql, start, rev, is_exact, p.threshold,
-                                   p.max_expected_errors, p.check_ee != 0, p.lut_cap, p.lut_raw, &out_key);
-            if (code == PCL_BC_CORRECTED) pcl_store_key(p.bc_key[j], p.bc_key_bytes[j], rec_i, out_key);
-        }
+        const bool is_exact = PCL_BC_CODE((uint32_t)p.fstatus[rec_i], j) == PCL_BC_EXACT;
+        uint64_t out_key = 0;
+        const uint32_t code = pcl_correct_one(p.tab[j], key, blen, ninv, ipos, ql, start, rev, is_exact, p.threshold,
+                                              p.max_expected_errors, p.check_ee != 0, p.lut_cap, p.lut_raw, &out_key);
+        if (code == PCL_BC_CORRECTED) pcl_store_key(p.bc_key[j], p.bc_key_bytes[j], rec_i, out_key);
         if (code != PCL_BC_EXACT && code != PCL_BC_NO_MATCH) pcl_fstatus_or(p.fstatus, rec_i, code << (4 + 3 * j));
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Pass 2 for reads whose tables are all 32-bit, in two kernels.
+//   k_filter  (launched by pcl_count right behind the count kernel: it needs no counts, so on several GPUs it runs
+//             while the all-reduce of the counts is in flight): worklist entry (record, packed key, N position) ->
+//             64-bit mask of the 1-Hamming neighbours that are whitelist members.  Touches neither the records nor
+//             the qualities: 12 bytes in, 8 bytes out per miss, plus the table lookups (bitmap words from L2, the
+//             neighbourhood buckets of the partial keys that exist).
+//   k_resolve (pcl_correct, after the all-reduce): candidates -> main-table slot -> global count -> fp64 posterior
+//             (likelihood1 / update_best_option / correct_barcode, barcode.rs:160-184,311-358).
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned long long pcl_ld_stream64(const unsigned long long *p) { return __ldcs(p); }
+
+// k_filter works in two phases per warp and 32 entries, because under divergence every lane of a warp pays for what
+// any lane does and only ~1.5 of the 4 neighbourhood tables of an entry are worth a look:
+//   A. lane per entry: decode (re-derive a barcode with non-ACGT bytes from its record), four bitmap words, and the
+//      (entry, table) pairs that survive go into a queue in shared memory;
+//   B. lane per queued pair, all lanes busy: one bucket of the pair's table; a chain that continues in the next bucket
+//      is queued again; results are OR-ed into the entry's mask in shared memory.
+#define PCL_FQ_CAP 192u      // 128 pairs of a round + room for continued chains
+struct FilterQueue {
+    uint32_t key[PCL_FQ_CAP], meta[PCL_FQ_CAP], bucket[PCL_FQ_CAP];
+    unsigned long long res[32];
+    uint32_t tail;
+};
+// meta: lane | q << 5 | len << 7 | has_n << 12 | n_p2 << 13 | j << 16 | continued << 18
+__global__ void __launch_bounds__(PCL_BLOCK) k_filter(const __grid_constant__ CorrectParams p) {
+    __shared__ FilterQueue fq[PCL_BLOCK / 32];
+    FilterQueue &Q = fq[threadIdx.x >> 5];
+    const unsigned long long n_work = *p.wl_count;
+    const DRead &rd = p.rd;
+    const bool rev = rd.is_reverse != 0;
+    const uint32_t lane = threadIdx.x & 31u, lt = (1u << lane) - 1u;
+    const uint64_t step = (uint64_t)gridDim.x * blockDim.x;
+    // wb is warp-uniform: every lane runs the same number of iterations (ballots and __syncwarp below)
+    for (uint64_t wb = (uint64_t)blockIdx.x * blockDim.x + (threadIdx.x & ~31u); wb < n_work; wb += step) {
+        const uint64_t w = wb + lane;
+        const bool in = w < n_work;
+        const unsigned long long ent = in ? pcl_ld_stream64(p.worklist + w) : PCL_WL_HOLE;
+        uint32_t key32 = in ? __ldcs(p.wl_key + w) : 0u;
+        unsigned long long pend = 0;
+        uint32_t live = 0, meta = 0;
+        if (ent != PCL_WL_HOLE) {
+            const uint32_t len = PCL_WL_LEN(ent), j = PCL_WL_J(ent);
+            uint32_t ninv = PCL_WL_NINV(ent), ipos = PCL_WL_IPOS(ent);
+            if (PCL_WL_IS_REPACK(ent)) {
+                // a FastLayout barcode with non-ACGT bytes: which bases, and the key with those bases read as 0
+                const uint64_t rec_i = PCL_WL_REC(ent);
+                const uint8_t *rec = p.seq + rec_i * (uint64_t)rd.stride;
+                uint32_t k2;
+                if (rd.fast.spec != PCL_FAST_SPEC_NONE) {                  // 16 bases in four aligned words (at byte 0 or 8)
+                    const uint2 lo = __ldg(reinterpret_cast<const uint2 *>(rec + rd.fast.bc_start));
+                    const uint2 hi = __ldg(reinterpret_cast<const uint2 *>(rec + rd.fast.bc_start) + 1);
+                    k2 = pcl_repack16(lo.x, lo.y, hi.x, hi.y, rev, &ninv, &ipos);
+                } else {
+                    const uint4 *r4 = reinterpret_cast<const uint4 *>(rec);
+                    const uint4 a = __ldg(r4), b = rd.stride == 32u ? __ldg(r4 + 1) : make_uint4(0u, 0u, 0u, 0u);
+                    const uint32_t wds[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+                    k2 = pcl_fast_repack(rd.fast, wds, rev, &ninv, &ipos);
+                }
+                if (k2 != key32) {                                  // an invalid byte other than 'N' left a non-zero code behind
+                    key32 = k2;
+                    p.wl_key[w] = k2;
+                    reinterpret_cast<uint32_t *>(p.bc_key[0])[rec_i] = k2;
+                }
+            }
+            const DTable &t = p.tab[j];
+            if (!pcl_filter_hopeless(t, len, ninv)) {
+                if (!t.nkeys[0]) pend = pcl_filter_direct(t, key32, len, ninv, ipos);
+                else {
+#pragma unroll
+                    for (uint32_t q = 0; q < 4u; ++q) live |= (uint32_t)pcl_filter_live(t, key32, len, ninv, ipos, q) << q;   // four independent loads
+                    const uint32_t n_p2 = (2u * (len - 1u - (ninv == 1u ? ipos : 0u))) & 7u;
+                    meta = lane | (len << 7) | ((ninv == 1u ? 1u : 0u) << 12) | (n_p2 << 13) | (j << 16);
+                }
+            }
+        }
+        // ---- queue the live (entry, table) pairs, table-major ----
+        Q.res[lane] = pend;
+        uint32_t at = 0, total = 0;
+#pragma unroll
+        for (uint32_t q = 0; q < 4u; ++q) {
+            const uint32_t bal = __ballot_sync(0xFFFFFFFFu, (live >> q) & 1u);
+            if ((live >> q) & 1u) {
+                at = total + __popc(bal & lt);
+                Q.key[at] = key32; Q.meta[at] = meta | (q << 5); Q.bucket[at] = 0;
+            }
+            total += __popc(bal);
+        }
+        if (lane == 0) Q.tail = total;
+        __syncwarp();
+        // ---- one bucket per lane and round ----
+        for (uint32_t head = 0; head < total;) {
+            const uint32_t i = head + lane, stop = min(head + 32u, total);     // pairs queued during this round wait for the next one
+            if (i < stop) {
+                const uint32_t k = Q.key[i], m = Q.meta[i];
+                const uint32_t q = (m >> 5) & 3u, len = (m >> 7) & 31u;
+                const DTable &t = p.tab[(m >> 16) & 3u];
+                const uint32_t b = (m >> 18) & 1u ? Q.bucket[i] : pcl_hash32_bucket(k & ~(0xFFu << (8u * q)), t.n_buckets);
+                bool full;
+                const uint32_t sub = pcl_filter_bucket(t.nkeys[q], b, k, q, (uint32_t)t.empty, (m >> 12) & 1u, (m >> 13) & 7u, &full);
+                if (sub) atomicOr(&Q.res[m & 31u], pcl_filter_place(sub, len, q));
+                if (full) {                                          // rare: the chain continues in the next bucket
+                    const uint32_t nxt = atomicAdd(&Q.tail, 1u);
+                    const uint32_t b1 = (b + 1u == t.n_buckets) ? 0u : b + 1u;
+                    if (nxt < PCL_FQ_CAP) { Q.key[nxt] = k; Q.meta[nxt] = m | (1u << 18); Q.bucket[nxt] = b1; }
+                    else {                                           // queue full (never seen): finish the chain here
+                        uint32_t bb = b1, s2 = 0;
+                        bool f2 = true;
+                        while (f2) {
+                            s2 |= pcl_filter_bucket(t.nkeys[q], bb, k, q, (uint32_t)t.empty, (m >> 12) & 1u, (m >> 13) & 7u, &f2);
+                            bb = (bb + 1u == t.n_buckets) ? 0u : bb + 1u;
+                        }
+                        if (s2) atomicOr(&Q.res[m & 31u], pcl_filter_place(s2, len, q));
+                    }
+                }
+            }
+            __syncwarp();
+            head = stop;
+            total = min(Q.tail, PCL_FQ_CAP);
+        }
+        __syncwarp();
+        if (in) __stcs(p.wl_cand + w, Q.res[lane]);
+        __syncwarp();
+    }
+}
+
+__global__ void __launch_bounds__(PCL_BLOCK) k_resolve(const __grid_constant__ CorrectParams p) {
+    const DRead &rd = p.rd;
+    const unsigned long long n_work = *p.wl_count;
+    const uint64_t step = (uint64_t)gridDim.x * blockDim.x;
+    const bool rev = rd.is_reverse != 0;
+    for (uint64_t w = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; w < n_work; w += step) {
+        const unsigned long long cand = pcl_ld_stream64(p.wl_cand + w);
+        if (!cand) continue;                                                      // holes and barcodes without a neighbour: NoMatch stays
+        const unsigned long long ent = pcl_ld_stream64(p.worklist + w);
+        const uint32_t key32 = __ldcs(p.wl_key + w);
+        const uint64_t rec_i = PCL_WL_REC(ent);
+        const uint32_t start = PCL_WL_START(ent), blen = PCL_WL_LEN(ent), j = PCL_WL_J(ent);
+        const uint8_t *ql = p.qual + rec_i * (uint64_t)rd.qstride - rd.qoff;     // record-relative indexing inside the window
+        uint32_t out32 = 0;
+        const uint32_t code = pcl_resolve32(p.tab[j], key32, blen, cand, ql, start, rev, p.threshold, p.lut_cap, &out32);
+        if (code == PCL_BC_CORRECTED) reinterpret_cast<uint32_t *>(p.bc_key[j])[rec_i] = out32;
+        if (code != PCL_BC_NO_MATCH) pcl_fstatus_or(p.fstatus, rec_i, code << (4 + 3 * j));
+    }
+}
+
+// pcl_whitelist_load: the bitmaps of the partial keys (DTable::nbits) from the main key table
+__global__ void __launch_bounds__(PCL_BLOCK) k_build_nbits(const uint32_t *__restrict__ keys, uint64_t n_slots, uint32_t empty,
+                                                          uint32_t *b0, uint32_t *b1, uint32_t *b2, uint32_t *b3) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_slots; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t k = keys[i];
+        if (k == empty) continue;
+        uint32_t *bm[4] = {b0, b1, b2, b3};
+#pragma unroll
+        for (uint32_t q = 0; q < 4u; ++q) {
+            const uint32_t idx = pcl_partial_index(k, q);
+            atomicOr(bm[q] + (idx >> 5), 1u << (idx & 31u));
+        }
     }
 }
 

@@ -75,6 +75,7 @@ struct Table {
     uint32_t *d_counts = nullptr;
     uint32_t *d_index_to_slot = nullptr;
     uint32_t *d_nkeys[4] = {nullptr, nullptr, nullptr, nullptr};
+    uint32_t *d_nbits = nullptr;               // 4 x PCL_NBITS_WORDS: bitmaps of the partial keys (DTable::nbits)
     unsigned long long *d_scalars = nullptr;   // [0] total, [1] mismatch
 };
 
@@ -113,6 +114,7 @@ struct pcl_ctx {
     // nccl
     NcclComm comm = nullptr;
     int nranks = 1, rank = 0;
+    bool reduced = false;         // counts hold the sum over ranks: pcl_count / a second all-reduce need pcl_counts_reset first
     // instrumentation
     bool profile = false;
     std::vector<EvPair> evs;
@@ -120,13 +122,16 @@ struct pcl_ctx {
     uint64_t prof_n[PCL_K_MAX] = {0};
     uint64_t launches = 0;
     int sm_count = 148;
-    int occ[12] = {1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1};   // resident CTAs per SM of each kernel (see OCC_*)
+    int occ[16] = {1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1};   // resident CTAs per SM of each kernel (see OCC_*)
     int fast_bits = 14, fast_waves = 1;
     uint32_t hist_admit_mask = 7, hist_two_choice = 1;
     bool no_fast_spec = false;    // PCL_NO_FAST_SPEC=1: the mask-driven instance of k_count_fast for every FastLayout
+    bool no_prefetch = false;     // PCL_NO_PREFETCH=1: k_count_spec (v3 forward instance) without the L2 prefetch of the next rows (experiments)
+    bool old_fast = false;        // PCL_OLD_FAST=1: the software-pipelined k_count_fast instances instead of k_count_spec
     bool no_plan = false;         // PCL_NO_PLAN=1: AnchorPlan layouts go through the interpreter kernels (tests compare both)
     bool force_generic = false;   // PCL_FORCE_GENERIC=1: only the generic kernels (tests compare both paths)
     bool no_neighbour_tables = false;   // PCL_NO_NEIGHBOUR_TABLES=1: 3*L direct probes instead of the 4 neighbourhood tables
+    bool no_nbits = false;              // PCL_NO_NBITS=1: no partial-key bitmaps in front of the neighbourhood tables
 };
 
 struct ReadBuf {
@@ -140,6 +145,9 @@ struct ReadBuf {
     uint32_t *ucoord[PCL_MAX_UMI_PER_READ] = {nullptr};
     unsigned long long *worklist = nullptr;
     unsigned long long *wl_count = nullptr;
+    uint32_t *wl_key = nullptr;               // reads whose tables are all 32-bit: packed key and candidate mask per entry
+    unsigned long long *wl_cand = nullptr;
+    bool filtered = false;                    // k_filter has run on the current worklist
     uint8_t *seq_stage = nullptr;             // pcl_chunk_upload_compact: the rows as uploaded, before k_repack_rows
     bool filled = false;
     // device-side text parse (pcl_text_*): name hashes and the small result words of this chunk's parse
@@ -203,7 +211,18 @@ void prof_end(pcl_ctx *ctx, cudaStream_t s) {
     cudaEventRecord(ctx->evs.back().b, s);
 }
 
-enum { OCC_COUNT = 0, OCC_COUNT_FAST, OCC_COUNT_LENONLY, OCC_ENUM, OCC_CORRECT_FAST, OCC_CORRECT, OCC_QC, OCC_GATHER, OCC_COUNT_CODES, OCC_COUNT_PLAN };
+enum { OCC_COUNT = 0, OCC_COUNT_FAST, OCC_COUNT_LENONLY, OCC_ENUM, OCC_FILTER, OCC_CORRECT, OCC_QC, OCC_GATHER, OCC_COUNT_CODES, OCC_COUNT_PLAN, OCC_RESOLVE };
+
+// every barcode of read r goes through the 32-bit tables (k_filter / k_resolve)
+bool read_all32(const pcl_ctx *ctx, int r) {
+    const pcl_read_info &inf = ctx->infos[r];
+    if (ctx->force_generic || inf.n_bc == 0) return false;
+    for (int j = 0; j < inf.n_bc; ++j) {
+        const Table &t = ctx->tables[ctx->bc_region[r][j]];
+        if (!t.loaded || t.d.mode == PCL_TAB_K64 || inf.bc_key_bytes[j] != 4) return false;
+    }
+    return true;
+}
 
 int grid_for(const pcl_ctx *ctx, uint64_t n_threads_wanted, int blocks_per_sm) {
     uint64_t blocks = (n_threads_wanted + PCL_BLOCK - 1) / PCL_BLOCK;
@@ -247,6 +266,7 @@ int pcl_ctx_create(pcl_ctx **out, int device) {
     { const char *g = getenv("PCL_NO_PLAN"); ctx->no_plan = g && g[0] == '1'; }
     { const char *g = getenv("PCL_NO_FAST_SPEC"); ctx->no_fast_spec = g && g[0] == '1'; }
     { const char *g = getenv("PCL_NO_NEIGHBOUR_TABLES"); ctx->no_neighbour_tables = g && g[0] == '1'; }
+    { const char *g = getenv("PCL_NO_NBITS"); ctx->no_nbits = g && g[0] == '1'; }
     memset(ctx->descs, 0, sizeof ctx->descs);
     memset(ctx->dreads, 0, sizeof ctx->dreads);
     memset(ctx->infos, 0, sizeof ctx->infos);
@@ -299,11 +319,19 @@ int pcl_ctx_create(pcl_ctx **out, int device) {
             int nb = 1;
             if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, fn, threads, smem) != cudaSuccess || nb < 1) nb = 1;
             ctx->occ[OCC_COUNT_FAST] = nb;
+            const void *spec_fns[6] = {(const void *)k_count_spec<PCL_FAST_SPEC_B0_U16x12, false>, (const void *)k_count_spec<PCL_FAST_SPEC_B0_U16x12, true>,
+                                       (const void *)k_count_spec<PCL_FAST_SPEC_B0, false>, (const void *)k_count_spec<PCL_FAST_SPEC_B0, true>,
+                                       (const void *)k_count_spec<PCL_FAST_SPEC_B8, false>, (const void *)k_count_spec<PCL_FAST_SPEC_B8, true>};
+            for (const void *f : spec_fns) cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 << 14);
+            cudaFuncSetAttribute((const void *)k_count_spec<PCL_FAST_SPEC_B0_U16x12, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 << 14);
+            { const char *g = getenv("PCL_NO_PREFETCH"); ctx->no_prefetch = g && g[0] == '1'; }
+            { const char *g = getenv("PCL_OLD_FAST"); ctx->old_fast = g && g[0] == '1'; }
         }
         ctx->occ[OCC_COUNT_LENONLY] = occ((const void *)k_count_lenonly);
         ctx->occ[OCC_ENUM] = occ((const void *)k_enum_all);
-        ctx->occ[OCC_CORRECT_FAST] = occ((const void *)k_correct<true>);
-        ctx->occ[OCC_CORRECT] = occ((const void *)k_correct<false>);
+        ctx->occ[OCC_FILTER] = occ((const void *)k_filter);
+        ctx->occ[OCC_RESOLVE] = occ((const void *)k_resolve);
+        ctx->occ[OCC_CORRECT] = occ((const void *)k_correct);
         ctx->occ[OCC_QC] = occ((const void *)k_qc);
         ctx->occ[OCC_GATHER] = occ((const void *)k_gather_counts);
     }
@@ -316,6 +344,7 @@ static void table_free(Table &t) {
     if (t.d_counts) cudaFree(t.d_counts);
     if (t.d_index_to_slot) cudaFree(t.d_index_to_slot);
     for (int q = 0; q < 4; ++q) if (t.d_nkeys[q]) cudaFree(t.d_nkeys[q]);
+    if (t.d_nbits) cudaFree(t.d_nbits);
     if (t.d_scalars) cudaFree(t.d_scalars);
     t = Table();
 }
@@ -439,11 +468,21 @@ int pcl_whitelist_load(pcl_ctx *ctx, int region_slot, const uint8_t *bytes, cons
     CU(ctx, cudaMemset(t.d_scalars, 0, 2 * sizeof(unsigned long long)));
     for (int q = 0; q < 4; ++q) {
         t.d.nkeys[q] = nullptr;
+        t.d.nbits[q] = nullptr;
         if (ht.mode != PCL_TAB_K64 && !ctx->no_neighbour_tables) {
             CU(ctx, cudaMalloc(&t.d_nkeys[q], n_slots * sizeof(uint32_t)));
             CU(ctx, cudaMemcpy(t.d_nkeys[q], ht.ntab32[q].data(), n_slots * sizeof(uint32_t), cudaMemcpyHostToDevice));
             t.d.nkeys[q] = t.d_nkeys[q];
         }
+    }
+    if (ht.mode != PCL_TAB_K64 && !ctx->no_neighbour_tables && !ctx->no_nbits) {
+        CU(ctx, cudaMalloc(&t.d_nbits, 4ull * PCL_NBITS_WORDS * sizeof(uint32_t)));
+        CU(ctx, cudaMemsetAsync(t.d_nbits, 0, 4ull * PCL_NBITS_WORDS * sizeof(uint32_t), ctx->stream));
+        k_build_nbits<<<grid_for(ctx, n_slots, 8), PCL_BLOCK, 0, ctx->stream>>>(
+            reinterpret_cast<const uint32_t *>(t.d_keys), n_slots, (uint32_t)ht.empty, t.d_nbits, t.d_nbits + PCL_NBITS_WORDS,
+            t.d_nbits + 2 * PCL_NBITS_WORDS, t.d_nbits + 3 * PCL_NBITS_WORDS);
+        CU(ctx, cudaGetLastError());
+        for (int q = 0; q < 4; ++q) t.d.nbits[q] = t.d_nbits + (uint64_t)q * PCL_NBITS_WORDS;
     }
     t.d.keys = t.d_keys;
     t.d.counts = t.d_counts;
@@ -455,6 +494,9 @@ int pcl_whitelist_load(pcl_ctx *ctx, int region_slot, const uint8_t *bytes, cons
     t.n_entries = m;
     t.n_slots = n_slots;
     t.loaded = true;
+    // the uploads above come from pageable memory and the memsets may be asynchronous: nothing else orders them against
+    // the (non-blocking) chunk streams
+    CU(ctx, cudaDeviceSynchronize());
     return PCL_OK;
 }
 
@@ -517,7 +559,11 @@ int pcl_chunk_create(pcl_ctx *ctx, uint64_t capacity_records, pcl_chunk **out) {
         if (inf.n_bc) {
             uint64_t warps = (uint64_t)ctx->sm_count * 24 * (PCL_BLOCK / 32), by_size = (cap + 31) / 32 + 32;
             if (warps > by_size) warps = by_size;             // a grid never has more warps than the chunk has records / 32
-            A((void **)&b.worklist, (cap + warps * PCL_WL_BATCH) * inf.n_bc * 8);
+            const uint64_t wl_cap = (cap + warps * PCL_WL_BATCH) * inf.n_bc;
+            A((void **)&b.worklist, wl_cap * 8);
+            bool k32 = true;                                  // whitelists may still be loaded later: go by the key widths
+            for (int j = 0; j < inf.n_bc; ++j) k32 = k32 && inf.bc_key_bytes[j] == 4;
+            if (k32) { A((void **)&b.wl_key, wl_cap * 4); A((void **)&b.wl_cand, wl_cap * 8); }
         }
         A((void **)&b.wl_count, 16);
     }
@@ -802,6 +848,41 @@ int pcl_counts_reset(pcl_ctx *ctx) {
     CU(ctx, cudaEventRecord(ctx->ev_reduced, ctx->stream));
     for (pcl_chunk *c : ctx->chunks) CU(ctx, cudaStreamWaitEvent(c->stream, ctx->ev_reduced, 0));
     memset(ctx->qc_reads, 0, sizeof ctx->qc_reads);
+    ctx->reduced = false;
+    return PCL_OK;
+}
+
+// CorrectParams of read r of a chunk (pass 2 and the filter stage of pass 1)
+static void correct_params(pcl_ctx *ctx, pcl_chunk *c, int r, CorrectParams &p) {
+    const pcl_read_info &inf = ctx->infos[r];
+    ReadBuf &b = c->rb[r];
+    memset(&p, 0, sizeof p);
+    p.rd = ctx->dreads[r];
+    for (int j = 0; j < inf.n_bc; ++j) {
+        p.tab[j] = ctx->tables[ctx->bc_region[r][j]].d;
+        p.bc_key[j] = b.bc_key[j]; p.bcoord[j] = b.bcoord[j];
+        p.bc_key_bytes[j] = inf.bc_key_bytes[j]; p.bc_elem[j] = inf.bc_elem[j];
+    }
+    memcpy(p.static_start, inf.static_start, sizeof p.static_start);
+    p.seq = b.seq; p.qual = b.qual; p.len = b.len; p.n = c->n;
+    p.fstatus = b.fstatus;
+    p.worklist = b.worklist; p.wl_key = b.wl_key; p.wl_cand = b.wl_cand; p.wl_count = b.wl_count;
+    p.lut_cap = ctx->d_lut; p.lut_raw = ctx->d_lut + 256;
+}
+
+// worst-case grid of a kernel that walks the worklist (its size lives on the device; idle CTAs exit at once)
+static int worklist_grid(const pcl_ctx *ctx, const pcl_chunk *c, int n_bc, bool all_entries, int occ) {
+    return grid_for(ctx, all_entries ? c->n * n_bc : (c->n * n_bc + 3) / 4 + 4096, occ);
+}
+
+static int launch_filter(pcl_ctx *ctx, pcl_chunk *c, int r) {
+    CorrectParams p;
+    correct_params(ctx, c, r, p);
+    prof_begin(ctx, c->stream, PCL_K_FILTER);
+    k_filter<<<worklist_grid(ctx, c, ctx->infos[r].n_bc, false, ctx->occ[OCC_FILTER]), PCL_BLOCK, 0, c->stream>>>(p);
+    prof_end(ctx, c->stream);
+    CU(ctx, cudaGetLastError());
+    c->rb[r].filtered = true;
     return PCL_OK;
 }
 
@@ -819,6 +900,8 @@ static int check_ready(pcl_ctx *ctx, pcl_chunk *c) {
 int pcl_count(pcl_ctx *ctx, pcl_chunk *c) {
     if (int r = check_ready(ctx, c)) return r;
     if (int r = bind(ctx)) return r;
+    if (ctx->reduced && ctx->nranks > 1)
+        return fail(ctx, PCL_ERR_ARG, "the counts already hold the sum over ranks: call pcl_counts_reset before counting again");
     if (c->n == 0) return PCL_OK;
     // Reads that hold barcodes first: the all-reduce of the counts only has to wait for their kernels (ev_counted), so it
     // runs while the length-only kernels of the insert reads are still going.
@@ -846,6 +929,8 @@ int pcl_count(pcl_ctx *ctx, pcl_chunk *c) {
         p.seq = b.seq; p.len = b.len; p.n = c->n;
         p.fstatus = b.fstatus; p.tcoord = b.tcoord;
         p.worklist = b.worklist; p.wl_count = b.wl_count;
+        p.wl_key = read_all32(ctx, r) ? b.wl_key : nullptr;
+        b.filtered = false;
         p.num_defect = ctx->d_qc + r;
         CU(ctx, cudaMemsetAsync(b.wl_count, 0, sizeof(unsigned long long), c->stream));
         const DRead &d = ctx->dreads[r];
@@ -858,7 +943,33 @@ int pcl_count(pcl_ctx *ctx, pcl_chunk *c) {
         // The generic counting kernels run THREE resident waves rather than one: with first-come cache lines a CTA
         // that lives a third as long lets fewer one-off barcodes occupy lines (measured on the former fast kernel:
         // 2.79 ms at one wave, 2.49 ms at three).  k_count_fast has an admission filter instead and runs one wave.
-        if (fast) {
+        const bool spec = fast && d.fast.spec != PCL_FAST_SPEC_NONE && !d.fast.has_tail_target && !ctx->no_fast_spec && !ctx->old_fast &&
+                          ctx->fast_bits == 14 && p.wl_key;
+        if (spec) {
+            // one 1024-thread CTA per SM (128 KB histogram cache), two records per thread and iteration
+            p.hist_admit_mask = ctx->hist_admit_mask;
+            p.hist_two_choice = ctx->hist_two_choice;
+            const int threads = 1024, smem = 8 << 14;
+            const uint64_t blocks = (c->n + 2 * threads - 1) / (2 * threads);
+            const int grid = (int)std::max<uint64_t>(1, std::min<uint64_t>(blocks, (uint64_t)ctx->sm_count * ctx->fast_waves));
+            const bool rv = d.is_reverse != 0;
+            switch (d.fast.spec) {
+                case PCL_FAST_SPEC_B0_U16x12:
+                    if (rv) k_count_spec<PCL_FAST_SPEC_B0_U16x12, true><<<grid, threads, smem, c->stream>>>(p);
+                    else if (ctx->no_prefetch) k_count_spec<PCL_FAST_SPEC_B0_U16x12, false, false><<<grid, threads, smem, c->stream>>>(p);
+                    else k_count_spec<PCL_FAST_SPEC_B0_U16x12, false><<<grid, threads, smem, c->stream>>>(p);
+                    break;
+                case PCL_FAST_SPEC_B0:
+                    if (rv) k_count_spec<PCL_FAST_SPEC_B0, true><<<grid, threads, smem, c->stream>>>(p);
+                    else k_count_spec<PCL_FAST_SPEC_B0, false><<<grid, threads, smem, c->stream>>>(p);
+                    break;
+                default:
+                    if (rv) k_count_spec<PCL_FAST_SPEC_B8, true><<<grid, threads, smem, c->stream>>>(p);
+                    else k_count_spec<PCL_FAST_SPEC_B8, false><<<grid, threads, smem, c->stream>>>(p);
+                    break;
+            }
+        }
+        else if (fast) {
             p.hist_admit_mask = ctx->hist_admit_mask;
             p.hist_two_choice = ctx->hist_two_choice;
             const int threads = PCL_BLOCK << (ctx->fast_bits - 12), smem = 8 << ctx->fast_bits;
@@ -879,7 +990,14 @@ int pcl_count(pcl_ctx *ctx, pcl_chunk *c) {
         prof_end(ctx, c->stream);
         CU(ctx, cudaGetLastError());
         ctx->qc_reads[r] += c->n;
-        if (oi + 1 == n_with_bc) { CU(ctx, cudaEventRecord(c->ev_counted, c->stream)); c->counted = true; }
+        if (oi + 1 == n_with_bc) {
+            CU(ctx, cudaEventRecord(c->ev_counted, c->stream)); c->counted = true;
+            // The neighbourhood filter of pass 2 needs no counts: it runs here, behind the event the all-reduce waits for,
+            // so on several GPUs the exchange of the counts is hidden under it.
+            for (int k = 0; k < n_with_bc; ++k)
+                if (read_all32(ctx, order[k]) && c->rb[order[k]].wl_key)
+                    if (int rc = launch_filter(ctx, c, order[k])) return rc;
+        }
     }
     return PCL_OK;
 }
@@ -899,6 +1017,7 @@ int pcl_counts_allreduce(pcl_ctx *ctx) {
     }
     if (ctx->nranks > 1) {
         if (!ctx->comm) return fail(ctx, PCL_ERR_NCCL, "communicator not initialised");
+        if (ctx->reduced) return fail(ctx, PCL_ERR_ARG, "the counts were already summed over the ranks (pcl_counts_reset starts a new round)");
         NcclApi &n = nccl();
         n.GroupStart();
         for (Table &t : ctx->tables) {
@@ -910,6 +1029,7 @@ int pcl_counts_allreduce(pcl_ctx *ctx) {
         int r = n.GroupEnd();
         if (r) return fail(ctx, PCL_ERR_NCCL, "ncclGroupEnd: %d", r);
     }
+    ctx->reduced = true;
     // ... and every chunk's later work waits for the reduced counts
     CU(ctx, cudaEventRecord(ctx->ev_reduced, ctx->stream));
     for (pcl_chunk *c : ctx->chunks) CU(ctx, cudaStreamWaitEvent(c->stream, ctx->ev_reduced, 0));
@@ -926,38 +1046,26 @@ int pcl_correct(pcl_ctx *ctx, pcl_chunk *c, double threshold, double max_expecte
         if (inf.n_bc == 0) continue;
         ReadBuf &b = c->rb[r];
         CorrectParams p;
-        memset(&p, 0, sizeof p);
-        p.rd = ctx->dreads[r];
-        for (int j = 0; j < inf.n_bc; ++j) {
-            p.tab[j] = ctx->tables[ctx->bc_region[r][j]].d;
-            p.bc_key[j] = b.bc_key[j]; p.bcoord[j] = b.bcoord[j];
-            p.bc_key_bytes[j] = inf.bc_key_bytes[j]; p.bc_elem[j] = inf.bc_elem[j];
-        }
-        memcpy(p.static_start, inf.static_start, sizeof p.static_start);
-        p.seq = b.seq; p.qual = b.qual; p.len = b.len; p.n = c->n;
-        p.fstatus = b.fstatus;
-        p.worklist = b.worklist; p.wl_count = b.wl_count;
-        p.lut_cap = ctx->d_lut; p.lut_raw = ctx->d_lut + 256;
+        correct_params(ctx, c, r, p);
         p.threshold = threshold; p.max_expected_errors = max_expected_errors; p.check_ee = check_ee;
         if (check_ee) {
+            // the expected-error test precedes the whitelist lookup: every present barcode needs its qualities
             CU(ctx, cudaMemsetAsync(b.wl_count, 0, sizeof(unsigned long long), c->stream));
+            b.filtered = false;
             prof_begin(ctx, c->stream, PCL_K_ENUM);
             k_enum_all<<<grid_for(ctx, c->n, ctx->occ[OCC_ENUM]), PCL_BLOCK, 0, c->stream>>>(p);
             prof_end(ctx, c->stream);
             CU(ctx, cudaGetLastError());
         }
-        // the worklist size lives on the device; size the grid for the worst case and let idle CTAs exit
-        bool all32 = !check_ee && !ctx->force_generic;
-        for (int j = 0; j < inf.n_bc; ++j) {
-            all32 = all32 && ctx->tables[ctx->bc_region[r][j]].d.mode != PCL_TAB_K64;
-            all32 = all32 && inf.bc_key_bytes[j] == 4;
+        const bool all32 = !check_ee && read_all32(ctx, r) && b.wl_key;
+        if (all32) {
+            if (!b.filtered) if (int rc = launch_filter(ctx, c, r)) return rc;
+            prof_begin(ctx, c->stream, PCL_K_CORRECT);
+            k_resolve<<<worklist_grid(ctx, c, inf.n_bc, false, ctx->occ[OCC_RESOLVE]), PCL_BLOCK, 0, c->stream>>>(p);
+        } else {
+            prof_begin(ctx, c->stream, PCL_K_CORRECT);
+            k_correct<<<worklist_grid(ctx, c, inf.n_bc, check_ee, ctx->occ[OCC_CORRECT]), PCL_BLOCK, 0, c->stream>>>(p);
         }
-        // the worklist size lives on the device; size the grid for the worst case and let idle CTAs exit
-        const int grid = grid_for(ctx, check_ee ? c->n * inf.n_bc : (c->n * inf.n_bc + 3) / 4 + 4096,
-                                  ctx->occ[all32 ? OCC_CORRECT_FAST : OCC_CORRECT]);
-        prof_begin(ctx, c->stream, PCL_K_CORRECT);
-        if (all32) k_correct<true><<<grid, PCL_BLOCK, 0, c->stream>>>(p);
-        else k_correct<false><<<grid, PCL_BLOCK, 0, c->stream>>>(p);
         prof_end(ctx, c->stream);
         CU(ctx, cudaGetLastError());
     }

@@ -55,6 +55,7 @@ int emu_run(const pcl_read_desc *reads, int n_reads, int n_regions, const uint8_
     std::vector<std::vector<uint32_t>> counts(n_regions);
     std::vector<unsigned long long> scal(2 * n_regions, 0);
     std::vector<DTable> dt(n_regions);
+    std::vector<std::vector<uint32_t>> nbits(n_regions);
     for (int g = 0; g < n_regions; ++g) {
         int rc = pcl_build_table(wl_bytes[g], wl_offs[g], wl_n[g], &ht[g], &e);
         if (rc != PCL_OK) { snprintf(err, errcap, "%s", e.c_str()); return rc; }
@@ -67,6 +68,19 @@ int emu_run(const pcl_read_desc *reads, int n_reads, int n_regions, const uint8_
         dt[g].n_buckets = (uint32_t)ht[g].n_buckets;
         dt[g].mode = ht[g].mode;
         for (int q = 0; q < 4; ++q) dt[g].nkeys[q] = (use_fast == 2 || ht[g].mode == PCL_TAB_K64) ? nullptr : ht[g].ntab32[q].data();
+        for (int q = 0; q < 4; ++q) dt[g].nbits[q] = nullptr;
+        if (dt[g].nkeys[0] && use_fast != 3) {                 // mirrors k_build_nbits (use_fast == 3: neighbourhood tables without bitmaps)
+            nbits[g].assign(4ull * PCL_NBITS_WORDS, 0u);
+            for (uint64_t i = 0; i < ht[g].n_slots; ++i) {
+                const uint32_t k = ht[g].tab32[i];
+                if (k == (uint32_t)ht[g].empty) continue;
+                for (uint32_t q = 0; q < 4; ++q) {
+                    const uint32_t idx = pcl_partial_index(k, q);
+                    nbits[g][(uint64_t)q * PCL_NBITS_WORDS + (idx >> 5)] |= 1u << (idx & 31u);
+                }
+            }
+            for (int q = 0; q < 4; ++q) dt[g].nbits[q] = nbits[g].data() + (uint64_t)q * PCL_NBITS_WORDS;
+        }
     }
     double lut[512];
     for (int q = 0; q < 256; ++q) {
@@ -80,7 +94,7 @@ int emu_run(const pcl_read_desc *reads, int n_reads, int n_regions, const uint8_
         int rc = pcl_build_read(r, reads[r], &dr[r], &inf[r], bcr[r].data(), &e);
         if (rc != PCL_OK) { snprintf(err, errcap, "%s", e.c_str()); return rc; }
     }
-    struct Work { uint64_t rec; uint32_t start, len, j; };
+    struct Work { unsigned long long ent; uint32_t key; };          // worklist entry (pcl_wl_pack) + 4-byte device key
     std::vector<std::vector<Work>> work(n_reads);
     // ---- pass 1 (mirrors k_count) ----
     for (int r = 0; r < n_reads; ++r) {
@@ -101,12 +115,15 @@ int emu_run(const pcl_read_desc *reads, int n_reads, int n_regions, const uint8_
                 if (rd.max_len && L > rd.max_len) L = rd.max_len;
                 uint32_t w[8] = {0, 0, 0, 0, 0, 0, 0, 0};
                 memcpy(w, io[r].seq + i * (uint64_t)rd.stride, rd.stride);
-                uint32_t bk, uk; bool bbad, ubad;
-                pcl_fast_extract_spec(f, w, rev, &bk, &bbad, &uk, &ubad);
-                {   // the specialised instances must agree with the mask-driven extraction
-                    uint32_t bk2, uk2; bool bb2, ub2;
-                    pcl_fast_extract(f, w, rev, &bk2, &bb2, &uk2, &ub2);
-                    if (bk2 != bk || uk2 != uk || bb2 != bbad || ub2 != ubad) return PCL_ERR_INPUT;
+                uint32_t bk, uk, bbad; bool ubad;
+                pcl_fast_extract_spec(f, w, rev, &bk, &bbad, &uk, &ubad, false);         // the count kernels: no flag word
+                {   // the specialised instances must agree with the mask-driven extraction, with and without the flag word
+                    uint32_t bk2, uk2, bb2, bk3, uk3, bb3, bk4, uk4, bb4; bool ub2, ub3, ub4;
+                    pcl_fast_extract(f, w, rev, &bk2, &bb2, &uk2, &ub2, false);
+                    if (bk2 != bk || uk2 != uk || (bb2 != 0) != (bbad != 0) || ub2 != ubad) return PCL_ERR_INPUT;
+                    pcl_fast_extract_spec(f, w, rev, &bk3, &bb3, &uk3, &ub3, true);
+                    pcl_fast_extract(f, w, rev, &bk4, &bb4, &uk4, &ub4, true);
+                    if (bk3 != bk4 || uk3 != uk4 || bb3 != bb4 || ub3 != ub4 || uk3 != uk || (bb3 != 0) != (bbad != 0)) return PCL_ERR_INPUT;
                 }
                 uint32_t fs = PCL_SPLIT_OK | absent_rest;
                 if (f.has_tail_target) {
@@ -124,7 +141,10 @@ int emu_run(const pcl_read_desc *reads, int n_reads, int n_regions, const uint8_
                     uint32_t slot = 0xFFFFFFFFu;
                     if (!bbad && len_ok) slot = pcl_probe32(tab, bk);
                     if (slot != 0xFFFFFFFFu) { code = PCL_BC_EXACT; tab.counts[slot]++; }
-                    else { code = PCL_BC_NO_MATCH; ++*tab.mismatch; work[r].push_back({i, f.bc_start, f.bc_len, 0}); }
+                    else {
+                        code = PCL_BC_NO_MATCH; ++*tab.mismatch;
+                        work[r].push_back({pcl_wl_pack(i, f.bc_start, f.bc_len, 0, bbad ? 1u : 0u, PCL_WL_REPACK_POS), bk});
+                    }
                 } else bk = 0;
                 fs |= code << 4;
                 ((uint32_t *)io[r].bc_key[0])[i] = bk;
@@ -157,7 +177,7 @@ int emu_run(const pcl_read_desc *reads, int n_reads, int n_regions, const uint8_
             uint32_t L = io[r].len[i];
             if (rd.max_len && L > rd.max_len) L = rd.max_len;
             const uint8_t *rec = io[r].seq ? io[r].seq + i * (uint64_t)rd.stride : nullptr;
-            bool plan = use_fast == 1 && rd.plan.enabled;                  // mirrors k_count<2>
+            bool plan = (use_fast == 1 || use_fast == 3) && rd.plan.enabled;                  // mirrors k_count<2>
             for (uint32_t j = 0; j < rd.n_bc; ++j) plan = plan && dt[bcr[r][j]].mode != PCL_TAB_K64;
             if (plan) {
                 uint32_t w[16] = {0};
@@ -184,14 +204,17 @@ int emu_run(const pcl_read_desc *reads, int n_reads, int n_regions, const uint8_
                     uint32_t code = PCL_BC_ABSENT, key = 0;
                     if (c != PCL_COORD_ABSENT) {
                         const uint32_t blen = c & 0xFFFFu;
-                        uint32_t ninv;
-                        key = pcl_anchor_key(rd, k, c2, bd2, e, c, &ninv);
+                        uint32_t ninv, ipos;
+                        key = pcl_anchor_key(rd, k, c2, bd2, e, c, &ninv, &ipos);
                         DTable &t = dt[bcr[r][j]];
                         uint32_t slot = 0xFFFFFFFFu;
                         if (ninv == 0u && (t.mode == PCL_TAB_K32_L16 ? blen == 16u : blen <= 15u)) slot = pcl_probe32(t, key);
                         ++*t.total;
                         if (slot != 0xFFFFFFFFu) { code = PCL_BC_EXACT; t.counts[slot]++; }
-                        else { code = PCL_BC_NO_MATCH; ++*t.mismatch; work[r].push_back({i, c >> 16, c & 0xFFFFu, j}); }
+                        else {
+                            code = PCL_BC_NO_MATCH; ++*t.mismatch;
+                            if (ninv <= 1u) work[r].push_back({pcl_wl_pack(i, c >> 16, c & 0xFFFFu, j, ninv, ipos), key});
+                        }
                     }
                     reinterpret_cast<uint32_t *>(io[r].bc_key[j])[i] = key;
                     fs |= code << (4 + 3 * j);
@@ -235,13 +258,21 @@ int emu_run(const pcl_read_desc *reads, int n_reads, int n_regions, const uint8_
                 uint64_t key = 0;
                 if (c != PCL_COORD_ABSENT) {
                     uint32_t ninv, ipos;
-                    key = codes ? pcl_pack_codes(rc, c >> 16, c & 0xFFFFu, rev, &ninv) : pcl_pack_key(rec, c >> 16, c & 0xFFFFu, rev, &ninv, &ipos);
+                    key = codes ? pcl_pack_codes(rc, c >> 16, c & 0xFFFFu, rev, &ninv, &ipos) : pcl_pack_key(rec, c >> 16, c & 0xFFFFu, rev, &ninv, &ipos);
+                    if (codes) {                                       // the code-space packer must agree with the byte packer
+                        uint32_t n2, i2;
+                        const uint64_t k2 = pcl_pack_key(rec, c >> 16, c & 0xFFFFu, rev, &n2, &i2);
+                        if (k2 != key || n2 != ninv || (ninv == 1u && i2 != ipos)) return PCL_ERR_INPUT;
+                    }
                     DTable &t = dt[bcr[r][j]];
                     uint32_t slot = 0xFFFFFFFFu;
                     if (ninv == 0) slot = pcl_probe(t, key, c & 0xFFFFu);
                     ++*t.total;
                     if (slot != 0xFFFFFFFFu) { code = PCL_BC_EXACT; t.counts[slot]++; }
-                    else { code = PCL_BC_NO_MATCH; ++*t.mismatch; work[r].push_back({i, c >> 16, c & 0xFFFFu, j}); }
+                    else {
+                        code = PCL_BC_NO_MATCH; ++*t.mismatch;
+                        if (ninv <= 1u) work[r].push_back({pcl_wl_pack(i, c >> 16, c & 0xFFFFu, j, ninv, ipos), (uint32_t)key});
+                    }
                 }
                 pcl_store_key(io[r].bc_key[j], in.bc_key_bytes[j], i, key);
                 fs |= code << (4 + 3 * j);
@@ -294,30 +325,39 @@ int emu_run(const pcl_read_desc *reads, int n_reads, int n_regions, const uint8_
                             if (rd.elems[el].min_len != rd.elems[el].max_len) l = (s + l < L ? s + l : L) - s;
                             c = (s << 16) | l;
                         } else c = io[r].bcoord[j][i];
-                        work[r].push_back({i, c >> 16, c & 0xFFFFu, j});
+                        work[r].push_back({pcl_wl_pack(i, c >> 16, c & 0xFFFFu, j, 0, 0), 0u});
                     }
                 }
             }
             bool all32 = use_fast && !check_ee;
             for (uint32_t j = 0; j < rd.n_bc; ++j) all32 = all32 && dt[bcr[r][j]].mode != PCL_TAB_K64 && in.bc_key_bytes[j] == 4;
-            for (const Work &w : work[r]) {
-                const uint8_t *rec = io[r].seq + w.rec * (uint64_t)rd.stride;
-                const uint8_t *ql = io[r].qual + w.rec * (uint64_t)rd.qstride - rd.qoff;
-                uint32_t ninv, ipos;
-                uint64_t key = pcl_pack_key(rec, w.start, w.len, rev, &ninv, &ipos);
-                bool is_exact = PCL_BC_CODE((uint32_t)io[r].fstatus[w.rec], w.j) == PCL_BC_EXACT;
+            for (const Work &wk : work[r]) {
+                const uint64_t rec_i = PCL_WL_REC(wk.ent);
+                const uint32_t w_start = PCL_WL_START(wk.ent), w_len = PCL_WL_LEN(wk.ent), w_j = PCL_WL_J(wk.ent);
+                const uint8_t *rec = io[r].seq + rec_i * (uint64_t)rd.stride;
+                const uint8_t *ql = io[r].qual + rec_i * (uint64_t)rd.qstride - rd.qoff;
                 uint64_t out_key = 0;
                 uint32_t code;
-                if (all32) {                          // mirrors k_correct<true>
-                    uint32_t out32 = 0;
-                    code = pcl_correct_one32(dt[bcr[r][w.j]], (uint32_t)key, w.len, ninv, ipos, ql, w.start, rev, threshold, lut, &out32);
+                if (all32) {                          // mirrors k_filter + k_resolve: key and N position come from the worklist
+                    uint32_t out32 = 0, key32 = wk.key, ninv = PCL_WL_NINV(wk.ent), ipos = PCL_WL_IPOS(wk.ent);
+                    if (PCL_WL_IS_REPACK(wk.ent)) {
+                        uint32_t wds[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+                        memcpy(wds, rec, rd.stride);
+                        const uint32_t k2 = pcl_fast_repack(rd.fast, wds, rev, &ninv, &ipos);
+                        if (k2 != key32) { key32 = k2; ((uint32_t *)io[r].bc_key[0])[rec_i] = k2; }
+                    }
+                    const uint64_t cand = pcl_filter32(dt[bcr[r][w_j]], key32, w_len, ninv, ipos);
+                    code = cand ? pcl_resolve32(dt[bcr[r][w_j]], key32, w_len, cand, ql, w_start, rev, threshold, lut, &out32) : PCL_BC_NO_MATCH;
                     out_key = out32;
-                } else {
-                    code = pcl_correct_one(dt[bcr[r][w.j]], key, w.len, ninv, ipos, ql, w.start, rev, is_exact, threshold,
+                } else {                              // mirrors k_correct
+                    uint32_t ninv, ipos;
+                    uint64_t key = pcl_pack_key(rec, w_start, w_len, rev, &ninv, &ipos);
+                    bool is_exact = PCL_BC_CODE((uint32_t)io[r].fstatus[rec_i], w_j) == PCL_BC_EXACT;
+                    code = pcl_correct_one(dt[bcr[r][w_j]], key, w_len, ninv, ipos, ql, w_start, rev, is_exact, threshold,
                                            max_ee, check_ee, lut, lut + 256, &out_key);
                 }
-                if (code == PCL_BC_CORRECTED) pcl_store_key(io[r].bc_key[w.j], in.bc_key_bytes[w.j], w.rec, out_key);
-                if (code != PCL_BC_EXACT && code != PCL_BC_NO_MATCH) io[r].fstatus[w.rec] |= (uint16_t)(code << (4 + 3 * w.j));
+                if (code == PCL_BC_CORRECTED) pcl_store_key(io[r].bc_key[w_j], in.bc_key_bytes[w_j], rec_i, out_key);
+                if (code != PCL_BC_EXACT && code != PCL_BC_NO_MATCH) io[r].fstatus[rec_i] |= (uint16_t)(code << (4 + 3 * w_j));
             }
         }
     }

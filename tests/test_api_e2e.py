@@ -54,6 +54,14 @@ def write_spec(td, hp, rt, forward_insert=False):
     return path
 
 
+def stripped(nm: bytes) -> bytes:
+    """strip_fq_suffix (fastq.rs:612-621): a trailing /1 or /2 of the NAME is dropped before annotate; the description stays."""
+    parts = nm.split(b" ", 1)
+    if len(parts[0]) > 2 and parts[0][-2:] in (b"/1", b"/2"):
+        parts[0] = parts[0][:-2]
+    return b" ".join(parts)
+
+
 def write_fastq(path, names, batch, gz):
     op = gzip.open if gz else open
     with op(path, "wb") as fh:
@@ -129,7 +137,8 @@ def test_gen_barcoded_fastq_matches_oracle(dataset, correct, device_parse):
     assert ("CB" in t) == (got[0].barcode.corrected is not None)
     # definitions: barcode/umi carry R1's definition line, read2 its own
     k = next(i for i, ln in enumerate(ores.lines) if ln)
-    assert got[0].barcode.raw.definition == dataset["names1"][k] and got[0].read2.definition == dataset["names2"][k]
+    assert got[0].barcode.raw.definition == stripped(dataset["names1"][k]) == b"read%d x:%d" % (k, k)
+    assert got[0].read2.definition == stripped(dataset["names2"][k]) == b"read%d" % k
     # QcFastq
     qc = proc.get_fastq_qc()
     cat = ores.qc_cat.astype(float)
@@ -171,7 +180,8 @@ def test_make_fastq(dataset, tmp_path):
         want.append((dataset["names1"][i], (f[2] + f[3] + f[5]).encode("latin-1"), (f[1] + f[4] + f[6]).encode("latin-1")))
     assert len(recs) == len(want) > 1000
     for r, (nm, s, q) in zip(recs, want):
-        assert r[0] == b"@" + nm and r[1] == s and r[2] == b"+" and r[3] == q
+        assert r[0] == b"@" + stripped(nm) and r[1] == s and r[2] == b"+" and r[3] == q
+    assert recs[0][0].startswith(b"@read") and b"/1" not in recs[0][0]
 
 
 def test_make_fastq_without_read1_fails_like_the_reference(dataset, tmp_path):
@@ -251,6 +261,7 @@ def test_make_fastq_paired_end_atac_like(tmp_path):
             continue
         want1.append(((f[2] + f[3] + f[5]).encode("latin-1"), (f[1] + f[4] + f[6]).encode("latin-1")))
         want2.append((f[7].encode("latin-1"), f[8].encode("latin-1")))
+    assert all(r1[i] == r2[i] and r1[i].startswith(b"@q") and b"/" not in r1[i] for i in range(0, len(r1) - 1, 4))   # /1 and /2 stripped
     got1 = [(r1[i + 1], r1[i + 3]) for i in range(0, len(r1) - 1, 4)]
     got2 = [(r2[i + 1], r2[i + 3]) for i in range(0, len(r2) - 1, 4)]
     assert got1 == want1 and got2 == want2 and len(want1) > 1500

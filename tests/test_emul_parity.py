@@ -86,11 +86,13 @@ NAMES = ["v3", "fast12_tail", "v2", "atac", "multiome_atac", "sci3", "share", "d
 
 
 @pytest.mark.parametrize("name", NAMES)
-@pytest.mark.parametrize("mode", ["correct", "nocorrect", "ee", "lower", "correct-generic", "correct-direct", "lower-direct"])
+@pytest.mark.parametrize("mode", ["correct", "nocorrect", "ee", "lower", "correct-generic", "correct-direct", "lower-direct", "correct-nobits",
+                                  "lower-generic"])
 def test_emul_matches_oracle(layouts, name, mode):
     # default: specialised kernels + neighbourhood tables; "-generic": interpreter kernels only;
-    # "-direct": specialised kernels with the 3*L direct probes instead of the neighbourhood tables
-    use_fast = {"generic": 0, "direct": 2}.get(mode.split("-")[-1], 1)
+    # "-direct": specialised kernels with the 3*L direct probes instead of the neighbourhood tables;
+    # "-nobits": neighbourhood tables without the partial-key bitmaps in front of them
+    use_fast = {"generic": 0, "direct": 2, "nobits": 3}.get(mode.split("-")[-1], 1)
     mode = mode.split("-")[0]
     layout = layouts[name]
     rng = np.random.default_rng(U.seed_of(name, mode))
@@ -212,7 +214,7 @@ def _dense_layouts(rng):
 
 
 @pytest.mark.parametrize("name", ["all6", "len15", "mix15_16", "len31", "near_dups"])
-@pytest.mark.parametrize("use_fast", [0, 1, 2])
+@pytest.mark.parametrize("use_fast", [0, 1, 2, 3])
 def test_emul_dense_and_boundary_whitelists(name, use_fast):
     layout = _dense_layouts(np.random.default_rng(77))[name]
     rng = np.random.default_rng(U.seed_of(name, "dense"))

@@ -56,12 +56,16 @@ def run_gpu(layout, dev_batches, correct=True, threshold=0.975, max_expected_err
 
 
 @pytest.mark.parametrize("name", NAMES)
-@pytest.mark.parametrize("mode", ["correct", "nocorrect", "ee", "lower", "correct-generic", "correct-direct", "lower-direct"])
+@pytest.mark.parametrize("mode", ["correct", "nocorrect", "ee", "lower", "correct-generic", "correct-direct", "lower-direct",
+                                  "correct-oldfast", "lower-oldfast", "correct-nobits"])
 def test_gpu_matches_oracle(layouts, name, mode, monkeypatch):
     # the specialised kernels + neighbourhood tables are the default; "-generic" forces the interpreter kernels,
-    # "-direct" the 3*L direct probes, on the same data
+    # "-direct" the 3*L direct probes, "-oldfast" the software-pipelined k_count_fast instead of k_count_spec,
+    # "-nobits" the neighbourhood tables without the partial-key bitmaps, on the same data
     monkeypatch.setenv("PCL_FORCE_GENERIC", "1" if mode.endswith("-generic") else "0")
     monkeypatch.setenv("PCL_NO_NEIGHBOUR_TABLES", "1" if mode.endswith("-direct") else "0")
+    monkeypatch.setenv("PCL_OLD_FAST", "1" if mode.endswith("-oldfast") else "0")
+    monkeypatch.setenv("PCL_NO_NBITS", "1" if mode.endswith("-nobits") else "0")
     mode = mode.split("-")[0]
     layout = layouts[name]
     rng = np.random.default_rng(U.seed_of(name, mode, "gpu"))
