@@ -33,11 +33,19 @@ if ROOT not in sys.path:
 N_WHITELIST = 6_800_000
 R2_LEN = 91
 THRESHOLD = 0.975          # make_fastq default (precellar/src/align/fastq.rs:39)
-# algorithmic bytes per read pair (SURVEY.md 8d / DESIGN.md): B = 108 + 1536 * f_mis, split per kernel launch
-B_COUNT_R1 = 30 + 32 + 10  # R1 seq + len, one probe sector, results (the count pass never reads qualities)
-B_CORRECT_QUAL = 28        # R1 qualities: SURVEY's B_in charges them for every pair; only the correction pass reads them
-B_COUNT_R2 = 2 + 6         # R2 len, fstatus+tcoord
-B_CORRECT_PER_MISS = 1536  # 3 * 16 neighbour probes * 32 B
+# Bytes of the IMPLEMENTED algorithm per unit of work (DESIGN.md section 3 has the derivation; every kernel's `frac` in
+# the JSON line is these bytes / its event-timed duration / the measured copy bandwidth):
+#   count kernel of a read with barcodes, per record: the payload bytes the layout can touch + 2 (length) + one 32-byte
+#       probe sector per barcode + the result words (fstatus 2, insert coordinates 4, keys 4/8 each, segment coordinates
+#       4 each for variable layouts) + 12 per missed barcode (worklist entry + packed key)
+#   count kernel of an insert read (lengths only), per record: 2 + 2 + 4
+#   k_filter, per missed barcode: 12 in + 8 out + four partial-key lookups of one sector each (answered by the bitmap
+#       word or by the neighbourhood bucket): 148
+#   k_resolve, per missed barcode: 20 (entry, key, candidates) + one sector each of qualities, main table and counts
+#       + 6 of result words: 122
+B_FILTER_PER_MISS = 12 + 8 + 4 * 32
+B_RESOLVE_PER_MISS = 20 + 3 * 32 + 6
+B_WORKLIST_PER_MISS = 12
 
 
 def env_int(name, default):
@@ -110,28 +118,16 @@ def pinned(nbytes: int, dtype, shape):
     return arr, p
 
 
-def run_reference_sample(wl, seq, qual, length, len2, n_threads, steps=1, warmup=0, want_outputs=False):
-    """The reference algorithm (oracle port: serial pass 1, parallel pass 2 over 128 sub-chunks per batch)
-    on host cores.  Returns (seconds per step list, OracleResult of the last step)."""
-    from oracle import pyoracle as O
-    from precellar_b200.configs import v3_layout
-    layout = v3_layout(wl, R2_LEN)
-    n_wl, k = wl.shape
-    orc = O.Oracle(O.reads_from_layout(layout), {0: (wl.reshape(-1), np.arange(n_wl + 1, dtype=np.uint64) * np.uint64(k), n_wl)})
-    orc.set_input(0, seq, qual, length, seq.shape[1])
-    orc.set_input(1, None, None, len2, 0)
-    times, res = [], None
-    for s in range(warmup + steps):
-        t0 = time.perf_counter()
-        orc.count()                                                     # BarcodeAnalyzer::new, serial
-        res = orc.annotate(correct=True, threshold=THRESHOLD, n_threads=n_threads, chunk_bases=1_000_000,
-                           outputs=want_outputs or s == warmup + steps - 1)
-        dt = time.perf_counter() - t0
-        if s >= warmup:
-            times.append(dt)
-    counts = orc.counts(0)
-    orc.close()
-    return times, res, counts
+def count_bytes_per_record(pipe, r: int) -> float:
+    """Implemented-algorithm bytes of pass 1 for one record of read r, without the worklist (see the table above)."""
+    info = pipe.infos[r]
+    if not info.needs_payload:
+        return 2 + 2 + (4 if info.has_target else 0)
+    b = pipe.payload_bytes(r) + 2 + 32 * info.n_bc + 2 + (4 if info.has_target else 0)
+    b += sum(info.bc_key_bytes[j] for j in range(info.n_bc)) + sum(info.umi_key_bytes[j] for j in range(info.n_umi))
+    if not info.fixed_layout:
+        b += 4 * (info.n_bc + info.n_umi)
+    return b
 
 
 def measure_device_ingest(pipe, p1: str, p2: str, n_pairs: int) -> dict:
@@ -300,6 +296,175 @@ def measure_ingest(syn, n_pairs: int, tmpdir: str, pipe=None) -> dict:
     return out
 
 
+# ------------------------------------------------------------------------------------------------------------------
+# device-resident measurement of one or several pipelines that live on the GPU at the same time
+# ------------------------------------------------------------------------------------------------------------------
+def load_traffic():
+    """DRAM bytes per unit of work of every kernel, from the committed ncu capture of this build (profiles/ncu_traffic.json;
+    `ncu --set full`, dram__bytes_read.sum + dram__bytes_write.sum).  Not measurable inside an un-profiled run."""
+    path = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    try:
+        return json.load(open(path))
+    except Exception:
+        return {}
+
+
+def kernel_table(pipe, w, n, prof, steps, mis_per_region, peak, traffic_key):
+    """Per-kernel {ms, implemented-algorithm bytes, GB/s, frac of the measured copy peak, ncu DRAM traffic} of one pipeline."""
+    from precellar_b200 import _ffi
+    infos = pipe.infos
+    n_miss = float(sum(mis_per_region))
+    bytes_count = sum(count_bytes_per_record(pipe, r) for r in range(len(infos)) if infos[r].needs_payload) * n + B_WORKLIST_PER_MISS * n_miss
+    bytes_len = sum(count_bytes_per_record(pipe, r) for r in range(len(infos)) if not infos[r].needs_payload) * n
+    t = lambda k: prof[k][0] / steps                  # all launches of that kind in one step (e.g. both insert reads of a triple)
+    rows = {
+        "count": {"ms": t(_ffi.K_COUNT), "alg_bytes": bytes_count, "unit_bytes": bytes_count / n, "per": "read group"},
+        "count_lenonly": {"ms": t(_ffi.K_COUNT_LENONLY), "alg_bytes": bytes_len, "unit_bytes": bytes_len / n, "per": "read group"},
+        "filter": {"ms": t(_ffi.K_FILTER), "alg_bytes": B_FILTER_PER_MISS * n_miss, "unit_bytes": B_FILTER_PER_MISS, "per": "missed barcode"},
+        "resolve": {"ms": t(_ffi.K_CORRECT), "alg_bytes": B_RESOLVE_PER_MISS * n_miss, "unit_bytes": B_RESOLVE_PER_MISS, "per": "missed barcode"},
+    }
+    tr = load_traffic().get(traffic_key, {})
+    out = {}
+    for name, kv in rows.items():
+        if kv["ms"] <= 0:
+            continue
+        gbs = kv["alg_bytes"] / (kv["ms"] / 1e3) / 1e9
+        units = n if kv["per"] == "read group" else n_miss
+        tb = tr.get(name)
+        out[name] = {"ms_per_launch": kv["ms"], "alg_bytes_per_launch": kv["alg_bytes"], "alg_bytes_per_unit": kv["unit_bytes"],
+                     "unit": kv["per"], "achieved_gbs": gbs, "frac": gbs / peak,
+                     "traffic": (float(tb) * units) if tb is not None else None}
+    return out
+
+
+class Resident:
+    """One workload resident on one GPU: pipeline + one chunk of n read groups generated in place."""
+
+    def __init__(self, w, n, device, world=1, rank=0, uid=None):
+        from precellar_b200.pipeline import BarcodePipeline
+        t0 = time.perf_counter()
+        self.w, self.n = w, n
+        self.pipe = BarcodePipeline(w.layout, device=device, nranks=world, rank=rank, nccl_uid=uid)
+        self.setup_s = time.perf_counter() - t0
+        self.chunk = self.pipe.new_chunk(n)
+        self.chunk.reset(n)
+        w.fill_chunk(self.pipe, self.chunk, rank * n, n, device)
+        self.pipe.sync()
+
+    def step(self):
+        p = self.pipe
+        p.reset_counts()
+        p.count(self.chunk)
+        p.allreduce()
+        p.correct(self.chunk, THRESHOLD)
+
+    def close(self):
+        self.pipe.close()
+
+
+def measure_resident(res_list, steps, warmup, barrier, max_over_ranks, clocks=None, sustained_s=0.0):
+    """Time `steps` steps of all pipelines in res_list together (CUDA events on the first pipeline's chunk stream when
+    there is one pipeline; host clock between device syncs when several share the GPU)."""
+    from precellar_b200 import _ffi
+    for _ in range(max(warmup, 3)):
+        for r in res_list:
+            r.step()
+    for r in res_list:
+        r.pipe.sync()
+        r.pipe.profile_enable(True)
+        r.pipe.profile_reset()
+    l0 = [r.pipe.launch_count() for r in res_list]
+    barrier()
+    if clocks:
+        clocks.start()
+    if len(res_list) == 1:
+        res_list[0].chunk.timer_start()
+        for _ in range(steps):
+            res_list[0].step()
+        ms_total = res_list[0].chunk.timer_stop_ms()
+    else:
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            for r in res_list:
+                r.step()
+        for r in res_list:
+            r.pipe.sync()
+        ms_total = (time.perf_counter() - t0) * 1e3
+    barrier()
+    launches = sum(r.pipe.launch_count() - a for r, a in zip(res_list, l0))
+    prof = [{k: r.pipe.profile_get(k) for k in (_ffi.K_COUNT, _ffi.K_CORRECT, _ffi.K_COUNT_LENONLY, _ffi.K_FILTER)} for r in res_list]
+    for r in res_list:
+        r.pipe.profile_enable(False)
+    ms_step = max_over_ranks(ms_total) / steps
+    sustained = None
+    if sustained_s > 0:                      # a longer region (the contract's K steps are a few tens of milliseconds)
+        k = max(steps, int(sustained_s * 1e3 / max(ms_step, 1e-3)))
+        barrier()
+        if len(res_list) == 1:
+            res_list[0].chunk.timer_start()
+            for _ in range(k):
+                res_list[0].step()
+            ms = res_list[0].chunk.timer_stop_ms()
+        else:
+            t0 = time.perf_counter()
+            for _ in range(k):
+                for r in res_list:
+                    r.step()
+            for r in res_list:
+                r.pipe.sync()
+            ms = (time.perf_counter() - t0) * 1e3
+        barrier()
+        sustained = {"steps": k, "ms_per_step": max_over_ranks(ms) / k}
+    if clocks:
+        clocks.stop()
+    return ms_step, prof, launches, sustained
+
+
+def parity_prefix(w, pipe, ns, device, world, rank, host_cores, gather):
+    """The first `ns` read groups of the workload, sharded over the ranks like the real job: count -> all-reduce ->
+    correct on every rank's shard, results gathered to rank 0 in rank order and compared field by field with the oracle
+    (the reference algorithm on the host) run on the whole prefix.  Returns (parity dict, cpu seconds) on rank 0."""
+    from precellar_b200.dist import shard_bounds
+    from tools.v3check import compare_bulk
+    lo, hi = shard_bounds(ns, world)[rank]
+    full = w.host_batches(lo, hi - lo)                 # the generator is a function of the record index: same bytes as resident
+    dev = w.device_batches(pipe, full)
+    ch = pipe.new_chunk(max(hi - lo, 1))
+    pipe.reset_counts()
+    ch.reset(hi - lo)
+    for r, b in enumerate(dev):
+        ch.upload(r, b)
+    pipe.count(ch)
+    pipe.allreduce()
+    pipe.correct(ch, THRESHOLD)
+    mine = [ch.fetch(r) for r in range(len(dev))]
+    counts = {g: pipe.counts(g) for g in range(len(w.layout.region_ids))}
+    defects = pipe.qc()[:, 1].copy()
+    ch.close()
+    pipe.chunks.remove(ch)
+    parts = gather(dict(res=[dict(fstatus=m.fstatus, tcoord=m.tcoord, bc_key=m.bc_key, umi_key=m.umi_key, bcoord=m.bcoord, ucoord=m.ucoord)
+                             for m in mine], defects=defects))
+    if rank != 0:
+        return None, None
+    cat = lambda xs: None if xs[0] is None else np.concatenate(xs)
+    results = []
+    for r in range(len(dev)):
+        res = pipe.alloc_results(r, 0)
+        ps = [p["res"][r] for p in parts]
+        res.fstatus, res.tcoord = cat([p["fstatus"] for p in ps]), cat([p["tcoord"] for p in ps])
+        res.bc_key = [cat([p["bc_key"][j] for p in ps]) for j in range(len(ps[0]["bc_key"]))]
+        res.umi_key = [cat([p["umi_key"][j] for p in ps]) for j in range(len(ps[0]["umi_key"]))]
+        res.bcoord = [cat([p["bcoord"][j] for p in ps]) for j in range(len(ps[0]["bcoord"]))]
+        res.ucoord = [cat([p["ucoord"][j] for p in ps]) for j in range(len(ps[0]["ucoord"]))]
+        results.append(res)
+    from tools.workloads import run_oracle
+    whole = w.host_batches(0, ns) if world > 1 else full
+    cpu_s, ores, ocounts = run_oracle(w, whole, THRESHOLD, host_cores)
+    fields = compare_bulk(w.layout, pipe.infos, results, counts, ores, ocounts)
+    fields["defect_counts"] = int((sum(p["defects"] for p in parts) != ores.qc_per_file[:, 1]).sum())
+    return {"checked_read_groups": int(ns), "ranks": world, "mismatches": int(sum(fields.values())), "fields": fields}, cpu_s
+
+
 def main():
     # stdout carries exactly one JSON line: libraries that print to fd 1 (e.g. NCCL's version banner) go to stderr
     json_fd = os.dup(1)
@@ -312,14 +477,17 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--pairs-per-gpu", type=int, default=125_000_000)
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--e2e-chunks", type=int, default=8)
     ap.add_argument("--cpu-sample", type=int, default=2_500_000)
+    ap.add_argument("--sustained-s", type=float, default=1.0)
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the oracle legs (parity, cpu_baseline) and the host ingest measurements")
+    ap.add_argument("--no-other", action="store_true", help="skip the other BASELINE configurations")
+    ap.add_argument("--other-n", type=int, default=0, help="read groups per other configuration (default: BASELINE sizes)")
     ap.add_argument("--ingest-sample", type=int, default=1_000_000)
     args = ap.parse_args()
 
@@ -329,31 +497,31 @@ def main():
     workload = (f"10x scRNA-seq v3 (16nt CB + 12nt UMI, R2 {R2_LEN}nt), {N_WHITELIST} whitelist, "
                 f"{n} synthetic read pairs per GPU (1B-pair / 8-GPU config)")
 
-    from tools import synth as S
-    wl = S.make_whitelist(N_WHITELIST, 16)
-    spec = S.SynthSpec(N_WHITELIST, bc_len=16, umi_len=12, stride=32, n_cells=10000)
+    from tools import workloads as W
 
     # ------------------------------------------------------------------ reference arm (host cores only)
     if args.impl == "reference":
         if rank != 0:
             return 0
-        syn = S.Synth(spec, wl)
+        w = W.v3(N_WHITELIST, R2_LEN)
         # bounded sample: calibrate on 200k pairs, then size the per-step sample so the whole run takes ~2 minutes
         nc = min(200_000, n)
-        seq, qual, length = syn.host_arrays(0, nc)
-        tcal, _, _ = run_reference_sample(wl, seq, qual, length, np.full(nc, R2_LEN, np.uint16), host_cores)
-        rate = nc / tcal[0]
-        w = min(args.warmup, 1)
-        ns = int(max(100_000, min(args.cpu_sample, n, 120.0 * rate / (args.steps + w))))
-        seq, qual, length = syn.host_arrays(0, ns)
-        len2 = np.full(ns, R2_LEN, np.uint16)
-        times, _, _ = run_reference_sample(wl, seq, qual, length, len2, host_cores, steps=args.steps, warmup=w)
+        tcal, _, _ = W.run_oracle(w, w.host_batches(0, nc), THRESHOLD, host_cores, outputs=False)
+        rate = nc / tcal
+        total_steps = args.steps + args.warmup
+        ns = int(max(50_000, min(args.cpu_sample, n, 110.0 * rate / max(total_steps, 1))))
+        full = w.host_batches(0, ns)
+        times = []
+        for s in range(total_steps):
+            dt, _, _ = W.run_oracle(w, full, THRESHOLD, host_cores, outputs=False)
+            if s >= args.warmup:
+                times.append(dt)
         ms = 1e3 * float(np.mean(times))
         v = ns / (ms / 1e3)
         cfg = {"workload": workload, "sample_pairs_per_step": ns, "l2": "inputs >> L2 (host arm)"}
         emit({
             "impl": "reference", "metric": "barcode-corrected read-pairs/sec", "value": v, "unit": "read-pairs/s",
-            "n_gpus": args.gpus, "steps": args.steps, "warmup": min(args.warmup, 1), "ms_per_step": ms,
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8/f64", "data": "synthetic",
             "config": cfg,
             "cpu_baseline": {"value": v, "unit": "read-pairs/s", "cores": host_cores, "kind": "port",
@@ -364,6 +532,7 @@ def main():
         return 0
 
     # ------------------------------------------------------------------ our arm
+    import pickle
     import torch
     import torch.distributed as dist
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
@@ -383,61 +552,16 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    def gather(obj):
+        if world == 1:
+            return [obj]
+        out = [None] * world
+        dist.all_gather_object(out, pickle.dumps(obj))
+        return [pickle.loads(b) for b in out]
+
     from precellar_b200 import _ffi
-    from precellar_b200.configs import v3_layout
     from precellar_b200.pipeline import BarcodePipeline, HostBatch
-
     from precellar_b200.dist import exchange_unique_id
-    uid = exchange_unique_id(BarcodePipeline.new_unique_id, rank, world)
-    layout = v3_layout(wl, R2_LEN)
-    t_setup = time.perf_counter()
-    pipe = BarcodePipeline(layout, device=local_rank, nranks=world, rank=rank, nccl_uid=uid)
-    t_setup = time.perf_counter() - t_setup          # ctx + layout + whitelist tables (host build and upload) + NCCL init
-    syn = S.Synth(spec, wl)
-    first = rank * n
-
-    # device-resident shard, generated in place
-    big = pipe.new_chunk(n)
-    big.reset(n)
-    s1, q1, l1 = big.device_ptrs(0)
-    _, _, l2 = big.device_ptrs(1)
-    syn.fill_device(local_rank, first, n, s1, q1, l1, big.stream, qual_window=pipe.qual_window(0))
-    syn.fill_u16_device(local_rank, l2, R2_LEN, n, big.stream)
-    pipe.sync()
-
-    def step_resident():
-        pipe.reset_counts()
-        pipe.count(big)
-        pipe.allreduce()
-        pipe.correct(big, THRESHOLD)
-
-    clocks = ClockSampler(local_rank)
-    for _ in range(max(args.warmup, 3)):
-        step_resident()
-    pipe.sync()
-    pipe.profile_enable(True)
-    pipe.profile_reset()
-    launches0 = pipe.launch_count()
-    barrier()
-    clocks.start()
-    big.timer_start()
-    for _ in range(args.steps):
-        step_resident()
-    ms_total = big.timer_stop_ms()
-    barrier()
-    clocks.stop()
-    launches = pipe.launch_count() - launches0
-    ms_total = max_over_ranks(ms_total)
-    ms_step = ms_total / args.steps
-    value = n * world / (ms_step / 1e3)
-    prof = {k: pipe.profile_get(k) for k in (_ffi.K_COUNT, _ffi.K_CORRECT, _ffi.K_COUNT_LENONLY, _ffi.K_FILTER)}
-    pipe.profile_enable(False)
-    cnt, mismatch, total = pipe.counts(0)
-    assert total == n * world, (total, n, world)                 # the allreduce summed every rank's shard
-    assert int(cnt.sum()) + mismatch == total
-    f_mis_global = mismatch / total
-    # the rank's own miss count drives its correct kernel
-    f_mis = f_mis_global
 
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(peaks_path):
@@ -445,42 +569,42 @@ def main():
         peak_src = "MEASURED_PEAKS.json hbm_gbs (measured copy bandwidth)"
     else:
         peak, peak_src = 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
-    t_count = prof[_ffi.K_COUNT][0] / max(prof[_ffi.K_COUNT][1], 1)
-    t_corr = prof[_ffi.K_CORRECT][0] / max(prof[_ffi.K_CORRECT][1], 1)
-    t_len = prof[_ffi.K_COUNT_LENONLY][0] / max(prof[_ffi.K_COUNT_LENONLY][1], 1)
-    t_filt = prof[_ffi.K_FILTER][0] / max(prof[_ffi.K_FILTER][1], 1)
-    kern = {
-        "k_filter(R1)": {"ms": t_filt, "alg_bytes": n * f_mis * (20 + 4 * 32)},
-        "k_count(R1)": {"ms": t_count, "alg_bytes": n * B_COUNT_R1},
-        "k_correct(R1)": {"ms": t_corr, "alg_bytes": n * (B_CORRECT_QUAL + f_mis * B_CORRECT_PER_MISS)},
-        "k_count(R2,len-only)": {"ms": t_len, "alg_bytes": n * B_COUNT_R2},
-    }
-    for kv in kern.values():
-        kv["gbs"] = kv["alg_bytes"] / (kv["ms"] / 1e3) / 1e9 if kv["ms"] > 0 else None
-    dom = max(kern, key=lambda k: kern[k]["ms"])
-    traffic = None                                   # DRAM bytes per launch of the dominant kernel, from the committed ncu capture
-    tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
-    if os.path.exists(tpath):
-        try:
-            ent = json.load(open(tpath)).get(dom)
-            traffic = float(ent["dram_bytes_per_pair"]) * n if ent else None
-        except Exception:
-            traffic = None
-    step_alg_bytes = n * (108 + B_CORRECT_PER_MISS * f_mis)
+
+    uid = exchange_unique_id(BarcodePipeline.new_unique_id, rank, world)
+    w3 = W.v3(N_WHITELIST, R2_LEN)
+    R = Resident(w3, n, local_rank, world, rank, uid)
+    pipe, big, syn = R.pipe, R.chunk, w3.gen
+    t_setup = R.setup_s                               # ctx + layout + whitelist tables (host build and upload) + NCCL init
+    first = rank * n
+
+    clocks = ClockSampler(local_rank)
+    ms_step, prof, launches, sustained = measure_resident([R], args.steps, args.warmup, barrier, max_over_ranks, clocks, args.sustained_s)
+    value = n * world / (ms_step / 1e3)
+    cnt, mismatch, total = pipe.counts(0)
+    assert total == n * world, (total, n, world)                 # the allreduce summed every rank's shard
+    assert int(cnt.sum()) + mismatch == total
+    f_mis_global = mismatch / total
+    kern = kernel_table(pipe, w3, n, prof[0], args.steps, [f_mis_global * n], peak, "v3")
+    dom = max(kern, key=lambda k: kern[k]["ms_per_launch"])
+    step_alg_bytes = sum(v["alg_bytes_per_launch"] for v in kern.values())
     roofline = {
-        "bound": "hbm", "kernel": dom, "achieved": kern[dom]["gbs"], "peak": peak, "unit": "GB/s",
-        "frac": (kern[dom]["gbs"] / peak) if kern[dom]["gbs"] else None, "traffic": traffic, "peak_source": peak_src,
-        "algorithmic_bytes_per_launch": kern[dom]["alg_bytes"], "ms_per_launch": kern[dom]["ms"],
-        "kernels": {k: {"ms_per_launch": v["ms"], "achieved_gbs": v["gbs"], "alg_bytes_per_launch": v["alg_bytes"]} for k, v in kern.items()},
-        "whole_step": {"alg_bytes_per_pair": 108 + B_CORRECT_PER_MISS * f_mis,
-                       "achieved_gbs": step_alg_bytes / (ms_step / 1e3) / 1e9,
-                       "frac": step_alg_bytes / (ms_step / 1e3) / 1e9 / peak},
+        "bound": "hbm", "kernel": dom, "achieved": kern[dom]["achieved_gbs"], "peak": peak, "unit": "GB/s",
+        "frac": kern[dom]["frac"], "traffic": kern[dom]["traffic"], "peak_source": peak_src,
+        "algorithmic_bytes_per_launch": kern[dom]["alg_bytes_per_launch"], "ms_per_launch": kern[dom]["ms_per_launch"],
+        "byte_model": "bytes of the implemented algorithm (bench.py header / DESIGN.md section 3); traffic = ncu dram bytes of the committed capture",
+        "kernels": kern,
+        "whole_step": {"alg_bytes_per_pair": step_alg_bytes / n, "achieved_gbs": step_alg_bytes / (ms_step / 1e3) / 1e9,
+                       "frac": step_alg_bytes / (ms_step / 1e3) / 1e9 / peak,
+                       "survey_model_bytes_per_pair": 108 + 1536 * f_mis_global,
+                       "note": "frac uses the implemented-algorithm bytes; SURVEY 8d's 108 + 1536 f_mis charges 48 probes per miss, which "
+                               "the neighbourhood tables replace by four (kept for reference only)"},
     }
 
     # ------------------------------------------------------------------ end to end from pinned host memory
     e2e = None
-    parity = None
     if not args.no_e2e:
+        s1, q1, l1 = big.device_ptrs(0)
+        _, _, l2 = big.device_ptrs(1)
         nc = max(1, args.e2e_chunks)
         bounds = np.linspace(0, n, nc + 1).astype(np.int64)
         cap = int(np.max(np.diff(bounds)))
@@ -547,42 +671,58 @@ def main():
                "d2h_bytes_per_step": int(d2h) * world, "h2d_bytes_per_step_per_gpu": int(h2d),
                "d2h_bytes_per_step_per_gpu": int(d2h), "ms_per_step": dt * 1e3, "chunks": nc,
                "note": "pinned host SoA planes (R1 rows of the 28 bytes the layout uses, widened to 32 on the device) -> H2D -> count -> allreduce -> correct -> D2H of every result plane"}
+        for ch in chunks:
+            ch.close()
+            pipe.chunks.remove(ch)
+        for ptr in (_p1, _p2, _p3, _p4, _p5, _p6, _p7, _p8, _p9):
+            _ffi.lib().pcl_host_free(ptr)
+        del seq_h, qual_h, len_h, len2_h, fs1_h, bck_h, umi_h, fs2_h, tc2_h, outs
 
-        # ------------------------------------------------------------- CPU baseline + parity on a bounded sample
-        if rank == 0 and world == 1 and not args.no_cpu:
-            ns = min(args.cpu_sample, n)
-            # GPU results for exactly this sample (counts are global, so rerun the path on the sample alone)
-            seq_s, qual_s, len_s = syn.host_arrays(first, ns)          # same bytes as the device generator (tested)
-            len2_s = np.full(ns, R2_LEN, np.uint16)
-            small = pipe.new_chunk(ns)
-            pipe.reset_counts()
-            small.reset(ns)
-            small.upload(0, pipe.host_planes(0, seq_s, qual_s, len_s))
-            small.upload(1, HostBatch(None, None, len2_s))
-            pipe.count(small)
-            pipe.allreduce()
-            pipe.correct(small, THRESHOLD)
-            g1, g2 = small.fetch(0), small.fetch(1)
-            gcnt, gmm, gtot = pipe.counts(0)
-            times, ores, ocounts = run_reference_sample(wl, seq_s, qual_s, len_s, len2_s, host_cores,
-                                                        steps=1, warmup=0, want_outputs=True)
-            cpu_v = ns / float(np.mean(times))
-            from tools.v3check import compare_v3
-            fields = compare_v3(wl, g1, g2, (gcnt, gmm, gtot), ores, ocounts)
-            parity = {"checked_pairs": int(ns), "mismatches": int(sum(fields.values())), "fields": fields}
-            cpu_baseline = {"value": cpu_v, "unit": "read-pairs/s", "cores": host_cores, "kind": "port",
+    # ------------------------------------------------------------------ parity (every rank takes part) + CPU baseline
+    parity = cpu_baseline = None
+    if not args.no_cpu:
+        ns = min(args.cpu_sample, n)
+        parity, cpu_s = parity_prefix(w3, pipe, ns, local_rank, world, rank, host_cores, gather)
+        if rank == 0:
+            cpu_baseline = {"value": ns / cpu_s, "unit": "read-pairs/s", "cores": host_cores, "kind": "port",
                             "sample": f"first {ns} read pairs of the workload, one pass: serial count + {host_cores}-thread "
                                       "correct (C++ restatement of the reference algorithm; in-memory SoA input, no gzip)"}
-        else:
-            cpu_baseline = None
-    else:
-        cpu_baseline = None
 
     ingest = None
     if rank == 0 and world == 1 and not args.no_cpu and args.ingest_sample > 0:
         import tempfile
         with tempfile.TemporaryDirectory() as td:
             ingest = measure_ingest(syn, args.ingest_sample, td, pipe)
+    R.close()
+
+    # ------------------------------------------------------------------ the other BASELINE configurations (one GPU)
+    other = None
+    if world == 1 and not args.no_other:
+        other = []
+        specs = [("configs[1] 10x scATAC", [W.atac()], 100_000_000, "atac"),
+                 ("configs[2] 10x multiome: RNA and ATAC pipelines resident together", [W.multiome_rna(), W.multiome_atac()], 50_000_000, "multiome"),
+                 ("configs[3] sci-RNA-seq3", [W.sci3()], 100_000_000, "sci3")]
+        for title, ws, n_cfg, key in specs:
+            n_cfg = args.other_n or n_cfg
+            rs = [Resident(wk, n_cfg, local_rank) for wk in ws]
+            ms, profs, ln, _ = measure_resident(rs, args.steps, args.warmup, barrier, max_over_ranks)
+            ent = {"config": title, "read_groups_per_pipeline": n_cfg, "pipelines": [], "ms_per_step": ms,
+                   "value": n_cfg * len(rs) / (ms / 1e3), "unit": "read-groups/s", "gpu_launches": int(ln),
+                   "timing": "CUDA events" if len(rs) == 1 else "host clock between device syncs (two contexts, kernels of both in flight)"}
+            for k, (r, pf) in enumerate(zip(rs, profs)):
+                tots = [r.pipe.counts(g) for g in range(len(r.w.layout.region_ids))]
+                kt = kernel_table(r.pipe, r.w, n_cfg, pf, args.steps, [t[1] for t in tots], peak, key if len(rs) == 1 else f"{key}{k}")
+                pent = {"workload": r.w.name, "unit": r.w.unit, "f_mis": [t[1] / max(t[2], 1) for t in tots],
+                        "whitelist_tables_resident": [int(r.pipe.whitelist_size(g)) for g in range(len(tots))],
+                        "defect_records": [int(x) for x in r.pipe.qc()[:, 1]], "setup_s": r.setup_s, "kernels": kt}
+                if not args.no_cpu:
+                    par, cpu_s = parity_prefix(r.w, r.pipe, min(args.cpu_sample, n_cfg), local_rank, 1, 0, host_cores, gather)
+                    pent["parity"] = par
+                    pent["cpu_baseline"] = {"value": par["checked_read_groups"] / cpu_s, "unit": "read-groups/s", "cores": host_cores, "kind": "port"}
+                ent["pipelines"].append(pent)
+            other.append(ent)
+            for r in rs:
+                r.close()
 
     if rank == 0:
         out = {
@@ -594,11 +734,11 @@ def main():
                        "whitelist replicated, one NCCL allreduce of the counts",
                        "l2": "inputs (6.3 GB per GPU) are far larger than L2; no flush needed"},
             "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": int(launches),
-            "clocks": clocks.summary(), "parity": parity, "host_cores": host_cores, "host_ingest": ingest,
+            "clocks": clocks.summary(), "sustained": sustained, "parity": parity, "host_cores": host_cores, "host_ingest": ingest,
+            "other_configs": other,
             "setup_s": {"pipeline_create_incl_whitelist_tables": t_setup},
         }
         emit(out)
-    pipe.close()
     if world > 1:
         dist.destroy_process_group()
     return 0

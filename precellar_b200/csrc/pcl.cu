@@ -276,7 +276,13 @@ int pcl_ctx_create(pcl_ctx **out, int device) {
         return PCL_ERR_CUDA;
     };
     if ((e = cudaSetDevice(device)) != cudaSuccess) return bail("cudaSetDevice", e);
-    if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", e);
+    {
+        // the ctx stream carries the all-reduce of the counts: highest priority, so that its CTAs take the first slots the
+        // kernels of the chunk streams free up (k_filter runs several waves for that reason)
+        int prio_lo = 0, prio_hi = 0;
+        cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+        if ((e = cudaStreamCreateWithPriority(&ctx->stream, cudaStreamNonBlocking, prio_hi)) != cudaSuccess) return bail("cudaStreamCreate", e);
+    }
     if ((e = cudaEventCreateWithFlags(&ctx->ev_reduced, cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", e);
     if ((e = cudaMalloc(&ctx->d_lut, 512 * sizeof(double))) != cudaSuccess) return bail("cudaMalloc", e);
     if ((e = cudaMalloc(&ctx->d_qc, (PCL_MAX_READS + 12) * sizeof(unsigned long long))) != cudaSuccess) return bail("cudaMalloc", e);
@@ -879,7 +885,9 @@ static int launch_filter(pcl_ctx *ctx, pcl_chunk *c, int r) {
     CorrectParams p;
     correct_params(ctx, c, r, p);
     prof_begin(ctx, c->stream, PCL_K_FILTER);
-    k_filter<<<worklist_grid(ctx, c, ctx->infos[r].n_bc, false, ctx->occ[OCC_FILTER]), PCL_BLOCK, 0, c->stream>>>(p);
+    // four waves instead of one resident wave: the first CTAs retire a quarter of the way in and make room for the
+    // all-reduce kernel that waits on the ctx stream (on one GPU the difference is not measurable)
+    k_filter<<<worklist_grid(ctx, c, ctx->infos[r].n_bc, false, 4 * ctx->occ[OCC_FILTER]), PCL_BLOCK, 0, c->stream>>>(p);
     prof_end(ctx, c->stream);
     CU(ctx, cudaGetLastError());
     c->rb[r].filtered = true;

@@ -265,6 +265,47 @@ def test_multiome_atac_config_linker_plus_reverse_barcode():
     assert sum(fields.values()) == 0, fields
 
 
+def test_multiome_config_rna_and_atac_pipelines_resident_together():
+    """BASELINE configs[2] as stated (10x_rna_atac.yaml): the RNA pipeline (v3 shape, 737 K gex list) and the ATAC
+    pipeline (I2 = linker 8 + neg-strand CB16, 737 K atac list) live on ONE GPU at the same time -- both whitelist tables
+    resident, their passes interleaved the way a caller with two assays would issue them -- and each equals the oracle
+    (precellar/src/align/fastq.rs:120-151: one analyzer, one set of counts per assay)."""
+    from precellar_b200.pipeline import BarcodePipeline
+    from tools import workloads as W
+    from tools.v3check import compare_bulk
+    n = 2_000_000
+    ws = [W.multiome_rna(), W.multiome_atac()]
+    assert [len(w.layout.whitelists[w.layout.region_ids[0]]) for w in ws] == [737_000, 737_000]
+    pipes = [BarcodePipeline(w.layout) for w in ws]
+    try:
+        fulls = [w.host_batches(0, n) for w in ws]
+        chunks = []
+        for w, pipe, full in zip(ws, pipes, fulls):           # both tables are loaded before any read is counted
+            ch = pipe.new_chunk(n)
+            ch.reset(n)
+            for r, b in enumerate(w.device_batches(pipe, full)):
+                ch.upload(r, b)
+            chunks.append(ch)
+        for pipe, ch in zip(pipes, chunks):                   # pass 1 of both, then the exchange, then pass 2 of both
+            pipe.count(ch)
+        for pipe in pipes:
+            pipe.allreduce()
+        for pipe, ch in zip(pipes, chunks):
+            pipe.correct(ch, 0.975)
+        for w, pipe, ch, full in zip(ws, pipes, chunks, fulls):
+            results = [ch.fetch(r) for r in range(len(full))]
+            counts = {0: pipe.counts(0)}
+            _, ores, ocounts = W.run_oracle(w, full, 0.975, 16)
+            fields = compare_bulk(w.layout, pipe.infos, results, counts, ores, ocounts)
+            assert sum(fields.values()) == 0, (w.name, fields)
+            assert np.array_equal(pipe.qc()[:, 1], ores.qc_per_file[:, 1])
+            code = (results[w.bc_read].fstatus.astype(np.uint32) >> 4) & 7
+            assert (code == _ffi.BC_EXACT).mean() > 0.7 and (code == _ffi.BC_CORRECTED).sum() > 50_000
+    finally:
+        for pipe in pipes:
+            pipe.close()
+
+
 def test_sci3_config_variable_hairpin_and_anchor():
     """BASELINE configs[3] shape (sci-RNA-seq3: hairpin 9|10 + CAGAGC anchor + UMI 8 + RT 10), 3 M pairs through the
     element-table interpreter kernel; includes anchor mismatches (defect records)."""
