@@ -26,6 +26,11 @@ from .pipeline import BarcodePipeline, Chunk, assemble, decode_key_py, rev_compl
 from .seqspec import Assay, parse_modality
 
 
+# Device chunks hold at least this many read groups whatever ``chunk_size`` asks for (results do not depend on the
+# batching; small chunks only multiply launches and allocations).  Tests lower it to exercise multi-chunk runs.
+MIN_CHUNK_RECORDS = 262144
+
+
 @dataclass
 class FastqRecord:
     """name + description (the FASTQ definition line without '@'), sequence, quality."""
@@ -79,9 +84,16 @@ def _as_assays(assay) -> List[Assay]:
 class FastqProcessor:
     """Barcode counting, correction and annotation of the FASTQ files named by one or more assays."""
 
-    def __init__(self, assay, device: int = 0, device_parse: bool = False):
+    def __init__(self, assay, device: int = 0, device_parse: bool = False, devices: Optional[Sequence[int]] = None):
+        """``devices``: several GPUs of the box.  The record stream is dealt out chunk by chunk (chunk k goes to
+        ``devices[k % len(devices)]``), every GPU counts its chunks against its own copy of the whitelist tables, the
+        counts are summed with one NCCL all-reduce (``pcl_counts_allreduce``, one rank per GPU inside this process) and
+        every GPU corrects its own chunks; records come out in input order.  ``device`` is the single-GPU form."""
         self.assays = _as_assays(assay)
-        self.device = device
+        self.devices = [int(d) for d in devices] if devices else [int(device)]
+        if len(set(self.devices)) != len(self.devices):
+            raise ValueError("devices must be distinct")
+        self.device = self.devices[0]
         # pass 1 reads the FASTQ text on the device (textingest.TextGroupReader) instead of the host record reader;
         # stricter dialect: no blank lines between records
         self.device_parse = bool(device_parse)
@@ -137,12 +149,13 @@ class FastqProcessor:
             for read, info in assay.get_segments_by_modality(modality):
                 if any(e.is_barcode() for e in info) and not read.fastq_paths():
                     raise RuntimeError(f"Failed to open FASTQ file: {read.read_id}")
-            pipe = BarcodePipeline(layout, device=self.device, qc=self.compute_qc)
+            pipes = self._make_pipes(layout)
+            pipe = pipes[0]
             try:
-                for text, results in self._run_assay(pipe, layout, correct_barcode, chunk_size):
+                for text, results in self._run_assay(pipes, layout, correct_barcode, chunk_size):
                     yield layout, pipe, text, results
-                q = pipe.qc()
-                cats += pipe.qc_categories() if self.compute_qc else 0
+                q = sum(pp.qc() for pp in pipes)
+                cats += sum(pp.qc_categories() for pp in pipes) if self.compute_qc else 0
                 if per_file is None:
                     per_file, read_ids = q.copy(), [p.read_id for p in layout.reads]
                 else:                                                                      # QcFastq::extend, keyed by read id
@@ -153,7 +166,8 @@ class FastqProcessor:
                             read_ids.append(p.read_id)
                             per_file = np.vstack([per_file, q[r:r + 1]])
             finally:
-                pipe.close()
+                for pp in pipes:
+                    pp.close()
             out = {}
             defect = {rid: float(per_file[k, 1]) / float(per_file[k, 0]) for k, rid in enumerate(read_ids) if per_file[k, 1] > 0}
             if defect:
@@ -162,7 +176,60 @@ class FastqProcessor:
             out["frac_q30_bases"] = {names[k]: float(cats[k, 2]) / float(cats[k, 1]) for k in range(4) if cats[k, 1] > 0}
             self._qc = out
 
-    def _run_assay(self, pipe: BarcodePipeline, layout: CompiledLayout, correct_barcode: bool, chunk_size: int):
+    def _make_pipes(self, layout: CompiledLayout) -> List[BarcodePipeline]:
+        """One pipeline (ctx, whitelist tables, NCCL rank) per GPU.  ncclCommInitRank waits for all ranks, so the
+        pipelines are created by one thread each (the ctypes calls release the GIL)."""
+        if len(self.devices) == 1:
+            return [BarcodePipeline(layout, device=self.devices[0], qc=self.compute_qc)]
+        import threading
+        uid = BarcodePipeline.new_unique_id()
+        G = len(self.devices)
+        out: List[Optional[BarcodePipeline]] = [None] * G
+        errs: List[BaseException] = []
+
+        def make(g):
+            try:
+                out[g] = BarcodePipeline(layout, device=self.devices[g], nranks=G, rank=g, nccl_uid=uid, qc=self.compute_qc)
+            except BaseException as e:          # noqa: BLE001 - re-raised below
+                errs.append(e)
+        ths = [threading.Thread(target=make, args=(g,)) for g in range(G)]
+        for t in ths:
+            t.start()
+        for t in ths:
+            t.join()
+        if errs:
+            for pp in out:
+                if pp is not None:
+                    pp.close()
+            raise errs[0]
+        return out          # type: ignore[return-value]
+
+    @staticmethod
+    def _allreduce_all(pipes: Sequence[BarcodePipeline]) -> None:
+        """The collective of every rank, issued by one thread per rank (a single thread driving several NCCL ranks
+        one after the other may deadlock)."""
+        if len(pipes) == 1:
+            pipes[0].allreduce()
+            return
+        import threading
+        errs: List[BaseException] = []
+
+        def go(pp):
+            try:
+                pp.allreduce()
+            except BaseException as e:          # noqa: BLE001
+                errs.append(e)
+        ths = [threading.Thread(target=go, args=(pp,)) for pp in pipes]
+        for t in ths:
+            t.start()
+        for t in ths:
+            t.join()
+        if errs:
+            raise errs[0]
+
+    def _run_assay(self, pipes: Sequence[BarcodePipeline], layout: CompiledLayout, correct_barcode: bool, chunk_size: int):
+        pipe = pipes[0]
+        G = len(pipes)
         n_reads = len(layout.reads)
         strides = [pipe.stride(r) for r in range(n_reads)]
         qonly = [bool(pipe.infos[r].qual_only) for r in range(n_reads)]
@@ -170,12 +237,15 @@ class FastqProcessor:
         bases = sum((p.max_len or 100) for p in layout.reads)
         # the reference batches >= chunk_size bases (fastq.rs:406-445); results do not depend on the batching, so the
         # device chunks are at least 256 K read groups to keep launches and allocations few
-        per_chunk = max(262144, int(chunk_size) // max(bases, 1))
+        per_chunk = max(MIN_CHUNK_RECORDS, int(chunk_size) // max(bases, 1))
 
         # pass 1 (BarcodeAnalyzer::new): every batch is uploaded, counted and kept resident on the device
         chunks: List[Chunk] = []
         sizes: List[int] = []
+        owners: List[BarcodePipeline] = []
         if self.device_parse:
+            if G > 1:
+                raise NotImplementedError("device_parse drives one GPU (the text staging buffers belong to one ctx)")
             from .textingest import TextGroupReader
             trdr = TextGroupReader(pipe, files, per_chunk, [2 * (p.max_len or 150) + 80 for p in layout.reads])
             try:
@@ -191,6 +261,7 @@ class FastqProcessor:
                         pipe.qc_accumulate(ch)
                     chunks.append(ch)
                     sizes.append(n)
+                    owners.append(pipe)
             finally:
                 trdr.close()
         rdr = GroupReader(files, strides, qonly, keep_text=False, qual_windows=[pipe.qual_window(r) for r in range(n_reads)])
@@ -200,38 +271,41 @@ class FastqProcessor:
                 if got is None:
                     break
                 n = len(got[0].batch.length)
-                ch = pipe.new_chunk(n)
+                own = pipes[len(chunks) % G]     # chunk k lives on GPU k mod G
+                ch = own.new_chunk(n)
                 ch.reset(n)
                 for r in range(n_reads):
                     ch.upload(r, got[r].batch)
-                pipe.count(ch)
+                own.count(ch)
                 if self.compute_qc:
-                    pipe.qc_accumulate(ch)
-                pipe.sync()                      # the host planes of this batch go out of scope
+                    own.qc_accumulate(ch)
+                own.sync()                       # the host planes of this batch go out of scope
                 chunks.append(ch)
                 sizes.append(n)
+                owners.append(own)
         finally:
             rdr.close()
+        self._allreduce_all(pipes)               # every GPU now holds the counts of the whole input
         # "All whitelists should have the same total read count" (barcode.rs:125-129)
         totals = {pipe.counts(g)[2] for g in range(len(layout.region_ids))}
         if len(totals) > 1:
             raise _ffi.PclError(_ffi.PCL_ERR_INPUT, "All whitelists should have the same total read count")
         self.num_reads = totals.pop() if totals else 0
-        pipe.allreduce()
 
         # pass 2 (AnnotatedFastqReader): correct, fetch, and rebuild the records from a second read of the files
         rdr = GroupReader(files, [0] * n_reads, [False] * n_reads, keep_text=True, qual_windows=[(0, 0)] * n_reads,
                           text_bytes=[2 * max(p.max_len, 1024) + 256 for p in layout.reads])
         try:
-            for ch, n in zip(chunks, sizes):
-                if correct_barcode:
-                    pipe.correct(ch, self.barcode_correct_prob)
+            if correct_barcode:                  # every GPU corrects its chunks while the host re-reads the files
+                for ch, own in zip(chunks, owners):
+                    own.correct(ch, self.barcode_correct_prob)
+            for ch, n, own in zip(chunks, sizes, owners):
                 results = [ch.fetch(r) for r in range(n_reads)]
                 text = rdr.next(n)
                 assert text is not None and len(text[0].batch.length) == n
                 yield text, results
                 ch.close()
-                pipe.chunks.remove(ch)
+                own.chunks.remove(ch)
         finally:
             rdr.close()
 
@@ -294,7 +368,8 @@ class FastqProcessor:
         return out
 
 
-def make_fastq(assay, *, modality: str, out_dir, correct_barcode: bool = False, device: int = 0) -> None:
+def make_fastq(assay, *, modality: str, out_dir, correct_barcode: bool = False, device: int = 0,
+               devices: Optional[Sequence[int]] = None) -> None:
     """Generate consolidated fastq files from the sequencing specification.
 
     The barcodes and UMIs are concatenated to the read 1 sequence; fixed sequences and linkers are removed
@@ -302,7 +377,7 @@ def make_fastq(assay, *, modality: str, out_dir, correct_barcode: bool = False, 
     ``correct_barcode`` reads whose barcode cannot be corrected are dropped and the corrected sequence is written.
     """
     from . import _zstd
-    proc = FastqProcessor(assay, device=device).with_modality(modality)
+    proc = FastqProcessor(assay, device=device, devices=devices).with_modality(modality)
     out_dir = os.fspath(out_dir)
     os.makedirs(out_dir, exist_ok=True)
     paired = proc.is_paired_end()

@@ -152,6 +152,50 @@ def test_gen_barcoded_fastq_matches_oracle(dataset, correct, device_parse):
     assert qc.get("frac_reads_with_misformed_structure", {}) == want_defect and want_defect
 
 
+def test_gen_barcoded_fastq_on_two_gpus(dataset, tmp_path, monkeypatch):
+    """FastqProcessor(devices=[0, 1]): chunks dealt out over two GPUs, one NCCL all-reduce of the counts inside the
+    process, records in input order and equal to the oracle; make_fastq(devices=...) writes the same bytes as one GPU."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs at least two GPUs")
+    from precellar_b200 import Assay, _zstd
+    from precellar_b200 import api
+    from precellar_b200.api import FastqProcessor, make_fastq
+    monkeypatch.setattr(api, "MIN_CHUNK_RECORDS", 700)                       # 5000 records -> 8 chunks, 4 per GPU
+    proc = FastqProcessor(dataset["assay"], devices=[0, 1]).with_modality("rna").with_barcode_correct_prob(0.9)
+    got = []
+    n_batches = 0
+    for batch in proc.gen_barcoded_fastq(True, chunk_size=60_000):          # several chunks per GPU
+        got.extend(batch)
+        n_batches += 1
+    assert n_batches >= 4
+    layout, ores = oracle_lines(dataset["assay"], dataset["full"], True, 0.9)
+    want = [ln for ln in ores.lines if ln]
+    assert len(got) == len(want) > 3000
+    for rec, line in zip(got, want):
+        f = line.split("\t")
+        mine = [rec.barcode.raw.sequence, rec.barcode.raw.quality, rec.barcode.corrected if rec.barcode.corrected is not None else b"*",
+                rec.umi.sequence if rec.umi else b"", rec.umi.quality if rec.umi else b"",
+                rec.read1.sequence if rec.read1 else b"", rec.read1.quality if rec.read1 else b"",
+                rec.read2.sequence if rec.read2 else b"", rec.read2.quality if rec.read2 else b""]
+        assert [m.decode("latin-1") for m in mine] == f
+    per = ores.qc_per_file
+    want_defect = {rid: per[r, 1] / per[r, 0] for r, rid in enumerate(("R1", "R2")) if per[r, 1] > 0}
+    assert proc.get_fastq_qc().get("frac_reads_with_misformed_structure", {}) == want_defect
+    # make_fastq: the forward-insert variant of the spec (R1.fq.zst only), one GPU against two
+    td = dataset["td"]
+    spec = write_spec(td, None, None, forward_insert=True)
+    outs = []
+    for k, devs in enumerate(([0], [0, 1])):
+        a = Assay(spec)
+        a.update_read("R1", fastq=[os.path.join(td, "R1_a.fq.gz"), os.path.join(td, "R1_b.fq")])
+        a.update_read("R2", fastq=os.path.join(td, "R2.fq.gz"))
+        out = str(tmp_path / f"out{k}")
+        make_fastq(a, modality="rna", out_dir=out, correct_barcode=True, devices=devs)
+        outs.append(_zstd.decompress_file(os.path.join(out, "R1.fq.zst")))
+    assert outs[0] == outs[1] and len(outs[0]) > 100_000
+
+
 def test_make_fastq(dataset, tmp_path):
     """R1.fq.zst = corrected barcode + UMI + read1 (python/src/lib.rs:153-163); the insert is read on the pos strand."""
     import copy
