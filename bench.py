@@ -600,6 +600,27 @@ def main():
                                "the neighbourhood tables replace by four (kept for reference only)"},
     }
 
+    # ------------------------------------------------------------------ downstream grouping of the resident shard
+    grouping = None
+    if not args.no_other:
+        import ctypes as C
+        L = _ffi.lib()
+        best = None
+        for _ in range(3):
+            pipe.sync()
+            t0 = time.perf_counter()
+            h = C.c_void_p()
+            _ffi.check(pipe.ctx, L.pcl_group_build(pipe.ctx, big.h, None, C.byref(h)))       # blocks until the outputs exist
+            dt = time.perf_counter() - t0
+            gi = _ffi.GroupInfo()
+            L.pcl_group_info_get(h, C.byref(gi))
+            L.pcl_group_destroy(h)
+            best = dt if best is None else min(best, dt)
+        grouping = {"read_groups": n, "assigned": int(gi.n_assigned), "barcodes": int(gi.n_barcodes), "duplicate_sets": int(gi.n_fragments),
+                    "ms": best * 1e3, "read_groups_per_s": n / best,
+                    "note": "pcl_group_build on the resident shard after pass 2: stable device radix sort on (corrected barcode, UMI), "
+                            "barcode boundaries and duplicate sets; host clock around the blocking call (allocations included)"}
+
     # ------------------------------------------------------------------ end to end from pinned host memory
     e2e = None
     if not args.no_e2e:
@@ -735,7 +756,7 @@ def main():
                        "l2": "inputs (6.3 GB per GPU) are far larger than L2; no flush needed"},
             "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": int(launches),
             "clocks": clocks.summary(), "sustained": sustained, "parity": parity, "host_cores": host_cores, "host_ingest": ingest,
-            "other_configs": other,
+            "other_configs": other, "grouping": grouping,
             "setup_s": {"pipeline_create_incl_whitelist_tables": t_setup},
         }
         emit(out)

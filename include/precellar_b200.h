@@ -311,6 +311,33 @@ int pcl_gzsrc_is_bgzf(const pcl_gzsrc *src);
 const char *pcl_gzsrc_error(const pcl_gzsrc *src);
 void pcl_gzsrc_close(pcl_gzsrc *src);
 
+/* ---- per-barcode grouping of a chunk ---------------------------------------------
+ * The first data-parallel step behind the aligner, keyed on this path's output:
+ *   sort_by_barcode + chunk_by(barcode)          precellar/src/fragment/mod.rs:359-363,434-455
+ *   RemoveDuplicates::remove_duplicates          precellar/src/fragment/dedups.rs:320-340 (FingerPrint: dedups.rs:52-66)
+ * pcl_group_build (after pcl_count / pcl_correct) sorts the read groups of the chunk whose barcode is assigned -- every
+ * present barcode segment EXACT or CORRECTED, i.e. the read carries a CB tag made of whitelist entries -- stably on
+ * (barcode, fingerprint, UMI) with a radix sort on the device.  (Raw barcodes that are not whitelist members may hold
+ * non-ACGT bytes, which the packed keys do not keep: they are not grouped.)
+ *   fingerprint  one 64-bit word per read group (host pointer, n values) with whatever the aligner contributes to
+ *                dedups.rs's FingerPrint (reference id, 5' coordinates, orientation), or NULL: barcode + UMI only
+ *   order        [n_assigned]       record indices in sorted order; ties keep input order
+ *   frag_start   [n_fragments + 1]  positions in `order` where a run of equal (barcode, fingerprint, UMI) starts: a
+ *                duplicate set.  order[frag_start[f]] is the record the reference keeps, frag_start[f+1] - frag_start[f]
+ *                its Fragment.count
+ *   bc_frag_start[n_barcodes + 1]   first fragment of every barcode, barcodes in the reference's (byte-string) order
+ *   bc_key       [n_barcodes]       the barcode: 2 bits per base left-aligned in bits 63..6, its length in bits 4..0
+ *                (pcl_group_key_decode); multi-segment barcodes are concatenated in join order
+ * UMIs are compared as byte strings over A C G T N; a read group whose UMI holds any other byte is not grouped
+ * (n_ungroupable).  Barcodes longer than 29 bases and UMIs longer than 19 are PCL_ERR_UNSUPPORTED / ungroupable. */
+typedef struct pcl_group pcl_group;
+typedef struct { uint64_t n_records, n_assigned, n_ungroupable, n_barcodes, n_fragments; } pcl_group_info;
+int pcl_group_build(pcl_ctx *ctx, pcl_chunk *chunk, const uint64_t *fingerprint, pcl_group **out);
+int pcl_group_info_get(const pcl_group *g, pcl_group_info *out);
+int pcl_group_fetch(pcl_group *g, uint32_t *order, uint32_t *frag_start, uint32_t *bc_frag_start, uint64_t *bc_key);
+int pcl_group_key_decode(uint64_t key, char *out32);
+int pcl_group_destroy(pcl_group *g);
+
 /* ---- pinned host memory ------------------------------------------------------------------- */
 void *pcl_host_alloc(uint64_t bytes);
 void pcl_host_free(void *p);

@@ -58,6 +58,11 @@ class HostRead(C.Structure):
     _fields_ = [("text", C.c_void_p), ("off", C.c_void_p), ("len", C.c_void_p), ("res", ReadResults)]
 
 
+class GroupInfo(C.Structure):
+    _fields_ = [("n_records", C.c_uint64), ("n_assigned", C.c_uint64), ("n_ungroupable", C.c_uint64),
+                ("n_barcodes", C.c_uint64), ("n_fragments", C.c_uint64)]
+
+
 class PclError(RuntimeError):
     def __init__(self, code: int, msg: str):
         super().__init__(f"precellar_b200 error {code}: {msg}")
@@ -79,6 +84,7 @@ SYMBOLS = [
     "pcl_text_scan", "pcl_text_lines", "pcl_text_fill", "pcl_text_names_check", "pcl_text_line_ends",
     "pcl_chunk_upload_compact", "pcl_read_payload_bytes",
     "pcl_gzsrc_open", "pcl_gzsrc_read", "pcl_gzsrc_is_bgzf", "pcl_gzsrc_error", "pcl_gzsrc_close",
+    "pcl_group_build", "pcl_group_info_get", "pcl_group_fetch", "pcl_group_key_decode", "pcl_group_destroy",
 ]
 
 _lib = None
@@ -148,6 +154,11 @@ def lib() -> C.CDLL:
         "pcl_gzsrc_is_bgzf": (i32, [vp]),
         "pcl_gzsrc_error": (C.c_char_p, [vp]),
         "pcl_gzsrc_close": (None, [vp]),
+        "pcl_group_build": (i32, [vp, vp, vp, C.POINTER(vp)]),
+        "pcl_group_info_get": (i32, [vp, C.POINTER(GroupInfo)]),
+        "pcl_group_fetch": (i32, [vp, vp, vp, vp, vp]),
+        "pcl_group_key_decode": (i32, [u64, C.c_char_p]),
+        "pcl_group_destroy": (i32, [vp]),
         "pcl_fastq_open": (i32, [C.POINTER(C.c_char_p), i32, C.POINTER(vp)]),
         "pcl_fastq_close": (None, [vp]),
         "pcl_fastq_error": (C.c_char_p, [vp]),

@@ -20,6 +20,7 @@
 #include "host_build.h"
 #include "kernels.cuh"
 #include "textparse.cuh"
+#include "group.cuh"
 
 // ------------------------------------------------------------------------------------------
 // NCCL through dlopen: the library has no link-time dependency on libnccl, and inside a process
@@ -1327,6 +1328,233 @@ int pcl_make_fastq_batch(pcl_ctx *ctx, const pcl_host_read *reads, uint64_t n, i
     *r1_used = u1;
     if (r2_used) *r2_used = u2;
     if (n_written) *n_written = written;
+    return PCL_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// per-barcode grouping (group.cuh)
+// ------------------------------------------------------------------------------------------
+}  // extern "C"
+
+struct pcl_group {
+    pcl_ctx *ctx = nullptr;
+    pcl_group_info info{};
+    uint32_t *d_order = nullptr, *d_frag_start = nullptr, *d_bc_frag_start = nullptr;
+    unsigned long long *d_bc_key = nullptr;
+    std::vector<void *> allocs;
+};
+
+namespace {
+
+// exclusive scan of n uint32 (out may alias in); *d_total receives the sum.  tmp: (n / PCL_SCAN_TILE + 1) uint32.
+int device_scan(pcl_ctx *ctx, cudaStream_t s, const uint32_t *in, uint32_t *out, uint64_t n, uint32_t *tmp, unsigned long long *d_total) {
+    const uint64_t tiles = (n + PCL_SCAN_TILE - 1) / PCL_SCAN_TILE;
+    if (tiles == 0) { CU(ctx, cudaMemsetAsync(d_total, 0, 8, s)); return PCL_OK; }
+    k_scan_tile_sums<<<(unsigned)tiles, 256, 0, s>>>(in, n, tmp);
+    k_scan_sums<<<1, 256, 0, s>>>(tmp, tiles, d_total);
+    k_scan_apply<<<(unsigned)tiles, 256, 0, s>>>(in, out, n, tmp);
+    ctx->launches += 3;
+    CU(ctx, cudaGetLastError());
+    return PCL_OK;
+}
+
+// stable sort of (keys, vals) on the bytes of the keys named by byte_mask; the result is in *keys / *vals (the buffers swap)
+int device_radix_sort(pcl_ctx *ctx, cudaStream_t s, unsigned long long **keys, uint32_t **vals, unsigned long long **keys_tmp,
+                      uint32_t **vals_tmp, uint64_t n, uint32_t byte_mask, uint32_t *hist, uint32_t *scan_tmp, unsigned long long *d_scratch) {
+    const uint32_t n_ctas = (uint32_t)((n + PCL_SORT_TILE - 1) / PCL_SORT_TILE);
+    if (n_ctas == 0) return PCL_OK;
+    for (uint32_t b = 0; b < 8; ++b) {
+        if (!((byte_mask >> b) & 1u)) continue;
+        k_radix_hist<<<n_ctas, PCL_SORT_BLOCK, 0, s>>>(*keys, n, 8u * b, hist, n_ctas);
+        ctx->launches += 1;
+        if (int rc = device_scan(ctx, s, hist, hist, 256ull * n_ctas, scan_tmp, d_scratch)) return rc;
+        k_radix_scatter<<<n_ctas, PCL_SORT_BLOCK, 0, s>>>(*keys, *vals, *keys_tmp, *vals_tmp, n, 8u * b, hist, n_ctas);
+        ctx->launches += 1;
+        CU(ctx, cudaGetLastError());
+        std::swap(*keys, *keys_tmp);
+        std::swap(*vals, *vals_tmp);
+    }
+    return PCL_OK;
+}
+
+uint32_t bytes_used(unsigned long long or_of_keys) {
+    uint32_t m = 0;
+    for (uint32_t b = 0; b < 8; ++b) if ((or_of_keys >> (8 * b)) & 0xFFull) m |= 1u << b;
+    return m;
+}
+
+}  // namespace
+
+extern "C" {
+
+int pcl_group_build(pcl_ctx *ctx, pcl_chunk *c, const uint64_t *fingerprint, pcl_group **out) {
+    if (!out) return PCL_ERR_ARG;
+    *out = nullptr;
+    if (int r = check_ready(ctx, c)) return r;
+    if (int r = bind(ctx)) return r;
+    const uint64_t n = c->n;
+    if (n >= (1ull << 32) - 1) return fail(ctx, PCL_ERR_ARG, "chunk too large for 32-bit record indices");
+    GroupKeyParams p;
+    memset(&p, 0, sizeof p);
+    int umi_read = -1;
+    for (int r = 0; r < ctx->n_reads; ++r) {
+        const pcl_read_info &inf = ctx->infos[r];
+        const pcl_read_desc &rd = ctx->descs[r];
+        for (int j = 0; j < inf.n_bc; ++j) {
+            if (p.n_seg >= PCL_GROUP_MAX_SEG) return fail(ctx, PCL_ERR_UNSUPPORTED, "more than %d barcode segments", PCL_GROUP_MAX_SEG);
+            const pcl_elem_desc &el = rd.elems[inf.bc_elem[j]];
+            GroupSeg &g = p.seg[p.n_seg++];
+            g.key = c->rb[r].bc_key[j];
+            g.fstatus = c->rb[r].fstatus;
+            g.key_bytes = inf.bc_key_bytes[j];
+            g.j = (uint8_t)j;
+            g.fixed_len = (inf.bc_key_bytes[j] == 4 && el.min_len == 16 && el.max_len == 16) ? 16 : 0;
+        }
+        if (inf.n_umi) {
+            if (umi_read >= 0) return fail(ctx, PCL_ERR_UNSUPPORTED, "grouping supports UMIs in one read file");
+            umi_read = r;
+        }
+    }
+    if (p.n_seg == 0) return fail(ctx, PCL_ERR_ARG, "the layout has no barcode");
+    if (umi_read >= 0) {
+        const pcl_read_info &inf = ctx->infos[umi_read];
+        const pcl_read_desc &rd = ctx->descs[umi_read];
+        const DRead &d = ctx->dreads[umi_read];
+        const ReadBuf &b = c->rb[umi_read];
+        const int ju = inf.n_umi - 1;                                            // the last UMI segment of a file wins (fastq.rs:502)
+        const pcl_elem_desc &el = rd.elems[inf.umi_elem[ju]];
+        p.useq = b.seq; p.ulen = b.len; p.ufstatus = b.fstatus;
+        p.ucoord = inf.fixed_layout ? nullptr : b.ucoord[ju];
+        p.ustride = d.stride; p.umax_len = d.max_len;
+        p.ustart = inf.static_start[inf.umi_elem[ju]]; p.ubases = el.max_len; p.umin = el.min_len;
+        if (p.ustart + p.ubases > d.stride && inf.fixed_layout) return fail(ctx, PCL_ERR_UNSUPPORTED, "UMI outside the uploaded record bytes");
+    }
+    p.n = n;
+
+    pcl_group *g = new pcl_group();
+    g->ctx = ctx;
+    g->info.n_records = n;
+    cudaStream_t s = c->stream;
+    int rc = PCL_OK;
+    auto A = [&](void **ptr, size_t bytes) {
+        if (rc != PCL_OK) return;
+        cudaError_t e = cudaMalloc(ptr, bytes ? bytes : 16);
+        if (e != cudaSuccess) { rc = fail(ctx, e == cudaErrorMemoryAllocation ? PCL_ERR_NOMEM : PCL_ERR_CUDA, "cudaMalloc(%zu): %s", bytes, cudaGetErrorString(e)); return; }
+        g->allocs.push_back(*ptr);
+    };
+    unsigned long long *d_bc = nullptr, *d_umi = nullptr, *d_fp = nullptr, *kA = nullptr, *kB = nullptr, *d_stats = nullptr;
+    uint32_t *pA = nullptr, *pB = nullptr, *hist = nullptr, *scan_tmp = nullptr;
+    const uint64_t n_ctas = (n + PCL_SORT_TILE - 1) / PCL_SORT_TILE;
+    A((void **)&d_bc, n * 8); A((void **)&d_umi, n * 8); A((void **)&kA, n * 8); A((void **)&kB, n * 8);
+    A((void **)&pA, n * 4); A((void **)&pB, n * 4);
+    A((void **)&hist, 256 * n_ctas * 4 + 16); A((void **)&scan_tmp, (256 * n_ctas / PCL_SCAN_TILE + n / PCL_SCAN_TILE + 4) * 4);
+    A((void **)&d_stats, 8 * 8);
+    if (fingerprint) A((void **)&d_fp, n * 8);
+    auto cleanup = [&](int code) { for (void *q : g->allocs) cudaFree(q); delete g; return code; };
+    if (rc != PCL_OK) return cleanup(rc);
+#define GCU(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return cleanup(fail(ctx, PCL_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(e_))); } while (0)
+    GCU(cudaMemsetAsync(d_stats, 0, 64, s));
+    if (fingerprint) GCU(cudaMemcpyAsync(d_fp, fingerprint, n * 8, cudaMemcpyHostToDevice, s));
+    p.bc_key = d_bc; p.umi_key = d_umi; p.perm = pA; p.stats = d_stats;
+    unsigned long long st[8] = {0};
+    if (n) {
+        k_group_keys<<<grid_for(ctx, n, 8), 256, 0, s>>>(p);
+        ctx->launches += 1;
+        GCU(cudaGetLastError());
+        GCU(cudaMemcpyAsync(st, d_stats, 64, cudaMemcpyDeviceToHost, s));
+        GCU(cudaStreamSynchronize(s));
+    }
+    g->info.n_assigned = st[0];
+    g->info.n_ungroupable = st[1];
+    // three stable sorts, least significant key first: UMI, fingerprint, barcode
+    if (n) {
+        if (p.useq && st[3]) {
+            k_group_gather<<<grid_for(ctx, n, 8), 256, 0, s>>>(d_umi, pA, kA, n, nullptr);
+            ctx->launches += 1;
+            if (int r2 = device_radix_sort(ctx, s, &kA, &pA, &kB, &pB, n, bytes_used(st[3]), hist, scan_tmp, d_stats + 4)) return cleanup(r2);
+        }
+        if (fingerprint) {
+            GCU(cudaMemsetAsync(d_stats + 5, 0, 8, s));
+            k_group_gather<<<grid_for(ctx, n, 8), 256, 0, s>>>(d_fp, pA, kA, n, d_stats + 5);
+            ctx->launches += 1;
+            unsigned long long orfp = 0;
+            GCU(cudaMemcpyAsync(&orfp, d_stats + 5, 8, cudaMemcpyDeviceToHost, s));
+            GCU(cudaStreamSynchronize(s));
+            if (int r2 = device_radix_sort(ctx, s, &kA, &pA, &kB, &pB, n, bytes_used(orfp), hist, scan_tmp, d_stats + 4)) return cleanup(r2);
+        }
+        k_group_gather<<<grid_for(ctx, n, 8), 256, 0, s>>>(d_bc, pA, kA, n, nullptr);
+        ctx->launches += 1;
+        // unassigned read groups carry the all-ones key: byte 0 tells them from every real key, so it is always sorted
+        if (int r2 = device_radix_sort(ctx, s, &kA, &pA, &kB, &pB, n, bytes_used(st[2]) | 1u, hist, scan_tmp, d_stats + 4)) return cleanup(r2);
+    }
+    const uint64_t na = g->info.n_assigned;
+    uint32_t *head_bc = nullptr, *head_frag = nullptr, *bc_id = nullptr, *frag_id = nullptr;
+    A((void **)&head_bc, na * 4); A((void **)&head_frag, na * 4); A((void **)&bc_id, na * 4); A((void **)&frag_id, na * 4);
+    if (rc != PCL_OK) return cleanup(rc);
+    unsigned long long tot[2] = {0, 0};
+    if (na) {
+        k_group_flags<<<grid_for(ctx, na, 8), 256, 0, s>>>(kA, pA, d_umi, d_fp, na, head_bc, head_frag);
+        ctx->launches += 1;
+        if (int r2 = device_scan(ctx, s, head_bc, bc_id, na, scan_tmp, d_stats + 6)) return cleanup(r2);
+        if (int r2 = device_scan(ctx, s, head_frag, frag_id, na, scan_tmp, d_stats + 7)) return cleanup(r2);
+        GCU(cudaMemcpyAsync(tot, d_stats + 6, 16, cudaMemcpyDeviceToHost, s));
+        GCU(cudaStreamSynchronize(s));
+    }
+    g->info.n_barcodes = tot[0];
+    g->info.n_fragments = tot[1];
+    A((void **)&g->d_frag_start, (tot[1] + 1) * 4); A((void **)&g->d_bc_frag_start, (tot[0] + 1) * 4); A((void **)&g->d_bc_key, (tot[0] + 1) * 8);
+    if (rc != PCL_OK) return cleanup(rc);
+    if (na) {
+        k_group_emit<<<grid_for(ctx, na, 8), 256, 0, s>>>(kA, head_bc, head_frag, bc_id, frag_id, na, g->d_frag_start, g->d_bc_frag_start, g->d_bc_key);
+        ctx->launches += 1;
+        GCU(cudaGetLastError());
+    }
+    const uint32_t end_frag = (uint32_t)na, end_bc = (uint32_t)tot[1];
+    GCU(cudaMemcpyAsync(g->d_frag_start + tot[1], &end_frag, 4, cudaMemcpyHostToDevice, s));
+    GCU(cudaMemcpyAsync(g->d_bc_frag_start + tot[0], &end_bc, 4, cudaMemcpyHostToDevice, s));
+    GCU(cudaStreamSynchronize(s));
+#undef GCU
+    g->d_order = pA;
+    // the scratch buffers are no longer needed: keep only what pcl_group_fetch hands out
+    for (void *q : g->allocs)
+        if (q != (void *)g->d_order && q != (void *)g->d_frag_start && q != (void *)g->d_bc_frag_start && q != (void *)g->d_bc_key) cudaFree(q);
+    g->allocs = {(void *)g->d_order, (void *)g->d_frag_start, (void *)g->d_bc_frag_start, (void *)g->d_bc_key};
+    *out = g;
+    return PCL_OK;
+}
+
+int pcl_group_info_get(const pcl_group *g, pcl_group_info *out) {
+    if (!g || !out) return PCL_ERR_ARG;
+    *out = g->info;
+    return PCL_OK;
+}
+
+int pcl_group_fetch(pcl_group *g, uint32_t *order, uint32_t *frag_start, uint32_t *bc_frag_start, uint64_t *bc_key) {
+    if (!g) return PCL_ERR_ARG;
+    pcl_ctx *ctx = g->ctx;
+    if (int r = bind(ctx)) return r;
+    if (order && g->info.n_assigned) CU(ctx, cudaMemcpy(order, g->d_order, g->info.n_assigned * 4, cudaMemcpyDeviceToHost));
+    if (frag_start) CU(ctx, cudaMemcpy(frag_start, g->d_frag_start, (g->info.n_fragments + 1) * 4, cudaMemcpyDeviceToHost));
+    if (bc_frag_start) CU(ctx, cudaMemcpy(bc_frag_start, g->d_bc_frag_start, (g->info.n_barcodes + 1) * 4, cudaMemcpyDeviceToHost));
+    if (bc_key && g->info.n_barcodes) CU(ctx, cudaMemcpy(bc_key, g->d_bc_key, g->info.n_barcodes * 8, cudaMemcpyDeviceToHost));
+    return PCL_OK;
+}
+
+int pcl_group_key_decode(uint64_t key, char *out32) {
+    if (!out32 || key == PCL_GROUP_NOKEY) return -1;
+    const int L = (int)(key & 31ull);
+    if (L > 29) return -1;
+    static const char B[4] = {'A', 'C', 'G', 'T'};
+    for (int k = 0; k < L; ++k) out32[k] = B[(key >> (62 - 2 * k)) & 3ull];
+    out32[L] = 0;
+    return L;
+}
+
+int pcl_group_destroy(pcl_group *g) {
+    if (!g) return PCL_OK;
+    cudaSetDevice(g->ctx->device);
+    for (void *q : g->allocs) cudaFree(q);
+    delete g;
     return PCL_OK;
 }
 

@@ -38,6 +38,27 @@ class ReadResults:
     ucoord: List[Optional[np.ndarray]]
 
 
+@dataclass
+class GroupResult:
+    """Per-barcode grouping of one chunk (pcl_group_*).  Fragment f = records order[frag_start[f]:frag_start[f+1]] (a
+    duplicate set; the first one is kept, the length is Fragment.count); barcode b = fragments
+    bc_frag_start[b]:bc_frag_start[b+1], barcodes in byte-string order."""
+    n_records: int
+    n_assigned: int
+    n_ungroupable: int
+    order: np.ndarray
+    frag_start: np.ndarray
+    bc_frag_start: np.ndarray
+    bc_key: np.ndarray
+
+    def barcode(self, b: int) -> bytes:
+        buf = C.create_string_buffer(40)
+        n = lib().pcl_group_key_decode(int(self.bc_key[b]), buf)
+        if n < 0:
+            raise ValueError("not a group key")
+        return buf.raw[:n]
+
+
 class Chunk:
     def __init__(self, pipe: "BarcodePipeline", capacity: int):
         self.pipe = pipe
@@ -331,6 +352,30 @@ class BarcodePipeline:
         names = ("umi", "barcode", "read1", "read2")
         out["frac_q30_bases"] = {names[k]: float(cat[k, 2]) / float(cat[k, 1]) for k in range(4) if cat[k, 1] > 0}
         return out
+
+    # -- downstream grouping ---------------------------------------------------------------------------
+    def group(self, chunk: Chunk, fingerprint: Optional[np.ndarray] = None) -> "GroupResult":
+        """Sort the chunk's assigned read groups by (barcode, fingerprint, UMI) on the device and mark the duplicate
+        sets: sort_by_barcode + chunk_by(barcode) + remove_duplicates of the reference (precellar/src/fragment/mod.rs:
+        359-363,434-455, fragment/dedups.rs:320-340).  ``fingerprint``: one uint64 per read group with the aligner's
+        part of the FingerPrint (reference id, 5' coordinates, orientation), or None."""
+        fp = None
+        if fingerprint is not None:
+            fp = np.ascontiguousarray(fingerprint, dtype=np.uint64)
+            assert len(fp) == chunk.n
+        h = C.c_void_p()
+        check(self.ctx, lib().pcl_group_build(self.ctx, chunk.h, fp.ctypes.data if fp is not None else None, C.byref(h)))
+        try:
+            info = _ffi.GroupInfo()
+            check(self.ctx, lib().pcl_group_info_get(h, C.byref(info)))
+            order = np.empty(info.n_assigned, np.uint32)
+            frag_start = np.empty(info.n_fragments + 1, np.uint32)
+            bc_frag_start = np.empty(info.n_barcodes + 1, np.uint32)
+            bc_key = np.empty(info.n_barcodes, np.uint64)
+            check(self.ctx, lib().pcl_group_fetch(h, order.ctypes.data, frag_start.ctypes.data, bc_frag_start.ctypes.data, bc_key.ctypes.data))
+        finally:
+            lib().pcl_group_destroy(h)
+        return GroupResult(int(info.n_records), int(info.n_assigned), int(info.n_ungroupable), order, frag_start, bc_frag_start, bc_key)
 
     # -- instrumentation -----------------------------------------------------------------------------
     def profile_enable(self, on: bool = True) -> None:

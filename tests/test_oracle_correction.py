@@ -91,3 +91,17 @@ def test_fp64_sum_order():
         total += x
     code, idx, prob = O.correct_one(wl, cnt, b"GC", q, threshold=0.1)
     assert idx == 0 and prob == likes[0] / total
+
+
+def test_grouping_restatement_hand_case():
+    """oracle/grouping.py on a hand-computed case: byte-string barcode order (a proper prefix first), first read of a
+    duplicate set kept, counts per (fingerprint, UMI) -- fragment/mod.rs:359-363,434-455, fragment/dedups.rs:320-340."""
+    from oracle.grouping import group_reference
+    bcs = [b"ACGT", None, b"ACG", b"ACGT", b"TTTT", b"ACGT", b"ACG", b"ACGT"]
+    umis = [b"AA", b"AA", b"CC", b"AA", None, b"AN", b"CC", b"AA"]
+    fps = [7, 7, 1, 7, 0, 7, 2, 8]
+    out = group_reference(bcs, umis, fps)
+    assert [b for b, _ in out] == [b"ACG", b"ACGT", b"TTTT"]
+    assert out[0][1] == {(1, b"CC"): [2, 1], (2, b"CC"): [6, 1]}
+    assert out[1][1] == {(7, b"AA"): [0, 2], (7, b"AN"): [5, 1], (8, b"AA"): [7, 1]}
+    assert out[2][1] == {(0, None): [4, 1]}
