@@ -72,6 +72,13 @@ struct AnchorPlan {
     uint8_t has_t;                   // the last element is variable too
     uint8_t t_elem;                  // the (only) target element, 0xFF if none
     uint8_t ustart[PCL_MAX_ELEMS];   // start of element e when the variable element has its minimal length
+    // straight-line path for records long enough to hold every element at every anchor position (pcl_plan_record_fast)
+    uint8_t n_pos;                   // anchor positions inside its window: vmax - vmin + 1
+    uint8_t a_start;                 // first window position: ustart[v] + vmin
+    uint8_t a_len, a_maxmis;         // anchor length and tolerated mismatches
+    uint16_t full_len;               // such records have L >= full_len
+    uint8_t n_words;                 // record words the fields can touch: ceil((full_len or stride) / 4), <= 16
+    uint8_t bc_elem[PCL_MAX_BC_PER_READ], umi_elem[PCL_MAX_UMI_PER_READ];
 };
 
 struct DRead {
@@ -1199,6 +1206,118 @@ PCL_HD uint32_t pcl_anchor_key(const DRead &rd, const Codes32 &k, const uint32_t
     }
     if (wlen < 16u) key |= 1u << (2u * wlen);
     return key;
+}
+
+// What pass 1 derives from one record of an AnchorPlan layout (keys in their 4-byte device form).
+struct PlanOut {
+    uint32_t status;                                   // PCL_SPLIT_*
+    uint32_t tcoord;                                   // (start << 16) | len of the target, or PCL_COORD_ABSENT
+    uint32_t bcoord[PCL_MAX_BC_PER_READ], bkey[PCL_MAX_BC_PER_READ], bninv[PCL_MAX_BC_PER_READ], bipos[PCL_MAX_BC_PER_READ];
+    uint32_t ucoord[PCL_MAX_UMI_PER_READ], ukey[PCL_MAX_UMI_PER_READ];
+};
+
+// The general route: element-by-element walk (pcl_anchor_split) and per-element coordinates, any record length.
+template <bool kRev>
+PCL_HD void pcl_plan_record(const DRead &rd, const uint32_t *w, uint32_t L, PlanOut &o) {
+    const uint32_t nbytes = L < rd.stride ? L : rd.stride;
+    Codes32 k;
+    pcl_codes32_t<kRev>(w, (int)((nbytes + 3u) >> 2), k);
+    AnchorSplit sp;
+    pcl_anchor_split(rd, k, L, sp);
+    uint32_t c2[4], bd2[4];                                 // the strings behind the anchor, at uniform offsets
+    pcl_shr_bases(k.c, sp.pos, c2);
+    pcl_shr_bases(k.bd, sp.pos, bd2);
+    o.status = sp.status;
+    o.tcoord = (rd.has_target && rd.plan.t_elem != 0xFFu) ? pcl_anchor_coord(rd, sp, rd.plan.t_elem) : PCL_COORD_ABSENT;
+    for (uint32_t j = 0; j < rd.n_bc; ++j) {
+        const uint32_t e = rd.plan.bc_elem[j], c = pcl_anchor_coord(rd, sp, e);
+        o.bcoord[j] = c; o.bkey[j] = 0; o.bninv[j] = 0; o.bipos[j] = 0;
+        if (c != PCL_COORD_ABSENT) o.bkey[j] = pcl_anchor_key(rd, k, c2, bd2, e, c, &o.bninv[j], &o.bipos[j]);
+    }
+    for (uint32_t j = 0; j < rd.n_umi; ++j) {
+        const uint32_t e = rd.plan.umi_elem[j], c = pcl_anchor_coord(rd, sp, e);
+        o.ucoord[j] = c; o.ukey[j] = PCL_KEY_ABSENT32;
+        if (c != PCL_COORD_ABSENT) {
+            uint32_t ninv;
+            const uint32_t key = pcl_anchor_key(rd, k, c2, bd2, e, c, &ninv);
+            o.ukey[j] = ninv ? 0u : key;
+        }
+    }
+}
+
+// Key of bases [start, start + len) of a code string (len <= 16) with its flag string: device form, invalid bases read
+// as 0; `start` must be the same in every lane of the warp.
+PCL_HD uint32_t pcl_plan_key(const uint32_t *c, const uint32_t *bd, uint32_t start, uint32_t len, bool rev, uint32_t *n_invalid, uint32_t *inv_pos) {
+    if (len == 0u) { *n_invalid = 0; *inv_pos = 0; return 1u; }
+    const uint32_t f = pcl_win32u(c, start, len), bad = pcl_win32u(bd, start, len);
+    pcl_flags_to_inv(bad, len, rev, n_invalid, inv_pos);
+    uint32_t key = pcl_field32_to_key(f, len, rev, bad);
+    if (len < 16u) key |= 1u << (2u * len);
+    return key;
+}
+
+// The same results for a record that holds every element whatever the anchor position (L >= plan.full_len): no walk,
+// no per-element bounds, only the words the fields can touch are converted.  Returns false for shorter records.
+template <bool kRev>
+PCL_HD bool pcl_plan_record_fast(const DRead &rd, const uint32_t *w, uint32_t L, PlanOut &o) {
+    const AnchorPlan &pl = rd.plan;
+    if (L < pl.full_len) return false;
+    Codes32 k;
+    pcl_codes32_t<kRev>(w, (int)pl.n_words, k);
+    // find_best_pattern_match over the n_pos window positions (leftmost strict minimum; segment.rs:496-535)
+    const uint32_t m = pl.a_len, v = pl.v, a = v + 1u;
+    const uint32_t needle = (uint32_t)(kRev ? rd.elems[a].a_rc : rd.elems[a].a_code);
+    const uint32_t even = m >= 16u ? 0x55555555u : (0x55555555u & ((1u << (2u * m)) - 1u));
+    uint32_t best = 0xFFFFFFFFu, bpos = 0;
+    for (uint32_t i = 0; i < pl.n_pos; ++i) {
+        const uint32_t p = pl.a_start + (kRev ? pl.n_pos - 1u - i : i);              // neg strand: position i of rev_compl(window)
+        const uint32_t x = pcl_win32u(k.c, p, m) ^ needle;
+        const uint32_t cnt = pcl_popc32(((x | (x >> 1)) | pcl_win32u(k.sb, p, m)) & even);
+        if (cnt < best) { best = cnt; bpos = i; }
+    }
+    uint32_t status = PCL_SPLIT_OK;
+    if (m == 1u && best != 0u) status = PCL_SPLIT_ANCHOR_NOT_FOUND;                   // (None, 1) (segment.rs:508-512)
+    else if (best > pl.a_maxmis) status = PCL_SPLIT_PATTERN_MISMATCH;                // the window lies inside the record (L >= full_len)
+    const bool ok = status == PCL_SPLIT_OK;
+    const uint32_t pos = ok ? bpos : 0u;
+    uint32_t c2[4], bd2[4];
+    pcl_shr_bases(k.c, pos, c2);
+    pcl_shr_bases(k.bd, pos, bd2);
+    o.status = status;
+    const uint32_t n = rd.n_elems, vmin = rd.elems[v].min_len;
+    o.tcoord = PCL_COORD_ABSENT;
+    if (ok && rd.has_target && pl.t_elem != 0xFFu) {
+        const uint32_t e = pl.t_elem;
+        const uint32_t start = pl.ustart[e] + (e > v ? pos : 0u);
+        uint32_t len = e == v ? vmin + pos : rd.elems[e].max_len;
+        if (pl.has_t && e + 1u == n) len = (start + rd.elems[e].max_len < L ? start + rd.elems[e].max_len : L) - start;   // tail consume_buf
+        o.tcoord = (start << 16) | len;
+    }
+    for (uint32_t j = 0; j < rd.n_bc; ++j) {
+        const uint32_t e = pl.bc_elem[j];
+        const bool behind = e > v;
+        const uint32_t us = pl.ustart[e];
+        uint32_t len = e == v ? vmin + pos : rd.elems[e].max_len;
+        if (pl.has_t && e + 1u == n) len = (us + pos + rd.elems[e].max_len < L ? us + pos + rd.elems[e].max_len : L) - (us + pos);
+        o.bcoord[j] = ok ? (((us + (behind ? pos : 0u)) << 16) | len) : PCL_COORD_ABSENT;
+        o.bkey[j] = 0; o.bninv[j] = 0; o.bipos[j] = 0;
+        if (ok) o.bkey[j] = pcl_plan_key(behind ? c2 : k.c, behind ? bd2 : k.bd, us, len > 16u ? 16u : len, kRev, &o.bninv[j], &o.bipos[j]);
+    }
+    for (uint32_t j = 0; j < rd.n_umi; ++j) {
+        const uint32_t e = pl.umi_elem[j];
+        const bool behind = e > v;
+        const uint32_t us = pl.ustart[e];
+        uint32_t len = e == v ? vmin + pos : rd.elems[e].max_len;
+        if (pl.has_t && e + 1u == n) len = (us + pos + rd.elems[e].max_len < L ? us + pos + rd.elems[e].max_len : L) - (us + pos);
+        o.ucoord[j] = ok ? (((us + (behind ? pos : 0u)) << 16) | len) : PCL_COORD_ABSENT;
+        o.ukey[j] = PCL_KEY_ABSENT32;
+        if (ok) {
+            uint32_t ninv, ipos;
+            const uint32_t key = pcl_plan_key(behind ? c2 : k.c, behind ? bd2 : k.bd, us, len > 16u ? 16u : len, kRev, &ninv, &ipos);
+            o.ukey[j] = ninv ? 0u : key;
+        }
+    }
+    return true;
 }
 
 // Store a key in its device width (see precellar_b200.h).

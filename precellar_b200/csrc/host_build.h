@@ -5,6 +5,7 @@
 #ifndef PCL_HOST_BUILD_H
 #define PCL_HOST_BUILD_H
 
+#include <algorithm>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -231,6 +232,29 @@ inline int pcl_build_read(int r, const pcl_read_desc &rd, DRead *out, pcl_read_i
         if (ok) {
             pl.enabled = 1; pl.v = (uint8_t)v; pl.has_t = has_t ? 1 : 0; pl.t_elem = 0xFF;
             for (int e = 0; e < ne; ++e) if (rd.elems[e].kind == PCL_KIND_TARGET) pl.t_elem = (uint8_t)e;
+            // straight-line path: every element fits whatever the anchor position when
+            //   L >= start of the last element (variable element at its longest) + its minimal length (a trailing variable
+            //   element is clipped at the record end, the others have min == max)
+            const uint32_t slack = rd.elems[v].max_len - rd.elems[v].min_len;
+            pl.n_pos = (uint8_t)(slack + 1);
+            pl.a_start = (uint8_t)(pl.ustart[v] + rd.elems[v].min_len);
+            pl.a_len = rd.elems[v + 1].seq_len;
+            pl.a_maxmis = d.elems[v + 1].max_mis;
+            const uint32_t last_end = pl.ustart[ne - 1] + slack + (has_t ? (uint32_t)std::max<int>(rd.elems[ne - 1].min_len, 1) : rd.elems[ne - 1].max_len);
+            // the walk breaks at an element when max_off >= len (segment.rs:245-248): for the trailing variable element that
+            // needs L > its latest start; last_end covers it because its minimal length counts as >= 1
+            pl.full_len = (uint16_t)last_end;
+            uint32_t touch = 0;                                  // bytes the barcode / UMI / anchor fields can reach
+            for (int e = 0; e < ne; ++e) {
+                const pcl_elem_desc &el = rd.elems[e];
+                if (el.kind == PCL_KIND_BARCODE || el.kind == PCL_KIND_UMI || e == v + 1 || e == v)
+                    touch = std::max<uint32_t>(touch, pl.ustart[e] + slack + (e == v ? rd.elems[e].min_len : el.max_len));
+            }
+            touch = std::min<uint32_t>(touch, stride);
+            pl.n_words = (uint8_t)std::min<uint32_t>(16, (touch + 3) / 4);
+            if (pl.n_pos > 16 || last_end > 0xFFFF) pl.full_len = 0xFFFF;     // never taken: general route only
+            for (int j = 0; j < info.n_bc; ++j) pl.bc_elem[j] = info.bc_elem[j];
+            for (int j = 0; j < info.n_umi; ++j) pl.umi_elem[j] = info.umi_elem[j];
         }
     }
     *out = d;

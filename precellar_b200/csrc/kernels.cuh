@@ -152,6 +152,10 @@ __device__ __forceinline__ void pcl_hist_add2(uint32_t *ck, uint32_t *cc, uint32
     atomicAdd(&gcounts[slot], 1u);
 }
 
+__device__ __forceinline__ void pcl_st_stream(uint32_t *p, uint32_t v) { __stcs(p, v); }
+__device__ __forceinline__ void pcl_st_stream(uint16_t *p, uint16_t v) { __stcs(p, v); }
+__device__ __forceinline__ void pcl_st_stream(uint4 *p, uint4 v) { __stcs(p, v); }
+
 __device__ __forceinline__ uint4 pcl_ld_stream(const uint4 *p) {
     uint4 r;
     asm volatile("ld.global.cs.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
@@ -372,13 +376,118 @@ __global__ void __launch_bounds__(PCL_BLOCK, kMode == 2 ? 4 : 1) k_count(const _
 }
 
 // ------------------------------------------------------------------------------------------------
+// k_count_plan: pass 1 for AnchorPlan layouts (sci-RNA-seq3 R1, dscATAC R1 ...: one variable element, then an anchor).
+// Thread per record; records long enough for every element go through the straight-line pcl_plan_record_fast (one window
+// search, fields cut at warp-uniform offsets), anything shorter through the element-by-element walk (out of line).
+// ------------------------------------------------------------------------------------------------
+template <bool kRev>
+__global__ void __launch_bounds__(PCL_BLOCK, 4) k_count_plan(const __grid_constant__ CountParams p) {
+    __shared__ uint32_t ck[PCL_HCACHE];
+    __shared__ uint32_t cc[PCL_HCACHE];
+    const DRead &rd = p.rd;
+    for (uint32_t h = threadIdx.x; h < PCL_HCACHE; h += blockDim.x) { ck[h] = PCL_HEMPTY; cc[h] = 0; }
+    __syncthreads();
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint64_t step = (uint64_t)gridDim.x * blockDim.x;
+    const uint32_t n_vec = rd.stride >> 4;                              // 16-byte vectors per record row (<= 4)
+    const uint32_t lcap = rd.max_len ? rd.max_len : 0xFFFFFFFFu;
+    const uint32_t n_bc = rd.n_bc, n_umi = rd.n_umi;
+    uint32_t n_total[PCL_MAX_BC_PER_READ] = {0, 0, 0, 0}, n_mis[PCL_MAX_BC_PER_READ] = {0, 0, 0, 0}, n_defect = 0;
+    WlCursor wl = {0, 0};
+    // every lane of a warp runs the same number of iterations (full-mask ballots below)
+    for (uint64_t base = (uint64_t)blockIdx.x * blockDim.x + (threadIdx.x & ~31u); base < p.n; base += step) {
+        const uint64_t i = base + lane;
+        const bool live = i < p.n;
+        const uint64_t ld = live ? i : p.n - 1;                         // out-of-range lanes re-read the last record
+        uint32_t w[16];
+        const uint4 *r4 = reinterpret_cast<const uint4 *>(p.seq + ld * (uint64_t)rd.stride);
+#pragma unroll
+        for (uint32_t v = 0; v < 4u; ++v) {
+            uint4 t = make_uint4(0u, 0u, 0u, 0u);
+            if (v < n_vec) t = pcl_ld_stream(r4 + v);
+            w[4 * v] = t.x; w[4 * v + 1] = t.y; w[4 * v + 2] = t.z; w[4 * v + 3] = t.w;
+        }
+        const uint32_t L = min((uint32_t)__ldcs(p.len + ld), lcap);     // FastqReader::read_record (read.rs:98-103)
+        PlanOut o;
+        // warp-uniform choice (a warp with one short record walks all of its records: same results, and rare)
+        if (__all_sync(0xFFFFFFFFu, L >= rd.plan.full_len)) (void)pcl_plan_record_fast<kRev>(rd, w, L, o);
+        else pcl_plan_record<kRev>(rd, w, L, o);
+        uint32_t fs = o.status;
+        n_defect += live & (o.status != PCL_SPLIT_OK);
+        if (rd.has_target) {
+            if (o.tcoord != PCL_COORD_ABSENT) fs |= PCL_FSTATUS_TARGET;
+            if (live) pcl_st_stream(p.tcoord + i, o.tcoord);
+        }
+        bool miss[PCL_MAX_BC_PER_READ];
+#pragma unroll
+        for (uint32_t j = 0; j < PCL_MAX_BC_PER_READ; ++j) {
+            miss[j] = false;
+            if (j >= n_bc) { fs |= PCL_BC_ABSENT << (4 + 3 * j); continue; }
+            const uint32_t c = o.bcoord[j];
+            uint32_t code = PCL_BC_ABSENT;
+            if (c != PCL_COORD_ABSENT) {
+                const uint32_t blen = c & 0xFFFFu;
+                const DTable &t = p.tab[j];
+                uint32_t slot = 0xFFFFFFFFu;
+                if (o.bninv[j] == 0u && (t.mode == PCL_TAB_K32_L16 ? blen == 16u : blen <= 15u)) slot = pcl_probe32(t, o.bkey[j]);
+                n_total[j] += live;                                     // WhitelistBuilder::add (barcode.rs:410-426)
+                if (slot != 0xFFFFFFFFu) {
+                    code = PCL_BC_EXACT;
+                    if (live) pcl_hist_add(ck, cc, j, slot, t.counts);
+                } else {
+                    code = PCL_BC_NO_MATCH;
+                    n_mis[j] += live;
+                    miss[j] = live & (o.bninv[j] <= 1u);                // two or more non-ACGT bases: NoMatch is final
+                }
+            }
+            if (live) {
+                pcl_st_stream(p.bcoord[j] + i, c);
+                pcl_st_stream(reinterpret_cast<uint32_t *>(p.bc_key[j]) + i, o.bkey[j]);
+            }
+            fs |= code << (4 + 3 * j);
+        }
+#pragma unroll
+        for (uint32_t j = 0; j < PCL_MAX_UMI_PER_READ; ++j) {
+            if (j >= n_umi) break;
+            if (live) {
+                pcl_st_stream(p.ucoord[j] + i, o.ucoord[j]);
+                pcl_st_stream(reinterpret_cast<uint32_t *>(p.umi_key[j]) + i, o.ukey[j]);
+            }
+        }
+        if (live) pcl_st_stream(p.fstatus + i, (uint16_t)fs);
+        // warp-batched append of the misses to the worklist
+#pragma unroll
+        for (uint32_t j = 0; j < PCL_MAX_BC_PER_READ; ++j) {
+            if (j >= n_bc) break;
+            const uint32_t c = o.bcoord[j];
+            pcl_wl_push(p, wl, miss[j], pcl_wl_pack(i, c >> 16, c & 0xFFFFu, j, o.bninv[j], o.bipos[j]), o.bkey[j], lane);
+        }
+    }
+    pcl_wl_finish(p, wl, lane);
+#pragma unroll
+    for (uint32_t j = 0; j < PCL_MAX_BC_PER_READ; ++j) {
+        if (j >= n_bc) break;
+        uint32_t t = n_total[j], m = n_mis[j];
+        for (int o = 16; o > 0; o >>= 1) { t += __shfl_xor_sync(0xFFFFFFFFu, t, o); m += __shfl_xor_sync(0xFFFFFFFFu, m, o); }
+        if (lane == 0) {
+            if (t) atomicAdd(p.tab[j].total, (unsigned long long)t);
+            if (m) atomicAdd(p.tab[j].mismatch, (unsigned long long)m);
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) n_defect += __shfl_xor_sync(0xFFFFFFFFu, n_defect, o);
+    if (lane == 0 && n_defect) atomicAdd(p.num_defect, (unsigned long long)n_defect);
+    __syncthreads();
+    for (uint32_t h = threadIdx.x; h < PCL_HCACHE; h += blockDim.x) {
+        const uint32_t id = ck[h], c = cc[h];
+        if (id != PCL_HEMPTY && c) atomicAdd(&p.tab[id >> 29].counts[id & 0x1FFFFFFFu], c);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // k_count_fast: pass 1 for reads with a FastLayout (10x v2/v3 R1, ATAC / multiome I2, ...).
 // One thread per record; the 32 record bytes arrive as two 128-bit streaming loads and stay in registers;
 // SWAR conversion to 2-bit codes; one bucket probe of the 32-bit key table.
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void pcl_st_stream(uint32_t *p, uint32_t v) { __stcs(p, v); }
-__device__ __forceinline__ void pcl_st_stream(uint16_t *p, uint16_t v) { __stcs(p, v); }
-__device__ __forceinline__ void pcl_st_stream(uint4 *p, uint4 v) { __stcs(p, v); }
 
 // kBits: log2 of the histogram cache entries; the CTA has 256 << (kBits - 12) threads (same cache per thread).
 // kSpec: PCL_FAST_SPEC_* instance of the field extraction (0: driven by the layout's byte masks).

@@ -212,7 +212,7 @@ void prof_end(pcl_ctx *ctx, cudaStream_t s) {
     cudaEventRecord(ctx->evs.back().b, s);
 }
 
-enum { OCC_COUNT = 0, OCC_COUNT_FAST, OCC_COUNT_LENONLY, OCC_ENUM, OCC_FILTER, OCC_CORRECT, OCC_QC, OCC_GATHER, OCC_COUNT_CODES, OCC_COUNT_PLAN, OCC_RESOLVE };
+enum { OCC_COUNT = 0, OCC_COUNT_FAST, OCC_COUNT_LENONLY, OCC_ENUM, OCC_FILTER, OCC_CORRECT, OCC_QC, OCC_GATHER, OCC_COUNT_CODES, OCC_COUNT_PLAN, OCC_RESOLVE, OCC_COUNT_PLAN2 };
 
 // every barcode of read r goes through the 32-bit tables (k_filter / k_resolve)
 bool read_all32(const pcl_ctx *ctx, int r) {
@@ -304,6 +304,7 @@ int pcl_ctx_create(pcl_ctx **out, int device) {
         ctx->occ[OCC_COUNT] = occ((const void *)k_count<0>);
         ctx->occ[OCC_COUNT_CODES] = occ((const void *)k_count<1>);
         ctx->occ[OCC_COUNT_PLAN] = occ((const void *)k_count<2>);
+        ctx->occ[OCC_COUNT_PLAN2] = occ((const void *)k_count_plan<false>);
         {
             // k_count_fast: 1024-thread CTAs with a 16 K-entry histogram cache (128 KB), one resident wave, two
             // candidate lines per key, a new key admitted on 1 of 8 sightings.  Measured on 125 M v3 records:
@@ -993,6 +994,11 @@ int pcl_count(pcl_ctx *ctx, pcl_chunk *c) {
             else k_count_fast<14><<<grid, threads, smem, c->stream>>>(p);
         }
         else if (lenonly) k_count_lenonly<<<grid_for(ctx, c->n / 8 + 8, ctx->occ[OCC_COUNT_LENONLY]), PCL_BLOCK, 0, c->stream>>>(p);
+        else if (plan && !ctx->old_fast && p.wl_key) {
+            const int g = grid_for(ctx, c->n, 3 * ctx->occ[OCC_COUNT_PLAN2]);
+            if (d.is_reverse) k_count_plan<true><<<g, PCL_BLOCK, 0, c->stream>>>(p);
+            else k_count_plan<false><<<g, PCL_BLOCK, 0, c->stream>>>(p);
+        }
         else if (plan) k_count<2><<<grid_for(ctx, c->n, 3 * ctx->occ[OCC_COUNT_PLAN]), PCL_BLOCK, 0, c->stream>>>(p);
         else if (d.codes_ok && !ctx->force_generic) k_count<1><<<grid_for(ctx, c->n, 3 * ctx->occ[OCC_COUNT_CODES]), PCL_BLOCK, 0, c->stream>>>(p);
         else k_count<0><<<grid_for(ctx, c->n, 3 * ctx->occ[OCC_COUNT]), PCL_BLOCK, 0, c->stream>>>(p);

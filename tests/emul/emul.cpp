@@ -182,30 +182,32 @@ int emu_run(const pcl_read_desc *reads, int n_reads, int n_regions, const uint8_
             if (plan) {
                 uint32_t w[16] = {0};
                 memcpy(w, rec, rd.stride);
-                const uint32_t nbytes = L < rd.stride ? L : rd.stride;
-                Codes32 k;
-                if (rev) pcl_codes32_t<true>(w, (int)((nbytes + 3u) >> 2), k); else pcl_codes32_t<false>(w, (int)((nbytes + 3u) >> 2), k);
-                AnchorSplit sp;
-                pcl_anchor_split(rd, k, L, sp);
-                uint32_t c2[4], bd2[4];
-                pcl_shr_bases(k.c, sp.pos, c2);
-                pcl_shr_bases(k.bd, sp.pos, bd2);
-                uint32_t fs = sp.status;
-                if (sp.status != PCL_SPLIT_OK) defects_out[r]++;
+                PlanOut po, pg;
+                memset(&po, 0, sizeof po); memset(&pg, 0, sizeof pg);
+                if (rev) pcl_plan_record<true>(rd, w, L, pg); else pcl_plan_record<false>(rd, w, L, pg);
+                const bool fastp = rev ? pcl_plan_record_fast<true>(rd, w, L, po) : pcl_plan_record_fast<false>(rd, w, L, po);
+                if (fastp) {                                       // the straight-line route must agree with the walk
+                    bool same = po.status == pg.status && po.tcoord == pg.tcoord;
+                    for (uint32_t j = 0; j < rd.n_bc; ++j)
+                        same = same && po.bcoord[j] == pg.bcoord[j] && po.bkey[j] == pg.bkey[j] && po.bninv[j] == pg.bninv[j] &&
+                               (po.bninv[j] != 1u || po.bipos[j] == pg.bipos[j]);
+                    for (uint32_t j = 0; j < rd.n_umi; ++j) same = same && po.ucoord[j] == pg.ucoord[j] && po.ukey[j] == pg.ukey[j];
+                    if (!same) { snprintf(err, errcap, "plan fast path disagrees with the walk at record %llu", (unsigned long long)i); return PCL_ERR_INPUT; }
+                } else po = pg;
+                uint32_t fs = po.status;
+                if (po.status != PCL_SPLIT_OK) defects_out[r]++;
                 if (rd.has_target) {
-                    const uint32_t tc = rd.plan.t_elem != 0xFFu ? pcl_anchor_coord(rd, sp, rd.plan.t_elem) : PCL_COORD_ABSENT;
-                    if (tc != PCL_COORD_ABSENT) fs |= PCL_FSTATUS_TARGET;
-                    io[r].tcoord[i] = tc;
+                    if (po.tcoord != PCL_COORD_ABSENT) fs |= PCL_FSTATUS_TARGET;
+                    io[r].tcoord[i] = po.tcoord;
                 }
                 for (uint32_t j = 0; j < PCL_MAX_BC_PER_READ; ++j) {
                     if (j >= rd.n_bc) { fs |= PCL_BC_ABSENT << (4 + 3 * j); continue; }
-                    const uint32_t e = in.bc_elem[j], c = pcl_anchor_coord(rd, sp, e);
+                    const uint32_t c = po.bcoord[j];
                     io[r].bcoord[j][i] = c;
                     uint32_t code = PCL_BC_ABSENT, key = 0;
                     if (c != PCL_COORD_ABSENT) {
-                        const uint32_t blen = c & 0xFFFFu;
-                        uint32_t ninv, ipos;
-                        key = pcl_anchor_key(rd, k, c2, bd2, e, c, &ninv, &ipos);
+                        const uint32_t blen = c & 0xFFFFu, ninv = po.bninv[j], ipos = po.bipos[j];
+                        key = po.bkey[j];
                         DTable &t = dt[bcr[r][j]];
                         uint32_t slot = 0xFFFFFFFFu;
                         if (ninv == 0u && (t.mode == PCL_TAB_K32_L16 ? blen == 16u : blen <= 15u)) slot = pcl_probe32(t, key);
@@ -220,15 +222,8 @@ int emu_run(const pcl_read_desc *reads, int n_reads, int n_regions, const uint8_
                     fs |= code << (4 + 3 * j);
                 }
                 for (uint32_t j = 0; j < rd.n_umi; ++j) {
-                    const uint32_t e = in.umi_elem[j], c = pcl_anchor_coord(rd, sp, e);
-                    io[r].ucoord[j][i] = c;
-                    uint32_t key = PCL_KEY_ABSENT32;
-                    if (c != PCL_COORD_ABSENT) {
-                        uint32_t ninv;
-                        key = pcl_anchor_key(rd, k, c2, bd2, e, c, &ninv);
-                        if (ninv) key = 0;
-                    }
-                    reinterpret_cast<uint32_t *>(io[r].umi_key[j])[i] = key;
+                    io[r].ucoord[j][i] = po.ucoord[j];
+                    reinterpret_cast<uint32_t *>(io[r].umi_key[j])[i] = po.ukey[j];
                 }
                 io[r].fstatus[i] = (uint16_t)fs;
                 continue;
