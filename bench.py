@@ -489,6 +489,7 @@ def main():
     ap.add_argument("--no-other", action="store_true", help="skip the other BASELINE configurations")
     ap.add_argument("--other-n", type=int, default=0, help="read groups per other configuration (default: BASELINE sizes)")
     ap.add_argument("--ingest-sample", type=int, default=1_000_000)
+    ap.add_argument("--api-sample", type=int, default=1_000_000, help="read triples of the API end-to-end leg (0: skip)")
     args = ap.parse_args()
 
     rank, local_rank, world = env_int("RANK", 0), env_int("LOCAL_RANK", 0), env_int("WORLD_SIZE", 1)
@@ -745,6 +746,14 @@ def main():
             for r in rs:
                 r.close()
 
+    # ------------------------------------------------------------------ through the reference's API: files -> make_fastq -> .fq.zst
+    api = None
+    if rank == 0 and world == 1 and not args.no_cpu and args.api_sample > 0:
+        import tempfile
+        from tools import api_bench
+        with tempfile.TemporaryDirectory() as td:
+            api = api_bench.api_e2e(td, args.api_sample, host_cores)
+
     if rank == 0:
         out = {
             "metric": "barcode-corrected read-pairs/sec", "value": value, "unit": "read-pairs/s", "n_gpus": world,
@@ -756,7 +765,7 @@ def main():
                        "l2": "inputs (6.3 GB per GPU) are far larger than L2; no flush needed"},
             "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": int(launches),
             "clocks": clocks.summary(), "sustained": sustained, "parity": parity, "host_cores": host_cores, "host_ingest": ingest,
-            "other_configs": other, "grouping": grouping,
+            "other_configs": other, "grouping": grouping, "api_e2e": api,
             "setup_s": {"pipeline_create_incl_whitelist_tables": t_setup},
         }
         emit(out)

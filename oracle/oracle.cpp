@@ -10,6 +10,9 @@
 
 #include "oracle.h"
 
+#include <dlfcn.h>
+#include <zlib.h>
+
 #include <algorithm>
 #include <atomic>
 #include <cmath>
@@ -409,6 +412,7 @@ int correct_barcode(const Whitelist &wl, const CorrectOptions &opt, const std::s
 struct Fq { std::string seq, qual; };                 // the parts of fastq::Record the path touches
 struct Barcode { Fq raw; bool corrected_some = false; std::string corrected; };   // fastq.rs:528-545
 struct Annotated {                                    // fastq.rs:549-556
+    int bc_file = -1, r1_file = -1, r2_file = -1;     // the file whose record (name, description) each part carries
     bool has_barcode = false; Barcode barcode;
     bool has_umi = false; Fq umi;
     bool has_read1 = false; Fq read1;
@@ -430,13 +434,13 @@ void barcode_extend(Barcode &self, const Barcode &other) {                      
 // AnnotatedFastq::join (fastq.rs:571-603); returns false on the reference's panics.
 bool annotated_join(Annotated &self, const Annotated &other) {
     if (self.has_barcode) { if (other.has_barcode) barcode_extend(self.barcode, other.barcode); }
-    else { self.has_barcode = other.has_barcode; self.barcode = other.barcode; }
+    else { self.has_barcode = other.has_barcode; self.barcode = other.barcode; self.bc_file = other.bc_file; }
     if (self.has_umi) { if (other.has_umi) extend_fastq_record(self.umi, other.umi); }
     else { self.has_umi = other.has_umi; self.umi = other.umi; }
     if (self.has_read1) { if (other.has_read1) return false; }
-    else { self.has_read1 = other.has_read1; self.read1 = other.read1; }
+    else { self.has_read1 = other.has_read1; self.read1 = other.read1; self.r1_file = other.r1_file; }
     if (self.has_read2) { if (other.has_read2) return false; }
-    else { self.has_read2 = other.has_read2; self.read2 = other.read2; }
+    else { self.has_read2 = other.has_read2; self.read2 = other.read2; self.r2_file = other.r2_file; }
     return true;
 }
 
@@ -493,6 +497,10 @@ struct orc {
     int n_bcsegs = 0;
     bool counted = false;
     bool keep_records = false;
+    // file-level driver (orc_fastq_load): planes and definitions read from FASTQ files, owned here
+    std::vector<std::vector<uint8_t>> own_seq, own_qual;
+    std::vector<std::vector<uint16_t>> own_len;
+    std::vector<std::vector<std::string>> defs;
     std::vector<Annotated> kept;     // per group, when keep_records
     std::vector<uint8_t> kept_flag;
     QcFastq qc;
@@ -547,6 +555,7 @@ int annotate(const orc &o, const ReadDef &rd, const RecordView &rec, const Corre
              AnnotateOut &aux) {
     const SegInfo &info = rd.info;
     out = Annotated();
+    const int this_file = (int)(&rd - o.reads.data());
     aux.bc.clear();
     int st = split_with_tolerance(info, (const uint8_t *)rec.seq.data(), rec.seq.size(), 1.0, 0.2, aux.segs, nullptr);
     aux.status = st;
@@ -572,7 +581,7 @@ int annotate(const orc &o, const ReadDef &rd, const RecordView &rec, const Corre
                 b.raw = fq;
                 aux.bc.push_back({segment.elem, err, b.corrected_some ? index : -1});
                 if (out.has_barcode) barcode_extend(out.barcode, b);
-                else { out.has_barcode = true; out.barcode = b; }
+                else { out.has_barcode = true; out.barcode = b; out.bc_file = this_file; }
             } else {
                 out.has_umi = true;                                        // `umi = Some(fq)`: a later UMI segment of the
                 out.umi = fq;                                              // same file REPLACES the earlier one (fastq.rs:502)
@@ -582,8 +591,8 @@ int annotate(const orc &o, const ReadDef &rd, const RecordView &rec, const Corre
             Fq fq;
             fq.seq = rec.seq.substr(segment.start, segment.len);
             fq.qual = rec.qual.substr(segment.start, segment.len);
-            if (info.is_reverse) { out.has_read2 = true; out.read2 = fq; }
-            else { out.has_read1 = true; out.read1 = fq; }
+            if (info.is_reverse) { out.has_read2 = true; out.read2 = fq; out.r2_file = this_file; }
+            else { out.has_read1 = true; out.read1 = fq; out.r1_file = this_file; }
         }
     }
     return ORC_SPLIT_OK;
@@ -925,6 +934,196 @@ int orc_correct_one(const uint8_t *wl_bytes, const uint64_t *wl_offsets, const u
     CorrectOptions opt;
     opt.some = true; opt.threshold = threshold; opt.max_expected_errors = max_expected_errors;
     return correct_barcode(w, opt, query, qual, len, index_out, &key);
+}
+
+// ---------------------------------------------------------------------------------------
+// File-level driver: the reference's make_fastq end to end on the host (bench.py api_e2e, reference arm).
+//   orc_fastq_load   Read::open + FastqReader::read_record (seqspec/src/read.rs:98-108,137-155; open_file,
+//                    seqspec/src/utils.rs:44-56) + strip_fq_suffix (precellar/src/align/fastq.rs:612-621)
+//   orc_make_fastq   the record loop of make_fastq (python/src/lib.rs:136-168) over the AnnotatedFastq kept by
+//                    orc_annotate, written through zstd at `level` with `threads` workers (create_file,
+//                    seqspec/src/utils.rs:17-42: level 9, multithread(8))
+// FASTQ dialect: four lines per record, definition = name [blank description]; the un-vendored noodles reader's
+// corner cases (blank lines, wrapped sequences) are not modelled ("parity unpinned").
+// ---------------------------------------------------------------------------------------
+struct LineReader {
+    gzFile f = nullptr;
+    std::vector<char> buf;
+    size_t pos = 0, end = 0;
+    bool open(const char *p) { f = gzopen(p, "rb"); if (f) { gzbuffer(f, 1 << 20); buf.resize(1 << 20); } return f != nullptr; }
+    void close() { if (f) gzclose(f); f = nullptr; }
+    bool getline(std::string &out) {
+        out.clear();
+        for (;;) {
+            if (pos == end) {
+                int n = gzread(f, buf.data(), (unsigned)buf.size());
+                if (n <= 0) return !out.empty();
+                pos = 0; end = (size_t)n;
+            }
+            const char *nl = (const char *)memchr(buf.data() + pos, '\n', end - pos);
+            if (nl) {
+                out.append(buf.data() + pos, nl - (buf.data() + pos));
+                pos = (size_t)(nl - buf.data()) + 1;
+                if (!out.empty() && out.back() == '\r') out.pop_back();
+                return true;
+            }
+            out.append(buf.data() + pos, end - pos);
+            pos = end;
+        }
+    }
+};
+
+int orc_fastq_load(orc_t *o, int file, const char *const *paths, int n_paths, uint32_t stride) {
+    if (file < 0 || (size_t)file >= o->reads.size()) { set_err(o, "bad file index"); return -1; }
+    const size_t nf = o->reads.size();
+    if (o->own_seq.size() < nf) { o->own_seq.resize(nf); o->own_qual.resize(nf); o->own_len.resize(nf); o->defs.resize(nf); }
+    std::vector<uint8_t> &S = o->own_seq[file], &Q = o->own_qual[file];
+    std::vector<uint16_t> &Ln = o->own_len[file];
+    std::vector<std::string> &D = o->defs[file];
+    S.clear(); Q.clear(); Ln.clear(); D.clear();
+    std::string l0, l1, l2, l3;
+    for (int k = 0; k < n_paths; ++k) {                                  // the files of a read are concatenated (read.rs:148-149)
+        LineReader rd;
+        if (!rd.open(paths[k])) { set_err(o, std::string("cannot open file: ") + paths[k]); return -2; }
+        while (rd.getline(l0)) {
+            if (l0.empty()) continue;
+            if (l0[0] != '@' || !rd.getline(l1) || !rd.getline(l2) || !rd.getline(l3) || l1.size() != l3.size()) {
+                rd.close(); set_err(o, "malformed FASTQ record"); return -3;
+            }
+            size_t e = 1;                                                // strip_fq_suffix on the name
+            while (e < l0.size() && l0[e] != ' ' && l0[e] != '\t') ++e;
+            size_t name_len = e - 1;
+            if (name_len > 2 && l0[e - 2] == '/' && (l0[e - 1] == '1' || l0[e - 1] == '2')) name_len -= 2;
+            D.emplace_back(l0.substr(1, name_len) + l0.substr(e));
+            const size_t L = l1.size(), c = std::min<size_t>(L, stride), at = S.size();
+            S.resize(at + stride, 'N'); Q.resize(at + stride, '!');
+            memcpy(S.data() + at, l1.data(), c);
+            memcpy(Q.data() + at, l3.data(), c);
+            Ln.push_back((uint16_t)std::min<size_t>(L, 65535));
+        }
+        rd.close();
+    }
+    FileInput &in = o->reads[file].in;
+    in.seq = S.data(); in.qual = Q.data(); in.len = Ln.data(); in.stride = stride; in.n = Ln.size(); in.set = true;
+    return 0;
+}
+
+uint64_t orc_n_records(orc_t *o, int file) {
+    return (file >= 0 && (size_t)file < o->reads.size() && o->reads[file].in.set) ? o->reads[file].in.n : 0;
+}
+
+namespace {
+struct ZBuf { void *ptr; size_t size, pos; };
+struct ZstdApi {
+    void *h = nullptr;
+    void *(*createCCtx)() = nullptr;
+    size_t (*freeCCtx)(void *) = nullptr;
+    size_t (*setParameter)(void *, int, int) = nullptr;
+    size_t (*compressStream2)(void *, ZBuf *, ZBuf *, int) = nullptr;
+    unsigned (*isError)(size_t) = nullptr;
+    bool ok = false;
+};
+ZstdApi &zstd_api() {
+    static ZstdApi a;
+    static bool tried = false;
+    if (tried) return a;
+    tried = true;
+    a.h = dlopen("libzstd.so.1", RTLD_NOW);
+    if (!a.h) return a;
+    a.createCCtx = (void *(*)())dlsym(a.h, "ZSTD_createCCtx");
+    a.freeCCtx = (size_t(*)(void *))dlsym(a.h, "ZSTD_freeCCtx");
+    a.setParameter = (size_t(*)(void *, int, int))dlsym(a.h, "ZSTD_CCtx_setParameter");
+    a.compressStream2 = (size_t(*)(void *, ZBuf *, ZBuf *, int))dlsym(a.h, "ZSTD_compressStream2");
+    a.isError = (unsigned (*)(size_t))dlsym(a.h, "ZSTD_isError");
+    a.ok = a.createCCtx && a.freeCCtx && a.setParameter && a.compressStream2 && a.isError;
+    return a;
+}
+struct ZWriter {                                     // zstd::stream::Encoder::new(file, level) + multithread(n)
+    FILE *f = nullptr;
+    void *cctx = nullptr;
+    std::vector<char> in, out;
+    size_t fill = 0;
+    int workers = 0;
+    bool open(const char *path, int level, int threads) {
+        ZstdApi &z = zstd_api();
+        if (!z.ok) return false;
+        f = fopen(path, "wb");
+        if (!f) return false;
+        cctx = z.createCCtx();
+        z.setParameter(cctx, 100 /* ZSTD_c_compressionLevel */, level);
+        workers = z.isError(z.setParameter(cctx, 400 /* ZSTD_c_nbWorkers */, threads)) ? 0 : threads;
+        in.resize(4 << 20); out.resize(4 << 20);
+        return true;
+    }
+    bool flush(int mode) {                           // 0 continue, 2 end
+        ZstdApi &z = zstd_api();
+        ZBuf ib{in.data(), fill, 0};
+        for (;;) {
+            ZBuf ob{out.data(), out.size(), 0};
+            const size_t r = z.compressStream2(cctx, &ob, &ib, mode);
+            if (z.isError(r)) return false;
+            if (ob.pos && fwrite(out.data(), 1, ob.pos, f) != ob.pos) return false;
+            if (mode == 2 ? r == 0 : ib.pos == ib.size) break;
+        }
+        fill = 0;
+        return true;
+    }
+    bool write(const char *p, size_t n) {
+        while (n) {
+            const size_t c = std::min(n, in.size() - fill);
+            memcpy(in.data() + fill, p, c);
+            fill += c; p += c; n -= c;
+            if (fill == in.size() && !flush(0)) return false;
+        }
+        return true;
+    }
+    bool close() {
+        bool ok = flush(2);
+        zstd_api().freeCCtx(cctx);
+        ok = fclose(f) == 0 && ok;
+        return ok;
+    }
+};
+}  // namespace
+
+// Returns the number of records written, or < 0.  *zstd_workers = worker threads the system libzstd accepted.
+int64_t orc_make_fastq(orc_t *o, int correct_barcode, const char *r1_path, const char *r2_path, int level, int threads,
+                       int *zstd_workers) {
+    if (!o->keep_records || o->kept.empty()) { set_err(o, "orc_annotate with kept records must run first"); return -1; }
+    ZWriter w1, w2;
+    if (!w1.open(r1_path, level, threads)) { set_err(o, "cannot create R1 output (libzstd.so.1 needed)"); return -2; }
+    if (r2_path && !w2.open(r2_path, level, threads)) { set_err(o, "cannot create R2 output"); return -2; }
+    if (zstd_workers) *zstd_workers = w1.workers;
+    int64_t written = 0;
+    std::string rec;
+    bool ok = true;
+    for (size_t i = 0; i < o->kept.size() && ok; ++i) {                  // for record in fq_reader.flatten() (lib.rs:149)
+        if (!o->kept_flag[i]) continue;                                  // groups without a barcode were dropped
+        const Annotated &a = o->kept[i];
+        if (correct_barcode && !a.barcode.corrected_some) continue;      // lib.rs:154
+        if (!a.has_read1) { set_err(o, "called `Option::unwrap()` on a `None` value: read1"); ok = false; break; }
+        rec.clear();
+        rec += '@'; rec += o->defs[a.bc_file][i]; rec += '\n';
+        rec += a.barcode.corrected_some ? a.barcode.corrected : a.barcode.raw.seq;
+        if (a.has_umi) rec += a.umi.seq;
+        rec += a.read1.seq; rec += "\n+\n";
+        rec += a.barcode.raw.qual;
+        if (a.has_umi) rec += a.umi.qual;
+        rec += a.read1.qual; rec += '\n';
+        ok = w1.write(rec.data(), rec.size());
+        if (r2_path) {
+            if (!a.has_read2) { set_err(o, "called `Option::unwrap()` on a `None` value: read2"); ok = false; break; }
+            rec.clear();
+            rec += '@'; rec += o->defs[a.r2_file][i]; rec += '\n';
+            rec += a.read2.seq; rec += "\n+\n"; rec += a.read2.qual; rec += '\n';
+            ok = ok && w2.write(rec.data(), rec.size());
+        }
+        ++written;
+    }
+    ok = w1.close() && ok;
+    if (r2_path) ok = w2.close() && ok;
+    if (!ok) { if (o->err.empty()) set_err(o, "write failed"); return -3; }
+    return written;
 }
 
 }  // extern "C"

@@ -125,6 +125,14 @@ int orc_correct_one(const uint8_t *wl_bytes, const uint64_t *wl_offsets, const u
                     const uint8_t *bc, const uint8_t *qual, uint32_t len, double threshold,
                     double max_expected_errors, int64_t *index_out, double *prob_out);
 
+/* File-level driver for the API end-to-end baseline (bench.py api_e2e, reference arm): read the concatenated FASTQ
+ * files (plain or gzip) of one read into planes owned by the oracle, then -- after orc_count and orc_annotate with kept
+ * records -- write R1.fq.zst / R2.fq.zst like make_fastq (python/src/lib.rs:136-168; zstd level 9, 8 workers). */
+int orc_fastq_load(orc_t *, int file, const char *const *paths, int n_paths, uint32_t stride);
+uint64_t orc_n_records(orc_t *, int file);
+int64_t orc_make_fastq(orc_t *, int correct_barcode, const char *r1_path, const char *r2_path /* or NULL */, int level, int threads,
+                       int *zstd_workers);
+
 #ifdef __cplusplus
 }
 #endif

@@ -66,6 +66,11 @@ def lib():
         L.orc_get_qc.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.orc_render.restype = C.c_int64
         L.orc_render.argtypes = [C.c_void_p, C.c_uint64, C.c_char_p, C.c_uint64]
+        L.orc_fastq_load.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_char_p), C.c_int, C.c_uint32]
+        L.orc_n_records.restype = C.c_uint64
+        L.orc_n_records.argtypes = [C.c_void_p, C.c_int]
+        L.orc_make_fastq.restype = C.c_int64
+        L.orc_make_fastq.argtypes = [C.c_void_p, C.c_int, C.c_char_p, C.c_char_p, C.c_int, C.c_int, C.POINTER(C.c_int)]
         L.orc_split_str.argtypes = [C.POINTER(_Elem), C.c_int, C.c_int, C.c_char_p, C.c_char_p, C.c_uint32,
                                     C.c_double, C.c_double, C.c_char_p, C.c_uint32]
         L.orc_truncate_max.argtypes = [C.POINTER(_Elem), C.c_int, C.c_uint32]
@@ -254,6 +259,23 @@ class Oracle:
         if rc < 0:
             raise RuntimeError(self.error())
 
+    def fastq_load(self, file: int, paths: Sequence[str], stride: int) -> int:
+        """Read the concatenated FASTQ files (plain / gzip) of one read into planes owned by the oracle."""
+        arr = (C.c_char_p * len(paths))(*[p.encode() for p in paths])
+        rc = self.L.orc_fastq_load(self.h, file, arr, len(paths), stride)
+        if rc < 0:
+            raise RuntimeError(self.error())
+        self.n = int(self.L.orc_n_records(self.h, file))
+        return self.n
+
+    def make_fastq(self, correct: bool, r1_path: str, r2_path: Optional[str], level: int = 9, threads: int = 8):
+        """make_fastq's record loop over the records kept by annotate(render=True); returns (records, zstd workers)."""
+        w = C.c_int(0)
+        n = self.L.orc_make_fastq(self.h, int(correct), r1_path.encode(), r2_path.encode() if r2_path else None, level, threads, C.byref(w))
+        if n < 0:
+            raise RuntimeError(self.error())
+        return int(n), w.value
+
     def count(self):
         rc = self.L.orc_count(self.h)
         if rc < 0:
@@ -269,9 +291,9 @@ class Oracle:
 
     def annotate(self, correct: bool = True, threshold: float = 0.975, max_expected_errors: float = F64_MAX,
                  n_threads: int = 1, chunk_bases: int = 1_000_000, render: bool = False,
-                 outputs: bool = True) -> OracleResult:
+                 outputs: bool = True, keep: bool = False) -> OracleResult:
         n = self.n
-        self.L.orc_set_keep_records(self.h, int(render))
+        self.L.orc_set_keep_records(self.h, int(render or keep))
         res = OracleResult(
             n=n,
             fstatus=np.zeros((self.n_files, n), np.uint8), tcoord=np.zeros((self.n_files, n), np.uint32),

@@ -91,23 +91,47 @@ def decompress_file(path: str) -> bytes:
 
 
 class Writer:
-    """Append-only .zst writer: independent frames of up to `block` bytes (a valid multi-frame zstd file)."""
+    """Append-only .zst writer: independent frames of up to `block` bytes (a valid multi-frame zstd file), compressed
+    by `threads` workers (ZSTD_compress through ctypes releases the GIL) and written in order.  The reference writes
+    its zstd outputs at level 9 with 8 worker threads (seqspec/src/utils.rs:33-36, python/src/lib.rs:138-142)."""
 
-    def __init__(self, path: str, level: int = 9, block: int = 8 << 20):
+    def __init__(self, path: str, level: int = 9, block: int = 4 << 20, threads: int = 8):
+        from concurrent.futures import ThreadPoolExecutor
         self.fh = open(path, "wb")
         self.level, self.block = level, block
         self.buf = bytearray()
+        self.pool = ThreadPoolExecutor(max_workers=max(1, threads))
+        self.pending = []                       # futures in file order
+        self.max_pending = 4 * max(1, threads)
 
-    def write(self, data: bytes) -> None:
-        self.buf += data
+    def _drain(self, keep: int) -> None:
+        while len(self.pending) > keep:
+            self.fh.write(self.pending.pop(0).result())
+
+    def _submit(self, chunk: bytes) -> None:
+        self.pending.append(self.pool.submit(compress, chunk, self.level))
+        self._drain(self.max_pending)
+
+    def write(self, data) -> None:
+        mv = memoryview(data)
+        if not self.buf and len(mv) >= self.block:          # large appends: cut frames straight out of the caller's buffer
+            k = 0
+            while len(mv) - k >= self.block:
+                self._submit(bytes(mv[k:k + self.block]))
+                k += self.block
+            mv = mv[k:]
+        self.buf += mv
         while len(self.buf) >= self.block:
-            self.fh.write(compress(bytes(self.buf[:self.block]), self.level))
+            self._submit(bytes(self.buf[:self.block]))
             del self.buf[:self.block]
 
     def close(self) -> None:
         if self.fh:
             if self.buf:
-                self.fh.write(compress(bytes(self.buf), self.level))
+                self._submit(bytes(self.buf))
+                self.buf = bytearray()
+            self._drain(0)
+            self.pool.shutdown(wait=True)
             self.fh.close()
             self.fh = None
 

@@ -26,6 +26,29 @@ from .pipeline import BarcodePipeline, Chunk, assemble, decode_key_py, rev_compl
 from .seqspec import Assay, parse_modality
 
 
+# Stage times of the last run (seconds), filled when PCL_API_TIMING=1: where an API-level run spends its wall clock.
+TIMING: dict = {}
+
+
+class _timed:
+    def __init__(self, name):
+        self.name = name
+
+    def __enter__(self):
+        import time
+        self.t0 = time.perf_counter()
+
+    def __exit__(self, *a):
+        import time
+        if os.environ.get("PCL_API_TIMING") == "1":
+            TIMING[self.name] = TIMING.get(self.name, 0.0) + time.perf_counter() - self.t0
+
+
+# Pass 2 needs the text of every record again.  The reference decodes the files a second time; here the text read in
+# pass 1 stays in host memory when the (estimated) decoded size of all files is below this many bytes, so that gzip
+# inputs are inflated once.  Larger inputs are re-read like the reference does.
+KEEP_TEXT_BYTES = int(os.environ.get("PCL_KEEP_TEXT_BYTES", 8 << 30))
+
 # Device chunks hold at least this many read groups whatever ``chunk_size`` asks for (results do not depend on the
 # batching; small chunks only multiply launches and allocations).  Tests lower it to exercise multi-chunk runs.
 MIN_CHUNK_RECORDS = 262144
@@ -101,6 +124,7 @@ class FastqProcessor:
         self.barcode_correct_prob = 0.975        # fastq.rs:39
         self.mismatch_in_barcode = 1             # fastq.rs:40 (no setter in the reference either)
         self._qc = None
+        self._layouts: dict = {}
         self.compute_qc = True
 
     def with_modality(self, modality: str) -> "FastqProcessor":
@@ -122,8 +146,15 @@ class FastqProcessor:
             raise RuntimeError("fastq qc not found")
         return self._qc
 
+    def _layout(self, assay) -> CompiledLayout:
+        """compile_layout reads the whitelist files: once per (assay, modality)."""
+        key = (id(assay), self.modality())
+        if key not in self._layouts:
+            self._layouts[key] = compile_layout(assay, self.modality(), require_files=True)
+        return self._layouts[key]
+
     def is_paired_end(self) -> bool:
-        vals = {is_paired_end(compile_layout(a, self.modality(), require_files=True)) for a in self.assays}
+        vals = {is_paired_end(self._layout(a)) for a in self.assays}
         if len(vals) != 1:
             raise RuntimeError("Not all readers are with the same paired-end status")
         return vals.pop()
@@ -141,7 +172,8 @@ class FastqProcessor:
         cats = np.zeros((4, 3), np.uint64)
         read_ids: List[str] = []
         for assay in self.assays:
-            layout = compile_layout(assay, modality, require_files=True)
+            with _timed("compile_layout+whitelists"):
+                layout = self._layout(assay)
             for p in layout.reads:
                 if p.has_barcode and not p.files:
                     raise RuntimeError(f"Failed to open FASTQ file: {p.read_id}")             # barcode.rs:88-90
@@ -149,7 +181,8 @@ class FastqProcessor:
             for read, info in assay.get_segments_by_modality(modality):
                 if any(e.is_barcode() for e in info) and not read.fastq_paths():
                     raise RuntimeError(f"Failed to open FASTQ file: {read.read_id}")
-            pipes = self._make_pipes(layout)
+            with _timed("pipeline_create"):
+                pipes = self._make_pipes(layout)
             pipe = pipes[0]
             try:
                 for text, results in self._run_assay(pipes, layout, correct_barcode, chunk_size):
@@ -264,10 +297,22 @@ class FastqProcessor:
                     owners.append(pipe)
             finally:
                 trdr.close()
-        rdr = GroupReader(files, strides, qonly, keep_text=False, qual_windows=[pipe.qual_window(r) for r in range(n_reads)])
+        est = 0
+        for fs_ in files:
+            for f in fs_:
+                try:
+                    est += os.path.getsize(f) * (5 if f.endswith((".gz", ".zst", ".bgz")) else 1)
+                except OSError:
+                    pass
+        keep = (not self.device_parse) and est <= KEEP_TEXT_BYTES
+        kept: List[Sequence[FastqBatch]] = []
+        text_bytes = [2 * max(p.max_len, 1024) + 256 for p in layout.reads]
+        rdr = GroupReader(files, strides, qonly, keep_text=keep, text_bytes=text_bytes if keep else None,
+                          qual_windows=[pipe.qual_window(r) for r in range(n_reads)])
         try:
             while not self.device_parse:
-                got = rdr.next(per_chunk)
+                with _timed("pass1_host_read"):
+                    got = rdr.next(per_chunk)
                 if got is None:
                     break
                 n = len(got[0].batch.length)
@@ -279,7 +324,10 @@ class FastqProcessor:
                 own.count(ch)
                 if self.compute_qc:
                     own.qc_accumulate(ch)
-                own.sync()                       # the host planes of this batch go out of scope
+                with _timed("pass1_device_wait"):
+                    own.sync()                   # the host planes of this batch go out of scope
+                if keep:
+                    kept.append(got)
                 chunks.append(ch)
                 sizes.append(n)
                 owners.append(own)
@@ -293,21 +341,26 @@ class FastqProcessor:
         self.num_reads = totals.pop() if totals else 0
 
         # pass 2 (AnnotatedFastqReader): correct, fetch, and rebuild the records from a second read of the files
-        rdr = GroupReader(files, [0] * n_reads, [False] * n_reads, keep_text=True, qual_windows=[(0, 0)] * n_reads,
-                          text_bytes=[2 * max(p.max_len, 1024) + 256 for p in layout.reads])
+        rdr = None if keep else GroupReader(files, [0] * n_reads, [False] * n_reads, keep_text=True, qual_windows=[(0, 0)] * n_reads,
+                                            text_bytes=text_bytes)
         try:
             if correct_barcode:                  # every GPU corrects its chunks while the host re-reads the files
                 for ch, own in zip(chunks, owners):
                     own.correct(ch, self.barcode_correct_prob)
-            for ch, n, own in zip(chunks, sizes, owners):
-                results = [ch.fetch(r) for r in range(n_reads)]
-                text = rdr.next(n)
+            for k, (ch, n, own) in enumerate(zip(chunks, sizes, owners)):
+                with _timed("pass2_fetch"):
+                    results = [ch.fetch(r) for r in range(n_reads)]
+                if keep:
+                    text, kept[k] = kept[k], None
+                else:
+                    text = rdr.next(n)
                 assert text is not None and len(text[0].batch.length) == n
                 yield text, results
                 ch.close()
                 own.chunks.remove(ch)
         finally:
-            rdr.close()
+            if rdr is not None:
+                rdr.close()
 
     @staticmethod
     def _annotate(layout: CompiledLayout, pipe: BarcodePipeline, text: Sequence[FastqBatch], results,
@@ -380,9 +433,12 @@ def make_fastq(assay, *, modality: str, out_dir, correct_barcode: bool = False, 
     proc = FastqProcessor(assay, device=device, devices=devices).with_modality(modality)
     out_dir = os.fspath(out_dir)
     os.makedirs(out_dir, exist_ok=True)
-    paired = proc.is_paired_end()
-    w1 = _zstd.Writer(os.path.join(out_dir, "R1.fq.zst"))
-    w2 = _zstd.Writer(os.path.join(out_dir, "R2.fq.zst")) if paired else None
+    with _timed("is_paired_end"):
+        paired = proc.is_paired_end()
+    # level 9 like the reference (seqspec/src/utils.rs:33-36); it asks for 8 worker threads, here every core up to 16 helps
+    zt = max(1, min(16, os.cpu_count() or 8))
+    w1 = _zstd.Writer(os.path.join(out_dir, "R1.fq.zst"), threads=zt)
+    w2 = _zstd.Writer(os.path.join(out_dir, "R2.fq.zst"), threads=zt) if paired else None
     import ctypes as C
     L = _ffi.lib()
     try:
@@ -409,17 +465,20 @@ def make_fastq(assay, *, modality: str, out_dir, correct_barcode: bool = False, 
             o1 = np.empty(cap1, np.uint8)
             o2 = np.empty(max(cap2, 1), np.uint8)
             u1, u2, nw = C.c_uint64(0), C.c_uint64(0), C.c_uint64(0)
-            _ffi.check(pipe.ctx, L.pcl_make_fastq_batch(pipe.ctx, hr, n, int(correct_barcode), int(paired), o1.ctypes.data, cap1,
-                                                        C.byref(u1), o2.ctypes.data if paired else None, cap2,
-                                                        C.byref(u2) if paired else None, C.byref(nw)))
-            w1.write(o1[:u1.value].tobytes())
-            if w2 is not None:
-                w2.write(o2[:u2.value].tobytes())
+            with _timed("assemble"):
+                _ffi.check(pipe.ctx, L.pcl_make_fastq_batch(pipe.ctx, hr, n, int(correct_barcode), int(paired), o1.ctypes.data, cap1,
+                                                            C.byref(u1), o2.ctypes.data if paired else None, cap2,
+                                                            C.byref(u2) if paired else None, C.byref(nw)))
+            with _timed("zstd_submit"):
+                w1.write(o1[:u1.value])
+                if w2 is not None:
+                    w2.write(o2[:u2.value])
     except _ffi.PclError as e:
         if "unwrap" in str(e):
             raise RuntimeError(str(e)) from e
         raise
     finally:
-        w1.close()
-        if w2 is not None:
-            w2.close()
+        with _timed("zstd_drain"):
+            w1.close()
+            if w2 is not None:
+                w2.close()

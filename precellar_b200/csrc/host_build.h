@@ -262,6 +262,50 @@ inline int pcl_build_read(int r, const pcl_read_desc &rd, DRead *out, pcl_read_i
     return PCL_OK;
 }
 
+// Whitelist byte strings -> marker-form 64-bit keys (file order, duplicates kept), in parallel.  Also tells whether every
+// entry has 16 bases / at most 15 (the two 32-bit table modes).
+inline int pcl_pack_whitelist(const uint8_t *bytes, const uint64_t *offsets, uint64_t n, std::vector<uint64_t> *keys, bool *all16,
+                              bool *all_le15, std::string *err) {
+    keys->resize(n);
+    unsigned T = std::thread::hardware_concurrency();
+    T = std::max(1u, std::min(T ? T : 1u, 16u));
+    if (n < 65536) T = 1;
+    std::vector<int> rc(T, PCL_OK);
+    std::vector<uint64_t> bad_at(T, 0);
+    std::vector<uint8_t> a16(T, 1), a15(T, 1);
+    auto work = [&](unsigned t) {
+        for (uint64_t i = n * t / T, e = n * (t + 1) / T; i < e; ++i) {
+            const uint64_t a = offsets[i], b = offsets[i + 1];
+            if (b < a) { rc[t] = PCL_ERR_ARG; bad_at[t] = i; return; }
+            const uint64_t L = b - a;
+            if (L < 1 || L > PCL_MAX_KEY_LEN) { rc[t] = PCL_ERR_UNSUPPORTED; bad_at[t] = i; return; }
+            uint32_t ninv, ipos;
+            const uint64_t key = pcl_pack_key(bytes + a, 0, (uint32_t)L, false, &ninv, &ipos);
+            if (ninv) { rc[t] = PCL_ERR_UNSUPPORTED + 100; bad_at[t] = i; return; }
+            (*keys)[i] = key;
+            if (L != 16) a16[t] = 0;
+            if (L > 15) a15[t] = 0;
+        }
+    };
+    if (T == 1) work(0);
+    else {
+        std::vector<std::thread> th;
+        for (unsigned t = 0; t < T; ++t) th.emplace_back(work, t);
+        for (auto &x : th) x.join();
+    }
+    *all16 = true; *all_le15 = true;
+    for (unsigned t = 0; t < T; ++t) {
+        if (rc[t] == PCL_ERR_ARG) return pcl_build_fail(err, PCL_ERR_ARG, "whitelist offsets not monotone at %llu", (unsigned long long)bad_at[t]);
+        if (rc[t] == PCL_ERR_UNSUPPORTED) return pcl_build_fail(err, PCL_ERR_UNSUPPORTED, "whitelist entry %llu has a length outside 1..%d",
+                                                                 (unsigned long long)bad_at[t], PCL_MAX_KEY_LEN);
+        if (rc[t] != PCL_OK) return pcl_build_fail(err, PCL_ERR_UNSUPPORTED, "whitelist entry %llu contains a byte outside upper-case ACGT",
+                                                    (unsigned long long)bad_at[t]);
+        *all16 = *all16 && a16[t];
+        *all_le15 = *all_le15 && a15[t];
+    }
+    return PCL_OK;
+}
+
 #define PCL_TABLE_LOAD_PCT 35
 
 struct HostTable {

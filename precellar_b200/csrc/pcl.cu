@@ -14,6 +14,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <unordered_map>
 #include <vector>
 
@@ -21,6 +22,7 @@
 #include "kernels.cuh"
 #include "textparse.cuh"
 #include "group.cuh"
+#include "tablebuild.cuh"
 
 // ------------------------------------------------------------------------------------------
 // NCCL through dlopen: the library has no link-time dependency on libnccl, and inside a process
@@ -77,6 +79,7 @@ struct Table {
     uint32_t *d_index_to_slot = nullptr;
     uint32_t *d_nkeys[4] = {nullptr, nullptr, nullptr, nullptr};
     uint32_t *d_nbits = nullptr;               // 4 x PCL_NBITS_WORDS: bitmaps of the partial keys (DTable::nbits)
+    uint32_t *d_dense = nullptr;               // n_entries counts in whitelist order: what the all-reduce sends
     unsigned long long *d_scalars = nullptr;   // [0] total, [1] mismatch
 };
 
@@ -132,6 +135,7 @@ struct pcl_ctx {
     bool no_plan = false;         // PCL_NO_PLAN=1: AnchorPlan layouts go through the interpreter kernels (tests compare both)
     bool force_generic = false;   // PCL_FORCE_GENERIC=1: only the generic kernels (tests compare both paths)
     bool no_neighbour_tables = false;   // PCL_NO_NEIGHBOUR_TABLES=1: 3*L direct probes instead of the 4 neighbourhood tables
+    uint64_t device_build_min = 100000; // whitelists from this many entries on are deduplicated and hashed on the device (PCL_DEVICE_BUILD_MIN)
     bool no_nbits = false;              // PCL_NO_NBITS=1: no partial-key bitmaps in front of the neighbourhood tables
 };
 
@@ -212,6 +216,11 @@ void prof_end(pcl_ctx *ctx, cudaStream_t s) {
     cudaEventRecord(ctx->evs.back().b, s);
 }
 
+int device_scan(pcl_ctx *ctx, cudaStream_t s, const uint32_t *in, uint32_t *out, uint64_t n, uint32_t *tmp, unsigned long long *d_total);
+int device_radix_sort(pcl_ctx *ctx, cudaStream_t s, unsigned long long **keys, uint32_t **vals, unsigned long long **keys_tmp,
+                      uint32_t **vals_tmp, uint64_t n, uint32_t byte_mask, uint32_t *hist, uint32_t *scan_tmp, unsigned long long *d_scratch);
+uint32_t bytes_used(unsigned long long or_of_keys);
+
 enum { OCC_COUNT = 0, OCC_COUNT_FAST, OCC_COUNT_LENONLY, OCC_ENUM, OCC_FILTER, OCC_CORRECT, OCC_QC, OCC_GATHER, OCC_COUNT_CODES, OCC_COUNT_PLAN, OCC_RESOLVE, OCC_COUNT_PLAN2 };
 
 // every barcode of read r goes through the 32-bit tables (k_filter / k_resolve)
@@ -268,6 +277,7 @@ int pcl_ctx_create(pcl_ctx **out, int device) {
     { const char *g = getenv("PCL_NO_FAST_SPEC"); ctx->no_fast_spec = g && g[0] == '1'; }
     { const char *g = getenv("PCL_NO_NEIGHBOUR_TABLES"); ctx->no_neighbour_tables = g && g[0] == '1'; }
     { const char *g = getenv("PCL_NO_NBITS"); ctx->no_nbits = g && g[0] == '1'; }
+    { const char *g = getenv("PCL_DEVICE_BUILD_MIN"); if (g) ctx->device_build_min = strtoull(g, nullptr, 10); }
     memset(ctx->descs, 0, sizeof ctx->descs);
     memset(ctx->dreads, 0, sizeof ctx->dreads);
     memset(ctx->infos, 0, sizeof ctx->infos);
@@ -353,6 +363,7 @@ static void table_free(Table &t) {
     if (t.d_index_to_slot) cudaFree(t.d_index_to_slot);
     for (int q = 0; q < 4; ++q) if (t.d_nkeys[q]) cudaFree(t.d_nkeys[q]);
     if (t.d_nbits) cudaFree(t.d_nbits);
+    if (t.d_dense) cudaFree(t.d_dense);
     if (t.d_scalars) cudaFree(t.d_scalars);
     t = Table();
 }
@@ -454,12 +465,102 @@ uint32_t pcl_read_stride(const pcl_ctx *ctx, int read_slot) {
 // ------------------------------------------------------------------------------------------
 // whitelist table
 // ------------------------------------------------------------------------------------------
+}  // extern "C"
+
+// Device build of a 32-bit whitelist table (tablebuild.cuh).  Returns PCL_OK, an error, or 1 when the list needs 64-bit keys.
+static int whitelist_load_device(pcl_ctx *ctx, int region_slot, const uint8_t *bytes, const uint64_t *offsets, uint64_t n) {
+    std::vector<uint64_t> hk;
+    bool all16 = true, all_le15 = true;
+    if (int rc = pcl_pack_whitelist(bytes, offsets, n, &hk, &all16, &all_le15, &ctx->err)) return rc;
+    if (!all16 && !all_le15) return 1;
+    if (n >= (1ull << 28)) return fail(ctx, PCL_ERR_UNSUPPORTED, "whitelist too large (%llu entries)", (unsigned long long)n);
+    cudaStream_t s = ctx->stream;
+    unsigned long long *kA = nullptr, *kB = nullptr, *d_tot = nullptr;
+    uint32_t *iA = nullptr, *iB = nullptr, *flag = nullptr, *pos = nullptr, *hist = nullptr, *scan_tmp = nullptr, *dense = nullptr;
+    const uint64_t n_ctas = (n + PCL_SORT_TILE - 1) / PCL_SORT_TILE;
+    std::vector<void *> tmp;
+    auto A = [&](void **p, size_t b) { cudaError_t e = cudaMalloc(p, b ? b : 16); if (e == cudaSuccess) tmp.push_back(*p); return e; };
+    auto done = [&](int code) { for (void *p : tmp) cudaFree(p); return code; };
+#define TCU(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return done(fail(ctx, e_ == cudaErrorMemoryAllocation ? PCL_ERR_NOMEM : PCL_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(e_))); } while (0)
+    TCU(A((void **)&kA, n * 8)); TCU(A((void **)&kB, n * 8)); TCU(A((void **)&iA, n * 4)); TCU(A((void **)&iB, n * 4));
+    TCU(A((void **)&flag, n * 4)); TCU(A((void **)&pos, n * 4)); TCU(A((void **)&dense, n * 4)); TCU(A((void **)&d_tot, 16));
+    TCU(A((void **)&hist, 256 * n_ctas * 4 + 16)); TCU(A((void **)&scan_tmp, (256 * n_ctas / PCL_SCAN_TILE + n / PCL_SCAN_TILE + 4) * 4));
+    // keys in file order stay in `orig`; (key, file index) pairs are sorted to find the duplicates
+    unsigned long long *orig = nullptr;
+    TCU(A((void **)&orig, n * 8));
+    TCU(cudaMemcpyAsync(orig, hk.data(), n * 8, cudaMemcpyHostToDevice, s));
+    TCU(cudaMemcpyAsync(kA, orig, n * 8, cudaMemcpyDeviceToDevice, s));
+    {   // iA = identity: an exclusive scan of ones
+        k_fill_u32<<<grid_for(ctx, n, 8), 256, 0, s>>>(flag, n, 1u);
+        if (int rc = device_scan(ctx, s, flag, iA, n, scan_tmp, d_tot)) return done(rc);
+    }
+    const uint32_t key_bytes_mask = all16 ? 0x1Fu : 0x0Fu;                 // marker-form keys: 33 bits for 16-mers, <= 31 bits otherwise
+    if (int rc = device_radix_sort(ctx, s, &kA, &iA, &kB, &iB, n, key_bytes_mask, hist, scan_tmp, d_tot)) return done(rc);
+    k_wl_mark_first<<<grid_for(ctx, n, 8), 256, 0, s>>>(kA, iA, n, flag);
+    if (int rc = device_scan(ctx, s, flag, pos, n, scan_tmp, d_tot)) return done(rc);
+    k_wl_compact<<<grid_for(ctx, n, 8), 256, 0, s>>>(orig, flag, pos, n, dense);
+    unsigned long long m = 0;
+    // the empty marker of a table of marker-less 16-mers: the largest 32-bit value that is not a key
+    std::vector<unsigned long long> top(std::min<uint64_t>(n, 4096));
+    TCU(cudaMemcpyAsync(&m, d_tot, 8, cudaMemcpyDeviceToHost, s));
+    TCU(cudaMemcpyAsync(top.data(), kA + (n - top.size()), top.size() * 8, cudaMemcpyDeviceToHost, s));
+    TCU(cudaStreamSynchronize(s));
+    uint32_t empty = 0xFFFFFFFFu;
+    if (all16)
+        for (size_t k = top.size(); k-- > 0;) {                            // sorted ascending: walk down from the largest key
+            const uint32_t v = (uint32_t)top[k];
+            if (v == empty) --empty; else if (v < empty) break;
+        }
+    Table &t = ctx->tables[region_slot];
+    table_free(t);
+    const uint32_t spb = 8;
+    uint64_t n_buckets = (100 * m / PCL_TABLE_LOAD_PCT + spb - 1) / spb;
+    if (n_buckets < 2) n_buckets = 2;
+    const uint64_t n_slots = n_buckets * spb;
+    if (n_slots >= (1ull << 29)) return done(fail(ctx, PCL_ERR_UNSUPPORTED, "whitelist too large (%llu entries)", m));
+    auto P = [&](void **p, size_t b) { return cudaMalloc(p, b ? b : 16); };     // persistent allocations: freed by table_free
+    TCU(P(&t.d_keys, n_slots * 4)); TCU(P((void **)&t.d_counts, n_slots * 4)); TCU(P((void **)&t.d_index_to_slot, m * 4));
+    TCU(P((void **)&t.d_scalars, 16)); TCU(P((void **)&t.d_dense, (m + 1) * 4));
+    for (int q = 0; q < 4; ++q) TCU(P((void **)&t.d_nkeys[q], n_slots * 4));
+    const int gfill = grid_for(ctx, n_slots, 8), gins = grid_for(ctx, m, 8);
+    k_fill_u32<<<gfill, 256, 0, s>>>((uint32_t *)t.d_keys, n_slots, empty);
+    k_wl_insert<true><<<gins, 256, 0, s>>>(dense, m, (uint32_t *)t.d_keys, (uint32_t)n_buckets, empty, 0u, t.d_index_to_slot);
+    for (uint32_t q = 0; q < 4; ++q) {
+        k_fill_u32<<<gfill, 256, 0, s>>>(t.d_nkeys[q], n_slots, empty);
+        k_wl_insert<false><<<gins, 256, 0, s>>>(dense, m, t.d_nkeys[q], (uint32_t)n_buckets, empty, q, nullptr);
+    }
+    ctx->launches += 12;
+    TCU(cudaMemsetAsync(t.d_counts, 0, n_slots * 4, s));
+    TCU(cudaMemsetAsync(t.d_scalars, 0, 16, s));
+    for (int q = 0; q < 4; ++q) { t.d.nkeys[q] = t.d_nkeys[q]; t.d.nbits[q] = nullptr; }
+    if (!ctx->no_nbits) {
+        TCU(P((void **)&t.d_nbits, 4ull * PCL_NBITS_WORDS * 4));
+        TCU(cudaMemsetAsync(t.d_nbits, 0, 4ull * PCL_NBITS_WORDS * 4, s));
+        k_build_nbits<<<gfill, PCL_BLOCK, 0, s>>>((const uint32_t *)t.d_keys, n_slots, empty, t.d_nbits, t.d_nbits + PCL_NBITS_WORDS,
+                                                  t.d_nbits + 2 * PCL_NBITS_WORDS, t.d_nbits + 3 * PCL_NBITS_WORDS);
+        for (int q = 0; q < 4; ++q) t.d.nbits[q] = t.d_nbits + (uint64_t)q * PCL_NBITS_WORDS;
+    }
+    TCU(cudaGetLastError());
+    TCU(cudaStreamSynchronize(s));
+#undef TCU
+    t.d.keys = t.d_keys; t.d.counts = t.d_counts; t.d.total = t.d_scalars; t.d.mismatch = t.d_scalars + 1;
+    t.d.empty = empty; t.d.n_buckets = (uint32_t)n_buckets; t.d.mode = all16 ? PCL_TAB_K32_L16 : PCL_TAB_K32_MARKER;
+    t.n_entries = m; t.n_slots = n_slots; t.loaded = true;
+    return done(PCL_OK);
+}
+
+extern "C" {
+
 int pcl_whitelist_load(pcl_ctx *ctx, int region_slot, const uint8_t *bytes, const uint64_t *offsets, uint64_t n) {
     if (!ctx || region_slot < 0 || region_slot >= PCL_MAX_REGIONS) return PCL_ERR_ARG;
     if (n && (!bytes || !offsets)) return fail(ctx, PCL_ERR_ARG, "NULL whitelist buffers");
     if (int r = bind(ctx)) return r;
     if (n == 0)
         return fail(ctx, PCL_ERR_UNSUPPORTED, "region %d has no whitelist: observed-barcode mode (precellar/src/barcode.rs:418-423) is not implemented on the device", region_slot);
+    if (n >= ctx->device_build_min && !ctx->no_neighbour_tables) {
+        const int rc = whitelist_load_device(ctx, region_slot, bytes, offsets, n);
+        if (rc != 1) return rc;                     // 1: not a 32-bit table -> host build below
+    }
     HostTable ht;
     if (int rc = pcl_build_table(bytes, offsets, n, &ht, &ctx->err)) return rc;
     Table &t = ctx->tables[region_slot];
@@ -501,6 +602,7 @@ int pcl_whitelist_load(pcl_ctx *ctx, int region_slot, const uint8_t *bytes, cons
     t.d.mode = ht.mode;
     t.n_entries = m;
     t.n_slots = n_slots;
+    CU(ctx, cudaMalloc(&t.d_dense, (m + 1) * sizeof(uint32_t)));
     t.loaded = true;
     // the uploads above come from pageable memory and the memsets may be asynchronous: nothing else orders them against
     // the (non-blocking) chunk streams
@@ -1034,15 +1136,28 @@ int pcl_counts_allreduce(pcl_ctx *ctx) {
         if (!ctx->comm) return fail(ctx, PCL_ERR_NCCL, "communicator not initialised");
         if (ctx->reduced) return fail(ctx, PCL_ERR_ARG, "the counts were already summed over the ranks (pcl_counts_reset starts a new round)");
         NcclApi &n = nccl();
+        // The counts travel in whitelist order (n_entries words instead of n_slots: a third of the bytes at the table's load
+        // factor), because ranks that built their tables on the device do not agree on slots.
+        for (Table &t : ctx->tables) {
+            if (!t.loaded || !t.n_entries) continue;
+            k_counts_gather32<<<grid_for(ctx, t.n_entries, 8), 256, 0, ctx->stream>>>(t.d_counts, t.d_index_to_slot, t.d_dense, t.n_entries);
+            ctx->launches += 1;
+        }
         n.GroupStart();
         for (Table &t : ctx->tables) {
             if (!t.loaded) continue;
-            int r1 = n.AllReduce(t.d_counts, t.d_counts, t.n_slots, kNcclUint32, kNcclSum, ctx->comm, ctx->stream);
+            int r1 = t.n_entries ? n.AllReduce(t.d_dense, t.d_dense, t.n_entries, kNcclUint32, kNcclSum, ctx->comm, ctx->stream) : 0;
             int r2 = n.AllReduce(t.d_scalars, t.d_scalars, 2, kNcclUint64, kNcclSum, ctx->comm, ctx->stream);
             if (r1 || r2) { n.GroupEnd(); return fail(ctx, PCL_ERR_NCCL, "ncclAllReduce failed (%d,%d)", r1, r2); }
         }
         int r = n.GroupEnd();
         if (r) return fail(ctx, PCL_ERR_NCCL, "ncclGroupEnd: %d", r);
+        for (Table &t : ctx->tables) {
+            if (!t.loaded || !t.n_entries) continue;
+            k_counts_scatter32<<<grid_for(ctx, t.n_entries, 8), 256, 0, ctx->stream>>>(t.d_counts, t.d_index_to_slot, t.d_dense, t.n_entries);
+            ctx->launches += 1;
+        }
+        CU(ctx, cudaGetLastError());
     }
     ctx->reduced = true;
     // ... and every chunk's later work waits for the reduced counts
@@ -1224,15 +1339,14 @@ static inline uint32_t static_coord(const pcl_read_desc &rd, const pcl_read_info
     return (s << 16) | (hi - s);
 }
 
-int pcl_make_fastq_batch(pcl_ctx *ctx, const pcl_host_read *reads, uint64_t n, int correct_barcode, int paired,
-                         uint8_t *r1_out, uint64_t r1_cap, uint64_t *r1_used, uint8_t *r2_out, uint64_t r2_cap,
-                         uint64_t *r2_used, uint64_t *n_written) {
-    if (!ctx || !reads || !r1_out || !r1_used) return PCL_ERR_ARG;
-    if (paired && (!r2_out || !r2_used)) return PCL_ERR_ARG;
+// One contiguous range of read groups -> FASTQ text appended to o1 / o2.  Returns 0 or a negative status with *msg set.
+static int make_fastq_range(const pcl_ctx *ctx, const pcl_host_read *reads, uint64_t i0, uint64_t i1, int correct_barcode, int paired,
+                            std::string &o1, std::string &o2, uint64_t *n_written, std::string *msg) {
     const int nr = ctx->n_reads;
-    uint64_t u1 = *r1_used, u2 = r2_used ? *r2_used : 0, written = 0;
+    uint64_t written = 0;
     std::string bseq, bqual, corr, useq, uqual, piece;
-    for (uint64_t i = 0; i < n; ++i) {
+    auto bad = [&](int code, const char *m) { *msg = m; return code; };
+    for (uint64_t i = i0; i < i1; ++i) {
         bseq.clear(); bqual.clear(); corr.clear(); useq.clear(); uqual.clear();
         bool has_bc = false, all_ok = true;
         int bc_def = -1, r1_file = -1, r2_file = -1;
@@ -1243,7 +1357,7 @@ int pcl_make_fastq_batch(pcl_ctx *ctx, const pcl_host_read *reads, uint64_t n, i
             const pcl_host_read &h = reads[r];
             const uint32_t fs = h.res.fstatus[i];
             const uint32_t st = fs & 3u;
-            if (st == PCL_SPLIT_MULTI_TARGET) return fail(ctx, PCL_ERR_INPUT, "Multiple target regions found in one fastq record!");
+            if (st == PCL_SPLIT_MULTI_TARGET) return bad(PCL_ERR_INPUT, "Multiple target regions found in one fastq record!");
             if (st != PCL_SPLIT_OK) continue;                                    // a defect file contributes nothing
             uint32_t L = h.len[i];
             if (rd.max_len && L > rd.max_len) L = rd.max_len;
@@ -1253,7 +1367,7 @@ int pcl_make_fastq_batch(pcl_ctx *ctx, const pcl_host_read *reads, uint64_t n, i
                 if (code == PCL_BC_ABSENT) continue;
                 const uint32_t e = inf.bc_elem[j];
                 const uint32_t c = inf.fixed_layout ? static_coord(rd, inf, e, L) : h.res.bcoord[j][i];
-                if (c == PCL_COORD_ABSENT) return fail(ctx, PCL_ERR_INPUT, "inconsistent barcode coordinates");
+                if (c == PCL_COORD_ABSENT) return bad(PCL_ERR_INPUT, "inconsistent barcode coordinates");
                 const uint32_t s0 = c >> 16, ln = c & 0xFFFFu;
                 piece.clear();
                 if (rd.is_reverse) { rc_append(piece, seq + s0, ln); rev_append(bqual, qual + s0, ln); }
@@ -1267,7 +1381,7 @@ int pcl_make_fastq_batch(pcl_ctx *ctx, const pcl_host_read *reads, uint64_t n, i
                     if (inf.bc_key_bytes[j] == 4 && rd.elems[e].min_len == 16 && rd.elems[e].max_len == 16) key |= 1ull << 32;
                     char buf[40];
                     const int kl = pcl_key_decode(key, buf);
-                    if (kl < 0) return fail(ctx, PCL_ERR_INPUT, "corrupt corrected key");
+                    if (kl < 0) return bad(PCL_ERR_INPUT, "corrupt corrected key");
                     corr.append(buf, kl);
                 } else all_ok = false;
             }
@@ -1283,53 +1397,87 @@ int pcl_make_fastq_batch(pcl_ctx *ctx, const pcl_host_read *reads, uint64_t n, i
             }
             if (inf.has_target && (fs & PCL_FSTATUS_TARGET)) {
                 if (rd.is_reverse) {
-                    if (r2_file >= 0) return fail(ctx, PCL_ERR_INPUT, "Read2 already exists");
+                    if (r2_file >= 0) return bad(PCL_ERR_INPUT, "Read2 already exists");
                     r2_file = r; r2c = h.res.tcoord[i];
                 } else {
-                    if (r1_file >= 0) return fail(ctx, PCL_ERR_INPUT, "Read1 already exists");
+                    if (r1_file >= 0) return bad(PCL_ERR_INPUT, "Read1 already exists");
                     r1_file = r; r1c = h.res.tcoord[i];
                 }
             }
         }
         if (!has_bc) continue;                                                   // dropped by process_chunk (fastq.rs:381-385)
         if (correct_barcode && !all_ok) continue;                                // lib.rs:154
-        if (r1_file < 0) return fail(ctx, PCL_ERR_INPUT, "called `Option::unwrap()` on a `None` value: read1");
-        if (paired && r2_file < 0) return fail(ctx, PCL_ERR_INPUT, "called `Option::unwrap()` on a `None` value: read2");
+        if (r1_file < 0) return bad(PCL_ERR_INPUT, "called `Option::unwrap()` on a `None` value: read1");
+        if (paired && r2_file < 0) return bad(PCL_ERR_INPUT, "called `Option::unwrap()` on a `None` value: read2");
         {
             const pcl_host_read &hb = reads[bc_def], &h1 = reads[r1_file];
-            const uint8_t *def = hb.text + hb.off[3 * i];
-            const uint64_t dl = hb.off[3 * i + 1] - hb.off[3 * i];
             const uint32_t s0 = r1c >> 16, ln = r1c & 0xFFFFu;
-            const uint64_t need = 1 + dl + 1 + corr.size() + useq.size() + ln + 3 + bqual.size() + uqual.size() + ln + 1;
-            if (u1 + need > r1_cap) return fail(ctx, PCL_ERR_NOMEM, "R1 output buffer too small");
-            uint8_t *o = r1_out + u1;
-            *o++ = '@'; memcpy(o, def, dl); o += dl; *o++ = '\n';
-            memcpy(o, corr.data(), corr.size()); o += corr.size();
-            memcpy(o, useq.data(), useq.size()); o += useq.size();
-            memcpy(o, h1.text + h1.off[3 * i + 1] + s0, ln); o += ln;
-            *o++ = '\n'; *o++ = '+'; *o++ = '\n';
-            memcpy(o, bqual.data(), bqual.size()); o += bqual.size();
-            memcpy(o, uqual.data(), uqual.size()); o += uqual.size();
-            memcpy(o, h1.text + h1.off[3 * i + 2] + s0, ln); o += ln;
-            *o++ = '\n';
-            u1 += need;
+            o1 += '@'; o1.append((const char *)hb.text + hb.off[3 * i], hb.off[3 * i + 1] - hb.off[3 * i]); o1 += '\n';
+            o1 += corr; o1 += useq; o1.append((const char *)h1.text + h1.off[3 * i + 1] + s0, ln);
+            o1 += "\n+\n";
+            o1 += bqual; o1 += uqual; o1.append((const char *)h1.text + h1.off[3 * i + 2] + s0, ln);
+            o1 += '\n';
         }
         if (paired) {
             const pcl_host_read &h2 = reads[r2_file];
-            const uint8_t *def = h2.text + h2.off[3 * i];
-            const uint64_t dl = h2.off[3 * i + 1] - h2.off[3 * i];
             const uint32_t s0 = r2c >> 16, ln = r2c & 0xFFFFu;
-            const uint64_t need = 1 + dl + 1 + ln + 3 + ln + 1;
-            if (u2 + need > r2_cap) return fail(ctx, PCL_ERR_NOMEM, "R2 output buffer too small");
-            uint8_t *o = r2_out + u2;
-            *o++ = '@'; memcpy(o, def, dl); o += dl; *o++ = '\n';
-            memcpy(o, h2.text + h2.off[3 * i + 1] + s0, ln); o += ln;
-            *o++ = '\n'; *o++ = '+'; *o++ = '\n';
-            memcpy(o, h2.text + h2.off[3 * i + 2] + s0, ln); o += ln;
-            *o++ = '\n';
-            u2 += need;
+            o2 += '@'; o2.append((const char *)h2.text + h2.off[3 * i], h2.off[3 * i + 1] - h2.off[3 * i]); o2 += '\n';
+            o2.append((const char *)h2.text + h2.off[3 * i + 1] + s0, ln);
+            o2 += "\n+\n";
+            o2.append((const char *)h2.text + h2.off[3 * i + 2] + s0, ln);
+            o2 += '\n';
         }
         ++written;
+    }
+    *n_written = written;
+    return PCL_OK;
+}
+
+int pcl_make_fastq_batch(pcl_ctx *ctx, const pcl_host_read *reads, uint64_t n, int correct_barcode, int paired,
+                         uint8_t *r1_out, uint64_t r1_cap, uint64_t *r1_used, uint8_t *r2_out, uint64_t r2_cap,
+                         uint64_t *r2_used, uint64_t *n_written) {
+    if (!ctx || !reads || !r1_out || !r1_used) return PCL_ERR_ARG;
+    if (paired && (!r2_out || !r2_used)) return PCL_ERR_ARG;
+    // contiguous ranges, one host thread each (the reference joins its records under rayon, fastq.rs:341-348); the pieces
+    // are concatenated in range order, so the output does not depend on the number of threads
+    unsigned T = std::thread::hardware_concurrency();
+    T = std::max(1u, std::min(T ? T : 1u, 16u));
+    if (n < 32768) T = 1;
+    std::vector<std::string> o1(T), o2(T), msgs(T);
+    std::vector<uint64_t> wr(T, 0);
+    std::vector<int> rcs(T, PCL_OK);
+    auto work = [&](unsigned t) {
+        const uint64_t i0 = n * t / T, i1 = n * (t + 1) / T;
+        o1[t].reserve((size_t)((i1 - i0) * 200));
+        if (paired) o2[t].reserve((size_t)((i1 - i0) * 160));
+        rcs[t] = make_fastq_range(ctx, reads, i0, i1, correct_barcode, paired, o1[t], o2[t], &wr[t], &msgs[t]);
+    };
+    if (T == 1) work(0);
+    else {
+        std::vector<std::thread> th;
+        for (unsigned t = 0; t < T; ++t) th.emplace_back(work, t);
+        for (auto &x : th) x.join();
+    }
+    uint64_t u1 = *r1_used, u2 = r2_used ? *r2_used : 0, written = 0;
+    std::vector<uint64_t> at1(T), at2(T);
+    for (unsigned t = 0; t < T; ++t) {
+        if (rcs[t] != PCL_OK) return fail(ctx, rcs[t], "%s", msgs[t].c_str());      // the first failing range in input order
+        at1[t] = u1; at2[t] = u2;
+        u1 += o1[t].size();
+        if (paired) u2 += o2[t].size();
+        written += wr[t];
+    }
+    if (u1 > r1_cap) return fail(ctx, PCL_ERR_NOMEM, "R1 output buffer too small");
+    if (paired && u2 > r2_cap) return fail(ctx, PCL_ERR_NOMEM, "R2 output buffer too small");
+    auto place = [&](unsigned t) {
+        memcpy(r1_out + at1[t], o1[t].data(), o1[t].size());
+        if (paired) memcpy(r2_out + at2[t], o2[t].data(), o2[t].size());
+    };
+    if (T == 1) place(0);
+    else {
+        std::vector<std::thread> th;
+        for (unsigned t = 0; t < T; ++t) th.emplace_back(place, t);
+        for (auto &x : th) x.join();
     }
     *r1_used = u1;
     if (r2_used) *r2_used = u2;

@@ -68,7 +68,8 @@ class FastqReader:
             return None
         g = int(got)
         hb = HostBatch(None if seq is None else seq[:g], None if qual is None else qual[:g], length[:g])
-        return FastqBatch(hb, nh[:g], text[:used.value] if keep_text else None, off[:3 * g + 1] if keep_text else None)
+        # (the arena is sized for the worst case: keep only what was written)
+        return FastqBatch(hb, nh[:g], text[:used.value].copy() if keep_text else None, off[:3 * g + 1].copy() if keep_text else None)
 
     def close(self):
         if self.h:

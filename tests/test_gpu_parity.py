@@ -306,6 +306,50 @@ def test_multiome_config_rna_and_atac_pipelines_resident_together():
             pipe.close()
 
 
+def test_device_built_table_with_duplicates_and_both_build_paths(monkeypatch):
+    """Whitelists of >= 100 K entries are deduplicated (first occurrence wins: IndexSet, region.rs:459-469) and hashed on
+    the device (tablebuild.cuh); smaller ones on the host.  The same list with duplicates through both paths: counts in
+    whitelist order, corrected barcodes and statuses equal the oracle."""
+    from oracle import pyoracle as O
+    from precellar_b200.configs import v3_layout
+    from precellar_b200.pipeline import BarcodePipeline
+    from tools import synth as S
+    from tools.v3check import compare_bulk
+    n_unique, n = 150_000, 1_000_000
+    base = S.make_whitelist(n_unique, 16, seed=77)
+    rng = np.random.default_rng(5)
+    dup_src = rng.integers(0, n_unique, 30_000)
+    order = np.concatenate([np.arange(n_unique), dup_src])
+    rng.shuffle(order)
+    wl = base[order]                                           # 180 K lines, 30 K of them repeats
+    _, first = np.unique(order, return_index=True)
+    uniq_in_file_order = wl[np.sort(first)]                    # what IndexSet keeps
+    syn = S.Synth(S.SynthSpec(n_unique, n_cells=3000), uniq_in_file_order)
+    seq, qual, length = syn.host_arrays(0, n)
+    l2 = np.full(n, 91, np.uint16)
+    layout_dup = v3_layout(wl, 91)
+    layout_ref = v3_layout(uniq_in_file_order, 91)
+    orc = O.Oracle(O.reads_from_layout(layout_dup), {0: (wl.reshape(-1), np.arange(len(wl) + 1, dtype=np.uint64) * np.uint64(16), n_unique)})
+    orc.set_input(0, seq, qual, length, 32)
+    orc.set_input(1, None, None, l2, 0)
+    orc.count()
+    ores = orc.annotate(correct=True, threshold=0.975, n_threads=16)
+    ocounts = {0: orc.counts(0)}
+    for min_device in ("1000", "100000000"):                   # device build, then host build
+        monkeypatch.setenv("PCL_DEVICE_BUILD_MIN", min_device)
+        pipe = BarcodePipeline(layout_dup)
+        try:
+            assert pipe.whitelist_size(0) == n_unique
+            from precellar_b200.pipeline import HostBatch
+            dev = [pipe.host_planes(0, seq, qual, length), HostBatch(None, None, l2)]
+            results = pipe.run(dev, correct=True, threshold=0.975)
+            counts = {0: pipe.counts(0)}
+            fields = compare_bulk(layout_ref, pipe.infos, results, counts, ores, ocounts)
+            assert sum(fields.values()) == 0, (min_device, fields)
+        finally:
+            pipe.close()
+
+
 def test_sci3_config_variable_hairpin_and_anchor():
     """BASELINE configs[3] shape (sci-RNA-seq3: hairpin 9|10 + CAGAGC anchor + UMI 8 + RT 10), 3 M pairs through the
     element-table interpreter kernel; includes anchor mismatches (defect records)."""
