@@ -136,6 +136,7 @@ struct pcl_ctx {
     bool force_generic = false;   // PCL_FORCE_GENERIC=1: only the generic kernels (tests compare both paths)
     bool no_neighbour_tables = false;   // PCL_NO_NEIGHBOUR_TABLES=1: 3*L direct probes instead of the 4 neighbourhood tables
     uint64_t device_build_min = 100000; // whitelists from this many entries on are deduplicated and hashed on the device (PCL_DEVICE_BUILD_MIN)
+    bool reduce_after_filter = false;   // PCL_REDUCE_AFTER_FILTER=1: the all-reduce waits for k_filter instead of overlapping it (experiments)
     bool no_nbits = false;              // PCL_NO_NBITS=1: no partial-key bitmaps in front of the neighbourhood tables
 };
 
@@ -277,6 +278,7 @@ int pcl_ctx_create(pcl_ctx **out, int device) {
     { const char *g = getenv("PCL_NO_FAST_SPEC"); ctx->no_fast_spec = g && g[0] == '1'; }
     { const char *g = getenv("PCL_NO_NEIGHBOUR_TABLES"); ctx->no_neighbour_tables = g && g[0] == '1'; }
     { const char *g = getenv("PCL_NO_NBITS"); ctx->no_nbits = g && g[0] == '1'; }
+    { const char *g = getenv("PCL_REDUCE_AFTER_FILTER"); ctx->reduce_after_filter = g && g[0] == '1'; }
     { const char *g = getenv("PCL_DEVICE_BUILD_MIN"); if (g) ctx->device_build_min = strtoull(g, nullptr, 10); }
     memset(ctx->descs, 0, sizeof ctx->descs);
     memset(ctx->dreads, 0, sizeof ctx->dreads);
@@ -1108,12 +1110,13 @@ int pcl_count(pcl_ctx *ctx, pcl_chunk *c) {
         CU(ctx, cudaGetLastError());
         ctx->qc_reads[r] += c->n;
         if (oi + 1 == n_with_bc) {
-            CU(ctx, cudaEventRecord(c->ev_counted, c->stream)); c->counted = true;
+            if (!ctx->reduce_after_filter) { CU(ctx, cudaEventRecord(c->ev_counted, c->stream)); c->counted = true; }
             // The neighbourhood filter of pass 2 needs no counts: it runs here, behind the event the all-reduce waits for,
             // so on several GPUs the exchange of the counts is hidden under it.
             for (int k = 0; k < n_with_bc; ++k)
                 if (read_all32(ctx, order[k]) && c->rb[order[k]].wl_key)
                     if (int rc = launch_filter(ctx, c, order[k])) return rc;
+            if (ctx->reduce_after_filter) { CU(ctx, cudaEventRecord(c->ev_counted, c->stream)); c->counted = true; }
         }
     }
     return PCL_OK;
