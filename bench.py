@@ -489,7 +489,7 @@ def main():
     ap.add_argument("--no-other", action="store_true", help="skip the other BASELINE configurations")
     ap.add_argument("--other-n", type=int, default=0, help="read groups per other configuration (default: BASELINE sizes)")
     ap.add_argument("--ingest-sample", type=int, default=1_000_000)
-    ap.add_argument("--api-sample", type=int, default=1_000_000, help="read triples of the API end-to-end leg (0: skip)")
+    ap.add_argument("--api-sample", type=int, default=2_000_000, help="read triples of the API end-to-end leg (0: skip)")
     args = ap.parse_args()
 
     rank, local_rank, world = env_int("RANK", 0), env_int("LOCAL_RANK", 0), env_int("WORLD_SIZE", 1)
@@ -660,25 +660,44 @@ def main():
             r1 = ReadResults(pipe.infos[0], fs1_h[lo:hi], None, [bck_h[lo:hi]], [umi_h[lo:hi]], [None], [None])
             r2 = ReadResults(pipe.infos[1], fs2_h[lo:hi], tc2_h[lo:hi], [], [], [], [])
             outs.append((r1, r2))
-        h2d = n * (st1 + qs + 2 + 2)
-        d2h = n * (2 + 4 + 4 + 2 + 4)
+        # Batch metadata an ingest stage has for free (min / max record length while parsing): when a read file's records
+        # all have one length, its length plane stays on the host (pcl_chunk_set_uniform_len) and the result planes of an
+        # insert read come back as one (fstatus, tcoord) pair per chunk (pcl_chunk_uniform_results_async).
+        uni1 = int(len_h.min()) == int(len_h.max())
+        uni2 = int(len2_h.min()) == int(len2_h.max())
+        L1u, L2u = int(len_h[0]), int(len2_h[0])
+        uni_res, _p10 = pinned(nc * 16, np.uint32, (nc, 4))
+        h2d = n * (st1 + qs + (0 if uni1 else 2) + (0 if uni2 else 2))
+        d2h = n * (2 + 4 + 4 + (0 if uni2 else 2 + 4)) + (16 * nc if uni2 else 0)
 
         def step_e2e():
             pipe.reset_counts()
             for c, ch in enumerate(chunks):
                 lo, hi = int(bounds[c]), int(bounds[c + 1])
                 ch.reset(hi - lo)
-                ch.upload_compact(0, HostBatch(seq_h[lo:hi], qual_h[lo:hi], len_h[lo:hi]))
-                ch.upload(1, HostBatch(None, None, len2_h[lo:hi]))
+                if uni1:
+                    ch.set_uniform_len(0, L1u)
+                ch.upload_compact(0, HostBatch(seq_h[lo:hi], qual_h[lo:hi], None if uni1 else len_h[lo:hi]))
+                if uni2:
+                    ch.set_uniform_len(1, L2u)
+                else:
+                    ch.upload(1, HostBatch(None, None, len2_h[lo:hi]))
                 pipe.count(ch)
                 # UMI keys and insert coordinates are final after pass 1: they travel back while later chunks upload
                 ch.fetch(0, outs[c][0], wait=False, planes=("umi_key",))
-                ch.fetch(1, outs[c][1], wait=False)
+                if uni2:
+                    ch.uniform_results_async(1, uni_res[c])
+                else:
+                    ch.fetch(1, outs[c][1], wait=False)
             pipe.allreduce()
             for c, ch in enumerate(chunks):
                 pipe.correct(ch, THRESHOLD)
                 ch.fetch(0, outs[c][0], wait=False, planes=("fstatus", "bc_key"))
             pipe.sync()
+            if uni2:
+                for c, ch in enumerate(chunks):
+                    if uni_res[c, 0] != 1:                    # not constant after all: the planes themselves
+                        ch.fetch(1, outs[c][1])
 
         for _ in range(2):
             step_e2e()
@@ -692,13 +711,16 @@ def main():
         e2e = {"value": n * world / dt, "unit": "read-pairs/s", "h2d_bytes_per_step": int(h2d) * world,
                "d2h_bytes_per_step": int(d2h) * world, "h2d_bytes_per_step_per_gpu": int(h2d),
                "d2h_bytes_per_step_per_gpu": int(d2h), "ms_per_step": dt * 1e3, "chunks": nc,
-               "note": "pinned host SoA planes (R1 rows of the 28 bytes the layout uses, widened to 32 on the device) -> H2D -> count -> allreduce -> correct -> D2H of every result plane"}
+               "uniform_lengths": [bool(uni1), bool(uni2)],
+               "note": "pinned host SoA planes (R1 rows of the 28 bytes the layout uses, widened to 32 on the device) -> H2D -> count -> allreduce -> correct -> D2H of every result plane; "
+                       "read files whose records all have one length send no length plane, and an insert read's constant result planes come back as one (fstatus, tcoord) pair per chunk"}
         for ch in chunks:
             ch.close()
             pipe.chunks.remove(ch)
-        for ptr in (_p1, _p2, _p3, _p4, _p5, _p6, _p7, _p8, _p9):
+        assert not uni2 or (uni_res[:, 0] == 1).all()
+        for ptr in (_p1, _p2, _p3, _p4, _p5, _p6, _p7, _p8, _p9, _p10):
             _ffi.lib().pcl_host_free(ptr)
-        del seq_h, qual_h, len_h, len2_h, fs1_h, bck_h, umi_h, fs2_h, tc2_h, outs
+        del seq_h, qual_h, len_h, len2_h, fs1_h, bck_h, umi_h, fs2_h, tc2_h, outs, uni_res
 
     # ------------------------------------------------------------------ parity (every rank takes part) + CPU baseline
     parity = cpu_baseline = None

@@ -209,6 +209,15 @@ int pcl_chunk_upload(pcl_chunk *chunk, int read_slot, const uint8_t *seq, const 
 int pcl_chunk_upload_compact(pcl_chunk *chunk, int read_slot, const uint8_t *seq, uint32_t row_bytes, const uint8_t *qual,
                              const uint16_t *len);
 uint32_t pcl_read_payload_bytes(const pcl_ctx *ctx, int read_slot);
+/* Every record of this read file has the same length (the usual case for a sequencing run): the length plane is filled
+ * on the device and never crosses PCIe; later pcl_chunk_upload* calls on this slot may pass len == NULL (until the next
+ * pcl_chunk_reset).  For a read that uploads lengths only (an insert read) this call alone makes the slot ready. */
+int pcl_chunk_set_uniform_len(pcl_chunk *chunk, int read_slot, uint16_t len);
+/* The result planes of an insert read are the same for every record when all lengths agree (fstatus, trimmed insert
+ * coordinates).  This asks the device whether they are and brings back 16 bytes instead of 6 per record: stream-ordered,
+ * `out` (pinned) is valid after pcl_sync / a blocking fetch.  uniform == 0: fetch the planes with pcl_chunk_fetch. */
+typedef struct { uint32_t uniform, fstatus, tcoord, reserved; } pcl_uniform_result;
+int pcl_chunk_uniform_results_async(pcl_chunk *chunk, int read_slot, pcl_uniform_result *out);
 /* Zero-copy producers (a GPU-side decoder or generator) may fill the device planes directly. */
 int pcl_chunk_device_ptrs(pcl_chunk *chunk, int read_slot, void **seq, void **qual, void **len);
 void *pcl_chunk_stream(pcl_chunk *chunk);                        /* cudaStream_t of the chunk        */

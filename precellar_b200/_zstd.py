@@ -48,12 +48,15 @@ def _check(code: int) -> int:
     return code
 
 
-def compress(data: bytes, level: int = 9) -> bytes:
-    """One frame (the reference's default level for zstd outputs is 9, seqspec/src/utils.rs:33-35)."""
+def compress(data, level: int = 9) -> bytes:
+    """One frame (the reference's default level for zstd outputs is 9, seqspec/src/utils.rs:33-35).  `data`: bytes, or a
+    writable contiguous buffer (memoryview / numpy slice), which is compressed in place without a copy."""
     L = lib()
-    cap = L.ZSTD_compressBound(len(data))
+    n_in = len(data)
+    cap = L.ZSTD_compressBound(n_in)
     out = C.create_string_buffer(cap)
-    n = _check(L.ZSTD_compress(out, cap, data, len(data), level))
+    src = data if isinstance(data, (bytes, bytearray)) and not isinstance(data, bytearray) else (C.c_char * n_in).from_buffer(data)
+    n = _check(L.ZSTD_compress(out, cap, src, n_in, level))
     return out.raw[:n]
 
 
@@ -113,11 +116,12 @@ class Writer:
         self._drain(self.max_pending)
 
     def write(self, data) -> None:
-        mv = memoryview(data)
-        if not self.buf and len(mv) >= self.block:          # large appends: cut frames straight out of the caller's buffer
-            k = 0
+        mv = memoryview(data).cast("B")
+        if not self.buf and len(mv) >= self.block:          # large appends: frames straight out of the caller's buffer,
+            k = 0                                           # no copy when it is writable (the slices keep it alive)
             while len(mv) - k >= self.block:
-                self._submit(bytes(mv[k:k + self.block]))
+                piece = mv[k:k + self.block]
+                self._submit(piece if not mv.readonly else bytes(piece))
                 k += self.block
             mv = mv[k:]
         self.buf += mv

@@ -188,6 +188,52 @@ int64_t pcl_fastq_read(pcl_fastq *r, uint64_t max_records, uint32_t stride, uint
     uint64_t n = 0, used = text_used ? *text_used : 0;
     if (off && n == 0) off[0] = used;
     while (n < max_records) {
+        // Fast route: the four lines of the record lie inside the decode buffer -> no per-line string copies.
+        // (Blank lines between records, "\r\n" and records that straddle a refill take the general route below.)
+        if (r->pos < r->end && r->buf[r->pos] == '@') {
+            const uint8_t *p0 = r->buf.data() + r->pos, *pe = r->buf.data() + r->end;
+            const uint8_t *e0 = (const uint8_t *)memchr(p0, '\n', pe - p0);
+            const uint8_t *e1 = e0 ? (const uint8_t *)memchr(e0 + 1, '\n', pe - (e0 + 1)) : nullptr;
+            const uint8_t *e2 = e1 ? (const uint8_t *)memchr(e1 + 1, '\n', pe - (e1 + 1)) : nullptr;
+            const uint8_t *e3 = e2 ? (const uint8_t *)memchr(e2 + 1, '\n', pe - (e2 + 1)) : nullptr;
+            if (e3 && e0 > p0 && e0[-1] != '\r' && e1[-1] != '\r' && e3[-1] != '\r' && e1 + 1 < e2 && e1[1] == '+' &&
+                (size_t)(e1 - (e0 + 1)) == (size_t)(e3 - (e2 + 1))) {
+                const uint8_t *sq = e0 + 1, *ql = e2 + 1;
+                const size_t L = (size_t)(e1 - sq), dlen = (size_t)(e0 - p0);        // dlen counts the '@'
+                len[n] = (uint16_t)(L > 65535 ? 65535 : L);
+                if (seq && stride) {
+                    const size_t c = L < stride ? L : stride;
+                    uint8_t *ds = seq + n * (uint64_t)stride;
+                    memcpy(ds, sq, c);
+                    if (c < stride) memset(ds + c, 'N', stride - c);
+                }
+                if (qual && qual_stride) {
+                    const size_t avail = L > qual_offset ? L - qual_offset : 0;
+                    const size_t c = avail < qual_stride ? avail : qual_stride;
+                    uint8_t *dq = qual + n * (uint64_t)qual_stride;
+                    if (c) memcpy(dq, ql + qual_offset, c);
+                    if (c < qual_stride) memset(dq + c, '!', qual_stride - c);
+                }
+                size_t e = 1;
+                while (e < dlen && p0[e] != ' ' && p0[e] != '\t') ++e;
+                size_t name_len = e - 1;
+                if (name_len > 2 && p0[e - 2] == '/' && (p0[e - 1] == '1' || p0[e - 1] == '2')) name_len -= 2;   // strip_fq_suffix
+                if (name_hash) name_hash[n] = fnv1a((const char *)p0 + 1, name_len);
+                if (text && off) {
+                    const uint64_t need = (dlen - 1) + 2 * L;
+                    if (used + need > text_cap) { r->err = "text arena too small"; return PCL_ERR_NOMEM; }
+                    memcpy(text + used, p0 + 1, name_len); used += name_len;
+                    memcpy(text + used, p0 + e, dlen - e); used += dlen - e;
+                    off[3 * n + 1] = used;
+                    memcpy(text + used, sq, L); used += L; off[3 * n + 2] = used;
+                    memcpy(text + used, ql, L); used += L; off[3 * n + 3] = used;
+                }
+                r->pos = (size_t)(e3 - r->buf.data()) + 1;
+                ++n;
+                ++r->n_records;
+                continue;
+            }
+        }
         if (!r->getline(r->line[0])) break;
         if (r->line[0].empty()) continue;                         // stray blank line between records
         if (r->line[0][0] != '@') { r->err = "FASTQ record " + std::to_string(r->n_records) + " does not start with '@'"; return PCL_ERR_INPUT; }

@@ -1204,6 +1204,26 @@ __global__ void __launch_bounds__(PCL_BLOCK) k_qc(const __grid_constant__ QcPara
     }
 }
 
+// pcl_chunk_set_uniform_len: every record of the read file has the same length (nothing travels over PCIe for the plane)
+__global__ void __launch_bounds__(PCL_BLOCK) k_fill_len(uint16_t *__restrict__ len, uint64_t n, uint16_t v) {
+    uint32_t *w = reinterpret_cast<uint32_t *>(len);
+    const uint32_t vv = (uint32_t)v | ((uint32_t)v << 16);
+    const uint64_t nw = (n + 1) >> 1;                               // the plane is allocated with slack
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nw; i += (uint64_t)gridDim.x * blockDim.x) w[i] = vv;
+}
+
+// pcl_chunk_uniform_results_async: do all records of a read file carry the same fstatus and insert coordinates?
+// out[0] = 1 if so (0 otherwise), out[1] = fstatus of record 0, out[2] = its tcoord.  out[0] must be 1 on entry.
+__global__ void __launch_bounds__(PCL_BLOCK) k_uniform_check(const uint16_t *__restrict__ fstatus, const uint32_t *__restrict__ tcoord, uint64_t n,
+                                                            uint32_t *out) {
+    const uint32_t f0 = fstatus[0], t0 = tcoord ? tcoord[0] : 0u;
+    bool same = true;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x)
+        same = same && fstatus[i] == f0 && (!tcoord || tcoord[i] == t0);
+    if (!__all_sync(0xFFFFFFFFu, same) && (threadIdx.x & 31u) == 0) atomicExch(out, 0u);
+    if (blockIdx.x == 0 && threadIdx.x == 0) { out[1] = f0; out[2] = t0; }
+}
+
 // counts in whitelist order for pcl_counts_fetch
 __global__ void k_gather_counts(const uint32_t *__restrict__ counts, const uint32_t *__restrict__ index_to_slot,
                                 unsigned long long *__restrict__ out, uint64_t n) {

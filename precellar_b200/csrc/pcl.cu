@@ -154,6 +154,8 @@ struct ReadBuf {
     uint32_t *wl_key = nullptr;               // reads whose tables are all 32-bit: packed key and candidate mask per entry
     unsigned long long *wl_cand = nullptr;
     bool filtered = false;                    // k_filter has run on the current worklist
+    bool uniform_len = false;                 // pcl_chunk_set_uniform_len since the last reset: uploads may pass len == NULL
+    uint32_t *d_uniform = nullptr;            // pcl_chunk_uniform_results_async: flag, fstatus, tcoord
     uint8_t *seq_stage = nullptr;             // pcl_chunk_upload_compact: the rows as uploaded, before k_repack_rows
     bool filled = false;
     // device-side text parse (pcl_text_*): name hashes and the small result words of this chunk's parse
@@ -644,7 +646,16 @@ int pcl_chunk_create(pcl_ctx *ctx, uint64_t capacity_records, pcl_chunk **out) {
     c->cap = capacity_records;
     const uint64_t cap = capacity_records;
     int rc = PCL_OK;
-    auto A = [&](void **p, size_t bytes) { if (rc == PCL_OK) rc = chunk_alloc(c, p, bytes); };
+    // every plane of the chunk comes out of ONE device allocation (cudaMalloc / cudaFree are slow and synchronise: an API run
+    // that creates a chunk per batch used to spend more time in them than in the kernels)
+    std::vector<std::pair<void **, size_t>> wants;
+    size_t slab_bytes = 0;
+    auto A = [&](void **p, size_t bytes) {
+        if (bytes == 0) bytes = 16;
+        bytes = (bytes + 255) & ~(size_t)255;
+        wants.push_back({p, slab_bytes});
+        slab_bytes += bytes;
+    };
     if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreateWithFlags(&c->ev, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&c->ev_counted, cudaEventDisableTiming) != cudaSuccess ||
@@ -678,6 +689,11 @@ int pcl_chunk_create(pcl_ctx *ctx, uint64_t capacity_records, pcl_chunk **out) {
             if (k32) { A((void **)&b.wl_key, wl_cap * 4); A((void **)&b.wl_cand, wl_cap * 8); }
         }
         A((void **)&b.wl_count, 16);
+    }
+    if (rc == PCL_OK) {
+        void *slab = nullptr;
+        rc = chunk_alloc(c, &slab, slab_bytes);
+        if (rc == PCL_OK) for (auto &w : wants) *w.first = (uint8_t *)slab + w.second;
     }
     if (rc != PCL_OK) {
         for (void *p : c->allocs) cudaFree(p);
@@ -714,7 +730,42 @@ int pcl_chunk_reset(pcl_chunk *c, uint64_t n_records) {
     if (!c) return PCL_ERR_ARG;
     if (n_records > c->cap) return fail(c->ctx, PCL_ERR_ARG, "n_records %llu exceeds chunk capacity %llu", (unsigned long long)n_records, (unsigned long long)c->cap);
     c->n = n_records;
-    for (int r = 0; r < c->ctx->n_reads; ++r) c->rb[r].filled = c->rb[r].text_filled = false;
+    for (int r = 0; r < c->ctx->n_reads; ++r) c->rb[r].filled = c->rb[r].text_filled = c->rb[r].uniform_len = false;
+    return PCL_OK;
+}
+
+int pcl_chunk_set_uniform_len(pcl_chunk *c, int read_slot, uint16_t len) {
+    if (!c) return PCL_ERR_ARG;
+    pcl_ctx *ctx = c->ctx;
+    if (read_slot < 0 || read_slot >= ctx->n_reads) return fail(ctx, PCL_ERR_ARG, "bad read_slot");
+    if (int r = bind(ctx)) return r;
+    ReadBuf &b = c->rb[read_slot];
+    if (c->n) {
+        k_fill_len<<<grid_for(ctx, c->n / 2 + 1, 8), PCL_BLOCK, 0, c->stream>>>(b.len, c->n, len);
+        ctx->launches += 1;
+        CU(ctx, cudaGetLastError());
+    }
+    b.uniform_len = true;
+    if (!ctx->dreads[read_slot].needs_payload && !ctx->dreads[read_slot].qual_only) b.filled = true;     // lengths are all such a read uploads
+    return PCL_OK;
+}
+
+int pcl_chunk_uniform_results_async(pcl_chunk *c, int read_slot, pcl_uniform_result *out) {
+    if (!c || !out) return PCL_ERR_ARG;
+    pcl_ctx *ctx = c->ctx;
+    if (read_slot < 0 || read_slot >= ctx->n_reads) return fail(ctx, PCL_ERR_ARG, "bad read_slot");
+    const pcl_read_info &inf = ctx->infos[read_slot];
+    if (inf.n_bc || inf.n_umi) return fail(ctx, PCL_ERR_ARG, "read %d holds barcodes / UMIs: its results are per record", read_slot);
+    if (int r = bind(ctx)) return r;
+    ReadBuf &b = c->rb[read_slot];
+    if (!b.d_uniform) if (int r = chunk_alloc(c, (void **)&b.d_uniform, 16)) return r;
+    if (c->n == 0) { out->uniform = 1; out->fstatus = 0; out->tcoord = PCL_COORD_ABSENT; return PCL_OK; }
+    static const uint32_t one[4] = {1u, 0u, 0u, 0u};
+    CU(ctx, cudaMemcpyAsync(b.d_uniform, one, 16, cudaMemcpyHostToDevice, c->stream));
+    k_uniform_check<<<grid_for(ctx, c->n, 8), PCL_BLOCK, 0, c->stream>>>(b.fstatus, inf.has_target ? b.tcoord : nullptr, c->n, b.d_uniform);
+    ctx->launches += 1;
+    CU(ctx, cudaGetLastError());
+    CU(ctx, cudaMemcpyAsync(out, b.d_uniform, 16, cudaMemcpyDeviceToHost, c->stream));
     return PCL_OK;
 }
 
@@ -722,7 +773,7 @@ int pcl_chunk_upload(pcl_chunk *c, int read_slot, const uint8_t *seq, const uint
     if (!c) return PCL_ERR_ARG;
     pcl_ctx *ctx = c->ctx;
     if (read_slot < 0 || read_slot >= ctx->n_reads) return fail(ctx, PCL_ERR_ARG, "bad read_slot");
-    if (!len) return fail(ctx, PCL_ERR_ARG, "len is NULL");
+    if (!len && !c->rb[read_slot].uniform_len) return fail(ctx, PCL_ERR_ARG, "len is NULL (and no pcl_chunk_set_uniform_len since the last reset)");
     if (int r = bind(ctx)) return r;
     const DRead &d = ctx->dreads[read_slot];
     ReadBuf &b = c->rb[read_slot];
@@ -735,7 +786,7 @@ int pcl_chunk_upload(pcl_chunk *c, int read_slot, const uint8_t *seq, const uint
         if (!qual) return fail(ctx, PCL_ERR_ARG, "read %d needs its quality plane (FASTQ QC is enabled)", read_slot);
         CU(ctx, cudaMemcpyAsync(b.qual, qual, c->n * d.qstride, cudaMemcpyHostToDevice, c->stream));
     }
-    CU(ctx, cudaMemcpyAsync(b.len, len, c->n * 2, cudaMemcpyHostToDevice, c->stream));
+    if (len) CU(ctx, cudaMemcpyAsync(b.len, len, c->n * 2, cudaMemcpyHostToDevice, c->stream));
     b.filled = true;
     return PCL_OK;
 }
@@ -750,7 +801,8 @@ int pcl_chunk_upload_compact(pcl_chunk *c, int read_slot, const uint8_t *seq, ui
     if ((row_bytes & 3u) || row_bytes < d.payload_bytes || row_bytes > d.stride)
         return fail(ctx, PCL_ERR_ARG, "read %d: compact rows must be a multiple of 4 bytes in [%u, %u]", read_slot,
                     (unsigned)d.payload_bytes, d.stride);
-    if (!seq || !len || (!qual && d.qstride)) return fail(ctx, PCL_ERR_ARG, "read %d needs seq, qual and len planes", read_slot);
+    if (!seq || (!len && !c->rb[read_slot].uniform_len) || (!qual && d.qstride))
+        return fail(ctx, PCL_ERR_ARG, "read %d needs seq, qual and len planes", read_slot);
     if (int r = bind(ctx)) return r;
     ReadBuf &b = c->rb[read_slot];
     if (!b.seq_stage) if (int r = chunk_alloc(c, (void **)&b.seq_stage, c->cap * (uint64_t)d.stride)) return r;
@@ -762,7 +814,7 @@ int pcl_chunk_upload_compact(pcl_chunk *c, int read_slot, const uint8_t *seq, ui
         CU(ctx, cudaGetLastError());
     }
     if (d.qstride) CU(ctx, cudaMemcpyAsync(b.qual, qual, c->n * (uint64_t)d.qstride, cudaMemcpyHostToDevice, c->stream));
-    CU(ctx, cudaMemcpyAsync(b.len, len, c->n * 2, cudaMemcpyHostToDevice, c->stream));
+    if (len) CU(ctx, cudaMemcpyAsync(b.len, len, c->n * 2, cudaMemcpyHostToDevice, c->stream));
     b.filled = true;
     return PCL_OK;
 }
@@ -1451,8 +1503,10 @@ int pcl_make_fastq_batch(pcl_ctx *ctx, const pcl_host_read *reads, uint64_t n, i
     std::vector<int> rcs(T, PCL_OK);
     auto work = [&](unsigned t) {
         const uint64_t i0 = n * t / T, i1 = n * (t + 1) / T;
-        o1[t].reserve((size_t)((i1 - i0) * 200));
-        if (paired) o2[t].reserve((size_t)((i1 - i0) * 160));
+        size_t est = 8 * (size_t)(i1 - i0) + 64;                  // the text of the range's records bounds what it can emit
+        for (int r = 0; r < ctx->n_reads; ++r) est += (size_t)(reads[r].off[3 * i1] - reads[r].off[3 * i0]);
+        o1[t].reserve(est);
+        if (paired) o2[t].reserve(est);
         rcs[t] = make_fastq_range(ctx, reads, i0, i1, correct_barcode, paired, o1[t], o2[t], &wr[t], &msgs[t]);
     };
     if (T == 1) work(0);

@@ -94,11 +94,21 @@ class Chunk:
         self._keep.append((batch, length))
         check(self.pipe.ctx, lib().pcl_chunk_upload(self.h, read_slot, sp, qp, length.ctypes.data))
 
+    def set_uniform_len(self, read_slot: int, length: int) -> None:
+        """All records of this read file are `length` long: no length plane crosses PCIe (``upload`` may then get a
+        batch whose ``length`` is None)."""
+        check(self.pipe.ctx, lib().pcl_chunk_set_uniform_len(self.h, read_slot, int(length)))
+
+    def uniform_results_async(self, read_slot: int, out: np.ndarray) -> None:
+        """Stream-ordered: out (uint32[4], pinned) = [uniform?, fstatus, tcoord, 0] of an insert read's result planes."""
+        assert out.dtype == np.uint32 and len(out) >= 4
+        check(self.pipe.ctx, lib().pcl_chunk_uniform_results_async(self.h, read_slot, out.ctypes.data))
+
     def upload_compact(self, read_slot: int, batch: HostBatch) -> None:
         """``upload`` with sequence rows narrower than the device stride (any multiple of 4 bytes from
         ``BarcodePipeline.payload_bytes`` up): fewer bytes over PCIe, widened on the device."""
-        length = np.ascontiguousarray(batch.length, dtype=np.uint16)
-        assert len(length) == self.n
+        length = None if batch.length is None else np.ascontiguousarray(batch.length, dtype=np.uint16)
+        assert length is None or len(length) == self.n
         info = self.pipe.infos[read_slot]
         if not info.needs_payload:
             return self.upload(read_slot, batch)
@@ -109,7 +119,7 @@ class Chunk:
             qp = batch.qual.ctypes.data
         self._keep.append((batch, length))
         check(self.pipe.ctx, lib().pcl_chunk_upload_compact(self.h, read_slot, batch.seq.ctypes.data, batch.seq.shape[1], qp,
-                                                            length.ctypes.data))
+                                                            length.ctypes.data if length is not None else None))
 
     # -- device-side FASTQ parse (pcl_text_*) ----------------------------------------------------------
     def text_scan(self, read_slot: int, text: np.ndarray, n_bytes: Optional[int] = None) -> None:

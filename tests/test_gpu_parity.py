@@ -500,3 +500,49 @@ def test_gpu_random_anchor_plan_layouts():
         U.compare_with_oracle(layout, ginfos, full, results, counts, defects, ores, ocounts)
         done += 1
     assert done >= 8
+
+
+def test_uniform_length_upload_and_uniform_results(layouts):
+    """pcl_chunk_set_uniform_len / pcl_chunk_uniform_results_async: a read file whose records all have one length sends no
+    length plane, and an insert read's constant result planes come back as one pair -- same results as the plain route."""
+    from precellar_b200.pipeline import BarcodePipeline, HostBatch
+    layout = layouts["v3"]
+    infos, strides = U.emul_infos(layout)
+    rng = np.random.default_rng(11)
+    full = U.gen_reads(rng, layout, 4000, strides, p_short=0.0)
+    full[0].length[:] = 28
+    full[1].length[:] = 91
+    dev = U.narrow(full, strides, infos)
+    ginfos, want, counts_w, _, _ = run_gpu(layout, dev)
+    pipe = BarcodePipeline(layout)
+    try:
+        n = 4000
+        ch = pipe.new_chunk(n)
+        ch.reset(n)
+        ch.set_uniform_len(0, 28)
+        ch.upload_compact(0, HostBatch(np.ascontiguousarray(dev[0].seq[:, :28]), dev[0].qual, None))
+        ch.set_uniform_len(1, 91)
+        pipe.count(ch)
+        pipe.allreduce()
+        pipe.correct(ch, 0.975)
+        import ctypes as C
+        buf = np.zeros(4, np.uint32)
+        ch.uniform_results_async(1, buf)
+        got0 = ch.fetch(0)
+        got1 = ch.fetch(1)
+        assert buf[0] == 1 and (got1.fstatus == buf[1]).all() and (got1.tcoord == buf[2]).all()
+        assert np.array_equal(got0.fstatus, want[0].fstatus) and np.array_equal(got0.bc_key[0], want[0].bc_key[0])
+        assert np.array_equal(got0.umi_key[0], want[0].umi_key[0]) and np.array_equal(got1.tcoord, want[1].tcoord)
+        # not uniform: one shorter insert
+        lens = np.full(n, 91, np.uint16); lens[17] = 40
+        ch.reset(n)
+        ch.set_uniform_len(0, 28)
+        ch.upload_compact(0, HostBatch(np.ascontiguousarray(dev[0].seq[:, :28]), dev[0].qual, None))
+        ch.upload(1, HostBatch(None, None, lens))
+        pipe.reset_counts()
+        pipe.count(ch)
+        ch.uniform_results_async(1, buf)
+        pipe.sync()
+        assert buf[0] == 0
+    finally:
+        pipe.close()
