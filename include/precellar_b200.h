@@ -181,6 +181,11 @@ int pcl_layout_set(pcl_ctx *ctx, const pcl_read_desc *reads, int n_reads);
  * Call before pcl_layout_set: reads that hold a target then carry a quality plane of ceil16(Read.max_len)
  * bytes per record (Read.max_len must be > 0), uploaded with pcl_chunk_upload like any other plane. */
 int pcl_qc_enable(pcl_ctx *ctx, int on);
+/* Assay::verify (seqspec/src/lib.rs:481-548) checks a sample of every read it is handed with
+ * split_with_tolerance(read, 0.2, 0.2): fixed sequences that the walk does not search for are compared with the read
+ * as well and more than 20 % mismatches make the record invalid (segment.rs:325-333).  Call before pcl_layout_set; the
+ * ctx then runs pass 1 with that rule (interpreter kernel) -- for verification samples, not for production runs. */
+int pcl_verify_enable(pcl_ctx *ctx, int on);
 int pcl_read_info_get(const pcl_ctx *ctx, int read_slot, pcl_read_info *out);
 /* Whitelist of one barcode region: n byte strings, string i = bytes[offsets[i] .. offsets[i+1]).
  * File order; duplicates are dropped keeping the first (IndexSet semantics).  Entries must be

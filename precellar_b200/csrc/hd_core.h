@@ -91,6 +91,8 @@ struct DRead {
     uint8_t qual_only, codes_ok;            // qual_only: QC-mode insert read; codes_ok: pcl_split_codes / pcl_pack_codes apply
     uint16_t payload_bytes;                 // record bytes the path can touch, rounded up to 4 (<= stride): the compact upload row
     uint32_t qoff, qstride;       // the quality plane holds record bytes [qoff, qoff + qstride) per record
+    uint32_t check_linkers;       // Assay::verify mode: split_with_tolerance(read, 0.2, 0.2) -- fixed sequences that are not
+                                  // searched for are compared with the read as well (segment.rs:325-333)
     DElem elems[PCL_MAX_ELEMS];
     FastLayout fast;
     AnchorPlan plan;
@@ -386,6 +388,10 @@ PCL_HD void pcl_split_t(const DRead &rd, uint32_t len, SplitOut &o, const Matche
                     buf_end = e; buf_sum_min += mn;                              // segment.rs:312-314
                 }
             } else {
+                if (rd.check_linkers && el.is_anchor && el.seq_len == mx) {      // linker_tolerance < 1.0 (segment.rs:325-333)
+                    const uint32_t d = match.fixed_distance(el, max_off);
+                    if ((double)d > 0.2 * (double)mx) { o.status = PCL_SPLIT_PATTERN_MISMATCH; return; }
+                }
                 uint32_t c = (max_off << 16) | mx;                               // segment.rs:315-344
                 o.seg[e] = c;
                 if (el.kind == PCL_KIND_TARGET) { o.tcoord = c; ++n_target; }
@@ -409,6 +415,12 @@ struct ByteMatcher {            // anchor search on the record bytes (any anchor
     bool rev;
     PCL_HD bool operator()(const DElem &el, uint32_t wstart, uint32_t wn, uint32_t *pos, uint32_t *mis) const {
         return pcl_best_match(rec + wstart, wn, el.seq, el.seq_len, rev, pos, mis);
+    }
+    // hamming(segment or its seqspec::utils::rev_compl, sequence) of a fixed element found at `start`
+    PCL_HD uint32_t fixed_distance(const DElem &el, uint32_t start) const {
+        uint32_t d = 0;
+        for (uint32_t k = 0; k < el.seq_len; ++k) d += pcl_window_byte(rec + start, el.seq_len, k, rev) != el.seq[k];
+        return d;
     }
 };
 
@@ -1014,6 +1026,12 @@ struct CodeMatcher {
         *mis = best;
         return true;
     }
+    PCL_HD uint32_t fixed_distance(const DElem &el, uint32_t start) const {      // anchors of <= 32 upper-case ACGT bases
+        const uint32_t m = el.seq_len;
+        const uint64_t even = m >= 32u ? 0x5555555555555555ull : (0x5555555555555555ull & ((1ull << (2u * m)) - 1ull));
+        const uint64_t x = pcl_bits128(rc->lo, rc->hi, start, m) ^ (rev ? el.a_rc : el.a_code);
+        return pcl_popc64(((x | (x >> 1)) | pcl_bits128(rc->sb_lo, rc->sb_hi, start, m)) & even);
+    }
 };
 
 PCL_HD void pcl_split_codes(const DRead &rd, const RecCodes &rc, uint32_t len, SplitOut &o) {
@@ -1052,6 +1070,35 @@ PCL_HD void pcl_codes32_t(const uint32_t *w, int n_words, Codes32 &k) {
                     (void)pcl_word_codes(x, &sbad);
                     sb |= pcl_flags8(sbad) << (8 * q);
                 }
+            }
+        }
+        k.c[g] = c; k.bd[g] = b; k.sb[g] = kRev ? sb : b;
+    }
+}
+
+// The same, converting exactly n_words words (warp-uniform): the fields of an AnchorPlan layout seldom end on a
+// 16-byte boundary, and the conversion is a quarter of that kernel's instructions.
+template <bool kRev>
+PCL_HD void pcl_codes32_exact(const uint32_t *w, int n_words, Codes32 &k) {
+#ifdef __CUDA_ARCH__
+#pragma unroll
+#endif
+    for (int g = 0; g < 4; ++g) {
+        uint32_t c = 0, b = 0, sb = 0;
+#ifdef __CUDA_ARCH__
+#pragma unroll
+#endif
+        for (int q = 0; q < 4; ++q) {
+            if (4 * g + q >= n_words) break;                          // warp-uniform
+            const uint32_t x = w[4 * g + q];
+            uint32_t bad;
+            const uint32_t c8 = pcl_word_codes(kRev ? (x & 0xDFDFDFDFu) : x, &bad);
+            c |= c8 << (8 * q);
+            b |= pcl_flags8(bad) << (8 * q);
+            if (kRev) {
+                uint32_t sbad;
+                (void)pcl_word_codes(x, &sbad);
+                sb |= pcl_flags8(sbad) << (8 * q);
             }
         }
         k.c[g] = c; k.bd[g] = b; k.sb[g] = kRev ? sb : b;
@@ -1263,7 +1310,7 @@ PCL_HD bool pcl_plan_record_fast(const DRead &rd, const uint32_t *w, uint32_t L,
     const AnchorPlan &pl = rd.plan;
     if (L < pl.full_len) return false;
     Codes32 k;
-    pcl_codes32_t<kRev>(w, (int)pl.n_words, k);
+    pcl_codes32_exact<kRev>(w, (int)pl.n_words, k);
     // find_best_pattern_match over the n_pos window positions (leftmost strict minimum; segment.rs:496-535)
     const uint32_t m = pl.a_len, v = pl.v, a = v + 1u;
     const uint32_t needle = (uint32_t)(kRev ? rd.elems[a].a_rc : rd.elems[a].a_code);

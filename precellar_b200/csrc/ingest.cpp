@@ -176,7 +176,7 @@ const char *pcl_fastq_error(const pcl_fastq *r) { return r ? r->err.c_str() : ""
 // Read up to max_records records.
 //   seq/qual : [max_records][stride] planes (may be NULL when the read needs lengths only); bytes beyond a
 //              record's length are filled with 'N' / '!'.
-//   len      : [max_records] sequence length (before any Read.max_len truncation; clamped to 65535)
+//   len      : [max_records] sequence length (before any Read.max_len truncation; records beyond 65535 bases are an error)
 //   name_hash: [max_records] FNV-1a of the read name (definition up to the first blank, trailing /1 or /2 removed)
 //   text/off : optional arena keeping definition, sequence and quality of every record:
 //              off[3*i], off[3*i+1], off[3*i+2], off[3*i+3] delimit them; *text_used is updated.
@@ -200,7 +200,8 @@ int64_t pcl_fastq_read(pcl_fastq *r, uint64_t max_records, uint32_t stride, uint
                 (size_t)(e1 - (e0 + 1)) == (size_t)(e3 - (e2 + 1))) {
                 const uint8_t *sq = e0 + 1, *ql = e2 + 1;
                 const size_t L = (size_t)(e1 - sq), dlen = (size_t)(e0 - p0);        // dlen counts the '@'
-                len[n] = (uint16_t)(L > 65535 ? 65535 : L);
+                if (L > 65535) { r->err = "FASTQ record " + std::to_string(r->n_records) + ": sequences longer than 65535 bases are not supported"; return PCL_ERR_UNSUPPORTED; }
+                len[n] = (uint16_t)L;
                 if (seq && stride) {
                     const size_t c = L < stride ? L : stride;
                     uint8_t *ds = seq + n * (uint64_t)stride;
@@ -245,7 +246,8 @@ int64_t pcl_fastq_read(pcl_fastq *r, uint64_t max_records, uint32_t stride, uint
         const std::string &def = r->line[0], &s = r->line[1], &q = r->line[3];
         if (s.size() != q.size()) { r->err = "FASTQ record " + std::to_string(r->n_records) + ": sequence and quality lengths differ"; return PCL_ERR_INPUT; }
         const size_t L = s.size();
-        len[n] = (uint16_t)(L > 65535 ? 65535 : L);
+        if (L > 65535) { r->err = "FASTQ record " + std::to_string(r->n_records) + ": sequences longer than 65535 bases are not supported"; return PCL_ERR_UNSUPPORTED; }
+        len[n] = (uint16_t)L;
         if (seq && stride) {
             const size_t c = L < stride ? L : stride;
             uint8_t *ds = seq + n * (uint64_t)stride;

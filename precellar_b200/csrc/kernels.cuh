@@ -100,6 +100,32 @@ __device__ __forceinline__ void pcl_wl_push(const P &p, WlCursor &cur, bool m, u
     }
 }
 
+// two entries per lane in one reservation step (two records of a lane, or the two barcodes of a record)
+template <typename P>
+__device__ __forceinline__ void pcl_wl_push2(const P &p, WlCursor &cur, bool m0, uint32_t hi0, uint32_t rec0, uint32_t key0, bool m1,
+                                             uint32_t hi1, uint32_t rec1, uint32_t key1, uint32_t lane) {
+    const uint32_t b0 = __ballot_sync(0xFFFFFFFFu, m0), b1 = __ballot_sync(0xFFFFFFFFu, m1);
+    if (!(b0 | b1)) return;
+    const uint32_t lt = (1u << lane) - 1u;
+    const uint32_t n0 = __popc(b0), need = n0 + __popc(b1);
+    const uint32_t r0 = __popc(b0 & lt), r1 = n0 + __popc(b1 & lt);
+    const unsigned long long rem = cur.end - cur.pos;   // warp-uniform
+    unsigned long long at0 = cur.pos + r0, at1 = cur.pos + r1;
+    if (need > rem) {
+        unsigned long long b = 0;
+        if (lane == 0) b = atomicAdd(p.wl_count, (unsigned long long)PCL_WL_BATCH);
+        b = __shfl_sync(0xFFFFFFFFu, b, 0);
+        if (r0 >= rem) at0 = b + r0 - rem;
+        if (r1 >= rem) at1 = b + r1 - rem;
+        cur.pos = b + need - rem;
+        cur.end = b + PCL_WL_BATCH;
+    } else {
+        cur.pos += need;
+    }
+    if (m0) { p.worklist[at0] = ((unsigned long long)hi0 << 32) | rec0; p.wl_key[at0] = key0; }
+    if (m1) { p.worklist[at1] = ((unsigned long long)hi1 << 32) | rec1; p.wl_key[at1] = key1; }
+}
+
 template <typename P>
 __device__ __forceinline__ void pcl_wl_finish(const P &p, const WlCursor &cur, uint32_t lane) {
     for (unsigned long long q = cur.pos + lane; q < cur.end; q += 32) p.worklist[q] = PCL_WL_HOLE;
@@ -455,9 +481,15 @@ __global__ void __launch_bounds__(PCL_BLOCK, 4) k_count_plan(const __grid_consta
             }
         }
         if (live) pcl_st_stream(p.fstatus + i, (uint16_t)fs);
-        // warp-batched append of the misses to the worklist
+        // warp-batched append of the misses to the worklist: one reservation for the first two barcodes of the record
+        {
+            const uint32_t c0 = o.bcoord[0], c1 = n_bc > 1u ? o.bcoord[1] : 0u;
+            const uint32_t h0 = (c0 >> 16) | ((c0 & 0xFFu) << 16) | ((o.bninv[0] == 1u ? 1u : 0u) << 26) | ((o.bninv[0] == 1u ? o.bipos[0] : 0u) << 27);
+            const uint32_t h1 = (c1 >> 16) | ((c1 & 0xFFu) << 16) | (1u << 24) | ((o.bninv[1] == 1u ? 1u : 0u) << 26) | ((o.bninv[1] == 1u ? o.bipos[1] : 0u) << 27);
+            pcl_wl_push2(p, wl, miss[0], h0, (uint32_t)i, o.bkey[0], n_bc > 1u && miss[1], h1, (uint32_t)i, o.bkey[1], lane);
+        }
 #pragma unroll
-        for (uint32_t j = 0; j < PCL_MAX_BC_PER_READ; ++j) {
+        for (uint32_t j = 2; j < PCL_MAX_BC_PER_READ; ++j) {
             if (j >= n_bc) break;
             const uint32_t c = o.bcoord[j];
             pcl_wl_push(p, wl, miss[j], pcl_wl_pack(i, c >> 16, c & 0xFFFFu, j, o.bninv[j], o.bipos[j]), o.bkey[j], lane);
@@ -668,32 +700,6 @@ __device__ __forceinline__ void pcl_spec_codes4(uint32_t w0, uint32_t w1, uint32
     const uint32_t c2 = pcl_word_codes(w2 & fold, &d2), c3 = pcl_word_codes(w3 & fold, &d3);
     *codes = c0 | (c1 << 8) | (c2 << 16) | (c3 << 24);
     *bad = d0 | d1 | d2 | d3;
-}
-
-// both records' misses in one reservation step (see pcl_wl_push)
-template <typename P>
-__device__ __forceinline__ void pcl_wl_push2(const P &p, WlCursor &cur, bool m0, uint32_t hi0, uint32_t rec0, uint32_t key0, bool m1,
-                                             uint32_t hi1, uint32_t rec1, uint32_t key1, uint32_t lane) {
-    const uint32_t b0 = __ballot_sync(0xFFFFFFFFu, m0), b1 = __ballot_sync(0xFFFFFFFFu, m1);
-    if (!(b0 | b1)) return;
-    const uint32_t lt = (1u << lane) - 1u;
-    const uint32_t n0 = __popc(b0), need = n0 + __popc(b1);
-    const uint32_t r0 = __popc(b0 & lt), r1 = n0 + __popc(b1 & lt);
-    const unsigned long long rem = cur.end - cur.pos;   // warp-uniform
-    unsigned long long at0 = cur.pos + r0, at1 = cur.pos + r1;
-    if (need > rem) {
-        unsigned long long b = 0;
-        if (lane == 0) b = atomicAdd(p.wl_count, (unsigned long long)PCL_WL_BATCH);
-        b = __shfl_sync(0xFFFFFFFFu, b, 0);
-        if (r0 >= rem) at0 = b + r0 - rem;
-        if (r1 >= rem) at1 = b + r1 - rem;
-        cur.pos = b + need - rem;
-        cur.end = b + PCL_WL_BATCH;
-    } else {
-        cur.pos += need;
-    }
-    if (m0) { p.worklist[at0] = ((unsigned long long)hi0 << 32) | rec0; p.wl_key[at0] = key0; }
-    if (m1) { p.worklist[at1] = ((unsigned long long)hi1 << 32) | rec1; p.wl_key[at1] = key1; }
 }
 
 template <int kSpec, bool kRev, bool kPrefetch = true>

@@ -112,6 +112,7 @@ struct pcl_ctx {
     double *d_lut = nullptr;                  // [0..255] capped, [256..511] raw
     unsigned long long *d_qc = nullptr;       // [PCL_MAX_READS] num_defect, then [12] QcFastq category counters
     bool qc_enabled = false;
+    bool verify_mode = false;                 // pcl_verify_enable: Assay::verify's split_with_tolerance(read, 0.2, 0.2)
     uint64_t qc_reads[PCL_MAX_READS] = {0};
     std::vector<pcl_chunk *> chunks;
     TextStage text[PCL_MAX_READS];
@@ -435,11 +436,20 @@ int pcl_layout_set(pcl_ctx *ctx, const pcl_read_desc *reads, int n_reads) {
         pcl_read_info info;
         int rc = pcl_build_read(r, reads[r], &d, &info, ctx->bc_region[r], &ctx->err, ctx->qc_enabled);
         if (rc != PCL_OK) return rc;
+        if (ctx->verify_mode) d.check_linkers = 1;
         ctx->descs[r] = reads[r];
         ctx->dreads[r] = d;
         ctx->infos[r] = info;
     }
     ctx->n_reads = n_reads;
+    return PCL_OK;
+}
+
+int pcl_verify_enable(pcl_ctx *ctx, int on) {
+    if (!ctx) return PCL_ERR_ARG;
+    if (ctx->n_reads) return fail(ctx, PCL_ERR_ARG, "pcl_verify_enable must be called before pcl_layout_set");
+    ctx->verify_mode = on != 0;
+    if (on) ctx->force_generic = true;        // the byte interpreter is the kernel that compares unsearched fixed sequences
     return PCL_OK;
 }
 

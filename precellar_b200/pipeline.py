@@ -207,7 +207,7 @@ class BarcodePipeline:
     """One GPU's instance of the hot path for one (assay, modality)."""
 
     def __init__(self, layout: CompiledLayout, device: int = 0, nranks: int = 1, rank: int = 0,
-                 nccl_uid: Optional[bytes] = None, qc: bool = False):
+                 nccl_uid: Optional[bytes] = None, qc: bool = False, verify: bool = False):
         L = lib()
         ctx = C.c_void_p()
         rc = L.pcl_ctx_create(C.byref(ctx), int(device))
@@ -219,6 +219,8 @@ class BarcodePipeline:
         self.qc_enabled = bool(qc)
         if qc:                                          # QcFastq needs the quality plane of insert reads too
             check(ctx, L.pcl_qc_enable(ctx, 1))
+        if verify:                                      # Assay::verify: split_with_tolerance(read, 0.2, 0.2)
+            check(ctx, L.pcl_verify_enable(ctx, 1))
         self._descs = layout.descs()
         check(ctx, L.pcl_layout_set(ctx, self._descs, len(layout.reads)))
         self.infos: List[_ffi.ReadInfo] = []

@@ -97,6 +97,9 @@ def read_lines(path: str) -> List[bytes]:
 # ---------------------------------------------------------------------------------------------
 # Onlist / File / Region / Read
 # ---------------------------------------------------------------------------------------------
+_ONLIST_CACHE: dict = {}
+
+
 @dataclass
 class Onlist:                                                            # region.rs:446-456
     file_id: str = ""
@@ -131,8 +134,23 @@ class Onlist:                                                            # regio
             "point the region's onlist at a local file (urltype: local)")
 
     def read(self) -> List[bytes]:
-        """Lines in file order with duplicates dropped (IndexSet, region.rs:459-469)."""
-        return list(dict.fromkeys(read_lines(self.path())))
+        """Lines in file order with duplicates dropped (IndexSet, region.rs:459-469).  The parsed list of a file is kept
+        per (path, size, mtime): update_read's verification and the run itself would otherwise parse a multi-million-line
+        whitelist several times."""
+        path = self.path()
+        try:
+            st = os.stat(path)
+            key = (path, st.st_size, st.st_mtime_ns)
+        except OSError:
+            key = None
+        if key is not None and key in _ONLIST_CACHE:
+            return _ONLIST_CACHE[key]
+        items = list(dict.fromkeys(read_lines(path)))
+        if key is not None:
+            if len(_ONLIST_CACHE) >= 8:
+                _ONLIST_CACHE.pop(next(iter(_ONLIST_CACHE)))
+            _ONLIST_CACHE[key] = items
+        return items
 
 
 @dataclass
@@ -530,7 +548,7 @@ class Assay:
     def update_read(self, read_id: str, *, modality: Optional[str] = None, primer_id: Optional[str] = None,
                     is_reverse: Optional[bool] = None, fastq=None, min_len: Optional[int] = None,
                     max_len: Optional[int] = None, compute_md5: bool = False, infer_read_length: bool = True,
-                    infer_read_length_sample: int = 10000) -> None:
+                    infer_read_length_sample: int = 10000, verify: bool = True) -> None:
         """Create or update a read (lib.rs:310-394; argument handling of pyseqspec.rs:246-291)."""
         if read_id in self.sequence_spec:
             read = copy.deepcopy(self.sequence_spec[read_id])
@@ -566,6 +584,8 @@ class Assay:
 
         if read.primer_id not in self._parent_map:                      # verify (lib.rs:482-485)
             raise ValueError(f"Primer not found: {read.primer_id}")
+        if verify:
+            self._verify(read, infer_read_length_sample)
         region = self._region_map.get(read.primer_id)
         if region is not None and not region.is_sequencing_primer():
             log.warning("primer_id '%s' is not a sequencing primer (type: %s). This will cause errors. If you are "
@@ -573,12 +593,92 @@ class Assay:
                         read.primer_id, region.region_type)
         self.sequence_spec[read_id] = read
 
+    # -- verification of a read against a sample of its records -----------------------------------------------------------
+    def _verify(self, read: "Read", sample_size: int) -> Optional[dict]:
+        """Assay::verify (lib.rs:481-548): split the first ``sample_size`` records with tolerances (0.2, 0.2) and warn when
+        fewer than half are valid or fewer than half of a barcode region's segments are on its onlist.  The sample goes
+        through the CUDA path (pcl_verify_enable: the same walk, fixed sequences compared too); there is no CPU route, so
+        without a usable device the check is skipped with a log line.  Returns the percentages (for tests)."""
+        info = self._segments_of(read)
+        paths = read.fastq_paths()
+        if info is None or not paths:
+            return None
+        try:
+            import numpy as np
+            from . import _ffi
+            from .ingest import FastqReader
+            from .layout import layout_from_elems
+            from .pipeline import BarcodePipeline
+            elems, wl = [], {}
+            for e in info:
+                if e.is_barcode():
+                    region = self._region_map.get(e.region_id)
+                    onlist = region.onlist.read() if (region is not None and region.onlist is not None) else None
+                    if onlist:
+                        wl[e.region_id] = onlist
+                        elems.append(e)
+                    else:                                               # no onlist: only the split matters (lib.rs:498-506)
+                        elems.append(SegmentInfoElem(e.region_id, "linker", e.sequence_type, e.sequence, e.min_len, e.max_len))
+                else:
+                    elems.append(e)
+            layout = layout_from_elems([dict(read_id=read.read_id, elems=elems, is_reverse=read.is_reverse(), max_len=int(read.max_len))],
+                                       wl, read.modality)
+            pipe = BarcodePipeline(layout, verify=True)
+        except (ImportError, OSError) as exc:
+            log.info("verification of read '%s' skipped: %s", read.read_id, exc)
+            return None
+        except Exception as exc:                                        # no device, or a layout the kernels do not take
+            code = getattr(exc, "code", None)
+            if code in (-2, -4):                                        # PCL_ERR_CUDA, PCL_ERR_UNSUPPORTED
+                log.info("verification of read '%s' skipped: %s", read.read_id, exc)
+                return None
+            raise
+        try:
+            rdr = FastqReader(paths)
+            try:
+                b = rdr.read(sample_size, pipe.stride(0), qual_only=bool(pipe.infos[0].qual_only), qual_window=pipe.qual_window(0))
+            finally:
+                rdr.close()
+            if b is None:
+                return None
+            n = len(b.batch.length)
+            ch = pipe.new_chunk(n)
+            ch.reset(n)
+            ch.upload(0, b.batch)
+            pipe.count(ch)
+            res = ch.fetch(0)
+            fs = res.fstatus.astype(np.uint32)
+            valid = (fs & 3) == 0
+            out = {"total": n, "percent_valid": float(valid.sum()) / n * 100.0, "percent_matched": {}}
+            if out["percent_valid"] < 50.0:
+                log.warning("Read '%s' has low percentage of valid records. Percentage of valid records: %.2f%%",
+                            read.read_id, out["percent_valid"])
+            j = 0
+            per_region: Dict[str, int] = {}
+            for e in elems:
+                if e.is_barcode():
+                    code = (fs >> (4 + 3 * j)) & 7
+                    per_region[e.region_id] = per_region.get(e.region_id, 0) + int((valid & (code == _ffi.BC_EXACT)).sum())
+                    j += 1
+            for rid, n_matched in per_region.items():
+                pm = n_matched / n * 100.0
+                out["percent_matched"][rid] = pm
+                if pm < 50.0:
+                    log.warning("Read '%s' has low percentage of matched records for region '%s'. Percentage of matched records: %.2f%%",
+                                read.read_id, rid, pm)
+            return out
+        finally:
+            pipe.close()
+
     # -- region table -----------------------------------------------------------------------------------
     def get_segments(self, read_id: str) -> Optional[SegmentInfo]:
         """Atomic regions covered by a read (lib.rs:433-440 -> read.rs:182-212 -> segment.rs:144-164)."""
         read = self.sequence_spec.get(read_id)
         if read is None:
             return None
+        return self._segments_of(read)
+
+    def _segments_of(self, read: "Read") -> Optional[SegmentInfo]:
         parent = self._parent_map.get(read.primer_id)
         if parent is None or parent.sequence_type != "joined":
             return None

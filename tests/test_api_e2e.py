@@ -309,3 +309,27 @@ def test_make_fastq_paired_end_atac_like(tmp_path):
     got1 = [(r1[i + 1], r1[i + 3]) for i in range(0, len(r1) - 1, 4)]
     got2 = [(r2[i + 1], r2[i + 3]) for i in range(0, len(r2) - 1, 4)]
     assert got1 == want1 and got2 == want2 and len(want1) > 1500
+
+
+def test_update_read_verifies_a_sample_on_the_device(dataset, tmp_path, caplog):
+    """Assay::verify (lib.rs:481-548): valid records and onlist matches of a sample, split with tolerances (0.2, 0.2)
+    on the CUDA path; a read whose linker does not match the spec is reported."""
+    import copy
+    import logging
+    a = copy.deepcopy(dataset["assay"])
+    r1 = a.sequence_spec["R1"]
+    got = a._verify(r1, 2000)
+    full = dataset["full"]
+    assert got is not None and got["total"] == 2000
+    # the split of R1 with the (1.0, 0.2) tolerances of the hot path is at least as permissive as (0.2, 0.2)
+    layout, ores = oracle_lines(dataset["assay"], full, False)
+    ok_ref = float((ores.fstatus[0][:2000] == 0).mean()) * 100.0
+    assert 50.0 < got["percent_valid"] <= ok_ref + 1e-9
+    assert set(got["percent_matched"]) == {"hairpin_barcode", "rt_barcode"} and all(v > 50.0 for v in got["percent_matched"].values())
+    # a spec whose linker is wrong: (nearly) nothing is valid any more and a warning is logged
+    bad = copy.deepcopy(dataset["assay"])
+    bad._region_map["linker"].sequence = "TTTTTT"
+    with caplog.at_level(logging.WARNING):
+        res = bad._verify(bad.sequence_spec["R1"], 2000)
+    assert res["percent_valid"] < 10.0
+    assert any("low percentage of valid records" in m for m in caplog.messages)
