@@ -237,6 +237,15 @@ int pcl_count(pcl_ctx *ctx, pcl_chunk *chunk);
  * already hold the global sums; adding to them or summing them again would multiply them by the number of ranks). */
 int pcl_counts_allreduce(pcl_ctx *ctx);
 int pcl_correct(pcl_ctx *ctx, pcl_chunk *chunk, double threshold, double max_expected_errors); /* pass 2 (async) */
+/* For callers that cannot keep every chunk resident between the passes (the reference streams its files twice in bounded
+ * memory, precellar/src/align/fastq.rs:109-153): after pcl_counts_allreduce, with the counts frozen, pcl_count recomputes a
+ * re-uploaded chunk's pass-1 outputs (split status, keys, coordinates, miss worklist) WITHOUT touching the whitelist
+ * counts, totals or QC counters; pcl_correct then works as usual. */
+int pcl_counts_freeze(pcl_ctx *ctx, int on);
+/* Device bytes one chunk of `capacity_records` takes (pcl_chunk_create allocates them in one piece), and the free /
+ * total memory of the ctx's device: what a host layer needs to decide how many chunks it can keep resident. */
+uint64_t pcl_chunk_bytes(const pcl_ctx *ctx, uint64_t capacity_records);
+int pcl_mem_info(pcl_ctx *ctx, uint64_t *free_bytes, uint64_t *total_bytes);
 
 /* ---- outputs ------------------------------------------------------------------------------ */
 int pcl_chunk_fetch(pcl_chunk *chunk, int read_slot, const pcl_read_results *out);   /* D2H + wait */

@@ -84,7 +84,7 @@ SYMBOLS = [
     "pcl_text_scan", "pcl_text_lines", "pcl_text_fill", "pcl_text_names_check", "pcl_text_line_ends",
     "pcl_chunk_upload_compact", "pcl_read_payload_bytes",
     "pcl_gzsrc_open", "pcl_gzsrc_read", "pcl_gzsrc_is_bgzf", "pcl_gzsrc_error", "pcl_gzsrc_close",
-    "pcl_verify_enable", "pcl_chunk_set_uniform_len", "pcl_chunk_uniform_results_async",
+    "pcl_counts_freeze", "pcl_chunk_bytes", "pcl_mem_info", "pcl_verify_enable", "pcl_chunk_set_uniform_len", "pcl_chunk_uniform_results_async",
     "pcl_group_build", "pcl_group_info_get", "pcl_group_fetch", "pcl_group_key_decode", "pcl_group_destroy",
 ]
 
@@ -155,6 +155,9 @@ def lib() -> C.CDLL:
         "pcl_gzsrc_is_bgzf": (i32, [vp]),
         "pcl_gzsrc_error": (C.c_char_p, [vp]),
         "pcl_gzsrc_close": (None, [vp]),
+        "pcl_counts_freeze": (i32, [vp, i32]),
+        "pcl_chunk_bytes": (u64, [vp, u64]),
+        "pcl_mem_info": (i32, [vp, C.POINTER(u64), C.POINTER(u64)]),
         "pcl_verify_enable": (i32, [vp, i32]),
         "pcl_chunk_set_uniform_len": (i32, [vp, i32, C.c_uint16]),
         "pcl_chunk_uniform_results_async": (i32, [vp, i32, vp]),

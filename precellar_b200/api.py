@@ -126,6 +126,10 @@ class FastqProcessor:
         self._qc = None
         self._layouts: dict = {}
         self.compute_qc = True
+        # device bytes per GPU the resident chunks may take (None: 60 % of the free memory); batches past it are
+        # streamed - counted in pass 1, uploaded and recounted against the frozen counts in pass 2
+        self.resident_bytes: Optional[int] = None
+        self.streamed_chunks = 0
 
     def with_modality(self, modality: str) -> "FastqProcessor":
         self.current_modality = parse_modality(modality)
@@ -309,6 +313,13 @@ class FastqProcessor:
         text_bytes = [2 * max(p.max_len, 1024) + 256 for p in layout.reads]
         rdr = GroupReader(files, strides, qonly, keep_text=keep, text_bytes=text_bytes if keep else None,
                           qual_windows=[pipe.qual_window(r) for r in range(n_reads)])
+        # chunks stay resident on their GPU up to a budget; the batches past it are "streamed": counted through one
+        # reusable chunk per GPU now, and uploaded again in pass 2 - which is what the reference does for every batch
+        # (two reads of the files, fastq.rs:183-199 then fastq.rs:268-331)
+        budget = [self._resident_budget(pp) for pp in pipes]
+        used = [0] * G
+        spare: List[Optional[Chunk]] = [None] * G
+        self.streamed_chunks = 0
         try:
             while not self.device_parse:
                 with _timed("pass1_host_read"):
@@ -316,14 +327,24 @@ class FastqProcessor:
                 if got is None:
                     break
                 n = len(got[0].batch.length)
-                own = pipes[len(chunks) % G]     # chunk k lives on GPU k mod G
-                ch = own.new_chunk(n)
-                ch.reset(n)
+                g = len(chunks) % G              # chunk k lives on GPU k mod G
+                own = pipes[g]
+                need = own.chunk_bytes(n)
+                if used[g] + need <= budget[g]:
+                    ch = own.new_chunk(n)
+                    used[g] += need
+                else:
+                    if spare[g] is None:
+                        spare[g] = own.new_chunk(per_chunk)
+                    ch = None
+                    self.streamed_chunks += 1
+                tgt = ch if ch is not None else spare[g]
+                tgt.reset(n)
                 for r in range(n_reads):
-                    ch.upload(r, got[r].batch)
-                own.count(ch)
+                    tgt.upload(r, got[r].batch)
+                own.count(tgt)
                 if self.compute_qc:
-                    own.qc_accumulate(ch)
+                    own.qc_accumulate(tgt)
                 with _timed("pass1_device_wait"):
                     own.sync()                   # the host planes of this batch go out of scope
                 if keep:
@@ -341,26 +362,57 @@ class FastqProcessor:
         self.num_reads = totals.pop() if totals else 0
 
         # pass 2 (AnnotatedFastqReader): correct, fetch, and rebuild the records from a second read of the files
-        rdr = None if keep else GroupReader(files, [0] * n_reads, [False] * n_reads, keep_text=True, qual_windows=[(0, 0)] * n_reads,
-                                            text_bytes=text_bytes)
+        streaming = any(ch is None for ch in chunks)
+        rdr = None
+        if not keep:                             # streamed batches need their sequence / quality planes again
+            rdr = GroupReader(files, strides if streaming else [0] * n_reads, qonly if streaming else [False] * n_reads,
+                              keep_text=True, qual_windows=[pipe.qual_window(r) for r in range(n_reads)] if streaming else [(0, 0)] * n_reads,
+                              text_bytes=text_bytes)
         try:
-            if correct_barcode:                  # every GPU corrects its chunks while the host re-reads the files
+            if streaming:                        # recounting a batch must not move the counts the correction reads
+                for pp in pipes:
+                    pp.freeze_counts(True)
+            if correct_barcode:                  # every GPU corrects its resident chunks while the host re-reads the files
                 for ch, own in zip(chunks, owners):
-                    own.correct(ch, self.barcode_correct_prob)
+                    if ch is not None:
+                        own.correct(ch, self.barcode_correct_prob)
             for k, (ch, n, own) in enumerate(zip(chunks, sizes, owners)):
-                with _timed("pass2_fetch"):
-                    results = [ch.fetch(r) for r in range(n_reads)]
                 if keep:
                     text, kept[k] = kept[k], None
                 else:
                     text = rdr.next(n)
                 assert text is not None and len(text[0].batch.length) == n
+                if ch is None:
+                    tgt = spare[pipes.index(own)]
+                    tgt.reset(n)
+                    for r in range(n_reads):
+                        tgt.upload(r, text[r].batch)
+                    own.count(tgt)
+                    if correct_barcode:
+                        own.correct(tgt, self.barcode_correct_prob)
+                else:
+                    tgt = ch
+                with _timed("pass2_fetch"):
+                    results = [tgt.fetch(r) for r in range(n_reads)]
                 yield text, results
-                ch.close()
-                own.chunks.remove(ch)
+                if ch is not None:
+                    ch.close()
+                    own.chunks.remove(ch)
         finally:
             if rdr is not None:
                 rdr.close()
+            if streaming:
+                for pp in pipes:
+                    pp.freeze_counts(False)
+
+    def _resident_budget(self, pipe: BarcodePipeline) -> int:
+        """Bytes of device memory the resident chunks of one GPU may take: `resident_bytes` (or the environment's
+        PCL_API_RESIDENT_BYTES), else 60 % of what is free after the whitelist tables were built."""
+        fixed = self.resident_bytes if self.resident_bytes is not None else os.environ.get("PCL_API_RESIDENT_BYTES")
+        if fixed is not None and str(fixed) != "":
+            return int(fixed)
+        free, _total = pipe.mem_info()
+        return int(free * 0.6)
 
     @staticmethod
     def _annotate(layout: CompiledLayout, pipe: BarcodePipeline, text: Sequence[FastqBatch], results,

@@ -80,6 +80,8 @@ struct Table {
     uint32_t *d_nkeys[4] = {nullptr, nullptr, nullptr, nullptr};
     uint32_t *d_nbits = nullptr;               // 4 x PCL_NBITS_WORDS: bitmaps of the partial keys (DTable::nbits)
     uint32_t *d_dense = nullptr;               // n_entries counts in whitelist order: what the all-reduce sends
+    uint32_t *d_scratch_counts = nullptr;      // pcl_counts_freeze: where a re-run of pass 1 puts its (discarded) increments
+    unsigned long long *d_scratch_scalars = nullptr;
     unsigned long long *d_scalars = nullptr;   // [0] total, [1] mismatch
 };
 
@@ -119,6 +121,8 @@ struct pcl_ctx {
     // nccl
     NcclComm comm = nullptr;
     int nranks = 1, rank = 0;
+    bool frozen = false;          // pcl_counts_freeze: pcl_count recomputes a chunk's outputs without touching counts / totals / QC
+    unsigned long long *d_qc_scratch = nullptr;
     bool reduced = false;         // counts hold the sum over ranks: pcl_count / a second all-reduce need pcl_counts_reset first
     // instrumentation
     bool profile = false;
@@ -369,6 +373,8 @@ static void table_free(Table &t) {
     for (int q = 0; q < 4; ++q) if (t.d_nkeys[q]) cudaFree(t.d_nkeys[q]);
     if (t.d_nbits) cudaFree(t.d_nbits);
     if (t.d_dense) cudaFree(t.d_dense);
+    if (t.d_scratch_counts) cudaFree(t.d_scratch_counts);
+    if (t.d_scratch_scalars) cudaFree(t.d_scratch_scalars);
     if (t.d_scalars) cudaFree(t.d_scalars);
     t = Table();
 }
@@ -384,6 +390,7 @@ int pcl_ctx_destroy(pcl_ctx *ctx) {
     if (ctx->comm && nccl().ok) nccl().CommDestroy(ctx->comm);
     if (ctx->d_lut) cudaFree(ctx->d_lut);
     if (ctx->d_qc) cudaFree(ctx->d_qc);
+    if (ctx->d_qc_scratch) cudaFree(ctx->d_qc_scratch);
     if (ctx->ev_reduced) cudaEventDestroy(ctx->ev_reduced);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -1076,8 +1083,19 @@ static int check_ready(pcl_ctx *ctx, pcl_chunk *c) {
 int pcl_count(pcl_ctx *ctx, pcl_chunk *c) {
     if (int r = check_ready(ctx, c)) return r;
     if (int r = bind(ctx)) return r;
-    if (ctx->reduced && ctx->nranks > 1)
+    if (ctx->reduced && ctx->nranks > 1 && !ctx->frozen)
         return fail(ctx, PCL_ERR_ARG, "the counts already hold the sum over ranks: call pcl_counts_reset before counting again");
+    if (ctx->frozen) {                         // discarded increments go to scratch arrays (never read, never cleared)
+        for (int r = 0; r < ctx->n_reads; ++r)
+            for (int j = 0; j < ctx->infos[r].n_bc; ++j) {
+                Table &t = ctx->tables[ctx->bc_region[r][j]];
+                if (!t.d_scratch_counts) {
+                    CU(ctx, cudaMalloc(&t.d_scratch_counts, t.n_slots * sizeof(uint32_t)));
+                    CU(ctx, cudaMalloc(&t.d_scratch_scalars, 2 * sizeof(unsigned long long)));
+                }
+            }
+        if (!ctx->d_qc_scratch) CU(ctx, cudaMalloc(&ctx->d_qc_scratch, (PCL_MAX_READS + 12) * sizeof(unsigned long long)));
+    }
     if (c->n == 0) return PCL_OK;
     // Reads that hold barcodes first: the all-reduce of the counts only has to wait for their kernels (ev_counted), so it
     // runs while the length-only kernels of the insert reads are still going.
@@ -1094,7 +1112,9 @@ int pcl_count(pcl_ctx *ctx, pcl_chunk *c) {
         memset(&p, 0, sizeof p);
         p.rd = ctx->dreads[r];
         for (int j = 0; j < inf.n_bc; ++j) {
-            p.tab[j] = ctx->tables[ctx->bc_region[r][j]].d;
+            const Table &t = ctx->tables[ctx->bc_region[r][j]];
+            p.tab[j] = t.d;
+            if (ctx->frozen) { p.tab[j].counts = t.d_scratch_counts; p.tab[j].total = t.d_scratch_scalars; p.tab[j].mismatch = t.d_scratch_scalars + 1; }
             p.bc_key[j] = b.bc_key[j]; p.bcoord[j] = b.bcoord[j];
             p.bc_key_bytes[j] = inf.bc_key_bytes[j]; p.bc_elem[j] = inf.bc_elem[j];
         }
@@ -1107,7 +1127,7 @@ int pcl_count(pcl_ctx *ctx, pcl_chunk *c) {
         p.worklist = b.worklist; p.wl_count = b.wl_count;
         p.wl_key = read_all32(ctx, r) ? b.wl_key : nullptr;
         b.filtered = false;
-        p.num_defect = ctx->d_qc + r;
+        p.num_defect = (ctx->frozen ? ctx->d_qc_scratch : ctx->d_qc) + r;
         CU(ctx, cudaMemsetAsync(b.wl_count, 0, sizeof(unsigned long long), c->stream));
         const DRead &d = ctx->dreads[r];
         const bool fast = d.fast.enabled && ctx->tables[ctx->bc_region[r][0]].d.mode != PCL_TAB_K64 && !ctx->force_generic &&
@@ -1170,7 +1190,7 @@ int pcl_count(pcl_ctx *ctx, pcl_chunk *c) {
         else k_count<0><<<grid_for(ctx, c->n, 3 * ctx->occ[OCC_COUNT]), PCL_BLOCK, 0, c->stream>>>(p);
         prof_end(ctx, c->stream);
         CU(ctx, cudaGetLastError());
-        ctx->qc_reads[r] += c->n;
+        if (!ctx->frozen) ctx->qc_reads[r] += c->n;
         if (oi + 1 == n_with_bc) {
             if (!ctx->reduce_after_filter) { CU(ctx, cudaEventRecord(c->ev_counted, c->stream)); c->counted = true; }
             // The neighbourhood filter of pass 2 needs no counts: it runs here, behind the event the all-reduce waits for,
@@ -1181,6 +1201,49 @@ int pcl_count(pcl_ctx *ctx, pcl_chunk *c) {
             if (ctx->reduce_after_filter) { CU(ctx, cudaEventRecord(c->ev_counted, c->stream)); c->counted = true; }
         }
     }
+    return PCL_OK;
+}
+
+int pcl_counts_freeze(pcl_ctx *ctx, int on) {
+    if (!ctx) return PCL_ERR_ARG;
+    ctx->frozen = on != 0;
+    return PCL_OK;
+}
+
+uint64_t pcl_chunk_bytes(const pcl_ctx *ctx, uint64_t cap) {
+    if (!ctx || ctx->n_reads == 0) return 0;
+    uint64_t total = 0;
+    auto A = [&](uint64_t b) { total += ((b ? b : 16) + 255) & ~255ull; };
+    for (int r = 0; r < ctx->n_reads; ++r) {                       // mirrors pcl_chunk_create
+        const DRead &d = ctx->dreads[r];
+        const pcl_read_info &inf = ctx->infos[r];
+        if (d.needs_payload) A(cap * d.stride);
+        if ((d.needs_payload || d.qual_only) && d.qstride) A(cap * d.qstride);
+        A(cap * 2 + 16); A(cap * 2 + 16);
+        if (inf.has_target) A(cap * 4);
+        for (int j = 0; j < inf.n_bc; ++j) { A(cap * inf.bc_key_bytes[j]); if (!inf.fixed_layout) A(cap * 4); }
+        for (int j = 0; j < inf.n_umi; ++j) { A(cap * inf.umi_key_bytes[j]); if (!inf.fixed_layout) A(cap * 4); }
+        if (inf.n_bc) {
+            uint64_t warps = (uint64_t)ctx->sm_count * 24 * (PCL_BLOCK / 32), by_size = (cap + 31) / 32 + 32;
+            if (warps > by_size) warps = by_size;
+            const uint64_t wl_cap = (cap + warps * PCL_WL_BATCH) * inf.n_bc;
+            A(wl_cap * 8);
+            bool k32 = true;
+            for (int j = 0; j < inf.n_bc; ++j) k32 = k32 && inf.bc_key_bytes[j] == 4;
+            if (k32) { A(wl_cap * 4); A(wl_cap * 8); }
+        }
+        A(16);
+    }
+    return total;
+}
+
+int pcl_mem_info(pcl_ctx *ctx, uint64_t *free_bytes, uint64_t *total_bytes) {
+    if (!ctx) return PCL_ERR_ARG;
+    if (int r = bind(ctx)) return r;
+    size_t f = 0, t = 0;
+    CU(ctx, cudaMemGetInfo(&f, &t));
+    if (free_bytes) *free_bytes = f;
+    if (total_bytes) *total_bytes = t;
     return PCL_OK;
 }
 

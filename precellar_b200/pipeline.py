@@ -327,6 +327,18 @@ class BarcodePipeline:
     def correct(self, chunk: Chunk, threshold: float = 0.975, max_expected_errors: float = _ffi.F64_MAX) -> None:
         check(self.ctx, lib().pcl_correct(self.ctx, chunk.h, float(threshold), float(max_expected_errors)))
 
+    def freeze_counts(self, on: bool = True) -> None:
+        """After the all-reduce: ``count`` then recomputes a re-uploaded chunk without changing counts / totals / QC."""
+        check(self.ctx, lib().pcl_counts_freeze(self.ctx, int(on)))
+
+    def chunk_bytes(self, capacity: int) -> int:
+        return int(lib().pcl_chunk_bytes(self.ctx, int(capacity)))
+
+    def mem_info(self):
+        f, t = C.c_uint64(), C.c_uint64()
+        check(self.ctx, lib().pcl_mem_info(self.ctx, C.byref(f), C.byref(t)))
+        return f.value, t.value
+
     def sync(self) -> None:
         check(self.ctx, lib().pcl_sync(self.ctx))
 

@@ -196,6 +196,47 @@ def test_gen_barcoded_fastq_on_two_gpus(dataset, tmp_path, monkeypatch):
     assert outs[0] == outs[1] and len(outs[0]) > 100_000
 
 
+@pytest.mark.parametrize("keep_text", [True, False])
+@pytest.mark.parametrize("correct", [False, True])
+def test_streamed_chunks_match_the_resident_run(dataset, monkeypatch, keep_text, correct):
+    """Inputs larger than the device budget: the first chunks stay resident, the rest are counted through one reusable
+    chunk and uploaded again in pass 2, recounted against the frozen counts (pcl_counts_freeze).  Records and QC equal
+    the oracle's - the same as the all-resident run."""
+    from precellar_b200 import api
+    from precellar_b200.api import FastqProcessor
+    monkeypatch.setattr(api, "MIN_CHUNK_RECORDS", 700)                       # 5000 records -> 8 chunks
+    if not keep_text:
+        monkeypatch.setattr(api, "KEEP_TEXT_BYTES", 0)                       # pass 2 re-reads the files
+    proc = FastqProcessor(dataset["assay"]).with_modality("rna").with_barcode_correct_prob(0.9)
+    probe = api.BarcodePipeline(api.compile_layout(dataset["assay"], "rna", require_files=True), device=0, qc=False)
+    try:
+        proc.resident_bytes = 3 * probe.chunk_bytes(700) + 1                 # three resident chunks, five streamed
+    finally:
+        probe.close()
+    got = []
+    for batch in proc.gen_barcoded_fastq(correct, chunk_size=60_000):
+        got.extend(batch)
+    assert proc.streamed_chunks == 5
+    layout, ores = oracle_lines(dataset["assay"], dataset["full"], correct, 0.9)
+    want = [ln for ln in ores.lines if ln]
+    assert len(got) == len(want) > 3000
+    for rec, line in zip(got, want):
+        f = line.split("\t")
+        mine = [rec.barcode.raw.sequence, rec.barcode.raw.quality, rec.barcode.corrected if rec.barcode.corrected is not None else b"*",
+                rec.umi.sequence if rec.umi else b"", rec.umi.quality if rec.umi else b"",
+                rec.read1.sequence if rec.read1 else b"", rec.read1.quality if rec.read1 else b"",
+                rec.read2.sequence if rec.read2 else b"", rec.read2.quality if rec.read2 else b""]
+        assert [m.decode("latin-1") for m in mine] == f
+    qc = proc.get_fastq_qc()
+    per = ores.qc_per_file
+    want_defect = {rid: per[r, 1] / per[r, 0] for r, rid in enumerate(("R1", "R2")) if per[r, 1] > 0}
+    assert qc.get("frac_reads_with_misformed_structure", {}) == want_defect and want_defect
+    cat = ores.qc_cat.astype(float)
+    for j, nm in enumerate(("umi", "barcode", "read1", "read2")):
+        if cat[j, 1] > 0:
+            assert qc["frac_q30_bases"][nm] == cat[j, 2] / cat[j, 1]
+
+
 def test_make_fastq(dataset, tmp_path):
     """R1.fq.zst = corrected barcode + UMI + read1 (python/src/lib.rs:153-163); the insert is read on the pos strand."""
     import copy
