@@ -131,6 +131,12 @@ typedef struct {
 #define PCL_KEY_ABSENT64 0xFFFFFFFFFFFFFFFFull
 #define PCL_COORD_ABSENT 0xFFFFFFFFu
 
+/* pcl_read_info.route: which pass-1 kernel a read with 4-byte keys takes.  WALK = generic element walk; FAST = fixed
+ * layout within 32 bytes; FAST_SPEC = the same with a compile-time field geometry; PLAN = one variable element then an
+ * anchor; PLAN_GEO = the same with a compile-time geometry instance (sci-RNA-seq3 R1).  8-byte-key tables and the
+ * PCL_* environment switches may still send a read down the WALK kernel at launch time. */
+enum { PCL_ROUTE_WALK = 0, PCL_ROUTE_FAST = 1, PCL_ROUTE_FAST_SPEC = 2, PCL_ROUTE_PLAN = 3, PCL_ROUTE_PLAN_GEO = 4, PCL_ROUTE_LENONLY = 5 };
+
 typedef struct {
     uint8_t n_bc;                          /* barcode elements, in element order                      */
     uint8_t n_umi;                         /* UMI elements                                            */
@@ -138,7 +144,8 @@ typedef struct {
     uint8_t fixed_layout;                  /* all elements fixed-length except an optional last one   */
     uint8_t needs_payload;                 /* seq/qual bytes are read (else lengths only)             */
     uint8_t qual_only;                     /* QC mode, insert read: only the quality plane is used    */
-    uint8_t reserved[2];
+    uint8_t route;                         /* pass-1 kernel family of this read (PCL_ROUTE_*, informational) */
+    uint8_t reserved;
     uint8_t bc_elem[PCL_MAX_BC_PER_READ];  /* element index of each barcode element                   */
     uint8_t bc_key_bytes[PCL_MAX_BC_PER_READ];   /* 4 or 8                                            */
     uint8_t umi_elem[PCL_MAX_UMI_PER_READ];      /* element index of each UMI element                 */

@@ -40,9 +40,12 @@ class ReadDesc(C.Structure):
                 ("elems", ElemDesc * PCL_MAX_ELEMS)]
 
 
+ROUTE_WALK, ROUTE_FAST, ROUTE_FAST_SPEC, ROUTE_PLAN, ROUTE_PLAN_GEO, ROUTE_LENONLY = range(6)     # pcl_read_info.route
+
+
 class ReadInfo(C.Structure):
     _fields_ = [("n_bc", C.c_uint8), ("n_umi", C.c_uint8), ("has_target", C.c_uint8), ("fixed_layout", C.c_uint8),
-                ("needs_payload", C.c_uint8), ("qual_only", C.c_uint8), ("reserved", C.c_uint8 * 2),
+                ("needs_payload", C.c_uint8), ("qual_only", C.c_uint8), ("route", C.c_uint8), ("reserved", C.c_uint8),
                 ("bc_elem", C.c_uint8 * PCL_MAX_BC_PER_READ), ("bc_key_bytes", C.c_uint8 * PCL_MAX_BC_PER_READ),
                 ("umi_elem", C.c_uint8 * PCL_MAX_UMI_PER_READ), ("umi_key_bytes", C.c_uint8 * PCL_MAX_UMI_PER_READ),
                 ("static_start", C.c_uint16 * PCL_MAX_ELEMS), ("qual_offset", C.c_uint16), ("qual_stride", C.c_uint16)]

@@ -1303,59 +1303,157 @@ PCL_HD uint32_t pcl_plan_key(const uint32_t *c, const uint32_t *bd, uint32_t sta
     return key;
 }
 
-// The same results for a record that holds every element whatever the anchor position (L >= plan.full_len): no walk,
-// no per-element bounds, only the words the fields can touch are converted.  Returns false for shorter records.
-template <bool kRev>
-PCL_HD bool pcl_plan_record_fast(const DRead &rd, const uint32_t *w, uint32_t L, PlanOut &o) {
-    const AnchorPlan &pl = rd.plan;
-    if (L < pl.full_len) return false;
+// ------------------------------------------------------------------------------------------
+// Geometry of an AnchorPlan layout as seen by the straight-line route: either read from the DRead at run time
+// (PlanGeoRt: any layout the plan accepts) or a set of compile-time constants (PlanGeoSci3 ...: element offsets, anchor
+// code, window width and field widths fold into immediates, the loops over positions / barcodes / UMIs unroll, and the
+// words of the code strings are picked without selects or uniform branches).  pcl_plan_geo_matches tells the host which
+// instance a layout may use; the results are the same by construction (one function body, pcl_plan_fast_g).
+// ------------------------------------------------------------------------------------------
+struct PlanGeoRt {
+    static constexpr bool kConst = false;
+    const DRead &rd;
+    PCL_HD explicit PlanGeoRt(const DRead &r) : rd(r) {}
+    PCL_HD uint32_t n_elems() const { return rd.n_elems; }
+    PCL_HD uint32_t v() const { return rd.plan.v; }
+    PCL_HD uint32_t vmin() const { return rd.elems[rd.plan.v].min_len; }
+    PCL_HD uint32_t n_pos() const { return rd.plan.n_pos; }
+    PCL_HD uint32_t a_start() const { return rd.plan.a_start; }
+    PCL_HD uint32_t a_len() const { return rd.plan.a_len; }
+    PCL_HD uint32_t a_maxmis() const { return rd.plan.a_maxmis; }
+    PCL_HD uint32_t needle(bool rev) const { return (uint32_t)(rev ? rd.elems[rd.plan.v + 1u].a_rc : rd.elems[rd.plan.v + 1u].a_code); }
+    PCL_HD uint32_t full_len() const { return rd.plan.full_len; }
+    PCL_HD uint32_t n_words() const { return rd.plan.n_words; }
+    PCL_HD uint32_t stride() const { return rd.stride; }
+    PCL_HD uint32_t n_bc() const { return rd.n_bc; }
+    PCL_HD uint32_t n_umi() const { return rd.n_umi; }
+    PCL_HD uint32_t bc_elem(uint32_t j) const { return rd.plan.bc_elem[j]; }
+    PCL_HD uint32_t umi_elem(uint32_t j) const { return rd.plan.umi_elem[j]; }
+    PCL_HD uint32_t ustart(uint32_t e) const { return rd.plan.ustart[e]; }
+    PCL_HD uint32_t max_len(uint32_t e) const { return rd.elems[e].max_len; }
+    PCL_HD bool has_t() const { return rd.plan.has_t != 0; }
+    PCL_HD bool has_target() const { return rd.has_target != 0 && rd.plan.t_elem != 0xFFu; }
+    PCL_HD uint32_t t_elem() const { return rd.plan.t_elem; }
+};
+
+// 2-bit code string of an upper-case ACGT literal, base i at bits 2i (DElem::a_code) / of its reverse complement (a_rc)
+constexpr uint32_t pcl_lit_code(const char *s, uint32_t n, bool rc) {
+    uint32_t out = 0;
+    for (uint32_t t = 0; t < n; ++t) {
+        const char b = s[t];
+        const uint32_t c = b == 'A' ? 0u : b == 'C' ? 1u : b == 'G' ? 2u : 3u;
+        out |= rc ? (3u - c) << (2u * (n - 1u - t)) : c << (2u * t);
+    }
+    return out;
+}
+
+// sci-RNA-seq3 R1 (seqspec_templates/sci_rna_seq3.yaml): hairpin barcode 9-10 | CAGAGC | UMI 8 | RT barcode 10
+struct PlanGeoSci3 {
+    static constexpr bool kConst = true;
+    PCL_HD explicit PlanGeoSci3(const DRead &) {}
+    PCL_HD static constexpr uint32_t n_elems() { return 4u; }
+    PCL_HD static constexpr uint32_t v() { return 0u; }
+    PCL_HD static constexpr uint32_t vmin() { return 9u; }
+    PCL_HD static constexpr uint32_t n_pos() { return 2u; }
+    PCL_HD static constexpr uint32_t a_start() { return 9u; }
+    PCL_HD static constexpr uint32_t a_len() { return 6u; }
+    PCL_HD static constexpr uint32_t a_maxmis() { return 1u; }                      // floor(0.2 * 6)
+    PCL_HD static constexpr uint32_t needle(bool rev) { return pcl_lit_code("CAGAGC", 6u, rev); }
+    PCL_HD static constexpr uint32_t full_len() { return 34u; }
+    PCL_HD static constexpr uint32_t n_words() { return 9u; }
+    PCL_HD static constexpr uint32_t stride() { return 48u; }                        // 34 record bytes in 16-byte vectors
+    PCL_HD static constexpr uint32_t n_bc() { return 2u; }
+    PCL_HD static constexpr uint32_t n_umi() { return 1u; }
+    PCL_HD static constexpr uint32_t bc_elem(uint32_t j) { return j == 0u ? 0u : 3u; }
+    PCL_HD static constexpr uint32_t umi_elem(uint32_t) { return 2u; }
+    PCL_HD static constexpr uint32_t ustart(uint32_t e) { return e == 0u ? 0u : e == 1u ? 9u : e == 2u ? 15u : 23u; }
+    PCL_HD static constexpr uint32_t max_len(uint32_t e) { return e == 0u ? 10u : e == 1u ? 6u : e == 2u ? 8u : 10u; }
+    PCL_HD static constexpr bool has_t() { return false; }
+    PCL_HD static constexpr bool has_target() { return false; }
+    PCL_HD static constexpr uint32_t t_elem() { return 0xFFu; }
+};
+
+// Host side: may layout `rd` run the instance G?  Every constant G holds is compared with the compiled plan.
+template <class G>
+inline bool pcl_plan_geo_matches(const DRead &rd) {
+    const PlanGeoRt r(rd);
+    const G g(rd);
+    if (!rd.plan.enabled || rd.plan.full_len == 0xFFFFu) return false;
+    bool ok = r.n_elems() == g.n_elems() && r.v() == g.v() && r.vmin() == g.vmin() && r.n_pos() == g.n_pos() && r.a_start() == g.a_start() &&
+              r.a_len() == g.a_len() && r.a_maxmis() == g.a_maxmis() && r.needle(false) == g.needle(false) && r.needle(true) == g.needle(true) &&
+              r.full_len() == g.full_len() && r.n_words() == g.n_words() && r.stride() == g.stride() && r.n_bc() == g.n_bc() && r.n_umi() == g.n_umi() &&
+              r.has_t() == g.has_t() && r.has_target() == g.has_target() && (!r.has_target() || r.t_elem() == g.t_elem());
+    for (uint32_t e = 0; ok && e < r.n_elems(); ++e) ok = r.ustart(e) == g.ustart(e) && r.max_len(e) == g.max_len(e);
+    for (uint32_t j = 0; ok && j < r.n_bc(); ++j) ok = r.bc_elem(j) == g.bc_elem(j);
+    for (uint32_t j = 0; ok && j < r.n_umi(); ++j) ok = r.umi_elem(j) == g.umi_elem(j);
+    return ok;
+}
+
+// The same results as pcl_plan_record for a record that holds every element whatever the anchor position
+// (L >= full_len): no walk, no per-element bounds, only the words the fields can touch are converted.  Returns false
+// for shorter records.
+template <bool kRev, class G>
+PCL_HD bool pcl_plan_fast_g(const G &g, const uint32_t *w, uint32_t L, PlanOut &o) {
+    if (L < g.full_len()) return false;
     Codes32 k;
-    pcl_codes32_exact<kRev>(w, (int)pl.n_words, k);
+    pcl_codes32_exact<kRev>(w, (int)g.n_words(), k);
     // find_best_pattern_match over the n_pos window positions (leftmost strict minimum; segment.rs:496-535)
-    const uint32_t m = pl.a_len, v = pl.v, a = v + 1u;
-    const uint32_t needle = (uint32_t)(kRev ? rd.elems[a].a_rc : rd.elems[a].a_code);
+    const uint32_t m = g.a_len(), v = g.v();
+    const uint32_t needle = g.needle(kRev);
     const uint32_t even = m >= 16u ? 0x55555555u : (0x55555555u & ((1u << (2u * m)) - 1u));
     uint32_t best = 0xFFFFFFFFu, bpos = 0;
-    for (uint32_t i = 0; i < pl.n_pos; ++i) {
-        const uint32_t p = pl.a_start + (kRev ? pl.n_pos - 1u - i : i);              // neg strand: position i of rev_compl(window)
+#ifdef __CUDA_ARCH__
+#pragma unroll(G::kConst ? 16 : 1)
+#endif
+    for (uint32_t i = 0; i < 16u; ++i) {
+        if (i >= g.n_pos()) break;
+        const uint32_t p = g.a_start() + (kRev ? g.n_pos() - 1u - i : i);            // neg strand: position i of rev_compl(window)
         const uint32_t x = pcl_win32u(k.c, p, m) ^ needle;
         const uint32_t cnt = pcl_popc32(((x | (x >> 1)) | pcl_win32u(k.sb, p, m)) & even);
         if (cnt < best) { best = cnt; bpos = i; }
     }
     uint32_t status = PCL_SPLIT_OK;
     if (m == 1u && best != 0u) status = PCL_SPLIT_ANCHOR_NOT_FOUND;                   // (None, 1) (segment.rs:508-512)
-    else if (best > pl.a_maxmis) status = PCL_SPLIT_PATTERN_MISMATCH;                // the window lies inside the record (L >= full_len)
+    else if (best > g.a_maxmis()) status = PCL_SPLIT_PATTERN_MISMATCH;               // the window lies inside the record (L >= full_len)
     const bool ok = status == PCL_SPLIT_OK;
     const uint32_t pos = ok ? bpos : 0u;
     uint32_t c2[4], bd2[4];
     pcl_shr_bases(k.c, pos, c2);
     pcl_shr_bases(k.bd, pos, bd2);
     o.status = status;
-    const uint32_t n = rd.n_elems, vmin = rd.elems[v].min_len;
+    const uint32_t n = g.n_elems(), vmin = g.vmin();
     o.tcoord = PCL_COORD_ABSENT;
-    if (ok && rd.has_target && pl.t_elem != 0xFFu) {
-        const uint32_t e = pl.t_elem;
-        const uint32_t start = pl.ustart[e] + (e > v ? pos : 0u);
-        uint32_t len = e == v ? vmin + pos : rd.elems[e].max_len;
-        if (pl.has_t && e + 1u == n) len = (start + rd.elems[e].max_len < L ? start + rd.elems[e].max_len : L) - start;   // tail consume_buf
-        o.tcoord = (start << 16) | len;
+    if (g.has_target()) {
+        const uint32_t e = g.t_elem();
+        const uint32_t start = g.ustart(e) + (e > v ? pos : 0u);
+        uint32_t len = e == v ? vmin + pos : g.max_len(e);
+        if (g.has_t() && e + 1u == n) len = (start + g.max_len(e) < L ? start + g.max_len(e) : L) - start;   // tail consume_buf
+        if (ok) o.tcoord = (start << 16) | len;
     }
-    for (uint32_t j = 0; j < rd.n_bc; ++j) {
-        const uint32_t e = pl.bc_elem[j];
+#ifdef __CUDA_ARCH__
+#pragma unroll(G::kConst ? 4 : 1)
+#endif
+    for (uint32_t j = 0; j < PCL_MAX_BC_PER_READ; ++j) {
+        if (j >= g.n_bc()) break;
+        const uint32_t e = g.bc_elem(j);
         const bool behind = e > v;
-        const uint32_t us = pl.ustart[e];
-        uint32_t len = e == v ? vmin + pos : rd.elems[e].max_len;
-        if (pl.has_t && e + 1u == n) len = (us + pos + rd.elems[e].max_len < L ? us + pos + rd.elems[e].max_len : L) - (us + pos);
+        const uint32_t us = g.ustart(e);
+        uint32_t len = e == v ? vmin + pos : g.max_len(e);
+        if (g.has_t() && e + 1u == n) len = (us + pos + g.max_len(e) < L ? us + pos + g.max_len(e) : L) - (us + pos);
         o.bcoord[j] = ok ? (((us + (behind ? pos : 0u)) << 16) | len) : PCL_COORD_ABSENT;
         o.bkey[j] = 0; o.bninv[j] = 0; o.bipos[j] = 0;
         if (ok) o.bkey[j] = pcl_plan_key(behind ? c2 : k.c, behind ? bd2 : k.bd, us, len > 16u ? 16u : len, kRev, &o.bninv[j], &o.bipos[j]);
     }
-    for (uint32_t j = 0; j < rd.n_umi; ++j) {
-        const uint32_t e = pl.umi_elem[j];
+#ifdef __CUDA_ARCH__
+#pragma unroll(G::kConst ? 4 : 1)
+#endif
+    for (uint32_t j = 0; j < PCL_MAX_UMI_PER_READ; ++j) {
+        if (j >= g.n_umi()) break;
+        const uint32_t e = g.umi_elem(j);
         const bool behind = e > v;
-        const uint32_t us = pl.ustart[e];
-        uint32_t len = e == v ? vmin + pos : rd.elems[e].max_len;
-        if (pl.has_t && e + 1u == n) len = (us + pos + rd.elems[e].max_len < L ? us + pos + rd.elems[e].max_len : L) - (us + pos);
+        const uint32_t us = g.ustart(e);
+        uint32_t len = e == v ? vmin + pos : g.max_len(e);
+        if (g.has_t() && e + 1u == n) len = (us + pos + g.max_len(e) < L ? us + pos + g.max_len(e) : L) - (us + pos);
         o.ucoord[j] = ok ? (((us + (behind ? pos : 0u)) << 16) | len) : PCL_COORD_ABSENT;
         o.ukey[j] = PCL_KEY_ABSENT32;
         if (ok) {
@@ -1365,6 +1463,11 @@ PCL_HD bool pcl_plan_record_fast(const DRead &rd, const uint32_t *w, uint32_t L,
         }
     }
     return true;
+}
+
+template <bool kRev>
+PCL_HD bool pcl_plan_record_fast(const DRead &rd, const uint32_t *w, uint32_t L, PlanOut &o) {
+    return pcl_plan_fast_g<kRev>(PlanGeoRt(rd), w, L, o);
 }
 
 // Store a key in its device width (see precellar_b200.h).

@@ -257,6 +257,10 @@ inline int pcl_build_read(int r, const pcl_read_desc &rd, DRead *out, pcl_read_i
             for (int j = 0; j < info.n_umi; ++j) pl.umi_elem[j] = info.umi_elem[j];
         }
     }
+    info.route = !d.needs_payload ? PCL_ROUTE_LENONLY
+                 : d.fast.enabled ? (d.fast.spec != PCL_FAST_SPEC_NONE ? PCL_ROUTE_FAST_SPEC : PCL_ROUTE_FAST)
+                 : d.plan.enabled ? ((!d.is_reverse && pcl_plan_geo_matches<PlanGeoSci3>(d)) ? PCL_ROUTE_PLAN_GEO : PCL_ROUTE_PLAN)
+                 : PCL_ROUTE_WALK;
     *out = d;
     *info_out = info;
     return PCL_OK;

@@ -9,6 +9,7 @@
 #define PCL_KERNELS_CUH
 
 #include <cuda_runtime.h>
+#include <type_traits>
 
 #include "hd_core.h"
 
@@ -406,27 +407,44 @@ __global__ void __launch_bounds__(PCL_BLOCK, kMode == 2 ? 4 : 1) k_count(const _
 // Thread per record; records long enough for every element go through the straight-line pcl_plan_record_fast (one window
 // search, fields cut at warp-uniform offsets), anything shorter through the element-by-element walk (out of line).
 // ------------------------------------------------------------------------------------------------
-template <bool kRev>
+template <bool kRev, class G>
 __global__ void __launch_bounds__(PCL_BLOCK, 4) k_count_plan(const __grid_constant__ CountParams p) {
     __shared__ uint32_t ck[PCL_HCACHE];
     __shared__ uint32_t cc[PCL_HCACHE];
     const DRead &rd = p.rd;
+    const G geo(rd);
     for (uint32_t h = threadIdx.x; h < PCL_HCACHE; h += blockDim.x) { ck[h] = PCL_HEMPTY; cc[h] = 0; }
     __syncthreads();
     const uint32_t lane = threadIdx.x & 31u;
-    const uint64_t step = (uint64_t)gridDim.x * blockDim.x;
-    const uint32_t n_vec = rd.stride >> 4;                              // 16-byte vectors per record row (<= 4)
+    const uint32_t n = (uint32_t)p.n;                                   // chunks hold fewer than 2^32 records (pcl_chunk_create)
+    const uint32_t step = gridDim.x * blockDim.x;
+    const uint32_t stride = G::kConst ? geo.stride() : rd.stride;
+    const uint32_t n_vec = stride >> 4;                                 // 16-byte vectors per record row (<= 4)
     const uint32_t lcap = rd.max_len ? rd.max_len : 0xFFFFFFFFu;
-    const uint32_t n_bc = rd.n_bc, n_umi = rd.n_umi;
+    const uint32_t n_bc = geo.n_bc(), n_umi = geo.n_umi();
+    const bool want_t = G::kConst ? geo.has_target() : rd.has_target != 0;
+    // a table of 16-mers only holds 16-base barcodes, the marker-form tables only shorter ones
+    bool l16[PCL_MAX_BC_PER_READ];
+#pragma unroll
+    for (uint32_t j = 0; j < PCL_MAX_BC_PER_READ; ++j) l16[j] = j < n_bc && p.tab[j].mode == PCL_TAB_K32_L16;
     uint32_t n_total[PCL_MAX_BC_PER_READ] = {0, 0, 0, 0}, n_mis[PCL_MAX_BC_PER_READ] = {0, 0, 0, 0}, n_defect = 0;
     WlCursor wl = {0, 0};
-    // every lane of a warp runs the same number of iterations (full-mask ballots below)
-    for (uint64_t base = (uint64_t)blockIdx.x * blockDim.x + (threadIdx.x & ~31u); base < p.n; base += step) {
-        const uint64_t i = base + lane;
-        const bool live = i < p.n;
-        const uint64_t ld = live ? i : p.n - 1;                         // out-of-range lanes re-read the last record
+
+    // One warp iteration = 32 consecutive records.  `full` (every lane holds a record: all but the last slice of the
+    // chunk) is a compile-time property of the body, so that the common case carries no per-lane bounds predicates.
+    auto body = [&](const uint32_t base, auto full_tag) {
+        constexpr bool kFull = decltype(full_tag)::value;
+        const uint32_t i = base + lane;
+        const bool live = kFull || i < n;
+        const uint32_t ld = live ? i : n - 1u;                          // out-of-range lanes re-read the last record
+        if (G::kConst && n - base > step) {
+            // the rows of the next iteration travel from DRAM to L2 while this one is processed (every 128-byte line of
+            // the warp's slice holds at least one row start: strides are <= 64)
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(p.seq + (uint64_t)(i + step) * stride));
+            if (lane == 0u) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.len + (i + step)));
+        }
         uint32_t w[16];
-        const uint4 *r4 = reinterpret_cast<const uint4 *>(p.seq + ld * (uint64_t)rd.stride);
+        const uint4 *r4 = reinterpret_cast<const uint4 *>(p.seq + (uint64_t)ld * stride);
 #pragma unroll
         for (uint32_t v = 0; v < 4u; ++v) {
             uint4 t = make_uint4(0u, 0u, 0u, 0u);
@@ -436,11 +454,11 @@ __global__ void __launch_bounds__(PCL_BLOCK, 4) k_count_plan(const __grid_consta
         const uint32_t L = min((uint32_t)__ldcs(p.len + ld), lcap);     // FastqReader::read_record (read.rs:98-103)
         PlanOut o;
         // warp-uniform choice (a warp with one short record walks all of its records: same results, and rare)
-        if (__all_sync(0xFFFFFFFFu, L >= rd.plan.full_len)) (void)pcl_plan_record_fast<kRev>(rd, w, L, o);
+        if (__all_sync(0xFFFFFFFFu, L >= geo.full_len())) (void)pcl_plan_fast_g<kRev>(geo, w, L, o);
         else pcl_plan_record<kRev>(rd, w, L, o);
         uint32_t fs = o.status;
         n_defect += live & (o.status != PCL_SPLIT_OK);
-        if (rd.has_target) {
+        if (want_t) {
             if (o.tcoord != PCL_COORD_ABSENT) fs |= PCL_FSTATUS_TARGET;
             if (live) pcl_st_stream(p.tcoord + i, o.tcoord);
         }
@@ -455,7 +473,7 @@ __global__ void __launch_bounds__(PCL_BLOCK, 4) k_count_plan(const __grid_consta
                 const uint32_t blen = c & 0xFFFFu;
                 const DTable &t = p.tab[j];
                 uint32_t slot = 0xFFFFFFFFu;
-                if (o.bninv[j] == 0u && (t.mode == PCL_TAB_K32_L16 ? blen == 16u : blen <= 15u)) slot = pcl_probe32(t, o.bkey[j]);
+                if (o.bninv[j] == 0u && (l16[j] ? blen == 16u : blen <= 15u)) slot = pcl_probe32(t, o.bkey[j]);
                 n_total[j] += live;                                     // WhitelistBuilder::add (barcode.rs:410-426)
                 if (slot != 0xFFFFFFFFu) {
                     code = PCL_BC_EXACT;
@@ -486,7 +504,7 @@ __global__ void __launch_bounds__(PCL_BLOCK, 4) k_count_plan(const __grid_consta
             const uint32_t c0 = o.bcoord[0], c1 = n_bc > 1u ? o.bcoord[1] : 0u;
             const uint32_t h0 = (c0 >> 16) | ((c0 & 0xFFu) << 16) | ((o.bninv[0] == 1u ? 1u : 0u) << 26) | ((o.bninv[0] == 1u ? o.bipos[0] : 0u) << 27);
             const uint32_t h1 = (c1 >> 16) | ((c1 & 0xFFu) << 16) | (1u << 24) | ((o.bninv[1] == 1u ? 1u : 0u) << 26) | ((o.bninv[1] == 1u ? o.bipos[1] : 0u) << 27);
-            pcl_wl_push2(p, wl, miss[0], h0, (uint32_t)i, o.bkey[0], n_bc > 1u && miss[1], h1, (uint32_t)i, o.bkey[1], lane);
+            pcl_wl_push2(p, wl, miss[0], h0, i, o.bkey[0], n_bc > 1u && miss[1], h1, i, o.bkey[1], lane);
         }
 #pragma unroll
         for (uint32_t j = 2; j < PCL_MAX_BC_PER_READ; ++j) {
@@ -494,6 +512,15 @@ __global__ void __launch_bounds__(PCL_BLOCK, 4) k_count_plan(const __grid_consta
             const uint32_t c = o.bcoord[j];
             pcl_wl_push(p, wl, miss[j], pcl_wl_pack(i, c >> 16, c & 0xFFFFu, j, o.bninv[j], o.bipos[j]), o.bkey[j], lane);
         }
+    };
+
+    // every lane of a warp runs the same iterations (full-mask ballots in the body); `n - base > step` instead of
+    // `base + step < n`: the index may not wrap
+    for (uint32_t base = blockIdx.x * blockDim.x + (threadIdx.x & ~31u); base < n;) {
+        if (n - base >= 32u) body(base, std::true_type{});
+        else body(base, std::false_type{});
+        if (n - base <= step) break;
+        base += step;
     }
     pcl_wl_finish(p, wl, lane);
 #pragma unroll

@@ -142,6 +142,7 @@ struct pcl_ctx {
     bool no_neighbour_tables = false;   // PCL_NO_NEIGHBOUR_TABLES=1: 3*L direct probes instead of the 4 neighbourhood tables
     uint64_t device_build_min = 100000; // whitelists from this many entries on are deduplicated and hashed on the device (PCL_DEVICE_BUILD_MIN)
     bool reduce_after_filter = false;   // PCL_REDUCE_AFTER_FILTER=1: the all-reduce waits for k_filter instead of overlapping it (experiments)
+    bool no_plan_geo = false;           // PCL_NO_PLAN_GEO=1: AnchorPlan layouts always run the run-time geometry (tests compare the two)
     bool no_nbits = false;              // PCL_NO_NBITS=1: no partial-key bitmaps in front of the neighbourhood tables
 };
 
@@ -285,6 +286,7 @@ int pcl_ctx_create(pcl_ctx **out, int device) {
     { const char *g = getenv("PCL_NO_FAST_SPEC"); ctx->no_fast_spec = g && g[0] == '1'; }
     { const char *g = getenv("PCL_NO_NEIGHBOUR_TABLES"); ctx->no_neighbour_tables = g && g[0] == '1'; }
     { const char *g = getenv("PCL_NO_NBITS"); ctx->no_nbits = g && g[0] == '1'; }
+    { const char *g = getenv("PCL_NO_PLAN_GEO"); ctx->no_plan_geo = g && g[0] == '1'; }
     { const char *g = getenv("PCL_REDUCE_AFTER_FILTER"); ctx->reduce_after_filter = g && g[0] == '1'; }
     { const char *g = getenv("PCL_DEVICE_BUILD_MIN"); if (g) ctx->device_build_min = strtoull(g, nullptr, 10); }
     memset(ctx->descs, 0, sizeof ctx->descs);
@@ -323,7 +325,7 @@ int pcl_ctx_create(pcl_ctx **out, int device) {
         ctx->occ[OCC_COUNT] = occ((const void *)k_count<0>);
         ctx->occ[OCC_COUNT_CODES] = occ((const void *)k_count<1>);
         ctx->occ[OCC_COUNT_PLAN] = occ((const void *)k_count<2>);
-        ctx->occ[OCC_COUNT_PLAN2] = occ((const void *)k_count_plan<false>);
+        ctx->occ[OCC_COUNT_PLAN2] = occ((const void *)k_count_plan<false, PlanGeoRt>);
         {
             // k_count_fast: 1024-thread CTAs with a 16 K-entry histogram cache (128 KB), one resident wave, two
             // candidate lines per key, a new key admitted on 1 of 8 sightings.  Measured on 125 M v3 records:
@@ -1182,8 +1184,10 @@ int pcl_count(pcl_ctx *ctx, pcl_chunk *c) {
         else if (lenonly) k_count_lenonly<<<grid_for(ctx, c->n / 8 + 8, ctx->occ[OCC_COUNT_LENONLY]), PCL_BLOCK, 0, c->stream>>>(p);
         else if (plan && !ctx->old_fast && p.wl_key) {
             const int g = grid_for(ctx, c->n, 3 * ctx->occ[OCC_COUNT_PLAN2]);
-            if (d.is_reverse) k_count_plan<true><<<g, PCL_BLOCK, 0, c->stream>>>(p);
-            else k_count_plan<false><<<g, PCL_BLOCK, 0, c->stream>>>(p);
+            // compile-time geometry for the layouts that have an instance (pcl_plan_geo_matches), else the run-time plan
+            if (!d.is_reverse && !ctx->no_plan_geo && pcl_plan_geo_matches<PlanGeoSci3>(d)) k_count_plan<false, PlanGeoSci3><<<g, PCL_BLOCK, 0, c->stream>>>(p);
+            else if (d.is_reverse) k_count_plan<true, PlanGeoRt><<<g, PCL_BLOCK, 0, c->stream>>>(p);
+            else k_count_plan<false, PlanGeoRt><<<g, PCL_BLOCK, 0, c->stream>>>(p);
         }
         else if (plan) k_count<2><<<grid_for(ctx, c->n, 3 * ctx->occ[OCC_COUNT_PLAN]), PCL_BLOCK, 0, c->stream>>>(p);
         else if (d.codes_ok && !ctx->force_generic) k_count<1><<<grid_for(ctx, c->n, 3 * ctx->occ[OCC_COUNT_CODES]), PCL_BLOCK, 0, c->stream>>>(p);

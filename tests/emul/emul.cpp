@@ -194,6 +194,20 @@ int emu_run(const pcl_read_desc *reads, int n_reads, int n_regions, const uint8_
                     for (uint32_t j = 0; j < rd.n_umi; ++j) same = same && po.ucoord[j] == pg.ucoord[j] && po.ukey[j] == pg.ukey[j];
                     if (!same) { snprintf(err, errcap, "plan fast path disagrees with the walk at record %llu", (unsigned long long)i); return PCL_ERR_INPUT; }
                 } else po = pg;
+                if (!rev && pcl_plan_geo_matches<PlanGeoSci3>(rd)) {      // ... and so must the compile-time geometry instance
+                    PlanOut ps;
+                    memset(&ps, 0, sizeof ps);
+                    const bool fasts = pcl_plan_fast_g<false>(PlanGeoSci3(rd), w, L, ps);
+                    bool same = fasts == fastp;
+                    if (fasts && same) {
+                        same = ps.status == pg.status && ps.tcoord == pg.tcoord;
+                        for (uint32_t j = 0; j < rd.n_bc; ++j)
+                            same = same && ps.bcoord[j] == pg.bcoord[j] && ps.bkey[j] == pg.bkey[j] && ps.bninv[j] == pg.bninv[j] &&
+                                   (ps.bninv[j] != 1u || ps.bipos[j] == pg.bipos[j]);
+                        for (uint32_t j = 0; j < rd.n_umi; ++j) same = same && ps.ucoord[j] == pg.ucoord[j] && ps.ukey[j] == pg.ukey[j];
+                    }
+                    if (!same) { snprintf(err, errcap, "PlanGeoSci3 disagrees with the walk at record %llu", (unsigned long long)i); return PCL_ERR_INPUT; }
+                }
                 uint32_t fs = po.status;
                 if (po.status != PCL_SPLIT_OK) defects_out[r]++;
                 if (rd.has_target) {

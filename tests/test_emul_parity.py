@@ -186,6 +186,13 @@ def test_fast_path_selection(layouts):
     assert sel("k64_rev") == [0, 3]              # 64-bit keys -> interpreter; neg strand [variable][anchor][UMI][target] -> plan
     assert sel("dsc") == [0, 2]                  # a fixed barcode between the variable run and the anchor: interpreter
     assert sel("share") == [2, 0]
+    # pcl_read_info.route: the compile-time instances (10x v3 R1 field geometry, sci-RNA-seq3 R1 plan geometry)
+    from precellar_b200 import _ffi
+    route = lambda name: [i.route for i in U.emul_infos(layouts[name])[0]]
+    assert _ffi.ROUTE_PLAN_GEO == 4
+    assert route("sci3") == [_ffi.ROUTE_PLAN_GEO, _ffi.ROUTE_LENONLY]
+    assert route("v3") == [_ffi.ROUTE_FAST_SPEC, _ffi.ROUTE_LENONLY]
+    assert route("k64_rev")[1] == _ffi.ROUTE_PLAN and route("dsc")[0] == _ffi.ROUTE_WALK
 
 
 def _dense_layouts(rng):
