@@ -285,6 +285,10 @@ const char *pcl_fastq_error(const pcl_fastq *r);
 int64_t pcl_fastq_read(pcl_fastq *r, uint64_t max_records, uint32_t stride, uint32_t qual_offset, uint32_t qual_stride,
                        uint8_t *seq, uint8_t *qual, uint16_t *len, uint64_t *name_hash, uint8_t *text, uint64_t text_cap,
                        uint64_t *off, uint64_t *text_used);
+/* 1 when that call stopped early because `text` was full.  Nothing is lost: call pcl_fastq_read again with a larger
+ * arena (the old contents copied, *text_used carried over) and seq / qual / len / name_hash / off advanced by the
+ * records already delivered (off by 3 per record), so that a batch keeps its size whatever the header lengths. */
+int pcl_fastq_text_full(const pcl_fastq *r);
 
 /* ---- host-side record assembly for writers ------------------------------------------------------
  * make_fastq's record loop (python/src/lib.rs:149-167) on top of FastqAnnotator::annotate / AnnotatedFastq::join /

@@ -82,7 +82,7 @@ SYMBOLS = [
     "pcl_host_alloc", "pcl_host_free", "pcl_profile_enable", "pcl_profile_get", "pcl_profile_reset",
     "pcl_launch_count", "pcl_timer_start", "pcl_timer_stop_ms",
     "pcl_qc_enable", "pcl_qc_accumulate", "pcl_qc_fetch_categories",
-    "pcl_fastq_open", "pcl_fastq_close", "pcl_fastq_error", "pcl_fastq_read", "pcl_chunk_fetch_async",
+    "pcl_fastq_open", "pcl_fastq_close", "pcl_fastq_error", "pcl_fastq_read", "pcl_fastq_text_full", "pcl_chunk_fetch_async",
     "pcl_make_fastq_batch",
     "pcl_text_scan", "pcl_text_lines", "pcl_text_fill", "pcl_text_names_check", "pcl_text_line_ends",
     "pcl_chunk_upload_compact", "pcl_read_payload_bytes",
@@ -173,6 +173,7 @@ def lib() -> C.CDLL:
         "pcl_fastq_close": (None, [vp]),
         "pcl_fastq_error": (C.c_char_p, [vp]),
         "pcl_fastq_read": (C.c_int64, [vp, u64, u32, u32, u32, vp, vp, vp, vp, vp, u64, vp, C.POINTER(u64)]),
+        "pcl_fastq_text_full": (C.c_int, [vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)

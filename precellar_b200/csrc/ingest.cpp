@@ -65,6 +65,8 @@ struct pcl_fastq {
     std::string err;
     uint64_t n_records = 0;
     std::string line[4];
+    bool text_full = false;             // the last pcl_fastq_read stopped because the caller's text arena was full
+    bool pending = false;               // ... with the record in line[0..3] read but not delivered yet
 
     static bool is_zst(const std::string &p) { return p.size() > 4 && p.compare(p.size() - 4, 4, ".zst") == 0; }
     void close_cur() {
@@ -187,10 +189,11 @@ int64_t pcl_fastq_read(pcl_fastq *r, uint64_t max_records, uint32_t stride, uint
     if (!r || !len) return PCL_ERR_ARG;
     uint64_t n = 0, used = text_used ? *text_used : 0;
     if (off && n == 0) off[0] = used;
+    r->text_full = false;
     while (n < max_records) {
         // Fast route: the four lines of the record lie inside the decode buffer -> no per-line string copies.
         // (Blank lines between records, "\r\n" and records that straddle a refill take the general route below.)
-        if (r->pos < r->end && r->buf[r->pos] == '@') {
+        if (!r->pending && r->pos < r->end && r->buf[r->pos] == '@') {
             const uint8_t *p0 = r->buf.data() + r->pos, *pe = r->buf.data() + r->end;
             const uint8_t *e0 = (const uint8_t *)memchr(p0, '\n', pe - p0);
             const uint8_t *e1 = e0 ? (const uint8_t *)memchr(e0 + 1, '\n', pe - (e0 + 1)) : nullptr;
@@ -222,7 +225,7 @@ int64_t pcl_fastq_read(pcl_fastq *r, uint64_t max_records, uint32_t stride, uint
                 if (name_hash) name_hash[n] = fnv1a((const char *)p0 + 1, name_len);
                 if (text && off) {
                     const uint64_t need = (dlen - 1) + 2 * L;
-                    if (used + need > text_cap) { r->err = "text arena too small"; return PCL_ERR_NOMEM; }
+                    if (used + need > text_cap) { r->text_full = true; break; }      // the record stays unread: the caller grows the arena
                     memcpy(text + used, p0 + 1, name_len); used += name_len;
                     memcpy(text + used, p0 + e, dlen - e); used += dlen - e;
                     off[3 * n + 1] = used;
@@ -235,17 +238,25 @@ int64_t pcl_fastq_read(pcl_fastq *r, uint64_t max_records, uint32_t stride, uint
                 continue;
             }
         }
-        if (!r->getline(r->line[0])) break;
-        if (r->line[0].empty()) continue;                         // stray blank line between records
-        if (r->line[0][0] != '@') { r->err = "FASTQ record " + std::to_string(r->n_records) + " does not start with '@'"; return PCL_ERR_INPUT; }
-        if (!r->getline(r->line[1]) || !r->getline(r->line[2]) || !r->getline(r->line[3])) {
-            r->err = "truncated FASTQ record " + std::to_string(r->n_records);
-            return PCL_ERR_INPUT;
+        if (!r->pending) {
+            if (!r->getline(r->line[0])) break;
+            if (r->line[0].empty()) continue;                     // stray blank line between records
+            if (r->line[0][0] != '@') { r->err = "FASTQ record " + std::to_string(r->n_records) + " does not start with '@'"; return PCL_ERR_INPUT; }
+            if (!r->getline(r->line[1]) || !r->getline(r->line[2]) || !r->getline(r->line[3])) {
+                r->err = "truncated FASTQ record " + std::to_string(r->n_records);
+                return PCL_ERR_INPUT;
+            }
         }
+        r->pending = false;
         if (r->line[2].empty() || r->line[2][0] != '+') { r->err = "FASTQ record " + std::to_string(r->n_records) + ": missing '+' line"; return PCL_ERR_INPUT; }
         const std::string &def = r->line[0], &s = r->line[1], &q = r->line[3];
         if (s.size() != q.size()) { r->err = "FASTQ record " + std::to_string(r->n_records) + ": sequence and quality lengths differ"; return PCL_ERR_INPUT; }
         const size_t L = s.size();
+        if (text && off && used + (def.size() - 1) + 2 * L > text_cap) {      // arena full: the record waits for the next call
+            r->text_full = true;
+            r->pending = true;
+            break;
+        }
         if (L > 65535) { r->err = "FASTQ record " + std::to_string(r->n_records) + ": sequences longer than 65535 bases are not supported"; return PCL_ERR_UNSUPPORTED; }
         len[n] = (uint16_t)L;
         if (seq && stride) {
@@ -269,11 +280,6 @@ int64_t pcl_fastq_read(pcl_fastq *r, uint64_t max_records, uint32_t stride, uint
             name_hash[n] = fnv1a(def.data() + 1, nl);
         }
         if (text && off) {
-            const uint64_t need = (def.size() - 1) + 2 * L;
-            if (used + need > text_cap) {                         // arena full: push the record back is not possible -> error
-                r->err = "text arena too small";
-                return PCL_ERR_NOMEM;
-            }
             // BatchedFqReader strips a trailing /1 or /2 from the NAME of every record before anything downstream sees
             // it (strip_fq_suffix, fastq.rs:421,612-621), so AnnotatedFastq and the make_fastq files carry the stripped
             // name; the description stays.
@@ -294,5 +300,9 @@ int64_t pcl_fastq_read(pcl_fastq *r, uint64_t max_records, uint32_t stride, uint
     if (n == 0 && !r->err.empty()) return PCL_ERR_INPUT;
     return (int64_t)n;
 }
+
+// 1 when the last pcl_fastq_read returned early because the text arena was full (the next record is still to come:
+// call again with a larger arena, `text_used` carried over, and the planes advanced by the records already delivered).
+int pcl_fastq_text_full(const pcl_fastq *r) { return r && r->text_full ? 1 : 0; }
 
 }  // extern "C"

@@ -58,15 +58,25 @@ class FastqReader:
         if keep_text:
             text = np.empty(n * text_bytes_per_record, np.uint8)
             off = np.zeros(3 * n + 1, np.uint64)
-        got = lib().pcl_fastq_read(self.h, n, stride, qoff, qstride, seq.ctypes.data if seq is not None else None,
-                                   qual.ctypes.data if qual is not None else None, length.ctypes.data, nh.ctypes.data,
-                                   text.ctypes.data if keep_text else None, len(text) if keep_text else 0,
-                                   off.ctypes.data if keep_text else None, C.byref(used))
-        if got < 0:
-            raise _ffi.PclError(int(got), lib().pcl_fastq_error(self.h).decode())
-        if got == 0:
+        # The arena is sized from `text_bytes_per_record`; records with long headers or untruncated long reads may
+        # outgrow it: pcl_fastq_read then stops in front of the record that does not fit, the arena is doubled and the
+        # same batch continues behind the records already delivered.
+        g = 0
+        at = lambda a, k: (a.ctypes.data + k * a.strides[0]) if a is not None else None
+        while True:
+            got = lib().pcl_fastq_read(self.h, n - g, stride, qoff, qstride, at(seq, g), at(qual, g), at(length, g), at(nh, g),
+                                       text.ctypes.data if keep_text else None, len(text) if keep_text else 0,
+                                       at(off, 3 * g) if keep_text else None, C.byref(used))
+            if got < 0:
+                raise _ffi.PclError(int(got), lib().pcl_fastq_error(self.h).decode())
+            g += int(got)
+            if not (keep_text and lib().pcl_fastq_text_full(self.h)):
+                break
+            bigger = np.empty(2 * len(text) + 4096, np.uint8)
+            bigger[:used.value] = text[:used.value]
+            text = bigger
+        if g == 0:
             return None
-        g = int(got)
         hb = HostBatch(None if seq is None else seq[:g], None if qual is None else qual[:g], length[:g])
         # (the arena is sized for the worst case: keep only what was written)
         return FastqBatch(hb, nh[:g], text[:used.value].copy() if keep_text else None, off[:3 * g + 1].copy() if keep_text else None)

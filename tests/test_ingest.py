@@ -69,6 +69,32 @@ def test_reads_every_format_and_concatenates(files):
     r.close()
 
 
+def test_text_arena_grows_when_records_outgrow_it(files):
+    """The arena is sized from an estimate (bytes per record); long headers / long reads outgrow it: the reader stops in
+    front of the record that does not fit, the arena is doubled and the same batch continues (pcl_fastq_text_full), on
+    the buffer route (plain LF records) and the line route (CRLF members) alike.  Batches keep their size."""
+    td, recs, paths = files
+    r = FastqReader(paths["all"])
+    got = 0
+    sizes = []
+    while True:
+        b = r.read(700, 32, keep_text=True, text_bytes_per_record=1, qual_window=(4, 16))     # 700 bytes for 700 records
+        if b is None:
+            break
+        sizes.append(len(b.batch.length))
+        for i in range(len(b.batch.length)):
+            d, s, q = recs[got + i]
+            nm, sep, desc = d.partition(b" ")
+            if len(nm) > 2 and nm[-2:] in (b"/1", b"/2"):
+                nm = nm[:-2]
+            assert b.record(i) == (nm + sep + desc, s, q)
+            assert b.batch.length[i] == len(s)
+            assert b.batch.seq[i].tobytes()[:min(len(s), 32)] == s[:32]
+        got += len(b.batch.length)
+    assert got == len(recs) and sizes == [700, 700, 700, 700, 200]
+    r.close()
+
+
 def test_group_reader_checks(files, tmp_path):
     td, recs, paths = files
     mates = [(d.replace(b"/1", b"/2"), s[::-1], q) for d, s, q in recs]
