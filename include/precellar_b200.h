@@ -367,6 +367,10 @@ void pcl_gzsrc_close(pcl_gzsrc *src);
 typedef struct pcl_group pcl_group;
 typedef struct { uint64_t n_records, n_assigned, n_ungroupable, n_barcodes, n_fragments; } pcl_group_info;
 int pcl_group_build(pcl_ctx *ctx, pcl_chunk *chunk, const uint64_t *fingerprint, pcl_group **out);
+/* The same over several chunks of one ctx (a run that did not fit one chunk): read group i of chunks[k] is record
+ * (n_0 + ... + n_{k-1}) + i of the grouping, `fingerprint` (or NULL) holds one word per record in that order, and
+ * `order` refers to those record numbers.  Fewer than 2^32 - 1 read groups in total. */
+int pcl_group_build_multi(pcl_ctx *ctx, pcl_chunk *const *chunks, int n_chunks, const uint64_t *fingerprint, pcl_group **out);
 int pcl_group_info_get(const pcl_group *g, pcl_group_info *out);
 int pcl_group_fetch(pcl_group *g, uint32_t *order, uint32_t *frag_start, uint32_t *bc_frag_start, uint64_t *bc_key);
 int pcl_group_key_decode(uint64_t key, char *out32);

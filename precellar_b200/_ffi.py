@@ -88,7 +88,7 @@ SYMBOLS = [
     "pcl_chunk_upload_compact", "pcl_read_payload_bytes",
     "pcl_gzsrc_open", "pcl_gzsrc_read", "pcl_gzsrc_is_bgzf", "pcl_gzsrc_error", "pcl_gzsrc_close",
     "pcl_counts_freeze", "pcl_chunk_bytes", "pcl_mem_info", "pcl_verify_enable", "pcl_chunk_set_uniform_len", "pcl_chunk_uniform_results_async",
-    "pcl_group_build", "pcl_group_info_get", "pcl_group_fetch", "pcl_group_key_decode", "pcl_group_destroy",
+    "pcl_group_build", "pcl_group_build_multi", "pcl_group_info_get", "pcl_group_fetch", "pcl_group_key_decode", "pcl_group_destroy",
 ]
 
 _lib = None
@@ -165,6 +165,7 @@ def lib() -> C.CDLL:
         "pcl_chunk_set_uniform_len": (i32, [vp, i32, C.c_uint16]),
         "pcl_chunk_uniform_results_async": (i32, [vp, i32, vp]),
         "pcl_group_build": (i32, [vp, vp, vp, C.POINTER(vp)]),
+        "pcl_group_build_multi": (i32, [vp, C.POINTER(vp), i32, vp, C.POINTER(vp)]),
         "pcl_group_info_get": (i32, [vp, C.POINTER(GroupInfo)]),
         "pcl_group_fetch": (i32, [vp, vp, vp, vp, vp]),
         "pcl_group_key_decode": (i32, [u64, C.c_char_p]),

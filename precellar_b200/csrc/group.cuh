@@ -175,7 +175,7 @@ struct GroupSeg {
 struct GroupKeyParams {
     GroupSeg seg[PCL_GROUP_MAX_SEG];
     uint32_t n_seg;
-    uint32_t pad0;
+    uint32_t perm_base;           // record i of this chunk is read group perm_base + i of the grouping (several chunks: pcl_group_build_multi)
     // UMI: the raw bytes of one segment of one read file
     const uint8_t *useq;          // NULL: no UMI
     const uint16_t *ulen;
@@ -255,7 +255,7 @@ __global__ void __launch_bounds__(256) k_group_keys(const __grid_constant__ Grou
         }
         p.bc_key[i] = bk;
         p.umi_key[i] = ok ? uk : 0ull;
-        p.perm[i] = (uint32_t)i;
+        p.perm[i] = p.perm_base + (uint32_t)i;
         if (ok) { ++n_assigned; or_bc |= bk; or_umi |= uk; }
     }
     for (int o = 16; o > 0; o >>= 1) {

@@ -1675,14 +1675,8 @@ uint32_t bytes_used(unsigned long long or_of_keys) {
 
 extern "C" {
 
-int pcl_group_build(pcl_ctx *ctx, pcl_chunk *c, const uint64_t *fingerprint, pcl_group **out) {
-    if (!out) return PCL_ERR_ARG;
-    *out = nullptr;
-    if (int r = check_ready(ctx, c)) return r;
-    if (int r = bind(ctx)) return r;
-    const uint64_t n = c->n;
-    if (n >= (1ull << 32) - 1) return fail(ctx, PCL_ERR_ARG, "chunk too large for 32-bit record indices");
-    GroupKeyParams p;
+// Key parameters of one chunk (which planes hold the barcode keys / statuses / UMI bytes); outputs are set by the caller.
+static int group_key_params(pcl_ctx *ctx, pcl_chunk *c, GroupKeyParams &p) {
     memset(&p, 0, sizeof p);
     int umi_read = -1;
     for (int r = 0; r < ctx->n_reads; ++r) {
@@ -1717,12 +1711,34 @@ int pcl_group_build(pcl_ctx *ctx, pcl_chunk *c, const uint64_t *fingerprint, pcl
         p.ustart = inf.static_start[inf.umi_elem[ju]]; p.ubases = el.max_len; p.umin = el.min_len;
         if (p.ustart + p.ubases > d.stride && inf.fixed_layout) return fail(ctx, PCL_ERR_UNSUPPORTED, "UMI outside the uploaded record bytes");
     }
-    p.n = n;
+    p.n = c->n;
+    return PCL_OK;
+}
+
+int pcl_group_build(pcl_ctx *ctx, pcl_chunk *c, const uint64_t *fingerprint, pcl_group **out) {
+    return pcl_group_build_multi(ctx, &c, 1, fingerprint, out);
+}
+
+int pcl_group_build_multi(pcl_ctx *ctx, pcl_chunk *const *chunks, int n_chunks, const uint64_t *fingerprint, pcl_group **out) {
+    if (!out) return PCL_ERR_ARG;
+    *out = nullptr;
+    if (!ctx || !chunks || n_chunks < 1) return PCL_ERR_ARG;
+    uint64_t n = 0;
+    std::vector<GroupKeyParams> kp((size_t)n_chunks);
+    for (int k = 0; k < n_chunks; ++k) {
+        if (int r = check_ready(ctx, chunks[k])) return r;
+        for (int q = 0; q < k; ++q) if (chunks[q] == chunks[k]) return fail(ctx, PCL_ERR_ARG, "chunk %d is listed twice", k);
+        if (int r = group_key_params(ctx, chunks[k], kp[(size_t)k])) return r;
+        n += chunks[k]->n;
+    }
+    if (int r = bind(ctx)) return r;
+    if (n >= (1ull << 32) - 1) return fail(ctx, PCL_ERR_ARG, "too many read groups for 32-bit record indices");
+    const bool has_umi = kp[0].useq != nullptr;
 
     pcl_group *g = new pcl_group();
     g->ctx = ctx;
     g->info.n_records = n;
-    cudaStream_t s = c->stream;
+    cudaStream_t s = chunks[0]->stream;
     int rc = PCL_OK;
     auto A = [&](void **ptr, size_t bytes) {
         if (rc != PCL_OK) return;
@@ -1743,11 +1759,21 @@ int pcl_group_build(pcl_ctx *ctx, pcl_chunk *c, const uint64_t *fingerprint, pcl
 #define GCU(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return cleanup(fail(ctx, PCL_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(e_))); } while (0)
     GCU(cudaMemsetAsync(d_stats, 0, 64, s));
     if (fingerprint) GCU(cudaMemcpyAsync(d_fp, fingerprint, n * 8, cudaMemcpyHostToDevice, s));
-    p.bc_key = d_bc; p.umi_key = d_umi; p.perm = pA; p.stats = d_stats;
     unsigned long long st[8] = {0};
     if (n) {
-        k_group_keys<<<grid_for(ctx, n, 8), 256, 0, s>>>(p);
-        ctx->launches += 1;
+        // the chunks' planes are final once their own streams have drained up to here; the grouping runs on chunk 0's
+        uint64_t base = 0;
+        for (int k = 0; k < n_chunks; ++k) {
+            pcl_chunk *ck = chunks[k];
+            if (k > 0) { GCU(cudaEventRecord(ck->ev, ck->stream)); GCU(cudaStreamWaitEvent(s, ck->ev, 0)); }
+            GroupKeyParams &p = kp[(size_t)k];
+            p.bc_key = d_bc + base; p.umi_key = d_umi + base; p.perm = pA + base; p.perm_base = (uint32_t)base; p.stats = d_stats;
+            if (p.n) {
+                k_group_keys<<<grid_for(ctx, p.n, 8), 256, 0, s>>>(p);
+                ctx->launches += 1;
+            }
+            base += p.n;
+        }
         GCU(cudaGetLastError());
         GCU(cudaMemcpyAsync(st, d_stats, 64, cudaMemcpyDeviceToHost, s));
         GCU(cudaStreamSynchronize(s));
@@ -1756,7 +1782,7 @@ int pcl_group_build(pcl_ctx *ctx, pcl_chunk *c, const uint64_t *fingerprint, pcl
     g->info.n_ungroupable = st[1];
     // three stable sorts, least significant key first: UMI, fingerprint, barcode
     if (n) {
-        if (p.useq && st[3]) {
+        if (has_umi && st[3]) {
             k_group_gather<<<grid_for(ctx, n, 8), 256, 0, s>>>(d_umi, pA, kA, n, nullptr);
             ctx->launches += 1;
             if (int r2 = device_radix_sort(ctx, s, &kA, &pA, &kB, &pB, n, bytes_used(st[3]), hist, scan_tmp, d_stats + 4)) return cleanup(r2);

@@ -378,17 +378,20 @@ class BarcodePipeline:
         return out
 
     # -- downstream grouping ---------------------------------------------------------------------------
-    def group(self, chunk: Chunk, fingerprint: Optional[np.ndarray] = None) -> "GroupResult":
-        """Sort the chunk's assigned read groups by (barcode, fingerprint, UMI) on the device and mark the duplicate
-        sets: sort_by_barcode + chunk_by(barcode) + remove_duplicates of the reference (precellar/src/fragment/mod.rs:
-        359-363,434-455, fragment/dedups.rs:320-340).  ``fingerprint``: one uint64 per read group with the aligner's
-        part of the FingerPrint (reference id, 5' coordinates, orientation), or None."""
+    def group(self, chunk, fingerprint: Optional[np.ndarray] = None) -> "GroupResult":
+        """Sort the assigned read groups of a chunk - or of a list of chunks, numbered one after the other - by (barcode,
+        fingerprint, UMI) on the device and mark the duplicate sets: sort_by_barcode + chunk_by(barcode) +
+        remove_duplicates of the reference (precellar/src/fragment/mod.rs:359-363,434-455, fragment/dedups.rs:320-340).
+        ``fingerprint``: one uint64 per read group with the aligner's part of the FingerPrint (reference id, 5'
+        coordinates, orientation), or None."""
+        chunks = list(chunk) if isinstance(chunk, (list, tuple)) else [chunk]
         fp = None
         if fingerprint is not None:
             fp = np.ascontiguousarray(fingerprint, dtype=np.uint64)
-            assert len(fp) == chunk.n
+            assert len(fp) == sum(c.n for c in chunks)
         h = C.c_void_p()
-        check(self.ctx, lib().pcl_group_build(self.ctx, chunk.h, fp.ctypes.data if fp is not None else None, C.byref(h)))
+        arr = (C.c_void_p * len(chunks))(*[c.h for c in chunks])
+        check(self.ctx, lib().pcl_group_build_multi(self.ctx, arr, len(chunks), fp.ctypes.data if fp is not None else None, C.byref(h)))
         try:
             info = _ffi.GroupInfo()
             check(self.ctx, lib().pcl_group_info_get(h, C.byref(info)))

@@ -106,6 +106,47 @@ def test_grouping_matches_the_reference_semantics(name, use_fp):
         assert n_dup > 50                                       # the data must contain real duplicate sets
 
 
+@pytest.mark.parametrize("name", ["v3", "sci3"])
+def test_grouping_over_several_chunks_equals_one_chunk(name):
+    """pcl_group_build_multi: a run split over three chunks (one of them empty) groups like the same records in one
+    chunk - same order, fragments, barcodes - and like the reference restatement."""
+    from precellar_b200.pipeline import BarcodePipeline, HostBatch
+    layout = _layouts(np.random.default_rng(20240607))[name]
+    rng = np.random.default_rng(U.seed_of(name, "group-multi"))
+    infos, strides = U.emul_infos(layout)
+    n = 20_000
+    multi = len(layout.region_ids) > 1
+    full = U.gen_reads(rng, layout, n, strides, p_short=0.0 if multi else 0.02, p_tiny=0.02 if multi else 0.0, hot=30)
+    fps = rng.integers(0, 4, n).astype(np.uint64)
+    dev = U.narrow(full, strides, infos)
+    cut = [0, 7000, 7000, 15500, n]                                        # chunk 1 is empty
+    sl = lambda b, lo, hi: HostBatch(None if b.seq is None else b.seq[lo:hi], None if b.qual is None else b.qual[lo:hi], b.length[lo:hi])
+    pipe = BarcodePipeline(layout)
+    try:
+        chunks = []
+        for lo, hi in zip(cut[:-1], cut[1:]):
+            ch = pipe.new_chunk(max(hi - lo, 1))
+            ch.reset(hi - lo)
+            for r, b in enumerate(dev):
+                ch.upload(r, sl(b, lo, hi))
+            pipe.count(ch)
+            chunks.append(ch)
+        pipe.allreduce()
+        for ch in chunks:
+            pipe.correct(ch, 0.9)
+        g = pipe.group(chunks, fingerprint=fps)
+        with pytest.raises(_ffi.PclError):
+            pipe.group([chunks[0], chunks[0]])
+    finally:
+        pipe.close()
+    one = _run(layout, full, fps)
+    assert g.n_records == n and g.n_assigned == one.n_assigned and g.n_ungroupable == one.n_ungroupable
+    for a, b in ((g.order, one.order), (g.frag_start, one.frag_start), (g.bc_frag_start, one.bc_frag_start), (g.bc_key, one.bc_key)):
+        np.testing.assert_array_equal(a, b)
+    bcs, umis = _expected(layout, full, True, 0.9)
+    _check(g, bcs, umis, fps)
+
+
 def test_grouping_without_correction_and_empty_input():
     """Without pcl_correct only the exact whitelist members are assigned (a raw barcode outside the whitelist may hold
     non-ACGT bytes, which the packed keys do not keep); an empty chunk gives empty outputs."""
