@@ -79,7 +79,8 @@ struct Table {
     uint32_t *d_index_to_slot = nullptr;
     uint32_t *d_nkeys[4] = {nullptr, nullptr, nullptr, nullptr};
     uint32_t *d_nbits = nullptr;               // 4 x PCL_NBITS_WORDS: bitmaps of the partial keys (DTable::nbits)
-    uint32_t *d_dense = nullptr;               // n_entries counts in whitelist order: what the all-reduce sends
+    uint32_t *d_dense = nullptr;               // n_entries counts of the occupied slots: what the all-reduce sends
+    uint32_t *d_order_slots = nullptr;         // the occupied slots, (nearly) ascending: the order of d_dense, the same on every rank
     uint32_t *d_scratch_counts = nullptr;      // pcl_counts_freeze: where a re-run of pass 1 puts its (discarded) increments
     unsigned long long *d_scratch_scalars = nullptr;
     unsigned long long *d_scalars = nullptr;   // [0] total, [1] mismatch
@@ -142,6 +143,12 @@ struct pcl_ctx {
     bool no_neighbour_tables = false;   // PCL_NO_NEIGHBOUR_TABLES=1: 3*L direct probes instead of the 4 neighbourhood tables
     uint64_t device_build_min = 100000; // whitelists from this many entries on are deduplicated and hashed on the device (PCL_DEVICE_BUILD_MIN)
     bool reduce_after_filter = false;   // PCL_REDUCE_AFTER_FILTER=1: the all-reduce waits for k_filter instead of overlapping it (experiments)
+    // PCL_TIMELINE=1 (diagnostic): events at the hand-over points of a step; pcl_correct prints their offsets to stderr
+    bool timeline = false;
+    cudaEvent_t tl[12] = {};
+    bool tl_set[12] = {};
+    int filter_waves = 16;              // PCL_FILTER_WAVES: resident waves of k_filter (see launch_filter)
+    bool reduce_slots = false;          // PCL_REDUCE_SLOTS=1: all-reduce the whole slot array instead of the occupied slots
     bool no_plan_geo = false;           // PCL_NO_PLAN_GEO=1: AnchorPlan layouts always run the run-time geometry (tests compare the two)
     bool no_nbits = false;              // PCL_NO_NBITS=1: no partial-key bitmaps in front of the neighbourhood tables
 };
@@ -287,6 +294,9 @@ int pcl_ctx_create(pcl_ctx **out, int device) {
     { const char *g = getenv("PCL_NO_NEIGHBOUR_TABLES"); ctx->no_neighbour_tables = g && g[0] == '1'; }
     { const char *g = getenv("PCL_NO_NBITS"); ctx->no_nbits = g && g[0] == '1'; }
     { const char *g = getenv("PCL_NO_PLAN_GEO"); ctx->no_plan_geo = g && g[0] == '1'; }
+    { const char *g = getenv("PCL_TIMELINE"); ctx->timeline = g && g[0] == '1'; }
+    { const char *g = getenv("PCL_REDUCE_SLOTS"); ctx->reduce_slots = g && g[0] == '1'; }
+    { const char *g = getenv("PCL_FILTER_WAVES"); if (g && atoi(g) > 0) ctx->filter_waves = atoi(g); }
     { const char *g = getenv("PCL_REDUCE_AFTER_FILTER"); ctx->reduce_after_filter = g && g[0] == '1'; }
     { const char *g = getenv("PCL_DEVICE_BUILD_MIN"); if (g) ctx->device_build_min = strtoull(g, nullptr, 10); }
     memset(ctx->descs, 0, sizeof ctx->descs);
@@ -375,6 +385,7 @@ static void table_free(Table &t) {
     for (int q = 0; q < 4; ++q) if (t.d_nkeys[q]) cudaFree(t.d_nkeys[q]);
     if (t.d_nbits) cudaFree(t.d_nbits);
     if (t.d_dense) cudaFree(t.d_dense);
+    if (t.d_order_slots) cudaFree(t.d_order_slots);
     if (t.d_scratch_counts) cudaFree(t.d_scratch_counts);
     if (t.d_scratch_scalars) cudaFree(t.d_scratch_scalars);
     if (t.d_scalars) cudaFree(t.d_scalars);
@@ -543,16 +554,24 @@ static int whitelist_load_device(pcl_ctx *ctx, int region_slot, const uint8_t *b
     if (n_slots >= (1ull << 29)) return done(fail(ctx, PCL_ERR_UNSUPPORTED, "whitelist too large (%llu entries)", m));
     auto P = [&](void **p, size_t b) { return cudaMalloc(p, b ? b : 16); };     // persistent allocations: freed by table_free
     TCU(P(&t.d_keys, n_slots * 4)); TCU(P((void **)&t.d_counts, n_slots * 4)); TCU(P((void **)&t.d_index_to_slot, m * 4));
-    TCU(P((void **)&t.d_scalars, 16)); TCU(P((void **)&t.d_dense, (m + 1) * 4));
+    TCU(P((void **)&t.d_scalars, 16)); TCU(P((void **)&t.d_dense, (m + 1) * 4)); TCU(P((void **)&t.d_order_slots, (m + 1) * 4));
     for (int q = 0; q < 4; ++q) TCU(P((void **)&t.d_nkeys[q], n_slots * 4));
     const int gfill = grid_for(ctx, n_slots, 8), gins = grid_for(ctx, m, 8);
     k_fill_u32<<<gfill, 256, 0, s>>>((uint32_t *)t.d_keys, n_slots, empty);
-    k_wl_insert<true><<<gins, 256, 0, s>>>(dense, m, (uint32_t *)t.d_keys, (uint32_t)n_buckets, empty, 0u, t.d_index_to_slot);
+    {   // main table: placement by rank inside the home bucket (every rank builds the same slots; see tablebuild.cuh)
+        k_wl_home<<<gins, 256, 0, s>>>(dense, m, (uint32_t)n_buckets, kA, iA);
+        if (int rc = device_radix_sort(ctx, s, &kA, &iA, &kB, &iB, m, 0x0Fu, hist, scan_tmp, d_tot)) return done(rc);
+        k_wl_place<<<gins, 256, 0, s>>>(kA, iA, dense, m, (uint32_t *)t.d_keys, t.d_index_to_slot, t.d_order_slots, flag);
+        if (int rc = device_scan(ctx, s, flag, pos, m, scan_tmp, d_tot)) return done(rc);
+        k_wl_overflow_list<<<gins, 256, 0, s>>>(flag, pos, m, iB);
+        k_wl_overflow<<<1, 32, 0, s>>>(kA, iA, dense, iB, d_tot, (uint32_t *)t.d_keys, (uint32_t)n_buckets, empty, t.d_index_to_slot, t.d_order_slots);
+        ctx->launches += 4;
+    }
     for (uint32_t q = 0; q < 4; ++q) {
         k_fill_u32<<<gfill, 256, 0, s>>>(t.d_nkeys[q], n_slots, empty);
         k_wl_insert<false><<<gins, 256, 0, s>>>(dense, m, t.d_nkeys[q], (uint32_t)n_buckets, empty, q, nullptr);
     }
-    ctx->launches += 12;
+    ctx->launches += 11;
     TCU(cudaMemsetAsync(t.d_counts, 0, n_slots * 4, s));
     TCU(cudaMemsetAsync(t.d_scalars, 0, 16, s));
     for (int q = 0; q < 4; ++q) { t.d.nkeys[q] = t.d_nkeys[q]; t.d.nbits[q] = nullptr; }
@@ -626,6 +645,12 @@ int pcl_whitelist_load(pcl_ctx *ctx, int region_slot, const uint8_t *bytes, cons
     t.n_entries = m;
     t.n_slots = n_slots;
     CU(ctx, cudaMalloc(&t.d_dense, (m + 1) * sizeof(uint32_t)));
+    {   // the occupied slots in ascending order: the order the all-reduce sends the counts in
+        std::vector<uint32_t> os(ht.index_to_slot);
+        std::sort(os.begin(), os.end());
+        CU(ctx, cudaMalloc(&t.d_order_slots, (m + 1) * sizeof(uint32_t)));
+        CU(ctx, cudaMemcpy(t.d_order_slots, os.data(), m * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    }
     t.loaded = true;
     // the uploads above come from pageable memory and the memsets may be asynchronous: nothing else orders them against
     // the (non-blocking) chunk streams
@@ -1058,13 +1083,37 @@ static int worklist_grid(const pcl_ctx *ctx, const pcl_chunk *c, int n_bc, bool 
     return grid_for(ctx, all_entries ? c->n * n_bc : (c->n * n_bc + 3) / 4 + 4096, occ);
 }
 
+enum { TL_COUNT_BEGIN = 0, TL_COUNTED, TL_FILTER_END, TL_COUNT_END, TL_REDUCE_BEGIN, TL_GATHERED, TL_ALLREDUCED, TL_REDUCED, TL_RESOLVE_BEGIN,
+       TL_RESOLVE_END, TL_N };
+static void tl_mark(pcl_ctx *ctx, int k, cudaStream_t s) {
+    if (!ctx->timeline) return;
+    if (!ctx->tl[k]) cudaEventCreate(&ctx->tl[k]);
+    cudaEventRecord(ctx->tl[k], s);
+    ctx->tl_set[k] = true;
+}
+static void tl_print(pcl_ctx *ctx) {
+    if (!ctx->timeline || !ctx->tl_set[TL_COUNT_BEGIN]) return;
+    static const char *names[TL_N] = {"count_begin", "counted", "filter_end", "count_end", "reduce_begin", "gathered", "allreduced", "reduced",
+                                      "resolve_begin", "resolve_end"};
+    cudaDeviceSynchronize();
+    fprintf(stderr, "[pcl timeline rank %d]", ctx->rank);
+    for (int k = 0; k < TL_N; ++k) {
+        float ms = 0;
+        if (ctx->tl_set[k] && cudaEventElapsedTime(&ms, ctx->tl[TL_COUNT_BEGIN], ctx->tl[k]) == cudaSuccess) fprintf(stderr, " %s=%.3f", names[k], ms);
+        ctx->tl_set[k] = false;
+    }
+    fprintf(stderr, "\n");
+}
+
 static int launch_filter(pcl_ctx *ctx, pcl_chunk *c, int r) {
     CorrectParams p;
     correct_params(ctx, c, r, p);
     prof_begin(ctx, c->stream, PCL_K_FILTER);
-    // four waves instead of one resident wave: the first CTAs retire a quarter of the way in and make room for the
-    // all-reduce kernel that waits on the ctx stream (on one GPU the difference is not measurable)
-    k_filter<<<worklist_grid(ctx, c, ctx->infos[r].n_bc, false, 4 * ctx->occ[OCC_FILTER]), PCL_BLOCK, 0, c->stream>>>(p);
+    // Sixteen short waves instead of one resident wave: CTA slots free up every ~70 us, so the gather / all-reduce /
+    // scatter kernels waiting on the (high-priority) ctx stream start at once instead of a quarter of the kernel later.
+    // Measured, v3, 125 M pairs per GPU: step at N=2 3.59 ms (4 waves) / 3.54 (8) / 3.49 (16) / 3.50 (32) / 3.52 (64);
+    // at N=1 3.47 (4) / 3.44 (16).
+    k_filter<<<worklist_grid(ctx, c, ctx->infos[r].n_bc, false, ctx->filter_waves * ctx->occ[OCC_FILTER]), PCL_BLOCK, 0, c->stream>>>(p);
     prof_end(ctx, c->stream);
     CU(ctx, cudaGetLastError());
     c->rb[r].filtered = true;
@@ -1106,6 +1155,7 @@ int pcl_count(pcl_ctx *ctx, pcl_chunk *c) {
     n_with_bc = n_order;
     for (int r = 0; r < ctx->n_reads; ++r) if (!ctx->infos[r].n_bc) order[n_order++] = r;
     if (n_with_bc == 0) { CU(ctx, cudaEventRecord(c->ev_counted, c->stream)); c->counted = true; }
+    tl_mark(ctx, TL_COUNT_BEGIN, c->stream);
     for (int oi = 0; oi < n_order; ++oi) {
         const int r = order[oi];
         const pcl_read_info &inf = ctx->infos[r];
@@ -1197,14 +1247,17 @@ int pcl_count(pcl_ctx *ctx, pcl_chunk *c) {
         if (!ctx->frozen) ctx->qc_reads[r] += c->n;
         if (oi + 1 == n_with_bc) {
             if (!ctx->reduce_after_filter) { CU(ctx, cudaEventRecord(c->ev_counted, c->stream)); c->counted = true; }
+            tl_mark(ctx, TL_COUNTED, c->stream);
             // The neighbourhood filter of pass 2 needs no counts: it runs here, behind the event the all-reduce waits for,
             // so on several GPUs the exchange of the counts is hidden under it.
             for (int k = 0; k < n_with_bc; ++k)
                 if (read_all32(ctx, order[k]) && c->rb[order[k]].wl_key)
                     if (int rc = launch_filter(ctx, c, order[k])) return rc;
             if (ctx->reduce_after_filter) { CU(ctx, cudaEventRecord(c->ev_counted, c->stream)); c->counted = true; }
+            tl_mark(ctx, TL_FILTER_END, c->stream);
         }
     }
+    tl_mark(ctx, TL_COUNT_END, c->stream);
     return PCL_OK;
 }
 
@@ -1264,34 +1317,45 @@ int pcl_counts_allreduce(pcl_ctx *ctx) {
             CU(ctx, cudaStreamWaitEvent(ctx->stream, c->ev, 0));
         }
     }
+    tl_mark(ctx, TL_REDUCE_BEGIN, ctx->stream);
     if (ctx->nranks > 1) {
         if (!ctx->comm) return fail(ctx, PCL_ERR_NCCL, "communicator not initialised");
         if (ctx->reduced) return fail(ctx, PCL_ERR_ARG, "the counts were already summed over the ranks (pcl_counts_reset starts a new round)");
         NcclApi &n = nccl();
-        // The counts travel in whitelist order (n_entries words instead of n_slots: a third of the bytes at the table's load
-        // factor), because ranks that built their tables on the device do not agree on slots.
-        for (Table &t : ctx->tables) {
-            if (!t.loaded || !t.n_entries) continue;
-            k_counts_gather32<<<grid_for(ctx, t.n_entries, 8), 256, 0, ctx->stream>>>(t.d_counts, t.d_index_to_slot, t.d_dense, t.n_entries);
-            ctx->launches += 1;
-        }
+        // Every rank builds the same table, slot for slot (host build: sequential; device build: placement by rank,
+        // tablebuild.cuh), so the counts may travel in any order the ranks agree on.  Default: the n_entries occupied
+        // slots in ascending slot order (a third of the bytes of the slot array at the table's load factor; gather and
+        // scatter stream through the counts).  PCL_REDUCE_SLOTS=1: the whole slot array, no kernels around the collective.
+        const bool by_slot = ctx->reduce_slots;
+        if (!by_slot)
+            for (Table &t : ctx->tables) {
+                if (!t.loaded || !t.n_entries) continue;
+                k_counts_gather32<<<grid_for(ctx, t.n_entries, 4), 256, 0, ctx->stream>>>(t.d_counts, t.d_order_slots, t.d_dense, t.n_entries);
+                ctx->launches += 1;
+            }
+        tl_mark(ctx, TL_GATHERED, ctx->stream);
         n.GroupStart();
         for (Table &t : ctx->tables) {
             if (!t.loaded) continue;
-            int r1 = t.n_entries ? n.AllReduce(t.d_dense, t.d_dense, t.n_entries, kNcclUint32, kNcclSum, ctx->comm, ctx->stream) : 0;
+            int r1 = 0;
+            if (t.n_entries) r1 = by_slot ? n.AllReduce(t.d_counts, t.d_counts, t.n_slots, kNcclUint32, kNcclSum, ctx->comm, ctx->stream)
+                                          : n.AllReduce(t.d_dense, t.d_dense, t.n_entries, kNcclUint32, kNcclSum, ctx->comm, ctx->stream);
             int r2 = n.AllReduce(t.d_scalars, t.d_scalars, 2, kNcclUint64, kNcclSum, ctx->comm, ctx->stream);
             if (r1 || r2) { n.GroupEnd(); return fail(ctx, PCL_ERR_NCCL, "ncclAllReduce failed (%d,%d)", r1, r2); }
         }
         int r = n.GroupEnd();
         if (r) return fail(ctx, PCL_ERR_NCCL, "ncclGroupEnd: %d", r);
-        for (Table &t : ctx->tables) {
-            if (!t.loaded || !t.n_entries) continue;
-            k_counts_scatter32<<<grid_for(ctx, t.n_entries, 8), 256, 0, ctx->stream>>>(t.d_counts, t.d_index_to_slot, t.d_dense, t.n_entries);
-            ctx->launches += 1;
-        }
+        tl_mark(ctx, TL_ALLREDUCED, ctx->stream);
+        if (!by_slot)
+            for (Table &t : ctx->tables) {
+                if (!t.loaded || !t.n_entries) continue;
+                k_counts_scatter32<<<grid_for(ctx, t.n_entries, 4), 256, 0, ctx->stream>>>(t.d_counts, t.d_order_slots, t.d_dense, t.n_entries);
+                ctx->launches += 1;
+            }
         CU(ctx, cudaGetLastError());
     }
     ctx->reduced = true;
+    tl_mark(ctx, TL_REDUCED, ctx->stream);
     // ... and every chunk's later work waits for the reduced counts
     CU(ctx, cudaEventRecord(ctx->ev_reduced, ctx->stream));
     for (pcl_chunk *c : ctx->chunks) CU(ctx, cudaStreamWaitEvent(c->stream, ctx->ev_reduced, 0));
@@ -1322,6 +1386,7 @@ int pcl_correct(pcl_ctx *ctx, pcl_chunk *c, double threshold, double max_expecte
         const bool all32 = !check_ee && read_all32(ctx, r) && b.wl_key;
         if (all32) {
             if (!b.filtered) if (int rc = launch_filter(ctx, c, r)) return rc;
+            tl_mark(ctx, TL_RESOLVE_BEGIN, c->stream);
             prof_begin(ctx, c->stream, PCL_K_CORRECT);
             k_resolve<<<worklist_grid(ctx, c, inf.n_bc, false, ctx->occ[OCC_RESOLVE]), PCL_BLOCK, 0, c->stream>>>(p);
         } else {
@@ -1331,6 +1396,8 @@ int pcl_correct(pcl_ctx *ctx, pcl_chunk *c, double threshold, double max_expecte
         prof_end(ctx, c->stream);
         CU(ctx, cudaGetLastError());
     }
+    tl_mark(ctx, TL_RESOLVE_END, c->stream);
+    tl_print(ctx);
     return PCL_OK;
 }
 
