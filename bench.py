@@ -331,9 +331,12 @@ def kernel_table(pipe, w, n, prof, steps, mis_per_region, peak, traffic_key):
         gbs = kv["alg_bytes"] / (kv["ms"] / 1e3) / 1e9
         units = n if kv["per"] == "read group" else n_miss
         tb = tr.get(name)
+        traffic = (float(tb) * units) if tb is not None else None
         out[name] = {"ms_per_launch": kv["ms"], "alg_bytes_per_launch": kv["alg_bytes"], "alg_bytes_per_unit": kv["unit_bytes"],
-                     "unit": kv["per"], "achieved_gbs": gbs, "frac": gbs / peak,
-                     "traffic": (float(tb) * units) if tb is not None else None}
+                     "unit": kv["per"], "achieved_gbs": gbs, "frac": gbs / peak, "traffic": traffic,
+                     # the same fraction on the DRAM bytes ncu counted: what the memory system really moved per second
+                     # (below `frac` where table sectors hit in L2, above it where sectors are fetched more than once)
+                     "frac_traffic": (traffic / (kv["ms"] / 1e3) / 1e9 / peak) if traffic is not None else None}
     return out
 
 
