@@ -992,20 +992,27 @@ __global__ void __launch_bounds__(PCL_BLOCK) k_correct(const __grid_constant__ C
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ unsigned long long pcl_ld_stream64(const unsigned long long *p) { return __ldcs(p); }
 
-// k_filter works in two phases per warp and 32 entries, because under divergence every lane of a warp pays for what
-// any lane does and only ~1.5 of the 4 neighbourhood tables of an entry are worth a look:
-//   A. lane per entry: decode (re-derive a barcode with non-ACGT bytes from its record), four bitmap words, and the
-//      (entry, table) pairs that survive go into a queue in shared memory;
-//   B. lane per queued pair, all lanes busy: one bucket of the pair's table; a chain that continues in the next bucket
-//      is queued again; results are OR-ed into the entry's mask in shared memory.
-#define PCL_FQ_CAP 192u      // 128 pairs of a round + room for continued chains
+// k_filter works in two phases per warp, because under divergence every lane of a warp pays for what any lane does and
+// only ~1.6 of the 4 neighbourhood tables of an entry are worth a look:
+//   A. lane per entry (32 entries per iteration): decode (re-derive a barcode with non-ACGT bytes from its record), four
+//      bitmap words; the (entry, table) pairs that survive go into a ring queue in shared memory and the entry's mask
+//      starts as 0 (or the direct result) in wl_cand;
+//   B. lane per queued pair, ALL 32 lanes busy: rounds run only while the queue holds 32 pairs -- what is left over waits
+//      for the pairs of the next iteration (and is drained after the last one).  One bucket of the pair's table per round;
+//      a chain that continues in the next bucket goes back to the tail of the queue.  Candidates are OR-ed into the
+//      entry's mask in wl_cand (a pair may be served one iteration after its entry was read).
+// Before the carry-over, an iteration ran 2.85 rounds at 18 active lanes (32 + 19 pairs, then the few continued chains);
+// now it runs 1.65 full ones (764 M -> 651 M warp instructions per 21.5 M entries).  The kernel is bound by memory latency
+// (ncu: long-scoreboard stalls, issue slots 55 % busy), hence the loads of the next iteration's entries ahead of time and
+// the L2 prefetch of the records its REPACK entries will need: 1.05 -> 0.99 ms.  Five CTAs per SM (48 registers); at six
+// (40 registers) the spills cost more than the occupancy gives (1.59 ms).
+#define PCL_FQ_CAP 256u      // ring: < 32 left over + <= 128 new pairs + <= 32 continued chains of a round
 struct FilterQueue {
-    uint32_t key[PCL_FQ_CAP], meta[PCL_FQ_CAP], bucket[PCL_FQ_CAP];
-    unsigned long long res[32];
+    uint32_t key[PCL_FQ_CAP], meta[PCL_FQ_CAP], bucket[PCL_FQ_CAP], widx[PCL_FQ_CAP];
     uint32_t tail;
 };
-// meta: lane | q << 5 | len << 7 | has_n << 12 | n_p2 << 13 | j << 16 | continued << 18
-__global__ void __launch_bounds__(PCL_BLOCK) k_filter(const __grid_constant__ CorrectParams p) {
+// meta: q << 5 | len << 7 | has_n << 12 | n_p2 << 13 | j << 16 | continued << 18;  widx: low 32 bits of the worklist index
+__global__ void __launch_bounds__(PCL_BLOCK, 5) k_filter(const __grid_constant__ CorrectParams p) {
     __shared__ FilterQueue fq[PCL_BLOCK / 32];
     FilterQueue &Q = fq[threadIdx.x >> 5];
     const unsigned long long n_work = *p.wl_count;
@@ -1013,12 +1020,53 @@ __global__ void __launch_bounds__(PCL_BLOCK) k_filter(const __grid_constant__ Co
     const bool rev = rd.is_reverse != 0;
     const uint32_t lane = threadIdx.x & 31u, lt = (1u << lane) - 1u;
     const uint64_t step = (uint64_t)gridDim.x * blockDim.x;
+    uint32_t head = 0, total = 0;                                   // ring positions (monotonic; masked on access)
+    if (lane == 0) Q.tail = 0;
+    __syncwarp();
+    uint64_t wb_last = 0;
+
+    // one round: the pairs at ring positions [head, stop), one per lane
+    auto round = [&](const uint32_t stop, const uint64_t wb_now) {
+        const uint32_t pos = head + lane;
+        if (pos < stop) {
+            const uint32_t at = pos & (PCL_FQ_CAP - 1u);
+            const uint32_t k = Q.key[at], m = Q.meta[at], w32 = Q.widx[at];
+            const uint32_t q = (m >> 5) & 3u, len = (m >> 7) & 31u;
+            const DTable &t = p.tab[(m >> 16) & 3u];
+            const uint32_t b = (m >> 18) & 1u ? Q.bucket[at] : pcl_hash32_bucket(k & ~(0xFFu << (8u * q)), t.n_buckets);
+            bool full;
+            const uint32_t sub = pcl_filter_bucket(t.nkeys[q], b, k, q, (uint32_t)t.empty, (m >> 12) & 1u, (m >> 13) & 7u, &full);
+            if (sub) {
+                uint64_t w = (wb_now & 0xFFFFFFFF00000000ull) | w32;      // the entry is at most a few iterations behind wb_now
+                if (w > wb_now + 31u) w -= 1ull << 32;
+                atomicOr(p.wl_cand + w, pcl_filter_place(sub, len, q));
+            }
+            if (full) {                                                  // rare: the chain continues in the next bucket
+                const uint32_t nxt = atomicAdd(&Q.tail, 1u) & (PCL_FQ_CAP - 1u);
+                Q.key[nxt] = k; Q.meta[nxt] = m | (1u << 18); Q.widx[nxt] = w32;
+                Q.bucket[nxt] = (b + 1u == t.n_buckets) ? 0u : b + 1u;
+            }
+        }
+        __syncwarp();
+        head = stop;
+        total = Q.tail;
+    };
+
     // wb is warp-uniform: every lane runs the same number of iterations (ballots and __syncwarp below)
-    for (uint64_t wb = (uint64_t)blockIdx.x * blockDim.x + (threadIdx.x & ~31u); wb < n_work; wb += step) {
+    // The entries of the NEXT iteration are loaded while this one is processed (their DRAM latency would otherwise head
+    // every iteration), and the records of its REPACK entries are pulled into L2 before the rounds start.
+    const uint64_t wb0 = (uint64_t)blockIdx.x * blockDim.x + (threadIdx.x & ~31u);
+    unsigned long long ent_n = PCL_WL_HOLE;
+    uint32_t key_n = 0;
+    if (wb0 + lane < n_work) { ent_n = pcl_ld_stream64(p.worklist + wb0 + lane); key_n = __ldcs(p.wl_key + wb0 + lane); }
+    for (uint64_t wb = wb0; wb < n_work; wb += step) {
+        wb_last = wb;
         const uint64_t w = wb + lane;
         const bool in = w < n_work;
-        const unsigned long long ent = in ? pcl_ld_stream64(p.worklist + w) : PCL_WL_HOLE;
-        uint32_t key32 = in ? __ldcs(p.wl_key + w) : 0u;
+        const unsigned long long ent = ent_n;
+        uint32_t key32 = key_n;
+        ent_n = PCL_WL_HOLE; key_n = 0;
+        if (w + step < n_work) { ent_n = pcl_ld_stream64(p.worklist + w + step); key_n = __ldcs(p.wl_key + w + step); }
         unsigned long long pend = 0;
         uint32_t live = 0, meta = 0;
         if (ent != PCL_WL_HOLE) {
@@ -1052,58 +1100,31 @@ __global__ void __launch_bounds__(PCL_BLOCK) k_filter(const __grid_constant__ Co
 #pragma unroll
                     for (uint32_t q = 0; q < 4u; ++q) live |= (uint32_t)pcl_filter_live(t, key32, len, ninv, ipos, q) << q;   // four independent loads
                     const uint32_t n_p2 = (2u * (len - 1u - (ninv == 1u ? ipos : 0u))) & 7u;
-                    meta = lane | (len << 7) | ((ninv == 1u ? 1u : 0u) << 12) | (n_p2 << 13) | (j << 16);
+                    meta = (len << 7) | ((ninv == 1u ? 1u : 0u) << 12) | (n_p2 << 13) | (j << 16);
                 }
             }
         }
+        if (in) p.wl_cand[w] = pend;                                 // the rounds OR the candidates in (same warp: ordered by __syncwarp)
         // ---- queue the live (entry, table) pairs, table-major ----
-        Q.res[lane] = pend;
-        uint32_t at = 0, total = 0;
+        uint32_t added = 0;
 #pragma unroll
         for (uint32_t q = 0; q < 4u; ++q) {
             const uint32_t bal = __ballot_sync(0xFFFFFFFFu, (live >> q) & 1u);
             if ((live >> q) & 1u) {
-                at = total + __popc(bal & lt);
-                Q.key[at] = key32; Q.meta[at] = meta | (q << 5); Q.bucket[at] = 0;
+                const uint32_t at = (total + added + __popc(bal & lt)) & (PCL_FQ_CAP - 1u);
+                Q.key[at] = key32; Q.meta[at] = meta | (q << 5); Q.widx[at] = (uint32_t)w;
             }
-            total += __popc(bal);
+            added += __popc(bal);
         }
+        total += added;
         if (lane == 0) Q.tail = total;
         __syncwarp();
-        // ---- one bucket per lane and round ----
-        for (uint32_t head = 0; head < total;) {
-            const uint32_t i = head + lane, stop = min(head + 32u, total);     // pairs queued during this round wait for the next one
-            if (i < stop) {
-                const uint32_t k = Q.key[i], m = Q.meta[i];
-                const uint32_t q = (m >> 5) & 3u, len = (m >> 7) & 31u;
-                const DTable &t = p.tab[(m >> 16) & 3u];
-                const uint32_t b = (m >> 18) & 1u ? Q.bucket[i] : pcl_hash32_bucket(k & ~(0xFFu << (8u * q)), t.n_buckets);
-                bool full;
-                const uint32_t sub = pcl_filter_bucket(t.nkeys[q], b, k, q, (uint32_t)t.empty, (m >> 12) & 1u, (m >> 13) & 7u, &full);
-                if (sub) atomicOr(&Q.res[m & 31u], pcl_filter_place(sub, len, q));
-                if (full) {                                          // rare: the chain continues in the next bucket
-                    const uint32_t nxt = atomicAdd(&Q.tail, 1u);
-                    const uint32_t b1 = (b + 1u == t.n_buckets) ? 0u : b + 1u;
-                    if (nxt < PCL_FQ_CAP) { Q.key[nxt] = k; Q.meta[nxt] = m | (1u << 18); Q.bucket[nxt] = b1; }
-                    else {                                           // queue full (never seen): finish the chain here
-                        uint32_t bb = b1, s2 = 0;
-                        bool f2 = true;
-                        while (f2) {
-                            s2 |= pcl_filter_bucket(t.nkeys[q], bb, k, q, (uint32_t)t.empty, (m >> 12) & 1u, (m >> 13) & 7u, &f2);
-                            bb = (bb + 1u == t.n_buckets) ? 0u : bb + 1u;
-                        }
-                        if (s2) atomicOr(&Q.res[m & 31u], pcl_filter_place(s2, len, q));
-                    }
-                }
-            }
-            __syncwarp();
-            head = stop;
-            total = min(Q.tail, PCL_FQ_CAP);
-        }
-        __syncwarp();
-        if (in) __stcs(p.wl_cand + w, Q.res[lane]);
-        __syncwarp();
+        if (ent_n != PCL_WL_HOLE && PCL_WL_IS_REPACK(ent_n))
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(p.seq + PCL_WL_REC(ent_n) * (uint64_t)rd.stride));
+        // ---- full rounds only; the rest waits for the next iteration ----
+        while (total - head >= 32u) round(head + 32u, wb);
     }
+    while (total != head) round(total - head >= 32u ? head + 32u : total, wb_last);       // drain
 }
 
 __global__ void __launch_bounds__(PCL_BLOCK) k_resolve(const __grid_constant__ CorrectParams p) {
