@@ -333,6 +333,36 @@ int pcl_text_fill(pcl_chunk *chunk, int read_slot, uint64_t *consumed);
 int pcl_text_names_check(pcl_chunk *chunk, int64_t *first_bad);
 int pcl_text_line_ends(pcl_chunk *chunk, int read_slot, uint32_t *out, uint64_t n_lines);
 
+/* ---- device-side make_fastq writer --------------------------------------------------------------------
+ * Replaces, for chunks whose text was parsed on the device, the record loop of make_fastq and the zstd encoder behind
+ * it (python/src/lib.rs:136-168, seqspec/src/utils.rs:33-36), i.e. what pcl_make_fastq_batch + a host zstd do for
+ * the host reader: the R1 (and R2) records of a chunk are assembled in HBM from the kept text and the result planes
+ * and, with `compress`, entropy-coded there into one standard zstd frame per file and call (RFC 8878: 128 KB
+ * blocks of Huffman-coded literals, no matches - any zstd decoder reads them; the ratio is that of an order-0
+ * coder, not of zstd level 9).
+ *   pcl_text_keep(chunk, slot)   after pcl_text_fill: the chunk keeps its own copy of the consumed text and line
+ *                                index (device to device, asynchronous) - the staging buffers move on to the next chunk
+ *   pcl_emit_fastq(chunk, correct_barcode, paired, compress, &res)
+ *                                after pcl_count (and pcl_correct when correct_barcode is set); blocks.  res.r1 / res.r2
+ *                                point at pinned host memory owned by the ctx holding the bytes to append to R1.fq(.zst)
+ *                                / R2.fq(.zst); they stay valid until the SECOND next pcl_emit_fastq on the ctx (two
+ *                                buffers alternate, so one call's bytes can be written to disk during the next call).
+ *                                Errors mirror the reference's panics (PCL_ERR_INPUT: a group with two targets, no read1 ...). */
+typedef struct {
+    const uint8_t *r1;           /* NULL when nothing was written                               */
+    uint64_t r1_bytes;           /* bytes at r1 (a whole zstd frame when compress != 0)         */
+    uint64_t r1_raw_bytes;       /* bytes of FASTQ text they hold                               */
+    const uint8_t *r2;
+    uint64_t r2_bytes;
+    uint64_t r2_raw_bytes;
+    uint64_t n_written;          /* read groups written                                         */
+} pcl_emit_result;
+int pcl_text_keep(pcl_chunk *chunk, int read_slot);
+int pcl_emit_fastq(pcl_chunk *chunk, int correct_barcode, int paired, int compress, pcl_emit_result *out);
+/* The block coder alone: n < 4 GiB host bytes -> one zstd frame in dst (at most 14 + n + 3 * (n / 131072 + 1) bytes);
+ * what zstd::stream::Encoder does for create_file (seqspec/src/utils.rs:20-42), on the device.  Blocks. */
+int pcl_zstd_frame(pcl_ctx *ctx, const uint8_t *src, uint64_t n, uint8_t *dst, uint64_t cap, uint64_t *used);
+
 /* ---- decompressed byte stream of one gzip file (feeds pcl_text_scan) ---------------------------------
  * Replaces open_file's MultiGzDecoder (seqspec/src/utils.rs:44-56) for the text path.  BGZF files (independent
  * <= 64 KB members with their sizes in the header) are inflated by n_threads threads straight into the caller's
@@ -382,7 +412,7 @@ void pcl_host_free(void *p);
 
 /* ---- instrumentation (used by bench.py; CUDA events on the launching stream) --------------- */
 enum { PCL_K_COUNT = 0, PCL_K_CORRECT = 1, PCL_K_COUNT_LENONLY = 2, PCL_K_ENUM = 3, PCL_K_QC = 4, PCL_K_TEXT_INDEX = 5,
-       PCL_K_TEXT_FILL = 6, PCL_K_FILTER = 7, PCL_K_MAX = 16 };
+       PCL_K_TEXT_FILL = 6, PCL_K_FILTER = 7, PCL_K_EMIT = 8, PCL_K_ZSTD = 9, PCL_K_MAX = 16 };
 int pcl_profile_enable(pcl_ctx *ctx, int on);                    /* bracket every kernel with events */
 /* accumulated ms and launches of kernel k since the last pcl_profile_reset (syncs the ctx) */
 int pcl_profile_get(pcl_ctx *ctx, int k, double *ms, uint64_t *launches);

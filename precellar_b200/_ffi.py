@@ -61,6 +61,11 @@ class HostRead(C.Structure):
     _fields_ = [("text", C.c_void_p), ("off", C.c_void_p), ("len", C.c_void_p), ("res", ReadResults)]
 
 
+class EmitResult(C.Structure):
+    _fields_ = [("r1", C.c_void_p), ("r1_bytes", C.c_uint64), ("r1_raw_bytes", C.c_uint64),
+                ("r2", C.c_void_p), ("r2_bytes", C.c_uint64), ("r2_raw_bytes", C.c_uint64), ("n_written", C.c_uint64)]
+
+
 class GroupInfo(C.Structure):
     _fields_ = [("n_records", C.c_uint64), ("n_assigned", C.c_uint64), ("n_ungroupable", C.c_uint64),
                 ("n_barcodes", C.c_uint64), ("n_fragments", C.c_uint64)]
@@ -89,6 +94,7 @@ SYMBOLS = [
     "pcl_gzsrc_open", "pcl_gzsrc_read", "pcl_gzsrc_is_bgzf", "pcl_gzsrc_error", "pcl_gzsrc_close",
     "pcl_counts_freeze", "pcl_chunk_bytes", "pcl_mem_info", "pcl_verify_enable", "pcl_chunk_set_uniform_len", "pcl_chunk_uniform_results_async",
     "pcl_group_build", "pcl_group_build_multi", "pcl_group_info_get", "pcl_group_fetch", "pcl_group_key_decode", "pcl_group_destroy",
+    "pcl_text_keep", "pcl_emit_fastq", "pcl_zstd_frame",
 ]
 
 _lib = None
@@ -153,6 +159,9 @@ def lib() -> C.CDLL:
         "pcl_text_fill": (i32, [vp, i32, C.POINTER(u64)]),
         "pcl_text_names_check": (i32, [vp, C.POINTER(C.c_int64)]),
         "pcl_text_line_ends": (i32, [vp, i32, vp, u64]),
+        "pcl_text_keep": (i32, [vp, i32]),
+        "pcl_emit_fastq": (i32, [vp, i32, i32, i32, C.POINTER(EmitResult)]),
+        "pcl_zstd_frame": (i32, [vp, vp, u64, vp, u64, C.POINTER(u64)]),
         "pcl_gzsrc_open": (i32, [C.c_char_p, i32, C.POINTER(vp)]),
         "pcl_gzsrc_read": (C.c_int64, [vp, vp, u64]),
         "pcl_gzsrc_is_bgzf": (i32, [vp]),

@@ -169,8 +169,10 @@ class FastqProcessor:
         for layout, pipe, text, results in self._gen_chunks(correct_barcode, chunk_size):
             yield self._annotate(layout, pipe, text, results, correct_barcode)
 
-    def _gen_chunks(self, correct_barcode: bool, chunk_size: int):
-        """(layout, pipeline, record text per read file, fetched result planes) per device chunk."""
+    def _gen_chunks(self, correct_barcode: bool, chunk_size: int, emit: Optional[dict] = None):
+        """(layout, pipeline, record text per read file, fetched result planes) per device chunk.  With ``emit``
+        ({"paired": bool, "compress": bool}, the device writer of make_fastq) the last two are None and what
+        ``Chunk.emit_fastq`` returned."""
         modality = self.modality()
         per_file = None
         cats = np.zeros((4, 3), np.uint64)
@@ -189,7 +191,10 @@ class FastqProcessor:
                 pipes = self._make_pipes(layout)
             pipe = pipes[0]
             try:
-                for text, results in self._run_assay(pipes, layout, correct_barcode, chunk_size):
+                if emit is not None:
+                    for got in self._emit_assay(pipe, layout, correct_barcode, chunk_size, emit):
+                        yield layout, pipe, None, got
+                for text, results in (() if emit is not None else self._run_assay(pipes, layout, correct_barcode, chunk_size)):
                     yield layout, pipe, text, results
                 q = sum(pp.qc() for pp in pipes)
                 cats += sum(pp.qc_categories() for pp in pipes) if self.compute_qc else 0
@@ -405,6 +410,74 @@ class FastqProcessor:
                 for pp in pipes:
                     pp.freeze_counts(False)
 
+    def _emit_assay(self, pipe: BarcodePipeline, layout: CompiledLayout, correct_barcode: bool, chunk_size: int, emit: dict):
+        """make_fastq with the device writer: the FASTQ text is parsed on the GPU and stays there (``Chunk.text_keep``),
+        pass 2 corrects the resident chunks and every chunk's records are assembled - and with emit["compress"]
+        entropy-coded into zstd frames - in HBM; the host appends finished bytes to the files."""
+        from .textingest import TextGroupReader
+        n_reads = len(layout.reads)
+        files = [p.files for p in layout.reads]
+        bases = sum((p.max_len or 100) for p in layout.reads)
+        per_chunk = max(MIN_CHUNK_RECORDS, int(chunk_size) // max(bases, 1))
+        chunks: List[Chunk] = []
+        trdr = TextGroupReader(pipe, files, per_chunk, [2 * (p.max_len or 150) + 80 for p in layout.reads])
+        try:
+            while True:
+                ch = pipe.new_chunk(per_chunk)
+                with _timed("pass1_text_parse"):
+                    n = trdr.next_into(ch)
+                if n == 0:
+                    ch.close()
+                    pipe.chunks.remove(ch)
+                    break
+                for r in range(n_reads):
+                    ch.text_keep(r)
+                pipe.count(ch)
+                if self.compute_qc:
+                    pipe.qc_accumulate(ch)
+                chunks.append(ch)
+        finally:
+            trdr.close()
+        pipe.allreduce()
+        totals = {pipe.counts(g)[2] for g in range(len(layout.region_ids))}
+        if len(totals) > 1:
+            raise _ffi.PclError(_ffi.PCL_ERR_INPUT, "All whitelists should have the same total read count")
+        self.num_reads = totals.pop() if totals else 0
+        if correct_barcode:
+            for ch in chunks:
+                pipe.correct(ch, self.barcode_correct_prob)
+        for ch in chunks:
+            with _timed("emit"):
+                got = ch.emit_fastq(correct_barcode, emit["paired"], emit["compress"])
+            yield got
+            ch.close()
+            pipe.chunks.remove(ch)
+
+    def device_writer_obstacle(self) -> Optional[str]:
+        """Why make_fastq cannot assemble its output on the device for these assays (None: it can)."""
+        if len(self.devices) != 1:
+            return "the device writer drives one GPU"
+        est = 0
+        for assay in self.assays:
+            layout = self._layout(assay)
+            for p in layout.reads:
+                if not p.files:
+                    return f"read {p.read_id} has no FASTQ files"
+                for f in p.files:
+                    try:
+                        est += os.path.getsize(f) * (6 if f.endswith((".gz", ".zst", ".bgz")) else 1)
+                    except OSError:
+                        return f"cannot stat {f}"
+        import torch
+        if not torch.cuda.is_available():
+            return None                          # let the CUDA library report the missing device
+        free, _total = torch.cuda.mem_get_info(self.devices[0])
+        fixed = self.resident_bytes if self.resident_bytes is not None else os.environ.get("PCL_API_RESIDENT_BYTES")
+        budget = int(fixed) if fixed not in (None, "") else int(free * 0.45)
+        if est > budget:
+            return f"about {est >> 20} MiB of FASTQ text do not fit the device budget of {budget >> 20} MiB"
+        return None
+
     def _resident_budget(self, pipe: BarcodePipeline) -> int:
         """Bytes of device memory the resident chunks of one GPU may take: `resident_bytes` (or the environment's
         PCL_API_RESIDENT_BYTES), else 60 % of what is free after the whitelist tables were built."""
@@ -474,19 +547,39 @@ class FastqProcessor:
 
 
 def make_fastq(assay, *, modality: str, out_dir, correct_barcode: bool = False, device: int = 0,
-               devices: Optional[Sequence[int]] = None) -> None:
+               devices: Optional[Sequence[int]] = None, writer: str = "auto", compression: str = "zstd") -> None:
     """Generate consolidated fastq files from the sequencing specification.
 
     The barcodes and UMIs are concatenated to the read 1 sequence; fixed sequences and linkers are removed
     (python/src/lib.rs:114-171).  Writes ``R1.fq.zst`` and, for paired-end layouts, ``R2.fq.zst``; with
     ``correct_barcode`` reads whose barcode cannot be corrected are dropped and the corrected sequence is written.
+
+    ``writer``: "device" parses the FASTQ text and assembles the output records on the GPU (one GPU, input text
+    resident on it; the stricter FASTQ dialect of the device parser: no blank lines between records), "host" reads
+    and assembles records on the host (any input size, several GPUs), "auto" picks the device writer when it applies.
+    ``compression``: "zstd" = libzstd level 9 on the host like the reference (seqspec/src/utils.rs:33-36); "device" =
+    zstd frames built on the GPU (Huffman-coded literals, no matches: every zstd decoder reads them, the files are
+    about 1.3-1.6 times the size of level 9) - only with the device writer.  The decompressed bytes are the same
+    in every combination.
     """
     from . import _zstd
+    if writer not in ("auto", "device", "host") or compression not in ("zstd", "device"):
+        raise ValueError("writer is 'auto', 'device' or 'host'; compression is 'zstd' or 'device'")
     proc = FastqProcessor(assay, device=device, devices=devices).with_modality(modality)
     out_dir = os.fspath(out_dir)
     os.makedirs(out_dir, exist_ok=True)
     with _timed("is_paired_end"):
         paired = proc.is_paired_end()
+    if writer != "host":
+        why = proc.device_writer_obstacle()
+        if why is not None and (writer == "device" or compression == "device"):
+            raise RuntimeError(f"make_fastq: the device writer does not apply: {why}")
+        writer = "device" if why is None else "host"
+    elif compression == "device":
+        raise ValueError("compression='device' needs the device writer")
+    if writer == "device":
+        _make_fastq_device(proc, out_dir, correct_barcode, paired, compression == "device")
+        return
     # level 9 like the reference (seqspec/src/utils.rs:33-36); it asks for 8 worker threads, here every core up to 16 helps
     zt = max(1, min(16, os.cpu_count() or 8))
     w1 = _zstd.Writer(os.path.join(out_dir, "R1.fq.zst"), threads=zt)
@@ -534,3 +627,62 @@ def make_fastq(assay, *, modality: str, out_dir, correct_barcode: bool = False, 
             w1.close()
             if w2 is not None:
                 w2.close()
+
+
+def _make_fastq_device(proc: FastqProcessor, out_dir: str, correct_barcode: bool, paired: bool, device_zstd: bool) -> None:
+    """The device writer: every chunk comes back as finished bytes - zstd frames built on the GPU (appended to the files
+    by a writer thread while the next chunk is emitted), or FASTQ text that goes through the host's level-9 encoder."""
+    from collections import deque
+    from concurrent.futures import ThreadPoolExecutor
+    from . import _zstd
+    p1, p2 = os.path.join(out_dir, "R1.fq.zst"), os.path.join(out_dir, "R2.fq.zst")
+    zt = max(1, min(16, os.cpu_count() or 8))
+    if device_zstd:
+        f1, f2 = open(p1, "wb"), (open(p2, "wb") if paired else None)
+        pool, pending = ThreadPoolExecutor(max_workers=1), deque()
+    else:
+        w1 = _zstd.Writer(p1, threads=zt)
+        w2 = _zstd.Writer(p2, threads=zt) if paired else None
+
+    def append(a, b):
+        if a is not None:
+            f1.write(a)
+        if b is not None and f2 is not None:
+            f2.write(b)
+    try:
+        gen = proc._gen_chunks(correct_barcode, 1_000_000, emit={"paired": paired, "compress": device_zstd})
+        while True:
+            if device_zstd:
+                while len(pending) > 1:          # the pinned result buffers alternate: the bytes of call k live until call k + 2
+                    pending.popleft().result()
+            try:
+                _layout, _pipe, _none, (r1, r2, _info) = next(gen)
+            except StopIteration:
+                break
+            if device_zstd:
+                pending.append(pool.submit(append, r1, r2))
+            else:
+                with _timed("zstd_submit"):
+                    if r1 is not None:
+                        w1.write(r1)             # read-only views: the writer copies the pieces it queues
+                    if r2 is not None and w2 is not None:
+                        w2.write(r2)
+    except _ffi.PclError as e:
+        if "unwrap" in str(e):
+            raise RuntimeError(str(e)) from e
+        raise
+    finally:
+        with _timed("zstd_drain"):
+            if device_zstd:
+                try:
+                    while pending:
+                        pending.popleft().result()
+                finally:
+                    pool.shutdown(wait=True)
+                    f1.close()
+                    if f2 is not None:
+                        f2.close()
+            else:
+                w1.close()
+                if w2 is not None:
+                    w2.close()

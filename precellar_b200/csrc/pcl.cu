@@ -23,6 +23,7 @@
 #include "textparse.cuh"
 #include "group.cuh"
 #include "tablebuild.cuh"
+#include "emit.cuh"
 
 // ------------------------------------------------------------------------------------------
 // NCCL through dlopen: the library has no link-time dependency on libnccl, and inside a process
@@ -101,6 +102,23 @@ struct TextStage {
     pcl_chunk *owner = nullptr;
 };
 
+// Scratch of pcl_emit_fastq, shared by the chunks of a ctx (the call blocks; one emission in flight per ctx).  The pinned
+// result buffers alternate, so the bytes of one call stay valid during the next one (the caller writes a file meanwhile).
+struct EmitStage {
+    uint32_t *d_sz[2] = {nullptr, nullptr}, *d_off[2] = {nullptr, nullptr}, *d_scan_tmp = nullptr;
+    uint64_t rec_cap = 0;
+    unsigned long long *d_meta = nullptr;        // [0..1] raw bytes of R1 / R2, [2] first error, [3..4] stream bytes, [5] groups written
+    unsigned long long *h_meta = nullptr;        // pinned copy
+    uint8_t *d_raw[2] = {nullptr, nullptr};
+    uint64_t raw_cap[2] = {0, 0};
+    uint8_t *d_slots[2] = {nullptr, nullptr}, *d_stream[2] = {nullptr, nullptr};
+    uint32_t *d_bsize[2] = {nullptr, nullptr};
+    uint64_t block_cap[2] = {0, 0};
+    uint8_t *h_out[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};     // [flip][file]
+    uint64_t h_cap[2][2] = {{0, 0}, {0, 0}};
+    int flip = 0;
+};
+
 struct pcl_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
@@ -119,6 +137,7 @@ struct pcl_ctx {
     uint64_t qc_reads[PCL_MAX_READS] = {0};
     std::vector<pcl_chunk *> chunks;
     TextStage text[PCL_MAX_READS];
+    EmitStage emit;
     // nccl
     NcclComm comm = nullptr;
     int nranks = 1, rank = 0;
@@ -177,6 +196,11 @@ struct ReadBuf {
     unsigned long long *h_tmeta = nullptr;    // pinned: [0] total, [1] err, [2] end of the last consumed line
     uint64_t text_lines = 0;
     bool text_scanned = false, text_filled = false;
+    // pcl_text_keep: this chunk's own copy of the consumed text and its line index (the staging buffers move on)
+    uint8_t *k_text = nullptr;
+    uint32_t *k_nl = nullptr;
+    uint64_t k_text_cap = 0, k_nl_cap = 0, k_records = 0;
+    bool text_kept = false;
 };
 
 struct pcl_chunk {
@@ -186,11 +210,22 @@ struct pcl_chunk {
     cudaEvent_t ev = nullptr, t0 = nullptr, t1 = nullptr;
     cudaEvent_t ev_counted = nullptr;    // recorded by pcl_count behind the last kernel that touches whitelist counts
     bool counted = false;
+    bool has_results = false;            // pcl_count has run on the records of the last reset
     ReadBuf rb[PCL_MAX_READS];
     std::vector<void *> allocs;
 };
 
 namespace {
+
+void emit_stage_free(EmitStage &e) {
+    for (int f = 0; f < 2; ++f) {
+        cudaFree(e.d_sz[f]); cudaFree(e.d_off[f]); cudaFree(e.d_raw[f]); cudaFree(e.d_slots[f]); cudaFree(e.d_stream[f]); cudaFree(e.d_bsize[f]);
+        for (int k = 0; k < 2; ++k) if (e.h_out[k][f]) cudaFreeHost(e.h_out[k][f]);
+    }
+    cudaFree(e.d_scan_tmp); cudaFree(e.d_meta);
+    if (e.h_meta) cudaFreeHost(e.h_meta);
+    e = EmitStage();
+}
 
 int fail(pcl_ctx *ctx, int code, const char *fmt, ...) {
     char buf[512];
@@ -399,6 +434,7 @@ int pcl_ctx_destroy(pcl_ctx *ctx) {
     while (!ctx->chunks.empty()) pcl_chunk_destroy(ctx->chunks.back());
     for (Table &t : ctx->tables) table_free(t);
     for (TextStage &t : ctx->text) { cudaFree(t.d_text); cudaFree(t.d_nl); cudaFree(t.d_tile_cnt); cudaFree(t.d_tile_off); }
+    emit_stage_free(ctx->emit);
     for (EvPair &p : ctx->evs) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
     if (ctx->comm && nccl().ok) nccl().CommDestroy(ctx->comm);
     if (ctx->d_lut) cudaFree(ctx->d_lut);
@@ -759,6 +795,7 @@ int pcl_chunk_destroy(pcl_chunk *c) {
     for (int r = 0; r < PCL_MAX_READS; ++r) {
         ReadBuf &b = c->rb[r];
         cudaFree(b.d_hash); cudaFree(b.d_tmeta);
+        cudaFree(b.k_text); cudaFree(b.k_nl);
         if (b.h_tmeta) cudaFreeHost(b.h_tmeta);
         if (ctx->text[r].owner == c) ctx->text[r].owner = nullptr;
     }
@@ -774,7 +811,8 @@ int pcl_chunk_reset(pcl_chunk *c, uint64_t n_records) {
     if (!c) return PCL_ERR_ARG;
     if (n_records > c->cap) return fail(c->ctx, PCL_ERR_ARG, "n_records %llu exceeds chunk capacity %llu", (unsigned long long)n_records, (unsigned long long)c->cap);
     c->n = n_records;
-    for (int r = 0; r < c->ctx->n_reads; ++r) c->rb[r].filled = c->rb[r].text_filled = c->rb[r].uniform_len = false;
+    c->has_results = false;
+    for (int r = 0; r < c->ctx->n_reads; ++r) c->rb[r].filled = c->rb[r].text_filled = c->rb[r].uniform_len = c->rb[r].text_kept = false;
     return PCL_OK;
 }
 
@@ -1036,6 +1074,235 @@ int pcl_text_line_ends(pcl_chunk *c, int read_slot, uint32_t *out, uint64_t n_li
     return PCL_OK;
 }
 
+
+// ------------------------------------------------------------------------------------------
+// device-side make_fastq writer (emit.cuh)
+// ------------------------------------------------------------------------------------------
+int pcl_text_keep(pcl_chunk *c, int read_slot) {
+    if (!c) return PCL_ERR_ARG;
+    pcl_ctx *ctx = c->ctx;
+    if (read_slot < 0 || read_slot >= ctx->n_reads) return fail(ctx, PCL_ERR_ARG, "bad read_slot");
+    ReadBuf &b = c->rb[read_slot];
+    const TextStage &t = ctx->text[read_slot];
+    if (!b.text_filled || t.owner != c) return fail(ctx, PCL_ERR_ARG, "pcl_text_keep follows pcl_text_fill of the same chunk and read file");
+    if (int r = bind(ctx)) return r;
+    const uint64_t bytes = c->n ? (b.h_tmeta[2] & 0xFFFFFFFFull) + 1 : 0, lines = 4 * c->n;
+    if (bytes + 16 > b.k_text_cap) {
+        CU(ctx, cudaStreamSynchronize(c->stream));
+        cudaFree(b.k_text);
+        b.k_text = nullptr; b.k_text_cap = 0;
+        const uint64_t cap = ((bytes + bytes / 16 + 16 + 4095) / 4096) * 4096;
+        cudaError_t e = cudaMalloc((void **)&b.k_text, cap);
+        if (e != cudaSuccess) return fail(ctx, e == cudaErrorMemoryAllocation ? PCL_ERR_NOMEM : PCL_ERR_CUDA, "kept text (%llu bytes): %s", (unsigned long long)cap, cudaGetErrorString(e));
+        b.k_text_cap = cap;
+    }
+    if (lines + 4 > b.k_nl_cap) {
+        CU(ctx, cudaStreamSynchronize(c->stream));
+        cudaFree(b.k_nl);
+        b.k_nl = nullptr; b.k_nl_cap = 0;
+        const uint64_t cap = std::max<uint64_t>(lines, 4 * c->cap) + 4;
+        cudaError_t e = cudaMalloc((void **)&b.k_nl, cap * 4);
+        if (e != cudaSuccess) return fail(ctx, e == cudaErrorMemoryAllocation ? PCL_ERR_NOMEM : PCL_ERR_CUDA, "kept line index: %s", cudaGetErrorString(e));
+        b.k_nl_cap = cap;
+    }
+    if (bytes) CU(ctx, cudaMemcpyAsync(b.k_text, t.d_text, bytes, cudaMemcpyDeviceToDevice, c->stream));
+    if (lines) CU(ctx, cudaMemcpyAsync(b.k_nl, t.d_nl, lines * 4, cudaMemcpyDeviceToDevice, c->stream));
+    b.k_records = c->n;
+    b.text_kept = true;
+    return PCL_OK;
+}
+
+static int emit_reserve(pcl_ctx *ctx, void **p, uint64_t *cap, uint64_t need, bool pinned) {
+    if (need <= *cap && *p) return PCL_OK;
+    if (*p) { if (pinned) cudaFreeHost(*p); else cudaFree(*p); }
+    *p = nullptr; *cap = 0;
+    const uint64_t want = ((need + need / 8 + 4095) / 4096) * 4096;
+    cudaError_t e = pinned ? cudaHostAlloc(p, want, cudaHostAllocDefault) : cudaMalloc(p, want);
+    if (e != cudaSuccess) { cudaGetLastError(); return fail(ctx, e == cudaErrorMemoryAllocation ? PCL_ERR_NOMEM : PCL_ERR_CUDA, "writer scratch (%llu bytes): %s", (unsigned long long)want, cudaGetErrorString(e)); }
+    *cap = want;
+    return PCL_OK;
+}
+
+int pcl_emit_fastq(pcl_chunk *c, int correct_barcode, int paired, int compress, pcl_emit_result *out) {
+    if (!c || !out) return PCL_ERR_ARG;
+    pcl_ctx *ctx = c->ctx;
+    memset(out, 0, sizeof *out);
+    if (!c->has_results) return fail(ctx, PCL_ERR_ARG, "pcl_emit_fastq needs a counted chunk (pcl_count, and pcl_correct when correct_barcode is set)");
+    if (int r = bind(ctx)) return r;
+    EmitStage &e = ctx->emit;
+    cudaStream_t s = c->stream;
+    const uint64_t n = c->n;
+    const int nf = paired ? 2 : 1;
+    EmitKernelParams k;
+    memset(&k, 0, sizeof k);
+    k.p.n_reads = ctx->n_reads; k.p.correct = correct_barcode ? 1 : 0; k.p.paired = paired ? 1 : 0; k.p.n = n;
+    uint64_t text_bytes = 0;
+    for (int r = 0; r < ctx->n_reads; ++r) {
+        const ReadBuf &b = c->rb[r];
+        const pcl_read_desc &rd = ctx->descs[r];
+        const pcl_read_info &inf = ctx->infos[r];
+        if (!b.text_kept || b.k_records != n) return fail(ctx, PCL_ERR_ARG, "read file %d: the chunk holds no kept text (pcl_text_keep)", r);
+        EmitRead &er = k.p.rd[r];
+        er.text = b.k_text; er.nl = b.k_nl; er.len = b.len; er.fstatus = b.fstatus; er.tcoord = b.tcoord;
+        pcl_emit_describe(er, rd, inf);
+        for (int j = 0; j < inf.n_bc; ++j) { er.bc_key[j] = b.bc_key[j]; er.bcoord[j] = b.bcoord[j]; }
+        for (int j = 0; j < inf.n_umi; ++j) er.ucoord[j] = b.ucoord[j];
+        text_bytes += n ? (b.h_tmeta[2] & 0xFFFFFFFFull) + 1 : 0;
+    }
+    e.flip ^= 1;
+    if (!e.d_meta) {
+        CU(ctx, cudaMalloc((void **)&e.d_meta, 64));
+        CU(ctx, cudaHostAlloc((void **)&e.h_meta, 64, cudaHostAllocDefault));
+    }
+    if (n == 0) return PCL_OK;
+    if (n > e.rec_cap) {
+        for (int f = 0; f < 2; ++f) { cudaFree(e.d_sz[f]); cudaFree(e.d_off[f]); e.d_sz[f] = e.d_off[f] = nullptr; }
+        cudaFree(e.d_scan_tmp); e.d_scan_tmp = nullptr;
+        e.rec_cap = 0;
+        const uint64_t cap = n + n / 8 + 1024;
+        for (int f = 0; f < 2; ++f) {
+            CU(ctx, cudaMalloc((void **)&e.d_sz[f], cap * 4));
+            CU(ctx, cudaMalloc((void **)&e.d_off[f], cap * 4));
+        }
+        CU(ctx, cudaMalloc((void **)&e.d_scan_tmp, (cap / PCL_SCAN_TILE + 2) * 4));
+        e.rec_cap = cap;
+    }
+    // every output byte comes from the text of the group (plus '@', "\n+\n" and line ends): the text bounds the output
+    const uint64_t bound = text_bytes + 8 * n + 64;
+    if (bound >= (1ull << 32)) return fail(ctx, PCL_ERR_UNSUPPORTED, "a chunk's output must stay below 4 GiB (use smaller chunks)");
+    for (int f = 0; f < nf; ++f)
+        if (int r = emit_reserve(ctx, (void **)&e.d_raw[f], &e.raw_cap[f], bound, false)) return r;
+    k.sz[0] = e.d_sz[0]; k.sz[1] = e.d_sz[1]; k.off[0] = e.d_off[0]; k.off[1] = e.d_off[1];
+    k.out[0] = e.d_raw[0]; k.out[1] = e.d_raw[1]; k.err = e.d_meta + 2; k.n_written = e.d_meta + 5;
+    CU(ctx, cudaMemsetAsync(e.d_meta, 0, 64, s));
+    CU(ctx, cudaMemsetAsync(e.d_meta + 2, 0xFF, 8, s));
+    prof_begin(ctx, s, PCL_K_EMIT);
+    k_emit_plan<<<grid_for(ctx, n, 8), PCL_EMIT_BLOCK, 0, s>>>(k);
+    prof_end(ctx, s);
+    CU(ctx, cudaGetLastError());
+    for (int f = 0; f < nf; ++f) {
+        if (int r = device_scan(ctx, s, e.d_sz[f], e.d_off[f], n, e.d_scan_tmp, e.d_meta + f)) return r;
+    }
+    CU(ctx, cudaMemcpyAsync(e.h_meta, e.d_meta, 48, cudaMemcpyDeviceToHost, s));
+    CU(ctx, cudaStreamSynchronize(s));
+    if (e.h_meta[2] != ~0ull) {
+        static const char *const what[] = {"", "Multiple target regions found in one fastq record!", "inconsistent barcode coordinates",
+                                           "corrupt corrected key", "Read1 already exists", "Read2 already exists",
+                                           "called `Option::unwrap()` on a `None` value: read1", "called `Option::unwrap()` on a `None` value: read2"};
+        const unsigned code = (unsigned)(e.h_meta[2] & 0xFF);
+        return fail(ctx, PCL_ERR_INPUT, "%s", what[code < 8 ? code : 0]);
+    }
+    const uint64_t raw[2] = {e.h_meta[0], paired ? e.h_meta[1] : 0};
+    if (raw[0] > bound || raw[1] > bound) return fail(ctx, PCL_ERR_CUDA, "writer: record sizes exceed the text they come from");
+    if (raw[0]) {
+        prof_begin(ctx, s, PCL_K_EMIT);
+        k_emit_fill<<<grid_for(ctx, n * 32, 8), PCL_EMIT_BLOCK, 0, s>>>(k);
+        prof_end(ctx, s);
+        CU(ctx, cudaGetLastError());
+    }
+    uint64_t out_bytes[2] = {raw[0], raw[1]};
+    const uint8_t *d_src[2] = {e.d_raw[0], e.d_raw[1]};
+    uint64_t head[2] = {0, 0};
+    if (compress) {
+        ZhParams zp;
+        memset(&zp, 0, sizeof zp);
+        uint32_t total_blocks = 0;
+        for (int f = 0; f < nf; ++f) {
+            const uint64_t nb = (raw[f] + ZH_BLOCK_BYTES - 1) / ZH_BLOCK_BYTES;
+            if (nb > e.block_cap[f]) {
+                cudaFree(e.d_slots[f]); cudaFree(e.d_stream[f]); cudaFree(e.d_bsize[f]);
+                e.d_slots[f] = e.d_stream[f] = nullptr; e.d_bsize[f] = nullptr; e.block_cap[f] = 0;
+                const uint64_t cap = nb + nb / 8 + 8;
+                CU(ctx, cudaMalloc((void **)&e.d_slots[f], cap * ZH_SLOT_BYTES));
+                CU(ctx, cudaMalloc((void **)&e.d_stream[f], cap * ZH_SLOT_BYTES));
+                CU(ctx, cudaMalloc((void **)&e.d_bsize[f], cap * 4));
+                e.block_cap[f] = cap;
+            }
+            ZhJob &j = zp.job[f];
+            j.src = e.d_raw[f]; j.n = raw[f]; j.slots = e.d_slots[f]; j.sizes = e.d_bsize[f]; j.stream = e.d_stream[f];
+            j.total = e.d_meta + 3 + f; j.n_blocks = (uint32_t)nb;
+            total_blocks += (uint32_t)nb;
+        }
+        if (total_blocks) {
+            prof_begin(ctx, s, PCL_K_ZSTD);
+            k_zh_blocks<<<total_blocks, ZH_THREADS, 0, s>>>(zp);
+            k_zh_compact<<<total_blocks, ZH_THREADS, 0, s>>>(zp);
+            prof_end(ctx, s);
+            ctx->launches += 1;
+            CU(ctx, cudaGetLastError());
+            CU(ctx, cudaMemcpyAsync(e.h_meta + 3, e.d_meta + 3, 16, cudaMemcpyDeviceToHost, s));
+            CU(ctx, cudaStreamSynchronize(s));
+        }
+        for (int f = 0; f < nf; ++f) {
+            out_bytes[f] = raw[f] ? e.h_meta[3 + f] : 0;
+            d_src[f] = e.d_stream[f];
+            head[f] = raw[f] ? ZH_FRAME_HEADER_BYTES : 0;
+        }
+    }
+    for (int f = 0; f < nf; ++f) {
+        if (!raw[f]) continue;
+        if (int r = emit_reserve(ctx, (void **)&e.h_out[e.flip][f], &e.h_cap[e.flip][f], head[f] + out_bytes[f], true)) return r;
+        if (compress) zh_put_frame_header(e.h_out[e.flip][f], raw[f]);
+        CU(ctx, cudaMemcpyAsync(e.h_out[e.flip][f] + head[f], d_src[f], out_bytes[f], cudaMemcpyDeviceToHost, s));
+    }
+    CU(ctx, cudaStreamSynchronize(s));
+    out->n_written = e.h_meta[5];
+    out->r1 = raw[0] ? e.h_out[e.flip][0] : nullptr; out->r1_bytes = head[0] + out_bytes[0]; out->r1_raw_bytes = raw[0];
+    out->r2 = raw[1] ? e.h_out[e.flip][1] : nullptr; out->r2_bytes = raw[1] ? head[1] + out_bytes[1] : 0; out->r2_raw_bytes = raw[1];
+    return PCL_OK;
+}
+
+
+// host bytes -> one zstd frame built by the block coder of the device writer (k_zh_blocks / k_zh_compact); blocks
+int pcl_zstd_frame(pcl_ctx *ctx, const uint8_t *src, uint64_t n, uint8_t *dst, uint64_t cap, uint64_t *used) {
+    if (!ctx || (!src && n) || !dst || !used) return PCL_ERR_ARG;
+    if (n >= (1ull << 32)) return fail(ctx, PCL_ERR_UNSUPPORTED, "pcl_zstd_frame takes less than 4 GiB per call");
+    if (int r = bind(ctx)) return r;
+    EmitStage &e = ctx->emit;
+    cudaStream_t s = ctx->stream;
+    const uint64_t nb = (n + ZH_BLOCK_BYTES - 1) / ZH_BLOCK_BYTES;
+    if (cap < ZH_FRAME_HEADER_BYTES + 3) return fail(ctx, PCL_ERR_NOMEM, "output buffer too small");
+    zh_put_frame_header(dst, n);
+    if (n == 0) {                                 // an empty frame: one empty raw block marked last
+        dst[ZH_FRAME_HEADER_BYTES] = 1; dst[ZH_FRAME_HEADER_BYTES + 1] = 0; dst[ZH_FRAME_HEADER_BYTES + 2] = 0;
+        *used = ZH_FRAME_HEADER_BYTES + 3;
+        return PCL_OK;
+    }
+    if (!e.d_meta) {
+        CU(ctx, cudaMalloc((void **)&e.d_meta, 64));
+        CU(ctx, cudaHostAlloc((void **)&e.h_meta, 64, cudaHostAllocDefault));
+    }
+    if (int r = emit_reserve(ctx, (void **)&e.d_raw[0], &e.raw_cap[0], n + 16, false)) return r;
+    if (nb > e.block_cap[0]) {
+        cudaFree(e.d_slots[0]); cudaFree(e.d_stream[0]); cudaFree(e.d_bsize[0]);
+        e.d_slots[0] = e.d_stream[0] = nullptr; e.d_bsize[0] = nullptr; e.block_cap[0] = 0;
+        const uint64_t bcap = nb + nb / 8 + 8;
+        CU(ctx, cudaMalloc((void **)&e.d_slots[0], bcap * ZH_SLOT_BYTES));
+        CU(ctx, cudaMalloc((void **)&e.d_stream[0], bcap * ZH_SLOT_BYTES));
+        CU(ctx, cudaMalloc((void **)&e.d_bsize[0], bcap * 4));
+        e.block_cap[0] = bcap;
+    }
+    CU(ctx, cudaMemcpyAsync(e.d_raw[0], src, n, cudaMemcpyHostToDevice, s));
+    ZhParams zp;
+    memset(&zp, 0, sizeof zp);
+    ZhJob &j = zp.job[0];
+    j.src = e.d_raw[0]; j.n = n; j.slots = e.d_slots[0]; j.sizes = e.d_bsize[0]; j.stream = e.d_stream[0];
+    j.total = e.d_meta + 3; j.n_blocks = (uint32_t)nb;
+    prof_begin(ctx, s, PCL_K_ZSTD);
+    k_zh_blocks<<<(unsigned)nb, ZH_THREADS, 0, s>>>(zp);
+    k_zh_compact<<<(unsigned)nb, ZH_THREADS, 0, s>>>(zp);
+    prof_end(ctx, s);
+    ctx->launches += 1;
+    CU(ctx, cudaGetLastError());
+    CU(ctx, cudaMemcpyAsync(e.h_meta + 3, e.d_meta + 3, 8, cudaMemcpyDeviceToHost, s));
+    CU(ctx, cudaStreamSynchronize(s));
+    const uint64_t bytes = e.h_meta[3];
+    if (ZH_FRAME_HEADER_BYTES + bytes > cap) return fail(ctx, PCL_ERR_NOMEM, "output buffer too small (%llu bytes needed)", (unsigned long long)(ZH_FRAME_HEADER_BYTES + bytes));
+    CU(ctx, cudaMemcpy(dst + ZH_FRAME_HEADER_BYTES, e.d_stream[0], bytes, cudaMemcpyDeviceToHost));
+    *used = ZH_FRAME_HEADER_BYTES + bytes;
+    return PCL_OK;
+}
+
 // ------------------------------------------------------------------------------------------
 // stages
 // ------------------------------------------------------------------------------------------
@@ -1134,6 +1401,7 @@ static int check_ready(pcl_ctx *ctx, pcl_chunk *c) {
 int pcl_count(pcl_ctx *ctx, pcl_chunk *c) {
     if (int r = check_ready(ctx, c)) return r;
     if (int r = bind(ctx)) return r;
+    c->has_results = true;
     if (ctx->reduced && ctx->nranks > 1 && !ctx->frozen)
         return fail(ctx, PCL_ERR_ARG, "the counts already hold the sum over ranks: call pcl_counts_reset before counting again");
     if (ctx->frozen) {                         // discarded increments go to scratch arrays (never read, never cleared)

@@ -140,6 +140,25 @@ class Chunk:
         check(self.pipe.ctx, lib().pcl_text_fill(self.h, read_slot, C.byref(v)))
         return v.value
 
+    def text_keep(self, read_slot: int) -> None:
+        """Keep this chunk's own device copy of the text consumed by ``text_fill`` (for ``emit_fastq``)."""
+        check(self.pipe.ctx, lib().pcl_text_keep(self.h, read_slot))
+
+    def emit_fastq(self, correct_barcode: bool, paired: bool, compress: bool):
+        """The chunk's make_fastq records, assembled (and with ``compress`` entropy-coded into one zstd frame per file)
+        on the device.  Returns (r1, r2, info): uint8 views of pinned memory that stay valid until the second next call
+        on this pipeline (None when nothing was written) and the byte / record counts."""
+        res = _ffi.EmitResult()
+        check(self.pipe.ctx, lib().pcl_emit_fastq(self.h, int(correct_barcode), int(paired), int(compress), C.byref(res)))
+        def view(p, n):
+            if not p or not n:
+                return None
+            a = np.frombuffer((C.c_uint8 * int(n)).from_address(p), dtype=np.uint8)
+            a.flags.writeable = False            # the bytes belong to the library (and are recycled two calls later)
+            return a
+        return view(res.r1, res.r1_bytes), view(res.r2, res.r2_bytes), {
+            "n_written": int(res.n_written), "r1_raw_bytes": int(res.r1_raw_bytes), "r2_raw_bytes": int(res.r2_raw_bytes)}
+
     def text_names_check(self) -> int:
         v = C.c_int64()
         check(self.pipe.ctx, lib().pcl_text_names_check(self.h, C.byref(v)))

@@ -11,6 +11,8 @@
 #include <vector>
 
 #include "../../precellar_b200/csrc/host_build.h"
+#include "../../precellar_b200/csrc/zhuff_core.h"
+#include "../../precellar_b200/csrc/emit_core.h"
 
 extern "C" {
 
@@ -371,6 +373,103 @@ int emu_run(const pcl_read_desc *reads, int n_reads, int n_regions, const uint8_
         }
     }
     return PCL_OK;
+}
+
+
+// ------------------------------------------------------------------------------------------
+// zhuff_core.h on the host: the CTA of k_zh_blocks emulated phase by phase, thread by thread
+// ------------------------------------------------------------------------------------------
+}  // extern "C"
+struct EmuExec {
+    template <class F> void each(F f) { for (uint32_t t = 0; t < ZH_THREADS; ++t) f(t); }
+};
+extern "C" {
+
+// src[0..n) -> one zstd frame (header + blocks) in dst; returns its size or -1 when dst is too small
+int64_t emu_zh_frame(const uint8_t *src, uint64_t n, uint8_t *dst, uint64_t cap, uint64_t *n_raw_blocks) {
+    const uint64_t n_blocks = n ? (n + ZH_BLOCK_BYTES - 1) / ZH_BLOCK_BYTES : 1;
+    if (cap < ZH_FRAME_HEADER_BYTES + n_blocks * (uint64_t)ZH_SLOT_BYTES) return -1;
+    zh_put_frame_header(dst, n);
+    uint64_t pos = ZH_FRAME_HEADER_BYTES, raw = 0;
+    std::vector<uint8_t> slot(ZH_SLOT_BYTES);
+    static ZhShared sh;
+    EmuExec ex;
+    for (uint64_t b = 0; b < n_blocks; ++b) {
+        const uint64_t lo = b * ZH_BLOCK_BYTES;
+        const uint32_t len = (uint32_t)(n - lo < ZH_BLOCK_BYTES ? n - lo : ZH_BLOCK_BYTES);
+        const uint32_t used = zh_compress_block(ex, sh, src + lo, len, b + 1 == n_blocks, slot.data());
+        raw += ((slot[0] >> 1) & 3u) == 0;
+        memcpy(dst + pos, slot.data(), used);
+        pos += used;
+    }
+    if (n_raw_blocks) *n_raw_blocks = raw;
+    return (int64_t)pos;
+}
+
+
+// ------------------------------------------------------------------------------------------
+// emit_core.h on the host: k_emit_plan (sizes) -> exclusive scan -> k_emit_fill (bytes), group by group
+// ------------------------------------------------------------------------------------------
+struct emu_emit_read {
+    const uint8_t *text;
+    const uint32_t *nl;
+    const uint16_t *len;
+    const uint16_t *fstatus;
+    const uint32_t *tcoord;
+    const void *bc_key[PCL_MAX_BC_PER_READ];
+    const uint32_t *bcoord[PCL_MAX_BC_PER_READ];
+    const uint32_t *ucoord[PCL_MAX_UMI_PER_READ];
+};
+
+// returns 0, a PCL_EMIT_* code (> 0, *bad_group set) or -1 when an output buffer is too small
+int emu_emit(const pcl_read_desc *reads, int n_reads, const emu_emit_read *io, uint64_t n, int correct, int paired,
+             uint8_t *o1, uint64_t cap1, uint64_t *u1, uint8_t *o2, uint64_t cap2, uint64_t *u2, uint64_t *n_written,
+             uint64_t *bad_group) {
+    EmitParams p;
+    memset(&p, 0, sizeof p);
+    p.n_reads = n_reads; p.correct = correct; p.paired = paired; p.n = n;
+    for (int r = 0; r < n_reads; ++r) {
+        DRead d;
+        pcl_read_info inf;
+        int bcr[PCL_MAX_BC_PER_READ];
+        std::string e;
+        if (pcl_build_read(0, reads[r], &d, &inf, bcr, &e) != PCL_OK) return -2;
+        EmitRead &er = p.rd[r];
+        pcl_emit_describe(er, reads[r], inf);
+        er.text = io[r].text; er.nl = io[r].nl; er.len = io[r].len; er.fstatus = io[r].fstatus; er.tcoord = io[r].tcoord;
+        for (int j = 0; j < PCL_MAX_BC_PER_READ; ++j) { er.bc_key[j] = io[r].bc_key[j]; er.bcoord[j] = io[r].bcoord[j]; }
+        for (int j = 0; j < PCL_MAX_UMI_PER_READ; ++j) er.ucoord[j] = io[r].ucoord[j];
+    }
+    std::vector<uint32_t> s1(n, 0), s2(n, 0);
+    uint64_t t1 = 0, t2 = 0, written = 0;
+    for (uint64_t i = 0; i < n; ++i) {
+        const EmitDecision d = pcl_emit_decide(p, i);
+        if (d.err) { *bad_group = i; return (int)d.err; }
+        if (!d.write) continue;
+        EmitCount c1;
+        pcl_emit_r1(p, i, d, c1);
+        s1[i] = c1.n; t1 += c1.n;
+        if (paired) { EmitCount c2; pcl_emit_r2(p, i, d, c2); s2[i] = c2.n; t2 += c2.n; }
+        ++written;
+    }
+    if (t1 > cap1 || t2 > cap2) return -1;
+    uint64_t a1 = 0, a2 = 0;
+    for (uint64_t i = 0; i < n; ++i) {
+        if (!s1[i]) continue;
+        const EmitDecision d = pcl_emit_decide(p, i);
+        EmitSerial w1{o1 + a1};
+        pcl_emit_r1(p, i, d, w1);
+        if ((uint64_t)(w1.dst - (o1 + a1)) != s1[i]) return -3;
+        a1 += s1[i];
+        if (paired) {
+            EmitSerial w2{o2 + a2};
+            pcl_emit_r2(p, i, d, w2);
+            if ((uint64_t)(w2.dst - (o2 + a2)) != s2[i]) return -3;
+            a2 += s2[i];
+        }
+    }
+    *u1 = t1; *u2 = t2; *n_written = written;
+    return 0;
 }
 
 }  // extern "C"

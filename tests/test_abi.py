@@ -48,11 +48,12 @@ def test_loads_and_struct_sizes(libpath):
     src = probe + ".c"
     with open(src, "w") as fh:
         fh.write('#include <stdio.h>\n#include "../../include/precellar_b200.h"\n'
-                 'int main(){printf("%zu %zu %zu %zu\\n", sizeof(pcl_elem_desc), sizeof(pcl_read_desc), '
-                 'sizeof(pcl_read_info), sizeof(pcl_read_results));return 0;}\n')
+                 'int main(){printf("%zu %zu %zu %zu %zu\\n", sizeof(pcl_elem_desc), sizeof(pcl_read_desc), '
+                 'sizeof(pcl_read_info), sizeof(pcl_read_results), sizeof(pcl_emit_result));return 0;}\n')
     subprocess.check_call(["gcc", "-o", probe, src])
     sizes = [int(x) for x in subprocess.check_output([probe], text=True).split()]
-    assert sizes == [C.sizeof(_ffi.ElemDesc), C.sizeof(_ffi.ReadDesc), C.sizeof(_ffi.ReadInfo), C.sizeof(_ffi.ReadResults)]
+    assert sizes == [C.sizeof(_ffi.ElemDesc), C.sizeof(_ffi.ReadDesc), C.sizeof(_ffi.ReadInfo), C.sizeof(_ffi.ReadResults),
+                     C.sizeof(_ffi.EmitResult)]
     os.remove(probe)
     os.remove(src)
 

@@ -237,18 +237,25 @@ def test_streamed_chunks_match_the_resident_run(dataset, monkeypatch, keep_text,
             assert qc["frac_q30_bases"][nm] == cat[j, 2] / cat[j, 1]
 
 
-def test_make_fastq(dataset, tmp_path):
-    """R1.fq.zst = corrected barcode + UMI + read1 (python/src/lib.rs:153-163); the insert is read on the pos strand."""
+WRITERS = [("host", "zstd", 262144), ("device", "zstd", 262144), ("device", "device", 262144), ("device", "device", 700)]
+
+
+@pytest.mark.parametrize("writer,compression,chunk_records", WRITERS)
+def test_make_fastq(dataset, tmp_path, monkeypatch, writer, compression, chunk_records):
+    """R1.fq.zst = corrected barcode + UMI + read1 (python/src/lib.rs:153-163); the insert is read on the pos strand.
+    Host writer (records assembled on the host, libzstd level 9) and device writer (records assembled in HBM; zstd
+    frames from libzstd or built on the GPU; one chunk or eight) must decompress to the same bytes."""
     import copy
-    from precellar_b200 import Assay, _zstd, compile_layout
+    from precellar_b200 import Assay, _zstd, api, compile_layout
     from precellar_b200.api import make_fastq
+    monkeypatch.setattr(api, "MIN_CHUNK_RECORDS", chunk_records)
     td = dataset["td"]
     spec = write_spec(td, None, None, forward_insert=True)           # whitelists are already on disk; only the YAML differs
     a = Assay(spec)
     a.update_read("R1", fastq=[os.path.join(td, "R1_a.fq.gz"), os.path.join(td, "R1_b.fq")])
     a.update_read("R2", fastq=os.path.join(td, "R2.fq.gz"))
     out = str(tmp_path / "out")
-    make_fastq(a, modality="rna", out_dir=out, correct_barcode=True)
+    make_fastq(a, modality="rna", out_dir=out, correct_barcode=True, writer=writer, compression=compression)
     layout = compile_layout(a, "rna", require_files=True)
     assert [p.is_reverse for p in layout.reads] == [False, False]
     ores, _ = U.run_oracle(layout, dataset["full"], correct=True, threshold=0.975)
@@ -269,11 +276,13 @@ def test_make_fastq(dataset, tmp_path):
     assert recs[0][0].startswith(b"@read") and b"/1" not in recs[0][0]
 
 
-def test_make_fastq_without_read1_fails_like_the_reference(dataset, tmp_path):
+@pytest.mark.parametrize("writer", ["host", "device"])
+def test_make_fastq_without_read1_fails_like_the_reference(dataset, tmp_path, writer):
     """sci-RNA-seq3 has no pos-strand insert: `record.read1.unwrap()` panics in the reference (python/src/lib.rs:160)."""
     from precellar_b200.api import make_fastq
-    with pytest.raises(RuntimeError):
-        make_fastq(dataset["assay"], modality="rna", out_dir=str(tmp_path / "o2"), correct_barcode=False)
+    with pytest.raises(RuntimeError) as ei:
+        make_fastq(dataset["assay"], modality="rna", out_dir=str(tmp_path / "o2"), correct_barcode=False, writer=writer)
+    assert "read1" in str(ei.value)
 
 
 @pytest.mark.parametrize("device_parse", [False, True])
@@ -294,10 +303,12 @@ def test_mismatched_names_are_rejected(dataset, tmp_path, device_parse):
     assert ei.value.code == _ffi.PCL_ERR_INPUT
 
 
-def test_make_fastq_paired_end_atac_like(tmp_path):
+@pytest.mark.parametrize("writer,compression,chunk_records", WRITERS)
+def test_make_fastq_paired_end_atac_like(tmp_path, monkeypatch, writer, compression, chunk_records):
     """Paired-end layout (targets on both strands): R1.fq.zst and R2.fq.zst, neg-strand barcode read (I2)."""
-    from precellar_b200 import Assay, _zstd, compile_layout
+    from precellar_b200 import Assay, _zstd, api, compile_layout
     from precellar_b200.api import make_fastq
+    monkeypatch.setattr(api, "MIN_CHUNK_RECORDS", chunk_records)
     td = str(tmp_path)
     rng = np.random.default_rng(21)
     wl = U.gen_whitelist(rng, 200, 16)
@@ -332,7 +343,7 @@ def test_make_fastq_paired_end_atac_like(tmp_path):
         write_fastq(os.path.join(td, rid + ".fq.gz"), names, full[r], True)
         a.update_read(rid, fastq=os.path.join(td, rid + ".fq.gz"))
     out = os.path.join(td, "out")
-    make_fastq(a, modality="atac", out_dir=out, correct_barcode=True)
+    make_fastq(a, modality="atac", out_dir=out, correct_barcode=True, writer=writer, compression=compression)
     layout = compile_layout(a, "atac", require_files=True)
     ores, _ = U.run_oracle(layout, full, correct=True, threshold=0.975)
     r1 = _zstd.decompress_file(os.path.join(out, "R1.fq.zst")).split(b"\n")

@@ -124,10 +124,11 @@ def _digest(path: str) -> str:
     return hashlib.sha256(_zstd.decompress_file(path)).hexdigest()
 
 
-def run_ours(spec: str, paths: dict, out_dir: str, devices=None) -> float:
+def run_ours(spec: str, paths: dict, out_dir: str, devices=None, writer: str = "auto", compression: str = "zstd") -> float:
     from precellar_b200.api import make_fastq
     t0 = time.perf_counter()
-    make_fastq(assay_for(spec, paths), modality="atac", out_dir=out_dir, correct_barcode=True, devices=devices)
+    make_fastq(assay_for(spec, paths), modality="atac", out_dir=out_dir, correct_barcode=True, devices=devices, writer=writer,
+               compression=compression)
     return time.perf_counter() - t0
 
 
