@@ -25,7 +25,7 @@ SPLIT_OK, SPLIT_ANCHOR_NOT_FOUND, SPLIT_PATTERN_MISMATCH, SPLIT_MULTI_TARGET = 0
 FSTATUS_TARGET = 0x4
 BC_EXACT, BC_ABSENT, BC_NO_MATCH, BC_CORRECTED, BC_LOW_CONF, BC_EXCEED_EE = 0, 3, 4, 5, 6, 7
 KEY_ABSENT32, KEY_ABSENT64, COORD_ABSENT = 0xFFFFFFFF, 0xFFFFFFFFFFFFFFFF, 0xFFFFFFFF
-K_COUNT, K_CORRECT, K_COUNT_LENONLY, K_ENUM, K_QC, K_TEXT_INDEX, K_TEXT_FILL, K_FILTER = 0, 1, 2, 3, 4, 5, 6, 7
+K_COUNT, K_CORRECT, K_COUNT_LENONLY, K_ENUM, K_QC, K_TEXT_INDEX, K_TEXT_FILL, K_FILTER, K_EMIT, K_ZSTD = 0, 1, 2, 3, 4, 5, 6, 7, 8, 9
 F64_MAX = 1.7976931348623157e308
 
 

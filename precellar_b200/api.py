@@ -104,6 +104,10 @@ def _as_assays(assay) -> List[Assay]:
     return [a if isinstance(a, Assay) else Assay(os.fspath(a)) for a in items]
 
 
+class DeviceWriterUnfit(RuntimeError):
+    """make_fastq's device writer does not apply to this input (raised before anything was written)."""
+
+
 class FastqProcessor:
     """Barcode counting, correction and annotation of the FASTQ files named by one or more assays."""
 
@@ -190,8 +194,11 @@ class FastqProcessor:
             with _timed("pipeline_create"):
                 pipes = self._make_pipes(layout)
             pipe = pipes[0]
+            if os.environ.get("PCL_API_KERNEL_MS") == "1":               # diagnostic: every kernel bracketed by events
+                pipe.profile_enable(True)
             try:
                 if emit is not None:
+                    self._check_device_writer_budget(pipe)
                     for got in self._emit_assay(pipe, layout, correct_barcode, chunk_size, emit):
                         yield layout, pipe, None, got
                 for text, results in (() if emit is not None else self._run_assay(pipes, layout, correct_barcode, chunk_size)):
@@ -208,6 +215,14 @@ class FastqProcessor:
                             read_ids.append(p.read_id)
                             per_file = np.vstack([per_file, q[r:r + 1]])
             finally:
+                if os.environ.get("PCL_API_KERNEL_MS") == "1":
+                    names = {_ffi.K_COUNT: "count", _ffi.K_COUNT_LENONLY: "count_lenonly", _ffi.K_FILTER: "filter", _ffi.K_CORRECT: "resolve",
+                             _ffi.K_QC: "qc", _ffi.K_TEXT_INDEX: "text_index", _ffi.K_TEXT_FILL: "text_fill", _ffi.K_EMIT: "emit",
+                             _ffi.K_ZSTD: "zstd_blocks"}
+                    try:
+                        TIMING["kernel_ms"] = {nm: round(pipe.profile_get(k)[0], 3) for k, nm in names.items()}
+                    except _ffi.PclError:
+                        pass
                 for pp in pipes:
                     pp.close()
             out = {}
@@ -420,38 +435,45 @@ class FastqProcessor:
         bases = sum((p.max_len or 100) for p in layout.reads)
         per_chunk = max(MIN_CHUNK_RECORDS, int(chunk_size) // max(bases, 1))
         chunks: List[Chunk] = []
-        trdr = TextGroupReader(pipe, files, per_chunk, [2 * (p.max_len or 150) + 80 for p in layout.reads])
+        with _timed("text_reader_open"):
+            trdr = TextGroupReader(pipe, files, per_chunk, [2 * (p.max_len or 150) + 80 for p in layout.reads])
         try:
             while True:
-                ch = pipe.new_chunk(per_chunk)
+                with _timed("chunk_create"):
+                    ch = pipe.new_chunk(per_chunk)
                 with _timed("pass1_text_parse"):
                     n = trdr.next_into(ch)
                 if n == 0:
                     ch.close()
                     pipe.chunks.remove(ch)
                     break
-                for r in range(n_reads):
-                    ch.text_keep(r)
-                pipe.count(ch)
-                if self.compute_qc:
-                    pipe.qc_accumulate(ch)
+                with _timed("pass1_keep_count"):
+                    for r in range(n_reads):
+                        ch.text_keep(r)
+                    pipe.count(ch)
+                    if self.compute_qc:
+                        pipe.qc_accumulate(ch)
                 chunks.append(ch)
         finally:
-            trdr.close()
-        pipe.allreduce()
-        totals = {pipe.counts(g)[2] for g in range(len(layout.region_ids))}
+            with _timed("text_reader_close"):
+                trdr.close()
+        with _timed("allreduce_counts"):
+            pipe.allreduce()
+            totals = {pipe.counts(g)[2] for g in range(len(layout.region_ids))}
         if len(totals) > 1:
             raise _ffi.PclError(_ffi.PCL_ERR_INPUT, "All whitelists should have the same total read count")
         self.num_reads = totals.pop() if totals else 0
         if correct_barcode:
-            for ch in chunks:
-                pipe.correct(ch, self.barcode_correct_prob)
+            with _timed("pass2_correct_launch"):
+                for ch in chunks:
+                    pipe.correct(ch, self.barcode_correct_prob)
         for ch in chunks:
             with _timed("emit"):
                 got = ch.emit_fastq(correct_barcode, emit["paired"], emit["compress"])
             yield got
-            ch.close()
-            pipe.chunks.remove(ch)
+            with _timed("chunk_close"):
+                ch.close()
+                pipe.chunks.remove(ch)
 
     def device_writer_obstacle(self) -> Optional[str]:
         """Why make_fastq cannot assemble its output on the device for these assays (None: it can)."""
@@ -468,15 +490,20 @@ class FastqProcessor:
                         est += os.path.getsize(f) * (6 if f.endswith((".gz", ".zst", ".bgz")) else 1)
                     except OSError:
                         return f"cannot stat {f}"
-        import torch
-        if not torch.cuda.is_available():
-            return None                          # let the CUDA library report the missing device
-        free, _total = torch.cuda.mem_get_info(self.devices[0])
-        fixed = self.resident_bytes if self.resident_bytes is not None else os.environ.get("PCL_API_RESIDENT_BYTES")
-        budget = int(fixed) if fixed not in (None, "") else int(free * 0.45)
-        if est > budget:
-            return f"about {est >> 20} MiB of FASTQ text do not fit the device budget of {budget >> 20} MiB"
+        self._text_estimate = est
         return None
+
+    def _check_device_writer_budget(self, pipe: BarcodePipeline) -> None:
+        """The text of all files stays on the device between the passes: refuse (DeviceWriterUnfit) what does not fit."""
+        est = getattr(self, "_text_estimate", 0)
+        fixed = self.resident_bytes if self.resident_bytes is not None else os.environ.get("PCL_API_RESIDENT_BYTES")
+        if fixed not in (None, ""):
+            budget = int(fixed)
+        else:
+            free, _total = pipe.mem_info()
+            budget = int(free * 0.45)
+        if est > budget:
+            raise DeviceWriterUnfit(f"about {est >> 20} MiB of FASTQ text do not fit the device budget of {budget >> 20} MiB")
 
     def _resident_budget(self, pipe: BarcodePipeline) -> int:
         """Bytes of device memory the resident chunks of one GPU may take: `resident_bytes` (or the environment's
@@ -570,16 +597,30 @@ def make_fastq(assay, *, modality: str, out_dir, correct_barcode: bool = False, 
     os.makedirs(out_dir, exist_ok=True)
     with _timed("is_paired_end"):
         paired = proc.is_paired_end()
+    asked_writer = writer
     if writer != "host":
-        why = proc.device_writer_obstacle()
+        with _timed("writer_choice"):
+            why = proc.device_writer_obstacle()
         if why is not None and (writer == "device" or compression == "device"):
             raise RuntimeError(f"make_fastq: the device writer does not apply: {why}")
         writer = "device" if why is None else "host"
     elif compression == "device":
         raise ValueError("compression='device' needs the device writer")
     if writer == "device":
-        _make_fastq_device(proc, out_dir, correct_barcode, paired, compression == "device")
-        return
+        state = {"wrote": False}
+        try:
+            _make_fastq_device(proc, out_dir, correct_barcode, paired, compression == "device", state)
+            return
+        except DeviceWriterUnfit as e:
+            if asked_writer == "device" or compression == "device":
+                raise RuntimeError(f"make_fastq: the device writer does not apply: {e}") from e
+        except (_ffi.PclError, RuntimeError) as e:
+            # the device parser's FASTQ dialect is stricter than the host reader's (no blank lines between records): in
+            # "auto" mode an input it rejects before anything was written gets the host path's verdict instead
+            code = getattr(e, "code", getattr(e.__cause__, "code", None))
+            if asked_writer != "auto" or compression == "device" or state["wrote"] or code != _ffi.PCL_ERR_INPUT:
+                raise
+        proc = FastqProcessor(assay, device=device, devices=devices).with_modality(modality)
     # level 9 like the reference (seqspec/src/utils.rs:33-36); it asks for 8 worker threads, here every core up to 16 helps
     zt = max(1, min(16, os.cpu_count() or 8))
     w1 = _zstd.Writer(os.path.join(out_dir, "R1.fq.zst"), threads=zt)
@@ -629,7 +670,8 @@ def make_fastq(assay, *, modality: str, out_dir, correct_barcode: bool = False, 
                 w2.close()
 
 
-def _make_fastq_device(proc: FastqProcessor, out_dir: str, correct_barcode: bool, paired: bool, device_zstd: bool) -> None:
+def _make_fastq_device(proc: FastqProcessor, out_dir: str, correct_barcode: bool, paired: bool, device_zstd: bool,
+                       state: Optional[dict] = None) -> None:
     """The device writer: every chunk comes back as finished bytes - zstd frames built on the GPU (appended to the files
     by a writer thread while the next chunk is emitted), or FASTQ text that goes through the host's level-9 encoder."""
     from collections import deque
@@ -659,6 +701,8 @@ def _make_fastq_device(proc: FastqProcessor, out_dir: str, correct_barcode: bool
                 _layout, _pipe, _none, (r1, r2, _info) = next(gen)
             except StopIteration:
                 break
+            if state is not None:
+                state["wrote"] = True
             if device_zstd:
                 pending.append(pool.submit(append, r1, r2))
             else:
@@ -679,9 +723,10 @@ def _make_fastq_device(proc: FastqProcessor, out_dir: str, correct_barcode: bool
                         pending.popleft().result()
                 finally:
                     pool.shutdown(wait=True)
-                    f1.close()
-                    if f2 is not None:
-                        f2.close()
+                    with _timed("file_close"):
+                        f1.close()
+                        if f2 is not None:
+                            f2.close()
             else:
                 w1.close()
                 if w2 is not None:

@@ -15,7 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libprecellar_b200.so")
 SOURCES = [os.path.join(CSRC, "pcl.cu"), os.path.join(CSRC, "ingest.cpp"), os.path.join(CSRC, "gzsrc.cpp")]
-DEPS = [os.path.join(CSRC, f) for f in ("pcl.cu", "kernels.cuh", "textparse.cuh", "hd_core.h", "host_build.h", "ingest.cpp", "gzsrc.cpp")] + \
+DEPS = [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if f.endswith((".cu", ".cuh", ".h", ".cpp"))] + \
        [os.path.join(HERE, "..", "include", "precellar_b200.h")]
 
 NVCC_FLAGS = [

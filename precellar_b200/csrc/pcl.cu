@@ -100,6 +100,12 @@ struct TextStage {
     uint32_t *d_nl = nullptr, *d_tile_cnt = nullptr, *d_tile_off = nullptr;
     uint64_t text_cap = 0, nl_cap = 0, text_bytes = 0;
     pcl_chunk *owner = nullptr;
+    // small result words and name hashes of the parse in flight: owned by the stage (one block per read file at a time),
+    // so that creating a chunk costs no pinned or device allocation on this path
+    uint64_t *d_hash = nullptr;
+    uint64_t hash_cap = 0;
+    unsigned long long *d_tmeta = nullptr;    // device: [0] newline total, [1] first bad record << 8 | code
+    unsigned long long *h_tmeta = nullptr;    // pinned: [0] total, [1] err, [2] end of the last consumed line
 };
 
 // Scratch of pcl_emit_fastq, shared by the chunks of a ctx (the call blocks; one emission in flight per ctx).  The pinned
@@ -138,6 +144,11 @@ struct pcl_ctx {
     std::vector<pcl_chunk *> chunks;
     TextStage text[PCL_MAX_READS];
     EmitStage emit;
+    // pcl_text_keep: the chunks' kept text and line indices are slices of a few large slabs (a cudaMalloc per chunk and
+    // read file costs more than the copies); the slabs are recycled when the last chunk holding a slice goes away
+    struct KeepSlab { uint8_t *p; uint64_t cap, used; };
+    std::vector<KeepSlab> keep_slabs;
+    uint64_t keep_live = 0;
     // nccl
     NcclComm comm = nullptr;
     int nranks = 1, rank = 0;
@@ -191,13 +202,14 @@ struct ReadBuf {
     uint8_t *seq_stage = nullptr;             // pcl_chunk_upload_compact: the rows as uploaded, before k_repack_rows
     bool filled = false;
     // device-side text parse (pcl_text_*): name hashes and the small result words of this chunk's parse
-    uint64_t *d_hash = nullptr;
-    unsigned long long *d_tmeta = nullptr;    // device: [0] newline total, [1] first bad record << 8 | code
-    unsigned long long *h_tmeta = nullptr;    // pinned: [0] total, [1] err, [2] end of the last consumed line
+    uint64_t *d_hash = nullptr;               // = the stage's, while this chunk owns it
+    unsigned long long *d_tmeta = nullptr;
+    unsigned long long *h_tmeta = nullptr;
+    uint64_t text_consumed = 0;               // bytes of the text block the filled records took
     uint64_t text_lines = 0;
     bool text_scanned = false, text_filled = false;
     // pcl_text_keep: this chunk's own copy of the consumed text and its line index (the staging buffers move on)
-    uint8_t *k_text = nullptr;
+    uint8_t *k_text = nullptr;                // slices of ctx->keep_slabs
     uint32_t *k_nl = nullptr;
     uint64_t k_text_cap = 0, k_nl_cap = 0, k_records = 0;
     bool text_kept = false;
@@ -214,6 +226,8 @@ struct pcl_chunk {
     ReadBuf rb[PCL_MAX_READS];
     std::vector<void *> allocs;
 };
+
+static void keep_release(pcl_ctx *ctx);
 
 namespace {
 
@@ -433,8 +447,12 @@ int pcl_ctx_destroy(pcl_ctx *ctx) {
     cudaDeviceSynchronize();
     while (!ctx->chunks.empty()) pcl_chunk_destroy(ctx->chunks.back());
     for (Table &t : ctx->tables) table_free(t);
-    for (TextStage &t : ctx->text) { cudaFree(t.d_text); cudaFree(t.d_nl); cudaFree(t.d_tile_cnt); cudaFree(t.d_tile_off); }
+    for (TextStage &t : ctx->text) {
+        cudaFree(t.d_text); cudaFree(t.d_nl); cudaFree(t.d_tile_cnt); cudaFree(t.d_tile_off); cudaFree(t.d_hash); cudaFree(t.d_tmeta);
+        if (t.h_tmeta) cudaFreeHost(t.h_tmeta);
+    }
     emit_stage_free(ctx->emit);
+    for (pcl_ctx::KeepSlab &k : ctx->keep_slabs) cudaFree(k.p);
     for (EvPair &p : ctx->evs) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
     if (ctx->comm && nccl().ok) nccl().CommDestroy(ctx->comm);
     if (ctx->d_lut) cudaFree(ctx->d_lut);
@@ -702,9 +720,11 @@ uint64_t pcl_whitelist_size(const pcl_ctx *ctx, int region_slot) {
 // ------------------------------------------------------------------------------------------
 // chunks
 // ------------------------------------------------------------------------------------------
-static void stage_free(TextStage &t) {
+static void stage_free(TextStage &t) {              // the text buffers only: the hash / meta words stay
     cudaFree(t.d_text); cudaFree(t.d_nl); cudaFree(t.d_tile_cnt); cudaFree(t.d_tile_off);
-    t = TextStage();
+    t.d_text = nullptr; t.d_nl = nullptr; t.d_tile_cnt = nullptr; t.d_tile_off = nullptr;
+    t.text_cap = t.nl_cap = t.text_bytes = 0;
+    t.owner = nullptr;
 }
 
 static int chunk_alloc(pcl_chunk *c, void **p, size_t bytes) {
@@ -794,9 +814,7 @@ int pcl_chunk_destroy(pcl_chunk *c) {
     for (void *p : c->allocs) cudaFree(p);
     for (int r = 0; r < PCL_MAX_READS; ++r) {
         ReadBuf &b = c->rb[r];
-        cudaFree(b.d_hash); cudaFree(b.d_tmeta);
-        cudaFree(b.k_text); cudaFree(b.k_nl);
-        if (b.h_tmeta) cudaFreeHost(b.h_tmeta);
+        if (b.k_text || b.k_nl) keep_release(ctx);
         if (ctx->text[r].owner == c) ctx->text[r].owner = nullptr;
     }
     cudaEventDestroy(c->ev); cudaEventDestroy(c->ev_counted); cudaEventDestroy(c->t0); cudaEventDestroy(c->t1);
@@ -919,11 +937,18 @@ void *pcl_chunk_stream(pcl_chunk *c) { return c ? (void *)c->stream : nullptr; }
 
 static int text_reserve(pcl_chunk *c, ReadBuf &b, TextStage &t, uint64_t n_bytes) {
     pcl_ctx *ctx = c->ctx;
-    if (!b.d_tmeta) {
-        CU(ctx, cudaMalloc((void **)&b.d_tmeta, 16));
-        CU(ctx, cudaMallocHost((void **)&b.h_tmeta, 32));
-        CU(ctx, cudaMalloc((void **)&b.d_hash, c->cap * 8 + 16));
+    if (!t.d_tmeta) {
+        CU(ctx, cudaMalloc((void **)&t.d_tmeta, 16));
+        CU(ctx, cudaMallocHost((void **)&t.h_tmeta, 32));
     }
+    if (c->cap > t.hash_cap) {
+        if (t.owner) CU(ctx, cudaStreamSynchronize(t.owner->stream));
+        cudaFree(t.d_hash);
+        t.d_hash = nullptr; t.hash_cap = 0;
+        CU(ctx, cudaMalloc((void **)&t.d_hash, c->cap * 8 + 16));
+        t.hash_cap = c->cap;
+    }
+    b.d_tmeta = t.d_tmeta; b.h_tmeta = t.h_tmeta; b.d_hash = t.d_hash;
     if (n_bytes + 16 <= t.text_cap) return PCL_OK;
     if (t.owner) CU(ctx, cudaStreamSynchronize(t.owner->stream));
     stage_free(t);
@@ -1029,7 +1054,8 @@ int pcl_text_fill(pcl_chunk *c, int read_slot, uint64_t *consumed) {
                         read_slot, what[code < 4 ? code : 0]);
         }
     }
-    if (consumed) *consumed = c->n ? (b.h_tmeta[2] & 0xFFFFFFFFull) + 1 : 0;
+    b.text_consumed = c->n ? (b.h_tmeta[2] & 0xFFFFFFFFull) + 1 : 0;
+    if (consumed) *consumed = b.text_consumed;
     b.filled = true;
     b.text_filled = true;
     return PCL_OK;
@@ -1078,6 +1104,44 @@ int pcl_text_line_ends(pcl_chunk *c, int read_slot, uint32_t *out, uint64_t n_li
 // ------------------------------------------------------------------------------------------
 // device-side make_fastq writer (emit.cuh)
 // ------------------------------------------------------------------------------------------
+}  // extern "C"
+
+namespace {
+const uint64_t kKeepSlabBytes = 1ull << 30;
+
+// `bytes` of device memory out of the keep slabs (256-byte aligned); NULL with the error set when the device is full
+uint8_t *keep_alloc(pcl_ctx *ctx, uint64_t bytes) {
+    bytes = (bytes + 255) & ~255ull;
+    if (!ctx->keep_slabs.empty()) {
+        pcl_ctx::KeepSlab &k = ctx->keep_slabs.back();
+        if (k.used + bytes <= k.cap) { uint8_t *p = k.p + k.used; k.used += bytes; return p; }
+    }
+    size_t free_b = 0, total_b = 0;
+    cudaMemGetInfo(&free_b, &total_b);
+    uint64_t cap = std::max<uint64_t>(bytes, std::min<uint64_t>(kKeepSlabBytes, free_b / 4));
+    cap = (cap + 255) & ~255ull;
+    uint8_t *p = nullptr;
+    cudaError_t e = cudaMalloc((void **)&p, cap);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        fail(ctx, e == cudaErrorMemoryAllocation ? PCL_ERR_NOMEM : PCL_ERR_CUDA, "kept text (%llu bytes): %s", (unsigned long long)cap, cudaGetErrorString(e));
+        return nullptr;
+    }
+    ctx->keep_slabs.push_back({p, cap, bytes});
+    return p;
+}
+}  // namespace
+
+// one read file of a chunk gave its slices back; with the last one the slabs start over (the first is kept for the next run)
+static void keep_release(pcl_ctx *ctx) {
+    if (ctx->keep_live) --ctx->keep_live;
+    if (ctx->keep_live) return;
+    while (ctx->keep_slabs.size() > 1) { cudaFree(ctx->keep_slabs.back().p); ctx->keep_slabs.pop_back(); }
+    if (!ctx->keep_slabs.empty()) ctx->keep_slabs[0].used = 0;
+}
+
+extern "C" {
+
 int pcl_text_keep(pcl_chunk *c, int read_slot) {
     if (!c) return PCL_ERR_ARG;
     pcl_ctx *ctx = c->ctx;
@@ -1086,24 +1150,14 @@ int pcl_text_keep(pcl_chunk *c, int read_slot) {
     const TextStage &t = ctx->text[read_slot];
     if (!b.text_filled || t.owner != c) return fail(ctx, PCL_ERR_ARG, "pcl_text_keep follows pcl_text_fill of the same chunk and read file");
     if (int r = bind(ctx)) return r;
-    const uint64_t bytes = c->n ? (b.h_tmeta[2] & 0xFFFFFFFFull) + 1 : 0, lines = 4 * c->n;
-    if (bytes + 16 > b.k_text_cap) {
-        CU(ctx, cudaStreamSynchronize(c->stream));
-        cudaFree(b.k_text);
-        b.k_text = nullptr; b.k_text_cap = 0;
-        const uint64_t cap = ((bytes + bytes / 16 + 16 + 4095) / 4096) * 4096;
-        cudaError_t e = cudaMalloc((void **)&b.k_text, cap);
-        if (e != cudaSuccess) return fail(ctx, e == cudaErrorMemoryAllocation ? PCL_ERR_NOMEM : PCL_ERR_CUDA, "kept text (%llu bytes): %s", (unsigned long long)cap, cudaGetErrorString(e));
-        b.k_text_cap = cap;
-    }
-    if (lines + 4 > b.k_nl_cap) {
-        CU(ctx, cudaStreamSynchronize(c->stream));
-        cudaFree(b.k_nl);
-        b.k_nl = nullptr; b.k_nl_cap = 0;
-        const uint64_t cap = std::max<uint64_t>(lines, 4 * c->cap) + 4;
-        cudaError_t e = cudaMalloc((void **)&b.k_nl, cap * 4);
-        if (e != cudaSuccess) return fail(ctx, e == cudaErrorMemoryAllocation ? PCL_ERR_NOMEM : PCL_ERR_CUDA, "kept line index: %s", cudaGetErrorString(e));
-        b.k_nl_cap = cap;
+    const uint64_t bytes = b.text_consumed, lines = 4 * c->n;
+    if (bytes + 16 > b.k_text_cap || lines + 4 > b.k_nl_cap) {     // a chunk that is reused with larger blocks takes new slices
+        if (!b.k_text) ++ctx->keep_live;
+        const uint64_t tcap = bytes + bytes / 16 + 16, lcap = std::max<uint64_t>(lines, 4 * c->cap) + 4;
+        uint8_t *p = keep_alloc(ctx, ((tcap + 255) & ~255ull) + lcap * 4);
+        if (!p) { if (!b.k_text) --ctx->keep_live; return PCL_ERR_NOMEM; }
+        b.k_text = p; b.k_text_cap = tcap;
+        b.k_nl = (uint32_t *)(p + ((tcap + 255) & ~255ull)); b.k_nl_cap = lcap;
     }
     if (bytes) CU(ctx, cudaMemcpyAsync(b.k_text, t.d_text, bytes, cudaMemcpyDeviceToDevice, c->stream));
     if (lines) CU(ctx, cudaMemcpyAsync(b.k_nl, t.d_nl, lines * 4, cudaMemcpyDeviceToDevice, c->stream));
@@ -1147,7 +1201,7 @@ int pcl_emit_fastq(pcl_chunk *c, int correct_barcode, int paired, int compress, 
         pcl_emit_describe(er, rd, inf);
         for (int j = 0; j < inf.n_bc; ++j) { er.bc_key[j] = b.bc_key[j]; er.bcoord[j] = b.bcoord[j]; }
         for (int j = 0; j < inf.n_umi; ++j) er.ucoord[j] = b.ucoord[j];
-        text_bytes += n ? (b.h_tmeta[2] & 0xFFFFFFFFull) + 1 : 0;
+        text_bytes += b.text_consumed;
     }
     e.flip ^= 1;
     if (!e.d_meta) {

@@ -30,6 +30,17 @@ def iter_fastq(paths: Sequence[str]) -> Iterator[Tuple[bytes, bytes, bytes]]:
 def infer_length(paths: Sequence[str], n: int) -> Tuple[int, int]:
     if not paths:
         raise RuntimeError("No fastq files found.")          # .expect("No fastq files found.")
+    try:                                                     # the C++ record reader: lengths only, no planes
+        from .ingest import FastqReader
+        rdr = FastqReader(list(paths))
+        try:
+            b = rdr.read(int(n), 0)
+        finally:
+            rdr.close()
+        if b is not None and len(b.batch.length):
+            return int(b.batch.length.min()), int(b.batch.length.max())
+    except Exception:                                        # records it does not take (> 65535 bases ...): the plain loop below
+        pass
     lo, hi = 1 << 62, 0
     for k, (_, seq, _) in enumerate(iter_fastq(paths)):
         if k >= n:

@@ -253,6 +253,10 @@ class BarcodePipeline:
             if isinstance(wl, np.ndarray):             # [n, k] uint8: large equal-length list, no Python objects
                 n, k = wl.shape
                 self.load_whitelist_packed(slot, wl.reshape(-1), np.arange(n + 1, dtype=np.uint64) * np.uint64(k))
+            elif getattr(wl, "unique", False) and hasattr(wl, "packed"):     # seqspec.OnlistItems: deduplicated, packed once
+                blob, offs = wl.packed()
+                self.load_whitelist_packed(slot, blob, offs)
+                self.wl_bytes[slot] = wl
             else:
                 self.load_whitelist(slot, list(dict.fromkeys(wl)))
         if nranks > 1:

@@ -100,6 +100,24 @@ def read_lines(path: str) -> List[bytes]:
 _ONLIST_CACHE: dict = {}
 
 
+class OnlistItems(list):
+    """The entries of an onlist file (duplicates dropped, file order) with a cached packed form - one byte blob and the
+    offsets of the entries - which is what ``pcl_whitelist_load`` takes: a 737 K-entry list is joined once per process,
+    not once per pipeline."""
+    unique = True
+
+    def packed(self):
+        got = getattr(self, "_packed", None)
+        if got is None:
+            import numpy as np
+            offs = np.zeros(len(self) + 1, dtype=np.uint64)
+            if self:
+                np.cumsum(np.fromiter(map(len, self), dtype=np.uint64, count=len(self)), out=offs[1:])
+            blob = np.frombuffer(b"".join(self), dtype=np.uint8) if self else np.zeros(1, np.uint8)
+            got = self._packed = (blob, offs)
+        return got
+
+
 @dataclass
 class Onlist:                                                            # region.rs:446-456
     file_id: str = ""
@@ -145,7 +163,7 @@ class Onlist:                                                            # regio
             key = None
         if key is not None and key in _ONLIST_CACHE:
             return _ONLIST_CACHE[key]
-        items = list(dict.fromkeys(read_lines(path)))
+        items = OnlistItems(dict.fromkeys(read_lines(path)))
         if key is not None:
             if len(_ONLIST_CACHE) >= 8:
                 _ONLIST_CACHE.pop(next(iter(_ONLIST_CACHE)))

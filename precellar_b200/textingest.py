@@ -23,11 +23,39 @@ from ._ffi import lib
 from .pipeline import BarcodePipeline, Chunk
 
 
+# Pinned blocks are expensive to create (the driver pins and maps every page: about a second per GB here), so the blocks
+# of a finished reader are parked and handed to the next one of this process instead of being freed.
+_PINNED_POOL: List[tuple] = []                   # (nbytes, address)
+_PINNED_POOL_MAX_BYTES = 2 << 30
+
+
 def _pinned(nbytes: int) -> np.ndarray:
-    p = lib().pcl_host_alloc(int(nbytes))
+    nbytes = int(nbytes)
+    best = None
+    for k, (sz, _p) in enumerate(_PINNED_POOL):
+        if nbytes <= sz <= 2 * nbytes + (1 << 20) and (best is None or sz < _PINNED_POOL[best][0]):
+            best = k
+    if best is not None:
+        sz, p = _PINNED_POOL.pop(best)
+    else:
+        sz, p = nbytes, lib().pcl_host_alloc(nbytes)
+        if not p:
+            raise MemoryError(f"pinned allocation of {nbytes} bytes failed")
+    return np.frombuffer((C.c_uint8 * sz).from_address(p), dtype=np.uint8), p
+
+
+def _unpin(arr: np.ndarray, p: int) -> None:
     if not p:
-        raise MemoryError(f"pinned allocation of {nbytes} bytes failed")
-    return np.frombuffer((C.c_uint8 * int(nbytes)).from_address(p), dtype=np.uint8), p
+        return
+    if sum(sz for sz, _ in _PINNED_POOL) + len(arr) <= _PINNED_POOL_MAX_BYTES:
+        _PINNED_POOL.append((len(arr), p))
+    else:
+        lib().pcl_host_free(p)
+
+
+def release_pinned_pool() -> None:
+    while _PINNED_POOL:
+        lib().pcl_host_free(_PINNED_POOL.pop()[1])
 
 
 class GzSource:
@@ -102,13 +130,13 @@ class TextSource:
         self.pending = None
 
     def _alloc(self, size: int) -> None:
-        self.size = int(size)
-        self.reserve = self.size // 2
         self.bufs, self.ptrs = [], []
         for _ in range(2):
-            a, p = _pinned(self.size)
+            a, p = _pinned(int(size))
             self.bufs.append(a)
             self.ptrs.append(p)
+        self.size = min(len(a) for a in self.bufs)       # a block out of the pool may be larger than asked for
+        self.reserve = self.size // 2
 
     def close(self) -> None:
         if self.pending is not None:
@@ -120,8 +148,8 @@ class TextSource:
         if self.fh is not None:
             self.fh.close()
             self.fh = None
-        for p in self.ptrs:
-            lib().pcl_host_free(p)
+        for a, p in zip(self.bufs, self.ptrs):
+            _unpin(a, p)
         self.ptrs, self.bufs = [], []
 
     def _read_into(self, which: int, offset: int, want: int) -> int:
@@ -194,15 +222,101 @@ class TextSource:
         need = tail + got
         fresh = np.concatenate([cur[lo:self.end], other[self.reserve:self.reserve + got]])
         if need > self.size - self.size // 2:
-            old = self.ptrs
+            old = list(zip(self.bufs, self.ptrs))
             self._alloc(4 * max(need, self.cap))
-            for p in old:
-                lib().pcl_host_free(p)
+            for a, p in old:
+                _unpin(a, p)
             self.cur = 0
         else:
             self.cur = 1 - self.cur
         self.bufs[self.cur][self.reserve - 0:self.reserve + need] = fresh
         self.start, self.end = self.reserve, self.reserve + need
+
+
+class _Done:
+    """Stands in for the future of a prefetch that needs no I/O."""
+    def result(self):
+        return 0
+
+
+class MmapSource:
+    """The files of one read as windows of their memory maps: uncompressed files that end in a newline need no staging
+    copy at all - the device copy reads the page cache (pageable memory) directly.  Same interface as TextSource; a
+    window never spans two files (the chunk at a file boundary is simply shorter)."""
+
+    def __init__(self, paths: Sequence[str], block_bytes: int):
+        import mmap
+        self.paths = list(paths)
+        self.maps, self.views = [], []
+        for p in self.paths:
+            fh = open(p, "rb")
+            try:
+                m = mmap.mmap(fh.fileno(), 0, access=mmap.ACCESS_READ)
+            finally:
+                fh.close()
+            self.maps.append(m)
+            self.views.append(np.frombuffer(m, dtype=np.uint8))
+        self.k = 0
+        self.start = self.end = 0
+        self.pending = None
+        self._want = 0
+        self.cap = int(block_bytes)
+        self.eof = False                         # like TextSource: set by the advance that found nothing left to add
+
+    @staticmethod
+    def eligible(paths: Sequence[str]) -> bool:
+        if not paths:
+            return False
+        for p in paths:
+            try:
+                with open(p, "rb") as fh:
+                    head = fh.read(2)
+                    size = os.fstat(fh.fileno()).st_size
+                    if size == 0 or head == b"\x1f\x8b" or p.endswith(".zst"):
+                        return False
+                    fh.seek(size - 1)
+                    if fh.read(1) != b"\n":
+                        return False
+            except OSError:
+                return False
+        return True
+
+    def bytes_per_record(self, default: float) -> float:
+        """Mean size of the first (up to 64) records of the first file."""
+        head = self.views[0][:1 << 16]
+        nl = np.flatnonzero(head == 10)
+        k = min(len(nl) // 4, 64)
+        return float(nl[4 * k - 1] + 1) / k if k else float(default)
+
+
+    def block(self) -> np.ndarray:
+        return self.views[self.k][self.start:self.end]
+
+    def prefetch(self, pool, want: int) -> None:
+        assert self.pending is None
+        self._want = max(0, int(want))
+        self.pending = _Done()
+
+    def advance(self, used: int) -> None:
+        want, self._want, self.pending = (self._want if self.pending is not None else 0), 0, None
+        self.start += int(used)
+        size = len(self.views[self.k])
+        if self.k + 1 >= len(self.views) and self.end >= size:
+            self.eof = True
+        if self.start >= size and self.k + 1 < len(self.views):          # this file is consumed: on to the next one
+            self.k += 1
+            self.start = self.end = 0
+            size = len(self.views[self.k])
+        self.end = min(size, max(self.end, self.start) + want)
+
+    def close(self) -> None:
+        self.views = []
+        for m in self.maps:
+            try:
+                m.close()
+            except BufferError:                  # a view is still referenced somewhere: the map goes with it
+                pass
+        self.maps = []
 
 
 class TextGroupReader:
@@ -216,7 +330,14 @@ class TextGroupReader:
         guess = list(bytes_per_record) if bytes_per_record is not None else [400] * self.n_reads
         self.bpr = [float(g) for g in guess]
         self.pool = ThreadPoolExecutor(max_workers=max(1, self.n_reads))
-        self.sources = [TextSource(f, int(self.target * b * 1.25) + (1 << 16)) for f, b in zip(files_per_read, self.bpr)]
+        self.sources = []
+        for r, f in enumerate(files_per_read):
+            if MmapSource.eligible(f):
+                src = MmapSource(f, 0)
+                self.bpr[r] = src.bytes_per_record(self.bpr[r])          # measured on the first records, not guessed
+            else:
+                src = TextSource(f, int(self.target * self.bpr[r] * 1.25) + (1 << 16))
+            self.sources.append(src)
         self.first = True
         self.records = 0
 

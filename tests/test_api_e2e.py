@@ -385,3 +385,46 @@ def test_update_read_verifies_a_sample_on_the_device(dataset, tmp_path, caplog):
         res = bad._verify(bad.sequence_spec["R1"], 2000)
     assert res["percent_valid"] < 10.0
     assert any("low percentage of valid records" in m for m in caplog.messages)
+
+
+def test_make_fastq_auto_writer_falls_back_to_the_host_path(dataset, tmp_path, monkeypatch):
+    """writer="auto": input the device parser rejects (blank lines between records: the host reader skips them) and input
+    that does not fit the device budget take the host path; writer="device" reports why it does not apply."""
+    from precellar_b200 import Assay, _ffi, _zstd
+    from precellar_b200.api import make_fastq
+    td = dataset["td"]
+    spec = write_spec(td, None, None, forward_insert=True)
+    full, n = dataset["full"], 400
+    r1, r2 = str(tmp_path / "R1_blank.fq"), str(tmp_path / "R2_blank.fq")
+    for path, names, b in ((r1, dataset["names1"], full[0]), (r2, dataset["names2"], full[1])):
+        with open(path, "wb") as fh:
+            for i in range(n):
+                L = int(b.length[i])
+                fh.write(b"@" + names[i] + b"\n" + b.seq[i, :L].tobytes() + b"\n+\n" + b.qual[i, :L].tobytes() + b"\n")
+                if i % 7 == 3:
+                    fh.write(b"\n")                                   # stray blank line
+    outs = {}
+    for writer in ("host", "auto"):
+        a = Assay(spec)
+        a.update_read("R1", fastq=r1, min_len=34, max_len=34)
+        a.update_read("R2", fastq=r2, min_len=40, max_len=60)
+        out = str(tmp_path / writer)
+        make_fastq(a, modality="rna", out_dir=out, correct_barcode=True, writer=writer)
+        outs[writer] = _zstd.decompress_file(os.path.join(out, "R1.fq.zst"))
+    assert outs["host"] == outs["auto"] and outs["host"].count(b"\n") > 400
+    a = Assay(spec)
+    a.update_read("R1", fastq=r1, min_len=34, max_len=34)
+    a.update_read("R2", fastq=r2, min_len=40, max_len=60)
+    with pytest.raises(_ffi.PclError):
+        make_fastq(a, modality="rna", out_dir=str(tmp_path / "dev"), correct_barcode=True, writer="device")
+    # device budget of 1 KB: the text cannot stay resident
+    monkeypatch.setenv("PCL_API_RESIDENT_BYTES", "1024")
+    b = Assay(spec)
+    b.update_read("R1", fastq=[os.path.join(td, "R1_a.fq.gz"), os.path.join(td, "R1_b.fq")])
+    b.update_read("R2", fastq=os.path.join(td, "R2.fq.gz"))
+    with pytest.raises(RuntimeError, match="device writer does not apply"):
+        make_fastq(b, modality="rna", out_dir=str(tmp_path / "dev2"), correct_barcode=True, writer="device")
+    make_fastq(b, modality="rna", out_dir=str(tmp_path / "auto2"), correct_barcode=True, writer="auto")
+    monkeypatch.delenv("PCL_API_RESIDENT_BYTES")
+    make_fastq(b, modality="rna", out_dir=str(tmp_path / "ref2"), correct_barcode=True, writer="host")
+    assert _zstd.decompress_file(str(tmp_path / "auto2" / "R1.fq.zst")) == _zstd.decompress_file(str(tmp_path / "ref2" / "R1.fq.zst"))

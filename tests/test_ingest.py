@@ -265,3 +265,43 @@ def test_text_source_reassembles_the_byte_stream(tmp_path, monkeypatch, seed):
     finally:
         src.close()
         pool.shutdown()
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_mmap_source_walks_plain_files_without_copies(tmp_path, seed):
+    """MmapSource: windows of the file maps, never spanning two files; only for uncompressed files that end in a newline."""
+    from precellar_b200 import textingest
+    rng = np.random.default_rng(seed)
+    parts = [text_of(make_records(int(rng.integers(200, 1500)))) for _ in range(3)]
+    paths = []
+    for k, data in enumerate(parts):
+        p = str(tmp_path / f"m{k}.fq")
+        open(p, "wb").write(data)
+        paths.append(p)
+    assert textingest.MmapSource.eligible(paths)
+    open(str(tmp_path / "nonl.fq"), "wb").write(parts[0][:-1])
+    open(str(tmp_path / "z.fq.gz"), "wb").write(gzip.compress(parts[0]))
+    open(str(tmp_path / "empty.fq"), "wb").close()
+    for bad in ("nonl.fq", "z.fq.gz", "empty.fq"):
+        assert not textingest.MmapSource.eligible([paths[0], str(tmp_path / bad)])
+    src = textingest.MmapSource(paths, 0)
+    assert abs(src.bytes_per_record(0.0) - len(b"".join(text_of([r]) for r in make_records(64))) / 64) < 1e-9
+    got = bytearray()
+    try:
+        src.prefetch(None, 5000)
+        src.advance(0)
+        for _ in range(100000):
+            blk = src.block()
+            if len(blk) == 0 and src.eof:
+                break
+            u = rng.random()
+            used = len(blk) if u < 0.4 else int(rng.integers(0, len(blk) + 1))
+            got += blk[:used].tobytes()
+            src.prefetch(None, int(rng.integers(0, 20000)))
+            src.advance(used)
+        else:
+            raise AssertionError("the source did not reach the end of its input")
+        assert bytes(got) == b"".join(parts)
+    finally:
+        del blk
+        src.close()

@@ -4,8 +4,9 @@ Bench tooling (bench.py `api_e2e`).  The workload is the 10x scATAC shape of BAS
 the neg strand, R1 / R2 = 50 nt gDNA, 737 K whitelist) because make_fastq needs a pos-strand insert: on 10x v3 (configs[0])
 `record.read1.unwrap()` panics in the reference (python/src/lib.rs:160) and raises here.
 
-  ours        precellar_b200.api.make_fastq (python/src/lib.rs:117-171): host decode -> H2D -> count -> all-reduce -> correct
-              -> D2H -> host record assembly -> zstd (level 9, 8 threads)
+  ours        precellar_b200.api.make_fastq (python/src/lib.rs:117-171), device writer: FASTQ text -> H2D -> parse on the GPU
+              -> count -> all-reduce -> correct -> records assembled in HBM -> D2H -> zstd (level 9, host threads), or with
+              compression="device" zstd frames built on the GPU -> D2H -> file
   reference   the oracle's file-level driver: FASTQ parse (one thread per file) -> serial count pass -> parallel annotate
               -> the record loop of make_fastq -> zstd (level 9, 8 workers)       [the CPU restatement, kind "port"]
 Both arms write the same bytes (checked).
@@ -156,17 +157,33 @@ def run_reference(w, spec: str, paths: dict, out_dir: str, n_threads: int):
 
 
 def api_e2e(td: str, n: int, host_cores: int, devices=None, formats=("plain", "gzip", "bgzf")) -> dict:
+    """Per input format: make_fastq as called by default (device writer when it applies, libzstd level 9 like the
+    reference), make_fastq(compression="device") (zstd frames built on the GPU) and the CPU port, same work each."""
     w, spec, files = make_inputs(td, n)
     out = {"workload": f"{w.name}: {n} read triples, FASTQ files -> make_fastq(correct_barcode=True) -> R1.fq.zst + R2.fq.zst",
-           "unit": "read-triples/s", "formats": {}}
+           "unit": "read-triples/s", "formats": {},
+           "note": "wall clock around Assay + update_read x 3 + make_fastq; best of two runs after one warm-up; outputs compared "
+                   "after decompression with libzstd; 'device_zstd' = make_fastq(compression='device'): frames of Huffman-coded "
+                   "literals built by k_zh_blocks (larger files, no host encoder)"}
+    names = ("R1.fq.zst", "R2.fq.zst")
     for fmt in formats:
-        o_ours, o_ref = os.path.join(td, f"ours_{fmt}"), os.path.join(td, f"ref_{fmt}")
+        o_ours, o_dev, o_ref = os.path.join(td, f"ours_{fmt}"), os.path.join(td, f"dev_{fmt}"), os.path.join(td, f"ref_{fmt}")
         run_ours(spec, files[fmt], o_ours, devices)                                    # warm-up: CUDA context, page cache
         t_ours = min(run_ours(spec, files[fmt], o_ours, devices) for _ in range(2))
         t_ref, written, workers = run_reference(w, spec, files[fmt], o_ref, host_cores)
-        same = all(_digest(os.path.join(o_ours, f)) == _digest(os.path.join(o_ref, f)) for f in ("R1.fq.zst", "R2.fq.zst"))
-        out["formats"][fmt] = {"ours_s": t_ours, "ours_value": n / t_ours, "reference_s": t_ref, "reference_value": n / t_ref,
-                               "speedup": t_ref / t_ours, "records_written": written, "outputs_identical": bool(same),
-                               "input_bytes": int(sum(os.path.getsize(p) for p in files[fmt].values())),
-                               "reference_zstd_workers": workers, "reference_threads": host_cores}
+        ref_digest = [_digest(os.path.join(o_ref, f)) for f in names]
+        same = [_digest(os.path.join(o_ours, f)) for f in names] == ref_digest
+        row = {"ours_s": t_ours, "ours_value": n / t_ours, "reference_s": t_ref, "reference_value": n / t_ref,
+               "speedup": t_ref / t_ours, "records_written": written, "outputs_identical": bool(same),
+               "input_bytes": int(sum(os.path.getsize(p) for p in files[fmt].values())),
+               "out_bytes": [os.path.getsize(os.path.join(o_ours, f)) for f in names],
+               "reference_out_bytes": [os.path.getsize(os.path.join(o_ref, f)) for f in names],
+               "reference_zstd_workers": workers, "reference_threads": host_cores}
+        if devices is None or len(devices) == 1:
+            run_ours(spec, files[fmt], o_dev, devices, compression="device")
+            t_dev = min(run_ours(spec, files[fmt], o_dev, devices, compression="device") for _ in range(2))
+            row["device_zstd"] = {"ours_s": t_dev, "ours_value": n / t_dev, "speedup": t_ref / t_dev,
+                                  "out_bytes": [os.path.getsize(os.path.join(o_dev, f)) for f in names],
+                                  "outputs_identical": bool([_digest(os.path.join(o_dev, f)) for f in names] == ref_digest)}
+        out["formats"][fmt] = row
     return out
