@@ -776,8 +776,13 @@ def main():
     if rank == 0 and world == 1 and not args.no_cpu and args.api_sample > 0:
         import tempfile
         from tools import api_bench
-        with tempfile.TemporaryDirectory() as td:
-            api = api_bench.api_e2e(td, args.api_sample, host_cores)
+        try:
+            with tempfile.TemporaryDirectory() as td:
+                api = api_bench.api_e2e(td, args.api_sample, host_cores)
+        except Exception as exc:                 # the API leg is an extra: a failure there must not take the headline line with it
+            import traceback
+            traceback.print_exc(file=sys.stderr)
+            api = {"error": f"{type(exc).__name__}: {exc}"}
 
     if rank == 0:
         out = {

@@ -104,8 +104,12 @@ def _as_assays(assay) -> List[Assay]:
     return [a if isinstance(a, Assay) else Assay(os.fspath(a)) for a in items]
 
 
-class DeviceWriterUnfit(RuntimeError):
-    """make_fastq's device writer does not apply to this input (raised before anything was written)."""
+# chunk_size make_fastq hands to gen_barcoded_fastq (python/src/lib.rs:133: 1000000 bases); tests lower it together with
+# MIN_CHUNK_RECORDS to run the writers over several chunks
+MAKE_FASTQ_CHUNK_BASES = 1_000_000
+
+# What the last make_fastq of this process did: {"writer": "device" | "host", "compression": ..., "streamed_chunks": n}
+LAST_RUN: dict = {}
 
 
 class FastqProcessor:
@@ -198,7 +202,6 @@ class FastqProcessor:
                 pipe.profile_enable(True)
             try:
                 if emit is not None:
-                    self._check_device_writer_budget(pipe)
                     for got in self._emit_assay(pipe, layout, correct_barcode, chunk_size, emit):
                         yield layout, pipe, None, got
                 for text, results in (() if emit is not None else self._run_assay(pipes, layout, correct_barcode, chunk_size)):
@@ -428,32 +431,48 @@ class FastqProcessor:
     def _emit_assay(self, pipe: BarcodePipeline, layout: CompiledLayout, correct_barcode: bool, chunk_size: int, emit: dict):
         """make_fastq with the device writer: the FASTQ text is parsed on the GPU and stays there (``Chunk.text_keep``),
         pass 2 corrects the resident chunks and every chunk's records are assembled - and with emit["compress"]
-        entropy-coded into zstd frames - in HBM; the host appends finished bytes to the files."""
+        entropy-coded into zstd frames - in HBM; the host appends finished bytes to the files.
+
+        Input whose text does not fit the device budget is streamed instead, the way the reference works (two reads of
+        the files, fastq.rs:183-199 then 268-331): pass 1 only counts, through one reusable chunk; pass 2 parses the files
+        again and counts each chunk against the frozen counts, corrects and emits it.  Device memory is O(chunk)."""
         from .textingest import TextGroupReader
         n_reads = len(layout.reads)
         files = [p.files for p in layout.reads]
         bases = sum((p.max_len or 100) for p in layout.reads)
         per_chunk = max(MIN_CHUNK_RECORDS, int(chunk_size) // max(bases, 1))
+        resident = self._device_writer_resident(pipe)
+        self.streamed_chunks = 0
+        bpr = [2 * (p.max_len or 150) + 80 for p in layout.reads]
         chunks: List[Chunk] = []
+        spare: Optional[Chunk] = None
         with _timed("text_reader_open"):
-            trdr = TextGroupReader(pipe, files, per_chunk, [2 * (p.max_len or 150) + 80 for p in layout.reads])
+            trdr = TextGroupReader(pipe, files, per_chunk, bpr)
         try:
             while True:
                 with _timed("chunk_create"):
-                    ch = pipe.new_chunk(per_chunk)
+                    ch = pipe.new_chunk(per_chunk) if (resident or spare is None) else spare
                 with _timed("pass1_text_parse"):
                     n = trdr.next_into(ch)
                 if n == 0:
-                    ch.close()
-                    pipe.chunks.remove(ch)
+                    if resident:
+                        ch.close()
+                        pipe.chunks.remove(ch)
+                    else:
+                        spare = ch
                     break
                 with _timed("pass1_keep_count"):
-                    for r in range(n_reads):
-                        ch.text_keep(r)
+                    if resident:
+                        for r in range(n_reads):
+                            ch.text_keep(r)
                     pipe.count(ch)
                     if self.compute_qc:
                         pipe.qc_accumulate(ch)
-                chunks.append(ch)
+                if resident:
+                    chunks.append(ch)
+                else:
+                    spare = ch
+                    self.streamed_chunks += 1
         finally:
             with _timed("text_reader_close"):
                 trdr.close()
@@ -463,17 +482,41 @@ class FastqProcessor:
         if len(totals) > 1:
             raise _ffi.PclError(_ffi.PCL_ERR_INPUT, "All whitelists should have the same total read count")
         self.num_reads = totals.pop() if totals else 0
-        if correct_barcode:
-            with _timed("pass2_correct_launch"):
-                for ch in chunks:
-                    pipe.correct(ch, self.barcode_correct_prob)
-        for ch in chunks:
-            with _timed("emit"):
-                got = ch.emit_fastq(correct_barcode, emit["paired"], emit["compress"])
-            yield got
-            with _timed("chunk_close"):
-                ch.close()
-                pipe.chunks.remove(ch)
+        if resident:
+            if correct_barcode:
+                with _timed("pass2_correct_launch"):
+                    for ch in chunks:
+                        pipe.correct(ch, self.barcode_correct_prob)
+            for ch in chunks:
+                with _timed("emit"):
+                    got = ch.emit_fastq(correct_barcode, emit["paired"], emit["compress"])
+                yield got
+                with _timed("chunk_close"):
+                    ch.close()
+                    pipe.chunks.remove(ch)
+            return
+        # streamed: the second read of the files
+        pipe.freeze_counts(True)                 # recounting a chunk must not move the counts the correction reads
+        trdr = TextGroupReader(pipe, files, per_chunk, bpr)
+        try:
+            while True:
+                with _timed("pass2_text_parse"):
+                    n = trdr.next_into(spare)
+                if n == 0:
+                    break
+                for r in range(n_reads):
+                    spare.text_keep(r)
+                pipe.count(spare)
+                if correct_barcode:
+                    pipe.correct(spare, self.barcode_correct_prob)
+                with _timed("emit"):
+                    got = spare.emit_fastq(correct_barcode, emit["paired"], emit["compress"])
+                yield got
+        finally:
+            trdr.close()
+            pipe.freeze_counts(False)
+            spare.close()
+            pipe.chunks.remove(spare)
 
     def device_writer_obstacle(self) -> Optional[str]:
         """Why make_fastq cannot assemble its output on the device for these assays (None: it can)."""
@@ -493,8 +536,8 @@ class FastqProcessor:
         self._text_estimate = est
         return None
 
-    def _check_device_writer_budget(self, pipe: BarcodePipeline) -> None:
-        """The text of all files stays on the device between the passes: refuse (DeviceWriterUnfit) what does not fit."""
+    def _device_writer_resident(self, pipe: BarcodePipeline) -> bool:
+        """Whether the text of all files may stay on the device between the passes (else the device writer streams)."""
         est = getattr(self, "_text_estimate", 0)
         fixed = self.resident_bytes if self.resident_bytes is not None else os.environ.get("PCL_API_RESIDENT_BYTES")
         if fixed not in (None, ""):
@@ -502,8 +545,7 @@ class FastqProcessor:
         else:
             free, _total = pipe.mem_info()
             budget = int(free * 0.45)
-        if est > budget:
-            raise DeviceWriterUnfit(f"about {est >> 20} MiB of FASTQ text do not fit the device budget of {budget >> 20} MiB")
+        return est <= budget
 
     def _resident_budget(self, pipe: BarcodePipeline) -> int:
         """Bytes of device memory the resident chunks of one GPU may take: `resident_bytes` (or the environment's
@@ -581,9 +623,10 @@ def make_fastq(assay, *, modality: str, out_dir, correct_barcode: bool = False, 
     (python/src/lib.rs:114-171).  Writes ``R1.fq.zst`` and, for paired-end layouts, ``R2.fq.zst``; with
     ``correct_barcode`` reads whose barcode cannot be corrected are dropped and the corrected sequence is written.
 
-    ``writer``: "device" parses the FASTQ text and assembles the output records on the GPU (one GPU, input text
-    resident on it; the stricter FASTQ dialect of the device parser: no blank lines between records), "host" reads
-    and assembles records on the host (any input size, several GPUs), "auto" picks the device writer when it applies.
+    ``writer``: "device" parses the FASTQ text and assembles the output records on the GPU (one GPU; the text stays
+    resident between the passes when it fits, else the files are read twice like the reference does; the stricter
+    FASTQ dialect of the device parser: no blank lines between records), "host" reads and assembles records on the
+    host (several GPUs), "auto" picks the device writer when it applies.
     ``compression``: "zstd" = libzstd level 9 on the host like the reference (seqspec/src/utils.rs:33-36); "device" =
     zstd frames built on the GPU (Huffman-coded literals, no matches: every zstd decoder reads them, the files are
     about 1.3-1.6 times the size of level 9) - only with the device writer.  The decompressed bytes are the same
@@ -610,10 +653,8 @@ def make_fastq(assay, *, modality: str, out_dir, correct_barcode: bool = False, 
         state = {"wrote": False}
         try:
             _make_fastq_device(proc, out_dir, correct_barcode, paired, compression == "device", state)
+            LAST_RUN.update(writer="device", compression=compression, streamed_chunks=proc.streamed_chunks)
             return
-        except DeviceWriterUnfit as e:
-            if asked_writer == "device" or compression == "device":
-                raise RuntimeError(f"make_fastq: the device writer does not apply: {e}") from e
         except (_ffi.PclError, RuntimeError) as e:
             # the device parser's FASTQ dialect is stricter than the host reader's (no blank lines between records): in
             # "auto" mode an input it rejects before anything was written gets the host path's verdict instead
@@ -621,6 +662,7 @@ def make_fastq(assay, *, modality: str, out_dir, correct_barcode: bool = False, 
             if asked_writer != "auto" or compression == "device" or state["wrote"] or code != _ffi.PCL_ERR_INPUT:
                 raise
         proc = FastqProcessor(assay, device=device, devices=devices).with_modality(modality)
+    LAST_RUN.update(writer="host", compression="zstd", streamed_chunks=0)
     # level 9 like the reference (seqspec/src/utils.rs:33-36); it asks for 8 worker threads, here every core up to 16 helps
     zt = max(1, min(16, os.cpu_count() or 8))
     w1 = _zstd.Writer(os.path.join(out_dir, "R1.fq.zst"), threads=zt)
@@ -628,7 +670,7 @@ def make_fastq(assay, *, modality: str, out_dir, correct_barcode: bool = False, 
     import ctypes as C
     L = _ffi.lib()
     try:
-        for layout, pipe, text, results in proc._gen_chunks(correct_barcode, 1_000_000):
+        for layout, pipe, text, results in proc._gen_chunks(correct_barcode, MAKE_FASTQ_CHUNK_BASES):
             n = len(text[0].batch.length)
             hr = (_ffi.HostRead * len(text))()
             keep = []
@@ -692,7 +734,7 @@ def _make_fastq_device(proc: FastqProcessor, out_dir: str, correct_barcode: bool
         if b is not None and f2 is not None:
             f2.write(b)
     try:
-        gen = proc._gen_chunks(correct_barcode, 1_000_000, emit={"paired": paired, "compress": device_zstd})
+        gen = proc._gen_chunks(correct_barcode, MAKE_FASTQ_CHUNK_BASES, emit={"paired": paired, "compress": device_zstd})
         while True:
             if device_zstd:
                 while len(pending) > 1:          # the pinned result buffers alternate: the bytes of call k live until call k + 2

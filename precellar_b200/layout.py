@@ -128,6 +128,7 @@ def layout_from_elems(reads, whitelists, modality: str = "rna") -> CompiledLayou
         slots = [slot_of[e.region_id] if e.is_barcode() else -1 for e in elems]
         plans.append(ReadPlan(r["read_id"], bool(r.get("is_reverse", False)), int(r.get("max_len", 0)), elems, slots,
                               list(r.get("files", []))))
-    wl = {k: (v if hasattr(v, "shape") else list(v)) for k, v in whitelists.items()}
+    # arrays and seqspec.OnlistItems (deduplicated, with a cached packed form) pass through; anything else is copied
+    wl = {k: (v if (hasattr(v, "shape") or getattr(v, "unique", False)) else list(v)) for k, v in whitelists.items()}
     return CompiledLayout(parse_modality(modality), plans, region_ids, wl, {k: True for k in region_ids},
                           any(e.is_umi() for p in plans for e in p.elems))

@@ -249,6 +249,7 @@ def test_make_fastq(dataset, tmp_path, monkeypatch, writer, compression, chunk_r
     from precellar_b200 import Assay, _zstd, api, compile_layout
     from precellar_b200.api import make_fastq
     monkeypatch.setattr(api, "MIN_CHUNK_RECORDS", chunk_records)
+    monkeypatch.setattr(api, "MAKE_FASTQ_CHUNK_BASES", 1_000_000 if chunk_records > 700 else 60_000)
     td = dataset["td"]
     spec = write_spec(td, None, None, forward_insert=True)           # whitelists are already on disk; only the YAML differs
     a = Assay(spec)
@@ -309,6 +310,7 @@ def test_make_fastq_paired_end_atac_like(tmp_path, monkeypatch, writer, compress
     from precellar_b200 import Assay, _zstd, api, compile_layout
     from precellar_b200.api import make_fastq
     monkeypatch.setattr(api, "MIN_CHUNK_RECORDS", chunk_records)
+    monkeypatch.setattr(api, "MAKE_FASTQ_CHUNK_BASES", 1_000_000 if chunk_records > 700 else 60_000)
     td = str(tmp_path)
     rng = np.random.default_rng(21)
     wl = U.gen_whitelist(rng, 200, 16)
@@ -340,8 +342,9 @@ def test_make_fastq_paired_end_atac_like(tmp_path, monkeypatch, writer, compress
     order = [p.read_id for p in layout0.reads]
     for r, rid in enumerate(order):
         names = [f"q{i}/{1 if rid != 'atac-R2' else 2}".encode() for i in range(n)]
-        write_fastq(os.path.join(td, rid + ".fq.gz"), names, full[r], True)
-        a.update_read(rid, fastq=os.path.join(td, rid + ".fq.gz"))
+        gz = chunk_records > 700                                   # the multi-chunk case reads plain files (memory-mapped input)
+        write_fastq(os.path.join(td, rid + (".fq.gz" if gz else ".fq")), names, full[r], gz)
+        a.update_read(rid, fastq=os.path.join(td, rid + (".fq.gz" if gz else ".fq")))
     out = os.path.join(td, "out")
     make_fastq(a, modality="atac", out_dir=out, correct_barcode=True, writer=writer, compression=compression)
     layout = compile_layout(a, "atac", require_files=True)
@@ -388,8 +391,8 @@ def test_update_read_verifies_a_sample_on_the_device(dataset, tmp_path, caplog):
 
 
 def test_make_fastq_auto_writer_falls_back_to_the_host_path(dataset, tmp_path, monkeypatch):
-    """writer="auto": input the device parser rejects (blank lines between records: the host reader skips them) and input
-    that does not fit the device budget take the host path; writer="device" reports why it does not apply."""
+    """writer="auto": input the device parser rejects (blank lines between records: the host reader skips them) takes the
+    host path, writer="device" reports the record; input that does not fit the device budget is streamed."""
     from precellar_b200 import Assay, _ffi, _zstd
     from precellar_b200.api import make_fastq
     td = dataset["td"]
@@ -417,14 +420,18 @@ def test_make_fastq_auto_writer_falls_back_to_the_host_path(dataset, tmp_path, m
     a.update_read("R2", fastq=r2, min_len=40, max_len=60)
     with pytest.raises(_ffi.PclError):
         make_fastq(a, modality="rna", out_dir=str(tmp_path / "dev"), correct_barcode=True, writer="device")
-    # device budget of 1 KB: the text cannot stay resident
-    monkeypatch.setenv("PCL_API_RESIDENT_BYTES", "1024")
+    # device budget of 1 KB: the text cannot stay resident -> the device writer streams (two reads of the files, one chunk
+    # of device memory), over several chunks here; same bytes as the host path
+    from precellar_b200 import api
+    monkeypatch.setattr(api, "MIN_CHUNK_RECORDS", 700)
+    monkeypatch.setattr(api, "MAKE_FASTQ_CHUNK_BASES", 60_000)
     b = Assay(spec)
     b.update_read("R1", fastq=[os.path.join(td, "R1_a.fq.gz"), os.path.join(td, "R1_b.fq")])
     b.update_read("R2", fastq=os.path.join(td, "R2.fq.gz"))
-    with pytest.raises(RuntimeError, match="device writer does not apply"):
-        make_fastq(b, modality="rna", out_dir=str(tmp_path / "dev2"), correct_barcode=True, writer="device")
-    make_fastq(b, modality="rna", out_dir=str(tmp_path / "auto2"), correct_barcode=True, writer="auto")
-    monkeypatch.delenv("PCL_API_RESIDENT_BYTES")
     make_fastq(b, modality="rna", out_dir=str(tmp_path / "ref2"), correct_barcode=True, writer="host")
-    assert _zstd.decompress_file(str(tmp_path / "auto2" / "R1.fq.zst")) == _zstd.decompress_file(str(tmp_path / "ref2" / "R1.fq.zst"))
+    want = _zstd.decompress_file(str(tmp_path / "ref2" / "R1.fq.zst"))
+    monkeypatch.setenv("PCL_API_RESIDENT_BYTES", "1024")
+    for k, comp in enumerate(("zstd", "device")):
+        make_fastq(b, modality="rna", out_dir=str(tmp_path / f"dev{k}"), correct_barcode=True, writer="device", compression=comp)
+        assert api.LAST_RUN["writer"] == "device" and api.LAST_RUN["streamed_chunks"] >= 7
+        assert _zstd.decompress_file(str(tmp_path / f"dev{k}" / "R1.fq.zst")) == want and len(want) > 100_000
