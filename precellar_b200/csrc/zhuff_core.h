@@ -37,6 +37,7 @@
 #define ZH_FRAME_HEADER_BYTES 14u                 // magic 4, descriptor 1, window 1, content size 8
 
 struct ZhTable {
+    uint32_t sym[256];           // code | number of bits << 16 (one shared-memory lookup per byte in the coding loops)
     uint16_t code[256];
     uint8_t nbits[256];
     uint8_t desc[72];            // Huffman_Tree_Description: header byte + packed 4-bit weights
@@ -64,6 +65,7 @@ ZH_HD_NOINLINE void zh_build_table(const uint32_t *hist, const uint16_t *rank, Z
     for (uint32_t s = 0; s < 256u; ++s) {
         t->code[s] = 0;
         t->nbits[s] = 0;
+        t->sym[s] = 0;
         if (rank[s] != 0xFFFFu) { sym[rank[s]] = (uint8_t)s; ++n; max_sym = s; }
     }
     t->ok = 0;
@@ -128,7 +130,7 @@ ZH_HD_NOINLINE void zh_build_table(const uint32_t *hist, const uint16_t *rank, Z
     uint64_t bits = 0;
     for (uint32_t s = 0; s < 256u; ++s) {
         const uint32_t L = t->nbits[s];
-        if (L) { t->code[s] = (uint16_t)next_val[L]++; bits += (uint64_t)hist[s] * L; }
+        if (L) { t->code[s] = (uint16_t)next_val[L]++; bits += (uint64_t)hist[s] * L; t->sym[s] = t->code[s] | (L << 16); }
     }
     // weights of the byte values 0 .. max_sym-1, four bits each; the weight of max_sym is deduced by the decoder
     const uint32_t n_listed = max_sym;
@@ -148,32 +150,73 @@ ZH_HD uint32_t zh_stream_begin(uint32_t n, uint32_t s) { return s * ((n + 3u) / 
 ZH_HD uint32_t zh_stream_len(uint32_t n, uint32_t s) { return s < 3u ? (n + 3u) / 4u : n - 3u * ((n + 3u) / 4u); }
 
 // A stream is written back to front (the decoder reads the bit buffer from its end): position p of the coding order
-// is byte src[len - 1 - p].  Thread t owns positions [t * per, min((t + 1) * per, len)).
-ZH_HD uint32_t zh_span_bits(const uint8_t *src, uint32_t len, uint32_t per, uint32_t tid, const uint8_t *nbits) {
-    const uint32_t lo = tid * per, hi = lo + per < len ? lo + per : len;
-    uint32_t b = 0;
-    for (uint32_t p = lo; p < hi; ++p) b += nbits[src[len - 1u - p]];
-    return b;
-}
-
+// is byte src[len - 1 - p].  Thread t owns positions [t * per, min((t + 1) * per, len)), i.e. the bytes
+// [len - min((t + 1) * per, len), len - t * per) walked downwards.  Spans that are whole 16-byte vectors (every span of
+// a full 128 KB block out of an aligned buffer) are read with 128-bit loads.
 #ifdef __CUDA_ARCH__
 #define ZH_OR(ptr, val) atomicOr((ptr), (val))
 #else
 #define ZH_OR(ptr, val) (*(ptr) |= (val))
 #endif
 
-// OR the codes of the thread's span into the zeroed bit buffer `out`, starting at bit `bitpos`
-ZH_HD void zh_span_encode(const uint8_t *src, uint32_t len, uint32_t per, uint32_t tid, const uint16_t *code, const uint8_t *nbits,
-                          uint32_t bitpos, uint32_t *out) {
+ZH_HD bool zh_span_is_vector(const uint8_t *lo_ptr, uint32_t n) { return n && (n & 15u) == 0 && (((uintptr_t)lo_ptr) & 15u) == 0; }
+
+struct ZhWord4 { uint32_t w[4]; };
+ZH_HD ZhWord4 zh_load16(const uint8_t *p) {
+#ifdef __CUDA_ARCH__
+    const uint4 v = *reinterpret_cast<const uint4 *>(p);
+    return ZhWord4{{v.x, v.y, v.z, v.w}};
+#else
+    ZhWord4 o;
+    for (int k = 0; k < 4; ++k) o.w[k] = (uint32_t)p[4 * k] | ((uint32_t)p[4 * k + 1] << 8) | ((uint32_t)p[4 * k + 2] << 16) | ((uint32_t)p[4 * k + 3] << 24);
+    return o;
+#endif
+}
+
+ZH_HD uint32_t zh_span_bits(const uint8_t *src, uint32_t len, uint32_t per, uint32_t tid, const uint32_t *sym) {
     const uint32_t lo = tid * per, hi = lo + per < len ? lo + per : len;
+    if (lo >= hi) return 0;
+    const uint8_t *base = src + (len - hi);                      // lowest byte of the span
+    const uint32_t n = hi - lo;
+    uint32_t b = 0;
+    if (zh_span_is_vector(base, n)) {
+        for (uint32_t v = 0; v < n; v += 16u) {
+            const ZhWord4 q = zh_load16(base + v);
+            for (int k = 0; k < 4; ++k)
+                b += (sym[q.w[k] & 255u] >> 16) + (sym[(q.w[k] >> 8) & 255u] >> 16) + (sym[(q.w[k] >> 16) & 255u] >> 16) + (sym[q.w[k] >> 24] >> 16);
+        }
+        return b;
+    }
+    for (uint32_t k = 0; k < n; ++k) b += sym[base[k]] >> 16;
+    return b;
+}
+
+// OR the codes of the thread's span into the zeroed bit buffer `out`, starting at bit `bitpos`
+ZH_HD void zh_span_encode(const uint8_t *src, uint32_t len, uint32_t per, uint32_t tid, const uint32_t *sym, uint32_t bitpos, uint32_t *out) {
+    const uint32_t lo = tid * per, hi = lo + per < len ? lo + per : len;
+    if (lo >= hi) return;
+    const uint8_t *base = src + (len - hi);
+    const uint32_t n = hi - lo;
     uint32_t w = bitpos >> 5, fill = bitpos & 31u;
     uint64_t acc = 0;
-    for (uint32_t p = lo; p < hi; ++p) {
-        const uint32_t s = src[len - 1u - p];
-        acc |= (uint64_t)code[s] << fill;
-        fill += nbits[s];
-        if (fill >= 32u) { ZH_OR(out + w, (uint32_t)acc); acc >>= 32; fill -= 32u; ++w; }
+#define ZH_PUT(byte_)                                                                         \
+    do {                                                                                      \
+        const uint32_t e_ = sym[(byte_)];                                                     \
+        acc |= (uint64_t)(e_ & 0xFFFFu) << fill;                                              \
+        fill += e_ >> 16;                                                                     \
+        if (fill >= 32u) { ZH_OR(out + w, (uint32_t)acc); acc >>= 32; fill -= 32u; ++w; }     \
+    } while (0)
+    if (zh_span_is_vector(base, n)) {
+        for (uint32_t v = n; v > 0; v -= 16u) {                  // downwards: the span's last byte is coded first
+            const ZhWord4 q = zh_load16(base + v - 16u);
+            for (int k = 3; k >= 0; --k) {
+                ZH_PUT(q.w[k] >> 24); ZH_PUT((q.w[k] >> 16) & 255u); ZH_PUT((q.w[k] >> 8) & 255u); ZH_PUT(q.w[k] & 255u);
+            }
+        }
+    } else {
+        for (uint32_t k = n; k > 0; --k) ZH_PUT(base[k - 1u]);
     }
+#undef ZH_PUT
     if (fill && (uint32_t)acc) ZH_OR(out + w, (uint32_t)acc);
 }
 
@@ -200,6 +243,7 @@ inline void zh_put_frame_header(uint8_t *dst, uint64_t content_bytes) {
 // Shared state of one CTA (device: __shared__; host emulation: a plain object)
 struct ZhShared {
     uint32_t hist[256];
+    uint32_t whist[ZH_THREADS / 32u][256];       // one histogram per warp: the bytes of FASTQ text collide on a handful of values
     uint16_t rank[256];
     ZhTable table;
     uint32_t span[ZH_THREADS];
@@ -218,8 +262,29 @@ struct ZhShared {
 // `ex.each(f)` runs f(tid) for the ZH_THREADS threads of the CTA and separates the phases (device: __syncthreads()).
 template <class Exec>
 ZH_HD uint32_t zh_compress_block(Exec &ex, ZhShared &sh, const uint8_t *src, uint32_t n, uint32_t last, uint8_t *slot) {
-    ex.each([&](uint32_t tid) { sh.hist[tid] = 0; if (tid == 0) { sh.fail = 0; sh.table.desc_len = 0; } });
-    ex.each([&](uint32_t tid) { for (uint32_t k = tid; k < n; k += ZH_THREADS) ZH_ADD(&sh.hist[src[k]], 1u); });
+    ex.each([&](uint32_t tid) {
+        for (uint32_t k = 0; k < ZH_THREADS / 32u; ++k) sh.whist[k][tid] = 0;
+        if (tid == 0) { sh.fail = 0; sh.table.desc_len = 0; }
+    });
+    ex.each([&](uint32_t tid) {
+        uint32_t *h = sh.whist[tid >> 5];
+        const uint32_t head = (uint32_t)((16u - (((uintptr_t)src) & 15u)) & 15u);      // bytes in front of the first aligned vector
+        const uint32_t n_head = head < n ? head : n, n_vec = (n - n_head) / 16u;
+        for (uint32_t v = tid; v < n_vec; v += ZH_THREADS) {
+            const ZhWord4 q = zh_load16(src + n_head + 16u * v);
+            for (int k = 0; k < 4; ++k) {
+                ZH_ADD(&h[q.w[k] & 255u], 1u); ZH_ADD(&h[(q.w[k] >> 8) & 255u], 1u);
+                ZH_ADD(&h[(q.w[k] >> 16) & 255u], 1u); ZH_ADD(&h[q.w[k] >> 24], 1u);
+            }
+        }
+        for (uint32_t k = tid; k < n_head; k += ZH_THREADS) ZH_ADD(&h[src[k]], 1u);
+        for (uint32_t k = n_head + 16u * n_vec + tid; k < n; k += ZH_THREADS) ZH_ADD(&h[src[k]], 1u);
+    });
+    ex.each([&](uint32_t tid) {
+        uint32_t c = 0;
+        for (uint32_t k = 0; k < ZH_THREADS / 32u; ++k) c += sh.whist[k][tid];
+        sh.hist[tid] = c;
+    });
     ex.each([&](uint32_t tid) { sh.rank[tid] = (uint16_t)zh_rank(sh.hist, tid); });
     ex.each([&](uint32_t tid) {
         if (tid) return;
@@ -237,7 +302,7 @@ ZH_HD uint32_t zh_compress_block(Exec &ex, ZhShared &sh, const uint8_t *src, uin
         const uint32_t slen = zh_stream_len(n, s), per = (slen + ZH_THREADS - 1u) / ZH_THREADS;
         ex.each([&](uint32_t tid) {
             for (uint32_t k = tid; k < ZH_STREAM_CAP_WORDS; k += ZH_THREADS) sh.out[k] = 0;
-            sh.span[tid] = zh_span_bits(ssrc, slen, per, tid, sh.table.nbits);
+            sh.span[tid] = zh_span_bits(ssrc, slen, per, tid, sh.table.sym);
         });
         ex.each([&](uint32_t tid) {
             if (tid) return;
@@ -248,7 +313,7 @@ ZH_HD uint32_t zh_compress_block(Exec &ex, ZhShared &sh, const uint8_t *src, uin
         });
         if (sh.fail) break;
         const uint32_t bits = sh.stream_bits, bytes = bits / 8u + 1u;
-        ex.each([&](uint32_t tid) { zh_span_encode(ssrc, slen, per, tid, sh.table.code, sh.table.nbits, sh.span[tid], sh.out); });
+        ex.each([&](uint32_t tid) { zh_span_encode(ssrc, slen, per, tid, sh.table.sym, sh.span[tid], sh.out); });
         ex.each([&](uint32_t tid) { if (tid == 0) sh.out[bits >> 5] |= 1u << (bits & 31u); });     // end mark above the last code
         ex.each([&](uint32_t tid) {
             const uint8_t *ob = reinterpret_cast<const uint8_t *>(sh.out);

@@ -386,7 +386,12 @@ struct EmuExec {
 extern "C" {
 
 // src[0..n) -> one zstd frame (header + blocks) in dst; returns its size or -1 when dst is too small
-int64_t emu_zh_frame(const uint8_t *src, uint64_t n, uint8_t *dst, uint64_t cap, uint64_t *n_raw_blocks) {
+// `shift` (0..63): the input is compressed from a copy that starts `shift` bytes behind a 64-byte boundary, so that both
+// the 128-bit-load route (shift 0) and the byte route of the span loops are reachable from the tests
+int64_t emu_zh_frame(const uint8_t *src_in, uint64_t n, uint8_t *dst, uint64_t cap, uint64_t *n_raw_blocks, uint32_t shift) {
+    std::vector<uint8_t> copy(n + 192);
+    uint8_t *src = copy.data() + ((64 - ((uintptr_t)copy.data() & 63)) & 63) + (shift & 63);
+    if (n) memcpy(src, src_in, n);
     const uint64_t n_blocks = n ? (n + ZH_BLOCK_BYTES - 1) / ZH_BLOCK_BYTES : 1;
     if (cap < ZH_FRAME_HEADER_BYTES + n_blocks * (uint64_t)ZH_SLOT_BYTES) return -1;
     zh_put_frame_header(dst, n);

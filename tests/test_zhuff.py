@@ -11,14 +11,16 @@ from precellar_b200 import _zstd
 from tests import util as U
 
 
-def zh_frame(data: bytes):
+def zh_frame(data: bytes, shift: int = 0):
+    """`shift` = 0: the input starts on a 64-byte boundary (the span loops take the 128-bit-load route, as in the CUDA
+    kernels whose buffers are aligned); any other value: the byte route."""
     L = U.emul_lib()
     L.emu_zh_frame.restype = C.c_int64
-    L.emu_zh_frame.argtypes = [C.c_char_p, C.c_uint64, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64)]
+    L.emu_zh_frame.argtypes = [C.c_char_p, C.c_uint64, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64), C.c_uint32]
     cap = 14 + (len(data) // 131072 + 2) * (131072 + 16)
     out = C.create_string_buffer(cap)
     raw = C.c_uint64(0)
-    n = L.emu_zh_frame(data, len(data), out, cap, C.byref(raw))
+    n = L.emu_zh_frame(data, len(data), out, cap, C.byref(raw), shift)
     assert n > 0
     return out.raw[:n], raw.value
 
@@ -39,6 +41,7 @@ def test_fastq_text_round_trip(n_records):
     data = fastq_text(rng, n_records)
     frame, raw_blocks = zh_frame(data)
     assert _zstd.decompress(frame) == data
+    assert zh_frame(data, shift=5)[0] == frame                           # vector and byte routes of the span loops agree
     if len(data) >= 4096:
         assert raw_blocks == 0 and len(frame) < 0.7 * len(data)          # order-0 coding of FASTQ text
 
@@ -50,6 +53,7 @@ def test_exact_block_multiples_and_ragged_tails():
         data = base[:n]
         frame, _ = zh_frame(data)
         assert _zstd.decompress(frame) == data, n
+        assert zh_frame(data, shift=1 + n % 15)[0] == frame, n
 
 
 def test_incompressible_and_degenerate_blocks_are_stored_raw():
