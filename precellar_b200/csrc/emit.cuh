@@ -7,8 +7,9 @@
 //   k_emit_plan     thread per read group: drop / error decision, bytes of its R1 and R2 records
 //   (device_scan)   byte offset of every record
 //   k_emit_fill     warp per read group: the record bytes, lanes striding over each copied piece
-//   k_zh_blocks     CTA per 128 KB of output: histogram -> length-limited Huffman code -> four bit streams -> one
-//                   zstd block in the block's slot
+//   k_zh_blocks     CTA per 128 KB of output: matches of every line against the same line of the previous record ->
+//                   literal bytes -> histogram -> length-limited Huffman code -> four bit streams; the matches as
+//                   FSE-coded sequences -> one zstd block in the block's slot
 //   k_zh_compact    CTA per block: slots -> one contiguous stream of blocks behind the room for the frame header
 #ifndef PCL_EMIT_CUH
 #define PCL_EMIT_CUH
@@ -97,6 +98,7 @@ struct ZhJob {
     uint32_t *sizes;                 // bytes used in each slot
     uint8_t *stream;                 // contiguous blocks (k_zh_compact)
     unsigned long long *total;       // bytes of the stream
+    ZhScratch *scratch;              // one per block (match finder, literal buffer, sequence bits); NULL: literals only
     uint32_t n_blocks;
 };
 struct ZhParams { ZhJob job[2]; };
@@ -105,8 +107,10 @@ struct ZhDevExec {
     template <class F> __device__ __forceinline__ void each(F f) { f(threadIdx.x); __syncthreads(); }
 };
 
+// dynamic shared memory: sizeof(ZhShared) (about 72 KB: bit buffer, per-warp histograms, code table, per-sequence codes)
 __global__ void __launch_bounds__(ZH_THREADS) k_zh_blocks(const __grid_constant__ ZhParams p) {
-    __shared__ ZhShared sh;
+    extern __shared__ __align__(16) unsigned char zh_smem[];
+    ZhShared &sh = *reinterpret_cast<ZhShared *>(zh_smem);
     uint32_t b = blockIdx.x;
     const int f = b >= p.job[0].n_blocks ? 1 : 0;
     if (f) b -= p.job[0].n_blocks;
@@ -114,7 +118,8 @@ __global__ void __launch_bounds__(ZH_THREADS) k_zh_blocks(const __grid_constant_
     const uint64_t lo = (uint64_t)b * ZH_BLOCK_BYTES;
     const uint32_t len = (uint32_t)(j.n - lo < ZH_BLOCK_BYTES ? j.n - lo : ZH_BLOCK_BYTES);
     ZhDevExec ex;
-    const uint32_t used = zh_compress_block(ex, sh, j.src + lo, len, b + 1u == j.n_blocks ? 1u : 0u, j.slots + (uint64_t)b * ZH_SLOT_BYTES);
+    const uint32_t used = zh_compress_block(ex, sh, j.scratch ? j.scratch + b : nullptr, j.src + lo, len, b + 1u == j.n_blocks ? 1u : 0u,
+                                            j.slots + (uint64_t)b * ZH_SLOT_BYTES);
     if (threadIdx.x == 0) j.sizes[b] = used;
 }
 

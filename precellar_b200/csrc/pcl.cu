@@ -119,6 +119,7 @@ struct EmitStage {
     uint64_t raw_cap[2] = {0, 0};
     uint8_t *d_slots[2] = {nullptr, nullptr}, *d_stream[2] = {nullptr, nullptr};
     uint32_t *d_bsize[2] = {nullptr, nullptr};
+    ZhScratch *d_scratch[2] = {nullptr, nullptr};
     uint64_t block_cap[2] = {0, 0};
     uint8_t *h_out[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};     // [flip][file]
     uint64_t h_cap[2][2] = {{0, 0}, {0, 0}};
@@ -181,6 +182,7 @@ struct pcl_ctx {
     bool reduce_slots = false;          // PCL_REDUCE_SLOTS=1: all-reduce the whole slot array instead of the occupied slots
     bool no_plan_geo = false;           // PCL_NO_PLAN_GEO=1: AnchorPlan layouts always run the run-time geometry (tests compare the two)
     bool no_nbits = false;              // PCL_NO_NBITS=1: no partial-key bitmaps in front of the neighbourhood tables
+    bool zh_no_match = false;           // PCL_ZH_NO_MATCH=1: the device zstd coder emits literals only (no sequences; experiments)
 };
 
 struct ReadBuf {
@@ -234,6 +236,7 @@ namespace {
 void emit_stage_free(EmitStage &e) {
     for (int f = 0; f < 2; ++f) {
         cudaFree(e.d_sz[f]); cudaFree(e.d_off[f]); cudaFree(e.d_raw[f]); cudaFree(e.d_slots[f]); cudaFree(e.d_stream[f]); cudaFree(e.d_bsize[f]);
+        cudaFree(e.d_scratch[f]);
         for (int k = 0; k < 2; ++k) if (e.h_out[k][f]) cudaFreeHost(e.h_out[k][f]);
     }
     cudaFree(e.d_scan_tmp); cudaFree(e.d_meta);
@@ -342,6 +345,7 @@ int pcl_ctx_create(pcl_ctx **out, int device) {
     { const char *g = getenv("PCL_NO_FAST_SPEC"); ctx->no_fast_spec = g && g[0] == '1'; }
     { const char *g = getenv("PCL_NO_NEIGHBOUR_TABLES"); ctx->no_neighbour_tables = g && g[0] == '1'; }
     { const char *g = getenv("PCL_NO_NBITS"); ctx->no_nbits = g && g[0] == '1'; }
+    { const char *g = getenv("PCL_ZH_NO_MATCH"); ctx->zh_no_match = g && g[0] == '1'; }
     { const char *g = getenv("PCL_NO_PLAN_GEO"); ctx->no_plan_geo = g && g[0] == '1'; }
     { const char *g = getenv("PCL_TIMELINE"); ctx->timeline = g && g[0] == '1'; }
     { const char *g = getenv("PCL_REDUCE_SLOTS"); ctx->reduce_slots = g && g[0] == '1'; }
@@ -1166,6 +1170,28 @@ int pcl_text_keep(pcl_chunk *c, int read_slot) {
     return PCL_OK;
 }
 
+// k_zh_blocks takes more than the 48 KB of shared memory a kernel gets without asking
+static int zh_kernel_ready(pcl_ctx *ctx) {
+    static bool done[64] = {false};
+    if (ctx->device < 64 && done[ctx->device]) return PCL_OK;
+    CU(ctx, cudaFuncSetAttribute(k_zh_blocks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ZhShared)));
+    if (ctx->device < 64) done[ctx->device] = true;
+    return PCL_OK;
+}
+
+// slots, block stream, sizes and per-block scratch of file f for nb blocks
+static int zh_reserve_blocks(pcl_ctx *ctx, EmitStage &e, int f, uint64_t nb) {
+    cudaFree(e.d_slots[f]); cudaFree(e.d_stream[f]); cudaFree(e.d_bsize[f]); cudaFree(e.d_scratch[f]);
+    e.d_slots[f] = e.d_stream[f] = nullptr; e.d_bsize[f] = nullptr; e.d_scratch[f] = nullptr; e.block_cap[f] = 0;
+    const uint64_t cap = nb + nb / 8 + 8;
+    CU(ctx, cudaMalloc((void **)&e.d_slots[f], cap * ZH_SLOT_BYTES));
+    CU(ctx, cudaMalloc((void **)&e.d_stream[f], cap * ZH_SLOT_BYTES));
+    CU(ctx, cudaMalloc((void **)&e.d_bsize[f], cap * 4));
+    CU(ctx, cudaMalloc((void **)&e.d_scratch[f], cap * sizeof(ZhScratch)));
+    e.block_cap[f] = cap;
+    return PCL_OK;
+}
+
 static int emit_reserve(pcl_ctx *ctx, void **p, uint64_t *cap, uint64_t need, bool pinned) {
     if (need <= *cap && *p) return PCL_OK;
     if (*p) { if (pinned) cudaFreeHost(*p); else cudaFree(*p); }
@@ -1264,22 +1290,18 @@ int pcl_emit_fastq(pcl_chunk *c, int correct_barcode, int paired, int compress, 
         for (int f = 0; f < nf; ++f) {
             const uint64_t nb = (raw[f] + ZH_BLOCK_BYTES - 1) / ZH_BLOCK_BYTES;
             if (nb > e.block_cap[f]) {
-                cudaFree(e.d_slots[f]); cudaFree(e.d_stream[f]); cudaFree(e.d_bsize[f]);
-                e.d_slots[f] = e.d_stream[f] = nullptr; e.d_bsize[f] = nullptr; e.block_cap[f] = 0;
-                const uint64_t cap = nb + nb / 8 + 8;
-                CU(ctx, cudaMalloc((void **)&e.d_slots[f], cap * ZH_SLOT_BYTES));
-                CU(ctx, cudaMalloc((void **)&e.d_stream[f], cap * ZH_SLOT_BYTES));
-                CU(ctx, cudaMalloc((void **)&e.d_bsize[f], cap * 4));
-                e.block_cap[f] = cap;
+                if (int r = zh_reserve_blocks(ctx, e, f, nb)) return r;
             }
             ZhJob &j = zp.job[f];
             j.src = e.d_raw[f]; j.n = raw[f]; j.slots = e.d_slots[f]; j.sizes = e.d_bsize[f]; j.stream = e.d_stream[f];
+            j.scratch = ctx->zh_no_match ? nullptr : e.d_scratch[f];
             j.total = e.d_meta + 3 + f; j.n_blocks = (uint32_t)nb;
             total_blocks += (uint32_t)nb;
         }
         if (total_blocks) {
             prof_begin(ctx, s, PCL_K_ZSTD);
-            k_zh_blocks<<<total_blocks, ZH_THREADS, 0, s>>>(zp);
+            if (int r = zh_kernel_ready(ctx)) return r;
+            k_zh_blocks<<<total_blocks, ZH_THREADS, sizeof(ZhShared), s>>>(zp);
             k_zh_compact<<<total_blocks, ZH_THREADS, 0, s>>>(zp);
             prof_end(ctx, s);
             ctx->launches += 1;
@@ -1328,22 +1350,18 @@ int pcl_zstd_frame(pcl_ctx *ctx, const uint8_t *src, uint64_t n, uint8_t *dst, u
     }
     if (int r = emit_reserve(ctx, (void **)&e.d_raw[0], &e.raw_cap[0], n + 16, false)) return r;
     if (nb > e.block_cap[0]) {
-        cudaFree(e.d_slots[0]); cudaFree(e.d_stream[0]); cudaFree(e.d_bsize[0]);
-        e.d_slots[0] = e.d_stream[0] = nullptr; e.d_bsize[0] = nullptr; e.block_cap[0] = 0;
-        const uint64_t bcap = nb + nb / 8 + 8;
-        CU(ctx, cudaMalloc((void **)&e.d_slots[0], bcap * ZH_SLOT_BYTES));
-        CU(ctx, cudaMalloc((void **)&e.d_stream[0], bcap * ZH_SLOT_BYTES));
-        CU(ctx, cudaMalloc((void **)&e.d_bsize[0], bcap * 4));
-        e.block_cap[0] = bcap;
+        if (int r = zh_reserve_blocks(ctx, e, 0, nb)) return r;
     }
     CU(ctx, cudaMemcpyAsync(e.d_raw[0], src, n, cudaMemcpyHostToDevice, s));
     ZhParams zp;
     memset(&zp, 0, sizeof zp);
     ZhJob &j = zp.job[0];
     j.src = e.d_raw[0]; j.n = n; j.slots = e.d_slots[0]; j.sizes = e.d_bsize[0]; j.stream = e.d_stream[0];
+    j.scratch = ctx->zh_no_match ? nullptr : e.d_scratch[0];
     j.total = e.d_meta + 3; j.n_blocks = (uint32_t)nb;
     prof_begin(ctx, s, PCL_K_ZSTD);
-    k_zh_blocks<<<(unsigned)nb, ZH_THREADS, 0, s>>>(zp);
+    if (int r = zh_kernel_ready(ctx)) return r;
+    k_zh_blocks<<<(unsigned)nb, ZH_THREADS, sizeof(ZhShared), s>>>(zp);
     k_zh_compact<<<(unsigned)nb, ZH_THREADS, 0, s>>>(zp);
     prof_end(ctx, s);
     ctx->launches += 1;

@@ -173,6 +173,17 @@ ZH_HD ZhWord4 zh_load16(const uint8_t *p) {
 #endif
 }
 
+// 16 bytes -> 16-bit mask of the positions holding '\n' (bit k = byte k)
+ZH_HD uint32_t zh_nl_mask16(const ZhWord4 q) {
+    uint32_t m = 0;
+    for (int k = 0; k < 4; ++k) {
+        const uint32_t x = q.w[k] ^ 0x0A0A0A0Au;
+        const uint32_t z = ~(((x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | x) & 0x80808080u;     // 0x80 where the byte was '\n'
+        m |= ((((z >> 7) * 0x01020408u) >> 24) & 0xFu) << (4 * k);
+    }
+    return m;
+}
+
 ZH_HD uint32_t zh_span_bits(const uint8_t *src, uint32_t len, uint32_t per, uint32_t tid, const uint32_t *sym) {
     const uint32_t lo = tid * per, hi = lo + per < len ? lo + per : len;
     if (lo >= hi) return 0;
@@ -240,6 +251,163 @@ inline void zh_put_frame_header(uint8_t *dst, uint64_t content_bytes) {
     for (int k = 0; k < 8; ++k) dst[6 + k] = (uint8_t)(content_bytes >> (8 * k));
 }
 
+// ------------------------------------------------------------------------------------------
+// Sequences (RFC 8878 §3.1.1.3.2): matches between a line and the line four lines earlier - in FASTQ text the same
+// line of the previous record - coded with the format's predefined FSE distributions.
+// ------------------------------------------------------------------------------------------
+#define ZH_MAX_LINES 4096u                        // lines of a block the match finder indexes (more: the block is coded without matches)
+#define ZH_MAX_SEQ (2u * ZH_MAX_LINES)            // a line yields at most a prefix and a suffix match
+#define ZH_MIN_MATCH 8u                           // shorter matches cost more (about 4.5 bytes per sequence) than their literals
+
+// Per-block scratch in global memory (the device keeps one per block of a launch; the host emulation one)
+struct ZhScratch {
+    uint32_t nl[ZH_MAX_LINES];                    // position of every '\n'
+    uint32_t cand_pos[ZH_MAX_SEQ], cand_off[ZH_MAX_SEQ];
+    uint16_t cand_len[ZH_MAX_SEQ];                // 0: no match
+    uint32_t seq_pos[ZH_MAX_SEQ + 1], seq_off[ZH_MAX_SEQ + 1];     // compacted, in text order; entry n_seq closes the block (length 0)
+    uint16_t seq_len[ZH_MAX_SEQ + 1];
+    uint32_t seq_lit[ZH_MAX_SEQ + 1];             // offset of the sequence's literal run in lit[]
+    uint8_t lit[ZH_BLOCK_BYTES + 64];             // the bytes no match covers, in text order
+};
+
+// FSE encoding table of one predefined distribution (the construction of FSE_buildCTable, RFC 8878 §4.1.1)
+struct ZhFse {
+    uint16_t state[64];          // next state, indexed by the symbol's cumulative rank
+    uint32_t delta_bits[53];     // (bits to flush << 16) - threshold
+    int32_t delta_state[53];
+    uint32_t log;
+};
+
+ZH_HD uint32_t zh_highbit(uint32_t v) {          // position of the highest set bit (v > 0)
+#ifdef __CUDA_ARCH__
+    return 31u - (uint32_t)__clz((int)v);
+#else
+    uint32_t r = 0;
+    while (v >>= 1) ++r;
+    return r;
+#endif
+}
+
+ZH_HD uint32_t zh_popc(uint32_t v) {
+#ifdef __CUDA_ARCH__
+    return (uint32_t)__popc(v);
+#else
+    uint32_t c = 0;
+    for (; v; v &= v - 1u) ++c;
+    return c;
+#endif
+}
+ZH_HD uint32_t zh_ctz(uint32_t v) {               // v > 0
+#ifdef __CUDA_ARCH__
+    return (uint32_t)__ffs((int)v) - 1u;
+#else
+    uint32_t k = 0;
+    while (!((v >> k) & 1u)) ++k;
+    return k;
+#endif
+}
+
+// length of the common run of x[0..lim) and y[0..lim) walking upwards (dir = +1) or downwards (dir = -1) from x / y;
+// eight bytes are fetched per round so that a round costs one memory latency, not eight
+ZH_HD uint32_t zh_common_run(const uint8_t *x, const uint8_t *y, uint32_t lim, int dir) {
+    uint32_t L = 0;
+    while (L + 8u <= lim) {
+        uint32_t diff = 0;
+        for (int k = 7; k >= 0; --k) {
+            const int o = dir * (int)(L + (uint32_t)k);
+            diff = (diff << 1) | (x[o] != y[o] ? 1u : 0u);
+        }
+        if (diff) {
+            uint32_t k = 0;
+            while (!((diff >> k) & 1u)) ++k;
+            return L + k;
+        }
+        L += 8u;
+    }
+    while (L < lim && x[dir * (int)L] == y[dir * (int)L]) ++L;
+    return L;
+}
+
+ZH_HD_NOINLINE void zh_fse_build(const int8_t *norm, uint32_t n_sym, uint32_t log, ZhFse *t) {
+    const uint32_t size = 1u << log, mask = size - 1u, step = (size >> 1) + (size >> 3) + 3u;
+    uint8_t spread[64];
+    uint32_t cumul[54];
+    uint32_t high = size - 1u;
+    cumul[0] = 0;
+    for (uint32_t u = 1; u <= n_sym; ++u) {
+        if (norm[u - 1] == -1) { cumul[u] = cumul[u - 1] + 1u; spread[high--] = (uint8_t)(u - 1); }
+        else cumul[u] = cumul[u - 1] + (uint32_t)norm[u - 1];
+    }
+    uint32_t pos = 0;
+    for (uint32_t sy = 0; sy < n_sym; ++sy)
+        for (int k = 0; k < norm[sy]; ++k) {
+            spread[pos] = (uint8_t)sy;
+            pos = (pos + step) & mask;
+            while (pos > high) pos = (pos + step) & mask;
+        }
+    for (uint32_t u = 0; u < size; ++u) { const uint32_t sy = spread[u]; t->state[cumul[sy]++] = (uint16_t)(size + u); }
+    uint32_t total = 0;
+    for (uint32_t sy = 0; sy < n_sym; ++sy) {
+        const int c = norm[sy];
+        if (c == 0) { t->delta_bits[sy] = ((log + 1u) << 16) - size; t->delta_state[sy] = 0; }
+        else if (c == -1 || c == 1) { t->delta_bits[sy] = (log << 16) - size; t->delta_state[sy] = (int32_t)total - 1; total += 1; }
+        else {
+            const uint32_t max_out = log - zh_highbit((uint32_t)c - 1u), min_plus = (uint32_t)c << max_out;
+            t->delta_bits[sy] = (max_out << 16) - min_plus;
+            t->delta_state[sy] = (int32_t)total - c;
+            total += (uint32_t)c;
+        }
+    }
+    t->log = log;
+}
+
+// predefined distributions of literal lengths, match lengths and offsets (RFC 8878 §3.1.1.3.2.2)
+ZH_HD_NOINLINE void zh_fse_predefined(ZhFse *ll, ZhFse *ml, ZhFse *of) {
+    const int8_t nll[36] = {4, 3, 2, 2, 2, 2, 2, 2, 2, 2, 2, 2, 2, 1, 1, 1, 2, 2, 2, 2, 2, 2, 2, 2, 2, 3, 2, 1, 1, 1, 1, 1, -1, -1, -1, -1};
+    const int8_t nml[53] = {1, 4, 3, 2, 2, 2, 2, 2, 2, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1,
+                            1, 1, 1, 1, 1, 1, 1, 1, 1, -1, -1, -1, -1, -1, -1, -1};
+    const int8_t nof[29] = {1, 1, 1, 1, 1, 1, 2, 2, 2, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, -1, -1, -1, -1, -1};
+    zh_fse_build(nll, 36, 6, ll);
+    zh_fse_build(nml, 53, 6, ml);
+    zh_fse_build(nof, 29, 5, of);
+}
+
+// code and number of extra bits of a literal length / of a match length minus 3 (ZSTD_LLcode / ZSTD_MLcode)
+ZH_HD uint32_t zh_ll_code(uint32_t v, uint32_t *bits) {
+    uint32_t c;
+    if (v < 16u) c = v;
+    else if (v < 24u) c = 16u + ((v - 16u) >> 1);
+    else if (v < 32u) c = 20u + ((v - 24u) >> 2);
+    else if (v < 48u) c = 22u + ((v - 32u) >> 3);
+    else if (v < 64u) c = 24u;
+    else c = zh_highbit(v) + 19u;
+    *bits = c < 16u ? 0u : c < 20u ? 1u : c < 22u ? 2u : c < 24u ? 3u : c == 24u ? 4u : c - 19u;
+    return c;
+}
+ZH_HD uint32_t zh_ml_code(uint32_t v, uint32_t *bits) {
+    uint32_t c;
+    if (v < 32u) c = v;
+    else if (v < 40u) c = 32u + ((v - 32u) >> 1);
+    else if (v < 48u) c = 36u + ((v - 40u) >> 2);
+    else if (v < 64u) c = 38u + ((v - 48u) >> 3);
+    else if (v < 96u) c = 40u + ((v - 64u) >> 4);
+    else if (v < 128u) c = 42u;
+    else c = zh_highbit(v) + 36u;
+    *bits = c < 32u ? 0u : c < 36u ? 1u : c < 38u ? 2u : c < 40u ? 3u : c < 42u ? 4u : c == 42u ? 5u : c - 36u;
+    return c;
+}
+
+// one step of an FSE encoder: the bits the state gives up for `sym` and the state that follows (FSE_encodeSymbol)
+ZH_HD uint32_t zh_fse_nbits(const ZhFse &t, uint32_t state, uint32_t sym) { return (state + t.delta_bits[sym]) >> 16; }
+ZH_HD uint32_t zh_fse_next(const ZhFse &t, uint32_t state, uint32_t sym) {
+    return t.state[(int32_t)(state >> zh_fse_nbits(t, state, sym)) + t.delta_state[sym]];
+}
+ZH_HD uint32_t zh_fse_first(const ZhFse &t, uint32_t sym) {       // FSE_initCState2
+    const uint32_t nb = (t.delta_bits[sym] + (1u << 15)) >> 16;
+    const uint32_t value = (nb << 16) - t.delta_bits[sym];
+    return t.state[(int32_t)(value >> nb) + t.delta_state[sym]];
+}
+
 // Shared state of one CTA (device: __shared__; host emulation: a plain object)
 struct ZhShared {
     uint32_t hist[256];
@@ -248,8 +416,14 @@ struct ZhShared {
     ZhTable table;
     uint32_t span[ZH_THREADS];
     uint32_t out[ZH_STREAM_CAP_WORDS];
+    ZhFse fse_ll, fse_ml, fse_of;
+    // per sequence: first its three codes (written by all threads), then - in place, by the one thread that walks the
+    // three state chains - the states the codes meet (minus the table size)
+    uint8_t seq_ll[ZH_MAX_SEQ], seq_ml[ZH_MAX_SEQ], seq_of[ZH_MAX_SEQ];
+    uint32_t end_ll, end_ml, end_of;             // states left after the last (text-order first) sequence
     uint32_t stream_bits;
     uint32_t fail;
+    uint32_t n_lines, n_seq, n_lit, seq_bytes, lit_bytes;
 };
 
 #ifdef __CUDA_ARCH__
@@ -258,27 +432,37 @@ struct ZhShared {
 #define ZH_ADD(ptr, val) (*(ptr) += (val))
 #endif
 
-// One block of n <= ZH_BLOCK_BYTES bytes -> block header + content in `slot` (ZH_SLOT_BYTES); returns the bytes used.
-// `ex.each(f)` runs f(tid) for the ZH_THREADS threads of the CTA and separates the phases (device: __syncthreads()).
+// exclusive scan of sh.span[] by one thread; returns nothing: sh.stream_bits receives the total
 template <class Exec>
-ZH_HD uint32_t zh_compress_block(Exec &ex, ZhShared &sh, const uint8_t *src, uint32_t n, uint32_t last, uint8_t *slot) {
+ZH_HD void zh_scan_spans(Exec &ex, ZhShared &sh) {
+    ex.each([&](uint32_t tid) {
+        if (tid) return;
+        uint32_t run = 0;
+        for (uint32_t k = 0; k < ZH_THREADS; ++k) { const uint32_t b = sh.span[k]; sh.span[k] = run; run += b; }
+        sh.stream_bits = run;
+    });
+}
+
+// Literals_Section of `n` bytes at `lit` -> dst; returns its size.  Huffman-coded in four streams when that pays, else raw.
+template <class Exec>
+ZH_HD uint32_t zh_literals_section(Exec &ex, ZhShared &sh, const uint8_t *lit, uint32_t n, uint8_t *dst) {
     ex.each([&](uint32_t tid) {
         for (uint32_t k = 0; k < ZH_THREADS / 32u; ++k) sh.whist[k][tid] = 0;
         if (tid == 0) { sh.fail = 0; sh.table.desc_len = 0; }
     });
     ex.each([&](uint32_t tid) {
         uint32_t *h = sh.whist[tid >> 5];
-        const uint32_t head = (uint32_t)((16u - (((uintptr_t)src) & 15u)) & 15u);      // bytes in front of the first aligned vector
+        const uint32_t head = (uint32_t)((16u - (((uintptr_t)lit) & 15u)) & 15u);      // bytes in front of the first aligned vector
         const uint32_t n_head = head < n ? head : n, n_vec = (n - n_head) / 16u;
         for (uint32_t v = tid; v < n_vec; v += ZH_THREADS) {
-            const ZhWord4 q = zh_load16(src + n_head + 16u * v);
+            const ZhWord4 q = zh_load16(lit + n_head + 16u * v);
             for (int k = 0; k < 4; ++k) {
                 ZH_ADD(&h[q.w[k] & 255u], 1u); ZH_ADD(&h[(q.w[k] >> 8) & 255u], 1u);
                 ZH_ADD(&h[(q.w[k] >> 16) & 255u], 1u); ZH_ADD(&h[q.w[k] >> 24], 1u);
             }
         }
-        for (uint32_t k = tid; k < n_head; k += ZH_THREADS) ZH_ADD(&h[src[k]], 1u);
-        for (uint32_t k = n_head + 16u * n_vec + tid; k < n; k += ZH_THREADS) ZH_ADD(&h[src[k]], 1u);
+        for (uint32_t k = tid; k < n_head; k += ZH_THREADS) ZH_ADD(&h[lit[k]], 1u);
+        for (uint32_t k = n_head + 16u * n_vec + tid; k < n; k += ZH_THREADS) ZH_ADD(&h[lit[k]], 1u);
     });
     ex.each([&](uint32_t tid) {
         uint32_t c = 0;
@@ -292,56 +476,284 @@ ZH_HD uint32_t zh_compress_block(Exec &ex, ZhShared &sh, const uint8_t *src, uin
         if (n < ZH_MIN_COMPRESS) return;
         zh_build_table(sh.hist, sh.rank, &sh.table);
         if (!sh.table.ok) return;
-        const uint64_t bound = 3u + 5u + sh.table.desc_len + 6u + sh.table.total_bits / 8u + 4u + 1u;
+        const uint64_t bound = 5u + sh.table.desc_len + 6u + sh.table.total_bits / 8u + 4u;
         if (bound < 3u + (uint64_t)n) sh.fail = 0;
     });
-    uint32_t pos = 3u + 5u + sh.table.desc_len + 6u;
+    uint32_t pos = 5u + sh.table.desc_len + 6u;
     uint32_t stream_bytes[4] = {0, 0, 0, 0};
     for (uint32_t s = 0; s < 4u && !sh.fail; ++s) {
-        const uint8_t *ssrc = src + zh_stream_begin(n, s);
+        const uint8_t *ssrc = lit + zh_stream_begin(n, s);
         const uint32_t slen = zh_stream_len(n, s), per = (slen + ZH_THREADS - 1u) / ZH_THREADS;
         ex.each([&](uint32_t tid) {
             for (uint32_t k = tid; k < ZH_STREAM_CAP_WORDS; k += ZH_THREADS) sh.out[k] = 0;
             sh.span[tid] = zh_span_bits(ssrc, slen, per, tid, sh.table.sym);
         });
-        ex.each([&](uint32_t tid) {
-            if (tid) return;
-            uint32_t run = 0;
-            for (uint32_t k = 0; k < ZH_THREADS; ++k) { const uint32_t b = sh.span[k]; sh.span[k] = run; run += b; }
-            sh.stream_bits = run;
-            if (run / 8u + 1u > 4u * ZH_STREAM_CAP_WORDS - 8u) sh.fail = 1;
-        });
+        zh_scan_spans(ex, sh);
+        ex.each([&](uint32_t tid) { if (tid == 0 && sh.stream_bits / 8u + 1u > 4u * ZH_STREAM_CAP_WORDS - 8u) sh.fail = 1; });
         if (sh.fail) break;
         const uint32_t bits = sh.stream_bits, bytes = bits / 8u + 1u;
         ex.each([&](uint32_t tid) { zh_span_encode(ssrc, slen, per, tid, sh.table.sym, sh.span[tid], sh.out); });
         ex.each([&](uint32_t tid) { if (tid == 0) sh.out[bits >> 5] |= 1u << (bits & 31u); });     // end mark above the last code
         ex.each([&](uint32_t tid) {
             const uint8_t *ob = reinterpret_cast<const uint8_t *>(sh.out);
-            for (uint32_t k = tid; k < bytes; k += ZH_THREADS) slot[pos + k] = ob[k];
+            for (uint32_t k = tid; k < bytes; k += ZH_THREADS) dst[pos + k] = ob[k];
         });
         stream_bytes[s] = bytes;
         pos += bytes;
     }
-    if (sh.fail) {                                 // Raw_Block
+    if (sh.fail) {                                 // Raw_Literals_Block: 3-byte header (20-bit size), the bytes
         ex.each([&](uint32_t tid) {
-            if (tid == 0) zh_put_block_header(slot, last, 0u, n);
-            for (uint32_t k = tid; k < n; k += ZH_THREADS) slot[3u + k] = src[k];
+            if (tid == 0) {
+                const uint32_t h = 0u | (3u << 2) | (n << 4);
+                dst[0] = (uint8_t)h; dst[1] = (uint8_t)(h >> 8); dst[2] = (uint8_t)(h >> 16);
+            }
+            for (uint32_t k = tid; k < n; k += ZH_THREADS) dst[3u + k] = lit[k];
         });
         return 3u + n;
     }
     ex.each([&](uint32_t tid) {
         if (tid) return;
         const uint32_t dl = sh.table.desc_len;
-        zh_put_block_header(slot, last, 2u, pos + 1u - 3u);
-        zh_put_literals_header(slot + 3, n, pos - 8u);                      // tree description + jump table + streams
-        for (uint32_t k = 0; k < dl; ++k) slot[8u + k] = sh.table.desc[k];
+        zh_put_literals_header(dst, n, pos - 5u);                           // tree description + jump table + streams
+        for (uint32_t k = 0; k < dl; ++k) dst[5u + k] = sh.table.desc[k];
         for (uint32_t k = 0; k < 3u; ++k) {
-            slot[8u + dl + 2u * k] = (uint8_t)stream_bytes[k];
-            slot[8u + dl + 2u * k + 1u] = (uint8_t)(stream_bytes[k] >> 8);
+            dst[5u + dl + 2u * k] = (uint8_t)stream_bytes[k];
+            dst[5u + dl + 2u * k + 1u] = (uint8_t)(stream_bytes[k] >> 8);
         }
-        slot[pos] = 0;                                                      // Number_of_Sequences = 0
     });
-    return pos + 1u;
+    return pos;
+}
+
+// Matches of every line against the line four lines earlier (a common prefix and a common suffix of at least ZH_MIN_MATCH
+// bytes, inside the line and its '\n'), compacted into sc.seq_*; the bytes outside the matches go to sc.lit.
+// Afterwards sh.n_seq / sh.n_lit hold the counts (n_seq = 0: lit is not filled - the caller codes the block from src).
+template <class Exec>
+ZH_HD void zh_find_matches(Exec &ex, ZhShared &sh, ZhScratch &sc, const uint8_t *src, uint32_t n) {
+    // every thread owns a slice of whole 16-byte vectors (the block starts on a 16-byte boundary whenever its buffer does)
+    const uint32_t slice = ((n + ZH_THREADS - 1u) / ZH_THREADS + 15u) & ~15u;
+    const bool vec = ((((uintptr_t)src) & 15u) == 0);
+    ex.each([&](uint32_t tid) {                                             // newlines of the thread's slice
+        const uint32_t lo = tid * slice < n ? tid * slice : n, hi = lo + slice < n ? lo + slice : n;
+        uint32_t c = 0, k = lo;
+        if (vec) for (; k + 16u <= hi; k += 16u) c += zh_popc(zh_nl_mask16(zh_load16(src + k)));
+        for (; k < hi; ++k) c += src[k] == (uint8_t)'\n';
+        sh.span[tid] = c;
+        if (tid == 0) { sh.n_seq = 0; sh.n_lit = 0; }
+    });
+    zh_scan_spans(ex, sh);
+    const uint32_t n_lines = sh.stream_bits;
+    if (n_lines < 5u || n_lines > ZH_MAX_LINES) return;
+    ex.each([&](uint32_t tid) {
+        const uint32_t lo = tid * slice < n ? tid * slice : n, hi = lo + slice < n ? lo + slice : n;
+        uint32_t at = sh.span[tid], k = lo;
+        if (vec) for (; k + 16u <= hi; k += 16u) {
+            uint32_t m = zh_nl_mask16(zh_load16(src + k));
+            while (m) { const uint32_t bit = zh_ctz(m); m &= m - 1u; sc.nl[at++] = k + bit; }
+        }
+        for (; k < hi; ++k) if (src[k] == (uint8_t)'\n') sc.nl[at++] = k;
+    });
+    const uint32_t per_line = (n_lines + ZH_THREADS - 1u) / ZH_THREADS;
+    ex.each([&](uint32_t tid) {                                             // candidates of the thread's lines, and how many
+        uint32_t c = 0;
+        const uint32_t k0 = tid * per_line, k1 = k0 + per_line < n_lines ? k0 + per_line : n_lines;
+        for (uint32_t k = k0; k < k1; ++k) {
+            uint32_t L = 0, S = 0;
+            if (k >= 4u) {
+                const uint32_t a = sc.nl[k - 1u] + 1u, e = sc.nl[k];        // line k: [a, e], e is its '\n'
+                const uint32_t b = k >= 5u ? sc.nl[k - 5u] + 1u : 0u, eb = sc.nl[k - 4u];
+                const uint32_t len_a = e - a + 1u, len_b = eb - b + 1u;
+                const uint32_t lim = (len_a < len_b ? len_a : len_b) < 65535u ? (len_a < len_b ? len_a : len_b) : 65535u;     // lengths are kept in 16 bits
+                L = zh_common_run(src + a, src + b, lim, 1);
+                S = zh_common_run(src + e, src + eb, lim - L, -1);
+                if (L < ZH_MIN_MATCH) L = 0;
+                if (S < ZH_MIN_MATCH) S = 0;
+                sc.cand_pos[2u * k] = a; sc.cand_off[2u * k] = a - b;
+                sc.cand_pos[2u * k + 1u] = e + 1u - S; sc.cand_off[2u * k + 1u] = e - eb;
+            }
+            sc.cand_len[2u * k] = (uint16_t)L;
+            sc.cand_len[2u * k + 1u] = (uint16_t)S;
+            c += (L != 0) + (S != 0);
+        }
+        sh.span[tid] = c;
+    });
+    zh_scan_spans(ex, sh);
+    const uint32_t n_seq = sh.stream_bits;
+    if (n_seq == 0) return;
+    ex.each([&](uint32_t tid) {                                             // compaction in text order
+        const uint32_t k0 = tid * per_line, k1 = k0 + per_line < n_lines ? k0 + per_line : n_lines;
+        uint32_t at = sh.span[tid];
+        for (uint32_t c = 2u * k0; c < 2u * k1; ++c)
+            if (sc.cand_len[c]) { sc.seq_pos[at] = sc.cand_pos[c]; sc.seq_off[at] = sc.cand_off[c]; sc.seq_len[at] = sc.cand_len[c]; ++at; }
+        if (tid == 0) { sc.seq_pos[n_seq] = n; sc.seq_off[n_seq] = 0; sc.seq_len[n_seq] = 0; }     // closes the last literal run
+    });
+    const uint32_t per_seq = (n_seq + 1u + ZH_THREADS - 1u) / ZH_THREADS;
+    ex.each([&](uint32_t tid) {                                             // literal bytes in front of the thread's sequences
+        const uint32_t j0 = tid * per_seq, j1 = j0 + per_seq < n_seq + 1u ? j0 + per_seq : n_seq + 1u;
+        uint32_t c = 0;
+        for (uint32_t j = j0; j < j1; ++j) c += sc.seq_pos[j] - (j ? sc.seq_pos[j - 1u] + sc.seq_len[j - 1u] : 0u);
+        sh.span[tid] = c;
+    });
+    zh_scan_spans(ex, sh);
+    ex.each([&](uint32_t tid) {                                             // where every literal run goes
+        const uint32_t j0 = tid * per_seq, j1 = j0 + per_seq < n_seq + 1u ? j0 + per_seq : n_seq + 1u;
+        uint32_t at = sh.span[tid];
+        for (uint32_t j = j0; j < j1; ++j) {
+            sc.seq_lit[j] = at;
+            at += sc.seq_pos[j] - (j ? sc.seq_pos[j - 1u] + sc.seq_len[j - 1u] : 0u);
+        }
+        if (tid == 0) { sh.n_seq = n_seq; sh.n_lit = sh.stream_bits; }
+    });
+    ex.each([&](uint32_t tid) {                                             // the bytes: a warp per run, lanes side by side
+        const uint32_t lane = tid & 31u, warp = tid >> 5;
+        for (uint32_t j = warp; j < n_seq + 1u; j += ZH_THREADS / 32u) {
+            const uint32_t from = j ? sc.seq_pos[j - 1u] + sc.seq_len[j - 1u] : 0u, run = sc.seq_pos[j] - from, at = sc.seq_lit[j];
+            for (uint32_t k = lane; k < run; k += 32u) sc.lit[at + k] = src[from + k];
+        }
+    });
+}
+
+// literal length, match length - 3 and offset + 3 of sequence j
+struct ZhSeqVal { uint32_t ll, mlb, ofb; };
+ZH_HD ZhSeqVal zh_seq_val(const ZhScratch &sc, uint32_t j) {
+    ZhSeqVal v;
+    v.ll = sc.seq_pos[j] - (j ? sc.seq_pos[j - 1u] + sc.seq_len[j - 1u] : 0u);
+    v.mlb = (uint32_t)sc.seq_len[j] - 3u;
+    v.ofb = sc.seq_off[j] + 3u;
+    return v;
+}
+
+// OR `nbits` low bits of `value` into the zeroed bit buffer at bit `at` (nbits <= 17)
+ZH_HD void zh_or_bits(uint32_t *out, uint32_t at, uint32_t value, uint32_t nbits) {
+    if (!nbits) return;
+    const uint64_t v = (uint64_t)(value & ((1u << nbits) - 1u)) << (at & 31u);
+    ZH_OR(out + (at >> 5), (uint32_t)v);
+    if ((uint32_t)(v >> 32)) ZH_OR(out + (at >> 5) + 1u, (uint32_t)(v >> 32));
+}
+
+// Sequences_Section of sc.seq_[0, n_seq) -> dst (ZSTD_encodeSequences with the predefined tables); returns its size, 0
+// when it does not fit the bit buffer.  The sequences are coded last to first; everything but the walk along the three
+// FSE state chains (a table lookup per sequence and chain, one thread) is done by all threads: the codes, the number
+// of bits every sequence contributes, and - after a scan - the bits themselves.
+template <class Exec>
+ZH_HD uint32_t zh_sequences_section(Exec &ex, ZhShared &sh, const ZhScratch &sc, uint32_t n_seq, uint8_t *dst, uint32_t dst_cap) {
+    const uint32_t hdr = n_seq < 128u ? 2u : 3u;                             // Number_of_Sequences + Symbol_Compression_Modes
+    const uint32_t per = (n_seq + ZH_THREADS - 1u) / ZH_THREADS;
+    ex.each([&](uint32_t tid) {
+        if (tid == 0) zh_fse_predefined(&sh.fse_ll, &sh.fse_ml, &sh.fse_of);
+        for (uint32_t k = tid; k < ZH_STREAM_CAP_WORDS; k += ZH_THREADS) sh.out[k] = 0;
+        for (uint32_t j = tid; j < n_seq; j += ZH_THREADS) {
+            const ZhSeqVal v = zh_seq_val(sc, j);
+            uint32_t eb;
+            sh.seq_ll[j] = (uint8_t)zh_ll_code(v.ll, &eb);
+            sh.seq_ml[j] = (uint8_t)zh_ml_code(v.mlb, &eb);
+            sh.seq_of[j] = (uint8_t)zh_highbit(v.ofb);
+        }
+    });
+    ex.each([&](uint32_t tid) {                                              // the three state chains
+        if (tid) return;
+        uint32_t j = n_seq - 1u;
+        uint32_t s_ll = zh_fse_first(sh.fse_ll, sh.seq_ll[j]), s_ml = zh_fse_first(sh.fse_ml, sh.seq_ml[j]), s_of = zh_fse_first(sh.fse_of, sh.seq_of[j]);
+        while (j-- > 0) {
+            const uint32_t c_ll = sh.seq_ll[j], c_ml = sh.seq_ml[j], c_of = sh.seq_of[j];
+            sh.seq_ll[j] = (uint8_t)(s_ll - 64u); sh.seq_ml[j] = (uint8_t)(s_ml - 64u); sh.seq_of[j] = (uint8_t)(s_of - 32u);
+            s_ll = zh_fse_next(sh.fse_ll, s_ll, c_ll);
+            s_ml = zh_fse_next(sh.fse_ml, s_ml, c_ml);
+            s_of = zh_fse_next(sh.fse_of, s_of, c_of);
+        }
+        sh.end_ll = s_ll; sh.end_ml = s_ml; sh.end_of = s_of;
+    });
+    // coding order position q <-> sequence j = n_seq - 1 - q; thread t owns positions [t * per, (t + 1) * per)
+    ex.each([&](uint32_t tid) {
+        const uint32_t q0 = tid * per < n_seq ? tid * per : n_seq, q1 = q0 + per < n_seq ? q0 + per : n_seq;
+        uint32_t bits = 0;
+        for (uint32_t q = q0; q < q1; ++q) {
+            const uint32_t j = n_seq - 1u - q;
+            const ZhSeqVal v = zh_seq_val(sc, j);
+            uint32_t ll_bits, ml_bits;
+            const uint32_t c_ll = zh_ll_code(v.ll, &ll_bits), c_ml = zh_ml_code(v.mlb, &ml_bits), c_of = zh_highbit(v.ofb);
+            bits += ll_bits + ml_bits + c_of;
+            if (q) bits += zh_fse_nbits(sh.fse_of, sh.seq_of[j] + 32u, c_of) + zh_fse_nbits(sh.fse_ml, sh.seq_ml[j] + 64u, c_ml) +
+                           zh_fse_nbits(sh.fse_ll, sh.seq_ll[j] + 64u, c_ll);
+        }
+        sh.span[tid] = bits;
+    });
+    zh_scan_spans(ex, sh);
+    const uint32_t body_bits = sh.stream_bits, total_bits = body_bits + sh.fse_ml.log + sh.fse_of.log + sh.fse_ll.log;
+    const uint32_t bytes = hdr + total_bits / 8u + 1u;
+    if (bytes + 8u > 4u * ZH_STREAM_CAP_WORDS || bytes > dst_cap) return 0;
+    ex.each([&](uint32_t tid) {
+        const uint32_t q0 = tid * per < n_seq ? tid * per : n_seq, q1 = q0 + per < n_seq ? q0 + per : n_seq;
+        uint32_t at = 8u * hdr + sh.span[tid];
+        for (uint32_t q = q0; q < q1; ++q) {
+            const uint32_t j = n_seq - 1u - q;
+            const ZhSeqVal v = zh_seq_val(sc, j);
+            uint32_t ll_bits, ml_bits;
+            const uint32_t c_ll = zh_ll_code(v.ll, &ll_bits), c_ml = zh_ml_code(v.mlb, &ml_bits), c_of = zh_highbit(v.ofb);
+            if (q) {
+                const uint32_t s_of = sh.seq_of[j] + 32u, s_ml = sh.seq_ml[j] + 64u, s_ll = sh.seq_ll[j] + 64u;
+                uint32_t nb = zh_fse_nbits(sh.fse_of, s_of, c_of);
+                zh_or_bits(sh.out, at, s_of, nb); at += nb;
+                nb = zh_fse_nbits(sh.fse_ml, s_ml, c_ml);
+                zh_or_bits(sh.out, at, s_ml, nb); at += nb;
+                nb = zh_fse_nbits(sh.fse_ll, s_ll, c_ll);
+                zh_or_bits(sh.out, at, s_ll, nb); at += nb;
+            }
+            zh_or_bits(sh.out, at, v.ll, ll_bits); at += ll_bits;
+            zh_or_bits(sh.out, at, v.mlb, ml_bits); at += ml_bits;
+            zh_or_bits(sh.out, at, v.ofb, c_of); at += c_of;
+        }
+    });
+    ex.each([&](uint32_t tid) {
+        if (tid) return;
+        uint32_t at = 8u * hdr + body_bits;                                  // the final states, then the end mark
+        zh_or_bits(sh.out, at, sh.end_ml, sh.fse_ml.log); at += sh.fse_ml.log;
+        zh_or_bits(sh.out, at, sh.end_of, sh.fse_of.log); at += sh.fse_of.log;
+        zh_or_bits(sh.out, at, sh.end_ll, sh.fse_ll.log); at += sh.fse_ll.log;
+        zh_or_bits(sh.out, at, 1u, 1u);
+        if (n_seq < 128u) sh.out[0] |= n_seq;                                // byte 1 (the modes) stays 0: predefined tables
+        else sh.out[0] |= ((n_seq >> 8) + 128u) | ((n_seq & 255u) << 8);     // n_seq <= ZH_MAX_SEQ < 0x7F00; byte 2 stays 0
+    });
+    ex.each([&](uint32_t tid) {
+        const uint8_t *ob = reinterpret_cast<const uint8_t *>(sh.out);
+        for (uint32_t k = tid; k < bytes; k += ZH_THREADS) dst[k] = ob[k];
+    });
+    return bytes;
+}
+
+// One block of n <= ZH_BLOCK_BYTES bytes -> block header + content in `slot` (ZH_SLOT_BYTES); returns the bytes used.
+// `ex.each(f)` runs f(tid) for the ZH_THREADS threads of the CTA and separates the phases (device: __syncthreads()).
+// `sc`: scratch of this block; NULL codes the block without matches.
+template <class Exec>
+ZH_HD uint32_t zh_compress_block(Exec &ex, ZhShared &sh, ZhScratch *sc, const uint8_t *src, uint32_t n, uint32_t last, uint8_t *slot) {
+    uint32_t n_seq = 0, n_lit = n;
+    const uint8_t *lit = src;
+    if (sc && n >= ZH_MIN_COMPRESS) {
+        zh_find_matches(ex, sh, *sc, src, n);
+        n_seq = sh.n_seq;
+        if (n_seq) { n_lit = sh.n_lit; lit = sc->lit; }
+    }
+    uint32_t total = 0;
+    if (n >= ZH_MIN_COMPRESS) {
+        const uint32_t lit_bytes = zh_literals_section(ex, sh, lit, n_lit, slot + 3u);
+        uint32_t seq_bytes = 1;
+        if (n_seq) seq_bytes = zh_sequences_section(ex, sh, *sc, n_seq, slot + 3u + lit_bytes, ZH_SLOT_BYTES - 3u - lit_bytes);
+        if (seq_bytes && 3u + lit_bytes + seq_bytes < 3u + n) {
+            ex.each([&](uint32_t tid) {
+                if (tid) return;
+                if (!n_seq) slot[3u + lit_bytes] = 0;                        // Number_of_Sequences = 0
+                zh_put_block_header(slot, last, 2u, lit_bytes + seq_bytes);
+            });
+            total = 3u + lit_bytes + seq_bytes;
+        }
+    }
+    if (!total) {                                  // Raw_Block
+        ex.each([&](uint32_t tid) {
+            if (tid == 0) zh_put_block_header(slot, last, 0u, n);
+            for (uint32_t k = tid; k < n; k += ZH_THREADS) slot[3u + k] = src[k];
+        });
+        total = 3u + n;
+    }
+    return total;
 }
 
 #endif  // PCL_ZHUFF_CORE_H

@@ -388,7 +388,7 @@ extern "C" {
 // src[0..n) -> one zstd frame (header + blocks) in dst; returns its size or -1 when dst is too small
 // `shift` (0..63): the input is compressed from a copy that starts `shift` bytes behind a 64-byte boundary, so that both
 // the 128-bit-load route (shift 0) and the byte route of the span loops are reachable from the tests
-int64_t emu_zh_frame(const uint8_t *src_in, uint64_t n, uint8_t *dst, uint64_t cap, uint64_t *n_raw_blocks, uint32_t shift) {
+int64_t emu_zh_frame(const uint8_t *src_in, uint64_t n, uint8_t *dst, uint64_t cap, uint64_t *n_raw_blocks, uint32_t shift, int use_matches) {
     std::vector<uint8_t> copy(n + 192);
     uint8_t *src = copy.data() + ((64 - ((uintptr_t)copy.data() & 63)) & 63) + (shift & 63);
     if (n) memcpy(src, src_in, n);
@@ -398,11 +398,12 @@ int64_t emu_zh_frame(const uint8_t *src_in, uint64_t n, uint8_t *dst, uint64_t c
     uint64_t pos = ZH_FRAME_HEADER_BYTES, raw = 0;
     std::vector<uint8_t> slot(ZH_SLOT_BYTES);
     static ZhShared sh;
+    static ZhScratch scratch;
     EmuExec ex;
     for (uint64_t b = 0; b < n_blocks; ++b) {
         const uint64_t lo = b * ZH_BLOCK_BYTES;
         const uint32_t len = (uint32_t)(n - lo < ZH_BLOCK_BYTES ? n - lo : ZH_BLOCK_BYTES);
-        const uint32_t used = zh_compress_block(ex, sh, src + lo, len, b + 1 == n_blocks, slot.data());
+        const uint32_t used = zh_compress_block(ex, sh, use_matches ? &scratch : nullptr, src + lo, len, b + 1 == n_blocks, slot.data());
         raw += ((slot[0] >> 1) & 3u) == 0;
         memcpy(dst + pos, slot.data(), used);
         pos += used;

@@ -6,7 +6,7 @@ import numpy as np
 import pytest
 
 from precellar_b200 import _ffi, _zstd
-from tests.test_zhuff import fastq_text, zh_frame
+from tests.test_zhuff import fastq_text, illumina_text, zh_frame
 
 pytestmark = pytest.mark.gpu
 
@@ -36,13 +36,16 @@ def test_frames_equal_the_emulation_and_decode(ctx):
     noise = rng.integers(0, 256, 300000, dtype=np.uint8).tobytes()
     w = 2.0 ** (-0.9 * np.arange(40))
     skew = rng.choice(np.arange(40, 80), 400000, p=w / w.sum()).astype(np.uint8).tobytes()
-    cases = [text, text[:131072], text[:131073], text[:1024], text[:1023], text[:5], b"", noise, skew, b"A" * 200000,
+    ill = illumina_text(rng, 5000)
+    cases = [ill, ill[:131072 + 9], b"@same name here\nACGTACGTACGTACGTACGT\n+\nFFFFFFFFFFFFFFFFFFFF\n" * 4000,
+             b"".join(b"ab%d\n" % (i % 7) for i in range(60000)), text, text[:131072], text[:131073], text[:1024], text[:1023], text[:5], b"", noise, skew, b"A" * 200000,
              text[:700000] + noise[:1000] + text[:300000]]
     for k, data in enumerate(cases):
         got = device_frame(ctx, data)
         assert _zstd.decompress(got) == data, k
         want, _ = zh_frame(data)
         assert got == want, k
-    big = fastq_text(rng, 120000)                      # ~ 20 MB: a few hundred CTAs
+    big = fastq_text(rng, 60000) + illumina_text(rng, 40000)      # ~ 20 MB: a few hundred CTAs
     got = device_frame(ctx, big)
-    assert _zstd.decompress(got) == big and len(got) < 0.7 * len(big)
+    assert _zstd.decompress(got) == big and len(got) < 0.6 * len(big)
+    assert got == zh_frame(big)[0]

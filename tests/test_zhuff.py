@@ -11,16 +11,16 @@ from precellar_b200 import _zstd
 from tests import util as U
 
 
-def zh_frame(data: bytes, shift: int = 0):
+def zh_frame(data: bytes, shift: int = 0, matches: bool = True):
     """`shift` = 0: the input starts on a 64-byte boundary (the span loops take the 128-bit-load route, as in the CUDA
     kernels whose buffers are aligned); any other value: the byte route."""
     L = U.emul_lib()
     L.emu_zh_frame.restype = C.c_int64
-    L.emu_zh_frame.argtypes = [C.c_char_p, C.c_uint64, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64), C.c_uint32]
+    L.emu_zh_frame.argtypes = [C.c_char_p, C.c_uint64, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64), C.c_uint32, C.c_int]
     cap = 14 + (len(data) // 131072 + 2) * (131072 + 16)
     out = C.create_string_buffer(cap)
     raw = C.c_uint64(0)
-    n = L.emu_zh_frame(data, len(data), out, cap, C.byref(raw), shift)
+    n = L.emu_zh_frame(data, len(data), out, cap, C.byref(raw), shift, int(matches))
     assert n > 0
     return out.raw[:n], raw.value
 
@@ -97,3 +97,78 @@ def test_symbol_128_and_two_symbol_blocks():
     data = rng.choice(np.array([0, 1], np.uint8), 5000).tobytes()
     frame, _ = zh_frame(data)
     assert _zstd.decompress(frame) == data
+
+
+def illumina_text(rng, n, read_len=100):
+    recs = []
+    qb = np.frombuffer(b"F:,#", np.uint8)
+    for i in range(n):
+        seq = rng.choice(np.frombuffer(b"ACGT", np.uint8), read_len).tobytes()
+        q = rng.choice(qb, read_len, p=[0.88, 0.07, 0.04, 0.01]).tobytes()
+        recs.append(b"@A00123:45:HXXXXXXXX:1:%d:%d:%d 1:N:0:ACGTACGT+TGCATGCA\n" % (1101 + i // 5000, 1000 + (i * 37) % 30000, 1000 + i % 40000)
+                    + seq + b"\n+\n" + q + b"\n")
+    return b"".join(recs)
+
+
+def test_matches_against_the_previous_record_shrink_fastq_text():
+    """Sequences (prefix / suffix matches of a line against the same line of the previous record, predefined FSE codes):
+    libzstd must decode them, and on text with instrument-style names they must pay."""
+    rng = np.random.default_rng(21)
+    data = illumina_text(rng, 6000)
+    with_m, raw_blocks = zh_frame(data)
+    without, _ = zh_frame(data, matches=False)
+    assert raw_blocks == 0 and _zstd.decompress(with_m) == data and _zstd.decompress(without) == data
+    assert len(with_m) < 0.8 * len(without)
+    assert zh_frame(data, shift=3)[0] == with_m
+    for n in (131072, 131073, 262144 + 77, 5000, 1500):
+        frame, _ = zh_frame(data[:n])
+        assert _zstd.decompress(frame) == data[:n], n
+
+
+def test_match_finder_corner_cases():
+    rng = np.random.default_rng(22)
+    cases = {
+        "identical records": b"@same name here\nACGTACGTACGTACGTACGT\n+\nFFFFFFFFFFFFFFFFFFFF\n" * 4000,
+        "more lines than the index holds": b"".join(b"ab%d\n" % (i % 7) for i in range(60000)),
+        "few lines": b"x" * 70000 + b"\n" + b"y" * 70000 + b"\n",
+        "lines longer than 64 K that repeat": (b"Q" * 30000 + b"\n" + b"ACGT" * 2000 + b"\n+\nzz\n") * 6,
+        "no newline at all": bytes(rng.integers(65, 70, 200000, dtype=np.uint8)),
+        "blank lines": b"\n" * 3000 + b"abcdefghijklmnop\n" * 3000,
+        "prefix and suffix overlap": b"".join(b"@common-prefix-%d-common-suffix-of-the-name\nAC\n+\nFF\n" % (i % 10) for i in range(5000)),
+        "long literal runs between matches": b"".join(b"@name-with-a-long-prefix:%d\n" % i + bytes(rng.integers(65, 91, 900, dtype=np.uint8)) + b"\n+\n"
+                                                     + bytes(rng.integers(65, 91, 900, dtype=np.uint8)) + b"\n" for i in range(300)),
+    }
+    for name, data in cases.items():
+        frame, _ = zh_frame(data)
+        assert _zstd.decompress(frame) == data, name
+        assert zh_frame(data, shift=7)[0] == frame, name
+    # 64 KB+ identical lines: match lengths at the 16-bit limit
+    line = bytes(rng.integers(65, 69, 66000, dtype=np.uint8)) + b"\n"
+    data = (line + b"s\n+\nq\n") * 5
+    frame, _ = zh_frame(data)
+    assert _zstd.decompress(frame) == data
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2, 3])
+def test_random_record_texts_round_trip(seed):
+    """Random four-line records (shared name prefixes and suffixes of random length, empty and long lines, CRLF, truncated
+    tails, small and large alphabets): whatever sequences and literals the coder picks, libzstd returns the input."""
+    rng = np.random.default_rng(1000 + seed)
+    for it in range(12):
+        nrec = int(rng.integers(1, 2500))
+        alpha = int(rng.choice([4, 8, 20, 60]))
+        pre = bytes(rng.integers(65, 65 + alpha, int(rng.integers(0, 70)), dtype=np.uint8))
+        suf = bytes(rng.integers(65, 65 + alpha, int(rng.integers(0, 40)), dtype=np.uint8))
+        recs = []
+        for i in range(nrec):
+            L = int(rng.integers(0, 150))
+            mid = bytes(rng.integers(48, 58, int(rng.integers(0, 9)), dtype=np.uint8))
+            s = bytes(rng.integers(65, 65 + alpha, L, dtype=np.uint8))
+            q = bytes(rng.choice(np.frombuffer(b"F:,#", np.uint8), L, p=[0.7, 0.1, 0.1, 0.1])) if rng.random() < 0.8 else b"F" * L
+            eol = b"\r\n" if rng.random() < 0.1 else b"\n"
+            recs.append(b"@" + pre + mid + suf + eol + s + eol + b"+" + eol + q + eol)
+        data = b"".join(recs)
+        if rng.random() < 0.3:
+            data = data[:int(rng.integers(0, len(data) + 1))]
+        frame, _ = zh_frame(data, shift=int(rng.integers(0, 16)))
+        assert _zstd.decompress(frame) == data, (seed, it)
