@@ -337,9 +337,9 @@ int pcl_text_line_ends(pcl_chunk *chunk, int read_slot, uint32_t *out, uint64_t 
  * Replaces, for chunks whose text was parsed on the device, the record loop of make_fastq and the zstd encoder behind
  * it (python/src/lib.rs:136-168, seqspec/src/utils.rs:33-36), i.e. what pcl_make_fastq_batch + a host zstd do for
  * the host reader: the R1 (and R2) records of a chunk are assembled in HBM from the kept text and the result planes
- * and, with `compress`, entropy-coded there into one standard zstd frame per file and call (RFC 8878: 128 KB
- * blocks of Huffman-coded literals, no matches - any zstd decoder reads them; the ratio is that of an order-0
- * coder, not of zstd level 9).
+ * and, with `compress`, coded there into one standard zstd frame per file and call (RFC 8878: 128 KB blocks of
+ * Huffman-coded literals plus sequences - matches of every line against the line four lines earlier, FSE-coded with
+ * the predefined distributions; any zstd decoder reads them; files come out about 1.3-1.4 x the size of level 9).
  *   pcl_text_keep(chunk, slot)   after pcl_text_fill: the chunk keeps its own copy of the consumed text and line
  *                                index (device to device, asynchronous) - the staging buffers move on to the next chunk
  *   pcl_emit_fastq(chunk, correct_barcode, paired, compress, &res)

@@ -628,8 +628,8 @@ def make_fastq(assay, *, modality: str, out_dir, correct_barcode: bool = False, 
     FASTQ dialect of the device parser: no blank lines between records), "host" reads and assembles records on the
     host (several GPUs), "auto" picks the device writer when it applies.
     ``compression``: "zstd" = libzstd level 9 on the host like the reference (seqspec/src/utils.rs:33-36); "device" =
-    zstd frames built on the GPU (Huffman-coded literals, no matches: every zstd decoder reads them, the files are
-    about 1.3-1.6 times the size of level 9) - only with the device writer.  The decompressed bytes are the same
+    zstd frames built on the GPU (Huffman-coded literals and FSE-coded matches against the previous record: every zstd
+    decoder reads them, the files are about 1.3-1.4 times the size of level 9) - only with the device writer.  The decompressed bytes are the same
     in every combination.
     """
     from . import _zstd

@@ -1,20 +1,22 @@
-// zhuff_core.h -- zstd frames whose blocks carry Huffman-coded literals only, built on the device.
+// zhuff_core.h -- standard zstd frames built on the device: Huffman-coded literals plus FSE-coded sequences.
 //
 // SURVEY.md §8(f) row 3 (the make_fastq writer).  The reference writes R1.fq.zst / R2.fq.zst through the zstd crate
 // (python/src/lib.rs:136-146, seqspec/src/utils.rs:33-36: level 9, 8 worker threads), which is the floor of an
 // API-level run once everything else is on the GPU.  This file produces standard zstd blocks (RFC 8878) on the
 // device instead: every block of up to 128 KB is either
-//   * a Compressed_Block whose Literals_Section is Huffman-coded in four streams with a directly encoded weight table
-//     (RFC 8878 §3.1.1.3.1, §4.2.1) and whose Sequences_Section is empty (Number_of_Sequences = 0), or
-//   * a Raw_Block, when the block is tiny, holds a byte above 128, a single distinct byte, or would not shrink.
-// Any zstd decoder reads the result; there are no matches, so the ratio is that of an order-0 entropy coder.
+//   * a Compressed_Block: the matches of every line against the line four lines earlier (the same line of the previous
+//     FASTQ record: a common prefix and a common suffix) as a Sequences_Section coded with the format's predefined
+//     FSE distributions (RFC 8878 §3.1.1.3.2), and the remaining bytes as a Literals_Section, Huffman-coded in four
+//     streams with a directly encoded weight table (§3.1.1.3.1, §4.2.1), or
+//   * a Raw_Block, when the block is tiny or would not shrink.
+// Any zstd decoder reads the result.
 //
 // The functions below are the per-thread phases of one CTA working on one block, written so that tests/emul can run
 // them on the host (phase by phase, thread by thread) and hand the output to libzstd's decoder in the CPU tier.
-//   zh_rank          position of every present byte value in (count, value) order  (thread per byte value)
-//   zh_build_table   Huffman code lengths limited to 11 bits, canonical codes, weight table    (one thread)
-//   zh_span_bits     bits the thread's span of a stream needs                       (thread per span)
-//   zh_span_encode   the span's codes OR-ed into the stream's bit buffer            (thread per span)
+//   zh_find_matches       newline index, prefix / suffix matches per line, compaction, literal buffer
+//   zh_literals_section   histogram, zh_rank / zh_build_table (length-limited Huffman code), zh_span_bits / zh_span_encode
+//   zh_sequences_section  codes, the three FSE state chains (one thread), bit counts, bits
+//   zh_compress_block     the block: sections, headers, raw fallback
 #ifndef PCL_ZHUFF_CORE_H
 #define PCL_ZHUFF_CORE_H
 
