@@ -363,15 +363,15 @@ ZH_HD_NOINLINE void zh_fse_build(const int8_t *norm, uint32_t n_sym, uint32_t lo
     t->log = log;
 }
 
-// predefined distributions of literal lengths, match lengths and offsets (RFC 8878 §3.1.1.3.2.2)
-ZH_HD_NOINLINE void zh_fse_predefined(ZhFse *ll, ZhFse *ml, ZhFse *of) {
+// predefined distributions of literal lengths (which = 0), match lengths (1) and offsets (2) (RFC 8878 §3.1.1.3.2.2)
+ZH_HD_NOINLINE void zh_fse_predefined(uint32_t which, ZhFse *t) {
     const int8_t nll[36] = {4, 3, 2, 2, 2, 2, 2, 2, 2, 2, 2, 2, 2, 1, 1, 1, 2, 2, 2, 2, 2, 2, 2, 2, 2, 3, 2, 1, 1, 1, 1, 1, -1, -1, -1, -1};
     const int8_t nml[53] = {1, 4, 3, 2, 2, 2, 2, 2, 2, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1,
                             1, 1, 1, 1, 1, 1, 1, 1, 1, -1, -1, -1, -1, -1, -1, -1};
     const int8_t nof[29] = {1, 1, 1, 1, 1, 1, 2, 2, 2, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, -1, -1, -1, -1, -1};
-    zh_fse_build(nll, 36, 6, ll);
-    zh_fse_build(nml, 53, 6, ml);
-    zh_fse_build(nof, 29, 5, of);
+    if (which == 0) zh_fse_build(nll, 36, 6, t);
+    else if (which == 1) zh_fse_build(nml, 53, 6, t);
+    else zh_fse_build(nof, 29, 5, t);
 }
 
 // code and number of extra bits of a literal length / of a match length minus 3 (ZSTD_LLcode / ZSTD_MLcode)
@@ -418,11 +418,11 @@ struct ZhShared {
     ZhTable table;
     uint32_t span[ZH_THREADS];
     uint32_t out[ZH_STREAM_CAP_WORDS];
-    ZhFse fse_ll, fse_ml, fse_of;
-    // per sequence: first its three codes (written by all threads), then - in place, by the one thread that walks the
-    // three state chains - the states the codes meet (minus the table size)
-    uint8_t seq_ll[ZH_MAX_SEQ], seq_ml[ZH_MAX_SEQ], seq_of[ZH_MAX_SEQ];
-    uint32_t end_ll, end_ml, end_of;             // states left after the last (text-order first) sequence
+    ZhFse fse[3];                                // literal lengths, match lengths, offsets
+    // per sequence and code: first the code (written by all threads), then - in place, by the thread that walks that
+    // code's state chain - the state the code meets (minus the table size)
+    uint8_t seq_code[3][ZH_MAX_SEQ];
+    uint32_t end_state[3];                       // states left after the last (text-order first) sequence
     uint32_t stream_bits;
     uint32_t fail;
     uint32_t n_lines, n_seq, n_lit, seq_bytes, lit_bytes;
@@ -605,13 +605,26 @@ ZH_HD void zh_find_matches(Exec &ex, ZhShared &sh, ZhScratch &sc, const uint8_t 
         }
         if (tid == 0) { sh.n_seq = n_seq; sh.n_lit = sh.stream_bits; }
     });
-    ex.each([&](uint32_t tid) {                                             // the bytes: a warp per run, lanes side by side
-        const uint32_t lane = tid & 31u, warp = tid >> 5;
-        for (uint32_t j = warp; j < n_seq + 1u; j += ZH_THREADS / 32u) {
-            const uint32_t from = j ? sc.seq_pos[j - 1u] + sc.seq_len[j - 1u] : 0u, run = sc.seq_pos[j] - from, at = sc.seq_lit[j];
-            for (uint32_t k = lane; k < run; k += 32u) sc.lit[at + k] = src[from + k];
-        }
-    });
+    // the bytes: batches of ZH_THREADS runs - every thread looks one run up, then each warp copies 32 of them, lanes side by side
+    for (uint32_t base = 0; base < n_seq + 1u; base += ZH_THREADS) {
+        ex.each([&](uint32_t tid) {
+            const uint32_t j = base + tid;
+            uint32_t from = 0, run = 0, at = 0;
+            if (j < n_seq + 1u) {
+                from = j ? sc.seq_pos[j - 1u] + sc.seq_len[j - 1u] : 0u;
+                run = sc.seq_pos[j] - from;
+                at = sc.seq_lit[j];
+            }
+            sh.whist[0][tid] = from; sh.whist[1][tid] = run; sh.whist[2][tid] = at;     // (the histograms are not in use yet)
+        });
+        ex.each([&](uint32_t tid) {
+            const uint32_t lane = tid & 31u, first = tid & ~31u;
+            for (uint32_t r = first; r < first + 32u; ++r) {
+                const uint32_t from = sh.whist[0][r], run = sh.whist[1][r], at = sh.whist[2][r];
+                for (uint32_t k = lane; k < run; k += 32u) sc.lit[at + k] = src[from + k];
+            }
+        });
+    }
 }
 
 // literal length, match length - 3 and offset + 3 of sequence j
@@ -641,28 +654,34 @@ ZH_HD uint32_t zh_sequences_section(Exec &ex, ZhShared &sh, const ZhScratch &sc,
     const uint32_t hdr = n_seq < 128u ? 2u : 3u;                             // Number_of_Sequences + Symbol_Compression_Modes
     const uint32_t per = (n_seq + ZH_THREADS - 1u) / ZH_THREADS;
     ex.each([&](uint32_t tid) {
-        if (tid == 0) zh_fse_predefined(&sh.fse_ll, &sh.fse_ml, &sh.fse_of);
+        if (tid < 3u) zh_fse_predefined(tid, &sh.fse[tid]);
         for (uint32_t k = tid; k < ZH_STREAM_CAP_WORDS; k += ZH_THREADS) sh.out[k] = 0;
         for (uint32_t j = tid; j < n_seq; j += ZH_THREADS) {
             const ZhSeqVal v = zh_seq_val(sc, j);
             uint32_t eb;
-            sh.seq_ll[j] = (uint8_t)zh_ll_code(v.ll, &eb);
-            sh.seq_ml[j] = (uint8_t)zh_ml_code(v.mlb, &eb);
-            sh.seq_of[j] = (uint8_t)zh_highbit(v.ofb);
+            sh.seq_code[0][j] = (uint8_t)zh_ll_code(v.ll, &eb);
+            sh.seq_code[1][j] = (uint8_t)zh_ml_code(v.mlb, &eb);
+            sh.seq_code[2][j] = (uint8_t)zh_highbit(v.ofb);
         }
     });
-    ex.each([&](uint32_t tid) {                                              // the three state chains
-        if (tid) return;
+    ex.each([&](uint32_t tid) {                                              // the three state chains, a thread each
+        if (tid >= 3u) return;
+        const ZhFse &t = sh.fse[tid];
+        uint8_t *code = sh.seq_code[tid];
+        const uint32_t size = 1u << t.log;
         uint32_t j = n_seq - 1u;
-        uint32_t s_ll = zh_fse_first(sh.fse_ll, sh.seq_ll[j]), s_ml = zh_fse_first(sh.fse_ml, sh.seq_ml[j]), s_of = zh_fse_first(sh.fse_of, sh.seq_of[j]);
+        uint32_t st = zh_fse_first(t, code[j]);
+        // the table words of the next code are fetched while the current step's lookup is in flight
+        uint32_t c = j ? code[j - 1u] : 0u, db = t.delta_bits[c];
+        int32_t ds = t.delta_state[c];
         while (j-- > 0) {
-            const uint32_t c_ll = sh.seq_ll[j], c_ml = sh.seq_ml[j], c_of = sh.seq_of[j];
-            sh.seq_ll[j] = (uint8_t)(s_ll - 64u); sh.seq_ml[j] = (uint8_t)(s_ml - 64u); sh.seq_of[j] = (uint8_t)(s_of - 32u);
-            s_ll = zh_fse_next(sh.fse_ll, s_ll, c_ll);
-            s_ml = zh_fse_next(sh.fse_ml, s_ml, c_ml);
-            s_of = zh_fse_next(sh.fse_of, s_of, c_of);
+            const uint32_t db_now = db;
+            const int32_t ds_now = ds;
+            if (j) { c = code[j - 1u]; db = t.delta_bits[c]; ds = t.delta_state[c]; }
+            code[j] = (uint8_t)(st - size);
+            st = t.state[(int32_t)(st >> ((st + db_now) >> 16)) + ds_now];
         }
-        sh.end_ll = s_ll; sh.end_ml = s_ml; sh.end_of = s_of;
+        sh.end_state[tid] = st;
     });
     // coding order position q <-> sequence j = n_seq - 1 - q; thread t owns positions [t * per, (t + 1) * per)
     ex.each([&](uint32_t tid) {
@@ -674,13 +693,13 @@ ZH_HD uint32_t zh_sequences_section(Exec &ex, ZhShared &sh, const ZhScratch &sc,
             uint32_t ll_bits, ml_bits;
             const uint32_t c_ll = zh_ll_code(v.ll, &ll_bits), c_ml = zh_ml_code(v.mlb, &ml_bits), c_of = zh_highbit(v.ofb);
             bits += ll_bits + ml_bits + c_of;
-            if (q) bits += zh_fse_nbits(sh.fse_of, sh.seq_of[j] + 32u, c_of) + zh_fse_nbits(sh.fse_ml, sh.seq_ml[j] + 64u, c_ml) +
-                           zh_fse_nbits(sh.fse_ll, sh.seq_ll[j] + 64u, c_ll);
+            if (q) bits += zh_fse_nbits(sh.fse[2], sh.seq_code[2][j] + 32u, c_of) + zh_fse_nbits(sh.fse[1], sh.seq_code[1][j] + 64u, c_ml) +
+                           zh_fse_nbits(sh.fse[0], sh.seq_code[0][j] + 64u, c_ll);
         }
         sh.span[tid] = bits;
     });
     zh_scan_spans(ex, sh);
-    const uint32_t body_bits = sh.stream_bits, total_bits = body_bits + sh.fse_ml.log + sh.fse_of.log + sh.fse_ll.log;
+    const uint32_t body_bits = sh.stream_bits, total_bits = body_bits + sh.fse[1].log + sh.fse[2].log + sh.fse[0].log;
     const uint32_t bytes = hdr + total_bits / 8u + 1u;
     if (bytes + 8u > 4u * ZH_STREAM_CAP_WORDS || bytes > dst_cap) return 0;
     ex.each([&](uint32_t tid) {
@@ -692,12 +711,12 @@ ZH_HD uint32_t zh_sequences_section(Exec &ex, ZhShared &sh, const ZhScratch &sc,
             uint32_t ll_bits, ml_bits;
             const uint32_t c_ll = zh_ll_code(v.ll, &ll_bits), c_ml = zh_ml_code(v.mlb, &ml_bits), c_of = zh_highbit(v.ofb);
             if (q) {
-                const uint32_t s_of = sh.seq_of[j] + 32u, s_ml = sh.seq_ml[j] + 64u, s_ll = sh.seq_ll[j] + 64u;
-                uint32_t nb = zh_fse_nbits(sh.fse_of, s_of, c_of);
+                const uint32_t s_of = sh.seq_code[2][j] + 32u, s_ml = sh.seq_code[1][j] + 64u, s_ll = sh.seq_code[0][j] + 64u;
+                uint32_t nb = zh_fse_nbits(sh.fse[2], s_of, c_of);
                 zh_or_bits(sh.out, at, s_of, nb); at += nb;
-                nb = zh_fse_nbits(sh.fse_ml, s_ml, c_ml);
+                nb = zh_fse_nbits(sh.fse[1], s_ml, c_ml);
                 zh_or_bits(sh.out, at, s_ml, nb); at += nb;
-                nb = zh_fse_nbits(sh.fse_ll, s_ll, c_ll);
+                nb = zh_fse_nbits(sh.fse[0], s_ll, c_ll);
                 zh_or_bits(sh.out, at, s_ll, nb); at += nb;
             }
             zh_or_bits(sh.out, at, v.ll, ll_bits); at += ll_bits;
@@ -708,9 +727,9 @@ ZH_HD uint32_t zh_sequences_section(Exec &ex, ZhShared &sh, const ZhScratch &sc,
     ex.each([&](uint32_t tid) {
         if (tid) return;
         uint32_t at = 8u * hdr + body_bits;                                  // the final states, then the end mark
-        zh_or_bits(sh.out, at, sh.end_ml, sh.fse_ml.log); at += sh.fse_ml.log;
-        zh_or_bits(sh.out, at, sh.end_of, sh.fse_of.log); at += sh.fse_of.log;
-        zh_or_bits(sh.out, at, sh.end_ll, sh.fse_ll.log); at += sh.fse_ll.log;
+        zh_or_bits(sh.out, at, sh.end_state[1], sh.fse[1].log); at += sh.fse[1].log;
+        zh_or_bits(sh.out, at, sh.end_state[2], sh.fse[2].log); at += sh.fse[2].log;
+        zh_or_bits(sh.out, at, sh.end_state[0], sh.fse[0].log); at += sh.fse[0].log;
         zh_or_bits(sh.out, at, 1u, 1u);
         if (n_seq < 128u) sh.out[0] |= n_seq;                                // byte 1 (the modes) stays 0: predefined tables
         else sh.out[0] |= ((n_seq >> 8) + 128u) | ((n_seq & 255u) << 8);     // n_seq <= ZH_MAX_SEQ < 0x7F00; byte 2 stays 0
