@@ -13,6 +13,7 @@
 #include "../../precellar_b200/csrc/host_build.h"
 #include "../../precellar_b200/csrc/zhuff_core.h"
 #include "../../precellar_b200/csrc/emit_core.h"
+#include "../../precellar_b200/csrc/inflate_core.h"
 
 extern "C" {
 
@@ -477,5 +478,38 @@ int emu_emit(const pcl_read_desc *reads, int n_reads, const emu_emit_read *io, u
     *u1 = t1; *u2 = t2; *n_written = written;
     return 0;
 }
+
+
+// ------------------------------------------------------------------------------------------
+// inflate_core.h on the host: the warp of k_bgzf_inflate emulated phase by phase, lane by lane
+// ------------------------------------------------------------------------------------------
+}  // extern "C"
+struct EmuWarpExec {
+    int reverse;                 // lanes in descending order: a phase whose lanes depend on one another shows up as a difference
+    template <class F> void each(F f) {
+        if (reverse) for (uint32_t l = INF_LANES; l-- > 0;) f(l);
+        else for (uint32_t l = 0; l < INF_LANES; ++l) f(l);
+    }
+};
+extern "C" {
+
+// comp[0 .. comp_bytes + INF_PAD_BYTES) readable; members[n]; out[out_cap].  Returns 0, or (member index + 1) << 8 | error
+// of the first member that fails.
+int64_t emu_inflate(const uint8_t *comp, uint64_t comp_bytes, const InfMember *members, uint32_t n, uint8_t *out, uint64_t out_cap,
+                    int reverse) {
+    uint32_t tab[256];
+    for (uint32_t t = 0; t < 256u; ++t) tab[t] = inf_crc_table_entry(t);
+    static InfWarp w;
+    EmuWarpExec ex{reverse};
+    for (uint32_t i = 0; i < n; ++i) {
+        const InfMember &m = members[i];
+        if ((uint64_t)m.src_off + m.clen > comp_bytes || (uint64_t)m.dst_off + m.isize > out_cap) return ((int64_t)(i + 1) << 8) | 0xFF;
+        const uint32_t e = inf_member(ex, w, tab, comp, m, out + m.dst_off);
+        if (e) return ((int64_t)(i + 1) << 8) | e;
+    }
+    return 0;
+}
+
+uint32_t emu_inflate_warp_bytes() { return (uint32_t)sizeof(InfWarp); }
 
 }  // extern "C"
