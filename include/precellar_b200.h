@@ -375,6 +375,47 @@ int pcl_gzsrc_is_bgzf(const pcl_gzsrc *src);
 const char *pcl_gzsrc_error(const pcl_gzsrc *src);
 void pcl_gzsrc_close(pcl_gzsrc *src);
 
+/* ---- BGZF members inflated on the device (csrc/inflate.cuh, inflate_core.h) -------------------------------
+ * Replaces open_file's MultiGzDecoder (seqspec/src/utils.rs:44-56; the reference inflates every file on one host thread,
+ * twice per run: seqspec/src/read.rs:83-155) for BGZF input: the host walks the member headers (pcl_bgzf_walk), the
+ * compressed bytes go to the device as they are and one warp inflates each member - CRC-32 and ISIZE of the trailer
+ * checked - into a text block that pcl_text_scan_device indexes without a trip through host memory.
+ *
+ * pcl_bgzf_walk      whole members at the front of buf[0..n_bytes): stops once they inflate to >= want_out bytes, at
+ *                    `cap` members, or at the first incomplete / non-BGZF member.  Members that inflate to nothing (the
+ *                    end-of-file marker) are consumed, not listed.  src_off is relative to buf, dst_off counts from 0.
+ *                    Returns PCL_ERR_INPUT when the bytes at buf[*consumed] are complete but no BGZF header.
+ * pcl_inflater_*     one handle per producer thread (own stream and staging; calls on one handle are not re-entrant,
+ *                    handles of one ctx may be driven from different threads).  A handle owns up to 4 text buffers
+ *                    ("slots") in device memory; pcl_inflater_buffer (re)allocates one (bytes = 0 frees it) and returns
+ *                    its address.  pcl_inflater_run copies comp[0..comp_bytes) (pageable or pinned host memory) to the
+ *                    device and inflates the members to slot bytes [dst_off + member.dst_off, ...); it blocks, and a
+ *                    damaged member is PCL_ERR_INPUT (pcl_inflater_error names the member and the defect).  move / fetch /
+ *                    poke copy device-to-device (between or inside slots, ranges must not overlap), device-to-host and
+ *                    host-to-device; all block.  pcl_inflater_stats: kernel time (CUDA events), inflated bytes, launches. */
+typedef struct pcl_bgzf_member {
+    uint32_t src_off;            /* first byte of the member's DEFLATE stream                    */
+    uint32_t clen;               /* length of the stream                                         */
+    uint32_t dst_off;            /* offset of the member's bytes in the inflated text            */
+    uint32_t isize;              /* ISIZE of the trailer                                         */
+    uint32_t crc;                /* CRC32 of the trailer                                         */
+} pcl_bgzf_member;
+int pcl_bgzf_walk(const uint8_t *buf, uint64_t n_bytes, uint64_t want_out, pcl_bgzf_member *members, uint32_t cap,
+                  uint32_t *n_members, uint64_t *consumed, uint64_t *out_bytes);
+typedef struct pcl_inflater pcl_inflater;
+int pcl_inflater_create(pcl_ctx *ctx, pcl_inflater **out);
+void pcl_inflater_destroy(pcl_inflater *inf);
+const char *pcl_inflater_error(const pcl_inflater *inf);
+int pcl_inflater_buffer(pcl_inflater *inf, int slot, uint64_t bytes, void **device_ptr);
+int pcl_inflater_run(pcl_inflater *inf, const uint8_t *comp, uint64_t comp_bytes, const pcl_bgzf_member *members,
+                     uint32_t n_members, int slot, uint64_t dst_off);
+int pcl_inflater_move(pcl_inflater *inf, int src_slot, uint64_t src_off, int dst_slot, uint64_t dst_off, uint64_t n_bytes);
+int pcl_inflater_fetch(pcl_inflater *inf, int slot, uint64_t off, uint64_t n_bytes, void *host_dst);
+int pcl_inflater_poke(pcl_inflater *inf, int slot, uint64_t off, const void *host_src, uint64_t n_bytes);
+int pcl_inflater_stats(const pcl_inflater *inf, double *kernel_ms, uint64_t *out_bytes, uint64_t *launches);
+/* pcl_text_scan for a block that is already in device memory (a slot of a pcl_inflater of the same ctx). */
+int pcl_text_scan_device(pcl_chunk *chunk, int read_slot, const void *device_text, uint64_t n_bytes);
+
 /* ---- per-barcode grouping of a chunk ---------------------------------------------
  * The first data-parallel step behind the aligner, keyed on this path's output:
  *   sort_by_barcode + chunk_by(barcode)          precellar/src/fragment/mod.rs:359-363,434-455

@@ -71,6 +71,10 @@ class GroupInfo(C.Structure):
                 ("n_barcodes", C.c_uint64), ("n_fragments", C.c_uint64)]
 
 
+class BgzfMember(C.Structure):
+    _fields_ = [("src_off", C.c_uint32), ("clen", C.c_uint32), ("dst_off", C.c_uint32), ("isize", C.c_uint32), ("crc", C.c_uint32)]
+
+
 class PclError(RuntimeError):
     def __init__(self, code: int, msg: str):
         super().__init__(f"precellar_b200 error {code}: {msg}")
@@ -95,6 +99,8 @@ SYMBOLS = [
     "pcl_counts_freeze", "pcl_chunk_bytes", "pcl_mem_info", "pcl_verify_enable", "pcl_chunk_set_uniform_len", "pcl_chunk_uniform_results_async",
     "pcl_group_build", "pcl_group_build_multi", "pcl_group_info_get", "pcl_group_fetch", "pcl_group_key_decode", "pcl_group_destroy",
     "pcl_text_keep", "pcl_emit_fastq", "pcl_zstd_frame",
+    "pcl_bgzf_walk", "pcl_inflater_create", "pcl_inflater_destroy", "pcl_inflater_error", "pcl_inflater_buffer", "pcl_inflater_run",
+    "pcl_inflater_move", "pcl_inflater_fetch", "pcl_inflater_poke", "pcl_inflater_stats", "pcl_text_scan_device",
 ]
 
 _lib = None
@@ -184,6 +190,17 @@ def lib() -> C.CDLL:
         "pcl_fastq_error": (C.c_char_p, [vp]),
         "pcl_fastq_read": (C.c_int64, [vp, u64, u32, u32, u32, vp, vp, vp, vp, vp, u64, vp, C.POINTER(u64)]),
         "pcl_fastq_text_full": (C.c_int, [vp]),
+        "pcl_bgzf_walk": (i32, [vp, u64, u64, C.POINTER(BgzfMember), u32, C.POINTER(u32), C.POINTER(u64), C.POINTER(u64)]),
+        "pcl_inflater_create": (i32, [vp, C.POINTER(vp)]),
+        "pcl_inflater_destroy": (None, [vp]),
+        "pcl_inflater_error": (C.c_char_p, [vp]),
+        "pcl_inflater_buffer": (i32, [vp, i32, u64, C.POINTER(vp)]),
+        "pcl_inflater_run": (i32, [vp, vp, u64, C.POINTER(BgzfMember), u32, i32, u64]),
+        "pcl_inflater_move": (i32, [vp, i32, u64, i32, u64, u64]),
+        "pcl_inflater_fetch": (i32, [vp, i32, u64, u64, vp]),
+        "pcl_inflater_poke": (i32, [vp, i32, u64, vp, u64]),
+        "pcl_inflater_stats": (i32, [vp, C.POINTER(f64), C.POINTER(u64), C.POINTER(u64)]),
+        "pcl_text_scan_device": (i32, [vp, i32, vp, u64]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)

@@ -232,4 +232,43 @@ int64_t pcl_gzsrc_read(pcl_gzsrc *s, uint8_t *dst, uint64_t cap) {
     return (int64_t)produced;
 }
 
+// The member table of the device inflate (inflate.cuh): whole BGZF members at the front of buf.
+int pcl_bgzf_walk(const uint8_t *buf, uint64_t n_bytes, uint64_t want_out, pcl_bgzf_member *members, uint32_t cap,
+                  uint32_t *n_members, uint64_t *consumed, uint64_t *out_bytes) {
+    if ((!buf && n_bytes) || (!members && cap) || !n_members || !consumed || !out_bytes) return PCL_ERR_ARG;
+    uint64_t p = 0, out = 0;
+    uint32_t n = 0;
+    int rc = PCL_OK;
+    while (out < want_out && n < cap && p < n_bytes) {
+        const uint64_t left = n_bytes - p;
+        const uint32_t bs = bgzf_block_size(buf + p, (size_t)left);
+        if (bs == 0) {
+            // too few bytes to tell (a header cut off by the end of buf) is "incomplete"; anything else is no BGZF member
+            const bool cut = left < 18 || (buf[p] == 0x1f && buf[p + 1] == 0x8b && buf[p + 2] == 8 && (buf[p + 3] & 4) &&
+                                           12 + (uint64_t)rd16(buf + p + 10) > left);
+            if (!cut) rc = PCL_ERR_INPUT;
+            break;
+        }
+        if (bs > left) break;                                                           // the member is cut off
+        const uint32_t hdr = 12 + rd16(buf + p + 10);
+        if (bs < hdr + 8) { rc = PCL_ERR_INPUT; break; }
+        const uint32_t isize = rd32(buf + p + bs - 4);
+        if (isize) {
+            if (p + hdr >= (1ull << 32) || out + isize >= (1ull << 32)) break;          // 32-bit offsets: the caller walks again from here
+            members[n].src_off = (uint32_t)(p + hdr);
+            members[n].clen = bs - hdr - 8;
+            members[n].dst_off = (uint32_t)out;
+            members[n].isize = isize;
+            members[n].crc = rd32(buf + p + bs - 8);
+            ++n;
+            out += isize;
+        }
+        p += bs;
+    }
+    *n_members = n;
+    *consumed = p;
+    *out_bytes = out;
+    return rc;
+}
+
 }  // extern "C"

@@ -24,6 +24,7 @@
 #include "group.cuh"
 #include "tablebuild.cuh"
 #include "emit.cuh"
+#include "inflate.cuh"
 
 // ------------------------------------------------------------------------------------------
 // NCCL through dlopen: the library has no link-time dependency on libnccl, and inside a process
@@ -975,7 +976,17 @@ static int text_reserve(pcl_chunk *c, ReadBuf &b, TextStage &t, uint64_t n_bytes
     return PCL_OK;
 }
 
+static int text_scan_from(pcl_chunk *c, int read_slot, const uint8_t *text, uint64_t n_bytes, cudaMemcpyKind kind);
+
 int pcl_text_scan(pcl_chunk *c, int read_slot, const uint8_t *text, uint64_t n_bytes) {
+    return text_scan_from(c, read_slot, text, n_bytes, cudaMemcpyHostToDevice);
+}
+
+int pcl_text_scan_device(pcl_chunk *c, int read_slot, const void *device_text, uint64_t n_bytes) {
+    return text_scan_from(c, read_slot, (const uint8_t *)device_text, n_bytes, cudaMemcpyDeviceToDevice);
+}
+
+static int text_scan_from(pcl_chunk *c, int read_slot, const uint8_t *text, uint64_t n_bytes, cudaMemcpyKind kind) {
     if (!c) return PCL_ERR_ARG;
     pcl_ctx *ctx = c->ctx;
     if (read_slot < 0 || read_slot >= ctx->n_reads) return fail(ctx, PCL_ERR_ARG, "bad read_slot");
@@ -989,7 +1000,7 @@ int pcl_text_scan(pcl_chunk *c, int read_slot, const uint8_t *text, uint64_t n_b
     // the previous user of the staging buffers has finished its fill (pcl_text_fill blocks) unless it never filled
     if (t.owner && t.owner != c) { CU(ctx, cudaStreamSynchronize(t.owner->stream)); t.owner->rb[read_slot].text_scanned = false; }
     t.owner = c;
-    if (n_bytes) CU(ctx, cudaMemcpyAsync(t.d_text, text, n_bytes, cudaMemcpyHostToDevice, s));
+    if (n_bytes) CU(ctx, cudaMemcpyAsync(t.d_text, text, n_bytes, kind, s));
     CU(ctx, cudaMemsetAsync(t.d_text + n_bytes, 0, 16, s));
     const uint64_t n_tiles = (n_bytes + PCL_TEXT_TILE - 1) / PCL_TEXT_TILE;
     const int grid = (int)std::min<uint64_t>(std::max<uint64_t>(n_tiles, 1), (uint64_t)ctx->sm_count * 8);
@@ -2276,6 +2287,207 @@ int pcl_group_destroy(pcl_group *g) {
     cudaSetDevice(g->ctx->device);
     for (void *q : g->allocs) cudaFree(q);
     delete g;
+    return PCL_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// BGZF members inflated on the device (inflate.cuh)
+// ------------------------------------------------------------------------------------------
+#define INF_SLOTS 4
+}  // extern "C"
+
+struct pcl_inflater {
+    int device = 0, sm_count = 1;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    uint8_t *d_comp = nullptr;
+    uint64_t comp_cap = 0;
+    InfMember *d_members = nullptr;
+    uint64_t members_cap = 0;
+    unsigned long long *d_err = nullptr, *h_err = nullptr;
+    uint8_t *slot[INF_SLOTS] = {nullptr, nullptr, nullptr, nullptr};
+    uint64_t slot_cap[INF_SLOTS] = {0, 0, 0, 0};
+    double kernel_ms = 0;
+    uint64_t out_bytes = 0, launches = 0;
+    std::string err;
+};
+
+namespace {
+int inf_fail(pcl_inflater *h, int code, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    h->err = buf;
+    return code;
+}
+#define CUI(h, call)                                                                                \
+    do {                                                                                            \
+        cudaError_t e_ = (call);                                                                    \
+        if (e_ != cudaSuccess) return inf_fail(h, e_ == cudaErrorMemoryAllocation ? PCL_ERR_NOMEM : PCL_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(e_)); \
+    } while (0)
+
+const char *inf_error_text(unsigned code) {
+    static const char *const what[] = {"", "reserved block type", "bad stored block", "bad dynamic block header", "bad code lengths",
+                                       "invalid code", "match before the start of the member", "more bytes than ISIZE",
+                                       "compressed data ends early", "fewer bytes than ISIZE", "CRC-32 mismatch"};
+    return code < sizeof what / sizeof what[0] ? what[code] : "error";
+}
+
+bool inf_range_ok(const pcl_inflater *h, int slot, uint64_t off, uint64_t n) {
+    return slot >= 0 && slot < INF_SLOTS && h->slot[slot] && off <= h->slot_cap[slot] && n <= h->slot_cap[slot] - off;
+}
+}  // namespace
+
+extern "C" {
+
+int pcl_inflater_create(pcl_ctx *ctx, pcl_inflater **out) {
+    if (!ctx || !out) return PCL_ERR_ARG;
+    *out = nullptr;
+    pcl_inflater *h = new pcl_inflater();
+    h->device = ctx->device;
+    h->sm_count = ctx->sm_count > 0 ? ctx->sm_count : 1;
+    cudaError_t e = cudaSetDevice(h->device);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreate(&h->ev0);
+    if (e == cudaSuccess) e = cudaEventCreate(&h->ev1);
+    if (e == cudaSuccess) e = cudaMalloc((void **)&h->d_err, 8);
+    if (e == cudaSuccess) e = cudaMallocHost((void **)&h->h_err, 8);
+    if (e != cudaSuccess) {
+        const int rc = fail(ctx, PCL_ERR_CUDA, "pcl_inflater_create: %s", cudaGetErrorString(e));
+        pcl_inflater_destroy(h);
+        return rc;
+    }
+    *out = h;
+    return PCL_OK;
+}
+
+void pcl_inflater_destroy(pcl_inflater *h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    for (int k = 0; k < INF_SLOTS; ++k) cudaFree(h->slot[k]);
+    cudaFree(h->d_comp); cudaFree(h->d_members); cudaFree(h->d_err);
+    if (h->h_err) cudaFreeHost(h->h_err);
+    if (h->ev0) cudaEventDestroy(h->ev0);
+    if (h->ev1) cudaEventDestroy(h->ev1);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    cudaGetLastError();
+    delete h;
+}
+
+const char *pcl_inflater_error(const pcl_inflater *h) { return h ? h->err.c_str() : ""; }
+
+int pcl_inflater_buffer(pcl_inflater *h, int slot, uint64_t bytes, void **device_ptr) {
+    if (!h || slot < 0 || slot >= INF_SLOTS) return PCL_ERR_ARG;
+    if (device_ptr) *device_ptr = nullptr;
+    CUI(h, cudaSetDevice(h->device));
+    if (bytes == 0 || bytes > h->slot_cap[slot]) {
+        CUI(h, cudaStreamSynchronize(h->stream));
+        cudaFree(h->slot[slot]);
+        h->slot[slot] = nullptr;
+        h->slot_cap[slot] = 0;
+        if (bytes) {
+            if (bytes >= (1ull << 32) - 4096) return inf_fail(h, PCL_ERR_ARG, "a text buffer must be smaller than 4 GiB");
+            CUI(h, cudaMalloc((void **)&h->slot[slot], bytes + 16));
+            h->slot_cap[slot] = bytes;
+        }
+    }
+    if (device_ptr) *device_ptr = h->slot[slot];
+    return PCL_OK;
+}
+
+int pcl_inflater_run(pcl_inflater *h, const uint8_t *comp, uint64_t comp_bytes, const pcl_bgzf_member *members, uint32_t n_members,
+                     int slot, uint64_t dst_off) {
+    if (!h || (!comp && comp_bytes) || (!members && n_members)) return PCL_ERR_ARG;
+    if (n_members == 0) return PCL_OK;
+    if (comp_bytes >= (1ull << 32) - 4096) return inf_fail(h, PCL_ERR_ARG, "a batch of compressed bytes must be smaller than 4 GiB");
+    uint64_t out_end = 0;
+    for (uint32_t i = 0; i < n_members; ++i) {
+        const pcl_bgzf_member &m = members[i];
+        if ((uint64_t)m.src_off + m.clen > comp_bytes) return inf_fail(h, PCL_ERR_ARG, "member %u leaves the compressed bytes", i);
+        out_end = std::max<uint64_t>(out_end, (uint64_t)m.dst_off + m.isize);
+    }
+    if (!inf_range_ok(h, slot, dst_off, out_end)) return inf_fail(h, PCL_ERR_ARG, "the members do not fit text buffer %d", slot);
+    CUI(h, cudaSetDevice(h->device));
+    if (comp_bytes + INF_PAD_BYTES > h->comp_cap) {
+        CUI(h, cudaStreamSynchronize(h->stream));
+        cudaFree(h->d_comp);
+        h->d_comp = nullptr; h->comp_cap = 0;
+        const uint64_t cap = ((comp_bytes + comp_bytes / 4 + INF_PAD_BYTES + 4095) / 4096) * 4096;
+        CUI(h, cudaMalloc((void **)&h->d_comp, cap));
+        h->comp_cap = cap;
+    }
+    if (n_members > h->members_cap) {
+        CUI(h, cudaStreamSynchronize(h->stream));
+        cudaFree(h->d_members);
+        h->d_members = nullptr; h->members_cap = 0;
+        const uint64_t cap = (uint64_t)n_members + n_members / 4 + 64;
+        CUI(h, cudaMalloc((void **)&h->d_members, cap * sizeof(InfMember)));
+        h->members_cap = cap;
+    }
+    cudaStream_t s = h->stream;
+    CUI(h, cudaMemcpyAsync(h->d_comp, comp, comp_bytes, cudaMemcpyHostToDevice, s));
+    CUI(h, cudaMemsetAsync(h->d_comp + comp_bytes, 0, INF_PAD_BYTES, s));
+    CUI(h, cudaMemcpyAsync(h->d_members, members, (uint64_t)n_members * sizeof(InfMember), cudaMemcpyHostToDevice, s));
+    CUI(h, cudaMemsetAsync(h->d_err, 0xFF, 8, s));
+    const uint32_t want = (n_members + INF_WARPS_PER_CTA - 1) / INF_WARPS_PER_CTA;
+    const uint32_t grid = std::min<uint32_t>(want, (uint32_t)h->sm_count * 8u);
+    CUI(h, cudaEventRecord(h->ev0, s));
+    k_bgzf_inflate<<<grid, INF_WARPS_PER_CTA * 32u, 0, s>>>(h->d_comp, h->d_members, n_members, h->slot[slot] + dst_off, h->d_err);
+    CUI(h, cudaGetLastError());
+    CUI(h, cudaEventRecord(h->ev1, s));
+    CUI(h, cudaMemcpyAsync(h->h_err, h->d_err, 8, cudaMemcpyDeviceToHost, s));
+    CUI(h, cudaStreamSynchronize(s));
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, h->ev0, h->ev1) == cudaSuccess) h->kernel_ms += ms;
+    h->launches += 1;
+    h->out_bytes += out_end;
+    if (*h->h_err != ~0ull) {
+        const unsigned long long v = *h->h_err;
+        return inf_fail(h, PCL_ERR_INPUT, "corrupt BGZF block (member %llu of the batch): %s", v >> 8, inf_error_text((unsigned)(v & 0xFF)));
+    }
+    return PCL_OK;
+}
+
+int pcl_inflater_move(pcl_inflater *h, int src_slot, uint64_t src_off, int dst_slot, uint64_t dst_off, uint64_t n_bytes) {
+    if (!h) return PCL_ERR_ARG;
+    if (!inf_range_ok(h, src_slot, src_off, n_bytes) || !inf_range_ok(h, dst_slot, dst_off, n_bytes)) return inf_fail(h, PCL_ERR_ARG, "pcl_inflater_move: bad range");
+    if (src_slot == dst_slot && src_off < dst_off + n_bytes && dst_off < src_off + n_bytes && n_bytes)
+        return inf_fail(h, PCL_ERR_ARG, "pcl_inflater_move: the ranges overlap");
+    if (n_bytes == 0) return PCL_OK;
+    CUI(h, cudaSetDevice(h->device));
+    CUI(h, cudaMemcpyAsync(h->slot[dst_slot] + dst_off, h->slot[src_slot] + src_off, n_bytes, cudaMemcpyDeviceToDevice, h->stream));
+    CUI(h, cudaStreamSynchronize(h->stream));
+    return PCL_OK;
+}
+
+int pcl_inflater_fetch(pcl_inflater *h, int slot, uint64_t off, uint64_t n_bytes, void *host_dst) {
+    if (!h || (!host_dst && n_bytes)) return PCL_ERR_ARG;
+    if (!inf_range_ok(h, slot, off, n_bytes)) return inf_fail(h, PCL_ERR_ARG, "pcl_inflater_fetch: bad range");
+    if (n_bytes == 0) return PCL_OK;
+    CUI(h, cudaSetDevice(h->device));
+    CUI(h, cudaMemcpyAsync(host_dst, h->slot[slot] + off, n_bytes, cudaMemcpyDeviceToHost, h->stream));
+    CUI(h, cudaStreamSynchronize(h->stream));
+    return PCL_OK;
+}
+
+int pcl_inflater_poke(pcl_inflater *h, int slot, uint64_t off, const void *host_src, uint64_t n_bytes) {
+    if (!h || (!host_src && n_bytes)) return PCL_ERR_ARG;
+    if (!inf_range_ok(h, slot, off, n_bytes)) return inf_fail(h, PCL_ERR_ARG, "pcl_inflater_poke: bad range");
+    if (n_bytes == 0) return PCL_OK;
+    CUI(h, cudaSetDevice(h->device));
+    CUI(h, cudaMemcpyAsync(h->slot[slot] + off, host_src, n_bytes, cudaMemcpyHostToDevice, h->stream));
+    CUI(h, cudaStreamSynchronize(h->stream));
+    return PCL_OK;
+}
+
+int pcl_inflater_stats(const pcl_inflater *h, double *kernel_ms, uint64_t *out_bytes, uint64_t *launches) {
+    if (!h) return PCL_ERR_ARG;
+    if (kernel_ms) *kernel_ms = h->kernel_ms;
+    if (out_bytes) *out_bytes = h->out_bytes;
+    if (launches) *launches = h->launches;
     return PCL_OK;
 }
 

@@ -125,6 +125,10 @@ class Chunk:
     def text_scan(self, read_slot: int, text: np.ndarray, n_bytes: Optional[int] = None) -> None:
         """Copy a block of uncompressed FASTQ text (uint8, starting at a record boundary) to the device and index
         its lines.  Asynchronous: ``text`` must stay untouched until ``text_lines`` returns."""
+        if hasattr(text, "ptr"):                     # textingest.DevBlock: the text is in device memory already
+            n = len(text) if n_bytes is None else int(n_bytes)
+            check(self.pipe.ctx, lib().pcl_text_scan_device(self.h, read_slot, text.ptr if n else None, n))
+            return
         assert text.dtype == np.uint8 and text.flags.c_contiguous
         n = len(text) if n_bytes is None else int(n_bytes)
         check(self.pipe.ctx, lib().pcl_text_scan(self.h, read_slot, text.ctypes.data if n else None, n))

@@ -319,6 +319,224 @@ class MmapSource:
         self.maps = []
 
 
+class DevBlock:
+    """A text block that already sits in device memory (a window of a BgzfDeviceSource buffer)."""
+
+    def __init__(self, backend, slot: int, base: int, start: int, n: int):
+        self.backend, self.slot, self.start, self.n = backend, slot, int(start), int(n)
+        self.ptr = int(base) + int(start)
+
+    def __len__(self) -> int:
+        return self.n
+
+    def __bytes__(self) -> bytes:
+        return self.backend.fetch(self.slot, self.start, self.n)
+
+
+class DeviceInflater:
+    """pcl_inflater_* of one ctx: device text buffers ("slots") and the kernel that inflates BGZF members into them."""
+
+    def __init__(self, ctx):
+        self.h = C.c_void_p()
+        _ffi.check(ctx, lib().pcl_inflater_create(ctx, C.byref(self.h)))
+
+    def _check(self, rc: int) -> None:
+        if rc < 0:
+            raise _ffi.PclError(rc, lib().pcl_inflater_error(self.h).decode(errors="replace"))
+
+    def buffer(self, slot: int, nbytes: int) -> int:
+        p = C.c_void_p()
+        self._check(lib().pcl_inflater_buffer(self.h, slot, int(nbytes), C.byref(p)))
+        return p.value or 0
+
+    def run(self, comp: np.ndarray, members, n_members: int, slot: int, dst_off: int) -> None:
+        self._check(lib().pcl_inflater_run(self.h, comp.ctypes.data, len(comp), members, n_members, slot, int(dst_off)))
+
+    def move(self, src_slot: int, src_off: int, dst_slot: int, dst_off: int, n: int) -> None:
+        self._check(lib().pcl_inflater_move(self.h, src_slot, int(src_off), dst_slot, int(dst_off), int(n)))
+
+    def fetch(self, slot: int, off: int, n: int) -> bytes:
+        buf = C.create_string_buffer(max(int(n), 1))
+        self._check(lib().pcl_inflater_fetch(self.h, slot, int(off), int(n), buf))
+        return buf.raw[:int(n)]
+
+    def poke(self, slot: int, off: int, data: bytes) -> None:
+        self._check(lib().pcl_inflater_poke(self.h, slot, int(off), data, len(data)))
+
+    def stats(self) -> dict:
+        ms, nb, nl = C.c_double(), C.c_uint64(), C.c_uint64()
+        lib().pcl_inflater_stats(self.h, C.byref(ms), C.byref(nb), C.byref(nl))
+        return {"kernel_ms": ms.value, "out_bytes": nb.value, "launches": nl.value}
+
+    def close(self) -> None:
+        if self.h:
+            lib().pcl_inflater_destroy(self.h)
+            self.h = None
+
+
+def device_inflate_enabled() -> bool:
+    """BGZF input is inflated on the device unless PCL_DEVICE_INFLATE=0 (then: the host threads of csrc/gzsrc.cpp)."""
+    return os.environ.get("PCL_DEVICE_INFLATE", "1") != "0"
+
+
+def bgzf_walk(view: np.ndarray, want_out: int, members, cap: int):
+    """pcl_bgzf_walk over the bytes of `view`: (number of members, compressed bytes consumed, inflated bytes)."""
+    n, used, out = C.c_uint32(), C.c_uint64(), C.c_uint64()
+    rc = lib().pcl_bgzf_walk(view.ctypes.data if len(view) else None, len(view), int(want_out), members, cap,
+                             C.byref(n), C.byref(used), C.byref(out))
+    return rc, n.value, used.value, out.value
+
+
+INFLATED_STATS = {"kernel_ms": 0.0, "out_bytes": 0, "launches": 0}      # summed over the closed sources of this process
+
+
+class BgzfDeviceSource:
+    """The files of one read, all BGZF, as a sliding block in DEVICE memory: the compressed bytes are read from the files'
+    memory maps, copied to the device as they are and inflated there (csrc/inflate.cuh), one warp per member.  Same
+    interface and the same double-buffer discipline as TextSource; block() is a DevBlock.
+
+    A batch always holds whole members, so a read may overshoot what was asked for by less than one member (64 KB):
+    the buffers carry that much slack."""
+
+    SLACK = 1 << 17
+    MEMBERS_CAP = 1 << 15
+
+    def __init__(self, paths: Sequence[str], block_bytes: int, backend):
+        import mmap
+        self.paths = list(paths)
+        self.backend = backend
+        self.maps, self.views = [], []
+        for p in self.paths:
+            with open(p, "rb") as fh:
+                m = mmap.mmap(fh.fileno(), 0, access=mmap.ACCESS_READ)
+            self.maps.append(m)
+            self.views.append(np.frombuffer(m, dtype=np.uint8))
+        self.k = 0                               # file being read, and the position in it
+        self.fpos = 0
+        self.last_byte = 0x0A
+        self.eof = False
+        self.cap = int(block_bytes)
+        self.members = (_ffi.BgzfMember * self.MEMBERS_CAP)()
+        self.slots = [0, 1]
+        self.base = [0, 0]
+        self._alloc(self.slots, 2 * self.cap)
+        self.cur = 0
+        self.start = self.end = self.reserve
+        self.pending = None
+
+    @staticmethod
+    def eligible(paths: Sequence[str]) -> bool:
+        """Every file starts with a BGZF member (gzip magic, FEXTRA with a 'BC' field)."""
+        if not paths:
+            return False
+        members = (_ffi.BgzfMember * 1)()
+        for p in paths:
+            try:
+                with open(p, "rb") as fh:
+                    head = np.frombuffer(fh.read(1 << 16), dtype=np.uint8)
+                    size = os.fstat(fh.fileno()).st_size
+            except OSError:
+                return False
+            if size == 0 or len(head) < 18 or head[0] != 0x1F or head[1] != 0x8B:
+                return False
+            rc, _n, used, _out = bgzf_walk(head, 1, members, 1)
+            if rc < 0 or (used == 0 and size <= len(head)):
+                return False
+        return True
+
+    def _alloc(self, slots, size: int) -> None:
+        self.size = int(size)
+        self.reserve = self.size // 2
+        for k, s in enumerate(slots):
+            self.base[k] = self.backend.buffer(s, self.size + self.SLACK + 16)
+
+    def close(self) -> None:
+        if self.pending is not None:
+            try:
+                self.pending.result()
+            except Exception:
+                pass
+            self.pending = None
+        if self.backend is not None:
+            if hasattr(self.backend, "stats"):
+                for key, v in self.backend.stats().items():
+                    INFLATED_STATS[key] += v
+            self.backend.close()
+            self.backend = None
+        self.views = []
+        for m in self.maps:
+            try:
+                m.close()
+            except BufferError:
+                pass
+        self.maps = []
+
+    def _read_into(self, which: int, offset: int, want: int) -> int:
+        """Inflate whole members into buffer `which` from `offset` on until at least `want` bytes are there (or the input
+        ends); a file that does not end in a newline gets one (Read::open chains the files, read.rs:98-108)."""
+        slot = self.slots[which]
+        got = 0
+        while got < want and not self.eof:
+            if self.k >= len(self.views):
+                self.eof = True
+                break
+            v = self.views[self.k]
+            if self.fpos >= len(v):                                   # this file is done
+                if self.last_byte != 0x0A:
+                    self.backend.poke(slot, offset + got, b"\n")
+                    got += 1
+                    self.last_byte = 0x0A
+                self.k += 1
+                self.fpos = 0
+                continue
+            rest = v[self.fpos:]
+            rc, n, used, out = bgzf_walk(rest, want - got, self.members, self.MEMBERS_CAP)
+            if rc < 0 or used == 0:
+                raise _ffi.PclError(_ffi.PCL_ERR_INPUT, f"truncated or non-BGZF block in {self.paths[self.k]}")
+            if n:
+                self.backend.run(rest[:used], self.members, n, slot, offset + got)
+                got += out
+                # the last byte so far: what is left of the file may be empty members only (the end-of-file marker)
+                self.last_byte = self.backend.fetch(slot, offset + got - 1, 1)[0]
+            self.fpos += used
+        return got
+
+    def block(self) -> DevBlock:
+        return DevBlock(self.backend, self.slots[self.cur], self.base[self.cur], self.start, self.end - self.start)
+
+    def prefetch(self, pool: ThreadPoolExecutor, want: int) -> None:
+        assert self.pending is None
+        want = max(0, min(int(want), self.size - self.reserve))
+        self.pending = pool.submit(self._read_into, 1 - self.cur, self.reserve, want)
+
+    def advance(self, used: int) -> None:
+        """Drop `used` bytes from the front of the block and append what the prefetch inflated."""
+        got = self.pending.result() if self.pending is not None else 0
+        self.pending = None
+        lo = self.start + int(used)
+        tail = self.end - lo
+        cur, other = self.slots[self.cur], self.slots[1 - self.cur]
+        if tail <= self.reserve:
+            self.backend.move(cur, lo, other, self.reserve - tail, tail)
+            self.start, self.end = self.reserve - tail, self.reserve + got
+            self.cur = 1 - self.cur
+            return
+        # this read is far ahead of the others: rebuild the block at the front half of a fresh (possibly larger) pair
+        need = tail + got
+        spare = [s for s in range(4) if s not in self.slots]
+        old = list(self.slots)
+        old_reserve = self.reserve
+        size = self.size if need <= self.size - self.size // 2 else 4 * max(need, self.cap)
+        self.slots = spare
+        self._alloc(spare, size)
+        self.backend.move(cur, lo, spare[0], self.reserve, tail)
+        self.backend.move(other, old_reserve, spare[0], self.reserve + tail, got)
+        for s in old:
+            self.backend.buffer(s, 0)
+        self.cur = 0
+        self.start, self.end = self.reserve, self.reserve + need
+
+
 class TextGroupReader:
     """Fills chunks of a pipeline from the FASTQ files of a read-group, one record per file per group."""
 
@@ -335,6 +553,8 @@ class TextGroupReader:
             if MmapSource.eligible(f):
                 src = MmapSource(f, 0)
                 self.bpr[r] = src.bytes_per_record(self.bpr[r])          # measured on the first records, not guessed
+            elif device_inflate_enabled() and BgzfDeviceSource.eligible(f):
+                src = BgzfDeviceSource(f, int(self.target * self.bpr[r] * 1.25) + (1 << 16), DeviceInflater(pipe.ctx))
             else:
                 src = TextSource(f, int(self.target * self.bpr[r] * 1.25) + (1 << 16))
             self.sources.append(src)

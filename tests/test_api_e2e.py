@@ -63,6 +63,12 @@ def stripped(nm: bytes) -> bytes:
 
 
 def write_fastq(path, names, batch, gz):
+    if gz == "bgzf":                                               # BGZF: independent members, inflated on the device
+        from tests.test_ingest import bgzf_bytes
+        text = b"".join(b"@" + nm + b"\n" + batch.seq[i, :int(batch.length[i])].tobytes() + b"\n+\n" +
+                        batch.qual[i, :int(batch.length[i])].tobytes() + b"\n" for i, nm in enumerate(names))
+        open(path, "wb").write(bgzf_bytes(text, block=20000))
+        return
     op = gzip.open if gz else open
     with op(path, "wb") as fh:
         for i, nm in enumerate(names):
@@ -304,9 +310,12 @@ def test_mismatched_names_are_rejected(dataset, tmp_path, device_parse):
     assert ei.value.code == _ffi.PCL_ERR_INPUT
 
 
-@pytest.mark.parametrize("writer,compression,chunk_records", WRITERS)
-def test_make_fastq_paired_end_atac_like(tmp_path, monkeypatch, writer, compression, chunk_records):
-    """Paired-end layout (targets on both strands): R1.fq.zst and R2.fq.zst, neg-strand barcode read (I2)."""
+@pytest.mark.parametrize("writer,compression,chunk_records,container",
+                         [w + (True if w[2] > 700 else False,) for w in WRITERS] +       # the multi-chunk case reads plain files (memory-mapped input)
+                         [("device", "device", 262144, "bgzf"), ("device", "zstd", 700, "bgzf"), ("host", "zstd", 262144, "bgzf")])
+def test_make_fastq_paired_end_atac_like(tmp_path, monkeypatch, writer, compression, chunk_records, container):
+    """Paired-end layout (targets on both strands): R1.fq.zst and R2.fq.zst, neg-strand barcode read (I2).  Input as plain
+    files, gzip files, or BGZF files (inflated on the device, csrc/inflate.cuh)."""
     from precellar_b200 import Assay, _zstd, api, compile_layout
     from precellar_b200.api import make_fastq
     monkeypatch.setattr(api, "MIN_CHUNK_RECORDS", chunk_records)
@@ -342,7 +351,7 @@ def test_make_fastq_paired_end_atac_like(tmp_path, monkeypatch, writer, compress
     order = [p.read_id for p in layout0.reads]
     for r, rid in enumerate(order):
         names = [f"q{i}/{1 if rid != 'atac-R2' else 2}".encode() for i in range(n)]
-        gz = chunk_records > 700                                   # the multi-chunk case reads plain files (memory-mapped input)
+        gz = container
         write_fastq(os.path.join(td, rid + (".fq.gz" if gz else ".fq")), names, full[r], gz)
         a.update_read(rid, fastq=os.path.join(td, rid + (".fq.gz" if gz else ".fq")))
     out = os.path.join(td, "out")

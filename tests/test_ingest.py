@@ -305,3 +305,137 @@ def test_mmap_source_walks_plain_files_without_copies(tmp_path, seed):
     finally:
         del blk
         src.close()
+
+
+# ---------------------------------------------------------------------------------------------------
+# textingest.BgzfDeviceSource: the sliding block in DEVICE memory, fed by the device inflate.  Host logic only: the
+# device buffers are numpy arrays and the kernel is the host run of csrc/inflate_core.h (tests/emul).
+# ---------------------------------------------------------------------------------------------------
+class FakeInflater:
+    def __init__(self):
+        self.slots = {}
+        self.closed = False
+        self.runs = 0
+
+    def buffer(self, slot, nbytes):
+        if nbytes == 0:
+            self.slots.pop(slot, None)
+            return 0
+        if slot not in self.slots or len(self.slots[slot]) < nbytes:
+            self.slots[slot] = np.full(nbytes, 0xEE, np.uint8)
+        return self.slots[slot].ctypes.data
+
+    def run(self, comp, members, n, slot, dst_off):
+        import ctypes as C
+        from tests import util as U
+        L = U.emul_lib()
+        L.emu_inflate.restype = C.c_int64
+        L.emu_inflate.argtypes = [C.c_char_p, C.c_uint64, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint64, C.c_int]
+        out = self.slots[slot][dst_off:]
+        rc = L.emu_inflate(comp.tobytes() + b"\0" * 16, len(comp), C.addressof(members), n, out.ctypes.data, len(out), self.runs & 1)
+        self.runs += 1
+        if rc:
+            raise _ffi.PclError(_ffi.PCL_ERR_INPUT, f"corrupt BGZF block: member {(rc >> 8) - 1}, error {rc & 0xFF}")
+
+    def move(self, ss, so, ds, do, n):
+        assert so + n <= len(self.slots[ss]) and do + n <= len(self.slots[ds])
+        assert ss != ds or so + n <= do or do + n <= so
+        self.slots[ds][do:do + n] = self.slots[ss][so:so + n]
+
+    def fetch(self, slot, off, n):
+        assert off + n <= len(self.slots[slot])
+        return self.slots[slot][off:off + n].tobytes()
+
+    def poke(self, slot, off, data):
+        self.slots[slot][off:off + len(data)] = np.frombuffer(data, np.uint8)
+
+    def close(self):
+        self.closed = True
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2, 3, 4])
+def test_bgzf_device_source_reassembles_the_byte_stream(tmp_path, seed):
+    from concurrent.futures import ThreadPoolExecutor
+    from precellar_b200 import textingest
+    rng = np.random.default_rng(seed)
+    parts = [text_of(make_records(int(rng.integers(200, 3000)))) for _ in range(4)]
+    parts[1] = parts[1][:-1]                                           # a file without a final newline
+    paths = []
+    for k, data in enumerate(parts):
+        p = str(tmp_path / f"f{k}.fq.gz")
+        open(p, "wb").write(bgzf_bytes(data, block=int(rng.integers(500, 65000)), eof_marker=bool(k % 2)))
+        paths.append(p)
+    assert textingest.BgzfDeviceSource.eligible(paths)
+    want = parts[0] + parts[1] + b"\n" + parts[2] + parts[3]
+    cap = int(rng.integers(3000, 200000))
+    backend = FakeInflater()
+    src = textingest.BgzfDeviceSource(paths, cap, backend)
+    pool = ThreadPoolExecutor(max_workers=1)
+    got = bytearray()
+    try:
+        src.prefetch(pool, cap)
+        src.advance(0)
+        for _ in range(100000):
+            blk = src.block()
+            if len(blk) == 0 and src.eof:
+                break
+            assert blk.ptr == backend.slots[blk.slot].ctypes.data + blk.start
+            text = bytes(blk)
+            u = rng.random()
+            used = len(blk) if u < 0.3 else int(rng.integers(0, len(blk) + 1)) if u < 0.8 else int(rng.integers(0, min(len(blk), 50) + 1))
+            got += text[:used]
+            src.prefetch(pool, int(rng.integers(0, 2 * cap)))
+            src.advance(used)
+        else:
+            raise AssertionError("the source did not reach the end of its input")
+        assert bytes(got) == want
+        assert len(backend.slots) == 2                                 # rebuilt pairs were released
+    finally:
+        src.close()
+        pool.shutdown()
+    assert backend.closed
+
+
+def test_bgzf_device_source_eligibility_and_errors(tmp_path):
+    from concurrent.futures import ThreadPoolExecutor
+    from precellar_b200 import textingest
+    data = text_of(make_records(3000))
+    good = bgzf_bytes(data, block=5000)
+    p_bgzf, p_gz, p_plain = str(tmp_path / "a.gz"), str(tmp_path / "b.gz"), str(tmp_path / "c.fq")
+    open(p_bgzf, "wb").write(good)
+    open(p_gz, "wb").write(gzip.compress(data))
+    open(p_plain, "wb").write(data)
+    assert textingest.BgzfDeviceSource.eligible([p_bgzf])
+    assert not textingest.BgzfDeviceSource.eligible([p_bgzf, p_gz])    # an ordinary gzip file among them: the host path
+    assert not textingest.BgzfDeviceSource.eligible([p_plain])
+    assert not textingest.BgzfDeviceSource.eligible([str(tmp_path / "missing.gz")])
+    assert not textingest.BgzfDeviceSource.eligible([])
+    pool = ThreadPoolExecutor(max_workers=1)
+
+    def read_all(blob):
+        p = str(tmp_path / "x.gz")
+        open(p, "wb").write(blob)
+        src = textingest.BgzfDeviceSource([p], 20000, FakeInflater())
+        out = bytearray()
+        try:
+            src.prefetch(pool, 20000)
+            src.advance(0)
+            while not (len(src.block()) == 0 and src.eof):
+                out += bytes(src.block())
+                n = len(src.block())
+                src.prefetch(pool, 20000)
+                src.advance(n)
+        finally:
+            src.close()
+        return bytes(out)
+
+    assert read_all(good) == data
+    bad = bytearray(good)
+    bad[len(bad) // 2] ^= 0x55                                         # a flipped bit inside some member
+    with pytest.raises(_ffi.PclError):
+        read_all(bytes(bad))
+    with pytest.raises(_ffi.PclError):
+        read_all(good[:len(good) // 2])                                # cut inside a member
+    with pytest.raises(_ffi.PclError):
+        read_all(good[:20000] + gzip.compress(data))                   # an ordinary gzip member behind BGZF members
+    pool.shutdown()
