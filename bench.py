@@ -221,9 +221,24 @@ def measure_device_ingest(pipe, p1: str, p2: str, n_pairs: int) -> dict:
         variants.append(("gzip_files_pairs_per_s", p1 + ".gz", p2 + ".gz"))
     bgzf(p1, p1 + ".bgz")
     bgzf(p2, p2 + ".bgz")
+    # BGZF twice: members inflated on the device (k_bgzf_inflate, the default) and by the host threads (PCL_DEVICE_INFLATE=0)
     variants.append(("bgzf_files_pairs_per_s", p1 + ".bgz", p2 + ".bgz"))
+    variants.append(("bgzf_files_host_inflate_pairs_per_s", p1 + ".bgz", p2 + ".bgz"))
+    from precellar_b200 import textingest
     for key, a, b in variants:
-        rdr = TextGroupReader(pipe, [[a], [b]], per, [80, 210])
+        host_inflate = key == "bgzf_files_host_inflate_pairs_per_s"
+        saved = os.environ.get("PCL_DEVICE_INFLATE")
+        if host_inflate:
+            os.environ["PCL_DEVICE_INFLATE"] = "0"
+        for kk in textingest.INFLATED_STATS:
+            textingest.INFLATED_STATS[kk] = 0
+        try:
+            rdr = TextGroupReader(pipe, [[a], [b]], per, [80, 210])
+        finally:
+            if host_inflate:
+                os.environ.pop("PCL_DEVICE_INFLATE", None)
+                if saved is not None:
+                    os.environ["PCL_DEVICE_INFLATE"] = saved
         chs = [pipe.new_chunk(per) for _ in range(2)]
         try:
             t0 = time.perf_counter()
@@ -242,6 +257,12 @@ def measure_device_ingest(pipe, p1: str, p2: str, n_pairs: int) -> dict:
             for c in chs:
                 c.close()
                 pipe.chunks.remove(c)
+        st = textingest.INFLATED_STATS
+        if key == "bgzf_files_pairs_per_s" and st["launches"]:
+            out["bgzf_device_inflate"] = {"kernel": "k_bgzf_inflate", "launches": int(st["launches"]), "text_bytes": int(st["out_bytes"]),
+                                          "kernel_ms_sum": st["kernel_ms"], "text_GBps_per_launch_stream": st["out_bytes"] / st["kernel_ms"] / 1e6,
+                                          "note": "one warp per <= 64 KB member; a launch holds one chunk's members of one file (latency-bound: "
+                                                  "its duration is that of one member), the files' launches overlap on their own streams"}
     out["inflate_threads_per_file"] = max(1, min(8, (os.cpu_count() or 2) // 2))
     out["note"] = ("raw text -> device; line index and SoA planes (R1 32 B rows + 16 B quality window + lengths, R2 lengths, "
                    "name hashes) built by k_text_* kernels; host cores only move bytes")
@@ -738,8 +759,13 @@ def main():
     ingest = None
     if rank == 0 and world == 1 and not args.no_cpu and args.ingest_sample > 0:
         import tempfile
-        with tempfile.TemporaryDirectory() as td:
-            ingest = measure_ingest(syn, args.ingest_sample, td, pipe)
+        try:
+            with tempfile.TemporaryDirectory() as td:
+                ingest = measure_ingest(syn, args.ingest_sample, td, pipe)
+        except Exception as exc:                 # an extra like the API leg: a failure here must not take the headline line with it
+            import traceback
+            traceback.print_exc(file=sys.stderr)
+            ingest = {"error": f"{type(exc).__name__}: {exc}"}
     R.close()
 
     # ------------------------------------------------------------------ the other BASELINE configurations (one GPU)

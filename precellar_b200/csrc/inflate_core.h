@@ -80,7 +80,7 @@ struct InfWarp {
     uint32_t n_matches, n_runs;
     // the decoding lane's registers between phases
     uint64_t bitbuf;
-    uint32_t bitcnt, in_pos, out_pos;
+    uint32_t bitcnt, in_pos, out_pos, next_word;
     uint32_t status, error, bfinal;
     uint32_t st_src, st_dst, st_len;              // stored block: the copy the warp makes
     uint32_t n_lit, n_dist;                       // symbols of the current block's two codes
@@ -107,13 +107,15 @@ struct InfBits {
     const uint8_t *in;
     uint32_t lim;                // last position a refill may read from (8 bytes behind the member's data)
     uint32_t over;               // a refill was asked for behind it: zeros were fed instead, the stream is truncated
+    uint32_t nw;                 // the 32 bits at ip, loaded one refill ahead so that the load's latency is not waited for
+    INF_HD void prime() { nw = ip <= lim ? inf_load32(in, ip) : 0u; }
     INF_HD void refill() {
         if (bc <= 32u) {
-            uint32_t v = 0;
-            if (ip <= lim) v = inf_load32(in, ip); else over = 1u;
-            bb |= (uint64_t)v << bc;
+            if (ip > lim) over = 1u;
+            bb |= (uint64_t)nw << bc;
             ip += 4u;
             bc += 32u;
+            prime();
         }
     }
     INF_HD uint32_t peek(uint32_t n) const { return (uint32_t)bb & ((1u << n) - 1u); }
@@ -203,7 +205,7 @@ INF_HD uint32_t inf_cl_order(uint32_t i) {
 // tables from lens[]) or ERROR.
 // ---------------------------------------------------------------------------------------------------------------
 INF_HD_NOINLINE void inf_block_header(InfWarp &w, const uint8_t *in, uint32_t in_end, uint32_t out_cap) {
-    InfBits b{w.bitbuf, w.bitcnt, w.in_pos, in, in_end + 8u, 0u};
+    InfBits b{w.bitbuf, w.bitcnt, w.in_pos, in, in_end + 8u, 0u, w.next_word};
     uint32_t err = 0, status = INF_ST_CODES;
     b.refill();
     w.bfinal = b.take(1);
@@ -221,6 +223,7 @@ INF_HD_NOINLINE void inf_block_header(InfWarp &w, const uint8_t *in, uint32_t in
             w.st_src = src; w.st_dst = w.out_pos; w.st_len = len;
             w.out_pos += len;
             b.bb = 0; b.bc = 0; b.ip = src + len;
+            b.prime();
             status = INF_ST_STORED;
         }
     } else if (btype == 1u) {
@@ -285,7 +288,7 @@ INF_HD_NOINLINE void inf_block_header(InfWarp &w, const uint8_t *in, uint32_t in
         if (!inf_canonical(w, 0, 0, w.n_lit) || !inf_canonical(w, 1, 288u, w.n_dist)) err = INF_ERR_LENS;
     }
     if (!err && (b.over || b.byte_pos() > in_end)) err = INF_ERR_INPUT;
-    w.bitbuf = b.bb; w.bitcnt = b.bc; w.in_pos = b.ip;
+    w.bitbuf = b.bb; w.bitcnt = b.bc; w.in_pos = b.ip; w.next_word = b.nw;
     w.error = err;
     w.status = err ? INF_ST_ERROR : status;
 }
@@ -295,7 +298,7 @@ INF_HD_NOINLINE void inf_block_header(InfWarp &w, const uint8_t *in, uint32_t in
 // stored on the way, matches are queued and grouped into runs.
 // ---------------------------------------------------------------------------------------------------------------
 INF_HD void inf_decode(InfWarp &w, const uint8_t *in, uint32_t in_end, uint8_t *out, uint32_t out_cap) {
-    InfBits b{w.bitbuf, w.bitcnt, w.in_pos, in, in_end + 8u, 0u};
+    InfBits b{w.bitbuf, w.bitcnt, w.in_pos, in, in_end + 8u, 0u, w.next_word};
     uint32_t op = w.out_pos, nq = 0, nr = 0, run_pos = 0, pre = 0;
     uint32_t err = 0, status = INF_ST_BLOCK_END;
     for (;;) {
@@ -352,7 +355,7 @@ INF_HD void inf_decode(InfWarp &w, const uint8_t *in, uint32_t in_end, uint8_t *
     if (!err && (b.over || b.byte_pos() > in_end)) err = INF_ERR_INPUT;
     w.rstart[nr] = (uint8_t)nq;
     w.n_matches = nq; w.n_runs = nr;
-    w.bitbuf = b.bb; w.bitcnt = b.bc; w.in_pos = b.ip; w.out_pos = op;
+    w.bitbuf = b.bb; w.bitcnt = b.bc; w.in_pos = b.ip; w.next_word = b.nw; w.out_pos = op;
     w.error = err;
     w.status = err ? INF_ST_ERROR : status;
 }
@@ -441,6 +444,7 @@ INF_HD uint32_t inf_member(Exec &ex, InfWarp &w, const uint32_t *crc_tab, const 
     ex.each([&](uint32_t lane) {
         if (lane == 0) {
             w.bitbuf = 0; w.bitcnt = 0; w.in_pos = m.src_off; w.out_pos = 0;
+            w.next_word = inf_load32(in, m.src_off);
             w.error = 0; w.bfinal = 0; w.status = INF_ST_BLOCK_END;
         }
     });
