@@ -54,7 +54,8 @@ ZstdApi &zstd() {
 struct pcl_fastq {
     std::vector<std::string> paths;
     size_t cur = 0;
-    gzFile gz = nullptr;
+    gzFile gz = nullptr;                // uncompressed input (zlib's transparent mode)
+    pcl_gzsrc *gs = nullptr;            // gzip input: gzsrc.cpp (BGZF members in parallel, any other gzip through fastinflate.h)
     FILE *zf = nullptr;                 // .zst input
     void *zds = nullptr;
     std::vector<uint8_t> zin;
@@ -71,6 +72,7 @@ struct pcl_fastq {
     static bool is_zst(const std::string &p) { return p.size() > 4 && p.compare(p.size() - 4, 4, ".zst") == 0; }
     void close_cur() {
         if (gz) { gzclose(gz); gz = nullptr; }
+        if (gs) { pcl_gzsrc_close(gs); gs = nullptr; }
         if (zf) { fclose(zf); zf = nullptr; }
         if (zds) { zstd().freeDStream(zds); zds = nullptr; }
     }
@@ -93,6 +95,8 @@ struct pcl_fastq {
             zstd().initDStream(zds);
             zin.resize(1u << 20);
             zin_pos = zin_end = 0;
+        } else if (gzip_magic) {
+            if (pcl_gzsrc_open(path.c_str(), 4, &gs) != PCL_OK) { err = "cannot open file: " + path; eof_all = true; return false; }
         } else {
             gz = gzopen(path.c_str(), "rb");       // transparent for uncompressed files
             if (!gz) { err = "cannot open file: " + path; eof_all = true; return false; }
@@ -103,7 +107,7 @@ struct pcl_fastq {
     }
     bool fill() {
         for (;;) {
-            if (!gz && !zf && !open_next()) return false;
+            if (!gz && !gs && !zf && !open_next()) return false;
             if (zf) {
                 if (zin_pos == zin_end) {
                     zin_end = fread(zin.data(), 1, zin.size(), zf);
@@ -116,6 +120,13 @@ struct pcl_fastq {
                 zin_pos = in.pos;
                 if (out.pos == 0) continue;
                 pos = 0; end = out.pos;
+                return true;
+            }
+            if (gs) {
+                const int64_t n = pcl_gzsrc_read(gs, buf.data(), buf.size());
+                if (n < 0) { err = pcl_gzsrc_error(gs); eof_all = true; return false; }
+                if (n == 0) { close_cur(); continue; }
+                pos = 0; end = (size_t)n;
                 return true;
             }
             int n = gzread(gz, buf.data(), (unsigned)buf.size());

@@ -513,3 +513,41 @@ int64_t emu_inflate(const uint8_t *comp, uint64_t comp_bytes, const InfMember *m
 uint32_t emu_inflate_warp_bytes() { return (uint32_t)sizeof(InfWarp); }
 
 }  // extern "C"
+
+// ------------------------------------------------------------------------------------------
+// fastinflate.h (the host decoder behind pcl_gzsrc for ordinary gzip files): one raw DEFLATE stream, the input arriving
+// in pieces of `piece` bytes, the output taken `take` bytes at a time
+// ------------------------------------------------------------------------------------------
+#include "../../precellar_b200/csrc/fastinflate.h"
+extern "C" {
+// returns the number of bytes produced, or -1 - (error: 1 decode error, 2 output too small, 3 stalled); *consumed = bytes
+// of the stream (so that the caller can check where it ended)
+int64_t emu_fast_inflate(const uint8_t *src, uint64_t n, uint8_t *dst, uint64_t cap, uint64_t piece, uint64_t take, uint64_t *consumed) {
+    std::vector<uint8_t> buf(n + 64, 0);
+    if (n) memcpy(buf.data(), src, n);
+    static pcl_fi::Inflater *fi = nullptr;
+    if (!fi) fi = new pcl_fi::Inflater();
+    fi->reset();
+    fi->rd = fi->out;
+    const uint8_t *in = buf.data();
+    uint64_t arrived = piece < n ? piece : n, produced = 0;
+    for (int guard = 0; guard < (1 << 28); ++guard) {
+        const pcl_fi::Status st = fi->run(&in, buf.data() + arrived, arrived == n);
+        while (fi->pending()) {
+            uint64_t k = fi->pending() < take ? fi->pending() : take;
+            if (produced + k > cap) return -3;
+            memcpy(dst + produced, fi->rd, k);
+            fi->rd += k;
+            produced += k;
+        }
+        if (fi->window_full()) fi->slide();
+        if (st == pcl_fi::FI_END) { *consumed = (uint64_t)(in - buf.data()); return (int64_t)produced; }
+        if (st == pcl_fi::FI_ERROR) return -2;
+        if (st == pcl_fi::FI_NEED_INPUT) {
+            if (arrived == n) return -4;
+            arrived = arrived + piece < n ? arrived + piece : n;
+        }
+    }
+    return -4;
+}
+}  // extern "C"

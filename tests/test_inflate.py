@@ -173,3 +173,80 @@ def test_damaged_members_are_errors():
         s = bytes(rng.integers(0, 256, int(rng.integers(1, 2000)), dtype=np.uint8))
         rc, _ = run([text], [s])
         assert rc != 0
+
+
+# ---------------------------------------------------------------------------------------------------
+# csrc/fastinflate.h: the host decoder behind pcl_gzsrc for ordinary gzip files (one DEFLATE stream per file), against zlib
+# ---------------------------------------------------------------------------------------------------
+def fast_inflate(stream: bytes, n_out: int, piece=1 << 30, take=1 << 30, tail=b""):
+    L = U.emul_lib()
+    L.emu_fast_inflate.restype = C.c_int64
+    L.emu_fast_inflate.argtypes = [C.c_char_p, C.c_uint64, C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, C.POINTER(C.c_uint64)]
+    out = np.full(n_out + 64, 0xEE, np.uint8)
+    used = C.c_uint64()
+    data = stream + tail
+    rc = L.emu_fast_inflate(data, len(data), out.ctypes.data, n_out, piece, take, C.byref(used))
+    assert bytes(out[n_out:]) == b"\xEE" * 64
+    return rc, bytes(out[:max(rc, 0)]), used.value
+
+
+@pytest.mark.parametrize("level", [0, 1, 6, 9])
+def test_fast_inflate_streams_of_every_kind(level):
+    rng = np.random.default_rng(40 + level)
+    text = fastq_text(rng, 12000)                              # ~ 3 MB: several windows of the decoder
+    noise = bytes(rng.integers(0, 256, 200000, dtype=np.uint8))
+    cases = [text, text[:1], b"", text[:700000] + noise + text[:900000], b"\0" * 1500000, b"AB" * 400000,
+             bytes(rng.integers(0, 4, 800000, dtype=np.uint8))]
+    for k, data in enumerate(cases):
+        for strategy, flush in ((zlib.Z_DEFAULT_STRATEGY, 0), (zlib.Z_FIXED, 0), (zlib.Z_DEFAULT_STRATEGY, 30011), (zlib.Z_RLE, 0)):
+            s = deflate(data, level, strategy, flush_every=flush)
+            rc, out, used = fast_inflate(s, len(data), tail=b"TRAILER!")
+            assert rc == len(data) and out == data and used == len(s), (k, strategy, flush)
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_fast_inflate_input_in_pieces_and_output_in_sips(seed):
+    """The input arrives in pieces (the decoder asks for more with fewer than 2 KB left), the output is taken in small
+    amounts; stored blocks span pieces and windows."""
+    rng = np.random.default_rng(60 + seed)
+    text = fastq_text(rng, 6000) + bytes(rng.integers(0, 256, 150000, dtype=np.uint8)) + fastq_text(rng, 2000)
+    for level in (0, 1, 6):
+        s = deflate(text, level, flush_every=int(rng.integers(0, 2)) * 50000)
+        for piece, take in ((1 << 30, 7), (4096, 1 << 30), (2049, 100000), (int(rng.integers(2100, 70000)), int(rng.integers(1, 300000))),
+                            (100, 1 << 30), (1, 65536)):
+            rc, out, used = fast_inflate(s, len(text), piece, take, tail=b"12345678")
+            assert rc == len(text) and out == text and used == len(s), (level, piece, take)
+
+
+def test_fast_inflate_damaged_streams_are_errors():
+    rng = np.random.default_rng(70)
+    text = fastq_text(rng, 3000)
+    good = deflate(text, 6)
+    rc, _, _ = fast_inflate(good[:len(good) // 2], len(text))
+    assert rc < 0                                              # truncated
+    rc, _, _ = fast_inflate(b"\x07" + good, len(text))
+    assert rc < 0                                              # reserved block type
+    rc, _, _ = fast_inflate(b"\x01\x05\x00\x00\x00abcde", 5)
+    assert rc < 0                                              # stored block whose NLEN is wrong
+    rc, out, _ = fast_inflate(b"\x01\x05\x00\xfa\xffabcde", 5)
+    assert rc == 5 and out == b"abcde"
+    bad = 0
+    for k in range(300):
+        s = bytearray(good)
+        for _ in range(int(rng.integers(1, 4))):
+            s[int(rng.integers(0, len(s)))] ^= 1 << int(rng.integers(0, 8))
+        if k % 3 == 0:
+            s = s[:int(rng.integers(1, len(s)))]
+        rc, out, _ = fast_inflate(bytes(s), len(text) + 70000, piece=[1 << 30, 5000][k % 2])
+        if rc < 0:
+            bad += 1
+        else:                                                  # decodes to something: zlib must agree byte for byte (no CRC at this level)
+            try:
+                want = zlib.decompressobj(-15).decompress(bytes(s))
+            except zlib.error:
+                want = None
+            assert want is None or out[:len(want)] == want[:len(out)]
+    assert bad >= 100                                          # every truncated stream at least (the CRC is the caller's: pcl_gzsrc)
+    for k in range(200):
+        rc, _, _ = fast_inflate(bytes(rng.integers(0, 256, int(rng.integers(1, 3000)), dtype=np.uint8)), 1 << 20)
+        assert rc < 0 or rc >= 0                               # noise: any outcome but a crash or an out-of-bounds write

@@ -439,3 +439,57 @@ def test_bgzf_device_source_eligibility_and_errors(tmp_path):
     with pytest.raises(_ffi.PclError):
         read_all(good[:20000] + gzip.compress(data))                   # an ordinary gzip member behind BGZF members
     pool.shutdown()
+
+
+def test_gzsrc_ordinary_gzip_members_headers_and_refills(tmp_path, monkeypatch):
+    """The fastinflate route of pcl_gzsrc: members with every optional header field, an empty member, input buffers of
+    8 KB..1 MB (many refills, stored blocks and headers across them), odd read sizes; zlib route for comparison."""
+    import struct
+    import zlib
+    rng = np.random.default_rng(9)
+    text = text_of(make_records(30000))
+    noise = bytes(rng.integers(0, 256, 200000, dtype=np.uint8))
+
+    def member(data, level=6, flags=0, extra=b"", name=b"", comment=b""):
+        co = zlib.compressobj(level, zlib.DEFLATED, -15)
+        body = co.compress(data) + co.flush()
+        head = b"\x1f\x8b\x08" + bytes([flags]) + b"\0\0\0\0\x00\x03"
+        if flags & 4:
+            head += struct.pack("<H", len(extra)) + extra
+        if flags & 8:
+            head += name + b"\0"
+        if flags & 16:
+            head += comment + b"\0"
+        if flags & 2:
+            head += struct.pack("<H", zlib.crc32(head) & 0xFFFF)
+        return head + body + struct.pack("<II", zlib.crc32(data) & 0xFFFFFFFF, len(data) & 0xFFFFFFFF)
+
+    parts = [text[:400000], b"", noise, text[400000:], b"x"]
+    blob = (member(parts[0], 6, 8, name=b"reads_R1.fastq") + member(parts[1], 6) + member(parts[2], 0, 4 | 16, extra=b"ab\x03\x00xyz", comment=b"c" * 300) +
+            member(parts[3], 1, 2 | 8 | 16, name=b"n", comment=b"") + member(parts[4], 9, 4, extra=b""))
+    want = b"".join(parts)
+    p = str(tmp_path / "m.gz")
+    open(p, "wb").write(blob)
+    for buf in (8192, 10000, 70001, 1 << 20, None):
+        if buf is None:
+            monkeypatch.delenv("PCL_GZSRC_BUF", raising=False)
+        else:
+            monkeypatch.setenv("PCL_GZSRC_BUF", str(buf))
+        for sizes in ([1 << 20], [7, 100000, 1, 65536, 333], [3_000_000]):
+            assert gz_read_all(p, sizes) == (want, False), (buf, sizes)
+    monkeypatch.setenv("PCL_ZLIB_INFLATE", "1")
+    assert gz_read_all(p, [1 << 20]) == (want, False)
+    monkeypatch.delenv("PCL_ZLIB_INFLATE")
+    monkeypatch.setenv("PCL_GZSRC_BUF", "8192")
+    one = member(text[:300000], 6)
+    for bad in (one[:-8] + struct.pack("<II", (zlib.crc32(text[:300000]) ^ 4) & 0xFFFFFFFF, 300000),      # CRC-32
+                one[:-4] + struct.pack("<I", 299999),                                                       # ISIZE
+                one + b"garbage after the member",                                                          # no gzip header
+                one + one[:200],                                                                            # second member cut off
+                one[:len(one) // 3],                                                                        # cut inside the stream
+                one[:10], b"\x1f\x8b\x08"):                                                                 # cut inside / right behind the header
+        open(p, "wb").write(bad)
+        with pytest.raises(_ffi.PclError):
+            gz_read_all(p, [50000])
+    open(p, "wb").write(one + one)
+    assert gz_read_all(p, [50000])[0] == text[:300000] * 2

@@ -188,7 +188,7 @@ def emul_lib():
         # how out-of-bounds accesses in the __host__ __device__ record logic are hunted
         san = os.environ.get("PCL_EMUL_SANITIZE") == "1"
         so = os.path.join(HERE, "emul", "libemul_san.so" if san else "libemul.so")
-        deps = [src] + [os.path.join(HERE, "..", "precellar_b200", "csrc", f) for f in ("hd_core.h", "host_build.h", "zhuff_core.h", "emit_core.h", "inflate_core.h")] + \
+        deps = [src] + [os.path.join(HERE, "..", "precellar_b200", "csrc", f) for f in ("hd_core.h", "host_build.h", "zhuff_core.h", "emit_core.h", "inflate_core.h", "fastinflate.h")] + \
                [os.path.join(HERE, "..", "include", "precellar_b200.h")]
         if not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps if os.path.exists(d)):
             subprocess.check_call(["g++", "-O1" if san else "-O2", "-g", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off"] +

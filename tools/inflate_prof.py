@@ -1,5 +1,8 @@
-"""BGZF input through the API with the members inflated on the device against the host threads:
-python tools/inflate_prof.py N [out.json]   (needs a GPU).  FASTQ(.bgz) files -> make_fastq(writer=device, compression=device)."""
+"""Compressed input through the API, new decoder against old, alternating in one process (needs a GPU):
+python tools/inflate_prof.py N [out.json] [bgzf|gzip]
+  bgzf: members inflated on the device (k_bgzf_inflate) against the host threads (PCL_DEVICE_INFLATE=0)
+  gzip: one stream per file through csrc/fastinflate.h against zlib (PCL_ZLIB_INFLATE=1)
+FASTQ files -> make_fastq(writer=device, compression=device)."""
 import json
 import os
 import sys
@@ -13,14 +16,17 @@ from precellar_b200 import api, textingest
 from precellar_b200.api import make_fastq
 
 n = int(sys.argv[1])
+fmt = sys.argv[3] if len(sys.argv) > 3 else "bgzf"
+SWITCH = {"bgzf": ("PCL_DEVICE_INFLATE", {"old": "0", "new": "1"}), "gzip": ("PCL_ZLIB_INFLATE", {"old": "1", "new": "0"})}[fmt]
 rows = []
 with tempfile.TemporaryDirectory() as td:
     w, spec, files = A.make_inputs(td, n)
-    comp_bytes = sum(os.path.getsize(p) for p in files["bgzf"].values())
+    comp_bytes = sum(os.path.getsize(p) for p in files[fmt].values())
     text_bytes = sum(os.path.getsize(p) for p in files["plain"].values())
     digests = set()
-    for mode in ("0", "1", "0", "1"):
-        os.environ["PCL_DEVICE_INFLATE"] = mode
+    for which in ("old", "new", "old", "new"):
+        mode = "1" if which == "new" else "0"
+        os.environ[SWITCH[0]] = SWITCH[1][which]
         out = os.path.join(td, "o_" + mode)
         best = None
         for rep in range(3):
@@ -28,13 +34,14 @@ with tempfile.TemporaryDirectory() as td:
                 textingest.INFLATED_STATS[k] = 0
             api.TIMING.clear()
             t0 = time.perf_counter()
-            a = A.assay_for(spec, files["bgzf"])
+            a = A.assay_for(spec, files[fmt])
             make_fastq(a, modality="atac", out_dir=out, correct_barcode=True, writer="device", compression="device")
             tot = time.perf_counter() - t0
             if rep and (best is None or tot < best[0]):
                 best = (tot, dict(api.TIMING), dict(textingest.INFLATED_STATS))
         digests.add(A._digest(os.path.join(out, "R1.fq.zst")) + A._digest(os.path.join(out, "R2.fq.zst")))
-        row = {"device_inflate": mode == "1", "n": n, "total_s": round(best[0], 4), "triples_per_s": round(n / best[0]),
+        row = {"format": fmt, "decoder": {"bgzf": ("host threads (zlib)", "k_bgzf_inflate"), "gzip": ("zlib", "fastinflate.h")}[fmt][which == "new"],
+               "device_inflate": fmt == "bgzf" and which == "new", "n": n, "total_s": round(best[0], 4), "triples_per_s": round(n / best[0]),
                "pass1_text_parse_s": round(best[1].get("pass1_text_parse", 0.0), 4), "inflate": best[2],
                "text_bytes": text_bytes, "compressed_bytes": comp_bytes}
         if best[2]["kernel_ms"]:
@@ -42,7 +49,7 @@ with tempfile.TemporaryDirectory() as td:
         rows.append(row)
         print(json.dumps(row), flush=True)
     ok = len(digests) == 1
-    print("outputs identical with and without the device inflate:", ok)
+    print("outputs identical with both decoders:", ok)
 if len(sys.argv) > 2:
     with open(sys.argv[2], "w") as fh:
         for r in rows:
