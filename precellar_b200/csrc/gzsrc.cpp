@@ -66,11 +66,13 @@ struct pcl_gzsrc {
     uint64_t member_bytes = 0, members = 0;
     bool file_eof = false;
 
+    size_t grow_to = 0;
     size_t ccap() const { return cbuf.size() - 64; }     // 64 zero bytes behind the data: the decoder reads ahead
     bool fill_c() {             // keep the unconsumed tail, read more
         if (cpos && cpos < cend) memmove(cbuf.data(), cbuf.data() + cpos, cend - cpos);
         cend -= cpos;
         cpos = 0;
+        if (ccap() < grow_to) cbuf.resize(grow_to + 64);
         const size_t got = fread(cbuf.data() + cend, 1, ccap() - cend, f);
         cend += got;
         memset(cbuf.data() + cend, 0, 64);
@@ -110,12 +112,16 @@ int pcl_gzsrc_open(const char *path, int n_threads, pcl_gzsrc **out) {
     s->f = f;
     s->path = path;
     s->n_threads = n_threads < 1 ? 1 : n_threads;
-    size_t buf_bytes = 64u << 20;
-    if (const char *b = getenv("PCL_GZSRC_BUF")) buf_bytes = std::max<size_t>(8192, (size_t)strtoull(b, nullptr, 10));   // tests: many refills
-    s->cbuf.resize(buf_bytes + 64);
-    s->cend = fread(s->cbuf.data(), 1, std::min<size_t>(s->ccap(), 1u << 20), f);     // enough for the format probe and a first batch
+    // the input buffer starts small (a reader that only looks at the first records - infer_length - must not pay for
+    // 32 MB of zeroed memory) and takes its working size once the format is known: BGZF batches feed several threads,
+    // a single stream only needs to keep fread busy
+    const char *bufenv = getenv("PCL_GZSRC_BUF");                                        // tests: many refills
+    const size_t forced = bufenv ? std::max<size_t>(8192, (size_t)strtoull(bufenv, nullptr, 10)) : 0;
+    s->cbuf.resize((forced ? forced : (size_t)(256u << 10)) + 64);
+    s->cend = fread(s->cbuf.data(), 1, s->ccap(), f);
     memset(s->cbuf.data() + s->cend, 0, 64);
     s->bgzf = bgzf_block_size(s->cbuf.data(), s->cend) != 0;
+    s->grow_to = forced ? forced : (s->bgzf ? (size_t)(32u << 20) : (size_t)(4u << 20));
     const char *force_zlib = getenv("PCL_ZLIB_INFLATE");
     if (!s->bgzf && !(force_zlib && force_zlib[0] == '1') && s->cend >= 3 && s->cbuf[0] == 0x1f && s->cbuf[1] == 0x8b && s->cbuf[2] == 8) {
         s->fi = new pcl_fi::Inflater();
