@@ -553,10 +553,19 @@ class TextGroupReader:
             if MmapSource.eligible(f):
                 src = MmapSource(f, 0)
                 self.bpr[r] = src.bytes_per_record(self.bpr[r])          # measured on the first records, not guessed
-            elif device_inflate_enabled() and BgzfDeviceSource.eligible(f):
-                src = BgzfDeviceSource(f, int(self.target * self.bpr[r] * 1.25) + (1 << 16), DeviceInflater(pipe.ctx))
             else:
-                src = TextSource(f, int(self.target * self.bpr[r] * 1.25) + (1 << 16))
+                src = None
+                if device_inflate_enabled() and BgzfDeviceSource.eligible(f):
+                    inf = DeviceInflater(pipe.ctx)
+                    try:
+                        src = BgzfDeviceSource(f, int(self.target * self.bpr[r] * 1.25) + (1 << 16), inf)
+                    except _ffi.PclError as exc:                     # no room for the device text buffers: the host threads inflate
+                        inf.close()
+                        if exc.code != _ffi.PCL_ERR_NOMEM:
+                            self.close()
+                            raise
+                if src is None:
+                    src = TextSource(f, int(self.target * self.bpr[r] * 1.25) + (1 << 16))
             self.sources.append(src)
         self.first = True
         self.records = 0
