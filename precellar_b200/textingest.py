@@ -400,8 +400,12 @@ class BgzfDeviceSource:
 
     SLACK = 1 << 17
     MEMBERS_CAP = 1 << 15
+    # A launch of the inflate kernel lasts as long as its slowest member takes one warp (about 4 ms for 64 KB), whatever the
+    # number of members up to the 4 736 warps a B200 holds: the source inflates up to this much text per launch (a whole
+    # file of a few hundred MB at once) and then nothing until fewer than two chunks are buffered (TextGroupReader._want).
+    AHEAD_BYTES = 256 << 20
 
-    def __init__(self, paths: Sequence[str], block_bytes: int, backend):
+    def __init__(self, paths: Sequence[str], block_bytes: int, backend, ahead_bytes: int = 0):
         import mmap
         self.paths = list(paths)
         self.backend = backend
@@ -411,6 +415,9 @@ class BgzfDeviceSource:
                 m = mmap.mmap(fh.fileno(), 0, access=mmap.ACCESS_READ)
             self.maps.append(m)
             self.views.append(np.frombuffer(m, dtype=np.uint8))
+        # text inflated per launch: no more than the files can hold (FASTQ text deflates to a fifth; 8 is generous)
+        self.ahead_bytes = min(int(ahead_bytes), 8 * sum(len(v) for v in self.views) + (1 << 16)) if ahead_bytes else 0
+        block_bytes = max(int(block_bytes), self.ahead_bytes)
         self.k = 0                               # file being read, and the position in it
         self.fpos = 0
         self.last_byte = 0x0A
@@ -501,8 +508,12 @@ class BgzfDeviceSource:
             self.fpos += used
         return got
 
-    def block(self) -> DevBlock:
-        return DevBlock(self.backend, self.slots[self.cur], self.base[self.cur], self.start, self.end - self.start)
+    def block(self, limit: Optional[int] = None) -> DevBlock:
+        """The buffered text, or its first `limit` bytes (the reader indexes one chunk's worth, not everything inflated ahead)."""
+        n = self.end - self.start
+        if limit is not None:
+            n = min(n, int(limit))
+        return DevBlock(self.backend, self.slots[self.cur], self.base[self.cur], self.start, n)
 
     def prefetch(self, pool: ThreadPoolExecutor, want: int) -> None:
         assert self.pending is None
@@ -513,6 +524,9 @@ class BgzfDeviceSource:
         """Drop `used` bytes from the front of the block and append what the prefetch inflated."""
         got = self.pending.result() if self.pending is not None else 0
         self.pending = None
+        if got == 0:                                     # nothing new behind the gap of the other buffer: the block shrinks in place
+            self.start += int(used)
+            return
         lo = self.start + int(used)
         tail = self.end - lo
         cur, other = self.slots[self.cur], self.slots[1 - self.cur]
@@ -558,7 +572,8 @@ class TextGroupReader:
                 if device_inflate_enabled() and BgzfDeviceSource.eligible(f):
                     inf = DeviceInflater(pipe.ctx)
                     try:
-                        src = BgzfDeviceSource(f, int(self.target * self.bpr[r] * 1.25) + (1 << 16), inf)
+                        # room for the two chunks that may still be buffered when the next batch is inflated behind them
+                        src = BgzfDeviceSource(f, int(self.target * self.bpr[r] * 2.2) + (1 << 16), inf, BgzfDeviceSource.AHEAD_BYTES)
                     except _ffi.PclError as exc:                     # no room for the device text buffers: the host threads inflate
                         inf.close()
                         if exc.code != _ffi.PCL_ERR_NOMEM:
@@ -579,6 +594,11 @@ class TextGroupReader:
         """Bytes to read so that, after `blocks_ahead - 1` chunks were cut off the front, a full chunk is buffered."""
         have = self.sources[r].end - self.sources[r].start
         per = self.target * self.bpr[r]
+        ahead = getattr(self.sources[r], "ahead_bytes", 0)
+        if ahead:                                        # device inflate: big batches, and none while two chunks are buffered
+            if blocks_ahead > 1 and have >= int(per * 2.03) + 4096:
+                return 0
+            return max(0, max(ahead, int(per * (blocks_ahead + 0.03)) + 4096) - have)
         return max(0, int(per * (blocks_ahead + 0.03)) + 4096 - have)
 
     def next_into(self, chunk: Chunk) -> int:
@@ -592,7 +612,9 @@ class TextGroupReader:
             self.first = False
         grow = 1
         while True:
-            blocks = [s.block() for s in self.sources]
+            # a source that inflates ahead hands over one chunk's worth of its text (more when no whole group was in it)
+            blocks = [s.block(int(self.target * self.bpr[r] * 1.03 * grow) + 4096) if getattr(s, "ahead_bytes", 0) else s.block()
+                      for r, s in enumerate(self.sources)]
             for r, s in enumerate(self.sources):
                 if s.pending is None:
                     s.prefetch(self.pool, self._want(r, 2) if grow == 1 else grow * (1 << 20))
@@ -605,6 +627,9 @@ class TextGroupReader:
             # no complete group in the blocks: either the input ended or a record is larger than the block
             for s in self.sources:
                 s.advance(0)
+            if any(len(b) < s.end - s.start for b, s in zip(blocks, self.sources)):       # only a window was looked at: widen it
+                grow *= 2
+                continue
             if all(s.eof for s in self.sources):
                 rest = [bytes(s.block()).strip() for s in self.sources]
                 if all(not x for x in rest):

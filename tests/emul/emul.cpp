@@ -499,7 +499,8 @@ int64_t emu_inflate(const uint8_t *comp, uint64_t comp_bytes, const InfMember *m
                     int reverse) {
     uint32_t tab[256];
     for (uint32_t t = 0; t < 256u; ++t) tab[t] = inf_crc_table_entry(t);
-    static InfWarp w;
+    std::vector<InfWarp> state(1);               // per call: the tests drive several emulated inflaters from different threads
+    InfWarp &w = state[0];
     EmuWarpExec ex{reverse};
     for (uint32_t i = 0; i < n; ++i) {
         const InfMember &m = members[i];
@@ -525,10 +526,8 @@ extern "C" {
 int64_t emu_fast_inflate(const uint8_t *src, uint64_t n, uint8_t *dst, uint64_t cap, uint64_t piece, uint64_t take, uint64_t *consumed) {
     std::vector<uint8_t> buf(n + 64, 0);
     if (n) memcpy(buf.data(), src, n);
-    static pcl_fi::Inflater *fi = nullptr;
-    if (!fi) fi = new pcl_fi::Inflater();
-    fi->reset();
-    fi->rd = fi->out;
+    std::vector<pcl_fi::Inflater> state(1);
+    pcl_fi::Inflater *fi = &state[0];
     const uint8_t *in = buf.data();
     uint64_t arrived = piece < n ? piece : n, produced = 0;
     for (int guard = 0; guard < (1 << 28); ++guard) {

@@ -493,3 +493,78 @@ def test_gzsrc_ordinary_gzip_members_headers_and_refills(tmp_path, monkeypatch):
             gz_read_all(p, [50000])
     open(p, "wb").write(one + one)
     assert gz_read_all(p, [50000])[0] == text[:300000] * 2
+
+
+class FakeChunk:
+    """Stands in for pipeline.Chunk in TextGroupReader.next_into: the line index is numpy, the 'planes' are the bytes consumed."""
+
+    def __init__(self, capacity, n_reads):
+        self.capacity, self.n_reads = capacity, n_reads
+        self.text = [np.zeros(0, np.uint8)] * n_reads
+        self.taken = [bytearray() for _ in range(n_reads)]
+        self.scanned_bytes = 0
+        self.n = 0
+
+    def text_scan(self, r, b):
+        self.text[r] = np.frombuffer(bytes(b), np.uint8) if hasattr(b, "ptr") else np.array(b, copy=True)
+        self.scanned_bytes += len(self.text[r])
+
+    def text_lines(self, r):
+        return int((self.text[r] == 10).sum())
+
+    def reset(self, n):
+        self.n = n
+
+    def text_fill(self, r):
+        used = int(np.flatnonzero(self.text[r] == 10)[4 * self.n - 1]) + 1
+        self.taken[r] += self.text[r][:used].tobytes()
+        return used
+
+    def text_names_check(self):
+        return -1
+
+
+@pytest.mark.parametrize("target,ahead", [(300, 1 << 30), (300, 20000), (5000, 1 << 30), (50, 0)])
+def test_text_group_reader_over_bgzf_device_sources(tmp_path, monkeypatch, target, ahead):
+    """TextGroupReader.next_into over BgzfDeviceSource (emulated device): batches inflated far ahead of the chunk that is
+    parsed, the reader looking at one chunk's worth at a time; every byte of every file arrives once, in order."""
+    import types
+    from precellar_b200 import textingest
+    rng = np.random.default_rng(target + ahead % 7)
+    n = 4000
+    recs1, recs2 = make_records(n), make_records(n)
+    recs2 = [(nm, s * 3, q * 3) for nm, s, q in recs2]                  # the second read's records are three times as long
+    t1, t2 = text_of(recs1), text_of(recs2)
+    cut1, cut2 = text_of(recs1[:1500]), text_of(recs2[:2500])
+    files = [[str(tmp_path / "a1.gz"), str(tmp_path / "b1.gz")], [str(tmp_path / "a2.gz"), str(tmp_path / "b2.gz")]]
+    open(files[0][0], "wb").write(bgzf_bytes(cut1, block=7000))
+    open(files[0][1], "wb").write(bgzf_bytes(t1[len(cut1):], block=65000))
+    open(files[1][0], "wb").write(bgzf_bytes(cut2[:-1], block=30000))     # no final newline: one is supplied
+    open(files[1][1], "wb").write(bgzf_bytes(t2[len(cut2):], block=900))
+    fakes = []
+
+    def make(ctx):
+        fakes.append(FakeInflater())
+        return fakes[-1]
+    monkeypatch.setattr(textingest, "DeviceInflater", make)
+    monkeypatch.setattr(textingest.BgzfDeviceSource, "AHEAD_BYTES", ahead)
+    monkeypatch.setenv("PCL_DEVICE_INFLATE", "1")
+    rdr = textingest.TextGroupReader(types.SimpleNamespace(ctx=None), files, target, [40, 40])      # a poor guess of the record size
+    assert [type(s).__name__ for s in rdr.sources] == ["BgzfDeviceSource"] * 2
+    ch = FakeChunk(target, 2)
+    total = 0
+    try:
+        while True:
+            got = rdr.next_into(ch)
+            if got == 0:
+                break
+            assert got <= target
+            total += got
+    finally:
+        rdr.close()
+    assert total == n and bytes(ch.taken[0]) == t1 and bytes(ch.taken[1]) == t2
+    runs = sum(f.runs for f in fakes)
+    if ahead == 1 << 30:                                               # a few launches per file, not one per chunk
+        assert runs <= 8, runs
+        assert ch.scanned_bytes < 4 * (len(t1) + len(t2))              # and no chunk indexed the whole buffered text
+    assert all(f.closed for f in fakes)
