@@ -261,8 +261,8 @@ def measure_device_ingest(pipe, p1: str, p2: str, n_pairs: int) -> dict:
         if key == "bgzf_files_pairs_per_s" and st["launches"]:
             out["bgzf_device_inflate"] = {"kernel": "k_bgzf_inflate", "launches": int(st["launches"]), "text_bytes": int(st["out_bytes"]),
                                           "kernel_ms_sum": st["kernel_ms"], "text_GBps_per_launch_stream": st["out_bytes"] / st["kernel_ms"] / 1e6,
-                                          "note": "one warp per <= 64 KB member; a launch holds one chunk's members of one file (latency-bound: "
-                                                  "its duration is that of one member), the files' launches overlap on their own streams"}
+                                          "note": "one warp per <= 64 KB member; latency-bound (a launch lasts as long as one member takes its warp), "
+                                                  "so a launch holds up to 256 MB of text - a whole file here; the files' launches overlap on their own streams"}
     out["inflate_threads_per_file"] = max(1, min(8, (os.cpu_count() or 2) // 2))
     out["note"] = ("raw text -> device; line index and SoA planes (R1 32 B rows + 16 B quality window + lengths, R2 lengths, "
                    "name hashes) built by k_text_* kernels; host cores only move bytes")
