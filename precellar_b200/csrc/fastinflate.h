@@ -260,21 +260,19 @@ struct Inflater {
                         e = len_entry(r & 0xFFFFu) | (r >> 16);
                         if (e & FI_LIT) { FI_TAKE(e & 15u); *o++ = (uint8_t)(e >> 16); continue; }
                     }
-                    FI_TAKE(e & 15u);
-                    if (e & FI_EOB) { state = bfinal ? ST_DONE : ST_HEADER; break; }
-                    uint32_t x = (e >> 8) & 15u;
-                    const uint32_t len = (e >> 16) + ((uint32_t)b & ((1u << x) - 1u));
-                    FI_TAKE(x);
+                    if (e & FI_EOB) { FI_TAKE(e & 15u); state = bfinal ? ST_DONE : ST_HEADER; break; }
+                    uint32_t cl = e & 15u, x = (e >> 8) & 15u;
+                    const uint32_t len = (e >> 16) + (((uint32_t)b >> cl) & ((1u << x) - 1u));
+                    FI_TAKE(cl + x);
                     uint32_t de = dt[b & ((1u << FI_DBITS) - 1u)];
                     if (!de) {
                         const uint32_t r = slow(dcode, b);
                         if (r == ~0u || (r & 0xFFFFu) > 29u) { produced += (uint64_t)(o - o0); FI_FAIL("invalid code"); }
                         de = dist_entry(r & 0xFFFFu) | (r >> 16);
                     }
-                    FI_TAKE(de & 15u);
-                    x = (de >> 8) & 15u;
-                    const uint32_t dist = (de >> 16) + ((uint32_t)b & ((1u << x) - 1u));
-                    FI_TAKE(x);
+                    cl = de & 15u; x = (de >> 8) & 15u;
+                    const uint32_t dist = (de >> 16) + (((uint32_t)b >> cl) & ((1u << x) - 1u));
+                    FI_TAKE(cl + x);
                     if ((uint64_t)dist > produced + (uint64_t)(o - o0)) { produced += (uint64_t)(o - o0); FI_FAIL("match before the start of the stream"); }
                     const uint8_t *s = o - dist;
                     uint8_t *d = o;
