@@ -31,8 +31,12 @@
  *   pcl_qc_fetch_categories (precellar/src/qc.rs:30-69)
  *   pcl_fastq_*             Read::open + FastqReader::read_record + the per-file half of BatchedFqReader::next
  *                           (seqspec/src/read.rs:98-108,137-155; precellar/src/align/fastq.rs:400-448,612-621)
+ *   pcl_gzsrc_*,            open_file's MultiGzDecoder (seqspec/src/utils.rs:44-56): ordinary gzip on a host thread,
+ *   pcl_bgzf_walk,          BGZF members on the device (one warp per member), the text indexed where it is
+ *   pcl_inflater_*,
+ *   pcl_text_scan_device
  *
- * Threading: one host thread drives one ctx (one GPU).  Calls on a ctx are not re-entrant.
+ * Threading (a pcl_inflater has its own stream and may be driven from a thread of its own, one per read file): one host thread drives one ctx (one GPU).  Calls on a ctx are not re-entrant.
  * Different ctxs are independent.  Work on a chunk is stream-ordered on the chunk's stream;
  * pcl_chunk_fetch / pcl_sync block.
  *
