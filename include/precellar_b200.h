@@ -36,9 +36,10 @@
  *   pcl_inflater_*,
  *   pcl_text_scan_device
  *
- * Threading (a pcl_inflater has its own stream and may be driven from a thread of its own, one per read file): one host thread drives one ctx (one GPU).  Calls on a ctx are not re-entrant.
+ * Threading: one host thread drives one ctx (one GPU).  Calls on a ctx are not re-entrant.
  * Different ctxs are independent.  Work on a chunk is stream-ordered on the chunk's stream;
- * pcl_chunk_fetch / pcl_sync block.
+ * pcl_chunk_fetch / pcl_sync block.  A pcl_inflater has its own stream and staging and may be driven
+ * from a thread of its own (one per read file) next to the thread that drives the ctx.
  *
  * Errors: every function returns 0 or a negative pcl_status; pcl_last_error() gives the message.
  * Nothing throws or aborts across this boundary.  Per-read structural failures are data
