@@ -93,6 +93,50 @@ def decompress_file(path: str) -> bytes:
         return decompress(fh.read())
 
 
+class Reader:
+    """The decompressed bytes of a (multi-frame) .zst file as a stream: ``readinto`` fills the caller's buffer straight
+    from ZSTD_decompressStream, the file is read 4 MB at a time.  What open_file's zstd::stream::Decoder does
+    (seqspec/src/utils.rs:44-56), without holding the whole text in memory."""
+
+    def __init__(self, path: str, piece: int = 4 << 20):
+        self.L = lib()
+        self.fh = open(path, "rb", buffering=0)
+        self.path = path
+        self.ds = self.L.ZSTD_createDStream()
+        _check(self.L.ZSTD_initDStream(self.ds))
+        self.src = C.create_string_buffer(piece)
+        self.inb = _Buf(C.cast(self.src, C.c_void_p), 0, 0)
+        self.file_eof = False
+        self.mid_frame = False
+
+    def readinto(self, mv) -> int:
+        n = len(mv)
+        if n == 0 or self.ds is None:
+            return 0
+        dst = (C.c_uint8 * n).from_buffer(mv)
+        outb = _Buf(C.cast(dst, C.c_void_p), n, 0)
+        while outb.pos < n:
+            if self.inb.pos == self.inb.size and not self.file_eof:
+                got = self.fh.readinto(self.src)
+                self.inb = _Buf(C.cast(self.src, C.c_void_p), got or 0, 0)
+                self.file_eof = not got
+            before = (self.inb.pos, outb.pos)
+            r = _check(self.L.ZSTD_decompressStream(self.ds, C.byref(outb), C.byref(self.inb)))
+            if (self.inb.pos, outb.pos) != before:
+                self.mid_frame = r != 0                  # 0: a frame was decoded and flushed completely
+            elif self.file_eof and self.inb.pos == self.inb.size:
+                if self.mid_frame:
+                    raise RuntimeError("zstd: truncated frame in " + self.path)
+                break
+        return outb.pos
+
+    def close(self) -> None:
+        if self.ds is not None:
+            self.L.ZSTD_freeDStream(self.ds)
+            self.ds = None
+        self.fh.close()
+
+
 class Writer:
     """Append-only .zst writer: independent frames of up to `block` bytes (a valid multi-frame zstd file), compressed
     by `threads` workers (ZSTD_compress through ctypes releases the GIL) and written in order.  The reference writes

@@ -95,7 +95,7 @@ def _open_raw(path: str):
         return GzSource(path)
     if path.endswith(".zst"):
         from . import _zstd
-        return io.BytesIO(_zstd.decompress_file(path))
+        return _zstd.Reader(path)
     return open(path, "rb", buffering=0)
 
 

@@ -225,7 +225,8 @@ def test_text_source_reassembles_the_byte_stream(tmp_path, monkeypatch, seed):
     monkeypatch.setattr(textingest, "_pinned", lambda n: (np.empty(int(n), np.uint8), 0))
     monkeypatch.setattr(textingest, "_IO_SLICE", 4096)                 # plain files go through the sliced parallel reads
     rng = np.random.default_rng(seed)
-    parts = [text_of(make_records(int(rng.integers(200, 1500)))) for _ in range(4)]
+    from precellar_b200 import _zstd
+    parts = [text_of(make_records(int(rng.integers(200, 1500)))) for _ in range(5)]
     parts[1] = parts[1][:-1]                                           # a file without a final newline
     paths = []
     for k, data in enumerate(parts):
@@ -236,10 +237,12 @@ def test_text_source_reassembles_the_byte_stream(tmp_path, monkeypatch, seed):
             p += ".fq.gz"; open(p, "wb").write(gzip.compress(data))
         elif k == 2:
             p += ".bgz"; open(p, "wb").write(bgzf_bytes(data, block=3000))
+        elif k == 3:
+            p += ".fq.zst"; open(p, "wb").write(_zstd.compress(data[:len(data) // 3]) + _zstd.compress(data[len(data) // 3:]))    # two frames, streamed
         else:
             p += ".fq"; open(p, "wb").write(data)
         paths.append(p)
-    want = parts[0] + parts[1] + b"\n" + parts[2] + parts[3]           # the missing newline is supplied between the files
+    want = parts[0] + parts[1] + b"\n" + parts[2] + parts[3] + parts[4]   # the missing newline is supplied between the files
     cap = int(rng.integers(3000, 40000))
     src = textingest.TextSource(paths, cap)
     pool = ThreadPoolExecutor(max_workers=1)
