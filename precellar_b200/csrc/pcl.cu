@@ -2325,7 +2325,10 @@ int inf_fail(pcl_inflater *h, int code, const char *fmt, ...) {
 #define CUI(h, call)                                                                                \
     do {                                                                                            \
         cudaError_t e_ = (call);                                                                    \
-        if (e_ != cudaSuccess) return inf_fail(h, e_ == cudaErrorMemoryAllocation ? PCL_ERR_NOMEM : PCL_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(e_)); \
+        if (e_ != cudaSuccess) {                                                                    \
+            cudaGetLastError();      /* the caller may fall back to the host inflate: leave no stale error for its thread */ \
+            return inf_fail(h, e_ == cudaErrorMemoryAllocation ? PCL_ERR_NOMEM : PCL_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(e_)); \
+        }                                                                                           \
     } while (0)
 
 const char *inf_error_text(unsigned code) {
