@@ -116,7 +116,7 @@ int pcl_gzsrc_open(const char *path, int n_threads, pcl_gzsrc **out) {
     // 32 MB of zeroed memory) and takes its working size once the format is known: BGZF batches feed several threads,
     // a single stream only needs to keep fread busy
     const char *bufenv = getenv("PCL_GZSRC_BUF");                                        // tests: many refills
-    const size_t forced = bufenv ? std::max<size_t>(8192, (size_t)strtoull(bufenv, nullptr, 10)) : 0;
+    const size_t forced = (bufenv && *bufenv) ? std::max<size_t>(8192, (size_t)strtoull(bufenv, nullptr, 10)) : 0;
     s->cbuf.resize((forced ? forced : (size_t)(256u << 10)) + 64);
     s->cend = fread(s->cbuf.data(), 1, s->ccap(), f);
     memset(s->cbuf.data() + s->cend, 0, 64);
