@@ -119,7 +119,6 @@ def test_reader_on_bgzf_files_equals_the_host_inflate(tmp_path, monkeypatch, tar
     """TextGroupReader over BGZF files: members inflated on the device (BgzfDeviceSource) or by the host threads
     (PCL_DEVICE_INFLATE=0); every result plane and count must be equal.  Two files per read, one with CRLF line ends,
     one without a final newline; the small target forces many carried-over tails."""
-    from precellar_b200 import textingest
     from precellar_b200.pipeline import BarcodePipeline
     from precellar_b200.textingest import TextGroupReader
     from tests.test_gpu_textparse import text_of, v3_like_layout

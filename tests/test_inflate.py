@@ -5,7 +5,6 @@ whose lanes depended on one another would give different bytes) and compared wit
 of the trailer is checked by the code under test.  Corrupted members must end in an error, never in wrong bytes.
 """
 import ctypes as C
-import struct
 import zlib
 
 import numpy as np
